@@ -1,0 +1,197 @@
+/*
+ * hulo_gpu.h -- C-ABI of libhulo_gpu.so: the B200 (sm_100a) implementation of the
+ * SfMLocalization hot path (exact Hamming 2-NN matching of 64-byte AKAZE/MLDB rows with
+ * the ratio test, and scoring of resection-RANSAC hypotheses).
+ *
+ * Plain C types only; every function returns an int status (HULO_OK == 0) and never
+ * throws.  hulo_last_error() returns the message of the last failure on the calling
+ * thread.  A hulo_gpu handle owns one device, one stream, its scratch buffers and
+ * (optionally) one NCCL communicator; it must be used from one thread at a time, which
+ * is how the reference's callers behave (VisionLocalizeServer/src/localizeImage.cc:71-74).
+ *
+ * There is no CPU fallback: without a CUDA device hulo_gpu_create fails with
+ * HULO_ERR_CUDA and nothing else can be called.
+ *
+ * Each entry point names the reference interface it stands behind (paths relative to
+ * the reference repository root).
+ */
+#ifndef HULO_GPU_H
+#define HULO_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HULO_OK 0
+#define HULO_ERR_ARG 1      /* bad argument (null pointer, stride, size, capacity) */
+#define HULO_ERR_CUDA 2     /* CUDA runtime failure, or no device */
+#define HULO_ERR_NCCL 3     /* NCCL failure, or communicator not initialised */
+#define HULO_ERR_CAPACITY 4 /* caller buffer too small; *n_out holds the size needed */
+
+#define HULO_ROW_BYTES 64         /* device row width, FileUtils.cpp:77-103 */
+#define HULO_DIST_NONE 2147483647 /* INT_MAX: "neighbour not found", MatchUtils.cpp:115 */
+#define HULO_IDX_NONE (-1)
+
+typedef struct hulo_gpu hulo_gpu; /* device context */
+typedef struct hulo_db hulo_db;   /* device-resident descriptor rows + segment table */
+
+/* ------------------------------------------------------------------ context */
+
+/* Number of CUDA devices visible (0 when there is none); never fails. */
+int hulo_device_count(void);
+
+/* Create a context on `device`.  New state with no reference counterpart: the reference
+ * keeps no descriptor database in memory (MatchUtils.cpp:328-332 re-reads every view's
+ * .desc per query); LocalizeEngine's constructor (LocalizeEngine.cc:84-198) is where a
+ * drop-in creates this handle. */
+int hulo_gpu_create(int device, hulo_gpu **out);
+void hulo_gpu_destroy(hulo_gpu *h);
+const char *hulo_last_error(void);
+const char *hulo_version(void);
+
+/* Pinned host memory for the buffers of the *_host entry points (optional, faster). */
+int hulo_host_alloc(size_t bytes, void **out);
+void hulo_host_free(void *p);
+
+/* Device timing of the calls issued since hulo_timer_start on the context's stream
+ * (CUDA events); hulo_timer_stop synchronises and returns milliseconds.  This fills the
+ * `putMatch` / `PnP` slots of the reference's times[] (LocalizeEngine.cc:643-658). */
+int hulo_timer_start(hulo_gpu *h);
+int hulo_timer_stop(hulo_gpu *h, float *ms);
+int hulo_synchronize(hulo_gpu *h);
+
+/* Number of kernels this library launched on the context since creation. */
+uint64_t hulo_launch_count(const hulo_gpu *h);
+
+/* ------------------------------------------------------------ descriptor rows */
+
+/* Upload n rows of `stride` bytes (61..64 used; bytes beyond 64 ignored, rows narrower
+ * than 64 zero padded -- hulo::saveAKAZEBin, FileUtils.cpp:77-92) as a device-resident
+ * table.  seg_offsets (n_seg+1 ascending row offsets, seg_offsets[0]=0,
+ * seg_offsets[n_seg]=n) records which rows belong to which view / image; pass NULL,0
+ * for a single segment.  Stands where hulo::readAKAZEBin (FileUtils.cpp:94-103) is
+ * called per view per query (MatchUtils.cpp:86-95, 328-332). */
+int hulo_db_upload(hulo_gpu *h, const uint8_t *rows, size_t n, size_t stride,
+                   const uint64_t *seg_offsets, size_t n_seg, hulo_db **out);
+/* Replace the rows of an existing table in place (same or smaller n; one segment). */
+int hulo_db_update(hulo_gpu *h, hulo_db *db, const uint8_t *rows, size_t n, size_t stride);
+void hulo_db_free(hulo_db *db);
+size_t hulo_db_rows(const hulo_db *db);
+size_t hulo_db_segments(const hulo_db *db);
+/* Copy rows [first, first+n) back to the host as 64-byte rows. */
+int hulo_db_download(hulo_gpu *h, const hulo_db *db, size_t first, size_t n, uint8_t *rows64);
+
+/* --------------------------------------------------------------- K1: 2-NN */
+
+/* Exact 2 nearest neighbours, under 512-bit Hamming distance, of every row of A among
+ * the rows of B, ordered by (distance, index) ascending.
+ *   idx2  nA x 2 int32 row-major: indices into B; HULO_IDX_NONE when B has < 2 (< 1) rows
+ *   dist2 nA x 2 int32 row-major: distances; HULO_DIST_NONE for a missing neighbour
+ * Replaces cv::flann::Index(...).knnSearch(desc1, idx, dist, 2, ...) at
+ * MatchUtils.cpp:105-108, 191-194, 308-310 + 339-340 (same output layout and the same
+ * "-1 / INT_MAX" convention), with exact search instead of LSH (BASELINE.json).
+ * Outputs are HOST pointers; pass NULL for both to leave the result on the device
+ * (used by the throughput benchmark; fetch later with hulo_knn2_fetch). */
+int hulo_knn2(hulo_gpu *h, const hulo_db *A, const hulo_db *B, int32_t *idx2, int32_t *dist2);
+int hulo_knn2_fetch(hulo_gpu *h, size_t nA, int32_t *idx2, int32_t *dist2);
+/* Same with host rows: uploads A and B, searches, downloads.  stride as hulo_db_upload. */
+int hulo_knn2_host(hulo_gpu *h, const uint8_t *A, size_t nA, size_t strideA, const uint8_t *B,
+                   size_t nB, size_t strideB, int32_t *idx2, int32_t *dist2);
+
+/* ------------------------------------- query localisation (reference direction) */
+
+/* hulo::matchAKAZEToQuery, MatchUtils.cpp:283-367 (decl MatchUtils.h:54-61), for the
+ * selected views `views[0..n_views)` (segment numbers of `map`): for every row i of each
+ * view, 2-NN among the query image's rows; keep when
+ * (0.0f + d0) / d1 < ratio (float32) and d1 < INT_MAX (:347-349).
+ * Output, in the reference's iteration order (views in the order given, i ascending):
+ *   out_view[k]  position in views[] of the match's view
+ *   out_i[k]     feature index inside the view   (IndMatch::i_)
+ *   out_j[k]     query feature index             (IndMatch::j_)
+ *   out_d0[k]    distance to the nearest query row (featDist, :351)
+ * view_counts[v] (n_views entries, may be NULL) receives the matches per view.
+ * cap is the capacity of the out_* arrays; *n_out the number of matches.  If cap is too
+ * small the call returns HULO_ERR_CAPACITY with *n_out = needed.
+ * views == NULL selects every segment of `map` in order. */
+int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, size_t n_views,
+                        const uint8_t *query, size_t nq, size_t q_stride, float ratio,
+                        uint32_t *out_view, uint32_t *out_i, uint32_t *out_j, int32_t *out_d0,
+                        size_t cap, size_t *n_out, uint32_t *view_counts);
+
+/* ------------------------------------------ image-pair matching (reconstruction) */
+
+#define HULO_PAIR_ONE_TO_ONE 1u /* drop every claimant of a train row claimed twice, :125-143 */
+#define HULO_PAIR_DROP_LAST 2u  /* reference quirk: the last row of image I is never emitted, :125,:146 */
+#define HULO_PAIR_REFERENCE (HULO_PAIR_ONE_TO_ONE | HULO_PAIR_DROP_LAST)
+
+/* hulo::matchAKAZE, MatchUtils.cpp:73-152 (decl MatchUtils.h:39-42), and the matching half
+ * of hulo::trackAKAZE, :164-237: for each pair p = (I, J) = (pairs[2p], pairs[2p+1]) of
+ * segments of `db`: skip when either has < 2 rows (:99-101); 2-NN of every row of I among
+ * the rows of J; ratio test (:112-121); optional one-to-one filter and last-row quirk.
+ *   pair_offsets  n_pairs+1 entries: matches of pair p are [pair_offsets[p], pair_offsets[p+1])
+ *   out_i/out_j   IndMatch(i, j), i ascending inside a pair
+ * Capacity protocol as hulo_match_to_query. */
+int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size_t n_pairs,
+                     float ratio, unsigned flags, uint64_t *pair_offsets, uint32_t *out_i,
+                     uint32_t *out_j, size_t cap, size_t *n_out);
+
+/* ------------------------------------------------------- K2: resection scoring */
+
+/* Score H pose hypotheses against N 2D-3D correspondences: the body of the model loop of
+ * openMVG::robust::ACRANSAC as run by SfM_Localizer::Localize (called at
+ * LocalizeEngine.cc:531, localization.cpp:508, adjust_sfm_data.cpp:135-137):
+ * squared reprojection residual in K^-1-normalised coordinates for every correspondence,
+ * ascending sort, a-contrario NFA scan.
+ *   models  H x 12 doubles, row-major 3x4 [R|t] (normalised camera)
+ *   x2d     N x 2 doubles, pixel coordinates;  X3d  N x 3 doubles;  K 3x3 row-major
+ *   thr_px  >= 0: also count correspondences with residual <= thr_px pixels into n_inl
+ * Outputs (each H entries, any may be NULL): nfa (log10 NFA), k_best (inlier count at the
+ * NFA minimum), err_k (residual in pixels of the k_best-th correspondence), n_inl. */
+int hulo_score_resection(hulo_gpu *h, const double *models, size_t H, const double *x2d,
+                         const double *X3d, size_t N, const double *K, double thr_px, float *nfa,
+                         int32_t *k_best, float *err_k, int32_t *n_inl);
+
+/* Residuals only (pixels, fp32 on the device), H x N row-major: parity check of K2. */
+int hulo_resection_residuals(hulo_gpu *h, const double *models, size_t H, const double *x2d,
+                             const double *X3d, size_t N, const double *K, float *res_px);
+
+/* P3P minimal solver on the device for T sample triplets (indices into the
+ * correspondences): up to 4 models each (openMVG::euclidean_resection::P3PSolver).
+ * models: T x 4 x 12 doubles; n_models: T entries. */
+int hulo_p3p(hulo_gpu *h, const uint32_t *triplets, size_t T, const double *x2d, const double *X3d,
+             size_t N, const double *K, double *models, int32_t *n_models);
+
+/* openMVG::sfm::SfM_Localizer::Localize (LocalizeEngine.cc:529-532): AC-RANSAC resection
+ * with P3P, max_iter iterations (the reference runs OpenMVG's default 4096), batched:
+ * 90 % of the triplets are drawn and scored in one batch, the reserved 10 % are drawn from
+ * the inliers of the best model so far.
+ * Outputs: P = K [R|t] (12 doubles), inliers (capacity N) sorted by residual, *n_inliers,
+ * *error_max in pixels.  *found is 1 iff inliers > 2.5 * 3 with NFA < 0. */
+int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size_t N,
+                         const double *K, size_t max_iter, uint64_t seed, double *P,
+                         int32_t *inliers, size_t *n_inliers, double *error_max, int *found);
+
+/* ------------------------------------------------------------------ multi GPU */
+
+/* One process per GPU.  Rank 0 obtains an id with hulo_comm_unique_id and distributes its
+ * 128 bytes out of band; every rank then calls hulo_comm_init. */
+int hulo_comm_unique_id(void *id128);
+int hulo_comm_init(hulo_gpu *h, const void *id128, int rank, int world);
+int hulo_comm_barrier(hulo_gpu *h);
+/* max over ranks of a device-time measurement */
+int hulo_comm_max_f64(hulo_gpu *h, double *value);
+
+/* Row-sharded database: this rank's B holds rows [row_base, row_base + rows(B)) of the
+ * global table.  Every rank passes the same A.  Each rank computes its local top-2 with
+ * global indices, one ncclAllGather exchanges nA x 16 bytes per rank, and every rank
+ * merges to the result a single GPU would give (bit-identical).  Outputs as hulo_knn2. */
+int hulo_knn2_sharded(hulo_gpu *h, const hulo_db *A, const hulo_db *B_shard, uint64_t row_base,
+                      int32_t *idx2, int32_t *dist2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HULO_GPU_H */

@@ -1,0 +1,236 @@
+"""ctypes/numpy front end of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+Each function documents the C function it wraps; those cite the reference lines.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+INT_MAX = 2**31 - 1
+
+
+def build(force=False):
+    """Compile liboracle.so with the committed Makefile (gcc, OpenMP)."""
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_match.c", "oracle_resect.c", "Makefile")]
+    if (not force and os.path.exists(_SO)
+            and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs)):
+        return _SO
+    subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        _lib = C.CDLL(_SO)
+        _lib.orc_logcombi.restype = C.c_float
+        _lib.orc_logcombi.argtypes = [C.c_size_t, C.c_size_t]
+        _lib.orc_best_nfa.restype = C.c_double
+        _lib.orc_ratio_pass.argtypes = [C.c_int32, C.c_int32, C.c_float]
+        for name in ("orc_match_view_to_query", "orc_pair_filter", "orc_match_pair",
+                     "orc_track_propagate", "orc_match_set"):
+            getattr(_lib, name).restype = C.c_size_t
+    return _lib
+
+
+def _p(a, t=None):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    assert a.ndim == 2
+    return a
+
+
+def num_threads():
+    return int(lib().orc_num_threads())
+
+
+def pad_rows(rows):
+    """orc_pad_rows: N x w (w <= 64) -> N x 64, zero padded (FileUtils.cpp:77-92)."""
+    rows = _u8(rows)
+    out = np.empty((rows.shape[0], 64), np.uint8)
+    lib().orc_pad_rows(_p(rows), C.c_size_t(rows.shape[0]), C.c_size_t(rows.shape[1]), _p(out))
+    return out
+
+
+def knn2(A, B):
+    """orc_knn2_hamming: exact 2-NN, (dist, idx) order.  Returns idx2, dist2 (nA x 2 int32)."""
+    A, B = _u8(A), _u8(B)
+    nA = A.shape[0]
+    idx2 = np.empty((nA, 2), np.int32)
+    dist2 = np.empty((nA, 2), np.int32)
+    lib().orc_knn2_hamming(_p(A), C.c_size_t(nA), C.c_size_t(A.shape[1]), _p(B),
+                           C.c_size_t(B.shape[0]), C.c_size_t(B.shape[1] if B.ndim == 2 else 64),
+                           _p(idx2), _p(dist2))
+    return idx2, dist2
+
+
+def ratio_pass(d0, d1, ratio):
+    return bool(lib().orc_ratio_pass(int(d0), int(d1), float(ratio)))
+
+
+def match_view_to_query(A, Bq, ratio):
+    """orc_match_view_to_query (MatchUtils.cpp:339-355) -> (i, j, d0) arrays."""
+    A, Bq = _u8(A), _u8(Bq)
+    nA = A.shape[0]
+    oi = np.empty(max(nA, 1), np.int32)
+    oj = np.empty(max(nA, 1), np.int32)
+    od = np.empty(max(nA, 1), np.int32)
+    n = lib().orc_match_view_to_query(_p(A), C.c_size_t(nA), C.c_size_t(A.shape[1]), _p(Bq),
+                                      C.c_size_t(Bq.shape[0]), C.c_size_t(Bq.shape[1]),
+                                      C.c_float(ratio), _p(oi), _p(oj), _p(od))
+    return oi[:n].copy(), oj[:n].copy(), od[:n].copy()
+
+
+def pair_filter(idx2, dist2, ratio):
+    """orc_pair_filter (MatchUtils.cpp:111-150) -> (i, j) arrays."""
+    idx2 = np.ascontiguousarray(idx2, np.int32)
+    dist2 = np.ascontiguousarray(dist2, np.int32)
+    nA = idx2.shape[0]
+    oi = np.empty(max(nA, 1), np.int32)
+    oj = np.empty(max(nA, 1), np.int32)
+    n = lib().orc_pair_filter(_p(idx2), _p(dist2), C.c_size_t(nA), C.c_float(ratio), _p(oi), _p(oj))
+    return oi[:n].copy(), oj[:n].copy()
+
+
+def match_pair(A, B, ratio):
+    """orc_match_pair (MatchUtils.cpp:94-150) -> (i, j) arrays."""
+    A, B = _u8(A), _u8(B)
+    nA = A.shape[0]
+    oi = np.empty(max(nA, 1), np.int32)
+    oj = np.empty(max(nA, 1), np.int32)
+    n = lib().orc_match_pair(_p(A), C.c_size_t(nA), C.c_size_t(A.shape[1]), _p(B),
+                             C.c_size_t(B.shape[0]), C.c_size_t(B.shape[1]), C.c_float(ratio),
+                             _p(oi), _p(oj))
+    return oi[:n].copy(), oj[:n].copy()
+
+
+def track_propagate(n_frames, max_frame_dist, feat_number, m_off, m_i, m_j):
+    """orc_track_propagate (MatchUtils.cpp:239-276) -> (f, to, i, j) arrays."""
+    feat_number = np.ascontiguousarray(feat_number, np.int32)
+    m_off = np.ascontiguousarray(m_off, np.int64)
+    m_i = np.ascontiguousarray(m_i, np.int32)
+    m_j = np.ascontiguousarray(m_j, np.int32)
+    need = C.c_size_t(0)
+    dummy = np.empty(1, np.int32)
+    lib().orc_track_propagate(C.c_size_t(n_frames), C.c_size_t(max_frame_dist), _p(feat_number),
+                              _p(m_off), _p(m_i), _p(m_j), _p(dummy), _p(dummy), _p(dummy),
+                              _p(dummy), C.c_size_t(0), C.byref(need))
+    cap = max(int(need.value), 1)
+    of, ot, oi, oj = (np.empty(cap, np.int32) for _ in range(4))
+    n = lib().orc_track_propagate(C.c_size_t(n_frames), C.c_size_t(max_frame_dist), _p(feat_number),
+                                  _p(m_off), _p(m_i), _p(m_j), _p(of), _p(ot), _p(oi), _p(oj),
+                                  C.c_size_t(cap), C.byref(need))
+    return of[:n].copy(), ot[:n].copy(), oi[:n].copy(), oj[:n].copy()
+
+
+def match_set(m_view, m_i, m_j, fd_view, fd_j, fd_d, lm_view, lm_feat, lm_id, n_query_feat):
+    """orc_match_set (SfMDataUtils.cpp:59-125) -> (query feat, landmark id) arrays."""
+    a32 = lambda x: np.ascontiguousarray(x, np.int32)
+    m_view, m_i, m_j = a32(m_view), a32(m_i), a32(m_j)
+    fd_view, fd_j, fd_d = a32(fd_view), a32(fd_j), a32(fd_d)
+    lm_view, lm_feat = a32(lm_view), a32(lm_feat)
+    lm_id = np.ascontiguousarray(lm_id, np.int64)
+    oj = np.empty(max(n_query_feat, 1), np.int32)
+    ol = np.empty(max(n_query_feat, 1), np.int64)
+    n = lib().orc_match_set(_p(m_view), _p(m_i), _p(m_j), C.c_size_t(len(m_view)),
+                            _p(fd_view), _p(fd_j), _p(fd_d), C.c_size_t(len(fd_view)),
+                            _p(lm_view), _p(lm_feat), _p(lm_id), C.c_size_t(len(lm_view)),
+                            C.c_size_t(n_query_feat), _p(oj), _p(ol))
+    return oj[:n].copy(), ol[:n].copy()
+
+
+# ---------------------------------------------------------------- resection
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def p3p(bearings, X):
+    """orc_p3p: bearings 3x3 (rows = unit vectors), X 3x3 (rows = points) -> list of 3x4."""
+    f, X = _f64(bearings), _f64(X)
+    out = np.zeros((4, 3, 4))
+    n = lib().orc_p3p(_p(f), _p(X), _p(out))
+    return out[:n].copy()
+
+
+def normalize_points(x2d, K):
+    """x2d N x 2 pixels -> N x 2 normalised (K^-1)."""
+    x2d, K = _f64(x2d), _f64(K)
+    out = np.empty_like(x2d)
+    lib().orc_normalize_points(_p(x2d), C.c_size_t(x2d.shape[0]), _p(K), _p(out))
+    return out
+
+
+def residuals(M, x2dn, X3d):
+    M, x2dn, X3d = _f64(M), _f64(x2dn), _f64(X3d)
+    N = x2dn.shape[0]
+    err = np.empty(N)
+    lib().orc_residuals(_p(M), _p(x2dn), _p(X3d), C.c_size_t(N), _p(err))
+    return err
+
+
+def logcombi(k, n):
+    return float(lib().orc_logcombi(k, n))
+
+
+def best_nfa(sorted_err, N=None):
+    e = _f64(sorted_err)
+    N = len(e) if N is None else N
+    lcn = np.empty(N + 1, np.float32)
+    lck = np.empty(N + 1, np.float32)
+    lib().orc_make_logcombi(C.c_size_t(N), _p(lcn), _p(lck))
+    kb = C.c_size_t(0)
+    nfa = lib().orc_best_nfa(_p(e), C.c_size_t(N), C.c_double(np.log10(np.pi)),
+                             C.c_double(np.log10(4.0 * (N - 3))), C.c_double(np.inf),
+                             _p(lcn), _p(lck), C.c_double(1.0), C.byref(kb))
+    return float(nfa), int(kb.value)
+
+
+def score_hypotheses(models, x2dn, X3d, thr2=-1.0):
+    """orc_score_hypotheses: models H x 3 x 4 -> nfa[H], k_best[H], err_k[H], n_inl[H]."""
+    models, x2dn, X3d = _f64(models), _f64(x2dn), _f64(X3d)
+    H = models.shape[0]
+    N = x2dn.shape[0]
+    nfa = np.empty(H)
+    kb = np.empty(H, np.int32)
+    ek = np.empty(H)
+    ni = np.empty(H, np.int32)
+    lib().orc_score_hypotheses(_p(models), C.c_size_t(H), _p(x2dn), _p(X3d), C.c_size_t(N),
+                               C.c_double(thr2), _p(nfa), _p(kb), _p(ek), _p(ni))
+    return nfa, kb, ek, ni
+
+
+def acransac(x2d, X3d, K, max_iter=4096, seed=1):
+    """orc_acransac -> dict(ok, P 3x4, inliers, error_max [px], nfa)."""
+    x2d, X3d, K = _f64(x2d), _f64(X3d), _f64(K)
+    N = x2d.shape[0]
+    P = np.zeros((3, 4))
+    inl = np.empty(max(N, 1), np.int32)
+    n_inl = C.c_size_t(0)
+    emax = C.c_double(0)
+    nfa = C.c_double(0)
+    ok = lib().orc_acransac(_p(x2d), _p(X3d), C.c_size_t(N), _p(K), C.c_size_t(max_iter),
+                            C.c_uint64(seed), _p(P), _p(inl), C.byref(n_inl), C.byref(emax),
+                            C.byref(nfa))
+    return dict(ok=bool(ok), P=P, inliers=inl[:n_inl.value].copy(), error_max=emax.value,
+                nfa=nfa.value)
+
+
+def krt_from_p(P):
+    P = _f64(P)
+    K = np.empty((3, 3)); R = np.empty((3, 3)); t = np.empty(3); c = np.empty(3)
+    lib().orc_krt_from_p(_p(P), _p(K), _p(R), _p(t), _p(c))
+    return K, R, t, c

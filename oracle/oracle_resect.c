@@ -1,0 +1,489 @@
+/*
+ * oracle_resect.c -- CPU fp64 restatement of the resection half of the hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle_match.c for the rule).
+ *
+ * PARITY UNPINNED.  The arithmetic lives in OpenMVG 1.1 (reference README.md:5,
+ * CMakeLists.txt:36-39), a third-party dependency that is neither vendored under
+ * /root/reference nor installed in this image, and the reference ships no test or golden
+ * vector for it.  The call sites that anchor this restatement are
+ *   VisionLocalizeServer/src/LocalizeEngine.cc:503-531,
+ *   OpenMVGLocalization_AKAZE/src/localization.cpp:479-509,
+ *   OpenMVG_BA/src/adjust_sfm_data.cpp:109-137
+ * (all call openMVG::sfm::SfM_Localizer::Localize with error_max = inf and the default
+ * max_iteration = 4096).  What is restated is OpenMVG 1.1's published algorithm
+ * (SURVEY.md appendix B):
+ *   sfm/pipelines/localization/SfM_Localizer.cpp          -> orc_localize
+ *   robust_estimation/robust_estimator_ACRansac.hpp        -> orc_acransac, orc_best_nfa,
+ *                                                             orc_logcombi
+ *   robust_estimation/robust_estimator_ACRansacKernelAdaptator.hpp
+ *        (ACKernelAdaptorResection_K)                      -> normalisation, logalpha0,
+ *                                                             unormalizeError
+ *   multiview/solver_resection_p3p.hpp (Kneip CVPR 2011)   -> orc_p3p
+ *   multiview/projection.hpp (Project, KRt_From_P)         -> orc_residuals, orc_krt_from_p
+ * The P3P solution set is cross-checked against cv2.solveP3P in tests/.
+ * Known deviations: (1) the sampler is a seeded splitmix64 instead of std::rand (upstream
+ * seeds non-deterministically, so traces are not comparable anyway); (2) P3P models with
+ * non-finite entries are skipped instead of being sorted with NaN residuals.
+ */
+#include <complex.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* ---------- small vector helpers ---------- */
+static void v_sub(const double *a, const double *b, double *o) { o[0]=a[0]-b[0]; o[1]=a[1]-b[1]; o[2]=a[2]-b[2]; }
+static void v_cross(const double *a, const double *b, double *o) {
+    double x = a[1]*b[2]-a[2]*b[1], y = a[2]*b[0]-a[0]*b[2], z = a[0]*b[1]-a[1]*b[0];
+    o[0]=x; o[1]=y; o[2]=z;
+}
+static double v_dot(const double *a, const double *b) { return a[0]*b[0]+a[1]*b[1]+a[2]*b[2]; }
+static double v_norm(const double *a) { return sqrt(v_dot(a, a)); }
+static void v_normalize(double *a) { double n = v_norm(a); a[0]/=n; a[1]/=n; a[2]/=n; }
+/* o = M v, M row-major 3x3 */
+static void m_mulv(const double *M, const double *v, double *o) {
+    double x = M[0]*v[0]+M[1]*v[1]+M[2]*v[2];
+    double y = M[3]*v[0]+M[4]*v[1]+M[5]*v[2];
+    double z = M[6]*v[0]+M[7]*v[1]+M[8]*v[2];
+    o[0]=x; o[1]=y; o[2]=z;
+}
+/* o = M^T v */
+static void m_tmulv(const double *M, const double *v, double *o) {
+    double x = M[0]*v[0]+M[3]*v[1]+M[6]*v[2];
+    double y = M[1]*v[0]+M[4]*v[1]+M[7]*v[2];
+    double z = M[2]*v[0]+M[5]*v[1]+M[8]*v[2];
+    o[0]=x; o[1]=y; o[2]=z;
+}
+static void m_mul(const double *A, const double *B, double *O) {
+    double T[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            T[3*i+j] = A[3*i]*B[j] + A[3*i+1]*B[3+j] + A[3*i+2]*B[6+j];
+    memcpy(O, T, sizeof T);
+}
+static void m_transpose(const double *A, double *O) {
+    double T[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) T[3*i+j] = A[3*j+i];
+    memcpy(O, T, sizeof T);
+}
+
+/* ---------- quartic, Ferrari closed form (real parts of the four complex roots) ---------- */
+static void solve_quartic(const double f[5], double roots[4]) {
+    double A = f[0], B = f[1], C = f[2], D = f[3], E = f[4];
+    double A2 = A*A, B2 = B*B, A3 = A2*A, B3 = B2*B, A4 = A3*A, B4 = B3*B;
+    double alpha = -3.0*B2/(8.0*A2) + C/A;
+    double beta = B3/(8.0*A3) - B*C/(2.0*A2) + D/A;
+    double gamma = -3.0*B4/(256.0*A4) + B2*C/(16.0*A3) - B*D/(4.0*A2) + E/A;
+    double alpha2 = alpha*alpha, alpha3 = alpha2*alpha;
+    double complex P = -alpha2/12.0 - gamma;
+    double complex Q = -alpha3/108.0 + alpha*gamma/3.0 - beta*beta/8.0;
+    double complex R = -Q/2.0 + csqrt(Q*Q/4.0 + P*P*P/27.0);
+    double complex U = cpow(R, 1.0/3.0);
+    double complex y;
+    if (creal(U) == 0.0) y = -5.0*alpha/6.0 - cpow(Q, 1.0/3.0);
+    else y = -5.0*alpha/6.0 - P/(3.0*U) + U;
+    double complex w = csqrt(alpha + 2.0*y);
+    double complex s1 = csqrt(-(3.0*alpha + 2.0*y + 2.0*beta/w));
+    double complex s2 = csqrt(-(3.0*alpha + 2.0*y - 2.0*beta/w));
+    double sh = -B/(4.0*A);
+    roots[0] = creal(sh + 0.5*( w + s1));
+    roots[1] = creal(sh + 0.5*( w - s1));
+    roots[2] = creal(sh + 0.5*(-w + s2));
+    roots[3] = creal(sh + 0.5*(-w - s2));
+}
+
+/*
+ * Kneip P3P.  f: three unit bearing vectors (f[3*i..]), X: three world points (X[3*i..]).
+ * models: up to 4 row-major 3x4 [R|t] with x_cam ~ R X + t.  Returns the number of models
+ * with finite entries (upstream always emits four, taking the real part of every root).
+ */
+int orc_p3p(const double *f_in, const double *X_in, double *models) {
+    double P1[3], P2[3], P3[3], f1[3], f2[3], f3[3];
+    memcpy(P1, X_in, 24); memcpy(P2, X_in+3, 24); memcpy(P3, X_in+6, 24);
+    memcpy(f1, f_in, 24); memcpy(f2, f_in+3, 24); memcpy(f3, f_in+6, 24);
+
+    double t1[3], t2[3], cr[3];
+    v_sub(P2, P1, t1); v_sub(P3, P1, t2); v_cross(t1, t2, cr);
+    if (v_norm(cr) == 0.0) return 0;               /* collinear world points */
+
+    double T[9], e1[3], e2[3], e3[3], f3t[3];
+    for (int pass = 0; pass < 2; ++pass) {
+        memcpy(e1, f1, 24);
+        v_cross(f1, f2, e3); v_normalize(e3);
+        v_cross(e3, e1, e2);
+        memcpy(T, e1, 24); memcpy(T+3, e2, 24); memcpy(T+6, e3, 24);
+        m_mulv(T, f3, f3t);
+        if (pass == 0 && f3t[2] > 0.0) {           /* enforce theta in [0, pi]: swap 1 <-> 2 */
+            double tmp[3];
+            memcpy(tmp, f1, 24); memcpy(f1, f2, 24); memcpy(f2, tmp, 24);
+            memcpy(tmp, P1, 24); memcpy(P1, P2, 24); memcpy(P2, tmp, 24);
+            continue;
+        }
+        break;
+    }
+
+    double n1[3], n2[3], n3[3], N[9], d[3];
+    v_sub(P2, P1, n1); v_normalize(n1);
+    v_sub(P3, P1, d);
+    v_cross(n1, d, n3); v_normalize(n3);
+    v_cross(n3, n1, n2);
+    memcpy(N, n1, 24); memcpy(N+3, n2, 24); memcpy(N+6, n3, 24);
+
+    double P3n[3];
+    m_mulv(N, d, P3n);
+    v_sub(P2, P1, d);
+    double d12 = v_norm(d);
+    double phi1 = f3t[0]/f3t[2], phi2 = f3t[1]/f3t[2];
+    double p1 = P3n[0], p2 = P3n[1];
+    double cosb = v_dot(f1, f2);
+    double b = 1.0/(1.0 - cosb*cosb) - 1.0;
+    b = cosb < 0.0 ? -sqrt(b) : sqrt(b);
+
+    double phi1_2 = phi1*phi1, phi2_2 = phi2*phi2;
+    double p1_2 = p1*p1, p1_3 = p1_2*p1, p1_4 = p1_3*p1;
+    double p2_2 = p2*p2, p2_3 = p2_2*p2, p2_4 = p2_3*p2;
+    double d12_2 = d12*d12, b_2 = b*b;
+
+    double fac[5];
+    fac[0] = -phi2_2*p2_4 - p2_4*phi1_2 - p2_4;
+    fac[1] = 2.0*p2_3*d12*b + 2.0*phi2_2*p2_3*d12*b - 2.0*phi2*p2_3*phi1*d12;
+    fac[2] = -phi2_2*p2_2*p1_2 - phi2_2*p2_2*d12_2*b_2 - phi2_2*p2_2*d12_2 + phi2_2*p2_4
+             + p2_4*phi1_2 + 2.0*p1*p2_2*d12 + 2.0*phi1*phi2*p1*p2_2*d12*b
+             - p2_2*p1_2*phi1_2 + 2.0*p1*p2_2*phi2_2*d12 - p2_2*d12_2*b_2 - 2.0*p1_2*p2_2;
+    fac[3] = 2.0*p1_2*p2*d12*b + 2.0*phi2*p2_3*phi1*d12 - 2.0*phi2_2*p2_3*d12*b
+             - 2.0*p1*p2*d12_2*b;
+    fac[4] = -2.0*phi2*p2_2*phi1*p1*d12*b + phi2_2*p2_2*d12_2 + 2.0*p1_3*d12 - p1_2*d12_2
+             + phi2_2*p2_2*p1_2 - p1_4 - 2.0*phi2_2*p2_2*p1*d12 + p2_2*phi1_2*p1_2
+             + phi2_2*p2_2*d12_2*b_2;
+
+    double roots[4];
+    solve_quartic(fac, roots);
+
+    int n_out = 0;
+    for (int i = 0; i < 4; ++i) {
+        double cot_alpha = (-phi1*p1/phi2 - roots[i]*p2 + d12*b)
+                         / (-phi1*roots[i]*p2/phi2 + p1 - d12);
+        double cos_theta = roots[i];
+        double sin_theta = sqrt(1.0 - roots[i]*roots[i]);
+        double sin_alpha = sqrt(1.0/(cot_alpha*cot_alpha + 1.0));
+        double cos_alpha = sqrt(1.0 - sin_alpha*sin_alpha);
+        if (cot_alpha < 0.0) cos_alpha = -cos_alpha;
+
+        double Cn[3] = { d12*cos_alpha*(sin_alpha*b + cos_alpha),
+                         cos_theta*d12*sin_alpha*(sin_alpha*b + cos_alpha),
+                         sin_theta*d12*sin_alpha*(sin_alpha*b + cos_alpha) };
+        double C[3];
+        m_tmulv(N, Cn, C);
+        C[0] += P1[0]; C[1] += P1[1]; C[2] += P1[2];
+
+        double Rr[9] = { -cos_alpha, -sin_alpha*cos_theta, -sin_alpha*sin_theta,
+                          sin_alpha, -cos_alpha*cos_theta, -cos_alpha*sin_theta,
+                          0.0,       -sin_theta,            cos_theta };
+        /* camera-to-world rotation  Rcw = N^T Rr^T T ; the model uses Rwc = Rcw^T */
+        double Nt[9], Rt[9], Rcw[9], Rwc[9];
+        m_transpose(N, Nt); m_transpose(Rr, Rt);
+        m_mul(Nt, Rt, Rcw); m_mul(Rcw, T, Rcw);
+        m_transpose(Rcw, Rwc);
+        double tv[3];
+        m_mulv(Rwc, C, tv);
+        double M[12] = { Rwc[0], Rwc[1], Rwc[2], -tv[0],
+                         Rwc[3], Rwc[4], Rwc[5], -tv[1],
+                         Rwc[6], Rwc[7], Rwc[8], -tv[2] };
+        int ok = 1;
+        for (int k = 0; k < 12; ++k) if (!isfinite(M[k])) ok = 0;
+        if (!ok) continue;
+        memcpy(models + 12*n_out, M, sizeof M);
+        ++n_out;
+    }
+    return n_out;
+}
+
+/* K^-1 for an upper-triangular pinhole K (row-major 3x3, K[8] == 1 not assumed). */
+static void k_inverse(const double *K, double *Ki) {
+    double fx = K[0], s = K[1], cx = K[2], fy = K[4], cy = K[5], w = K[8];
+    Ki[0] = 1.0/fx; Ki[1] = -s/(fx*fy); Ki[2] = (s*cy - cx*fy)/(fx*fy*w);
+    Ki[3] = 0.0;    Ki[4] = 1.0/fy;     Ki[5] = -cy/(fy*w);
+    Ki[6] = 0.0;    Ki[7] = 0.0;        Ki[8] = 1.0/w;
+}
+
+/* x2dn = dehomogenised K^-1 [x;1]   (ACKernelAdaptorResection_K constructor).
+ * x2d, x2dn: 2xN column-major (x2d[2*i], x2d[2*i+1]). */
+void orc_normalize_points(const double *x2d, size_t N, const double *K, double *x2dn) {
+    double Ki[9];
+    k_inverse(K, Ki);
+    for (size_t i = 0; i < N; ++i) {
+        double p[3] = { x2d[2*i], x2d[2*i+1], 1.0 }, q[3];
+        m_mulv(Ki, p, q);
+        x2dn[2*i] = q[0]/q[2];
+        x2dn[2*i+1] = q[1]/q[2];
+    }
+}
+
+/* Squared reprojection residual of every correspondence under the 3x4 model M (row-major),
+ * ResectionSquaredResidualError: || hnormalized(M [X;1]) - x ||^2.  X3d is 3xN column-major. */
+void orc_residuals(const double *M, const double *x2dn, const double *X3d, size_t N, double *err) {
+    for (size_t i = 0; i < N; ++i) {
+        const double *X = X3d + 3*i;
+        double u = M[0]*X[0] + M[1]*X[1] + M[2]*X[2]  + M[3];
+        double v = M[4]*X[0] + M[5]*X[1] + M[6]*X[2]  + M[7];
+        double w = M[8]*X[0] + M[9]*X[1] + M[10]*X[2] + M[11];
+        double dx = u/w - x2dn[2*i], dy = v/w - x2dn[2*i+1];
+        err[i] = dx*dx + dy*dy;
+    }
+}
+
+/* log10 of the binomial coefficient C(n,k), accumulated in double, stored as float. */
+float orc_logcombi(size_t k, size_t n) {
+    if (k >= n || k == 0) return 0.0f;
+    if (n - k < k) k = n - k;
+    double r = 0.0;
+    for (size_t i = 1; i <= k; ++i) r += log10((double)(n - i + 1)) - log10((double)i);
+    return (float)r;
+}
+/* logc_n[k] = log10 C(N,k), logc_k[n] = log10 C(n,3), both N+1 floats. */
+void orc_make_logcombi(size_t N, float *logc_n, float *logc_k) {
+    for (size_t k = 0; k <= N; ++k) logc_n[k] = orc_logcombi(k, N);
+    for (size_t n = 0; n <= N; ++n) logc_k[n] = orc_logcombi(3, n);
+}
+
+/*
+ * bestNFA over residuals sorted ascending (ties already ordered by index).
+ * Returns the minimal NFA and writes its k (number of inliers) to *k_best; first minimum wins.
+ */
+double orc_best_nfa(const double *sorted_err, size_t N, double logalpha0, double loge0,
+                    double max_threshold, const float *logc_n, const float *logc_k,
+                    double mult_error, size_t *k_best) {
+    const size_t start = 3;
+    double best = INFINITY;
+    size_t bk = start;
+    for (size_t k = start + 1; k <= N && sorted_err[k-1] <= max_threshold; ++k) {
+        double logalpha = logalpha0 + mult_error * log10(sorted_err[k-1] + (double)FLT_EPSILON);
+        double nfa = loge0 + logalpha * (double)(k - start) + (double)logc_n[k] + (double)logc_k[k];
+        if (nfa < best) { best = nfa; bk = k; }
+    }
+    *k_best = bk;
+    return best;
+}
+
+typedef struct { double e; size_t i; } err_idx;
+static int cmp_err_idx(const void *a, const void *b) {
+    const err_idx *x = (const err_idx *)a, *y = (const err_idx *)b;
+    if (x->e < y->e) return -1;
+    if (x->e > y->e) return 1;
+    return (x->i > y->i) - (x->i < y->i);
+}
+
+/*
+ * Score H hypotheses (row-major 3x4 each) against all N correspondences: the inner body of
+ * the ACRANSAC model loop.  Outputs per hypothesis: minimal NFA, its k, the k-th smallest
+ * squared residual (normalised units) and, when thr2 >= 0, the count of residuals <= thr2.
+ */
+void orc_score_hypotheses(const double *models, size_t H, const double *x2dn, const double *X3d,
+                          size_t N, double thr2, double *nfa, int32_t *k_best, double *err_k,
+                          int32_t *n_inl) {
+    float *logc_n = (float *)malloc(sizeof(float) * (N + 1));
+    float *logc_k = (float *)malloc(sizeof(float) * (N + 1));
+    orc_make_logcombi(N, logc_n, logc_k);
+    double loge0 = log10(4.0 * (double)(N - 3));
+    double logalpha0 = log10(M_PI);
+#pragma omp parallel
+    {
+        double *err = (double *)malloc(sizeof(double) * (N ? N : 1));
+        err_idx *ei = (err_idx *)malloc(sizeof(err_idx) * (N ? N : 1));
+#pragma omp for schedule(static)
+        for (long long h = 0; h < (long long)H; ++h) {
+            orc_residuals(models + 12*h, x2dn, X3d, N, err);
+            int32_t cnt = 0;
+            for (size_t i = 0; i < N; ++i) { ei[i].e = err[i]; ei[i].i = i; if (thr2 >= 0 && err[i] <= thr2) ++cnt; }
+            qsort(ei, N, sizeof(err_idx), cmp_err_idx);
+            for (size_t i = 0; i < N; ++i) err[i] = ei[i].e;
+            size_t kb;
+            nfa[h] = orc_best_nfa(err, N, logalpha0, loge0, INFINITY, logc_n, logc_k, 1.0, &kb);
+            k_best[h] = (int32_t)kb;
+            err_k[h] = (kb >= 1 && kb <= N) ? err[kb-1] : INFINITY;
+            if (n_inl) n_inl[h] = cnt;
+        }
+        free(err); free(ei);
+    }
+    free(logc_n); free(logc_k);
+}
+
+/* ---------- sampler ---------- */
+static uint64_t splitmix64(uint64_t *s) {
+    uint64_t z = (*s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+/* three distinct positions in [0, total) (UniformSample of rand_sampling.hpp) */
+void orc_sample3(uint64_t *state, size_t total, size_t out[3]) {
+    for (int i = 0; i < 3; ++i) {
+        size_t r = (size_t)(splitmix64(state) % (uint64_t)(total - i));
+        int j;
+        for (j = 0; j < i && r >= out[j]; ++j) ++r;
+        for (int k = i; k > j; --k) out[k] = out[k-1];
+        out[j] = r;
+    }
+}
+
+/*
+ * ACRANSAC over the P3P kernel (robust_estimator_ACRansac.hpp, ACKernelAdaptorResection_K).
+ *   x2d 2xN pixels, X3d 3xN, K 3x3 row-major, max_iter (4096 in the reference), seed.
+ * Outputs: P = K [R|t] (row-major 3x4), inliers (indices, sorted by residual), *n_inl,
+ * *error_max in pixels, *min_nfa.  Returns 1 when a meaningful model (NFA < 0) was found.
+ */
+int orc_acransac(const double *x2d, const double *X3d, size_t N, const double *K, size_t max_iter,
+                 uint64_t seed, double *P, int32_t *inliers, size_t *n_inl, double *error_max,
+                 double *min_nfa_out) {
+    *n_inl = 0; *error_max = 0.0; if (min_nfa_out) *min_nfa_out = 0.0;
+    if (N <= 3) return 0;
+    double *x2dn = (double *)malloc(sizeof(double) * 2 * N);
+    orc_normalize_points(x2d, N, K, x2dn);
+    float *logc_n = (float *)malloc(sizeof(float) * (N + 1));
+    float *logc_k = (float *)malloc(sizeof(float) * (N + 1));
+    orc_make_logcombi(N, logc_n, logc_k);
+    double loge0 = log10(4.0 * (double)(N - 3));
+    double logalpha0 = log10(M_PI);
+    double *err = (double *)malloc(sizeof(double) * N);
+    err_idx *ei = (err_idx *)malloc(sizeof(err_idx) * N);
+    size_t *pool = (size_t *)malloc(sizeof(size_t) * N);
+    size_t n_pool = N;
+    for (size_t i = 0; i < N; ++i) pool[i] = i;
+    size_t *best_inl = (size_t *)malloc(sizeof(size_t) * N);
+    size_t n_best = 0;
+    double best_model[12] = {0};
+    double minNFA = INFINITY, errorMax = INFINITY;
+    uint64_t rng = seed;
+
+    size_t nIter = max_iter;
+    size_t nIterReserve = nIter / 10;
+    nIter -= nIterReserve;
+
+    for (size_t iter = 0; iter < nIter; ++iter) {
+        size_t pos[3];
+        orc_sample3(&rng, n_pool, pos);
+        double f[9], Xs[9];
+        for (int s = 0; s < 3; ++s) {
+            size_t id = pool[pos[s]];
+            double b[3] = { x2dn[2*id], x2dn[2*id+1], 1.0 };
+            v_normalize(b);
+            memcpy(f + 3*s, b, 24);
+            memcpy(Xs + 3*s, X3d + 3*id, 24);
+        }
+        double models[48];
+        int nm = orc_p3p(f, Xs, models);
+        int better = 0;
+        for (int m = 0; m < nm; ++m) {
+            orc_residuals(models + 12*m, x2dn, X3d, N, err);
+            for (size_t i = 0; i < N; ++i) { ei[i].e = err[i]; ei[i].i = i; }
+            qsort(ei, N, sizeof(err_idx), cmp_err_idx);
+            for (size_t i = 0; i < N; ++i) err[i] = ei[i].e;
+            size_t kb;
+            double nfa = orc_best_nfa(err, N, logalpha0, loge0, INFINITY, logc_n, logc_k, 1.0, &kb);
+            if (nfa < minNFA) {
+                better = 1;
+                minNFA = nfa;
+                n_best = kb;
+                for (size_t i = 0; i < kb; ++i) best_inl[i] = ei[i].i;
+                errorMax = err[kb-1];
+                memcpy(best_model, models + 12*m, sizeof best_model);
+            }
+        }
+        if ((better && minNFA < 0) || (iter + 1 == nIter && nIterReserve)) {
+            if (n_best == 0) {
+                nIter++;
+                nIterReserve--;
+            } else {
+                n_pool = n_best;
+                memcpy(pool, best_inl, sizeof(size_t) * n_best);
+                if (nIterReserve) {
+                    nIter = iter + 1 + nIterReserve;
+                    nIterReserve = 0;
+                }
+            }
+        }
+    }
+    int ok = 0;
+    if (minNFA >= 0) n_best = 0;
+    if (n_best > 0) {
+        /* Unnormalize: P = K * model ; error in pixels = sqrt(e) / Kinv(0,0) */
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 4; ++c)
+                P[4*r+c] = K[3*r]*best_model[c] + K[3*r+1]*best_model[4+c] + K[3*r+2]*best_model[8+c];
+        *error_max = sqrt(errorMax) * K[0];
+        for (size_t i = 0; i < n_best; ++i) inliers[i] = (int32_t)best_inl[i];
+        *n_inl = n_best;
+        ok = 1;
+    }
+    if (min_nfa_out) *min_nfa_out = minNFA;
+    free(x2dn); free(logc_n); free(logc_k); free(err); free(ei); free(pool); free(best_inl);
+    return ok;
+}
+
+/*
+ * SfM_Localizer::Localize acceptance: success iff #inliers > 2.5 * 3.
+ * The engines then require #inliers > 10 (LocalizeEngine.cc:560, localization.cpp:511).
+ */
+int orc_localize(const double *x2d, const double *X3d, size_t N, const double *K, size_t max_iter,
+                 uint64_t seed, double *P, int32_t *inliers, size_t *n_inl, double *error_max) {
+    double nfa;
+    orc_acransac(x2d, X3d, N, K, max_iter, seed, P, inliers, n_inl, error_max, &nfa);
+    return (double)*n_inl > 2.5 * 3.0;
+}
+
+/*
+ * KRt_From_P for P = K [R|t] with K upper triangular, positive diagonal, K[8] normalised to 1
+ * (RQ decomposition of the left 3x3 block by Givens rotations), projection.hpp.
+ * Also returns the camera centre c = -R^T t (LocalizeEngine.cc:582-585).
+ */
+void orc_krt_from_p(const double *P, double *Kout, double *Rout, double *tout, double *centre) {
+    double Kk[9] = { P[0], P[1], P[2], P[4], P[5], P[6], P[8], P[9], P[10] };
+    double Q[9] = {1,0,0, 0,1,0, 0,0,1};
+    /* zero K(2,1) with a rotation about x */
+    {
+        double c = -Kk[8], s = Kk[7], l = sqrt(c*c + s*s); c /= l; s /= l;
+        double Rx[9] = {1,0,0, 0,c,-s, 0,s,c};
+        m_mul(Kk, Rx, Kk); m_mul(Q, Rx, Q);
+    }
+    /* zero K(2,0) with a rotation about y */
+    {
+        double c = Kk[8], s = Kk[6], l = sqrt(c*c + s*s); c /= l; s /= l;
+        double Ry[9] = {c,0,s, 0,1,0, -s,0,c};
+        m_mul(Kk, Ry, Kk); m_mul(Q, Ry, Q);
+    }
+    /* zero K(1,0) with a rotation about z */
+    {
+        double c = -Kk[4], s = Kk[3], l = sqrt(c*c + s*s); c /= l; s /= l;
+        double Rz[9] = {c,-s,0, s,c,0, 0,0,1};
+        m_mul(Kk, Rz, Kk); m_mul(Q, Rz, Q);
+    }
+    double R[9];
+    m_transpose(Q, R);
+    /* make the diagonal of K positive */
+    for (int ax = 0; ax < 3; ++ax) {
+        if (Kk[4*ax] < 0) {
+            for (int r = 0; r < 3; ++r) Kk[3*r+ax] = -Kk[3*r+ax];
+            for (int c = 0; c < 3; ++c) R[3*ax+c] = -R[3*ax+c];
+        }
+    }
+    /* det(R) must be +1 */
+    double det = R[0]*(R[4]*R[8]-R[5]*R[7]) - R[1]*(R[3]*R[8]-R[5]*R[6]) + R[2]*(R[3]*R[7]-R[4]*R[6]);
+    double p4[3] = { P[3], P[7], P[11] };
+    if (det < 0) { for (int k = 0; k < 9; ++k) R[k] = -R[k]; p4[0] = -p4[0]; p4[1] = -p4[1]; p4[2] = -p4[2]; }
+    /* t = K^-1 p4 */
+    double Ki[9]; k_inverse(Kk, Ki);
+    /* k_inverse assumes upper-triangular input, true after the three rotations */
+    double t[3]; m_mulv(Ki, p4, t);
+    double sc = Kk[8];
+    for (int k = 0; k < 9; ++k) Kk[k] /= sc;
+    if (Kout) memcpy(Kout, Kk, sizeof Kk);
+    if (Rout) memcpy(Rout, R, sizeof R);
+    if (tout) memcpy(tout, t, sizeof t);
+    if (centre) { double c[3]; m_tmulv(R, t, c); centre[0] = -c[0]; centre[1] = -c[1]; centre[2] = -c[2]; }
+}

@@ -1,0 +1,631 @@
+// api.cu -- C-ABI of libhulo_gpu.so (include/hulo_gpu.h): context, descriptor tables,
+// K1 entry points (flat 2-NN, query localisation, image-pair matching).
+#include <algorithm>
+#include <climits>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "context.cuh"
+#include "match_post.cuh"
+
+namespace hulo {
+
+static thread_local std::string g_error;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+// ---------------------------------------------------------------- K1 planning
+struct FlatPlan {
+    KnnConfig cfg;
+    uint32_t n_tiles = 0, n_chunks = 0, rows_per_chunk = 0;
+    uint64_t slot_stride = 0;
+    int grid = 0;
+};
+
+static int env_int(const char *name, int dflt) {
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// Searcher-tile shape: the widest tile (fewest B re-reads) that the searcher count still fills.
+static KnnConfig choose_config(const hulo_gpu *h, size_t nA) {
+    if (h->knn_cfg_forced) return h->knn_cfg;
+    KnnConfig c = h->knn_cfg;
+    if (nA <= 512) c = KnnConfig{128, 4, 7};
+    else if (nA <= 1024) c = KnnConfig{256, 4, 7};
+    return c;
+}
+
+// Split nB database rows into chunks so that tiles x chunks fills the persistent grid evenly.
+static void plan_chunks(uint32_t n_tiles, size_t nB, int n_ctas, uint32_t *n_chunks, uint32_t *rows_per_chunk) {
+    if (nB == 0) { *n_chunks = 0; *rows_per_chunk = 1; return; }
+    const uint32_t min_rows = 256;
+    uint32_t c_min = (uint32_t)((nB + kMaxChunkRows - 1) / kMaxChunkRows);
+    uint32_t c_max = (uint32_t)std::max<size_t>(c_min, nB / min_rows);
+    c_max = std::min<uint32_t>(c_max, std::max<uint32_t>(c_min, (uint32_t)(64 * n_ctas) / std::max(1u, n_tiles) + 1));
+    uint32_t best_c = c_min;
+    double best_eff = -1.0;
+    for (uint32_t c = c_min; c <= c_max; ++c) {
+        const uint64_t items = (uint64_t)n_tiles * c;
+        const uint64_t waves = (items + n_ctas - 1) / n_ctas;
+        const double eff = (double)items / (double)(waves * n_ctas);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_c = c; }
+        if (eff >= 0.97) { best_c = c; break; }
+    }
+    uint32_t rpc = (uint32_t)((nB + best_c - 1) / best_c);
+    *rows_per_chunk = rpc;
+    *n_chunks = (uint32_t)((nB + rpc - 1) / rpc);
+}
+
+static FlatPlan plan_flat(const hulo_gpu *h, size_t nA, size_t nB) {
+    FlatPlan p;
+    p.cfg = choose_config(h, nA);
+    const uint32_t tile = knn2_tile_rows(p.cfg);
+    p.n_tiles = (uint32_t)((nA + tile - 1) / tile);
+    int ctas_per_sm = 1;
+    knn2_kernel_info(p.cfg, nullptr, &ctas_per_sm, nullptr);
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    p.grid = h->sm_count * ctas_per_sm;
+    plan_chunks(p.n_tiles, nB, p.grid, &p.n_chunks, &p.rows_per_chunk);
+    p.slot_stride = (nA + 31) & ~(size_t)31;
+    const uint64_t items = (uint64_t)p.n_tiles * p.n_chunks;
+    if ((uint64_t)p.grid > items) p.grid = (int)std::max<uint64_t>(items, 1);
+    return p;
+}
+
+// K1 + chunk merge for a flat searcher table against a flat database, results left in
+// h->knn_idx / h->knn_dist (and h->packed when want_packed).
+static int run_flat(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t nB, uint32_t row_base,
+                    bool want_packed) {
+    HULO_ARG(nA < (size_t)INT_MAX && nB + (size_t)row_base < (size_t)INT_MAX, "table too large for int32 indices");
+    HULO_CUDA(h->knn_idx.reserve(std::max<size_t>(nA, 1) * 2 * sizeof(int32_t)));
+    HULO_CUDA(h->knn_dist.reserve(std::max<size_t>(nA, 1) * 2 * sizeof(int32_t)));
+    if (want_packed) HULO_CUDA(h->packed.reserve(std::max<size_t>(nA, 1) * sizeof(int4)));
+    h->last_nA = nA;
+    if (nA == 0) return HULO_OK;
+    FlatPlan pl = plan_flat(h, nA, nB);
+    if (pl.n_chunks > 0) {
+        HULO_CUDA(h->partial.reserve((size_t)pl.n_chunks * pl.slot_stride * sizeof(uint2)));
+        HULO_CUDA(h->counter.reserve(sizeof(unsigned int)));
+        HULO_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(unsigned int), h->stream));
+        KnnParams kp{};
+        kp.A = A; kp.B = B; kp.items = nullptr;
+        kp.n_items = pl.n_tiles * pl.n_chunks;
+        kp.nA = (uint32_t)nA; kp.nB = (uint32_t)nB;
+        kp.n_tiles = pl.n_tiles; kp.rows_per_chunk = pl.rows_per_chunk;
+        kp.slot_stride = pl.slot_stride;
+        kp.partial = h->partial.as<uint2>();
+        kp.counter = h->counter.as<unsigned int>();
+        HULO_CUDA(knn2_launch(kp, pl.cfg, pl.grid, h->stream));
+        h->launches++;
+    }
+    HULO_CUDA(knn2_merge_launch(h->partial.as<uint2>(), (uint32_t)nA, pl.n_chunks, pl.slot_stride,
+                                pl.rows_per_chunk, row_base, h->knn_idx.as<int32_t>(),
+                                h->knn_dist.as<int32_t>(), want_packed ? h->packed.as<int4>() : nullptr,
+                                h->stream));
+    h->launches++;
+    return HULO_OK;
+}
+
+// Expand rows of `stride` bytes into zero-padded 64-byte rows inside a pinned staging buffer.
+static const uint8_t *stage_rows(HostBuf &hb, const uint8_t *rows, size_t n, size_t stride, cudaError_t *err) {
+    *err = cudaSuccess;
+    if (stride == HULO_ROW_BYTES) return rows;
+    *err = hb.reserve(std::max<size_t>(n, 1) * HULO_ROW_BYTES);
+    if (*err != cudaSuccess) return nullptr;
+    uint8_t *dst = hb.as<uint8_t>();
+    const size_t w = std::min<size_t>(stride, HULO_ROW_BYTES);
+    for (size_t i = 0; i < n; ++i) {
+        memcpy(dst + i * HULO_ROW_BYTES, rows + i * stride, w);
+        if (w < HULO_ROW_BYTES) memset(dst + i * HULO_ROW_BYTES + w, 0, HULO_ROW_BYTES - w);
+    }
+    return dst;
+}
+
+int run_flat_packed(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t nB, uint32_t row_base) {
+    return run_flat(h, A, nA, B, nB, row_base, true);
+}
+
+}  // namespace hulo
+
+using namespace hulo;
+
+extern "C" {
+
+int hulo_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *hulo_last_error(void) { return g_error.c_str(); }
+const char *hulo_version(void) { return "sfmlocalization_b200 0.1 (sm_100a)"; }
+
+int hulo_gpu_create(int device, hulo_gpu **out) {
+    HULO_ARG(out != nullptr, "out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("hulo_gpu_create: no CUDA device (%s); this library has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        return HULO_ERR_CUDA;
+    }
+    HULO_ARG(device >= 0 && device < n, "device index out of range");
+    HULO_CUDA(cudaSetDevice(device));
+    hulo_gpu *h = new (std::nothrow) hulo_gpu();
+    HULO_ARG(h != nullptr, "out of host memory");
+    h->device = device;
+    cudaDeviceProp prop;
+    HULO_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error("hulo_gpu_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                  prop.major, prop.minor);
+        delete h;
+        return HULO_ERR_CUDA;
+    }
+    h->sm_count = prop.multiProcessorCount;
+    HULO_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    HULO_CUDA(cudaEventCreate(&h->ev_start));
+    HULO_CUDA(cudaEventCreate(&h->ev_stop));
+    // tuning overrides (benchmark sweeps): HULO_KNN_THREADS / HULO_KNN_QPT / HULO_KNN_CSA
+    const int t = env_int("HULO_KNN_THREADS", 0), q = env_int("HULO_KNN_QPT", 0), c = env_int("HULO_KNN_CSA", -1);
+    if (t > 0 || q > 0 || c >= 0) {
+        if (t > 0) h->knn_cfg.threads = t;
+        if (q > 0) h->knn_cfg.qpt = q;
+        if (c >= 0) h->knn_cfg.csa = c;
+        h->knn_cfg_forced = true;
+        if (knn2_kernel_info(h->knn_cfg, nullptr, nullptr, nullptr) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("hulo_gpu_create: no K1 variant threads=%d qpt=%d csa=%d", h->knn_cfg.threads,
+                      h->knn_cfg.qpt, h->knn_cfg.csa);
+            hulo_gpu_destroy(h);
+            return HULO_ERR_ARG;
+        }
+    }
+    *out = h;
+    return HULO_OK;
+}
+
+void hulo_comm_destroy_internal(hulo_gpu *h);
+
+void hulo_gpu_destroy(hulo_gpu *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    hulo_comm_destroy_internal(h);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    DevBuf *bufs[] = {&h->partial, &h->counter, &h->items, &h->knn_idx, &h->knn_dist, &h->packed, &h->gathered,
+                      &h->stageA, &h->stageB, &h->scratch0, &h->scratch1, &h->scratch2, &h->scratch3};
+    for (DevBuf *b : bufs) b->release();
+    h->hstage0.release();
+    h->hstage1.release();
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int hulo_host_alloc(size_t bytes, void **out) {
+    HULO_ARG(out != nullptr, "out is null");
+    HULO_CUDA(cudaMallocHost(out, std::max<size_t>(bytes, 1)));
+    return HULO_OK;
+}
+void hulo_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int hulo_timer_start(hulo_gpu *h) {
+    HULO_ARG(h != nullptr, "null context");
+    HULO_CUDA(cudaEventRecord(h->ev_start, h->stream));
+    return HULO_OK;
+}
+int hulo_timer_stop(hulo_gpu *h, float *ms) {
+    HULO_ARG(h != nullptr && ms != nullptr, "null argument");
+    HULO_CUDA(cudaEventRecord(h->ev_stop, h->stream));
+    HULO_CUDA(cudaEventSynchronize(h->ev_stop));
+    HULO_CUDA(cudaEventElapsedTime(ms, h->ev_start, h->ev_stop));
+    return HULO_OK;
+}
+int hulo_synchronize(hulo_gpu *h) {
+    HULO_ARG(h != nullptr, "null context");
+    HULO_CUDA(cudaStreamSynchronize(h->stream));
+    return HULO_OK;
+}
+uint64_t hulo_launch_count(const hulo_gpu *h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------ descriptor rows
+int hulo_db_upload(hulo_gpu *h, const uint8_t *rows, size_t n, size_t stride, const uint64_t *seg_offsets,
+                   size_t n_seg, hulo_db **out) {
+    HULO_ARG(h != nullptr && out != nullptr, "null argument");
+    *out = nullptr;
+    HULO_ARG(n == 0 || rows != nullptr, "rows is null");
+    HULO_ARG(stride >= 1, "stride must be >= 1");
+    HULO_ARG(n < (size_t)INT_MAX, "too many rows");
+    if (seg_offsets) {
+        HULO_ARG(n_seg >= 1, "n_seg must be >= 1 when seg_offsets is given");
+        HULO_ARG(seg_offsets[0] == 0 && seg_offsets[n_seg] == n, "seg_offsets must start at 0 and end at n");
+        for (size_t s = 0; s < n_seg; ++s) HULO_ARG(seg_offsets[s] <= seg_offsets[s + 1], "seg_offsets not ascending");
+    }
+    HULO_CUDA(cudaSetDevice(h->device));
+    hulo_db *db = new (std::nothrow) hulo_db();
+    HULO_ARG(db != nullptr, "out of host memory");
+    db->owner = h;
+    db->n = n;
+    db->cap_rows = std::max<size_t>(n, 1);
+    cudaError_t e = cudaMalloc(&db->rows, db->cap_rows * HULO_ROW_BYTES);
+    if (e != cudaSuccess) {
+        set_error("hulo_db_upload: cudaMalloc(%zu) -> %s", db->cap_rows * (size_t)HULO_ROW_BYTES, cudaGetErrorString(e));
+        delete db;
+        return HULO_ERR_CUDA;
+    }
+    if (seg_offsets) db->seg.assign(seg_offsets, seg_offsets + n_seg + 1);
+    else db->seg = {0, (uint64_t)n};
+    int rc = hulo_db_update(h, db, rows, n, stride);
+    if (rc != HULO_OK) { hulo_db_free(db); return rc; }
+    *out = db;
+    return HULO_OK;
+}
+
+int hulo_db_update(hulo_gpu *h, hulo_db *db, const uint8_t *rows, size_t n, size_t stride) {
+    HULO_ARG(h != nullptr && db != nullptr, "null argument");
+    HULO_ARG(n <= db->cap_rows, "more rows than the table was created with");
+    HULO_ARG(n == 0 || rows != nullptr, "rows is null");
+    HULO_ARG(stride >= 1, "stride must be >= 1");
+    if (n != db->n) { db->n = n; db->seg = {0, (uint64_t)n}; }
+    if (n == 0) return HULO_OK;
+    if (stride == HULO_ROW_BYTES) {
+        HULO_CUDA(cudaMemcpyAsync(db->rows, rows, n * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
+    } else if (stride > HULO_ROW_BYTES) {
+        HULO_CUDA(cudaMemcpy2DAsync(db->rows, HULO_ROW_BYTES, rows, stride, HULO_ROW_BYTES, n,
+                                    cudaMemcpyHostToDevice, h->stream));
+    } else {
+        HULO_CUDA(cudaMemsetAsync(db->rows, 0, n * HULO_ROW_BYTES, h->stream));
+        HULO_CUDA(cudaMemcpy2DAsync(db->rows, HULO_ROW_BYTES, rows, stride, stride, n, cudaMemcpyHostToDevice,
+                                    h->stream));
+    }
+    HULO_CUDA(cudaStreamSynchronize(h->stream));
+    return HULO_OK;
+}
+
+void hulo_db_free(hulo_db *db) {
+    if (!db) return;
+    if (db->owner) cudaSetDevice(db->owner->device);
+    if (db->rows) cudaFree(db->rows);
+    delete db;
+}
+size_t hulo_db_rows(const hulo_db *db) { return db ? db->n : 0; }
+size_t hulo_db_segments(const hulo_db *db) { return db ? db->seg.size() - 1 : 0; }
+
+int hulo_db_download(hulo_gpu *h, const hulo_db *db, size_t first, size_t n, uint8_t *rows64) {
+    HULO_ARG(h != nullptr && db != nullptr, "null argument");
+    HULO_ARG(first + n <= db->n, "row range out of bounds");
+    if (n == 0) return HULO_OK;
+    HULO_ARG(rows64 != nullptr, "rows64 is null");
+    HULO_CUDA(cudaMemcpyAsync(rows64, db->rows + first * 4, n * HULO_ROW_BYTES, cudaMemcpyDeviceToHost, h->stream));
+    HULO_CUDA(cudaStreamSynchronize(h->stream));
+    return HULO_OK;
+}
+
+// ------------------------------------------------------------------- K1: 2-NN
+int hulo_knn2_fetch(hulo_gpu *h, size_t nA, int32_t *idx2, int32_t *dist2) {
+    HULO_ARG(h != nullptr, "null context");
+    HULO_ARG(nA <= h->last_nA, "more rows requested than the last search produced");
+    if (nA > 0) {
+        if (idx2) HULO_CUDA(cudaMemcpyAsync(idx2, h->knn_idx.ptr, nA * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        if (dist2) HULO_CUDA(cudaMemcpyAsync(dist2, h->knn_dist.ptr, nA * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    }
+    HULO_CUDA(cudaStreamSynchronize(h->stream));
+    return HULO_OK;
+}
+
+int hulo_knn2(hulo_gpu *h, const hulo_db *A, const hulo_db *B, int32_t *idx2, int32_t *dist2) {
+    HULO_ARG(h != nullptr && A != nullptr && B != nullptr, "null argument");
+    HULO_CUDA(cudaSetDevice(h->device));
+    int rc = run_flat(h, A->rows, A->n, B->rows, B->n, 0, false);
+    if (rc != HULO_OK) return rc;
+    if (idx2 || dist2) return hulo_knn2_fetch(h, A->n, idx2, dist2);
+    return HULO_OK;
+}
+
+int hulo_knn2_host(hulo_gpu *h, const uint8_t *A, size_t nA, size_t strideA, const uint8_t *B, size_t nB,
+                   size_t strideB, int32_t *idx2, int32_t *dist2) {
+    HULO_ARG(h != nullptr, "null context");
+    HULO_ARG((nA == 0 || A != nullptr) && (nB == 0 || B != nullptr), "null rows");
+    HULO_ARG(strideA >= 1 && strideB >= 1, "stride must be >= 1");
+    HULO_ARG(nA == 0 || (idx2 != nullptr && dist2 != nullptr), "null output");
+    HULO_CUDA(cudaSetDevice(h->device));
+    HULO_CUDA(h->stageA.reserve(std::max<size_t>(nA, 1) * HULO_ROW_BYTES));
+    HULO_CUDA(h->stageB.reserve(std::max<size_t>(nB, 1) * HULO_ROW_BYTES));
+    cudaError_t e;
+    const uint8_t *a64 = stage_rows(h->hstage0, A, nA, strideA, &e);
+    HULO_CUDA(e);
+    const uint8_t *b64 = stage_rows(h->hstage1, B, nB, strideB, &e);
+    HULO_CUDA(e);
+    if (nA) HULO_CUDA(cudaMemcpyAsync(h->stageA.ptr, a64, nA * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
+    if (nB) HULO_CUDA(cudaMemcpyAsync(h->stageB.ptr, b64, nB * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
+    int rc = run_flat(h, h->stageA.as<uint4>(), nA, h->stageB.as<uint4>(), nB, 0, false);
+    if (rc != HULO_OK) return rc;
+    return hulo_knn2_fetch(h, nA, idx2, dist2);
+}
+
+// --------------------------------------------- query localisation, reference direction
+int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, size_t n_views,
+                        const uint8_t *query, size_t nq, size_t q_stride, float ratio, uint32_t *out_view,
+                        uint32_t *out_i, uint32_t *out_j, int32_t *out_d0, size_t cap, size_t *n_out,
+                        uint32_t *view_counts) {
+    HULO_ARG(h != nullptr && map != nullptr && n_out != nullptr, "null argument");
+    HULO_ARG(nq == 0 || query != nullptr, "query is null");
+    HULO_ARG(q_stride >= 1, "stride must be >= 1");
+    HULO_ARG(nq <= kMaxChunkRows * 64ull, "query too large");
+    *n_out = 0;
+    HULO_CUDA(cudaSetDevice(h->device));
+    const size_t n_seg = map->seg.size() - 1;
+    if (views == nullptr) n_views = n_seg;
+    for (size_t v = 0; views && v < n_views; ++v) HULO_ARG(views[v] < n_seg, "view index out of range");
+    if (view_counts) memset(view_counts, 0, n_views * sizeof(uint32_t));
+    // MatchUtils.cpp:299-301: nothing to do without query rows
+    if (nq < 1 || n_views == 0) return HULO_OK;
+
+    // compact row space: the rows of the selected views, concatenated in the order given
+    std::vector<uint64_t> sel_off(n_views + 1, 0);
+    for (size_t v = 0; v < n_views; ++v) {
+        const size_t s = views ? views[v] : v;
+        sel_off[v + 1] = sel_off[v] + (map->seg[s + 1] - map->seg[s]);
+    }
+    const uint64_t n_rows = sel_off[n_views];
+    HULO_ARG(n_rows < (uint64_t)INT_MAX, "too many rows selected");
+    if (n_rows == 0) return HULO_OK;
+
+    // upload the query rows
+    HULO_CUDA(h->stageB.reserve(nq * HULO_ROW_BYTES));
+    cudaError_t e;
+    const uint8_t *q64 = stage_rows(h->hstage1, query, nq, q_stride, &e);
+    HULO_CUDA(e);
+    HULO_CUDA(cudaMemcpyAsync(h->stageB.ptr, q64, nq * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
+
+    // items: maximal runs of views that are contiguous in the table, tiled, x chunks of the query
+    const KnnConfig cfg = choose_config(h, (size_t)n_rows);
+    const uint32_t tile = knn2_tile_rows(cfg);
+    struct Run { uint64_t a0, rows, slot0; };
+    std::vector<Run> runs;
+    for (size_t v = 0; v < n_views; ++v) {
+        const size_t s = views ? views[v] : v;
+        const uint64_t a0 = map->seg[s], rows = map->seg[s + 1] - map->seg[s];
+        if (rows == 0) continue;
+        if (!runs.empty() && runs.back().a0 + runs.back().rows == a0) runs.back().rows += rows;
+        else runs.push_back(Run{a0, rows, sel_off[v]});
+    }
+    uint64_t n_tiles = 0;
+    for (const Run &r : runs) n_tiles += (r.rows + tile - 1) / tile;
+    int ctas_per_sm = 1;
+    knn2_kernel_info(cfg, nullptr, &ctas_per_sm, nullptr);
+    int grid = h->sm_count * std::max(1, ctas_per_sm);
+    uint32_t n_chunks = 0, rows_per_chunk = 1;
+    plan_chunks((uint32_t)n_tiles, nq, grid, &n_chunks, &rows_per_chunk);
+    const uint64_t slot_stride = (n_rows + 31) & ~31ull;
+    std::vector<KnnItem> items;
+    items.reserve((size_t)n_tiles * n_chunks);
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const uint32_t b0 = c * rows_per_chunk;
+        const uint32_t brows = (uint32_t)std::min<uint64_t>(rows_per_chunk, nq - b0);
+        for (const Run &r : runs)
+            for (uint64_t t0 = 0; t0 < r.rows; t0 += tile) {
+                KnnItem it{};
+                it.a_row0 = (uint32_t)(r.a0 + t0);
+                it.a_rows = (uint32_t)std::min<uint64_t>(tile, r.rows - t0);
+                it.b_row0 = b0;
+                it.b_rows = brows;
+                it.out_slot0 = (uint64_t)c * slot_stride + r.slot0 + t0;
+                items.push_back(it);
+            }
+    }
+    grid = (int)std::min<size_t>((size_t)grid, items.size());
+
+    HULO_CUDA(h->items.reserve(items.size() * sizeof(KnnItem)));
+    HULO_CUDA(cudaMemcpyAsync(h->items.ptr, items.data(), items.size() * sizeof(KnnItem), cudaMemcpyHostToDevice, h->stream));
+    HULO_CUDA(h->partial.reserve((size_t)n_chunks * slot_stride * sizeof(uint2)));
+    HULO_CUDA(h->counter.reserve(sizeof(unsigned int)));
+    HULO_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(unsigned int), h->stream));
+    // scratch0: val | dist ; scratch1: seg offsets (device) ; scratch2: block counts, seg_out_off, total
+    // scratch3: compacted outputs view | i | j | d0
+    const size_t n_blocks = (n_rows + kCompactBlockRows - 1) / kCompactBlockRows;
+    HULO_CUDA(h->scratch0.reserve(n_rows * 2 * sizeof(int32_t)));
+    HULO_CUDA(h->scratch1.reserve((n_views + 1) * sizeof(uint64_t)));
+    HULO_CUDA(h->scratch2.reserve((n_blocks + 2) * sizeof(uint32_t) + (n_views + 2) * sizeof(uint64_t) + 64));
+    HULO_CUDA(h->scratch3.reserve(n_rows * 4 * sizeof(uint32_t)));
+    HULO_CUDA(cudaMemcpyAsync(h->scratch1.ptr, sel_off.data(), (n_views + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+
+    KnnParams kp{};
+    kp.A = map->rows; kp.B = h->stageB.as<uint4>();
+    kp.items = h->items.as<KnnItem>();
+    kp.n_items = (uint32_t)items.size();
+    kp.partial = h->partial.as<uint2>();
+    kp.counter = h->counter.as<unsigned int>();
+    HULO_CUDA(knn2_launch(kp, cfg, grid, h->stream));
+    h->launches++;
+
+    int32_t *val = h->scratch0.as<int32_t>();
+    int32_t *dist = val + n_rows;
+    HULO_CUDA(post_query_launch(h->partial.as<uint2>(), (uint32_t)n_rows, n_chunks, slot_stride, rows_per_chunk,
+                                ratio, val, dist, h->stream));
+    h->launches++;
+    uint8_t *s2 = h->scratch2.as<uint8_t>();
+    uint64_t *d_total = reinterpret_cast<uint64_t *>(s2);
+    uint64_t *d_seg_out = d_total + 1;
+    uint32_t *d_blocks = reinterpret_cast<uint32_t *>(d_seg_out + (n_views + 1));
+    uint32_t *o_view = h->scratch3.as<uint32_t>();
+    uint32_t *o_i = o_view + n_rows, *o_j = o_i + n_rows;
+    int32_t *o_d = reinterpret_cast<int32_t *>(o_j + n_rows);
+    HULO_CUDA(compact_launch(val, dist, (uint32_t)n_rows, h->scratch1.as<uint64_t>(), (uint32_t)n_views, d_blocks,
+                             o_view, o_i, o_j, o_d, d_seg_out, d_total, h->stream));
+    h->launches += kCompactLaunches;
+
+    // total + per-view offsets first, then exactly the survivors
+    HULO_CUDA(h->hstage0.reserve((n_views + 2) * sizeof(uint64_t)));
+    uint64_t *h_tot = h->hstage0.as<uint64_t>();
+    HULO_CUDA(cudaMemcpyAsync(h_tot, d_total, (n_views + 2) * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    HULO_CUDA(cudaStreamSynchronize(h->stream));
+    const uint64_t total = h_tot[0];
+    *n_out = (size_t)total;
+    if (view_counts)
+        for (size_t v = 0; v < n_views; ++v) view_counts[v] = (uint32_t)(h_tot[2 + v] - h_tot[1 + v]);
+    if (total > cap) {
+        set_error("hulo_match_to_query: %llu matches, capacity %zu", (unsigned long long)total, cap);
+        return HULO_ERR_CAPACITY;
+    }
+    if (total > 0) {
+        HULO_ARG(out_i != nullptr && out_j != nullptr, "null output");
+        if (out_view) HULO_CUDA(cudaMemcpyAsync(out_view, o_view, total * 4, cudaMemcpyDeviceToHost, h->stream));
+        HULO_CUDA(cudaMemcpyAsync(out_i, o_i, total * 4, cudaMemcpyDeviceToHost, h->stream));
+        HULO_CUDA(cudaMemcpyAsync(out_j, o_j, total * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (out_d0) HULO_CUDA(cudaMemcpyAsync(out_d0, o_d, total * 4, cudaMemcpyDeviceToHost, h->stream));
+        HULO_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return HULO_OK;
+}
+
+// ------------------------------------------------ image-pair matching (reconstruction)
+int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size_t n_pairs, float ratio,
+                     unsigned flags, uint64_t *pair_offsets, uint32_t *out_i, uint32_t *out_j, size_t cap,
+                     size_t *n_out) {
+    HULO_ARG(h != nullptr && db != nullptr && n_out != nullptr, "null argument");
+    HULO_ARG(n_pairs == 0 || pairs != nullptr, "pairs is null");
+    *n_out = 0;
+    HULO_CUDA(cudaSetDevice(h->device));
+    const size_t n_seg = db->seg.size() - 1;
+    for (size_t p = 0; p < n_pairs; ++p)
+        HULO_ARG(pairs[2 * p] < n_seg && pairs[2 * p + 1] < n_seg, "pair refers to a segment that does not exist");
+    if (pair_offsets) pair_offsets[0] = 0;
+
+    const KnnConfig cfg = h->knn_cfg_forced ? h->knn_cfg : KnnConfig{256, 4, 7};
+    const uint32_t tile = knn2_tile_rows(cfg);
+    int ctas_per_sm = 1;
+    knn2_kernel_info(cfg, nullptr, &ctas_per_sm, nullptr);
+    const int full_grid = h->sm_count * std::max(1, ctas_per_sm);
+
+    // batches bounded by compact searcher rows so the scratch stays modest
+    const uint64_t max_batch_rows = (uint64_t)std::max(1, env_int("HULO_PAIR_BATCH_ROWS", 16 << 20));
+    size_t total_out = 0;
+    bool overflow = false;
+    size_t p0 = 0;
+    std::vector<uint64_t> row_off, hist_off, h_seg_out;
+    std::vector<KnnItem> items;
+    while (p0 < n_pairs) {
+        row_off.assign(1, 0);
+        hist_off.assign(1, 0);
+        items.clear();
+        size_t p1 = p0;
+        while (p1 < n_pairs) {
+            const uint32_t I = pairs[2 * p1], J = pairs[2 * p1 + 1];
+            const uint64_t nI = db->seg[I + 1] - db->seg[I], nJ = db->seg[J + 1] - db->seg[J];
+            // MatchUtils.cpp:99-101: pairs with fewer than two rows on either side are skipped
+            const bool skip = nI < 2 || nJ < 2;
+            HULO_ARG(skip || nJ <= kMaxChunkRows, "image with more than 4 Mi descriptors");
+            const uint64_t add = skip ? 0 : nI;
+            if (p1 > p0 && row_off.back() + add > max_batch_rows) break;
+            if (!skip) {
+                for (uint64_t t0 = 0; t0 < nI; t0 += tile) {
+                    KnnItem it{};
+                    it.a_row0 = (uint32_t)(db->seg[I] + t0);
+                    it.a_rows = (uint32_t)std::min<uint64_t>(tile, nI - t0);
+                    it.b_row0 = (uint32_t)db->seg[J];
+                    it.b_rows = (uint32_t)nJ;
+                    it.out_slot0 = row_off.back() + t0;
+                    items.push_back(it);
+                }
+            }
+            row_off.push_back(row_off.back() + add);
+            hist_off.push_back(hist_off.back() + (skip ? 0 : nJ));
+            ++p1;
+        }
+        const size_t bp = p1 - p0;
+        const uint64_t n_rows = row_off.back();
+        HULO_ARG(n_rows < (uint64_t)INT_MAX, "batch too large");
+        if (n_rows > 0) {
+            const size_t n_blocks = (n_rows + kCompactBlockRows - 1) / kCompactBlockRows;
+            HULO_CUDA(h->items.reserve(items.size() * sizeof(KnnItem)));
+            HULO_CUDA(cudaMemcpyAsync(h->items.ptr, items.data(), items.size() * sizeof(KnnItem), cudaMemcpyHostToDevice, h->stream));
+            HULO_CUDA(h->partial.reserve(n_rows * sizeof(uint2)));
+            HULO_CUDA(h->counter.reserve(sizeof(unsigned int)));
+            HULO_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(unsigned int), h->stream));
+            // scratch0: val ; scratch1: row_off | hist_off (device) ; scratch2: total, seg_out_off, block counts
+            // scratch3: out_i | out_j ; gathered (reused): claim histogram
+            HULO_CUDA(h->scratch0.reserve(n_rows * sizeof(int32_t)));
+            HULO_CUDA(h->scratch1.reserve(2 * (bp + 1) * sizeof(uint64_t)));
+            HULO_CUDA(h->scratch2.reserve((n_blocks + 2) * sizeof(uint32_t) + (bp + 2) * sizeof(uint64_t) + 64));
+            HULO_CUDA(h->scratch3.reserve(n_rows * 2 * sizeof(uint32_t)));
+            HULO_CUDA(h->gathered.reserve(std::max<uint64_t>(hist_off.back(), 1) * sizeof(uint32_t)));
+            uint64_t *d_row_off = h->scratch1.as<uint64_t>();
+            uint64_t *d_hist_off = d_row_off + (bp + 1);
+            HULO_CUDA(cudaMemcpyAsync(d_row_off, row_off.data(), (bp + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+            HULO_CUDA(cudaMemcpyAsync(d_hist_off, hist_off.data(), (bp + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+            HULO_CUDA(cudaMemsetAsync(h->gathered.ptr, 0, std::max<uint64_t>(hist_off.back(), 1) * sizeof(uint32_t), h->stream));
+
+            KnnParams kp{};
+            kp.A = db->rows; kp.B = db->rows;
+            kp.items = h->items.as<KnnItem>();
+            kp.n_items = (uint32_t)items.size();
+            kp.partial = h->partial.as<uint2>();
+            kp.counter = h->counter.as<unsigned int>();
+            HULO_CUDA(knn2_launch(kp, cfg, (int)std::min<size_t>((size_t)full_grid, items.size()), h->stream));
+            h->launches++;
+
+            int32_t *val = h->scratch0.as<int32_t>();
+            uint32_t *hist = h->gathered.as<uint32_t>();
+            HULO_CUDA(post_pair_claim_launch(h->partial.as<uint2>(), (uint32_t)n_rows, d_row_off, d_hist_off,
+                                             (uint32_t)bp, ratio, val, hist, h->stream));
+            h->launches++;
+            if (flags & (HULO_PAIR_ONE_TO_ONE | HULO_PAIR_DROP_LAST)) {
+                HULO_CUDA(post_pair_filter_launch((uint32_t)n_rows, d_row_off, d_hist_off, (uint32_t)bp, flags, val,
+                                                  hist, h->stream));
+                h->launches++;
+            }
+            uint8_t *s2 = h->scratch2.as<uint8_t>();
+            uint64_t *d_total = reinterpret_cast<uint64_t *>(s2);
+            uint64_t *d_seg_out = d_total + 1;
+            uint32_t *d_blocks = reinterpret_cast<uint32_t *>(d_seg_out + (bp + 1));
+            uint32_t *o_i = h->scratch3.as<uint32_t>(), *o_j = o_i + n_rows;
+            HULO_CUDA(compact_launch(val, nullptr, (uint32_t)n_rows, d_row_off, (uint32_t)bp, d_blocks, nullptr, o_i,
+                                     o_j, nullptr, d_seg_out, d_total, h->stream));
+            h->launches += kCompactLaunches;
+
+            h_seg_out.resize(bp + 2);
+            HULO_CUDA(cudaMemcpyAsync(h_seg_out.data(), d_total, (bp + 2) * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+            HULO_CUDA(cudaStreamSynchronize(h->stream));
+            const uint64_t total = h_seg_out[0];
+            if (pair_offsets)
+                for (size_t p = 0; p < bp; ++p) pair_offsets[p0 + p + 1] = total_out + h_seg_out[2 + p];
+            if (!overflow && total_out + total <= cap) {
+                if (total > 0) {
+                    HULO_ARG(out_i != nullptr && out_j != nullptr, "null output");
+                    HULO_CUDA(cudaMemcpyAsync(out_i + total_out, o_i, total * 4, cudaMemcpyDeviceToHost, h->stream));
+                    HULO_CUDA(cudaMemcpyAsync(out_j + total_out, o_j, total * 4, cudaMemcpyDeviceToHost, h->stream));
+                    HULO_CUDA(cudaStreamSynchronize(h->stream));
+                }
+            } else {
+                overflow = true;
+            }
+            total_out += total;
+        } else if (pair_offsets) {
+            for (size_t p = 0; p < bp; ++p) pair_offsets[p0 + p + 1] = total_out;
+        }
+        p0 = p1;
+    }
+    *n_out = total_out;
+    if (overflow) {
+        set_error("hulo_match_pairs: %zu matches, capacity %zu", total_out, cap);
+        return HULO_ERR_CAPACITY;
+    }
+    return HULO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// context.cuh -- internal state behind the opaque handles of include/hulo_gpu.h.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+
+#include "../../include/hulo_gpu.h"
+#include "knn2.cuh"
+
+namespace hulo {
+
+void set_error(const char *fmt, ...);
+
+#define HULO_CUDA(expr)                                                                       \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            hulo::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+            return HULO_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+#define HULO_ARG(cond, msg)                                  \
+    do {                                                     \
+        if (!(cond)) {                                       \
+            hulo::set_error("%s: %s", __func__, msg);        \
+            return HULO_ERR_ARG;                             \
+        }                                                    \
+    } while (0)
+
+// A device buffer that only ever grows (scratch reused across calls).
+struct DevBuf {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&ptr, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+// Same for pinned host staging.
+struct HostBuf {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&ptr, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFreeHost(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(ptr); }
+};
+
+}  // namespace hulo
+
+struct hulo_db {
+    hulo_gpu *owner = nullptr;
+    uint4 *rows = nullptr;             // n x 64 bytes
+    size_t n = 0;
+    size_t cap_rows = 0;
+    std::vector<uint64_t> seg;         // n_seg + 1 offsets
+};
+
+struct hulo_gpu {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    uint64_t launches = 0;
+    hulo::KnnConfig knn_cfg{256, 8, 7};
+    bool knn_cfg_forced = false;
+
+    hulo::DevBuf partial;      // K1 per-item keys
+    hulo::DevBuf counter;      // K1 dynamic item counter
+    hulo::DevBuf items;        // K1 item list (pair / view modes)
+    hulo::DevBuf knn_idx, knn_dist;   // final nA x 2 results
+    hulo::DevBuf packed;       // nA x int4 (sharded exchange)
+    hulo::DevBuf gathered;     // world x nA x int4
+    hulo::DevBuf stageA, stageB;      // uploaded rows of the *_host entry points
+    hulo::DevBuf scratch0, scratch1, scratch2, scratch3;   // post-processing / K2
+    hulo::HostBuf hstage0, hstage1;
+    size_t last_nA = 0;
+
+    // NCCL (loaded lazily)
+    void *nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};

@@ -1,0 +1,363 @@
+// knn2.cu -- K1 kernels (see knn2.cuh for the design).
+#include "knn2.cuh"
+
+#include <climits>
+
+namespace hulo {
+
+namespace {
+
+constexpr int kTileRows = 64;  // database rows per smem stage (4 KB)
+constexpr int kStages = 3;
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ uint32_t xor3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+// carry-save adder: three words of weight w -> one of weight w (lo) and one of weight 2w (hi)
+#define HULO_CSA(hi, lo, a, b, c) \
+    do {                          \
+        lo = xor3(a, b, c);       \
+        hi = maj3(a, b, c);       \
+    } while (0)
+
+// 512-bit Hamming distance of a register-resident searcher row q and a database row w.
+// CSA = number of carry-save adders applied before the POPCs (0: plain 16 POPC).
+template <int CSA>
+__device__ __forceinline__ uint32_t hamming512(const uint32_t (&q)[16], const uint32_t (&w)[16]) {
+    uint32_t x[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x[k] = q[k] ^ w[k];
+    if constexpr (CSA == 0) {
+        uint32_t d = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d += __popc(x[k]);
+        return d;
+    } else {
+        // level 1: 15 words -> 5 sums (weight 1) + 5 carries (weight 2); x[15] left over
+        uint32_t s0, s1, s2, s3, s4, c0, c1, c2, c3, c4;
+        HULO_CSA(c0, s0, x[0], x[1], x[2]);
+        HULO_CSA(c1, s1, x[3], x[4], x[5]);
+        HULO_CSA(c2, s2, x[6], x[7], x[8]);
+        HULO_CSA(c3, s3, x[9], x[10], x[11]);
+        HULO_CSA(c4, s4, x[12], x[13], x[14]);
+        if constexpr (CSA == 5) {
+            uint32_t ones = __popc(s0) + __popc(s1) + __popc(s2) + __popc(s3) + __popc(s4) + __popc(x[15]);
+            uint32_t twos = __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) + __popc(c4);
+            return ones + 2u * twos;
+        } else {
+            // level 2: the six weight-1 words -> 2 sums + 2 carries
+            uint32_t s5, s6, c5, c6;
+            HULO_CSA(c5, s5, s0, s1, s2);
+            HULO_CSA(c6, s6, s3, s4, x[15]);
+            if constexpr (CSA == 7) {
+                uint32_t ones = __popc(s5) + __popc(s6);
+                uint32_t twos = __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) + __popc(c4) + __popc(c5) +
+                                __popc(c6);
+                return ones + 2u * twos;
+            } else {
+                // level 3: seven weight-2 words -> (t0, t1, c6) + two weight-4 words
+                uint32_t t0, t1, f0, f1;
+                HULO_CSA(f0, t0, c0, c1, c2);
+                HULO_CSA(f1, t1, c3, c4, c5);
+                if constexpr (CSA == 9) {
+                    uint32_t ones = __popc(s5) + __popc(s6);
+                    uint32_t twos = __popc(t0) + __popc(t1) + __popc(c6);
+                    uint32_t fours = __popc(f0) + __popc(f1);
+                    return ones + 2u * twos + 4u * fours;
+                } else {
+                    static_assert(CSA == 11, "unsupported CSA depth");
+                    uint32_t t2, f2, f3, e0;
+                    HULO_CSA(f2, t2, t0, t1, c6);
+                    HULO_CSA(e0, f3, f0, f1, f2);
+                    uint32_t ones = __popc(s5) + __popc(s6);
+                    return ones + 2u * __popc(t2) + 4u * __popc(f3) + 8u * __popc(e0);
+                }
+            }
+        }
+    }
+}
+
+template <int THREADS, int QPT, int CSA>
+__global__ void __launch_bounds__(THREADS, 1) knn2_kernel(const KnnParams p) {
+    constexpr int kWarps = THREADS / 32;
+    __shared__ __align__(128) uint4 s_tiles[kStages][kTileRows * 4];
+    __shared__ __align__(8) uint64_t s_full[kStages];
+    __shared__ __align__(8) uint64_t s_empty[kStages];
+    __shared__ uint32_t s_item;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], kWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    uint32_t n_cons = 0;   // tiles consumed so far by this thread (all threads agree)
+    uint32_t n_prod = 0;   // tiles issued so far (thread 0)
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(p.counter, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        __syncthreads();
+        if (item >= p.n_items) break;
+
+        uint32_t a_row0, a_rows, b_row0, b_rows;
+        uint64_t out_slot0;
+        if (p.items != nullptr) {
+            const KnnItem it = p.items[item];
+            a_row0 = it.a_row0; a_rows = it.a_rows; b_row0 = it.b_row0; b_rows = it.b_rows;
+            out_slot0 = it.out_slot0;
+        } else {
+            const uint32_t tile = item % p.n_tiles, chunk = item / p.n_tiles;
+            a_row0 = tile * (uint32_t)(THREADS * QPT);
+            a_rows = min((uint32_t)(THREADS * QPT), p.nA - a_row0);
+            b_row0 = chunk * p.rows_per_chunk;
+            b_rows = min(p.rows_per_chunk, p.nB - b_row0);
+            out_slot0 = (uint64_t)chunk * p.slot_stride + a_row0;
+        }
+
+        // searcher rows -> registers
+        uint32_t q[QPT][16];
+        uint32_t best0[QPT], best1[QPT];
+#pragma unroll
+        for (int qi = 0; qi < QPT; ++qi) {
+            const uint32_t r = (uint32_t)(qi * THREADS + tid);
+            best0[qi] = kKeyNone;
+            best1[qi] = kKeyNone;
+            if (r < a_rows) {
+                const uint4 *src = p.A + (size_t)(a_row0 + r) * 4;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const uint4 t = __ldg(src + v);
+                    q[qi][4 * v + 0] = t.x; q[qi][4 * v + 1] = t.y;
+                    q[qi][4 * v + 2] = t.z; q[qi][4 * v + 3] = t.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) q[qi][k] = 0u;
+            }
+        }
+
+        const uint32_t n_tiles = (b_rows + kTileRows - 1) / kTileRows;
+        const uint4 *bsrc = p.B + (size_t)b_row0 * 4;
+
+        // producer prologue: fill the ring
+        if (tid == 0) {
+            const uint32_t pre = n_tiles < (uint32_t)kStages ? n_tiles : (uint32_t)kStages;
+            for (uint32_t t = 0; t < pre; ++t) {
+                const uint32_t stage = n_prod % kStages;
+                if (n_prod >= (uint32_t)kStages) mbar_wait(&s_empty[stage], ((n_prod / kStages) - 1) & 1);
+                const uint32_t rows = min((uint32_t)kTileRows, b_rows - t * kTileRows);
+                mbar_expect_tx(&s_full[stage], rows * 64u);
+                tma_load_1d(&s_tiles[stage][0], bsrc + (size_t)t * kTileRows * 4, rows * 64u, &s_full[stage]);
+                ++n_prod;
+            }
+        }
+
+        for (uint32_t t = 0; t < n_tiles; ++t) {
+            const uint32_t stage = n_cons % kStages;
+            mbar_wait(&s_full[stage], (n_cons / kStages) & 1);
+            const uint32_t rows = min((uint32_t)kTileRows, b_rows - t * kTileRows);
+            const uint4 *tile = &s_tiles[stage][0];
+            const uint32_t key_base = t * kTileRows;
+#pragma unroll 2
+            for (uint32_t r = 0; r < rows; ++r) {
+                uint32_t w[16];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const uint4 tv = tile[r * 4 + v];   // same address in every lane: broadcast
+                    w[4 * v + 0] = tv.x; w[4 * v + 1] = tv.y; w[4 * v + 2] = tv.z; w[4 * v + 3] = tv.w;
+                }
+                const uint32_t ridx = key_base + r;
+#pragma unroll
+                for (int qi = 0; qi < QPT; ++qi) {
+                    const uint32_t d = hamming512<CSA>(q[qi], w);
+                    const uint32_t key = (d << kKeyIdxBits) + ridx;
+                    const uint32_t hi = max(best0[qi], key);
+                    best0[qi] = min(best0[qi], key);
+                    best1[qi] = min(best1[qi], hi);
+                }
+            }
+            ++n_cons;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[stage]);
+            // producer: refill this stage with tile t + kStages
+            if (tid == 0 && t + kStages < n_tiles) {
+                const uint32_t tn = t + kStages;
+                const uint32_t pstage = n_prod % kStages;   // == stage
+                mbar_wait(&s_empty[pstage], ((n_prod / kStages) - 1) & 1);
+                const uint32_t prow = min((uint32_t)kTileRows, b_rows - tn * kTileRows);
+                mbar_expect_tx(&s_full[pstage], prow * 64u);
+                tma_load_1d(&s_tiles[pstage][0], bsrc + (size_t)tn * kTileRows * 4, prow * 64u, &s_full[pstage]);
+                ++n_prod;
+            }
+        }
+
+#pragma unroll
+        for (int qi = 0; qi < QPT; ++qi) {
+            const uint32_t r = (uint32_t)(qi * THREADS + tid);
+            if (r < a_rows) p.partial[out_slot0 + r] = make_uint2(best0[qi], best1[qi]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------- merge
+__device__ __forceinline__ void top2_insert(uint64_t k, uint64_t &m0, uint64_t &m1) {
+    const uint64_t hi = k > m0 ? k : m0;
+    m0 = k < m0 ? k : m0;
+    m1 = hi < m1 ? hi : m1;
+}
+
+constexpr uint64_t kNone64 = ~0ull;
+
+__device__ __forceinline__ void write_result(uint64_t m0, uint64_t m1, uint32_t row, int32_t *out_idx2,
+                                             int32_t *out_dist2, int4 *out_packed) {
+    const int32_t d0 = m0 == kNone64 ? INT_MAX : (int32_t)(m0 >> 32);
+    const int32_t i0 = m0 == kNone64 ? -1 : (int32_t)(uint32_t)m0;
+    const int32_t d1 = m1 == kNone64 ? INT_MAX : (int32_t)(m1 >> 32);
+    const int32_t i1 = m1 == kNone64 ? -1 : (int32_t)(uint32_t)m1;
+    if (out_idx2) reinterpret_cast<int2 *>(out_idx2)[row] = make_int2(i0, i1);
+    if (out_dist2) reinterpret_cast<int2 *>(out_dist2)[row] = make_int2(d0, d1);
+    if (out_packed) out_packed[row] = make_int4(d0, i0, d1, i1);
+}
+
+__global__ void knn2_merge_kernel(const uint2 *__restrict__ partial, uint32_t nA, uint32_t n_chunks,
+                                  uint64_t slot_stride, uint32_t rows_per_chunk, uint32_t row_base,
+                                  int32_t *out_idx2, int32_t *out_dist2, int4 *out_packed) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nA) return;
+    uint64_t m0 = kNone64, m1 = kNone64;
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const uint2 k = partial[(uint64_t)c * slot_stride + row];
+        const uint32_t base = row_base + c * rows_per_chunk;
+        if (k.x != kKeyNone)
+            top2_insert(((uint64_t)(k.x >> kKeyIdxBits) << 32) | (uint64_t)(base + (k.x & kKeyIdxMask)), m0, m1);
+        if (k.y != kKeyNone)
+            top2_insert(((uint64_t)(k.y >> kKeyIdxBits) << 32) | (uint64_t)(base + (k.y & kKeyIdxMask)), m0, m1);
+    }
+    write_result(m0, m1, row, out_idx2, out_dist2, out_packed);
+}
+
+__global__ void knn2_merge_ranks_kernel(const int4 *__restrict__ gathered, uint32_t nA, int world,
+                                        int32_t *out_idx2, int32_t *out_dist2) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nA) return;
+    uint64_t m0 = kNone64, m1 = kNone64;
+    for (int g = 0; g < world; ++g) {
+        const int4 c = gathered[(size_t)g * nA + row];
+        if (c.y >= 0) top2_insert(((uint64_t)(uint32_t)c.x << 32) | (uint32_t)c.y, m0, m1);
+        if (c.w >= 0) top2_insert(((uint64_t)(uint32_t)c.z << 32) | (uint32_t)c.w, m0, m1);
+    }
+    write_result(m0, m1, row, out_idx2, out_dist2, nullptr);
+}
+
+template <int THREADS, int QPT, int CSA>
+cudaError_t launch_variant(const KnnParams &p, int grid, cudaStream_t stream) {
+    knn2_kernel<THREADS, QPT, CSA><<<grid, THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+template <int THREADS, int QPT, int CSA>
+cudaError_t info_variant(int *regs, int *ctas, size_t *smem) {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, knn2_kernel<THREADS, QPT, CSA>);
+    if (e != cudaSuccess) return e;
+    if (regs) *regs = a.numRegs;
+    if (smem) *smem = a.sharedSizeBytes;
+    int n = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, knn2_kernel<THREADS, QPT, CSA>, THREADS, 0);
+    if (ctas) *ctas = n;
+    return e;
+}
+
+}  // namespace
+
+#define HULO_KNN_VARIANTS(X) \
+    X(256, 8, 0) X(256, 8, 5) X(256, 8, 7) X(256, 8, 9) X(256, 8, 11) \
+    X(512, 4, 0) X(512, 4, 7) X(512, 4, 9) \
+    X(256, 4, 7) X(256, 4, 9) X(128, 8, 7) X(128, 8, 9) X(128, 4, 7) X(256, 6, 7) X(256, 6, 9)
+
+cudaError_t knn2_launch(const KnnParams &p, const KnnConfig &cfg, int grid_ctas, cudaStream_t stream) {
+#define X(T, Q, C) \
+    if (cfg.threads == T && cfg.qpt == Q && cfg.csa == C) return launch_variant<T, Q, C>(p, grid_ctas, stream);
+    HULO_KNN_VARIANTS(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t knn2_kernel_info(const KnnConfig &cfg, int *regs, int *max_ctas_per_sm, size_t *smem) {
+#define X(T, Q, C) \
+    if (cfg.threads == T && cfg.qpt == Q && cfg.csa == C) return info_variant<T, Q, C>(regs, max_ctas_per_sm, smem);
+    HULO_KNN_VARIANTS(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t knn2_merge_launch(const uint2 *partial, uint32_t nA, uint32_t n_chunks, uint64_t slot_stride,
+                              uint32_t rows_per_chunk, uint32_t row_base, int32_t *out_idx2,
+                              int32_t *out_dist2, int4 *out_packed, cudaStream_t stream) {
+    if (nA == 0) return cudaSuccess;
+    const int threads = 256;
+    knn2_merge_kernel<<<(nA + threads - 1) / threads, threads, 0, stream>>>(
+        partial, nA, n_chunks, slot_stride, rows_per_chunk, row_base, out_idx2, out_dist2, out_packed);
+    return cudaGetLastError();
+}
+
+cudaError_t knn2_merge_ranks_launch(const int4 *gathered, uint32_t nA, int world, int32_t *out_idx2,
+                                    int32_t *out_dist2, cudaStream_t stream) {
+    if (nA == 0) return cudaSuccess;
+    const int threads = 256;
+    knn2_merge_ranks_kernel<<<(nA + threads - 1) / threads, threads, 0, stream>>>(gathered, nA, world,
+                                                                                  out_idx2, out_dist2);
+    return cudaGetLastError();
+}
+
+}  // namespace hulo

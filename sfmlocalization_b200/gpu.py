@@ -1,0 +1,261 @@
+"""numpy front end over the C-ABI (test / benchmark harness; the product boundary is the
+C-ABI itself and the C++ hulo:: layer in csrc/host).  All arrays are host numpy arrays;
+device memory lives behind the opaque handles of libhulo_gpu.so."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import HuloError, check  # noqa: F401
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _rows(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.ndim != 2:
+        raise ValueError("descriptor rows must be a 2-D uint8 array")
+    return a
+
+
+class PinnedArray:
+    """A numpy view over page-locked host memory (hulo_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        self.lib = _lib.load()
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(shape)
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(self.lib.hulo_host_alloc(max(n, 1), C.byref(p)))
+        self._p = p
+        buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            self.lib.hulo_host_free(self._p)
+            self._p = None
+
+
+class DescriptorDb:
+    """Device-resident 64-byte descriptor rows with a segment (view / image) table."""
+
+    def __init__(self, gpu, rows, seg_offsets=None):
+        rows = _rows(rows)
+        self.gpu = gpu
+        self.lib = gpu.lib
+        h = C.c_void_p()
+        seg = None
+        n_seg = 0
+        if seg_offsets is not None:
+            seg = np.ascontiguousarray(seg_offsets, dtype=np.uint64)
+            n_seg = len(seg) - 1
+        stride = rows.shape[1] if rows.shape[0] else 64
+        check(self.lib.hulo_db_upload(gpu.h, _ptr(rows), rows.shape[0], stride, _ptr(seg), n_seg, C.byref(h)))
+        self.h = h
+
+    def __len__(self):
+        return int(self.lib.hulo_db_rows(self.h))
+
+    @property
+    def n_segments(self):
+        return int(self.lib.hulo_db_segments(self.h))
+
+    def update(self, rows):
+        rows = _rows(rows)
+        check(self.lib.hulo_db_update(self.gpu.h, self.h, _ptr(rows), rows.shape[0],
+                                      rows.shape[1] if rows.shape[0] else 64))
+
+    def download(self, first=0, n=None):
+        n = len(self) - first if n is None else n
+        out = np.empty((n, 64), np.uint8)
+        check(self.lib.hulo_db_download(self.gpu.h, self.h, first, n, _ptr(out)))
+        return out
+
+    def free(self):
+        if self.h is not None:
+            self.lib.hulo_db_free(self.h)
+            self.h = None
+
+
+class HuloGpu:
+    """One device context (hulo_gpu_create).  Raises HuloError when there is no B200."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        check(self.lib.hulo_gpu_create(device, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h is not None:
+            self.lib.hulo_gpu_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- bookkeeping
+    def db(self, rows, seg_offsets=None):
+        return DescriptorDb(self, rows, seg_offsets)
+
+    def timer_start(self):
+        check(self.lib.hulo_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        check(self.lib.hulo_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self):
+        check(self.lib.hulo_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.hulo_launch_count(self.h))
+
+    # -- K1
+    def knn2(self, A, B, fetch=True):
+        """A, B: DescriptorDb.  Returns (idx2, dist2) int32 nA x 2, or None when fetch=False."""
+        nA = len(A)
+        if not fetch:
+            check(self.lib.hulo_knn2(self.h, A.h, B.h, None, None))
+            return None
+        idx2 = np.empty((nA, 2), np.int32)
+        dist2 = np.empty((nA, 2), np.int32)
+        check(self.lib.hulo_knn2(self.h, A.h, B.h, _ptr(idx2), _ptr(dist2)))
+        return idx2, dist2
+
+    def knn2_fetch(self, nA):
+        idx2 = np.empty((nA, 2), np.int32)
+        dist2 = np.empty((nA, 2), np.int32)
+        check(self.lib.hulo_knn2_fetch(self.h, nA, _ptr(idx2), _ptr(dist2)))
+        return idx2, dist2
+
+    def knn2_host(self, A, B, idx2=None, dist2=None):
+        A, B = _rows(A), _rows(B)
+        nA = A.shape[0]
+        idx2 = np.empty((nA, 2), np.int32) if idx2 is None else idx2
+        dist2 = np.empty((nA, 2), np.int32) if dist2 is None else dist2
+        check(self.lib.hulo_knn2_host(self.h, _ptr(A), nA, A.shape[1] if nA else 64, _ptr(B), B.shape[0],
+                                      B.shape[1] if B.shape[0] else 64, _ptr(idx2), _ptr(dist2)))
+        return idx2, dist2
+
+    def knn2_sharded(self, A, B_shard, row_base, fetch=True):
+        nA = len(A)
+        if not fetch:
+            check(self.lib.hulo_knn2_sharded(self.h, A.h, B_shard.h, row_base, None, None))
+            return None
+        idx2 = np.empty((nA, 2), np.int32)
+        dist2 = np.empty((nA, 2), np.int32)
+        check(self.lib.hulo_knn2_sharded(self.h, A.h, B_shard.h, row_base, _ptr(idx2), _ptr(dist2)))
+        return idx2, dist2
+
+    def match_to_query(self, map_db, query, ratio, views=None, cap=None):
+        """hulo_match_to_query -> dict(view, i, j, d0, view_counts)."""
+        query = _rows(query)
+        nq = query.shape[0]
+        if views is not None:
+            views = np.ascontiguousarray(views, dtype=np.uint32)
+            n_views = len(views)
+        else:
+            n_views = map_db.n_segments
+        if cap is None:
+            cap = max(len(map_db), 1)
+        ov = np.empty(cap, np.uint32); oi = np.empty(cap, np.uint32)
+        oj = np.empty(cap, np.uint32); od = np.empty(cap, np.int32)
+        vc = np.zeros(max(n_views, 1), np.uint32)
+        n = C.c_size_t(0)
+        check(self.lib.hulo_match_to_query(self.h, map_db.h, _ptr(views), n_views, _ptr(query), nq,
+                                           query.shape[1] if nq else 64, ratio, _ptr(ov), _ptr(oi), _ptr(oj),
+                                           _ptr(od), cap, C.byref(n), _ptr(vc)))
+        k = n.value
+        return dict(view=ov[:k].copy(), i=oi[:k].copy(), j=oj[:k].copy(), d0=od[:k].copy(),
+                    view_counts=vc[:n_views].copy())
+
+    def match_pairs(self, db, pairs, ratio, flags=_lib.PAIR_REFERENCE, cap=None):
+        """hulo_match_pairs -> (pair_offsets uint64[P+1], i, j)."""
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        P = pairs.shape[0]
+        if cap is None:
+            cap = 1 << 20
+        while True:
+            off = np.zeros(P + 1, np.uint64)
+            oi = np.empty(max(cap, 1), np.uint32)
+            oj = np.empty(max(cap, 1), np.uint32)
+            n = C.c_size_t(0)
+            st = self.lib.hulo_match_pairs(self.h, db.h, _ptr(pairs), P, ratio, flags, _ptr(off), _ptr(oi),
+                                           _ptr(oj), cap, C.byref(n))
+            if st == _lib.ERR_CAPACITY:
+                cap = int(n.value)
+                continue
+            check(st)
+            return off, oi[:n.value].copy(), oj[:n.value].copy()
+
+    # -- K2
+    def score_resection(self, models, x2d, X3d, K, thr_px=-1.0):
+        models = np.ascontiguousarray(models, np.float64).reshape(-1, 12)
+        x2d = np.ascontiguousarray(x2d, np.float64); X3d = np.ascontiguousarray(X3d, np.float64)
+        K = np.ascontiguousarray(K, np.float64)
+        H, N = models.shape[0], x2d.shape[0]
+        nfa = np.empty(H, np.float32); kb = np.empty(H, np.int32)
+        ek = np.empty(H, np.float32); ni = np.empty(H, np.int32)
+        check(self.lib.hulo_score_resection(self.h, _ptr(models), H, _ptr(x2d), _ptr(X3d), N, _ptr(K), thr_px,
+                                            _ptr(nfa), _ptr(kb), _ptr(ek), _ptr(ni)))
+        return nfa, kb, ek, ni
+
+    def resection_residuals(self, models, x2d, X3d, K):
+        models = np.ascontiguousarray(models, np.float64).reshape(-1, 12)
+        x2d = np.ascontiguousarray(x2d, np.float64); X3d = np.ascontiguousarray(X3d, np.float64)
+        K = np.ascontiguousarray(K, np.float64)
+        H, N = models.shape[0], x2d.shape[0]
+        res = np.empty((H, N), np.float32)
+        check(self.lib.hulo_resection_residuals(self.h, _ptr(models), H, _ptr(x2d), _ptr(X3d), N, _ptr(K),
+                                                _ptr(res)))
+        return res
+
+    def p3p(self, triplets, x2d, X3d, K):
+        triplets = np.ascontiguousarray(triplets, np.uint32).reshape(-1, 3)
+        x2d = np.ascontiguousarray(x2d, np.float64); X3d = np.ascontiguousarray(X3d, np.float64)
+        K = np.ascontiguousarray(K, np.float64)
+        T = triplets.shape[0]
+        models = np.zeros((T, 4, 3, 4)); nm = np.zeros(T, np.int32)
+        check(self.lib.hulo_p3p(self.h, _ptr(triplets), T, _ptr(x2d), _ptr(X3d), x2d.shape[0], _ptr(K),
+                                _ptr(models), _ptr(nm)))
+        return models, nm
+
+    def resect_acransac(self, x2d, X3d, K, max_iter=4096, seed=1):
+        x2d = np.ascontiguousarray(x2d, np.float64); X3d = np.ascontiguousarray(X3d, np.float64)
+        K = np.ascontiguousarray(K, np.float64)
+        N = x2d.shape[0]
+        P = np.zeros((3, 4)); inl = np.empty(max(N, 1), np.int32)
+        n_inl = C.c_size_t(0); emax = C.c_double(0); found = C.c_int(0)
+        check(self.lib.hulo_resect_acransac(self.h, _ptr(x2d), _ptr(X3d), N, _ptr(K), max_iter, seed, _ptr(P),
+                                            _ptr(inl), C.byref(n_inl), C.byref(emax), C.byref(found)))
+        return dict(found=bool(found.value), P=P, inliers=inl[:n_inl.value].copy(), error_max=emax.value)
+
+    # -- multi GPU
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * 128)()
+        check(_lib.load().hulo_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(self.lib.hulo_comm_init(self.h, buf, rank, world))
+
+    def comm_barrier(self):
+        check(self.lib.hulo_comm_barrier(self.h))
+
+    def comm_max(self, value):
+        v = C.c_double(value)
+        check(self.lib.hulo_comm_max_f64(self.h, C.byref(v)))
+        return v.value

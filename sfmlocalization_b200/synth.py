@@ -1,0 +1,125 @@
+"""Seeded synthetic inputs for the hot path: random AKAZE/MLDB-like
+descriptor rows with planted true matches, and 3D maps with projected, noise-perturbed
+observations.  numpy only; shared by tests/ and bench.py so both sides see identical data."""
+import numpy as np
+
+ROW = 64
+DESC_BITS = 486
+# iPhone-6 intrinsics shipped with the reference:
+# VisionLocalizeServer/config/camera/iphone6-1920x1080/K.txt:1-3
+K_IPHONE6 = np.array([[1861.73, 0.0, 1043.21], [0.0, 1870.67, 644.65], [0.0, 0.0, 1.0]])
+IMAGE_WH = (1920, 1080)
+
+
+def random_rows(n, seed):
+    """n x 64 uint8: bits 0..485 i.i.d. Bernoulli(0.5), bits 486..511 zero (61-byte AKAZE
+    descriptor zero padded to 64, FileUtils.cpp:77-92)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    rows = rng.integers(0, 256, size=(n, ROW), dtype=np.uint8)
+    rows[:, 60] &= 0x3F
+    rows[:, 61:] = 0
+    return rows
+
+
+def plant_matches(A, B, seed, frac=0.3, flip_p=0.10):
+    """Overwrite a fraction of the rows of A with noisy copies of random rows of B
+    (each of the 486 bits flipped with probability flip_p).  Returns (rows, target) with
+    target[i] = planted row of B or -1."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nA = A.shape[0]
+    target = np.full(nA, -1, np.int64)
+    if nA == 0 or B.shape[0] == 0:
+        return A, target
+    sel = rng.random(nA) < frac
+    idx = np.nonzero(sel)[0]
+    tgt = rng.integers(0, B.shape[0], size=len(idx))
+    target[idx] = tgt
+    rows = B[tgt].copy()
+    flips = rng.random((len(idx), ROW * 8)) < flip_p
+    flips[:, DESC_BITS:] = False
+    rows ^= np.packbits(flips, axis=1, bitorder="little")
+    A = A.copy()
+    A[idx] = rows
+    return A, target
+
+
+def tie_heavy_rows(n, seed, varying_bits=12):
+    """Rows in which only `varying_bits` bits differ, so distances tie constantly."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    rows = np.zeros((n, ROW), np.uint8)
+    bits = rng.integers(0, 2, size=(n, varying_bits), dtype=np.uint8)
+    rows[:, :2] = np.packbits(np.pad(bits, ((0, 0), (0, 16 - varying_bits))), axis=1, bitorder="little")
+    return rows
+
+
+def descriptor_sets(nA, nB, seed, frac=0.3):
+    """The standard benchmark pair: database B, searchers A with planted matches."""
+    B = random_rows(nB, seed)
+    A = random_rows(nA, seed + 7919)
+    A, target = plant_matches(A, B, seed + 104729, frac=frac)
+    return A, B, target
+
+
+def image_collection(n_images, rows_per_image, seed, overlap=0.3, jitter=0):
+    """Reconstruction-style collection: image k+1 shares `overlap` of its rows (noisy) with
+    image k.  Returns (rows, seg_offsets)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    counts = [rows_per_image + (int(rng.integers(-jitter, jitter + 1)) if jitter else 0)
+              for _ in range(n_images)]
+    segs = []
+    prev = None
+    for k, c in enumerate(counts):
+        rows = random_rows(c, seed * 1000 + k)
+        if prev is not None and c > 0 and prev.shape[0] > 0:
+            rows, _ = plant_matches(rows, prev, seed * 1000 + 500 + k, frac=overlap)
+        segs.append(rows)
+        prev = rows
+    off = np.zeros(n_images + 1, np.uint64)
+    off[1:] = np.cumsum(counts)
+    return (np.concatenate(segs, axis=0) if segs else np.zeros((0, ROW), np.uint8)), off
+
+
+def rodrigues(rv):
+    th = np.linalg.norm(rv)
+    if th < 1e-12:
+        return np.eye(3)
+    k = rv / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * (Kx @ Kx)
+
+
+def resection_scene(N, seed, outlier_frac=0.5, noise_px=0.7, K=K_IPHONE6):
+    """N 3D points in a 10 x 6 x 10 m box 4..14 m in front of a random camera (rotation <= 30
+    deg), projected with K, N(0, noise_px^2) pixel noise, a fraction replaced by uniform
+    outliers.  Returns dict(x2d N x 2, X3d N x 3, R, t, inlier_mask, K)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    rv = rng.normal(size=3)
+    rv *= np.deg2rad(rng.uniform(0, 30)) / np.linalg.norm(rv)
+    R = rodrigues(rv)
+    t = rng.normal(size=3) * 0.5
+    Xc = np.stack([rng.uniform(-5, 5, N), rng.uniform(-3, 3, N), rng.uniform(4, 14, N)], axis=1)
+    # keep the points inside the image
+    for _ in range(20):
+        uvw = Xc @ K.T
+        uv = uvw[:, :2] / uvw[:, 2:]
+        bad = (uv[:, 0] < 0) | (uv[:, 0] >= IMAGE_WH[0]) | (uv[:, 1] < 0) | (uv[:, 1] >= IMAGE_WH[1])
+        if not bad.any():
+            break
+        nb = int(bad.sum())
+        Xc[bad] = np.stack([rng.uniform(-5, 5, nb), rng.uniform(-3, 3, nb), rng.uniform(4, 14, nb)], axis=1)
+    X = (Xc - t) @ R          # X_world = R^T (X_cam - t)
+    uvw = Xc @ K.T
+    x = uvw[:, :2] / uvw[:, 2:] + rng.normal(scale=noise_px, size=(N, 2))
+    out = rng.random(N) < outlier_frac
+    n_out = int(out.sum())
+    x[out] = np.stack([rng.uniform(0, IMAGE_WH[0], n_out), rng.uniform(0, IMAGE_WH[1], n_out)], axis=1)
+    return dict(x2d=x, X3d=X, R=R, t=t, inlier_mask=~out, K=K.copy())
+
+
+def sample_triplets(N, T, seed):
+    """T triplets of distinct correspondence indices."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tri = np.empty((T, 3), np.uint32)
+    for k in range(T):
+        tri[k] = rng.choice(N, size=3, replace=False)
+    return tri

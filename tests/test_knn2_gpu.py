@@ -1,0 +1,108 @@
+"""GPU parity suite for K1 (exact Hamming 2-NN) through the C-ABI: bit-exact against the CPU
+oracle and the committed OpenCV golden vectors."""
+import numpy as np
+import pytest
+
+from sfmlocalization_b200 import synth
+
+pytestmark = pytest.mark.gpu
+INT_MAX = 2**31 - 1
+
+
+def run_gpu(gpu, A, B):
+    return gpu.knn2_host(A, B)
+
+
+@pytest.mark.parametrize("name", ["tie", "pl", "w61", "dup"])
+def test_golden_vectors(gpu, golden, name):
+    idx, dist = run_gpu(gpu, golden[name + "_A"], golden[name + "_B"])
+    assert np.array_equal(idx, golden[name + "_idx"])
+    assert np.array_equal(dist, golden[name + "_dist"])
+
+
+@pytest.mark.parametrize("nA,nB", [(1, 1), (1, 2), (5, 0), (5, 1), (5, 2), (5, 3), (0, 10), (33, 65), (257, 63),
+                                   (2049, 129), (300, 4097), (4096, 1000), (1000, 20000)])
+def test_shapes_vs_oracle(gpu, orc, nA, nB):
+    A, B, _ = synth.descriptor_sets(nA, nB, 100 + nA + nB)
+    idx, dist = run_gpu(gpu, A, B)
+    ri, rd = orc.knn2(A, B)
+    assert np.array_equal(dist, rd)
+    assert np.array_equal(idx, ri)
+
+
+def test_tie_heavy_large(gpu, orc):
+    """Distances tie constantly; every merge level must keep (distance, index) order."""
+    B = synth.tie_heavy_rows(50000, 7, varying_bits=10)
+    A = synth.tie_heavy_rows(3000, 8, varying_bits=10)
+    idx, dist = run_gpu(gpu, A, B)
+    ri, rd = orc.knn2(A, B)
+    assert np.array_equal(dist, rd) and np.array_equal(idx, ri)
+    assert (dist[:, 0] == dist[:, 1]).mean() > 0.5
+
+
+def test_all_identical_rows(gpu):
+    B = np.tile(synth.random_rows(1, 3), (5000, 1))
+    A = B[:100].copy()
+    idx, dist = run_gpu(gpu, A, B)
+    assert (dist == 0).all() and (idx[:, 0] == 0).all() and (idx[:, 1] == 1).all()
+
+
+def test_full_distance_512(gpu):
+    """Rows that differ in all 512 bits (not producible by AKAZE, but the key packing must hold)."""
+    B = np.zeros((10, 64), np.uint8)
+    A = np.full((3, 64), 0xFF, np.uint8)
+    idx, dist = run_gpu(gpu, A, B)
+    assert (dist == 512).all() and (idx[:, 0] == 0).all() and (idx[:, 1] == 1).all()
+
+
+def test_device_resident_tables(gpu, orc):
+    A, B, target = synth.descriptor_sets(2500, 30000, 77)
+    dA, dB = gpu.db(A), gpu.db(B)
+    try:
+        idx, dist = gpu.knn2(dA, dB)
+        assert gpu.knn2(dA, dB, fetch=False) is None
+        idx_b, dist_b = gpu.knn2_fetch(len(dA))
+    finally:
+        dA.free(); dB.free()
+    ri, rd = orc.knn2(A, B)
+    assert np.array_equal(idx, ri) and np.array_equal(dist, rd)
+    assert np.array_equal(idx_b, ri) and np.array_equal(dist_b, rd)
+    hit = target >= 0
+    assert np.array_equal(idx[hit, 0], target[hit])
+
+
+def test_planted_property_at_scale(gpu):
+    """Full-size property check (no oracle): every planted row finds its source as first
+    neighbour at the planted distance, and d0 <= d1, on a 4096 x 2M problem."""
+    nA, nB = 4096, 2_000_000
+    B = synth.random_rows(nB, 5)
+    A = synth.random_rows(nA, 6)
+    A, target = synth.plant_matches(A, B, 9, frac=0.3)
+    idx, dist = run_gpu(gpu, A, B)
+    hit = np.nonzero(target >= 0)[0]
+    assert np.array_equal(idx[hit, 0], target[hit])
+    x = np.bitwise_xor(A[hit], B[target[hit]])
+    d_true = np.unpackbits(x, axis=1).sum(axis=1)
+    assert np.array_equal(dist[hit, 0], d_true)
+    assert (dist[:, 0] <= dist[:, 1]).all()
+    assert (idx >= 0).all() and (idx < nB).all() and (idx[:, 0] != idx[:, 1]).all()
+    # spot-check the reported second neighbours' distances
+    rows = np.arange(0, nA, 97)
+    x = np.bitwise_xor(A[rows], B[idx[rows, 1]])
+    assert np.array_equal(np.unpackbits(x, axis=1).sum(axis=1), dist[rows, 1])
+
+
+def test_split_database_merge_is_associative(gpu, orc):
+    """Searching two halves and merging on (distance, global index) equals one search: the
+    property the row-sharded multi-GPU mode relies on."""
+    A, B, _ = synth.descriptor_sets(500, 9000, 55)
+    i_full, d_full = run_gpu(gpu, A, B)
+    cut = 4321
+    i1, d1 = run_gpu(gpu, A, B[:cut])
+    i2, d2 = run_gpu(gpu, A, B[cut:])
+    i2 = i2 + cut
+    cand_d = np.concatenate([d1, d2], axis=1).astype(np.int64)
+    cand_i = np.concatenate([i1, i2], axis=1).astype(np.int64)
+    order = np.lexsort((cand_i, cand_d), axis=1)[:, :2]
+    md = np.take_along_axis(cand_d, order, axis=1); mi = np.take_along_axis(cand_i, order, axis=1)
+    assert np.array_equal(md, d_full) and np.array_equal(mi, i_full)

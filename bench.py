@@ -150,12 +150,13 @@ def cpu_baseline_sample(A, shard, budget_s=12.0):
     from oracle import oracle as orc
     orc.build()
     threads = orc.num_threads()
-    nq = min(A.shape[0], 8 * max(1, threads))
+    grp = 8 * max(1, threads)                       # the port walks 8 searcher rows per thread
     nb_probe = min(shard.shape[0], 200_000)
     t0 = time.perf_counter()
-    orc.knn2(A[:nq], shard[:nb_probe])
-    rate = nq * nb_probe / max(time.perf_counter() - t0, 1e-6)          # dist/s
-    nb = int(min(shard.shape[0], max(nb_probe, rate * budget_s / nq)))
+    orc.knn2(A[:grp], shard[:nb_probe])
+    rate = grp * nb_probe / max(time.perf_counter() - t0, 1e-6)          # dist/s
+    nb = int(min(shard.shape[0], 2_000_000))
+    nq = int(min(A.shape[0], max(grp, (rate * budget_s / nb) // grp * grp)))
     t0 = time.perf_counter()
     idx, dist = orc.knn2(A[:nq], shard[:nb])
     dt = time.perf_counter() - t0

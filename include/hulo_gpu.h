@@ -191,6 +191,12 @@ int hulo_comm_max_f64(hulo_gpu *h, double *value);
 int hulo_knn2_sharded(hulo_gpu *h, const hulo_db *A, const hulo_db *B_shard, uint64_t row_base,
                       int32_t *idx2, int32_t *dist2);
 
+/* The merge step on its own, for hosts that move the candidates themselves (another
+ * transport, several nodes): cand holds `world` lists of nA records {d0, i0, d1, i1} (int32,
+ * global indices, HULO_IDX_NONE / HULO_DIST_NONE for a missing neighbour), list after list.
+ * Writes the (distance, index)-ordered best two per searcher row. */
+int hulo_merge_top2(hulo_gpu *h, const int32_t *cand, size_t nA, int world, int32_t *idx2, int32_t *dist2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,22 +45,29 @@ static KnnConfig choose_config(const hulo_gpu *h, size_t nA) {
 }
 
 // Split nB database rows into chunks so that tiles x chunks fills the persistent grid evenly.
+// Items are handed out dynamically, so the makespan is (items per CTA, rounded up) x (cost of one
+// item); the cost of an item is its chunk rows plus a fixed per-item overhead (loading the
+// searcher tile into registers, writing its keys), expressed in equivalent rows.
 static void plan_chunks(uint32_t n_tiles, size_t nB, int n_ctas, uint32_t *n_chunks, uint32_t *rows_per_chunk) {
     if (nB == 0) { *n_chunks = 0; *rows_per_chunk = 1; return; }
-    const uint32_t min_rows = 256;
-    uint32_t c_min = (uint32_t)((nB + kMaxChunkRows - 1) / kMaxChunkRows);
+    if (n_tiles == 0) n_tiles = 1;
+    const uint64_t overhead_rows = 24;
+    const uint32_t min_rows = 128;
+    const uint32_t c_min = (uint32_t)((nB + kMaxChunkRows - 1) / kMaxChunkRows);
     uint32_t c_max = (uint32_t)std::max<size_t>(c_min, nB / min_rows);
-    c_max = std::min<uint32_t>(c_max, std::max<uint32_t>(c_min, (uint32_t)(64 * n_ctas) / std::max(1u, n_tiles) + 1));
+    // no point in more than ~16 items per CTA
+    c_max = std::min<uint32_t>(c_max, std::max<uint32_t>(c_min, (uint32_t)((16ull * n_ctas + n_tiles - 1) / n_tiles)));
     uint32_t best_c = c_min;
-    double best_eff = -1.0;
+    uint64_t best_cost = ~0ull;
     for (uint32_t c = c_min; c <= c_max; ++c) {
-        const uint64_t items = (uint64_t)n_tiles * c;
-        const uint64_t waves = (items + n_ctas - 1) / n_ctas;
-        const double eff = (double)items / (double)(waves * n_ctas);
-        if (eff > best_eff + 1e-9) { best_eff = eff; best_c = c; }
-        if (eff >= 0.97) { best_c = c; break; }
+        const uint64_t rpc = (nB + c - 1) / c;
+        const uint64_t chunks = (nB + rpc - 1) / rpc;
+        const uint64_t items = (uint64_t)n_tiles * chunks;
+        const uint64_t per_cta = (items + n_ctas - 1) / n_ctas;
+        const uint64_t cost = per_cta * (rpc + overhead_rows);
+        if (cost < best_cost) { best_cost = cost; best_c = c; }
     }
-    uint32_t rpc = (uint32_t)((nB + best_c - 1) / best_c);
+    const uint32_t rpc = (uint32_t)((nB + best_c - 1) / best_c);
     *rows_per_chunk = rpc;
     *n_chunks = (uint32_t)((nB + rpc - 1) / rpc);
 }

@@ -2,6 +2,7 @@
 // top-2 per searcher row and the candidates (16 bytes per row per rank) are merged after a
 // single ncclAllGather over NVLink.  NCCL is bound lazily with dlopen so that single-GPU use
 // and the CPU-side symbol check do not need it.
+#include <algorithm>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -144,6 +145,22 @@ int hulo_knn2_sharded(hulo_gpu *h, const hulo_db *A, const hulo_db *B_shard, uin
     }
     if (idx2 || dist2) return hulo_knn2_fetch(h, nA, idx2, dist2);
     return HULO_OK;
+}
+
+int hulo_merge_top2(hulo_gpu *h, const int32_t *cand, size_t nA, int world, int32_t *idx2, int32_t *dist2) {
+    HULO_ARG(h != nullptr && world >= 1, "bad argument");
+    HULO_ARG(nA == 0 || (cand != nullptr && idx2 != nullptr && dist2 != nullptr), "null argument");
+    HULO_CUDA(cudaSetDevice(h->device));
+    HULO_CUDA(h->knn_idx.reserve(std::max<size_t>(nA, 1) * 2 * sizeof(int32_t)));
+    HULO_CUDA(h->knn_dist.reserve(std::max<size_t>(nA, 1) * 2 * sizeof(int32_t)));
+    h->last_nA = nA;
+    if (nA == 0) return HULO_OK;
+    HULO_CUDA(h->gathered.reserve((size_t)world * nA * sizeof(int4)));
+    HULO_CUDA(cudaMemcpyAsync(h->gathered.ptr, cand, (size_t)world * nA * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    HULO_CUDA(knn2_merge_ranks_launch(h->gathered.as<int4>(), (uint32_t)nA, world, h->knn_idx.as<int32_t>(),
+                                      h->knn_dist.as<int32_t>(), h->stream));
+    h->launches++;
+    return hulo_knn2_fetch(h, nA, idx2, dist2);
 }
 
 }  // extern "C"

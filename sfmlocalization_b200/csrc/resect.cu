@@ -1,0 +1,691 @@
+// resect.cu -- K2: batched scoring of resection-RANSAC hypotheses, the P3P minimal solver,
+// and the batched AC-RANSAC driver, sm_100a.
+//
+// Stands behind openMVG::sfm::SfM_Localizer::Localize as the reference calls it
+// (VisionLocalizeServer/src/LocalizeEngine.cc:503-531, OpenMVGLocalization_AKAZE/src/
+// localization.cpp:479-509, OpenMVG_BA/src/adjust_sfm_data.cpp:109-137): AC-RANSAC over the
+// P3P kernel, K^-1-normalised squared reprojection residuals, a-contrario NFA, max 4096
+// iterations.  OpenMVG 1.1 is third-party and not vendored; SURVEY.md appendix B records the
+// published algorithm this follows.
+//
+// One thread block scores one hypothesis against all N correspondences:
+//   projection [R|t] X and the subtraction from the observation in fp64 (12 DFMA per point:
+//   keeps the residual within 1e-4 px at f ~ 1860 px, which plain fp32 cannot guarantee),
+//   squared residual stored as fp32, ascending bitonic sort in shared memory (the NFA needs the
+//   order statistics, so a histogram would not be exact), then the NFA scan
+//   nfa_k = loge0 + (logalpha0 + log10(e_k + FLT_EPSILON)) (k-3) + logC(N,k) + logC(k,3)
+//   with a block-wide lexicographic (nfa, k) minimum so the first minimum wins like the
+//   sequential scan.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "context.cuh"
+
+namespace hulo {
+namespace {
+
+constexpr int kScoreThreads = 256;
+constexpr uint32_t kMaxPoints = 32768;
+
+struct Mat3 { double m[9]; };
+
+// ------------------------------------------------------------------ device math
+__device__ __forceinline__ void proj_residual(const double *__restrict__ M, const double *__restrict__ X,
+                                              const double *__restrict__ x, double &dx, double &dy) {
+    const double u = fma(M[0], X[0], fma(M[1], X[1], fma(M[2], X[2], M[3])));
+    const double v = fma(M[4], X[0], fma(M[5], X[1], fma(M[6], X[2], M[7])));
+    const double w = fma(M[8], X[0], fma(M[9], X[1], fma(M[10], X[2], M[11])));
+    dx = u / w - x[0];
+    dy = v / w - x[1];
+}
+
+struct NfaMin { double nfa; int k; };
+__device__ __forceinline__ NfaMin nfa_min(NfaMin a, NfaMin b) {
+    if (b.nfa < a.nfa || (b.nfa == a.nfa && b.k < a.k)) return b;
+    return a;
+}
+
+// One CTA per hypothesis.  smem: npad floats.
+__global__ void __launch_bounds__(kScoreThreads) score_kernel(
+    const double *__restrict__ models, uint32_t H, const double *__restrict__ x2dn,
+    const double *__restrict__ X3d, uint32_t N, uint32_t npad, const float *__restrict__ logc_n,
+    const float *__restrict__ logc_k, double loge0, double logalpha0, float thr2, double *__restrict__ out_nfa,
+    int32_t *__restrict__ out_k, float *__restrict__ out_errk, int32_t *__restrict__ out_ninl) {
+    extern __shared__ float s_e[];
+    __shared__ double s_M[12];
+    __shared__ NfaMin s_red[kScoreThreads / 32];
+    __shared__ int s_cnt[kScoreThreads / 32];
+    const uint32_t h = blockIdx.x;
+    if (h >= H) return;
+    const int tid = threadIdx.x;
+    if (tid < 12) s_M[tid] = models[(size_t)h * 12 + tid];
+    __syncthreads();
+    // a solver slot without a model is marked by a NaN in its first entry
+    if (!(s_M[0] == s_M[0]) || N < 4) {
+        if (tid == 0) {
+            out_nfa[h] = INFINITY;
+            if (out_k) out_k[h] = 3;
+            if (out_errk) out_errk[h] = INFINITY;
+            if (out_ninl) out_ninl[h] = 0;
+        }
+        return;
+    }
+    int cnt = 0;
+    for (uint32_t i = tid; i < npad; i += kScoreThreads) {
+        float e = INFINITY;
+        if (i < N) {
+            double dx, dy;
+            proj_residual(s_M, X3d + 3 * (size_t)i, x2dn + 2 * (size_t)i, dx, dy);
+            const float fx = (float)dx, fy = (float)dy;
+            e = fmaf(fx, fx, fy * fy);
+            if (!(e == e)) e = INFINITY;          // NaN residual (point on the principal plane) sorts last
+            if (thr2 >= 0.0f && e <= thr2) ++cnt;
+        }
+        s_e[i] = e;
+    }
+    __syncthreads();
+    // bitonic sort, ascending
+    for (uint32_t k = 2; k <= npad; k <<= 1) {
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = tid; t < (npad >> 1); t += kScoreThreads) {
+                const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const uint32_t p = i | j;
+                const float a = s_e[i], b = s_e[p];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) { s_e[i] = b; s_e[p] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    // NFA scan over k = 4 .. N
+    NfaMin best{INFINITY, 3};
+    for (uint32_t k = 4 + tid; k <= N; k += kScoreThreads) {
+        const float e = s_e[k - 1];
+        if (e == INFINITY) continue;
+        const double logalpha = logalpha0 + log10((double)e + (double)FLT_EPSILON);
+        const double nfa = loge0 + logalpha * (double)(k - 3) + (double)logc_n[k] + (double)logc_k[k];
+        if (nfa < best.nfa) { best.nfa = nfa; best.k = (int)k; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        NfaMin other;
+        other.nfa = __shfl_xor_sync(0xffffffffu, best.nfa, o);
+        other.k = __shfl_xor_sync(0xffffffffu, best.k, o);
+        best = nfa_min(best, other);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((tid & 31) == 0) { s_red[tid >> 5] = best; s_cnt[tid >> 5] = cnt; }
+    __syncthreads();
+    if (tid == 0) {
+        NfaMin b = s_red[0];
+        int c = s_cnt[0];
+        for (int w = 1; w < kScoreThreads / 32; ++w) { b = nfa_min(b, s_red[w]); c += s_cnt[w]; }
+        out_nfa[h] = b.nfa;
+        if (out_k) out_k[h] = b.k;
+        if (out_errk) out_errk[h] = b.k >= 1 ? s_e[b.k - 1] : INFINITY;
+        if (out_ninl) out_ninl[h] = c;
+    }
+}
+
+// residuals in pixels (sqrt(e) * fx), H x N, for the parity test of the projection arithmetic
+__global__ void residual_kernel(const double *__restrict__ models, uint32_t H, const double *__restrict__ x2dn,
+                                const double *__restrict__ X3d, uint32_t N, float fx, float *__restrict__ res) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t h = blockIdx.y;
+    if (i >= N || h >= H) return;
+    double dx, dy;
+    proj_residual(models + (size_t)h * 12, X3d + 3 * (size_t)i, x2dn + 2 * (size_t)i, dx, dy);
+    const float fxx = (float)dx, fyy = (float)dy;
+    res[(size_t)h * N + i] = sqrtf(fmaf(fxx, fxx, fyy * fyy)) * fx;
+}
+
+// ------------------------------------------------------------------ P3P (Kneip, CVPR 2011)
+struct Cplx { double re, im; };
+__device__ __forceinline__ Cplx c_add(Cplx a, Cplx b) { return {a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ Cplx c_sub(Cplx a, Cplx b) { return {a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ Cplx c_mul(Cplx a, Cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ Cplx c_scale(Cplx a, double s) { return {a.re * s, a.im * s}; }
+__device__ __forceinline__ Cplx c_div(Cplx a, Cplx b) {
+    const double d = b.re * b.re + b.im * b.im;
+    return {(a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d};
+}
+__device__ __forceinline__ Cplx c_sqrt(Cplx z) {   // principal branch
+    const double r = hypot(z.re, z.im);
+    if (r == 0.0) return {0.0, 0.0};
+    double a = sqrt(0.5 * (r + fabs(z.re)));
+    double b = 0.5 * z.im / a;
+    if (z.re >= 0.0) return {a, b};
+    return {fabs(b), copysign(a, z.im)};
+}
+__device__ __forceinline__ Cplx c_cbrt(Cplx z) {   // principal value of z^(1/3)
+    const double r = hypot(z.re, z.im);
+    if (r == 0.0) return {0.0, 0.0};
+    const double th = atan2(z.im, z.re) / 3.0;
+    const double m = cbrt(r);
+    double s, c;
+    sincos(th, &s, &c);
+    return {m * c, m * s};
+}
+
+__device__ void solve_quartic(const double f[5], double roots[4]) {
+    const double A = f[0], B = f[1], C = f[2], D = f[3], E = f[4];
+    const double A2 = A * A, B2 = B * B, A3 = A2 * A, B3 = B2 * B, A4 = A3 * A, B4 = B3 * B;
+    const double alpha = -3.0 * B2 / (8.0 * A2) + C / A;
+    const double beta = B3 / (8.0 * A3) - B * C / (2.0 * A2) + D / A;
+    const double gamma = -3.0 * B4 / (256.0 * A4) + B2 * C / (16.0 * A3) - B * D / (4.0 * A2) + E / A;
+    const double alpha2 = alpha * alpha, alpha3 = alpha2 * alpha;
+    const Cplx P{-alpha2 / 12.0 - gamma, 0.0};
+    const Cplx Q{-alpha3 / 108.0 + alpha * gamma / 3.0 - beta * beta / 8.0, 0.0};
+    const Cplx disc = c_add(c_scale(c_mul(Q, Q), 0.25), c_scale(c_mul(c_mul(P, P), P), 1.0 / 27.0));
+    const Cplx R = c_add(c_scale(Q, -0.5), c_sqrt(disc));
+    const Cplx U = c_cbrt(R);
+    Cplx y;
+    if (U.re == 0.0) y = c_sub(Cplx{-5.0 * alpha / 6.0, 0.0}, c_cbrt(Q));
+    else y = c_add(c_sub(Cplx{-5.0 * alpha / 6.0, 0.0}, c_div(P, c_scale(U, 3.0))), U);
+    const Cplx w = c_sqrt(c_add(Cplx{alpha, 0.0}, c_scale(y, 2.0)));
+    const Cplx bw = c_div(Cplx{2.0 * beta, 0.0}, w);
+    const Cplx base = c_add(Cplx{3.0 * alpha, 0.0}, c_scale(y, 2.0));
+    const Cplx s1 = c_sqrt(c_scale(c_add(base, bw), -1.0));
+    const Cplx s2 = c_sqrt(c_scale(c_sub(base, bw), -1.0));
+    const double sh = -B / (4.0 * A);
+    roots[0] = sh + 0.5 * (w.re + s1.re);
+    roots[1] = sh + 0.5 * (w.re - s1.re);
+    roots[2] = sh + 0.5 * (-w.re + s2.re);
+    roots[3] = sh + 0.5 * (-w.re - s2.re);
+}
+
+__device__ __forceinline__ void cross3(const double *a, const double *b, double *o) {
+    const double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z;
+}
+__device__ __forceinline__ double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void norm3(double *a) {
+    const double n = sqrt(dot3(a, a));
+    a[0] /= n; a[1] /= n; a[2] /= n;
+}
+
+// One thread per sample triplet.  models: T x 4 x 12; an absent model has NaN in entry 0.
+__global__ void p3p_kernel(const uint32_t *__restrict__ triplets, uint32_t T, const double *__restrict__ x2dn,
+                           const double *__restrict__ X3d, double *__restrict__ models,
+                           int32_t *__restrict__ n_models) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double *out = models + (size_t)t * 48;
+    for (int m = 0; m < 4; ++m) out[12 * m] = NAN;
+    double P1[3], P2[3], P3[3], f1[3], f2[3], f3[3];
+    {
+        const uint32_t i0 = triplets[3 * t], i1 = triplets[3 * t + 1], i2 = triplets[3 * t + 2];
+        for (int c = 0; c < 3; ++c) { P1[c] = X3d[3 * (size_t)i0 + c]; P2[c] = X3d[3 * (size_t)i1 + c]; P3[c] = X3d[3 * (size_t)i2 + c]; }
+        f1[0] = x2dn[2 * (size_t)i0]; f1[1] = x2dn[2 * (size_t)i0 + 1]; f1[2] = 1.0;
+        f2[0] = x2dn[2 * (size_t)i1]; f2[1] = x2dn[2 * (size_t)i1 + 1]; f2[2] = 1.0;
+        f3[0] = x2dn[2 * (size_t)i2]; f3[1] = x2dn[2 * (size_t)i2 + 1]; f3[2] = 1.0;
+        norm3(f1); norm3(f2); norm3(f3);
+    }
+    int n_out = 0;
+    double d1[3], d2[3], cr[3];
+    for (int c = 0; c < 3; ++c) { d1[c] = P2[c] - P1[c]; d2[c] = P3[c] - P1[c]; }
+    cross3(d1, d2, cr);
+    if (dot3(cr, cr) == 0.0) { n_models[t] = 0; return; }   // collinear world points
+
+    double e1[3], e2[3], e3[3], f3t[3];
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int c = 0; c < 3; ++c) e1[c] = f1[c];
+        cross3(f1, f2, e3); norm3(e3);
+        cross3(e3, e1, e2);
+        f3t[0] = dot3(e1, f3); f3t[1] = dot3(e2, f3); f3t[2] = dot3(e3, f3);
+        if (pass == 0 && f3t[2] > 0.0) {
+            for (int c = 0; c < 3; ++c) {
+                double tmp = f1[c]; f1[c] = f2[c]; f2[c] = tmp;
+                tmp = P1[c]; P1[c] = P2[c]; P2[c] = tmp;
+            }
+            continue;
+        }
+        break;
+    }
+    double n1[3], n2[3], n3[3], dd[3];
+    for (int c = 0; c < 3; ++c) { n1[c] = P2[c] - P1[c]; dd[c] = P3[c] - P1[c]; }
+    const double d12 = sqrt(dot3(n1, n1));
+    norm3(n1);
+    cross3(n1, dd, n3); norm3(n3);
+    cross3(n3, n1, n2);
+    const double p1 = dot3(n1, dd), p2 = dot3(n2, dd);
+    const double phi1 = f3t[0] / f3t[2], phi2 = f3t[1] / f3t[2];
+    const double cosb = dot3(f1, f2);
+    double b = 1.0 / (1.0 - cosb * cosb) - 1.0;
+    b = cosb < 0.0 ? -sqrt(b) : sqrt(b);
+
+    const double phi1_2 = phi1 * phi1, phi2_2 = phi2 * phi2;
+    const double p1_2 = p1 * p1, p1_3 = p1_2 * p1, p1_4 = p1_3 * p1;
+    const double p2_2 = p2 * p2, p2_3 = p2_2 * p2, p2_4 = p2_3 * p2;
+    const double d12_2 = d12 * d12, b_2 = b * b;
+    double fac[5];
+    fac[0] = -phi2_2 * p2_4 - p2_4 * phi1_2 - p2_4;
+    fac[1] = 2.0 * p2_3 * d12 * b + 2.0 * phi2_2 * p2_3 * d12 * b - 2.0 * phi2 * p2_3 * phi1 * d12;
+    fac[2] = -phi2_2 * p2_2 * p1_2 - phi2_2 * p2_2 * d12_2 * b_2 - phi2_2 * p2_2 * d12_2 + phi2_2 * p2_4 +
+             p2_4 * phi1_2 + 2.0 * p1 * p2_2 * d12 + 2.0 * phi1 * phi2 * p1 * p2_2 * d12 * b -
+             p2_2 * p1_2 * phi1_2 + 2.0 * p1 * p2_2 * phi2_2 * d12 - p2_2 * d12_2 * b_2 - 2.0 * p1_2 * p2_2;
+    fac[3] = 2.0 * p1_2 * p2 * d12 * b + 2.0 * phi2 * p2_3 * phi1 * d12 - 2.0 * phi2_2 * p2_3 * d12 * b -
+             2.0 * p1 * p2 * d12_2 * b;
+    fac[4] = -2.0 * phi2 * p2_2 * phi1 * p1 * d12 * b + phi2_2 * p2_2 * d12_2 + 2.0 * p1_3 * d12 - p1_2 * d12_2 +
+             phi2_2 * p2_2 * p1_2 - p1_4 - 2.0 * phi2_2 * p2_2 * p1 * d12 + p2_2 * phi1_2 * p1_2 +
+             phi2_2 * p2_2 * d12_2 * b_2;
+    double roots[4];
+    solve_quartic(fac, roots);
+
+    for (int i = 0; i < 4; ++i) {
+        const double cot_alpha = (-phi1 * p1 / phi2 - roots[i] * p2 + d12 * b) / (-phi1 * roots[i] * p2 / phi2 + p1 - d12);
+        const double cos_theta = roots[i];
+        const double sin_theta = sqrt(1.0 - roots[i] * roots[i]);
+        const double sin_alpha = sqrt(1.0 / (cot_alpha * cot_alpha + 1.0));
+        double cos_alpha = sqrt(1.0 - sin_alpha * sin_alpha);
+        if (cot_alpha < 0.0) cos_alpha = -cos_alpha;
+        const double sc = d12 * (sin_alpha * b + cos_alpha);
+        const double Cn[3] = {cos_alpha * sc, cos_theta * sin_alpha * sc, sin_theta * sin_alpha * sc};
+        double C[3];
+        for (int c = 0; c < 3; ++c) C[c] = P1[c] + n1[c] * Cn[0] + n2[c] * Cn[1] + n3[c] * Cn[2];
+        // Rr (rows), camera-to-world rotation Rcw = N^T Rr^T T, model rotation = Rcw^T = T^T Rr N
+        const double Rr[9] = {-cos_alpha, -sin_alpha * cos_theta, -sin_alpha * sin_theta,
+                              sin_alpha,  -cos_alpha * cos_theta, -cos_alpha * sin_theta,
+                              0.0,        -sin_theta,             cos_theta};
+        const double *Nrow[3] = {n1, n2, n3};
+        const double *Trow[3] = {e1, e2, e3};
+        double RrN[9];   // Rr * N
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                RrN[3 * r + c] = Rr[3 * r] * Nrow[0][c] + Rr[3 * r + 1] * Nrow[1][c] + Rr[3 * r + 2] * Nrow[2][c];
+        double M[12];
+        bool ok = true;
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c)   // (T^T)[r][k] = Trow[k][r]
+                M[4 * r + c] = Trow[0][r] * RrN[c] + Trow[1][r] * RrN[3 + c] + Trow[2][r] * RrN[6 + c];
+            M[4 * r + 3] = -(M[4 * r] * C[0] + M[4 * r + 1] * C[1] + M[4 * r + 2] * C[2]);
+        }
+        for (int k = 0; k < 12; ++k) ok = ok && isfinite(M[k]);
+        if (!ok) continue;
+        for (int k = 0; k < 12; ++k) out[12 * n_out + k] = M[k];
+        ++n_out;
+    }
+    n_models[t] = n_out;
+}
+
+// ------------------------------------------------------------------ host helpers
+void k_inverse(const double *K, double *Ki) {
+    const double fx = K[0], s = K[1], cx = K[2], fy = K[4], cy = K[5], w = K[8];
+    Ki[0] = 1.0 / fx; Ki[1] = -s / (fx * fy); Ki[2] = (s * cy - cx * fy) / (fx * fy * w);
+    Ki[3] = 0.0; Ki[4] = 1.0 / fy; Ki[5] = -cy / (fy * w);
+    Ki[6] = 0.0; Ki[7] = 0.0; Ki[8] = 1.0 / w;
+}
+
+// x2dn = dehomogenised K^-1 [x; 1]  (ACKernelAdaptorResection_K)
+void normalize_points(const double *x2d, size_t N, const double *K, std::vector<double> &out) {
+    double Ki[9];
+    k_inverse(K, Ki);
+    out.resize(2 * N);
+    for (size_t i = 0; i < N; ++i) {
+        const double x = x2d[2 * i], y = x2d[2 * i + 1];
+        const double a = Ki[0] * x + Ki[1] * y + Ki[2];
+        const double b = Ki[3] * x + Ki[4] * y + Ki[5];
+        const double c = Ki[6] * x + Ki[7] * y + Ki[8];
+        out[2 * i] = a / c;
+        out[2 * i + 1] = b / c;
+    }
+}
+
+// log10 C(N,k) for k = 0..N and log10 C(n,3) for n = 0..N, double sums stored as float with the
+// same summation order as the sequential definition (prefix sums reproduce it exactly).
+void make_logcombi(size_t N, std::vector<float> &logc_n, std::vector<float> &logc_k) {
+    logc_n.assign(N + 1, 0.0f);
+    logc_k.assign(N + 1, 0.0f);
+    std::vector<double> prefix(N / 2 + 2, 0.0);   // prefix[j] = sum_{i=1..j} log10(N-i+1) - log10(i)
+    for (size_t j = 1; j < prefix.size(); ++j)
+        prefix[j] = prefix[j - 1] + (log10((double)(N - j + 1)) - log10((double)j));
+    for (size_t k = 0; k <= N; ++k) {
+        if (k >= N || k == 0) { logc_n[k] = 0.0f; continue; }
+        const size_t kk = (N - k < k) ? N - k : k;
+        logc_n[k] = (float)prefix[kk];
+    }
+    for (size_t n = 0; n <= N; ++n) {
+        size_t k = 3;
+        if (k >= n) { logc_k[n] = 0.0f; continue; }
+        if (n - k < k) k = n - k;
+        double r = 0.0;
+        for (size_t i = 1; i <= k; ++i) r += log10((double)(n - i + 1)) - log10((double)i);
+        logc_k[n] = (float)r;
+    }
+}
+
+uint32_t next_pow2(uint32_t v) {
+    uint32_t p = 64;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// Device-side staging of one resection problem.
+struct Problem {
+    size_t N = 0;
+    double *d_x2dn = nullptr, *d_X3d = nullptr;
+    float *d_logc_n = nullptr, *d_logc_k = nullptr;
+    double loge0 = 0, logalpha0 = 0;
+};
+
+// scratch0: x2dn | X3d | logc_n | logc_k   (problem);  scratch1: models; scratch2: outputs; scratch3: triplets
+int stage_problem(hulo_gpu *h, const std::vector<double> &x2dn, const double *X3d, size_t N, Problem &pb) {
+    std::vector<float> lcn, lck;
+    make_logcombi(N, lcn, lck);
+    const size_t bytes = N * 5 * sizeof(double) + 2 * (N + 1) * sizeof(float) + 64;
+    HULO_CUDA(h->scratch0.reserve(bytes));
+    pb.N = N;
+    pb.d_x2dn = h->scratch0.as<double>();
+    pb.d_X3d = pb.d_x2dn + 2 * N;
+    pb.d_logc_n = reinterpret_cast<float *>(pb.d_X3d + 3 * N);
+    pb.d_logc_k = pb.d_logc_n + (N + 1);
+    pb.loge0 = log10(4.0 * (double)(N > 3 ? N - 3 : 1));
+    pb.logalpha0 = log10(M_PI);
+    if (N > 0) {
+        HULO_CUDA(cudaMemcpyAsync(pb.d_x2dn, x2dn.data(), 2 * N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        HULO_CUDA(cudaMemcpyAsync(pb.d_X3d, X3d, 3 * N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    HULO_CUDA(cudaMemcpyAsync(pb.d_logc_n, lcn.data(), (N + 1) * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    HULO_CUDA(cudaMemcpyAsync(pb.d_logc_k, lck.data(), (N + 1) * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    // the host vectors die with this frame; the copies above are from pageable memory and have
+    // been staged by the runtime before cudaMemcpyAsync returned
+    return HULO_OK;
+}
+
+struct ScoreOut { double *nfa; int32_t *k; float *errk; int32_t *ninl; };
+
+int launch_score(hulo_gpu *h, const Problem &pb, const double *d_models, size_t H, float thr2, ScoreOut &o) {
+    const size_t bytes = H * (sizeof(double) + 2 * sizeof(int32_t) + sizeof(float)) + 64;
+    HULO_CUDA(h->scratch2.reserve(bytes));
+    o.nfa = h->scratch2.as<double>();
+    o.k = reinterpret_cast<int32_t *>(o.nfa + H);
+    o.errk = reinterpret_cast<float *>(o.k + H);
+    o.ninl = reinterpret_cast<int32_t *>(o.errk + H);
+    if (H == 0) return HULO_OK;
+    const uint32_t npad = next_pow2((uint32_t)pb.N);
+    const size_t smem = npad * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        HULO_CUDA(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    score_kernel<<<(unsigned)H, kScoreThreads, smem, h->stream>>>(d_models, (uint32_t)H, pb.d_x2dn, pb.d_X3d,
+                                                                (uint32_t)pb.N, npad, pb.d_logc_n, pb.d_logc_k,
+                                                                pb.loge0, pb.logalpha0, thr2, o.nfa, o.k, o.errk,
+                                                                o.ninl);
+    HULO_CUDA(cudaGetLastError());
+    h->launches++;
+    return HULO_OK;
+}
+
+uint64_t splitmix64(uint64_t &s) {
+    uint64_t z = (s += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+// three distinct positions in [0, total), ascending insertion (UniformSample, rand_sampling.hpp)
+void sample3(uint64_t &state, size_t total, size_t out[3]) {
+    for (int i = 0; i < 3; ++i) {
+        size_t r = (size_t)(splitmix64(state) % (uint64_t)(total - i));
+        int j;
+        for (j = 0; j < i && r >= out[j]; ++j) ++r;
+        for (int k = i; k > j; --k) out[k] = out[k - 1];
+        out[j] = r;
+    }
+}
+
+}  // namespace
+}  // namespace hulo
+
+using namespace hulo;
+
+extern "C" {
+
+int hulo_score_resection(hulo_gpu *h, const double *models, size_t H, const double *x2d, const double *X3d,
+                         size_t N, const double *K, double thr_px, float *nfa, int32_t *k_best, float *err_k,
+                         int32_t *n_inl) {
+    HULO_ARG(h != nullptr && K != nullptr, "null argument");
+    HULO_ARG(H == 0 || models != nullptr, "models is null");
+    HULO_ARG(N == 0 || (x2d != nullptr && X3d != nullptr), "null correspondences");
+    HULO_ARG(N <= kMaxPoints, "more than 32768 correspondences");
+    HULO_CUDA(cudaSetDevice(h->device));
+    std::vector<double> x2dn;
+    normalize_points(x2d, N, K, x2dn);
+    Problem pb;
+    int rc = stage_problem(h, x2dn, X3d, N, pb);
+    if (rc != HULO_OK) return rc;
+    HULO_CUDA(h->scratch1.reserve(std::max<size_t>(H, 1) * 12 * sizeof(double)));
+    if (H) HULO_CUDA(cudaMemcpyAsync(h->scratch1.ptr, models, H * 12 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const double fx = K[0];
+    const float thr2 = thr_px >= 0.0 ? (float)((thr_px / fx) * (thr_px / fx)) : -1.0f;
+    ScoreOut o;
+    rc = launch_score(h, pb, h->scratch1.as<double>(), H, thr2, o);
+    if (rc != HULO_OK) return rc;
+    if (H) {
+        std::vector<double> h_nfa(H);
+        std::vector<float> h_err(H);
+        HULO_CUDA(cudaMemcpyAsync(h_nfa.data(), o.nfa, H * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (k_best) HULO_CUDA(cudaMemcpyAsync(k_best, o.k, H * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        HULO_CUDA(cudaMemcpyAsync(h_err.data(), o.errk, H * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        if (n_inl) HULO_CUDA(cudaMemcpyAsync(n_inl, o.ninl, H * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        HULO_CUDA(cudaStreamSynchronize(h->stream));
+        for (size_t i = 0; i < H; ++i) {
+            if (nfa) nfa[i] = (float)h_nfa[i];
+            // unormalizeError: sqrt(e) / Kinv(0,0) = sqrt(e) * fx
+            if (err_k) err_k[i] = (float)(sqrt((double)h_err[i]) * fx);
+        }
+    }
+    return HULO_OK;
+}
+
+int hulo_resection_residuals(hulo_gpu *h, const double *models, size_t H, const double *x2d, const double *X3d,
+                             size_t N, const double *K, float *res_px) {
+    HULO_ARG(h != nullptr && K != nullptr, "null argument");
+    HULO_ARG(H == 0 || models != nullptr, "models is null");
+    HULO_ARG(N == 0 || (x2d != nullptr && X3d != nullptr), "null correspondences");
+    if (H == 0 || N == 0) return HULO_OK;
+    HULO_ARG(res_px != nullptr, "null output");
+    HULO_ARG(H <= 65535, "more than 65535 hypotheses in one residual dump");
+    HULO_CUDA(cudaSetDevice(h->device));
+    std::vector<double> x2dn;
+    normalize_points(x2d, N, K, x2dn);
+    Problem pb;
+    int rc = stage_problem(h, x2dn, X3d, N, pb);
+    if (rc != HULO_OK) return rc;
+    HULO_CUDA(h->scratch1.reserve(H * 12 * sizeof(double)));
+    HULO_CUDA(cudaMemcpyAsync(h->scratch1.ptr, models, H * 12 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    HULO_CUDA(h->scratch2.reserve(H * N * sizeof(float)));
+    dim3 grid((unsigned)((N + 255) / 256), (unsigned)H);
+    residual_kernel<<<grid, 256, 0, h->stream>>>(h->scratch1.as<double>(), (uint32_t)H, pb.d_x2dn, pb.d_X3d,
+                                                 (uint32_t)N, (float)K[0], h->scratch2.as<float>());
+    HULO_CUDA(cudaGetLastError());
+    h->launches++;
+    HULO_CUDA(cudaMemcpyAsync(res_px, h->scratch2.ptr, H * N * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    HULO_CUDA(cudaStreamSynchronize(h->stream));
+    return HULO_OK;
+}
+
+int hulo_p3p(hulo_gpu *h, const uint32_t *triplets, size_t T, const double *x2d, const double *X3d, size_t N,
+             const double *K, double *models, int32_t *n_models) {
+    HULO_ARG(h != nullptr && K != nullptr, "null argument");
+    HULO_ARG(T == 0 || (triplets != nullptr && models != nullptr && n_models != nullptr), "null argument");
+    HULO_ARG(N == 0 || (x2d != nullptr && X3d != nullptr), "null correspondences");
+    for (size_t t = 0; t < 3 * T; ++t) HULO_ARG(triplets[t] < N, "triplet index out of range");
+    if (T == 0) return HULO_OK;
+    HULO_CUDA(cudaSetDevice(h->device));
+    std::vector<double> x2dn;
+    normalize_points(x2d, N, K, x2dn);
+    Problem pb;
+    int rc = stage_problem(h, x2dn, X3d, N, pb);
+    if (rc != HULO_OK) return rc;
+    HULO_CUDA(h->scratch3.reserve(T * 3 * sizeof(uint32_t)));
+    HULO_CUDA(h->scratch1.reserve(T * 48 * sizeof(double) + T * sizeof(int32_t)));
+    HULO_CUDA(cudaMemcpyAsync(h->scratch3.ptr, triplets, T * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    double *d_models = h->scratch1.as<double>();
+    int32_t *d_nm = reinterpret_cast<int32_t *>(d_models + T * 48);
+    p3p_kernel<<<(unsigned)((T + 127) / 128), 128, 0, h->stream>>>(h->scratch3.as<uint32_t>(), (uint32_t)T, pb.d_x2dn,
+                                                                 pb.d_X3d, d_models, d_nm);
+    HULO_CUDA(cudaGetLastError());
+    h->launches++;
+    HULO_CUDA(cudaMemcpyAsync(models, d_models, T * 48 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    HULO_CUDA(cudaMemcpyAsync(n_models, d_nm, T * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    HULO_CUDA(cudaStreamSynchronize(h->stream));
+    return HULO_OK;
+}
+
+int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size_t N, const double *K,
+                         size_t max_iter, uint64_t seed, double *P, int32_t *inliers, size_t *n_inliers,
+                         double *error_max, int *found) {
+    HULO_ARG(h != nullptr && K != nullptr && P != nullptr && n_inliers != nullptr && error_max != nullptr &&
+                 found != nullptr, "null argument");
+    HULO_ARG(N == 0 || (x2d != nullptr && X3d != nullptr && inliers != nullptr), "null correspondences");
+    HULO_ARG(N <= kMaxPoints, "more than 32768 correspondences");
+    *n_inliers = 0; *error_max = 0.0; *found = 0;
+    // ACRANSAC: nothing to do with N <= MINIMUM_SAMPLES
+    if (N <= 3 || max_iter == 0) return HULO_OK;
+    HULO_CUDA(cudaSetDevice(h->device));
+    std::vector<double> x2dn;
+    normalize_points(x2d, N, K, x2dn);
+    Problem pb;
+    int rc = stage_problem(h, x2dn, X3d, N, pb);
+    if (rc != HULO_OK) return rc;
+
+    // Schedule of the sequential algorithm: 10 % of the iterations are reserved; once a
+    // meaningful model (NFA < 0) exists the sampler draws from its inliers and only the reserved
+    // iterations remain.  Batched: global batches until a meaningful model appears (at most
+    // max_iter - reserve draws), then one batch of `reserve` draws from the inliers.
+    const size_t reserve = max_iter / 10;
+    const size_t global_budget = max_iter - reserve;
+    const size_t batch = std::min<size_t>(global_budget, 512);
+    uint64_t rng = seed;
+    std::vector<size_t> pool(N);
+    for (size_t i = 0; i < N; ++i) pool[i] = i;
+
+    double best_nfa = INFINITY;
+    double best_model[12] = {0};
+    std::vector<uint32_t> tri;
+    std::vector<double> h_nfa;
+    std::vector<double> h_model(12);
+
+    auto run_batch = [&](size_t T) -> int {
+        tri.resize(3 * T);
+        for (size_t t = 0; t < T; ++t) {
+            size_t pos[3];
+            sample3(rng, pool.size(), pos);
+            for (int s = 0; s < 3; ++s) tri[3 * t + s] = (uint32_t)pool[pos[s]];
+        }
+        HULO_CUDA(h->scratch3.reserve(T * 3 * sizeof(uint32_t)));
+        HULO_CUDA(h->scratch1.reserve(T * 48 * sizeof(double) + T * sizeof(int32_t)));
+        HULO_CUDA(cudaMemcpyAsync(h->scratch3.ptr, tri.data(), T * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        double *d_models = h->scratch1.as<double>();
+        int32_t *d_nm = reinterpret_cast<int32_t *>(d_models + T * 48);
+        p3p_kernel<<<(unsigned)((T + 127) / 128), 128, 0, h->stream>>>(h->scratch3.as<uint32_t>(), (uint32_t)T,
+                                                                     pb.d_x2dn, pb.d_X3d, d_models, d_nm);
+        HULO_CUDA(cudaGetLastError());
+        h->launches++;
+        ScoreOut o;
+        int rc2 = launch_score(h, pb, d_models, 4 * T, -1.0f, o);
+        if (rc2 != HULO_OK) return rc2;
+        h_nfa.resize(4 * T);
+        HULO_CUDA(cudaMemcpyAsync(h_nfa.data(), o.nfa, 4 * T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        HULO_CUDA(cudaStreamSynchronize(h->stream));
+        // sequential update rule: strict <, so the earliest hypothesis wins ties
+        size_t arg = (size_t)-1;
+        for (size_t i = 0; i < 4 * T; ++i)
+            if (h_nfa[i] < best_nfa) { best_nfa = h_nfa[i]; arg = i; }
+        if (arg != (size_t)-1) {
+            HULO_CUDA(cudaMemcpyAsync(best_model, d_models + 12 * arg, 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            HULO_CUDA(cudaStreamSynchronize(h->stream));
+        }
+        return HULO_OK;
+    };
+
+    // Final scoring of a model in fp64 on the host: residuals, (residual, index) order, NFA.
+    std::vector<float> lcn, lck;
+    make_logcombi(N, lcn, lck);
+    struct EI { double e; size_t i; };
+    std::vector<EI> ei(N);
+    size_t best_k = 0;
+    double best_err = 0.0;
+    auto finalize = [&](const double *M) -> double {
+        for (size_t i = 0; i < N; ++i) {
+            const double *X = X3d + 3 * i;
+            const double u = M[0] * X[0] + M[1] * X[1] + M[2] * X[2] + M[3];
+            const double v = M[4] * X[0] + M[5] * X[1] + M[6] * X[2] + M[7];
+            const double w = M[8] * X[0] + M[9] * X[1] + M[10] * X[2] + M[11];
+            const double dx = u / w - x2dn[2 * i], dy = v / w - x2dn[2 * i + 1];
+            double e = dx * dx + dy * dy;
+            if (!(e == e)) e = INFINITY;
+            ei[i] = EI{e, i};
+        }
+        std::sort(ei.begin(), ei.end(), [](const EI &a, const EI &b) { return a.e < b.e || (a.e == b.e && a.i < b.i); });
+        double bn = INFINITY;
+        size_t bk = 3;
+        for (size_t k = 4; k <= N; ++k) {
+            if (!(ei[k - 1].e < INFINITY)) break;
+            const double logalpha = pb.logalpha0 + log10(ei[k - 1].e + (double)FLT_EPSILON);
+            const double nfa = pb.loge0 + logalpha * (double)(k - 3) + (double)lcn[k] + (double)lck[k];
+            if (nfa < bn) { bn = nfa; bk = k; }
+        }
+        best_k = bk;
+        best_err = bk >= 1 ? ei[bk - 1].e : 0.0;
+        return bn;
+    };
+
+    size_t drawn = 0;
+    while (drawn < global_budget) {
+        const size_t T = std::min(batch, global_budget - drawn);
+        rc = run_batch(T);
+        if (rc != HULO_OK) return rc;
+        drawn += T;
+        if (best_nfa < 0.0) break;
+    }
+    double final_nfa = INFINITY;
+    if (best_nfa < INFINITY) final_nfa = finalize(best_model);
+    if (reserve > 0 && final_nfa < 0.0 && best_k >= 3) {
+        // focused sampling among the inliers of the best model so far
+        pool.resize(best_k);
+        for (size_t i = 0; i < best_k; ++i) pool[i] = ei[i].i;
+        double prev_model[12];
+        memcpy(prev_model, best_model, sizeof prev_model);
+        const double prev_nfa = best_nfa;
+        rc = run_batch(reserve);
+        if (rc != HULO_OK) return rc;
+        if (best_nfa < prev_nfa) {
+            const double keep_nfa = final_nfa;
+            const size_t keep_k = best_k;
+            const double keep_err = best_err;
+            std::vector<EI> keep_ei(ei.begin(), ei.begin() + keep_k);
+            const double cand = finalize(best_model);
+            if (cand < keep_nfa) {
+                final_nfa = cand;
+            } else {   // fp32 ranking disagreed with the fp64 rescoring: keep the earlier model
+                memcpy(best_model, prev_model, sizeof prev_model);
+                best_k = keep_k; best_err = keep_err;
+                std::copy(keep_ei.begin(), keep_ei.end(), ei.begin());
+            }
+        }
+    } else if (reserve > 0 && !(final_nfa < 0.0)) {
+        // no meaningful model yet: the reserved iterations keep sampling globally
+        rc = run_batch(reserve);
+        if (rc != HULO_OK) return rc;
+        if (best_nfa < INFINITY) final_nfa = finalize(best_model);
+    }
+    if (!(final_nfa < 0.0)) return HULO_OK;   // minNFA >= 0: inliers cleared, not found
+
+    // Unnormalize: P = K * model ; error in pixels = sqrt(e) / Kinv(0,0)
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c)
+            P[4 * r + c] = K[3 * r] * best_model[c] + K[3 * r + 1] * best_model[4 + c] + K[3 * r + 2] * best_model[8 + c];
+    *error_max = sqrt(best_err) * K[0];
+    for (size_t i = 0; i < best_k; ++i) inliers[i] = (int32_t)ei[i].i;
+    *n_inliers = best_k;
+    // SfM_Localizer::Localize: resection succeeded iff #inliers > 2.5 * MINIMUM_SAMPLES
+    *found = (double)best_k > 2.5 * 3.0 ? 1 : 0;
+    return HULO_OK;
+}
+
+}  // extern "C"

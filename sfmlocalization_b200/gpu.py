@@ -158,6 +158,15 @@ class HuloGpu:
         check(self.lib.hulo_knn2_sharded(self.h, A.h, B_shard.h, row_base, _ptr(idx2), _ptr(dist2)))
         return idx2, dist2
 
+    def merge_top2(self, cand):
+        """cand: world x nA x 4 int32 records {d0, i0, d1, i1} with global indices."""
+        cand = np.ascontiguousarray(cand, np.int32)
+        world, nA = cand.shape[0], cand.shape[1]
+        idx2 = np.empty((nA, 2), np.int32)
+        dist2 = np.empty((nA, 2), np.int32)
+        check(self.lib.hulo_merge_top2(self.h, _ptr(cand), nA, world, _ptr(idx2), _ptr(dist2)))
+        return idx2, dist2
+
     def match_to_query(self, map_db, query, ratio, views=None, cap=None):
         """hulo_match_to_query -> dict(view, i, j, d0, view_counts)."""
         query = _rows(query)

@@ -1,0 +1,140 @@
+"""GPU parity suite for K2 (resection hypothesis scoring), the device P3P solver and the
+batched AC-RANSAC driver, through the C-ABI, against the fp64 CPU oracle.
+Tolerance (BASELINE.json): residuals within 1e-4 px of the fp64 restatement."""
+import math
+
+import numpy as np
+import pytest
+
+from sfmlocalization_b200 import synth
+
+pytestmark = pytest.mark.gpu
+TOL_PX = 1e-4
+
+
+def hypotheses(orc, sc, T, seed):
+    """P3P models of T seeded triplets (oracle), flattened H x 3 x 4."""
+    xn = orc.normalize_points(sc["x2d"], sc["K"])
+    tri = synth.sample_triplets(len(xn), T, seed)
+    models = []
+    for a in tri:
+        f = np.c_[xn[a], np.ones(3)]
+        f /= np.linalg.norm(f, axis=1, keepdims=True)
+        models += list(orc.p3p(f, sc["X3d"][a]))
+    return np.array(models), tri
+
+
+@pytest.mark.parametrize("N,outl", [(100, 0.3), (500, 0.5), (2000, 0.7)])
+def test_residuals_within_1e4_px(gpu, orc, N, outl):
+    sc = synth.resection_scene(N, 70 + N, outlier_frac=outl)
+    models, _ = hypotheses(orc, sc, 64, 1)
+    models = models[np.abs(models).max(axis=(1, 2)) < 1e3][:200]
+    res = gpu.resection_residuals(models, sc["x2d"], sc["X3d"], sc["K"])
+    xn = orc.normalize_points(sc["x2d"], sc["K"])
+    fx = sc["K"][0, 0]
+    worst = 0.0
+    for h, M in enumerate(models):
+        want = np.sqrt(orc.residuals(M, xn, sc["X3d"])) * fx
+        # absolute 1e-4 px; beyond ~800 px one fp32 ulp of the value itself exceeds that
+        tol = np.maximum(TOL_PX, want * 2.0 ** -22)
+        ok = np.isfinite(want)
+        assert (np.abs(res[h][ok] - want[ok]) <= tol[ok]).all()
+        small = ok & (want < 100)
+        if small.any():
+            worst = max(worst, float(np.abs(res[h][small] - want[small]).max()))
+    assert worst <= TOL_PX
+
+
+@pytest.mark.parametrize("N,outl", [(12, 0.2), (100, 0.3), (500, 0.5), (2000, 0.5), (2049, 0.7)])
+def test_scores_vs_oracle(gpu, orc, N, outl):
+    sc = synth.resection_scene(N, 90 + N, outlier_frac=outl)
+    models, _ = hypotheses(orc, sc, 96, 2)
+    true = np.c_[sc["R"], sc["t"].reshape(3, 1)][None]
+    models = np.concatenate([true, models[np.abs(models).max(axis=(1, 2)) < 1e3]])
+    thr = 4.0
+    nfa, kb, ek, ni = gpu.score_resection(models, sc["x2d"], sc["X3d"], sc["K"], thr_px=thr)
+    xn = orc.normalize_points(sc["x2d"], sc["K"])
+    fx = sc["K"][0, 0]
+    onfa, okb, oek, oni = orc.score_hypotheses(models, xn, sc["X3d"], thr2=(thr / fx) ** 2)
+    assert nfa[0] < 0 and abs(int(kb[0]) - int(sc["inlier_mask"].sum())) <= max(6, N // 50)
+    fin = np.isfinite(onfa)
+    assert (np.isfinite(nfa) == fin).all()
+    assert np.abs(nfa[fin] - onfa[fin]).max() <= 2e-3 + 2e-6 * np.abs(onfa[fin]).max()
+    assert int(np.argmin(nfa)) == int(np.argmin(onfa))
+    same = kb == okb
+    assert same.mean() > 0.97
+    assert same[0]
+    oek_px = np.sqrt(oek) * fx
+    assert np.abs(ek[same & fin] - oek_px[same & fin]).max() <= np.maximum(TOL_PX, 1e-6 * oek_px[same & fin]).max()
+    # inlier counts at a fixed threshold: identical except points within tolerance of it
+    assert np.abs(ni - oni).max() <= 1
+
+
+def test_scores_degenerate_inputs(gpu):
+    sc = synth.resection_scene(3, 5, outlier_frac=0.0)
+    M = np.c_[sc["R"], sc["t"].reshape(3, 1)][None]
+    nfa, kb, ek, ni = gpu.score_resection(M, sc["x2d"], sc["X3d"], sc["K"])
+    assert np.isinf(nfa[0]) and kb[0] == 3
+    bad = np.full((1, 3, 4), np.nan)
+    sc = synth.resection_scene(50, 6)
+    nfa, kb, ek, ni = gpu.score_resection(bad, sc["x2d"], sc["X3d"], sc["K"])
+    assert np.isinf(nfa[0])
+
+
+def test_device_p3p_vs_oracle(gpu, orc):
+    sc = synth.resection_scene(400, 11, outlier_frac=0.3)
+    tri = synth.sample_triplets(400, 256, 4)
+    models, nm = gpu.p3p(tri, sc["x2d"], sc["X3d"], sc["K"])
+    xn = orc.normalize_points(sc["x2d"], sc["K"])
+    checked = 0
+    for t, a in enumerate(tri):
+        f = np.c_[xn[a], np.ones(3)]
+        f /= np.linalg.norm(f, axis=1, keepdims=True)
+        want = orc.p3p(f, sc["X3d"][a])
+        assert nm[t] == len(want)
+        for m in range(nm[t]):
+            scale = max(1.0, np.abs(want[m]).max())
+            if scale > 1e6:
+                continue
+            assert np.abs(models[t, m] - want[m]).max() <= 1e-7 * scale
+            checked += 1
+    assert checked > 700
+
+
+def test_device_p3p_golden_triplets(gpu):
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = dict(np.load(os.path.join(root, "tests", "golden", "resect_golden.npz")))
+    for x, X, sols, n in zip(g["x2d"], g["X3d"], g["solutions"], g["n_solutions"]):
+        models, nm = gpu.p3p(np.array([[0, 1, 2]]), x, X, g["K"])
+        for s in sols[:n]:
+            assert min(np.abs(models[0, m] - s).max() for m in range(nm[0])) < 1e-6
+
+
+@pytest.mark.parametrize("N,outl,seed", [(100, 0.3, 1), (500, 0.5, 2), (500, 0.7, 3), (2000, 0.7, 4)])
+def test_acransac_recovers_pose(gpu, orc, N, outl, seed):
+    sc = synth.resection_scene(N, 300 + N + seed, outlier_frac=outl)
+    r = gpu.resect_acransac(sc["x2d"], sc["X3d"], sc["K"], max_iter=4096, seed=seed)
+    assert r["found"]
+    K, R, t, c = orc.krt_from_p(r["P"])
+    c_true = -sc["R"].T @ sc["t"]
+    assert np.linalg.norm(c - c_true) < 0.05
+    assert np.abs(R - sc["R"]).max() < 5e-3
+    inl = set(r["inliers"].tolist())
+    truth = set(np.nonzero(sc["inlier_mask"])[0].tolist())
+    assert len(inl & truth) >= 0.85 * len(truth)
+    assert len(inl - truth) <= max(3, 0.05 * len(truth))
+    # same model quality as the sequential CPU restatement on the same data
+    o = orc.acransac(sc["x2d"], sc["X3d"], sc["K"], max_iter=4096, seed=seed)
+    assert o["ok"]
+    assert abs(len(r["inliers"]) - len(o["inliers"])) <= max(5, 0.05 * len(o["inliers"]))
+    assert r["error_max"] < 2.0 * o["error_max"] + 0.5
+
+
+def test_acransac_not_found_cases(gpu):
+    sc = synth.resection_scene(3, 1, outlier_frac=0.0)
+    r = gpu.resect_acransac(sc["x2d"], sc["X3d"], sc["K"])
+    assert not r["found"] and len(r["inliers"]) == 0
+    sc = synth.resection_scene(60, 9, outlier_frac=1.0)
+    r = gpu.resect_acransac(sc["x2d"], sc["X3d"], sc["K"], max_iter=512, seed=3)
+    assert not r["found"]

@@ -174,6 +174,48 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
                          const double *K, size_t max_iter, uint64_t seed, double *P,
                          int32_t *inliers, size_t *n_inliers, double *error_max, int *found);
 
+/* ------------------------------------------------- query localisation, end to end */
+
+typedef struct hulo_engine hulo_engine;
+
+/* The device-resident state LocalizeEngine builds once per map (LocalizeEngine.cc:84-198):
+ * every view's descriptor rows (segments = views, in ascending view id), the
+ * (view, feature) -> landmark table of hulo::structureToMapViewFeatTo3D
+ * (SfMDataUtils.cpp:33-46) and the landmark positions.
+ *   obs_view/obs_feat/obs_landmark  n_obs observations; obs_landmark indexes landmark_X
+ *   landmark_X                      n_landmarks x 3 doubles
+ *   K                               3x3 row-major pinhole intrinsics of the query camera
+ * The engine keeps a reference to `h`, which must outlive it. */
+int hulo_engine_create(hulo_gpu *h, const uint8_t *rows, size_t n, size_t stride, const uint64_t *seg_offsets,
+                       size_t n_views, const uint32_t *obs_view, const uint32_t *obs_feat,
+                       const uint32_t *obs_landmark, size_t n_obs, const double *landmark_X, size_t n_landmarks,
+                       const double *K, hulo_engine **out);
+void hulo_engine_destroy(hulo_engine *e);
+
+/* Acceptance thresholds of the reference (LocalizeEngine.cc:63-65): a view is kept with at
+ * least min_putative putative matches (16, :428-434), resection is tried with more than
+ * min_points correspondences (8, :529) and accepted with more than min_inliers inliers (10, :560).
+ * max_iter is the AC-RANSAC budget (4096 = OpenMVG's default, which the reference never overrides). */
+int hulo_engine_configure(hulo_engine *e, float ratio, int min_putative, int min_points, int min_inliers,
+                          size_t max_iter);
+
+/* LocalizeEngine::localize from the putative matching on (LocalizeEngine.cc:423-602) for one
+ * query image given its descriptors and (undistorted) keypoint positions:
+ *   hulo::matchAKAZEToQuery -> drop views with too few matches -> hulo::matchProviderToMatchSet
+ *   (2D-3D assembly, closest descriptor wins) -> SfM_Localizer::Localize -> KRt_From_P.
+ * The F-matrix geometric filter between matching and assembly (hulo::geometricMatch, :458) is
+ * not applied: the assembly consumes the putative matches.
+ *   views / n_views   selected map views (NULL: all), as the `pairs` argument of matchAKAZEToQuery
+ *   pose12            camera centre -R^T t (3) then R row-major (9), as LocalizeEngine.cc:593-602
+ *   *localized        1 iff resection succeeded with enough inliers
+ *   corr_qfeat / corr_landmark (capacity nq, may be NULL) the 2D-3D pairs, ascending query feature
+ *   inliers (capacity nq, may be NULL) indices into the pair list
+ *   times_ms[3]       putMatch, assembly, PnP (device + host wall time per stage) */
+int hulo_engine_localize(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t q_stride, const double *qxy,
+                         const uint32_t *views, size_t n_views, uint64_t seed, double *pose12, int *localized,
+                         uint32_t *corr_qfeat, uint32_t *corr_landmark, size_t *n_corr, int32_t *inliers,
+                         size_t *n_inliers, double *times_ms);
+
 /* ------------------------------------------------------------------ multi GPU */
 
 /* One process per GPU.  Rank 0 obtains an id with hulo_comm_unique_id and distributes its

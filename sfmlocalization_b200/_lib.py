@@ -54,6 +54,11 @@ SIGNATURES = {
     "hulo_p3p": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _vp]),
     "hulo_resect_acransac": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _sz, _u64, _vp, _vp, C.POINTER(_sz),
                                        C.POINTER(_f64), C.POINTER(C.c_int)]),
+    "hulo_engine_create": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _pp]),
+    "hulo_engine_destroy": (None, [_vp]),
+    "hulo_engine_configure": (C.c_int, [_vp, _f32, C.c_int, C.c_int, C.c_int, _sz]),
+    "hulo_engine_localize": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _vp, _sz, _u64, _vp, C.POINTER(C.c_int), _vp, _vp,
+                                       C.POINTER(_sz), _vp, C.POINTER(_sz), _vp]),
     "hulo_comm_unique_id": (C.c_int, [_vp]),
     "hulo_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "hulo_comm_barrier": (C.c_int, [_vp]),

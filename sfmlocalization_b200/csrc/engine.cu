@@ -1,0 +1,273 @@
+// engine.cu -- the per-query pipeline of LocalizeEngine::localize around the two kernels
+// (VisionLocalizeServer/src/LocalizeEngine.cc:423-602; CLI twin
+// OpenMVGLocalization_AKAZE/src/localization.cpp:398-547): putative matching (K1), the
+// "< 16 matches" view filter, the 2D-3D assembly of hulo::matchProviderToMatchSet
+// (VisionLocalizeCommon/src/SfMDataUtils.cpp:59-125), AC-RANSAC resection (K2) and the pose
+// extraction.  Host side C++; the map state lives on the device for the life of the engine.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "context.cuh"
+
+struct hulo_engine {
+    hulo_gpu *h = nullptr;
+    hulo_db *map = nullptr;
+    size_t n_views = 0;
+    // (view, feat) -> landmark, sorted by key = view << 32 | feat
+    std::vector<uint64_t> obs_key;
+    std::vector<uint32_t> obs_lm;
+    std::vector<double> X;     // n_landmarks x 3
+    double K[9];
+    float ratio = 0.6f;        // secondTestRatio, localizeImage.cc:46-59
+    int min_putative = 16, min_points = 8, min_inliers = 10;
+    size_t max_iter = 4096;
+    // per-query scratch
+    std::vector<uint32_t> m_view, m_i, m_j, view_counts;
+    std::vector<int32_t> m_d0;
+    std::vector<int32_t> fd, fd_stamp, best_d;
+    std::vector<int64_t> best_lm;
+    std::vector<double> x2d, X3d;
+    std::vector<int32_t> inl;
+};
+
+namespace hulo {
+namespace {
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+void mat3_mul(const double *A, const double *B, double *O) {
+    double T[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) T[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+    memcpy(O, T, sizeof T);
+}
+
+// KRt_From_P (openMVG multiview/projection.hpp): RQ decomposition of the left 3x3 block with
+// three Givens rotations, positive diagonal for K, det(R) = +1, K(2,2) = 1.
+void krt_from_p(const double *P, double *K, double *R, double *t) {
+    double Kk[9] = {P[0], P[1], P[2], P[4], P[5], P[6], P[8], P[9], P[10]};
+    double Q[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    {   // zero (2,1)
+        double c = -Kk[8], s = Kk[7];
+        const double l = std::sqrt(c * c + s * s);
+        c /= l; s /= l;
+        const double G[9] = {1, 0, 0, 0, c, -s, 0, s, c};
+        mat3_mul(Kk, G, Kk); mat3_mul(Q, G, Q);
+    }
+    {   // zero (2,0)
+        double c = Kk[8], s = Kk[6];
+        const double l = std::sqrt(c * c + s * s);
+        c /= l; s /= l;
+        const double G[9] = {c, 0, s, 0, 1, 0, -s, 0, c};
+        mat3_mul(Kk, G, Kk); mat3_mul(Q, G, Q);
+    }
+    {   // zero (1,0)
+        double c = -Kk[4], s = Kk[3];
+        const double l = std::sqrt(c * c + s * s);
+        c /= l; s /= l;
+        const double G[9] = {c, -s, 0, s, c, 0, 0, 0, 1};
+        mat3_mul(Kk, G, Kk); mat3_mul(Q, G, Q);
+    }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = Q[3 * j + i];
+    for (int a = 0; a < 3; ++a)
+        if (Kk[4 * a] < 0) {
+            for (int r = 0; r < 3; ++r) Kk[3 * r + a] = -Kk[3 * r + a];
+            for (int c = 0; c < 3; ++c) R[3 * a + c] = -R[3 * a + c];
+        }
+    const double det = R[0] * (R[4] * R[8] - R[5] * R[7]) - R[1] * (R[3] * R[8] - R[5] * R[6]) +
+                       R[2] * (R[3] * R[7] - R[4] * R[6]);
+    double p4[3] = {P[3], P[7], P[11]};
+    if (det < 0) {
+        for (int k = 0; k < 9; ++k) R[k] = -R[k];
+        for (int k = 0; k < 3; ++k) p4[k] = -p4[k];
+    }
+    // t = K^-1 p4, K upper triangular
+    t[2] = p4[2] / Kk[8];
+    t[1] = (p4[1] - Kk[5] * t[2]) / Kk[4];
+    t[0] = (p4[0] - Kk[1] * t[1] - Kk[2] * t[2]) / Kk[0];
+    const double sc = Kk[8];
+    for (int k = 0; k < 9; ++k) K[k] = Kk[k] / sc;
+}
+
+}  // namespace
+}  // namespace hulo
+
+using namespace hulo;
+
+extern "C" {
+
+int hulo_engine_create(hulo_gpu *h, const uint8_t *rows, size_t n, size_t stride, const uint64_t *seg_offsets,
+                       size_t n_views, const uint32_t *obs_view, const uint32_t *obs_feat,
+                       const uint32_t *obs_landmark, size_t n_obs, const double *landmark_X, size_t n_landmarks,
+                       const double *K, hulo_engine **out) {
+    HULO_ARG(h != nullptr && out != nullptr && K != nullptr, "null argument");
+    *out = nullptr;
+    HULO_ARG(seg_offsets != nullptr && n_views >= 1, "the map needs a view table");
+    HULO_ARG(n_obs == 0 || (obs_view && obs_feat && obs_landmark), "null observation table");
+    HULO_ARG(n_landmarks == 0 || landmark_X != nullptr, "null landmark positions");
+    for (size_t k = 0; k < n_obs; ++k) {
+        HULO_ARG(obs_view[k] < n_views, "observation refers to a view that does not exist");
+        HULO_ARG(obs_landmark[k] < n_landmarks, "observation refers to a landmark that does not exist");
+    }
+    hulo_engine *e = new (std::nothrow) hulo_engine();
+    HULO_ARG(e != nullptr, "out of host memory");
+    e->h = h;
+    int rc = hulo_db_upload(h, rows, n, stride, seg_offsets, n_views, &e->map);
+    if (rc != HULO_OK) { delete e; return rc; }
+    e->n_views = n_views;
+    std::vector<size_t> order(n_obs);
+    for (size_t k = 0; k < n_obs; ++k) order[k] = k;
+    auto key = [&](size_t k) { return ((uint64_t)obs_view[k] << 32) | obs_feat[k]; };
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return key(a) < key(b); });
+    e->obs_key.reserve(n_obs);
+    e->obs_lm.reserve(n_obs);
+    for (size_t k = 0; k < n_obs; ++k) {
+        const uint64_t kk = key(order[k]);
+        // a (view, feature) observed by several landmarks keeps the last one written, like the
+        // map[view][feat] = landmark assignment of SfMDataUtils.cpp:42
+        if (!e->obs_key.empty() && e->obs_key.back() == kk) e->obs_lm.back() = obs_landmark[order[k]];
+        else { e->obs_key.push_back(kk); e->obs_lm.push_back(obs_landmark[order[k]]); }
+    }
+    e->X.assign(landmark_X, landmark_X + 3 * n_landmarks);
+    memcpy(e->K, K, sizeof e->K);
+    *out = e;
+    return HULO_OK;
+}
+
+void hulo_engine_destroy(hulo_engine *e) {
+    if (!e) return;
+    hulo_db_free(e->map);
+    delete e;
+}
+
+int hulo_engine_configure(hulo_engine *e, float ratio, int min_putative, int min_points, int min_inliers,
+                          size_t max_iter) {
+    HULO_ARG(e != nullptr, "null engine");
+    HULO_ARG(ratio > 0.0f && min_putative >= 0 && min_points >= 3 && min_inliers >= 0 && max_iter >= 1, "bad threshold");
+    e->ratio = ratio;
+    e->min_putative = min_putative;
+    e->min_points = min_points;
+    e->min_inliers = min_inliers;
+    e->max_iter = max_iter;
+    return HULO_OK;
+}
+
+int hulo_engine_localize(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t q_stride, const double *qxy,
+                         const uint32_t *views, size_t n_views, uint64_t seed, double *pose12, int *localized,
+                         uint32_t *corr_qfeat, uint32_t *corr_landmark, size_t *n_corr, int32_t *inliers,
+                         size_t *n_inliers, double *times_ms) {
+    HULO_ARG(e != nullptr && pose12 != nullptr && localized != nullptr, "null argument");
+    HULO_ARG(nq == 0 || (qdesc != nullptr && qxy != nullptr), "null query");
+    *localized = 0;
+    if (n_corr) *n_corr = 0;
+    if (n_inliers) *n_inliers = 0;
+    if (times_ms) times_ms[0] = times_ms[1] = times_ms[2] = 0.0;
+    if (views == nullptr) n_views = e->n_views;
+    const double t0 = now_ms();
+
+    // ---- putative matching, hulo::matchAKAZEToQuery (LocalizeEngine.cc:423)
+    const size_t cap = hulo_db_rows(e->map);
+    e->m_view.resize(std::max<size_t>(cap, 1));
+    e->m_i.resize(std::max<size_t>(cap, 1));
+    e->m_j.resize(std::max<size_t>(cap, 1));
+    e->m_d0.resize(std::max<size_t>(cap, 1));
+    e->view_counts.assign(std::max<size_t>(n_views, 1), 0);
+    size_t n_m = 0;
+    int rc = hulo_match_to_query(e->h, e->map, views, n_views, qdesc, nq, q_stride, e->ratio, e->m_view.data(),
+                                 e->m_i.data(), e->m_j.data(), e->m_d0.data(), cap, &n_m, e->view_counts.data());
+    if (rc != HULO_OK) return rc;
+    const double t1 = now_ms();
+
+    // ---- 2D-3D assembly, hulo::matchProviderToMatchSet (SfMDataUtils.cpp:59-125).
+    // The reference walks a std::map keyed by (view id, query id): ascending view id, and inside
+    // a view the matches in emission order.  featDist[(v,q)][j] is the distance of the LAST
+    // match of view v onto query feature j (MatchUtils.cpp:351); every candidate of that view for
+    // j is weighed with it, and a candidate replaces the current one only if strictly closer.
+    std::vector<size_t> start(n_views + 1, 0);
+    for (size_t v = 0; v < n_views; ++v) start[v + 1] = start[v] + e->view_counts[v];
+    std::vector<size_t> order(n_views);
+    for (size_t v = 0; v < n_views; ++v) order[v] = v;
+    if (views)
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return views[a] < views[b]; });
+    e->fd.assign(nq, 0);
+    e->fd_stamp.assign(nq, -1);
+    e->best_lm.assign(nq, -1);
+    e->best_d.assign(nq, 0);
+    int32_t prev_view_id = -1;
+    for (size_t oi = 0; oi < n_views; ++oi) {
+        const size_t v = order[oi];
+        const uint32_t view_id = views ? views[v] : (uint32_t)v;
+        if ((int32_t)view_id == prev_view_id) continue;              // a view listed twice: one map key
+        prev_view_id = (int32_t)view_id;
+        // views with fewer putative matches than the threshold are dropped (LocalizeEngine.cc:428-434)
+        if ((int)e->view_counts[v] < e->min_putative) continue;
+        for (size_t k = start[v]; k < start[v + 1]; ++k) {
+            const uint32_t j = e->m_j[k];
+            e->fd[j] = e->m_d0[k];
+            e->fd_stamp[j] = (int32_t)oi;
+        }
+        for (size_t k = start[v]; k < start[v + 1]; ++k) {
+            const uint64_t key = ((uint64_t)view_id << 32) | e->m_i[k];
+            auto it = std::lower_bound(e->obs_key.begin(), e->obs_key.end(), key);
+            if (it == e->obs_key.end() || *it != key) continue;      // feature has no landmark
+            const uint32_t lm = e->obs_lm[(size_t)(it - e->obs_key.begin())];
+            const uint32_t j = e->m_j[k];
+            if (e->fd_stamp[j] != (int32_t)oi) continue;
+            const int32_t d = e->fd[j];
+            if (e->best_lm[j] < 0 || (float)e->best_d[j] > (float)d) {
+                e->best_lm[j] = lm;
+                e->best_d[j] = d;
+            }
+        }
+    }
+    e->x2d.clear();
+    e->X3d.clear();
+    size_t N = 0;
+    for (size_t j = 0; j < nq; ++j) {
+        if (e->best_lm[j] < 0) continue;
+        if (corr_qfeat) corr_qfeat[N] = (uint32_t)j;
+        if (corr_landmark) corr_landmark[N] = (uint32_t)e->best_lm[j];
+        e->x2d.push_back(qxy[2 * j]);
+        e->x2d.push_back(qxy[2 * j + 1]);
+        const double *X = &e->X[3 * (size_t)e->best_lm[j]];
+        e->X3d.insert(e->X3d.end(), X, X + 3);
+        ++N;
+    }
+    if (n_corr) *n_corr = N;
+    const double t2 = now_ms();
+
+    // ---- resection, SfM_Localizer::Localize (LocalizeEngine.cc:529-532) and acceptance (:560)
+    if ((int)N > e->min_points) {
+        double P[12];
+        e->inl.resize(N);
+        size_t n_inl = 0;
+        double err_max = 0.0;
+        int found = 0;
+        rc = hulo_resect_acransac(e->h, e->x2d.data(), e->X3d.data(), N, e->K, e->max_iter, seed, P, e->inl.data(),
+                                  &n_inl, &err_max, &found);
+        if (rc != HULO_OK) return rc;
+        if (inliers) memcpy(inliers, e->inl.data(), n_inl * sizeof(int32_t));
+        if (n_inliers) *n_inliers = n_inl;
+        if (found && (int)n_inl > e->min_inliers) {
+            double Kd[9], R[9], t[3];
+            krt_from_p(P, Kd, R, t);
+            // t_out = -R^T t  (LocalizeEngine.cc:582-585), result = [t_out, R row-major] (:593-602)
+            for (int c = 0; c < 3; ++c) pose12[c] = -(R[c] * t[0] + R[3 + c] * t[1] + R[6 + c] * t[2]);
+            memcpy(pose12 + 3, R, 9 * sizeof(double));
+            *localized = 1;
+        }
+    }
+    const double t3 = now_ms();
+    if (times_ms) { times_ms[0] = t1 - t0; times_ms[1] = t2 - t1; times_ms[2] = t3 - t2; }
+    return HULO_OK;
+}
+
+}  // extern "C"

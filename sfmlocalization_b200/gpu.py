@@ -268,3 +268,49 @@ class HuloGpu:
         v = C.c_double(value)
         check(self.lib.hulo_comm_max_f64(self.h, C.byref(v)))
         return v.value
+
+
+class LocalizeEngine:
+    """hulo_engine_*: the hot path of LocalizeEngine::localize (LocalizeEngine.cc:423-602) with
+    the map resident on the device."""
+
+    def __init__(self, gpu, rows, seg_offsets, obs_view, obs_feat, obs_landmark, landmark_X, K,
+                 ratio=0.6, min_putative=16, min_points=8, min_inliers=10, max_iter=4096):
+        self.gpu = gpu
+        self.lib = gpu.lib
+        rows = _rows(rows)
+        seg = np.ascontiguousarray(seg_offsets, np.uint64)
+        ov = np.ascontiguousarray(obs_view, np.uint32); of = np.ascontiguousarray(obs_feat, np.uint32)
+        ol = np.ascontiguousarray(obs_landmark, np.uint32)
+        X = np.ascontiguousarray(landmark_X, np.float64); K = np.ascontiguousarray(K, np.float64)
+        h = C.c_void_p()
+        check(self.lib.hulo_engine_create(gpu.h, _ptr(rows), rows.shape[0], rows.shape[1] if rows.shape[0] else 64,
+                                          _ptr(seg), len(seg) - 1, _ptr(ov), _ptr(of), _ptr(ol), len(ov), _ptr(X),
+                                          X.shape[0], _ptr(K), C.byref(h)))
+        self.h = h
+        check(self.lib.hulo_engine_configure(self.h, ratio, min_putative, min_points, min_inliers, max_iter))
+
+    def localize(self, qdesc, qxy, views=None, seed=1):
+        qdesc = _rows(qdesc)
+        qxy = np.ascontiguousarray(qxy, np.float64)
+        nq = qdesc.shape[0]
+        n_views = 0
+        if views is not None:
+            views = np.ascontiguousarray(views, np.uint32)
+            n_views = len(views)
+        pose = np.zeros(12); loc = C.c_int(0)
+        cq = np.empty(max(nq, 1), np.uint32); cl = np.empty(max(nq, 1), np.uint32)
+        inl = np.empty(max(nq, 1), np.int32)
+        nc = C.c_size_t(0); ni = C.c_size_t(0)
+        times = np.zeros(3)
+        check(self.lib.hulo_engine_localize(self.h, _ptr(qdesc), nq, qdesc.shape[1] if nq else 64, _ptr(qxy),
+                                            _ptr(views), n_views, seed, _ptr(pose), C.byref(loc), _ptr(cq), _ptr(cl),
+                                            C.byref(nc), _ptr(inl), C.byref(ni), _ptr(times)))
+        return dict(localized=bool(loc.value), center=pose[:3].copy(), R=pose[3:].reshape(3, 3).copy(),
+                    corr_qfeat=cq[:nc.value].copy(), corr_landmark=cl[:nc.value].copy(),
+                    inliers=inl[:ni.value].copy(), times_ms=times)
+
+    def close(self):
+        if self.h is not None:
+            self.lib.hulo_engine_destroy(self.h)
+            self.h = None

@@ -123,3 +123,53 @@ def sample_triplets(N, T, seed):
     for k in range(T):
         tri[k] = rng.choice(N, size=3, replace=False)
     return tri
+
+
+def _noisy_copies(base, seed, flip_p):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    flips = rng.random((base.shape[0], ROW * 8)) < flip_p
+    flips[:, DESC_BITS:] = False
+    return base ^ np.packbits(flips, axis=1, bitorder="little")
+
+
+def localization_scene(n_views, feats_per_view, n_landmarks, nq, seed, track_frac=0.6, query_inlier_frac=0.35,
+                       noise_px=0.7, flip_p=0.08, K=K_IPHONE6):
+    """A synthetic SfM map and one query image.
+    Map: n_landmarks 3D points, each with a base descriptor; every view holds feats_per_view
+    features of which track_frac observe a random landmark (descriptor = noisy copy of the
+    landmark's) and the rest are clutter.  Query: nq features, query_inlier_frac of them observe
+    landmarks (projected with the true pose + pixel noise), the rest are clutter at random
+    positions.  Returns a dict with everything hulo_engine_create / localize need plus truth."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    sc = resection_scene(n_landmarks, seed + 1, outlier_frac=0.0, noise_px=0.0, K=K)
+    X, R, t = sc["X3d"], sc["R"], sc["t"]
+    lm_desc = random_rows(n_landmarks, seed + 2)
+    rows, off = [], [0]
+    obs_view, obs_feat, obs_lm = [], [], []
+    for v in range(n_views):
+        n_obs = int(feats_per_view * track_frac)
+        lms = rng.choice(n_landmarks, size=min(n_obs, n_landmarks), replace=False)
+        d_obs = _noisy_copies(lm_desc[lms], seed * 7919 + v, flip_p)
+        d_clutter = random_rows(feats_per_view - len(lms), seed * 104729 + v)
+        d = np.concatenate([d_obs, d_clutter], axis=0)
+        perm = rng.permutation(d.shape[0])
+        d = d[perm]
+        inv = np.empty_like(perm); inv[perm] = np.arange(len(perm))
+        rows.append(d); off.append(off[-1] + d.shape[0])
+        obs_view += [v] * len(lms); obs_feat += inv[:len(lms)].tolist(); obs_lm += lms.tolist()
+    n_in = int(nq * query_inlier_frac)
+    q_lms = rng.choice(n_landmarks, size=min(n_in, n_landmarks), replace=False)
+    q_desc = np.concatenate([_noisy_copies(lm_desc[q_lms], seed + 3, flip_p), random_rows(nq - len(q_lms), seed + 4)])
+    Xc = X[q_lms] @ R.T + t
+    uv = (Xc @ K.T); uv = uv[:, :2] / uv[:, 2:]
+    uv += rng.normal(scale=noise_px, size=uv.shape)
+    q_xy = np.concatenate([uv, np.stack([rng.uniform(0, IMAGE_WH[0], nq - len(q_lms)),
+                                         rng.uniform(0, IMAGE_WH[1], nq - len(q_lms))], axis=1)])
+    perm = rng.permutation(nq)
+    q_desc, q_xy = q_desc[perm], q_xy[perm]
+    q_truth = np.full(nq, -1, np.int64)
+    q_truth[np.argsort(perm)[:len(q_lms)]] = q_lms
+    return dict(rows=np.concatenate(rows), seg_offsets=np.array(off, np.uint64),
+                obs_view=np.array(obs_view, np.uint32), obs_feat=np.array(obs_feat, np.uint32),
+                obs_landmark=np.array(obs_lm, np.uint32), landmark_X=X, K=K.copy(), R=R, t=t,
+                center=-R.T @ t, q_desc=q_desc, q_xy=q_xy, q_truth=q_truth)

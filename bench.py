@@ -202,6 +202,64 @@ def run_reference(args, rank, world):
     }))
 
 
+def localize_bench(g, with_cpu=True, reps=20):
+    """Second half of the metric (BASELINE.json: query localizations/sec): configs[0], one query
+    image of 2000 descriptors against a 200k-descriptor map (100 views x 2000), ratio 0.6
+    (the server's secondTestRatio, localizeImage.cc:46-59), AC-RANSAC resection with the
+    reference's 4096-iteration budget.  End to end through hulo_engine_localize: query
+    descriptors and keypoints in host memory, pose back in host memory."""
+    from sfmlocalization_b200.gpu import LocalizeEngine
+    sc = synth.localization_scene(100, 2000, 20000, 2000, 1000)
+    eng = LocalizeEngine(g, sc["rows"], sc["seg_offsets"], sc["obs_view"], sc["obs_feat"], sc["obs_landmark"],
+                         sc["landmark_X"], sc["K"], ratio=0.6)
+    for k in range(3):
+        r = eng.localize(sc["q_desc"], sc["q_xy"], seed=k)
+    wall, stages, ok, err = [], [], 0, []
+    for k in range(reps):
+        t0 = time.perf_counter()
+        r = eng.localize(sc["q_desc"], sc["q_xy"], seed=100 + k)
+        wall.append((time.perf_counter() - t0) * 1e3)
+        stages.append(r["times_ms"])
+        if r["localized"]:
+            ok += 1
+            err.append(float(np.linalg.norm(r["center"] - sc["center"])))
+    eng.close()
+    ms = float(np.median(wall))
+    st = np.median(np.array(stages), axis=0)
+    out = {"workload": "C1: 2000 query descriptors vs 200000 map descriptors (100 views), ratio 0.6, "
+                       "AC-RANSAC + P3P, max 4096 iterations",
+           "ms_per_query": ms, "localizations_per_s": 1e3 / ms,
+           "stage_ms": {"putMatch": float(st[0]), "assembly": float(st[1]), "PnP": float(st[2])},
+           "fraction_localized": ok / reps, "centre_error_m_median": float(np.median(err)) if err else None,
+           "correspondences": int(len(r["corr_qfeat"])), "inliers": int(len(r["inliers"])),
+           "target_ms": 5.0}
+    if with_cpu:
+        from oracle import oracle as orc
+        orc.build()
+        t0 = time.perf_counter()
+        off = sc["seg_offsets"]
+        m_view, m_i, m_j, m_d = [], [], [], []
+        for v in range(len(off) - 1):
+            oi, oj, od = orc.match_view_to_query(sc["rows"][int(off[v]):int(off[v + 1])], sc["q_desc"], 0.6)
+            if len(oi) < 16:
+                continue
+            m_view += [v] * len(oi); m_i += oi.tolist(); m_j += oj.tolist(); m_d += od.tolist()
+        t1 = time.perf_counter()
+        order = np.lexsort((sc["obs_feat"], sc["obs_view"]))
+        cj, cl = orc.match_set(m_view, m_i, m_j, m_view, m_j, m_d, sc["obs_view"][order], sc["obs_feat"][order],
+                               sc["obs_landmark"][order].astype(np.int64), len(sc["q_desc"]))
+        t2 = time.perf_counter()
+        ro = orc.acransac(sc["q_xy"][cj], sc["landmark_X"][cl], sc["K"], max_iter=4096, seed=1)
+        t3 = time.perf_counter()
+        out["cpu_baseline"] = {"ms_per_query": (t3 - t0) * 1e3, "cores": orc.num_threads(), "kind": "port",
+                               "stage_ms": {"putMatch": (t1 - t0) * 1e3, "assembly": (t2 - t1) * 1e3,
+                                            "PnP": (t3 - t2) * 1e3},
+                               "sample": "1 query: exact per-view 2-NN on all cores, sequential AC-RANSAC on one "
+                                         "thread (as the reference runs it)",
+                               "localized": bool(ro["ok"]), "inliers": int(len(ro["inliers"]))}
+    return out
+
+
 def workload_config(n_gpus):
     return {"workload": "C3 building-scale map: %d queries x %d map descriptors (64-byte AKAZE/MLDB rows), "
                         "exact Hamming 2-NN, planted matches (30%%)" % (N_QUERIES, N_MAP),
@@ -340,6 +398,8 @@ def main():
             "roofline": roofline,
             "result_check": "planted matches found, d0<=d1" if ok else "FAILED",
         }
+        if world == 1:
+            line["localize"] = localize_bench(g, with_cpu=not args.no_cpu_baseline)
         if not args.no_cpu_baseline and world == 1:
             cb, (ci, cd, nq, nb) = cpu_baseline_sample(A, shard)
             # the same sample through the GPU path must agree bit for bit

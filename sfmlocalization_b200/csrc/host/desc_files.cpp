@@ -1,0 +1,120 @@
+#include "desc_files.h"
+
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace hulo {
+
+bool readAKAZEBin(const std::string &filename, std::vector<uint8_t> &rows, std::size_t &count) {
+    rows.clear();
+    count = 0;
+    std::ifstream f(filename, std::ios::binary);
+    if (!f.is_open()) return false;
+    uint64_t n = 0;
+    f.read(reinterpret_cast<char *>(&n), sizeof n);
+    if (!f) return false;
+    rows.resize((std::size_t)n * 64);
+    if (n) f.read(reinterpret_cast<char *>(rows.data()), (std::streamsize)rows.size());
+    if (!f) { rows.clear(); return false; }
+    count = (std::size_t)n;
+    return true;
+}
+
+bool saveAKAZEBin(const std::string &filename, const uint8_t *rows, std::size_t count, std::size_t width) {
+    std::ofstream f(filename, std::ios::binary);
+    if (!f.is_open()) return false;
+    const uint64_t n = count;
+    f.write(reinterpret_cast<const char *>(&n), sizeof n);
+    uint8_t row[64];
+    const std::size_t w = width < 64 ? width : 64;
+    for (std::size_t i = 0; i < count; ++i) {
+        memcpy(row, rows + i * width, w);
+        if (w < 64) memset(row + w, 0, 64 - w);
+        f.write(reinterpret_cast<const char *>(row), 64);
+    }
+    return (bool)f;
+}
+
+bool exportPairWiseMatches(const PairWiseMatches &matches, const std::string &filename) {
+    std::ofstream f(filename);
+    if (!f.is_open()) return false;
+    for (const auto &kv : matches) {
+        f << kv.first.first << ' ' << kv.first.second << '\n' << kv.second.size() << '\n';
+        for (const IndMatch &m : kv.second) f << m.i_ << ' ' << m.j_ << '\n';
+    }
+    return (bool)f;
+}
+
+bool importPairWiseMatches(const std::string &filename, PairWiseMatches &matches) {
+    std::ifstream f(filename);
+    if (!f.is_open()) return false;
+    std::size_t I, J, n;
+    while (f >> I >> J >> n) {
+        IndMatches v(n);
+        for (std::size_t k = 0; k < n; ++k)
+            if (!(f >> v[k].i_ >> v[k].j_)) return false;
+        matches[Pair(I, J)] = v;
+    }
+    return true;
+}
+
+bool readPairFile(const std::string &filename, std::vector<Pair> &pairs) {
+    std::ifstream f(filename);
+    if (!f.is_open()) return false;
+    std::size_t a, b;
+    while (f >> a >> b) pairs.push_back(Pair(a, b));
+    return true;
+}
+
+bool readViewsFromList(const std::string &filename, Views &views) {
+    std::ifstream f(filename);
+    if (!f.is_open()) return false;
+    std::size_t id;
+    std::string path;
+    while (f >> id >> path) views[id] = View{id, path};
+    return true;
+}
+
+// Minimal scanner: inside the "views" array every element carries "filename": "<path>" and
+// "id_view": <n> (cereal writes filename first).  Stops at the "intrinsics" key.
+bool readViewsFromSfmData(const std::string &sfm_data_json, Views &views) {
+    std::ifstream f(sfm_data_json);
+    if (!f.is_open()) return false;
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string s = ss.str();
+    std::size_t pos = s.find("\"views\"");
+    if (pos == std::string::npos) return false;
+    const std::size_t end = s.find("\"intrinsics\"", pos);
+    for (;;) {
+        std::size_t kf = s.find("\"filename\"", pos);
+        if (kf == std::string::npos || (end != std::string::npos && kf > end)) break;
+        std::size_t q0 = s.find('"', s.find(':', kf) + 1);
+        std::size_t q1 = s.find('"', q0 + 1);
+        if (q0 == std::string::npos || q1 == std::string::npos) return false;
+        const std::string path = s.substr(q0 + 1, q1 - q0 - 1);
+        std::size_t ki = s.find("\"id_view\"", q1);
+        if (ki == std::string::npos) return false;
+        const std::size_t id = (std::size_t)std::strtoull(s.c_str() + s.find(':', ki) + 1, nullptr, 10);
+        views[id] = View{id, path};
+        pos = ki + 9;
+    }
+    return !views.empty();
+}
+
+std::string descPath(const std::string &dir, const std::string &img_path, bool strip_extension) {
+    std::string base = img_path;
+    const std::size_t slash = base.find_last_of("/\\");
+    if (slash != std::string::npos) base = base.substr(slash + 1);
+    if (strip_extension) {
+        const std::size_t dot = base.find_last_of('.');
+        if (dot != std::string::npos && dot != 0) base = base.substr(0, dot);
+    }
+    std::string d = dir;
+    if (!d.empty() && d.back() != '/') d += '/';
+    return d + base + ".desc";
+}
+
+}  // namespace hulo

@@ -1,0 +1,115 @@
+// host_capi.cpp -- a small extern "C" surface over the C++ host layer so the CPU test-suite can
+// exercise the parts that need no GPU (file formats, pair lists, track propagation) through
+// ctypes.  Not part of the drop-in boundary (that is include/hulo_gpu.h).
+#include <cstring>
+
+#include "desc_files.h"
+#include "match_utils_gpu.h"
+#include "pair_lists.h"
+
+using namespace hulo;
+
+extern "C" {
+
+// .desc round trip: returns row count or -1
+long long hulo_host_read_desc(const char *path, unsigned char *rows64, unsigned long long cap_rows) {
+    std::vector<uint8_t> r;
+    std::size_t n = 0;
+    if (!readAKAZEBin(path, r, n)) return -1;
+    if (rows64 && n <= cap_rows) memcpy(rows64, r.data(), r.size());
+    return (long long)n;
+}
+int hulo_host_write_desc(const char *path, const unsigned char *rows, unsigned long long n, unsigned long long width) {
+    return saveAKAZEBin(path, rows, (std::size_t)n, (std::size_t)width) ? 0 : 1;
+}
+
+// pair generators over views with ids 0..n-1 (or arbitrary ids given): out holds 2 * cap entries
+static Views make_views(const unsigned long long *ids, unsigned long long n) {
+    Views v;
+    for (unsigned long long k = 0; k < n; ++k) v[(std::size_t)ids[k]] = View{(std::size_t)ids[k], ""};
+    return v;
+}
+static unsigned long long emit(const std::vector<Pair> &p, unsigned long long *out, unsigned long long cap) {
+    for (std::size_t k = 0; k < p.size() && k < cap; ++k) { out[2 * k] = p[k].first; out[2 * k + 1] = p[k].second; }
+    return p.size();
+}
+unsigned long long hulo_host_all_pairs(const unsigned long long *ids, unsigned long long n, unsigned long long *out,
+                                       unsigned long long cap) {
+    std::vector<Pair> p;
+    generateAllPairs(make_views(ids, n), p);
+    return emit(p, out, cap);
+}
+unsigned long long hulo_host_video_pairs(const unsigned long long *ids, unsigned long long n, int frame,
+                                         unsigned long long *out, unsigned long long cap) {
+    std::vector<Pair> p;
+    generateVideoMatchPairs(make_views(ids, n), p, frame);
+    return emit(p, out, cap);
+}
+unsigned long long hulo_host_remove_dup_pairs(unsigned long long *pairs, unsigned long long n) {
+    std::vector<Pair> p;
+    for (unsigned long long k = 0; k < n; ++k) p.push_back(Pair(pairs[2 * k], pairs[2 * k + 1]));
+    removeDupPairs(p);
+    return emit(p, pairs, n);
+}
+// positions of `rank`'s pairs; rows[v] = descriptor count of view v (ids 0..n_views-1)
+unsigned long long hulo_host_partition_pairs(const unsigned long long *pairs, unsigned long long n,
+                                             const unsigned long long *rows, unsigned long long n_views, int rank,
+                                             int world, unsigned long long *out_pos) {
+    std::vector<Pair> p;
+    for (unsigned long long k = 0; k < n; ++k) p.push_back(Pair(pairs[2 * k], pairs[2 * k + 1]));
+    std::map<std::size_t, std::size_t> r;
+    for (unsigned long long v = 0; v < n_views; ++v) r[(std::size_t)v] = (std::size_t)rows[v];
+    const std::vector<std::size_t> mine = partitionPairs(p, r, rank, world);
+    for (std::size_t k = 0; k < mine.size(); ++k) out_pos[k] = mine[k];
+    return mine.size();
+}
+
+// track propagation: consecutive matches in (m_off, m_i, m_j) form -> appended (f, to, i, j)
+unsigned long long hulo_host_propagate_tracks(unsigned long long n_frames, unsigned long long max_frame_dist,
+                                              const int *feat_number, const long long *m_off, const int *m_i,
+                                              const int *m_j, int *out4, unsigned long long cap) {
+    PairWiseMatches m;
+    std::vector<int> fn(feat_number, feat_number + (n_frames ? n_frames - 1 : 0));
+    for (unsigned long long f = 0; f + 1 < n_frames; ++f)
+        for (long long k = m_off[f]; k < m_off[f + 1]; ++k)
+            m[Pair(f, f + 1)].push_back(IndMatch((uint32_t)m_i[k], (uint32_t)m_j[k]));
+    propagateTracks((std::size_t)n_frames, (std::size_t)max_frame_dist, fn, m);
+    unsigned long long n = 0;
+    for (const auto &kv : m) {
+        if (kv.first.second == kv.first.first + 1) continue;
+        for (const IndMatch &im : kv.second) {
+            if (n < cap) {
+                out4[4 * n] = (int)kv.first.first; out4[4 * n + 1] = (int)kv.first.second;
+                out4[4 * n + 2] = (int)im.i_; out4[4 * n + 3] = (int)im.j_;
+            }
+            ++n;
+        }
+    }
+    return n;
+}
+
+// match file round trip through the C++ writer / reader: returns number of pairs read back
+long long hulo_host_matches_roundtrip(const char *in_path, const char *out_path) {
+    PairWiseMatches m;
+    if (!importPairWiseMatches(in_path, m)) return -1;
+    if (!exportPairWiseMatches(m, out_path)) return -2;
+    return (long long)m.size();
+}
+
+long long hulo_host_views_from_sfm_data(const char *path, unsigned long long *ids, char *names, unsigned long long cap,
+                                        unsigned long long name_stride) {
+    Views v;
+    if (!readViewsFromSfmData(path, v)) return -1;
+    unsigned long long k = 0;
+    for (const auto &kv : v) {
+        if (k < cap) {
+            ids[k] = kv.first;
+            strncpy(names + k * name_stride, kv.second.s_Img_path.c_str(), name_stride - 1);
+            names[k * name_stride + name_stride - 1] = 0;
+        }
+        ++k;
+    }
+    return (long long)k;
+}
+
+}  // extern "C"

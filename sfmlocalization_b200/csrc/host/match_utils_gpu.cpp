@@ -1,0 +1,211 @@
+#include "match_utils_gpu.h"
+
+#include <algorithm>
+#include <iostream>
+#include <stdexcept>
+
+#include "../../../include/hulo_gpu.h"
+#include "desc_files.h"
+
+namespace hulo {
+
+namespace {
+void must(int status, const char *what) {
+    if (status != HULO_OK) throw std::runtime_error(std::string(what) + ": " + hulo_last_error());
+}
+}  // namespace
+
+struct GpuSession::State {
+    hulo_gpu *gpu = nullptr;
+    std::map<std::string, std::shared_ptr<Table>> cache;
+    ~State() {
+        for (auto &kv : cache)
+            if (kv.second && kv.second->db) hulo_db_free(kv.second->db);
+        if (gpu) hulo_gpu_destroy(gpu);
+    }
+};
+
+GpuSession::GpuSession(int device) : st_(std::make_shared<State>()) {
+    must(hulo_gpu_create(device, &st_->gpu), "hulo_gpu_create");
+}
+hulo_gpu *GpuSession::gpu() const { return st_->gpu; }
+
+void GpuSession::clearCache() {
+    for (auto &kv : st_->cache)
+        if (kv.second && kv.second->db) hulo_db_free(kv.second->db);
+    st_->cache.clear();
+}
+
+std::shared_ptr<GpuSession::Table> GpuSession::table(const Views &views, const std::string &sMatchesDir,
+                                                     const std::vector<std::size_t> &view_ids) {
+    std::string key = sMatchesDir + "|";
+    for (std::size_t v : view_ids) key += std::to_string(v) + ",";
+    auto it = st_->cache.find(key);
+    if (it != st_->cache.end()) return it->second;
+    auto t = std::make_shared<Table>();
+    std::vector<uint8_t> all, rows;
+    std::vector<uint64_t> off(1, 0);
+    for (std::size_t v : view_ids) {
+        std::size_t n = 0;
+        // an unreadable file behaves as an image without descriptors
+        readAKAZEBin(descPath(sMatchesDir, views.at(v).s_Img_path, true), rows, n);
+        all.insert(all.end(), rows.begin(), rows.end());
+        off.push_back(off.back() + n);
+        t->seg_of_view[v] = (uint32_t)t->view_ids.size();
+        t->rows_of_view[v] = n;
+        t->view_ids.push_back(v);
+    }
+    static const uint8_t none = 0;
+    must(hulo_db_upload(st_->gpu, all.empty() ? &none : all.data(), (std::size_t)off.back(), HULO_ROW_BYTES,
+                        off.data(), view_ids.size(), &t->db),
+         "hulo_db_upload");
+    st_->cache[key] = t;
+    return t;
+}
+
+GpuSession &defaultSession() {
+    static GpuSession s(0);
+    return s;
+}
+
+// ------------------------------------------------------------------ matchAKAZE
+static void match_pair_list(GpuSession &s, const Views &views, const std::string &sMatchesDir,
+                            const std::vector<Pair> &pairs, float fDistRatio, PairWiseMatches &matches,
+                            std::map<std::size_t, std::size_t> *rows_of_view) {
+    std::vector<std::size_t> ids;
+    for (const Pair &p : pairs) { ids.push_back(p.first); ids.push_back(p.second); }
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    auto t = s.table(views, sMatchesDir, ids);
+    if (rows_of_view) *rows_of_view = t->rows_of_view;
+    std::vector<uint32_t> seg_pairs(2 * pairs.size());
+    for (std::size_t k = 0; k < pairs.size(); ++k) {
+        seg_pairs[2 * k] = t->seg_of_view.at(pairs[k].first);
+        seg_pairs[2 * k + 1] = t->seg_of_view.at(pairs[k].second);
+    }
+    std::vector<uint64_t> off(pairs.size() + 1, 0);
+    std::vector<uint32_t> oi(1), oj(1);
+    std::size_t n = 0;
+    int rc = hulo_match_pairs(s.gpu(), t->db, seg_pairs.data(), pairs.size(), fDistRatio, HULO_PAIR_REFERENCE,
+                              off.data(), oi.data(), oj.data(), 0, &n);
+    if (rc == HULO_ERR_CAPACITY) {
+        oi.resize(n); oj.resize(n);
+        rc = hulo_match_pairs(s.gpu(), t->db, seg_pairs.data(), pairs.size(), fDistRatio, HULO_PAIR_REFERENCE,
+                              off.data(), oi.data(), oj.data(), n, &n);
+    }
+    must(rc, "hulo_match_pairs");
+    for (std::size_t k = 0; k < pairs.size(); ++k) {
+        // a pair without a surviving match never gets a key (insertion happens on push_back,
+        // MatchUtils.cpp:148); a pair listed twice appends twice, as the reference does
+        for (uint64_t m = off[k]; m < off[k + 1]; ++m) matches[pairs[k]].push_back(IndMatch(oi[m], oj[m]));
+    }
+}
+
+void matchAKAZE(GpuSession &s, const Views &views, const std::string &sMatchesDir, const std::vector<Pair> &pairs,
+                const float fDistRatio, PairWiseMatches &matches) {
+    std::cout << "Start putative matching" << std::endl;
+    match_pair_list(s, views, sMatchesDir, pairs, fDistRatio, matches, nullptr);
+}
+
+// ------------------------------------------------------------------ trackAKAZE
+void propagateTracks(std::size_t n_frames, std::size_t maxFrameDist, const std::vector<int> &feat_number,
+                     PairWiseMatches &matches) {
+    if (n_frames < 2) return;
+    std::vector<std::vector<int>> trackPointer(n_frames - 1);
+    for (std::size_t f = 0; f + 1 < n_frames; ++f) {
+        trackPointer[f].assign((std::size_t)feat_number[f], -1);
+        // operator[] on purpose: the reference creates the (f, f+1) key here when it is absent
+        for (const IndMatch &m : matches[Pair(f, f + 1)]) trackPointer[f][m.i_] = (int)m.j_;
+    }
+    for (std::size_t f = 0; f + 1 < n_frames; ++f) {
+        const std::size_t lim = std::min(f + maxFrameDist, n_frames);
+        for (std::size_t to = f + 2; to < lim; ++to) {
+            for (std::size_t i = 0; i < trackPointer[f].size(); ++i) {
+                const int t = trackPointer[f][i];
+                if (t == -1) continue;
+                const int nx = trackPointer[to - 1][(std::size_t)t];
+                trackPointer[f][i] = nx;
+                if (nx != -1) matches[Pair(f, to)].push_back(IndMatch((uint32_t)i, (uint32_t)nx));
+            }
+        }
+    }
+}
+
+void trackAKAZE(GpuSession &s, const Views &views, const std::string &sMatchesDir, const std::size_t maxFrameDist,
+                const float fDistRatio, PairWiseMatches &matches) {
+    std::cout << "Start putative matching" << std::endl;
+    if (views.size() < 2) return;
+    // consecutive frames: (id, id + 1) for every view but the last in map order (:164-237);
+    // like the reference this assumes consecutive view ids starting at 0
+    std::vector<Pair> pairs;
+    std::size_t k = 0;
+    for (auto it = views.begin(); k + 1 < views.size(); ++it, ++k) pairs.push_back(Pair(it->first, it->first + 1));
+    std::map<std::size_t, std::size_t> rows_of_view;
+    match_pair_list(s, views, sMatchesDir, pairs, fDistRatio, matches, &rows_of_view);
+    std::vector<int> feat_number(views.size() - 1, 0);
+    for (const Pair &p : pairs)
+        if (p.first < feat_number.size()) feat_number[p.first] = (int)rows_of_view[p.first];   // :183
+    propagateTracks(views.size(), maxFrameDist, feat_number, matches);
+}
+
+// ------------------------------------------------------------------ matchAKAZEToQuery
+void matchAKAZEToQuery(GpuSession &s, const Views &views, const std::string &sMatchesDir,
+                       const std::string &sQueryMatchesDir, const std::vector<std::size_t> &pairs,
+                       const std::size_t queryInd, const float fDistRatio, PairWiseMatches &matches,
+                       FeatDistMap &featDist) {
+    std::cout << "Start putative matching" << std::endl;
+    std::vector<uint8_t> q;
+    std::size_t nq = 0;
+    // the query descriptor file is named by s_Img_path itself, not its basename part (:295)
+    readAKAZEBin(descPath(sQueryMatchesDir, views.at(queryInd).s_Img_path, false), q, nq);
+    if (nq < 1) return;                                                            // :299-301
+    for (std::size_t v : pairs) matches.insert(std::make_pair(Pair(v, queryInd), IndMatches()));   // :314-319
+
+    // the resident table holds every map view (all but the query); `pairs` selects segments
+    std::vector<std::size_t> ids;
+    for (const auto &kv : views)
+        if (kv.first != queryInd) ids.push_back(kv.first);
+    auto t = s.table(views, sMatchesDir, ids);
+    std::vector<uint32_t> segs(pairs.size());
+    std::size_t total_rows = 0;
+    for (std::size_t k = 0; k < pairs.size(); ++k) {
+        segs[k] = t->seg_of_view.at(pairs[k]);
+        total_rows += t->rows_of_view.at(pairs[k]);
+    }
+    const std::size_t cap = std::max<std::size_t>(total_rows, 1);
+    std::vector<uint32_t> ov(cap), oi(cap), oj(cap), counts(std::max<std::size_t>(pairs.size(), 1));
+    std::vector<int32_t> od(cap);
+    std::size_t n = 0;
+    must(hulo_match_to_query(s.gpu(), t->db, segs.data(), pairs.size(), q.data(), nq, HULO_ROW_BYTES, fDistRatio,
+                             ov.data(), oi.data(), oj.data(), od.data(), cap, &n, counts.data()),
+         "hulo_match_to_query");
+    std::size_t m = 0;
+    for (std::size_t k = 0; k < pairs.size(); ++k) {
+        const Pair key(pairs[k], queryInd);
+        IndMatches ind;
+        std::map<std::size_t, int> fd;
+        for (uint32_t c = 0; c < counts[k]; ++c, ++m) {
+            ind.push_back(IndMatch(oi[m], oj[m]));
+            fd[oj[m]] = od[m];                                                     // last i wins, :351
+        }
+        matches[key] = ind;                                                        // :358
+        featDist[key] = fd;                                                        // :359
+    }
+}
+
+// ------------------------------------------------------------------ default-session overloads
+void matchAKAZE(const Views &views, const std::string &d, const std::vector<Pair> &pairs, const float r,
+                PairWiseMatches &m) {
+    matchAKAZE(defaultSession(), views, d, pairs, r, m);
+}
+void trackAKAZE(const Views &views, const std::string &d, const std::size_t maxFrameDist, const float r,
+                PairWiseMatches &m) {
+    trackAKAZE(defaultSession(), views, d, maxFrameDist, r, m);
+}
+void matchAKAZEToQuery(const Views &views, const std::string &d, const std::string &qd,
+                       const std::vector<std::size_t> &pairs, const std::size_t queryInd, const float r,
+                       PairWiseMatches &m, FeatDistMap &fd) {
+    matchAKAZEToQuery(defaultSession(), views, d, qd, pairs, queryInd, r, m, fd);
+}
+
+}  // namespace hulo

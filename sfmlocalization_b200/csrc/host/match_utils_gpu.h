@@ -1,0 +1,71 @@
+// match_utils_gpu.h -- the reference's putative-matching entry points
+// (VisionLocalizeCommon/src/MatchUtils.h:39-61) on top of the C-ABI of libhulo_gpu.so.
+// Same names, argument order, argument meaning and result containers; SfM_Data is replaced by
+// the view list the functions actually read from it (hulo_types.h).  Error behaviour follows
+// the reference: the functions return void, unreadable descriptor files behave as empty
+// images; a CUDA / library failure throws std::runtime_error (the reference has no equivalent
+// because its matcher cannot fail).
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "hulo_types.h"
+
+struct hulo_gpu;
+struct hulo_db;
+
+namespace hulo {
+
+// Owns the device context and the descriptor tables kept resident between calls -- the state
+// the reference lacks: it re-reads every view's .desc file on every query
+// (MatchUtils.cpp:328-332).  Copyable handle (shared state), so it can live inside a
+// LocalizeEngine that is stored by value (localizeImage.cc:100).
+class GpuSession {
+public:
+    explicit GpuSession(int device = 0);
+    hulo_gpu *gpu() const;
+    // Descriptor table of the given views read from sMatchesDir (cached per directory + view set).
+    struct Table {
+        hulo_db *db = nullptr;
+        std::vector<std::size_t> view_ids;          // segment s holds view view_ids[s]
+        std::map<std::size_t, uint32_t> seg_of_view;
+        std::map<std::size_t, std::size_t> rows_of_view;
+    };
+    std::shared_ptr<Table> table(const Views &views, const std::string &sMatchesDir,
+                                 const std::vector<std::size_t> &view_ids);
+    void clearCache();
+    struct State;
+private:
+    std::shared_ptr<State> st_;
+};
+GpuSession &defaultSession();
+
+// hulo::matchAKAZE, MatchUtils.cpp:73-152
+void matchAKAZE(const Views &views, const std::string &sMatchesDir, const std::vector<Pair> &pairs,
+                const float fDistRatio, PairWiseMatches &matches);
+// hulo::trackAKAZE, MatchUtils.cpp:156-277
+void trackAKAZE(const Views &views, const std::string &sMatchesDir, const std::size_t maxFrameDist,
+                const float fDistRatio, PairWiseMatches &matches);
+// hulo::matchAKAZEToQuery, MatchUtils.cpp:283-367
+void matchAKAZEToQuery(const Views &views, const std::string &sMatchesDir, const std::string &sQueryMatchesDir,
+                       const std::vector<std::size_t> &pairs, const std::size_t queryInd, const float fDistRatio,
+                       PairWiseMatches &matches, FeatDistMap &featDist);
+
+// the same three against an explicit session (several GPUs, tests)
+void matchAKAZE(GpuSession &s, const Views &views, const std::string &sMatchesDir, const std::vector<Pair> &pairs,
+                const float fDistRatio, PairWiseMatches &matches);
+void trackAKAZE(GpuSession &s, const Views &views, const std::string &sMatchesDir, const std::size_t maxFrameDist,
+                const float fDistRatio, PairWiseMatches &matches);
+void matchAKAZEToQuery(GpuSession &s, const Views &views, const std::string &sMatchesDir,
+                       const std::string &sQueryMatchesDir, const std::vector<std::size_t> &pairs,
+                       const std::size_t queryInd, const float fDistRatio, PairWiseMatches &matches,
+                       FeatDistMap &featDist);
+
+// Track propagation half of trackAKAZE (MatchUtils.cpp:239-276): extends consecutive-frame
+// matches (f, f+1) to pairs (f, f+2 .. f+maxFrameDist-1).  n_frames = number of views,
+// feat_number[f] = descriptor count of frame f (f < n_frames - 1).
+void propagateTracks(std::size_t n_frames, std::size_t maxFrameDist, const std::vector<int> &feat_number,
+                     PairWiseMatches &matches);
+
+}  // namespace hulo

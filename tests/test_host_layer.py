@@ -1,0 +1,114 @@
+"""CPU suite for the C++ host layer above the C-ABI (csrc/host): file formats, pair lists,
+pair-list sharding, track propagation.  None of this needs a GPU."""
+import json
+import os
+
+import numpy as np
+
+from sfmlocalization_b200 import synth
+from tests import hostlib
+
+
+def test_desc_file_round_trip(tmp_path):
+    rows61 = np.ascontiguousarray(synth.random_rows(37, 1)[:, :61])
+    p = str(tmp_path / "a.desc")
+    assert hostlib.write_desc(p, rows61) == 0                 # saveAKAZEBin pads 61 -> 64
+    raw = open(p, "rb").read()
+    assert len(raw) == 8 + 37 * 64 and int(np.frombuffer(raw[:8], np.uint64)[0]) == 37
+    back = hostlib.read_desc(p)
+    assert back.shape == (37, 64) and np.array_equal(back[:, :61], rows61) and (back[:, 61:] == 0).all()
+    q = str(tmp_path / "b.desc")
+    hostlib.write_desc_numpy(q, rows61)                       # independent writer, same bytes
+    assert open(q, "rb").read() == raw
+    hostlib.write_desc_numpy(q, np.zeros((0, 64), np.uint8))
+    assert hostlib.read_desc(q).shape == (0, 64)
+    assert hostlib.read_desc(str(tmp_path / "missing.desc")) is None
+
+
+def test_pair_generators():
+    ids = [0, 1, 2, 5, 9]
+    want = [(a, b) for k, a in enumerate(ids) for b in ids[k + 1:]]
+    assert hostlib.all_pairs(ids).tolist() == [list(p) for p in want]
+    want_v = [(ids[a], ids[b]) for a in range(5) for b in range(a + 1, min(5, a + 3))]
+    assert hostlib.video_pairs(ids, 2).tolist() == [list(p) for p in want_v]
+    assert len(hostlib.video_pairs(ids, 0)) == 0
+
+
+def ref_remove_dup(pairs):
+    """python restatement of SfMDataUtils.cpp:168-190 (in-place normalisation included)."""
+    pairs = [list(p) for p in pairs]
+    dup = []
+    for i in range(len(pairs) - 1, 0, -1):
+        for j in range(i - 1, -1, -1):
+            if pairs[j][0] > pairs[j][1]:
+                pairs[j] = [pairs[j][1], pairs[j][0]]
+            if pairs[i] == pairs[j] or pairs[i] == [pairs[j][1], pairs[j][0]]:
+                dup.append(i)
+                break
+    for d in dup:
+        del pairs[d]
+    return pairs
+
+
+def test_remove_dup_pairs_matches_reference_algorithm():
+    rng = np.random.default_rng(4)
+    for _ in range(20):
+        p = rng.integers(0, 6, size=(rng.integers(1, 25), 2))
+        assert hostlib.remove_dup_pairs(p).tolist() == ref_remove_dup(p.tolist())
+
+
+def test_partition_pairs_covers_and_balances():
+    rng = np.random.default_rng(5)
+    rows = rng.integers(500, 6000, size=40)
+    pairs = [(a, b) for a in range(40) for b in range(a + 1, 40)]
+    cost = np.array([rows[a] * rows[b] for a, b in pairs], np.float64)
+    for world in (2, 3, 8):
+        parts = [hostlib.partition_pairs(pairs, rows, r, world) for r in range(world)]
+        allpos = np.sort(np.concatenate(parts))
+        assert np.array_equal(allpos, np.arange(len(pairs)))             # every pair exactly once
+        loads = np.array([cost[p].sum() for p in parts])
+        assert loads.max() / loads.mean() < 1.02                         # balanced by n_I * n_J
+        assert all((np.diff(p) > 0).all() for p in parts)
+    assert np.array_equal(hostlib.partition_pairs(pairs, rows, 0, 1), np.arange(len(pairs)))
+
+
+def test_track_propagation_matches_oracle(orc):
+    rng = np.random.default_rng(6)
+    V, n = 7, 40
+    feat = [n] * (V - 1)
+    m_off, m_i, m_j = [0], [], []
+    for f in range(V - 1):
+        src = np.sort(rng.choice(n, size=25, replace=False)); dst = rng.permutation(n)[:25]
+        m_i += src.tolist(); m_j += dst.tolist(); m_off.append(len(m_i))
+    for max_dist in (2, 3, 5, 20):
+        got = hostlib.propagate_tracks(V, max_dist, feat, m_off, m_i, m_j)
+        f, t, i, j = orc.track_propagate(V, max_dist, feat, m_off, m_i, m_j)
+        want = sorted(zip(f.tolist(), t.tolist(), i.tolist(), j.tolist()), key=lambda r: (r[0], r[1]))
+        # the C++ layer returns map order (pair ascending), inside a pair emission order
+        assert [tuple(r) for r in got.tolist()] == want
+
+
+def test_match_file_round_trip(tmp_path):
+    src = tmp_path / "in.txt"
+    src.write_text("0 1\n2\n3 4\n5 6\n0 2\n0\n7 9\n1\n10 11\n")
+    dst = tmp_path / "out.txt"
+    assert hostlib.lib().hulo_host_matches_roundtrip(str(src).encode(), str(dst).encode()) == 3
+    assert hostlib.parse_matches(str(dst)) == {(0, 1): [(3, 4), (5, 6)], (0, 2): [], (7, 9): [(10, 11)]}
+    assert dst.read_text() == src.read_text()
+
+
+def test_views_from_sfm_data_json(tmp_path):
+    views = [{"key": k, "value": {"polymorphic_id": 1073741824, "ptr_wrapper": {"id": 2147483649 + k, "data": {
+        "local_path": "/", "filename": "img%03d.jpg" % (3 * k), "width": 1920, "height": 1080, "id_view": k,
+        "id_intrinsic": 0, "id_pose": k}}}} for k in range(5)]
+    doc = {"sfm_data_version": "0.2", "root_path": "/data", "views": views,
+           "intrinsics": [{"key": 0, "value": {"filename": "not-a-view", "id_view": 99}}], "extrinsics": []}
+    p = tmp_path / "sfm_data.json"
+    p.write_text(json.dumps(doc, indent=4))
+    import ctypes as C
+    ids = np.zeros(16, np.uint64); names = np.zeros((16, 64), np.uint8)
+    n = hostlib.lib().hulo_host_views_from_sfm_data(str(p).encode(), ids.ctypes.data_as(C.c_void_p),
+                                                    names.ctypes.data_as(C.c_void_p), C.c_ulonglong(16),
+                                                    C.c_ulonglong(64))
+    assert n == 5 and ids[:5].tolist() == [0, 1, 2, 3, 4]
+    assert bytes(names[2]).split(b"\0")[0] == b"img006.jpg"

@@ -1,0 +1,83 @@
+#!/usr/bin/env python
+"""Secondary measurements on one B200 for the other BASELINE.json configs (bench.py carries the
+headline C3 line).  Prints one JSON object per config; run under gpurun and keep the output in
+profiles/.  Timing: CUDA events on the library stream (hulo_timer_*), 1 warm-up + N timed steps."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sfmlocalization_b200 import synth  # noqa: E402
+from sfmlocalization_b200.gpu import HuloGpu  # noqa: E402
+
+
+def timed(g, fn, steps):
+    fn()
+    g.synchronize()
+    g.timer_start()
+    for _ in range(steps):
+        fn()
+    return g.timer_stop() / steps
+
+
+def flat(g, name, nA, nB, seed, steps=3):
+    A, B, _ = synth.descriptor_sets(nA, nB, seed)
+    dA, dB = g.db(A), g.db(B)
+    ms = timed(g, lambda: g.knn2(dA, dB, fetch=False), steps)
+    dA.free(); dB.free()
+    print(json.dumps({"config": name, "nA": nA, "nB": nB, "ms": ms, "gdist_per_s": nA * nB / ms / 1e6}), flush=True)
+
+
+def pairs(g, name, n_img, rows, n_pairs, seed):
+    allrows, off = synth.image_collection(n_img, rows, seed, overlap=0.3)
+    db = g.db(allrows, off)
+    pl = [(a, b) for a in range(n_img) for b in range(a + 1, n_img)][:n_pairs]
+    g.match_pairs(db, pl[:64], 0.7)
+    t0 = time.perf_counter()
+    off_, oi, oj = g.match_pairs(db, pl, 0.7, cap=len(pl) * rows)
+    dt = time.perf_counter() - t0
+    db.free()
+    dist = len(pl) * rows * rows
+    print(json.dumps({"config": name, "images": n_img, "rows": rows, "pairs": len(pl), "wall_ms": dt * 1e3,
+                      "gdist_per_s_wall": dist / dt / 1e9, "matches": int(len(oi)),
+                      "note": "wall clock of hulo_match_pairs incl. item list upload, post filters, D2H"}), flush=True)
+
+
+def scoring(g, name, H, N, seed):
+    sc = synth.resection_scene(N, seed, outlier_frac=0.5)
+    tri = synth.sample_triplets(N, H // 4, seed)
+    models, nm = g.p3p(tri, sc["x2d"], sc["X3d"], sc["K"])
+    models = models.reshape(-1, 3, 4)
+    g.score_resection(models[:64], sc["x2d"], sc["X3d"], sc["K"])
+    t0 = time.perf_counter()
+    g.score_resection(models, sc["x2d"], sc["X3d"], sc["K"])
+    dt = time.perf_counter() - t0
+    print(json.dumps({"config": name, "hypotheses": int(models.shape[0]), "N": N, "wall_ms": dt * 1e3,
+                      "hyp_per_s": models.shape[0] / dt,
+                      "note": "wall clock of hulo_score_resection incl. H2D of models and D2H of scores"}), flush=True)
+
+
+def main():
+    which = sys.argv[1:] or ["c1", "c1r", "c2", "c4", "c5", "k2"]
+    with HuloGpu(0) as g:
+        if "c1" in which:
+            flat(g, "C1 query->map 2000 x 200000", 2000, 200000, 1000, steps=20)
+        if "c1r" in which:
+            flat(g, "C1 reference direction 200000 x 2000", 200000, 2000, 1001, steps=20)
+        if "c2" in which:
+            pairs(g, "C2 pairwise 200 x 5000 (first 2000 of 19900 pairs)", 200, 5000, 2000, 2000)
+        if "c4" in which:
+            flat(g, "C4 768000 x 2000000", 768000, 2000000, 4000, steps=1)
+        if "c5" in which:
+            flat(g, "C5 one of 8 shards: 16384 x 6250000", 16384, 6250000, 5000, steps=2)
+        if "k2" in which:
+            for N in (100, 500, 2000):
+                scoring(g, "K2 scoring 4096 triplets x <=4 models", 16384, N, 4000 + N)
+
+
+if __name__ == "__main__":
+    main()

@@ -39,8 +39,8 @@ static int env_int(const char *name, int dflt) {
 static KnnConfig choose_config(const hulo_gpu *h, size_t nA) {
     if (h->knn_cfg_forced) return h->knn_cfg;
     KnnConfig c = h->knn_cfg;
-    if (nA <= 512) c = KnnConfig{128, 4, 7};
-    else if (nA <= 1024) c = KnnConfig{256, 4, 7};
+    if (nA <= 512) c = KnnConfig{128, 4, 7, 0};
+    else if (nA <= 1024) c = KnnConfig{256, 4, 8, 3};
     return c;
 }
 
@@ -109,6 +109,7 @@ static int run_flat(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size
         kp.nA = (uint32_t)nA; kp.nB = (uint32_t)nB;
         kp.n_tiles = pl.n_tiles; kp.rows_per_chunk = pl.rows_per_chunk;
         kp.slot_stride = pl.slot_stride;
+        kp.key_unit = 1u << kKeyIdxBits;
         kp.partial = h->partial.as<uint2>();
         kp.counter = h->counter.as<unsigned int>();
         HULO_CUDA(knn2_launch(kp, pl.cfg, pl.grid, h->stream));
@@ -186,15 +187,17 @@ int hulo_gpu_create(int device, hulo_gpu **out) {
     HULO_CUDA(cudaEventCreate(&h->ev_stop));
     // tuning overrides (benchmark sweeps): HULO_KNN_THREADS / HULO_KNN_QPT / HULO_KNN_CSA
     const int t = env_int("HULO_KNN_THREADS", 0), q = env_int("HULO_KNN_QPT", 0), c = env_int("HULO_KNN_CSA", -1);
-    if (t > 0 || q > 0 || c >= 0) {
+    const int o = env_int("HULO_KNN_OPT", -1);
+    if (t > 0 || q > 0 || c >= 0 || o >= 0) {
         if (t > 0) h->knn_cfg.threads = t;
         if (q > 0) h->knn_cfg.qpt = q;
         if (c >= 0) h->knn_cfg.csa = c;
+        if (o >= 0) h->knn_cfg.opt = o;
         h->knn_cfg_forced = true;
         if (knn2_kernel_info(h->knn_cfg, nullptr, nullptr, nullptr) != cudaSuccess) {
             cudaGetLastError();
-            set_error("hulo_gpu_create: no K1 variant threads=%d qpt=%d csa=%d", h->knn_cfg.threads,
-                      h->knn_cfg.qpt, h->knn_cfg.csa);
+            set_error("hulo_gpu_create: no K1 variant threads=%d qpt=%d csa=%d opt=%d", h->knn_cfg.threads,
+                      h->knn_cfg.qpt, h->knn_cfg.csa, h->knn_cfg.opt);
             hulo_gpu_destroy(h);
             return HULO_ERR_ARG;
         }
@@ -455,6 +458,7 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     kp.A = map->rows; kp.B = h->stageB.as<uint4>();
     kp.items = h->items.as<KnnItem>();
     kp.n_items = (uint32_t)items.size();
+    kp.key_unit = 1u << kKeyIdxBits;
     kp.partial = h->partial.as<uint2>();
     kp.counter = h->counter.as<unsigned int>();
     HULO_CUDA(knn2_launch(kp, cfg, grid, h->stream));
@@ -513,7 +517,7 @@ int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size
         HULO_ARG(pairs[2 * p] < n_seg && pairs[2 * p + 1] < n_seg, "pair refers to a segment that does not exist");
     if (pair_offsets) pair_offsets[0] = 0;
 
-    const KnnConfig cfg = h->knn_cfg_forced ? h->knn_cfg : KnnConfig{256, 4, 7};
+    const KnnConfig cfg = h->knn_cfg_forced ? h->knn_cfg : KnnConfig{256, 4, 8, 3};   // 1024-row tiles fit 5000-row images with 2 % waste
     const uint32_t tile = knn2_tile_rows(cfg);
     int ctas_per_sm = 1;
     knn2_kernel_info(cfg, nullptr, &ctas_per_sm, nullptr);
@@ -581,6 +585,7 @@ int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size
             kp.A = db->rows; kp.B = db->rows;
             kp.items = h->items.as<KnnItem>();
             kp.n_items = (uint32_t)items.size();
+            kp.key_unit = 1u << kKeyIdxBits;
             kp.partial = h->partial.as<uint2>();
             kp.counter = h->counter.as<unsigned int>();
             HULO_CUDA(knn2_launch(kp, cfg, (int)std::min<size_t>((size_t)full_grid, items.size()), h->stream));

@@ -62,18 +62,33 @@ __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
         hi = maj3(a, b, c);       \
     } while (0)
 
-// 512-bit Hamming distance of a register-resident searcher row q and a database row w.
-// CSA = number of carry-save adders applied before the POPCs (0: plain 16 POPC).
-template <int CSA>
-__device__ __forceinline__ uint32_t hamming512(const uint32_t (&q)[16], const uint32_t (&w)[16]) {
+// acc + m * popc(x): the multiply-add runs on the FMA pipe (IMAD), which K1 leaves idle, instead
+// of an IADD3 on the ALU pipe that the XORs and adders saturate.
+__device__ __forceinline__ uint32_t popc_mad(uint32_t x, uint32_t m, uint32_t acc) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"((uint32_t)__popc(x)), "r"(m), "r"(acc));
+    return r;
+}
+
+// key = base + (distance << kKeyIdxBits) for a register-resident searcher row q and a database
+// row w; distance = 512-bit Hamming.  CSA = number of carry-save adders applied before the POPCs
+// (0: plain 16 POPC).  `unit` is 1 << kKeyIdxBits held in a register so ptxas keeps the IMADs.
+template <int CSA, bool IMAD>
+__device__ __forceinline__ uint32_t hamming_key(const uint32_t (&q)[16], const uint32_t (&w)[16], uint32_t base,
+                                                uint32_t unit) {
     uint32_t x[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) x[k] = q[k] ^ w[k];
+    uint32_t n1 = 0, n2 = 0, n4 = 0, n8 = 0;      // counts of weight 1 / 2 / 4 / 8 (plain-add path)
+    uint32_t key = base;                           // IMAD path accumulates straight into the key
+#define HULO_ACC(word, weight, cnt)                                  \
+    do {                                                             \
+        if constexpr (IMAD) key = popc_mad(word, unit * (weight), key); \
+        else cnt += __popc(word);                                    \
+    } while (0)
     if constexpr (CSA == 0) {
-        uint32_t d = 0;
 #pragma unroll
-        for (int k = 0; k < 16; ++k) d += __popc(x[k]);
-        return d;
+        for (int k = 0; k < 16; ++k) HULO_ACC(x[k], 1u, n1);
     } else {
         // level 1: 15 words -> 5 sums (weight 1) + 5 carries (weight 2); x[15] left over
         uint32_t s0, s1, s2, s3, s4, c0, c1, c2, c3, c4;
@@ -83,44 +98,54 @@ __device__ __forceinline__ uint32_t hamming512(const uint32_t (&q)[16], const ui
         HULO_CSA(c3, s3, x[9], x[10], x[11]);
         HULO_CSA(c4, s4, x[12], x[13], x[14]);
         if constexpr (CSA == 5) {
-            uint32_t ones = __popc(s0) + __popc(s1) + __popc(s2) + __popc(s3) + __popc(s4) + __popc(x[15]);
-            uint32_t twos = __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) + __popc(c4);
-            return ones + 2u * twos;
+            HULO_ACC(s0, 1u, n1); HULO_ACC(s1, 1u, n1); HULO_ACC(s2, 1u, n1); HULO_ACC(s3, 1u, n1);
+            HULO_ACC(s4, 1u, n1); HULO_ACC(x[15], 1u, n1);
+            HULO_ACC(c0, 2u, n2); HULO_ACC(c1, 2u, n2); HULO_ACC(c2, 2u, n2); HULO_ACC(c3, 2u, n2);
+            HULO_ACC(c4, 2u, n2);
         } else {
             // level 2: the six weight-1 words -> 2 sums + 2 carries
             uint32_t s5, s6, c5, c6;
             HULO_CSA(c5, s5, s0, s1, s2);
             HULO_CSA(c6, s6, s3, s4, x[15]);
+            HULO_ACC(s5, 1u, n1); HULO_ACC(s6, 1u, n1);
             if constexpr (CSA == 7) {
-                uint32_t ones = __popc(s5) + __popc(s6);
-                uint32_t twos = __popc(c0) + __popc(c1) + __popc(c2) + __popc(c3) + __popc(c4) + __popc(c5) +
-                                __popc(c6);
-                return ones + 2u * twos;
+                HULO_ACC(c0, 2u, n2); HULO_ACC(c1, 2u, n2); HULO_ACC(c2, 2u, n2); HULO_ACC(c3, 2u, n2);
+                HULO_ACC(c4, 2u, n2); HULO_ACC(c5, 2u, n2); HULO_ACC(c6, 2u, n2);
             } else {
-                // level 3: seven weight-2 words -> (t0, t1, c6) + two weight-4 words
-                uint32_t t0, t1, f0, f1;
+                // level 3: weight-2 words folded three at a time
+                uint32_t t0, f0;
                 HULO_CSA(f0, t0, c0, c1, c2);
-                HULO_CSA(f1, t1, c3, c4, c5);
-                if constexpr (CSA == 9) {
-                    uint32_t ones = __popc(s5) + __popc(s6);
-                    uint32_t twos = __popc(t0) + __popc(t1) + __popc(c6);
-                    uint32_t fours = __popc(f0) + __popc(f1);
-                    return ones + 2u * twos + 4u * fours;
+                if constexpr (CSA == 8) {
+                    HULO_ACC(t0, 2u, n2); HULO_ACC(c3, 2u, n2); HULO_ACC(c4, 2u, n2); HULO_ACC(c5, 2u, n2);
+                    HULO_ACC(c6, 2u, n2); HULO_ACC(f0, 4u, n4);
                 } else {
-                    static_assert(CSA == 11, "unsupported CSA depth");
-                    uint32_t t2, f2, f3, e0;
-                    HULO_CSA(f2, t2, t0, t1, c6);
-                    HULO_CSA(e0, f3, f0, f1, f2);
-                    uint32_t ones = __popc(s5) + __popc(s6);
-                    return ones + 2u * __popc(t2) + 4u * __popc(f3) + 8u * __popc(e0);
+                    uint32_t t1, f1;
+                    HULO_CSA(f1, t1, c3, c4, c5);
+                    if constexpr (CSA == 9) {
+                        HULO_ACC(t0, 2u, n2); HULO_ACC(t1, 2u, n2); HULO_ACC(c6, 2u, n2);
+                        HULO_ACC(f0, 4u, n4); HULO_ACC(f1, 4u, n4);
+                    } else {
+                        static_assert(CSA == 11, "unsupported CSA depth");
+                        uint32_t t2, f2, f3, e0;
+                        HULO_CSA(f2, t2, t0, t1, c6);
+                        HULO_CSA(e0, f3, f0, f1, f2);
+                        HULO_ACC(t2, 2u, n2); HULO_ACC(f3, 4u, n4); HULO_ACC(e0, 8u, n8);
+                    }
                 }
             }
         }
     }
+#undef HULO_ACC
+    if constexpr (IMAD) return key;
+    else return base + ((n1 + 2u * n2 + 4u * n4 + 8u * n8) << kKeyIdxBits);
 }
 
-template <int THREADS, int QPT, int CSA>
+// OPT bit 0: adds on the FMA pipe (IMAD); bit 1: rows taken two at a time so the best-2 update
+// uses 3-input min/max (VIMNMX3): 5 instead of 6 instructions per two keys.
+template <int THREADS, int QPT, int CSA, int OPT>
 __global__ void __launch_bounds__(THREADS, 1) knn2_kernel(const KnnParams p) {
+    constexpr bool kImad = (OPT & 1) != 0;
+    constexpr bool kPairRows = (OPT & 2) != 0;
     constexpr int kWarps = THREADS / 32;
     __shared__ __align__(128) uint4 s_tiles[kStages][kTileRows * 4];
     __shared__ __align__(8) uint64_t s_full[kStages];
@@ -209,19 +234,38 @@ __global__ void __launch_bounds__(THREADS, 1) knn2_kernel(const KnnParams p) {
             const uint32_t rows = min((uint32_t)kTileRows, b_rows - t * kTileRows);
             const uint4 *tile = &s_tiles[stage][0];
             const uint32_t key_base = t * kTileRows;
-#pragma unroll 2
-            for (uint32_t r = 0; r < rows; ++r) {
-                uint32_t w[16];
+            const uint32_t unit = p.key_unit;      // 1 << kKeyIdxBits, opaque to the compiler
+            auto load_row = [&](uint32_t r, uint32_t (&w)[16]) {
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
                     const uint4 tv = tile[r * 4 + v];   // same address in every lane: broadcast
                     w[4 * v + 0] = tv.x; w[4 * v + 1] = tv.y; w[4 * v + 2] = tv.z; w[4 * v + 3] = tv.w;
                 }
-                const uint32_t ridx = key_base + r;
+            };
+            uint32_t r = 0;
+            if constexpr (kPairRows) {
+                for (; r + 2 <= rows; r += 2) {
+                    uint32_t w0[16], w1[16];
+                    load_row(r, w0);
+                    load_row(r + 1, w1);
+#pragma unroll
+                    for (int qi = 0; qi < QPT; ++qi) {
+                        const uint32_t k0 = hamming_key<CSA, kImad>(q[qi], w0, key_base + r, unit);
+                        const uint32_t k1 = hamming_key<CSA, kImad>(q[qi], w1, key_base + r + 1, unit);
+                        const uint32_t lo = min(k0, k1), hi = max(k0, k1);
+                        const uint32_t m = max(best0[qi], lo);
+                        best0[qi] = min(best0[qi], lo);
+                        best1[qi] = min(min(best1[qi], hi), m);
+                    }
+                }
+            }
+#pragma unroll 2
+            for (; r < rows; ++r) {
+                uint32_t w[16];
+                load_row(r, w);
 #pragma unroll
                 for (int qi = 0; qi < QPT; ++qi) {
-                    const uint32_t d = hamming512<CSA>(q[qi], w);
-                    const uint32_t key = (d << kKeyIdxBits) + ridx;
+                    const uint32_t key = hamming_key<CSA, kImad>(q[qi], w, key_base + r, unit);
                     const uint32_t hi = max(best0[qi], key);
                     best0[qi] = min(best0[qi], key);
                     best1[qi] = min(best1[qi], hi);
@@ -300,20 +344,20 @@ __global__ void knn2_merge_ranks_kernel(const int4 *__restrict__ gathered, uint3
     write_result(m0, m1, row, out_idx2, out_dist2, nullptr);
 }
 
-template <int THREADS, int QPT, int CSA>
+template <int THREADS, int QPT, int CSA, int OPT>
 cudaError_t launch_variant(const KnnParams &p, int grid, cudaStream_t stream) {
-    knn2_kernel<THREADS, QPT, CSA><<<grid, THREADS, 0, stream>>>(p);
+    knn2_kernel<THREADS, QPT, CSA, OPT><<<grid, THREADS, 0, stream>>>(p);
     return cudaGetLastError();
 }
-template <int THREADS, int QPT, int CSA>
+template <int THREADS, int QPT, int CSA, int OPT>
 cudaError_t info_variant(int *regs, int *ctas, size_t *smem) {
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, knn2_kernel<THREADS, QPT, CSA>);
+    cudaError_t e = cudaFuncGetAttributes(&a, knn2_kernel<THREADS, QPT, CSA, OPT>);
     if (e != cudaSuccess) return e;
     if (regs) *regs = a.numRegs;
     if (smem) *smem = a.sharedSizeBytes;
     int n = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, knn2_kernel<THREADS, QPT, CSA>, THREADS, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, knn2_kernel<THREADS, QPT, CSA, OPT>, THREADS, 0);
     if (ctas) *ctas = n;
     return e;
 }
@@ -321,21 +365,25 @@ cudaError_t info_variant(int *regs, int *ctas, size_t *smem) {
 }  // namespace
 
 #define HULO_KNN_VARIANTS(X) \
-    X(256, 8, 0) X(256, 8, 5) X(256, 8, 7) X(256, 8, 9) X(256, 8, 11) \
-    X(512, 4, 0) X(512, 4, 7) X(512, 4, 9) \
-    X(256, 4, 7) X(256, 4, 9) X(128, 8, 7) X(128, 8, 9) X(128, 4, 7) X(256, 6, 7) X(256, 6, 9)
+    X(256, 8, 0, 0) X(256, 8, 5, 0) X(256, 8, 7, 0) X(256, 8, 9, 0) X(256, 8, 11, 0) \
+    X(256, 8, 7, 1) X(256, 8, 7, 2) X(256, 8, 7, 3) X(256, 8, 8, 0) X(256, 8, 8, 1) X(256, 8, 8, 3) \
+    X(512, 4, 7, 0) X(512, 4, 7, 1) X(512, 4, 7, 3) X(512, 4, 8, 1) X(512, 4, 8, 3) X(512, 4, 9, 0) \
+    X(256, 4, 7, 0) X(256, 4, 7, 3) X(256, 4, 8, 3) X(128, 8, 7, 0) X(128, 4, 7, 0) X(128, 4, 7, 3) \
+    X(1024, 2, 7, 0) X(1024, 2, 7, 3) X(1024, 2, 8, 3)
 
 cudaError_t knn2_launch(const KnnParams &p, const KnnConfig &cfg, int grid_ctas, cudaStream_t stream) {
-#define X(T, Q, C) \
-    if (cfg.threads == T && cfg.qpt == Q && cfg.csa == C) return launch_variant<T, Q, C>(p, grid_ctas, stream);
+#define X(T, Q, C, O) \
+    if (cfg.threads == T && cfg.qpt == Q && cfg.csa == C && cfg.opt == O) \
+        return launch_variant<T, Q, C, O>(p, grid_ctas, stream);
     HULO_KNN_VARIANTS(X)
 #undef X
     return cudaErrorInvalidValue;
 }
 
 cudaError_t knn2_kernel_info(const KnnConfig &cfg, int *regs, int *max_ctas_per_sm, size_t *smem) {
-#define X(T, Q, C) \
-    if (cfg.threads == T && cfg.qpt == Q && cfg.csa == C) return info_variant<T, Q, C>(regs, max_ctas_per_sm, smem);
+#define X(T, Q, C, O) \
+    if (cfg.threads == T && cfg.qpt == Q && cfg.csa == C && cfg.opt == O) \
+        return info_variant<T, Q, C, O>(regs, max_ctas_per_sm, smem);
     HULO_KNN_VARIANTS(X)
 #undef X
     return cudaErrorInvalidValue;

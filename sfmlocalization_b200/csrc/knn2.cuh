@@ -42,6 +42,7 @@ struct KnnParams {
     // flat mode: item w -> tile (w % n_tiles), chunk (w / n_tiles)
     uint32_t nA, nB, n_tiles, rows_per_chunk;
     uint64_t slot_stride;  // partial slot of (chunk, row) = chunk * slot_stride + row
+    uint32_t key_unit;     // 1 << kKeyIdxBits (a kernel argument so IMAD multipliers stay in registers)
     uint2 *partial;        // packed keys (best, second)
     unsigned int *counter; // dynamic item counter, zeroed before launch
 };
@@ -49,7 +50,8 @@ struct KnnParams {
 struct KnnConfig {
     int threads;
     int qpt;
-    int csa;   // carry-save depth: number of CSAs applied before POPC (0, 5, 7, 9, 11)
+    int csa;   // carry-save depth: number of CSAs applied before POPC (0, 5, 7, 8, 9, 11)
+    int opt;   // bit 0: adds on the FMA pipe (IMAD); bit 1: two rows per best-2 update (VIMNMX3)
 };
 
 // Launch K1 (variant chosen by cfg) on `stream`; grid_ctas persistent CTAs.

@@ -145,18 +145,30 @@ def make_tables(world, rank):
     return A, target, shard, row_base
 
 
+def calibrate_queries(orc, A, shard, grp, target_s):
+    """Number of query rows (a multiple of the port's 8-rows-per-thread group) for which one
+    exact pass over `shard` takes about target_s on this host: doubling probes until a probe
+    runs >= 0.5 s (short probes under-read the rate while the OpenMP pool and clocks ramp up)."""
+    nq = grp
+    while True:
+        t0 = time.perf_counter()
+        orc.knn2(A[:nq], shard)
+        dt = time.perf_counter() - t0
+        if dt >= 0.5 or nq >= A.shape[0]:
+            break
+        nq = min(A.shape[0], nq * 2)
+    want = nq * target_s / max(dt, 1e-6)
+    return int(min(A.shape[0], max(grp, want // grp * grp)))
+
+
 def cpu_baseline_sample(A, shard, budget_s=12.0):
     """Times the oracle port (exact 2-NN, all host cores) on a bounded sample of the workload."""
     from oracle import oracle as orc
     orc.build()
     threads = orc.num_threads()
     grp = 8 * max(1, threads)                       # the port walks 8 searcher rows per thread
-    nb_probe = min(shard.shape[0], 200_000)
-    t0 = time.perf_counter()
-    orc.knn2(A[:grp], shard[:nb_probe])
-    rate = grp * nb_probe / max(time.perf_counter() - t0, 1e-6)          # dist/s
     nb = int(shard.shape[0])
-    nq = int(min(A.shape[0], max(grp, (rate * budget_s / nb) // grp * grp)))
+    nq = calibrate_queries(orc, A, shard, grp, budget_s)
     t0 = time.perf_counter()
     idx, dist = orc.knn2(A[:nq], shard[:nb])
     dt = time.perf_counter() - t0
@@ -179,11 +191,8 @@ def run_reference(args, rank, world):
     threads = orc.num_threads()
     grp = 8 * max(1, threads)                       # the port walks 8 searcher rows per thread
     # size one step to ~2 s of CPU work: all 1M staged map rows, as many queries as that allows
-    t0 = time.perf_counter()
-    orc.knn2(A[:grp], shard[:100_000])
-    rate = grp * 100_000 / max(time.perf_counter() - t0, 1e-6)
     nb = int(shard.shape[0])
-    nq = int(min(A.shape[0], max(grp, (rate * 2.0 / nb) // grp * grp)))
+    nq = calibrate_queries(orc, A, shard, grp, 2.0)
     for _ in range(args.warmup):
         orc.knn2(A[:nq], shard[:nb])
     t0 = time.perf_counter()

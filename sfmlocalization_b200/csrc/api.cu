@@ -88,17 +88,17 @@ static FlatPlan plan_flat(const hulo_gpu *h, size_t nA, size_t nB) {
     return p;
 }
 
-// K1 + chunk merge for a flat searcher table against a flat database, results left in
-// h->knn_idx / h->knn_dist (and h->packed when want_packed).
-static int run_flat(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t nB, uint32_t row_base,
-                    bool want_packed) {
+// K1 for a flat searcher table against a flat database: per-chunk keys left in h->partial.
+int run_flat_k1(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t nB, uint32_t row_base,
+                FlatRun *run) {
     HULO_ARG(nA < (size_t)INT_MAX && nB + (size_t)row_base < (size_t)INT_MAX, "table too large for int32 indices");
     HULO_CUDA(h->knn_idx.reserve(std::max<size_t>(nA, 1) * 2 * sizeof(int32_t)));
     HULO_CUDA(h->knn_dist.reserve(std::max<size_t>(nA, 1) * 2 * sizeof(int32_t)));
-    if (want_packed) HULO_CUDA(h->packed.reserve(std::max<size_t>(nA, 1) * sizeof(int4)));
     h->last_nA = nA;
+    run->n_chunks = 0; run->rows_per_chunk = 1; run->slot_stride = 0;
     if (nA == 0) return HULO_OK;
     FlatPlan pl = plan_flat(h, nA, nB);
+    run->n_chunks = pl.n_chunks; run->rows_per_chunk = pl.rows_per_chunk; run->slot_stride = pl.slot_stride;
     if (pl.n_chunks > 0) {
         HULO_CUDA(h->partial.reserve((size_t)pl.n_chunks * pl.slot_stride * sizeof(uint2)));
         HULO_CUDA(h->counter.reserve(sizeof(unsigned int)));
@@ -115,8 +115,19 @@ static int run_flat(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size
         HULO_CUDA(knn2_launch(kp, pl.cfg, pl.grid, h->stream));
         h->launches++;
     }
-    HULO_CUDA(knn2_merge_launch(h->partial.as<uint2>(), (uint32_t)nA, pl.n_chunks, pl.slot_stride,
-                                pl.rows_per_chunk, row_base, h->knn_idx.as<int32_t>(),
+    return HULO_OK;
+}
+
+// K1 + chunk merge, results left in h->knn_idx / h->knn_dist (and h->packed when want_packed).
+static int run_flat(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t nB, uint32_t row_base,
+                    bool want_packed) {
+    FlatRun run;
+    int rc = run_flat_k1(h, A, nA, B, nB, row_base, &run);
+    if (rc != HULO_OK) return rc;
+    if (want_packed) HULO_CUDA(h->packed.reserve(std::max<size_t>(nA, 1) * sizeof(int4)));
+    if (nA == 0) return HULO_OK;
+    HULO_CUDA(knn2_merge_launch(h->partial.as<uint2>(), (uint32_t)nA, run.n_chunks, run.slot_stride,
+                                run.rows_per_chunk, row_base, h->knn_idx.as<int32_t>(),
                                 h->knn_dist.as<int32_t>(), want_packed ? h->packed.as<int4>() : nullptr,
                                 h->stream));
     h->launches++;

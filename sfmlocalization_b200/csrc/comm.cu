@@ -3,6 +3,9 @@
 // single ncclAllGather over NVLink.  NCCL is bound lazily with dlopen so that single-GPU use
 // and the CPU-side symbol check do not need it.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -11,6 +14,7 @@
 namespace hulo {
 
 int run_flat_packed(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t nB, uint32_t row_base);
+int run_flat_k1(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t nB, uint32_t row_base, FlatRun *run);
 
 namespace {
 
@@ -65,6 +69,72 @@ bool load_nccl() {
         }                                                                                            \
     } while (0)
 
+// ---- exchange buffers over CUDA IPC.  Layout of one rank's buffer:
+//   [2][world][cap] int4 records | [2][world] uint32 flags | done counter | status
+size_t px_bytes(int world, uint32_t cap) { return (size_t)2 * world * cap * sizeof(int4) + 4096; }
+
+void px_release(hulo_gpu *h) {
+    for (int g = 0; g < h->world && g < kMaxPeers; ++g) {
+        if (g != h->rank && h->px_peer_base[g]) cudaIpcCloseMemHandle(h->px_peer_base[g]);
+        h->px_peer_base[g] = nullptr;
+    }
+    if (h->px_own) cudaFree(h->px_own);
+    h->px_own = nullptr;
+    h->px_ready = false;
+}
+
+// (Re)build the exchange buffers for `rows` searcher rows: collective over the communicator.
+int px_setup(hulo_gpu *h, size_t rows) {
+    if (h->world > kMaxPeers) { h->px_disabled = true; return HULO_OK; }
+    px_release(h);
+    const uint32_t cap = (uint32_t)((rows + 255) & ~(size_t)255);
+    const size_t bytes = px_bytes(h->world, cap);
+    HULO_CUDA(cudaMalloc(&h->px_own, bytes));
+    HULO_CUDA(cudaMemsetAsync(h->px_own, 0, bytes, h->stream));
+    cudaIpcMemHandle_t mine;
+    HULO_CUDA(cudaIpcGetMemHandle(&mine, h->px_own));
+    // all-gather the 64-byte handles with the communicator that already exists
+    HULO_CUDA(h->scratch2.reserve((size_t)(h->world + 1) * sizeof(cudaIpcMemHandle_t)));
+    uint8_t *d_all = h->scratch2.as<uint8_t>();
+    uint8_t *d_mine = d_all + (size_t)h->world * sizeof(cudaIpcMemHandle_t);
+    HULO_CUDA(cudaMemcpyAsync(d_mine, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+    HULO_NCCL(g_nccl.AllGather(d_mine, d_all, sizeof mine, ncclChar, (ncclComm_t)h->nccl_comm, h->stream));
+    std::vector<cudaIpcMemHandle_t> all((size_t)h->world);
+    HULO_CUDA(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof mine, cudaMemcpyDeviceToHost, h->stream));
+    HULO_CUDA(cudaStreamSynchronize(h->stream));
+    bool ok = true;
+    for (int g = 0; g < h->world; ++g) {
+        if (g == h->rank) { h->px_peer_base[g] = h->px_own; continue; }
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, all[(size_t)g], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        h->px_peer_base[g] = p;
+    }
+    // every rank must agree on whether peer mapping works (min over ranks)
+    double flag = ok ? 1.0 : 0.0, neg = -flag;
+    int rc = hulo_comm_max_f64(h, &neg);
+    if (rc != HULO_OK) return rc;
+    if (-neg < 0.5) {
+        px_release(h);
+        h->px_disabled = true;                  // fall back to the NCCL all-gather exchange
+        return HULO_OK;
+    }
+    PeerExchange &px = h->px;
+    px.rank = h->rank; px.world = h->world; px.cap = cap; px.seq = 0;
+    for (int g = 0; g < h->world; ++g) {
+        uint8_t *base = static_cast<uint8_t *>(h->px_peer_base[g]);
+        px.records[g] = reinterpret_cast<int4 *>(base);
+        px.flags[g] = reinterpret_cast<uint32_t *>(base + (size_t)2 * h->world * cap * sizeof(int4));
+    }
+    uint8_t *tail = static_cast<uint8_t *>(h->px_own) + (size_t)2 * h->world * cap * sizeof(int4);
+    px.done_counter = reinterpret_cast<unsigned int *>(tail + 2048);
+    px.status = reinterpret_cast<unsigned int *>(tail + 2052);
+    h->px_seq = 0;
+    h->px_ready = true;
+    // nobody may start storing into a buffer that a peer is still zeroing
+    return hulo_comm_barrier(h);
+}
+
 }  // namespace
 }  // namespace hulo
 
@@ -73,6 +143,7 @@ using namespace hulo;
 extern "C" {
 
 void hulo_comm_destroy_internal(hulo_gpu *h) {
+    if (h) px_release(h);
     if (h && h->nccl_comm && g_nccl.lib) {
         g_nccl.CommDestroy((ncclComm_t)h->nccl_comm);
         h->nccl_comm = nullptr;
@@ -129,19 +200,45 @@ int hulo_knn2_sharded(hulo_gpu *h, const hulo_db *A, const hulo_db *B_shard, uin
     HULO_ARG(row_base + B_shard->n < (uint64_t)INT32_MAX, "global row index exceeds int32");
     HULO_CUDA(cudaSetDevice(h->device));
     const size_t nA = A->n;
+    if (h->world > 1 && !h->nccl_comm) { set_error("hulo_knn2_sharded: communicator not initialised"); return HULO_ERR_NCCL; }
+    // exchange flavour: stores into peer-mapped buffers fused into the merge epilogue (default),
+    // or one ncclAllGather (HULO_EXCHANGE=nccl, or when the peers cannot be mapped)
+    const char *ex = getenv("HULO_EXCHANGE");
+    bool use_peers = h->world > 1 && !h->px_disabled && !(ex && strcmp(ex, "nccl") == 0);
+    if (use_peers && (!h->px_ready || h->px.cap < nA)) {
+        int rc = px_setup(h, std::max<size_t>(nA, 4096));
+        if (rc != HULO_OK) return rc;
+        use_peers = h->px_ready;
+    }
+    if (use_peers) {
+        FlatRun run;
+        int rc = run_flat_k1(h, A->rows, nA, B_shard->rows, B_shard->n, (uint32_t)row_base, &run);
+        if (rc != HULO_OK) return rc;
+        h->px.seq = ++h->px_seq;
+        HULO_CUDA(knn2_merge_store_peers_launch(h->partial.as<uint2>(), (uint32_t)nA, run.n_chunks, run.slot_stride,
+                                                run.rows_per_chunk, (uint32_t)row_base, h->px, h->stream));
+        HULO_CUDA(knn2_merge_from_peers_launch(h->px, (uint32_t)nA, h->knn_idx.as<int32_t>(),
+                                               h->knn_dist.as<int32_t>(), h->stream));
+        h->launches += 2;
+        if (idx2 || dist2) {
+            int rc2 = hulo_knn2_fetch(h, nA, idx2, dist2);
+            if (rc2 != HULO_OK) return rc2;
+            unsigned int st = 0;
+            HULO_CUDA(cudaMemcpy(&st, h->px.status, sizeof st, cudaMemcpyDeviceToHost));
+            if (st) { set_error("hulo_knn2_sharded: a peer did not deliver its candidates within 10 s"); return HULO_ERR_NCCL; }
+        }
+        return HULO_OK;
+    }
     int rc = run_flat_packed(h, A->rows, nA, B_shard->rows, B_shard->n, (uint32_t)row_base);
     if (rc != HULO_OK) return rc;
-    if (h->world > 1) {
-        if (!h->nccl_comm) { set_error("hulo_knn2_sharded: communicator not initialised"); return HULO_ERR_NCCL; }
-        if (nA > 0) {
-            HULO_CUDA(h->gathered.reserve((size_t)h->world * nA * sizeof(int4)));
-            // one all-gather of nA x 16 bytes per rank
-            HULO_NCCL(g_nccl.AllGather(h->packed.ptr, h->gathered.ptr, nA * sizeof(int4), ncclChar,
-                                       (ncclComm_t)h->nccl_comm, h->stream));
-            HULO_CUDA(knn2_merge_ranks_launch(h->gathered.as<int4>(), (uint32_t)nA, h->world,
-                                              h->knn_idx.as<int32_t>(), h->knn_dist.as<int32_t>(), h->stream));
-            h->launches++;
-        }
+    if (h->world > 1 && nA > 0) {
+        HULO_CUDA(h->gathered.reserve((size_t)h->world * nA * sizeof(int4)));
+        // one all-gather of nA x 16 bytes per rank
+        HULO_NCCL(g_nccl.AllGather(h->packed.ptr, h->gathered.ptr, nA * sizeof(int4), ncclChar,
+                                   (ncclComm_t)h->nccl_comm, h->stream));
+        HULO_CUDA(knn2_merge_ranks_launch(h->gathered.as<int4>(), (uint32_t)nA, h->world,
+                                          h->knn_idx.as<int32_t>(), h->knn_dist.as<int32_t>(), h->stream));
+        h->launches++;
     }
     if (idx2 || dist2) return hulo_knn2_fetch(h, nA, idx2, dist2);
     return HULO_OK;

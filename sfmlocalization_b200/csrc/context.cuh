@@ -14,6 +14,12 @@ namespace hulo {
 
 void set_error(const char *fmt, ...);
 
+// what a flat K1 launch left in the partial-key buffer
+struct FlatRun {
+    uint32_t n_chunks, rows_per_chunk;
+    uint64_t slot_stride;
+};
+
 #define HULO_CUDA(expr)                                                                       \
     do {                                                                                      \
         cudaError_t e__ = (expr);                                                             \
@@ -108,4 +114,10 @@ struct hulo_gpu {
     // NCCL (loaded lazily)
     void *nccl_comm = nullptr;
     int rank = 0, world = 1;
+    // fused exchange over peer memory (CUDA IPC): set up on the first sharded search
+    hulo::PeerExchange px{};
+    void *px_own = nullptr;            // this rank's exchange buffer (records + flags)
+    void *px_peer_base[hulo::kMaxPeers] = {nullptr};
+    bool px_ready = false, px_disabled = false;
+    uint32_t px_seq = 0;
 };

@@ -344,6 +344,88 @@ __global__ void knn2_merge_ranks_kernel(const int4 *__restrict__ gathered, uint3
     write_result(m0, m1, row, out_idx2, out_dist2, nullptr);
 }
 
+// ---- fused exchange over peer memory
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int4 ld_relaxed_sys_v4(const int4 *p) {
+    int4 v;
+    asm volatile("ld.relaxed.sys.global.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void knn2_merge_store_peers_kernel(const uint2 *__restrict__ partial, uint32_t nA, uint32_t n_chunks,
+                                              uint64_t slot_stride, uint32_t rows_per_chunk, uint32_t row_base,
+                                              const PeerExchange px) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row < nA) {
+        uint64_t m0 = kNone64, m1 = kNone64;
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            const uint2 k = partial[(uint64_t)c * slot_stride + row];
+            const uint32_t base = row_base + c * rows_per_chunk;
+            if (k.x != kKeyNone)
+                top2_insert(((uint64_t)(k.x >> kKeyIdxBits) << 32) | (uint64_t)(base + (k.x & kKeyIdxMask)), m0, m1);
+            if (k.y != kKeyNone)
+                top2_insert(((uint64_t)(k.y >> kKeyIdxBits) << 32) | (uint64_t)(base + (k.y & kKeyIdxMask)), m0, m1);
+        }
+        const int4 rec = make_int4(m0 == kNone64 ? INT_MAX : (int32_t)(m0 >> 32), m0 == kNone64 ? -1 : (int32_t)(uint32_t)m0,
+                                   m1 == kNone64 ? INT_MAX : (int32_t)(m1 >> 32), m1 == kNone64 ? -1 : (int32_t)(uint32_t)m1);
+        const size_t slot = ((size_t)(px.seq & 1u) * px.world + px.rank) * px.cap + row;
+        for (int g = 0; g < px.world; ++g) px.records[g][slot] = rec;      // 16-byte stores, peers over NVLink
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(px.done_counter, 1u) + 1u;
+        if (done == gridDim.x) {               // last block: every record of this rank is visible
+            *px.done_counter = 0u;
+            __threadfence_system();
+            for (int g = 0; g < px.world; ++g)
+                st_release_sys(px.flags[g] + (size_t)(px.seq & 1u) * px.world + px.rank, px.seq);
+        }
+    }
+}
+
+__global__ void knn2_merge_from_peers_kernel(const PeerExchange px, uint32_t nA, int32_t *out_idx2,
+                                             int32_t *out_dist2) {
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        // all ranks run this step concurrently (one process per GPU); bounded spin so that a
+        // dead peer surfaces as an error instead of a hang
+        const uint32_t *fl = px.flags[px.rank] + (size_t)(px.seq & 1u) * px.world;
+        int ok = 1;
+        const long long t0 = clock64();
+        for (int g = 0; g < px.world; ++g) {
+            while (ld_acquire_sys(fl + g) != px.seq) {
+                if (clock64() - t0 > 20000000000ll) { ok = 0; break; }      // ~10 s
+                __nanosleep(200);
+            }
+            if (!ok) break;
+        }
+        if (!ok) *px.status = 1u;
+        s_ok = ok;
+    }
+    __syncthreads();
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nA) return;
+    uint64_t m0 = kNone64, m1 = kNone64;
+    if (s_ok) {
+        const int4 *mine = px.records[px.rank] + (size_t)(px.seq & 1u) * px.world * px.cap;
+        for (int g = 0; g < px.world; ++g) {
+            const int4 c = ld_relaxed_sys_v4(mine + (size_t)g * px.cap + row);
+            if (c.y >= 0) top2_insert(((uint64_t)(uint32_t)c.x << 32) | (uint32_t)c.y, m0, m1);
+            if (c.w >= 0) top2_insert(((uint64_t)(uint32_t)c.z << 32) | (uint32_t)c.w, m0, m1);
+        }
+    }
+    write_result(m0, m1, row, out_idx2, out_dist2, nullptr);
+}
+
 template <int THREADS, int QPT, int CSA, int OPT>
 cudaError_t launch_variant(const KnnParams &p, int grid, cudaStream_t stream) {
     knn2_kernel<THREADS, QPT, CSA, OPT><<<grid, THREADS, 0, stream>>>(p);
@@ -396,6 +478,24 @@ cudaError_t knn2_merge_launch(const uint2 *partial, uint32_t nA, uint32_t n_chun
     const int threads = 256;
     knn2_merge_kernel<<<(nA + threads - 1) / threads, threads, 0, stream>>>(
         partial, nA, n_chunks, slot_stride, rows_per_chunk, row_base, out_idx2, out_dist2, out_packed);
+    return cudaGetLastError();
+}
+
+cudaError_t knn2_merge_store_peers_launch(const uint2 *partial, uint32_t nA, uint32_t n_chunks,
+                                          uint64_t slot_stride, uint32_t rows_per_chunk, uint32_t row_base,
+                                          const PeerExchange &px, cudaStream_t stream) {
+    const int threads = 256;
+    const uint32_t blocks = nA == 0 ? 1 : (nA + threads - 1) / threads;
+    knn2_merge_store_peers_kernel<<<blocks, threads, 0, stream>>>(partial, nA, n_chunks, slot_stride,
+                                                                 rows_per_chunk, row_base, px);
+    return cudaGetLastError();
+}
+
+cudaError_t knn2_merge_from_peers_launch(const PeerExchange &px, uint32_t nA, int32_t *out_idx2,
+                                         int32_t *out_dist2, cudaStream_t stream) {
+    const int threads = 256;
+    const uint32_t blocks = nA == 0 ? 1 : (nA + threads - 1) / threads;
+    knn2_merge_from_peers_kernel<<<blocks, threads, 0, stream>>>(px, nA, out_idx2, out_dist2);
     return cudaGetLastError();
 }
 

@@ -73,4 +73,28 @@ cudaError_t knn2_merge_launch(const uint2 *partial, uint32_t nA, uint32_t n_chun
 cudaError_t knn2_merge_ranks_launch(const int4 *gathered, uint32_t nA, int world, int32_t *out_idx2,
                                     int32_t *out_dist2, cudaStream_t stream);
 
+// ---- fused exchange over peer memory (row-sharded database, one process per GPU) ----
+// Every rank owns an exchange buffer that all peers have mapped (CUDA IPC over NVLink):
+//   records: [2 parities][world][cap] int4 {d0,i0,d1,i1};  flags: [2][world] uint32 sequence numbers.
+constexpr int kMaxPeers = 16;
+struct PeerExchange {
+    int4 *records[kMaxPeers];       // records[g]: rank g's buffer as mapped in this process
+    uint32_t *flags[kMaxPeers];     // flags[g]:   rank g's flag words
+    int rank, world;
+    uint32_t cap;                   // rows per (parity, rank) slot
+    uint32_t seq;                   // sequence number of this exchange (>= 1)
+    unsigned int *done_counter;     // local: blocks of the store kernel that have finished
+    unsigned int *status;           // local: set to 1 when a wait timed out
+};
+// Step 1 (the K1 chunk-merge epilogue): fold the chunk keys of every searcher row and STORE the
+// packed top-2 record straight into slot [seq&1][rank] of every rank's buffer (peer stores over
+// NVLink), then publish flags[g][seq&1][rank] = seq on every rank.
+cudaError_t knn2_merge_store_peers_launch(const uint2 *partial, uint32_t nA, uint32_t n_chunks,
+                                          uint64_t slot_stride, uint32_t rows_per_chunk, uint32_t row_base,
+                                          const PeerExchange &px, cudaStream_t stream);
+// Step 2: wait until every rank's record list for `seq` has landed in the local buffer, then
+// merge them per row on (distance, global index).
+cudaError_t knn2_merge_from_peers_launch(const PeerExchange &px, uint32_t nA, int32_t *out_idx2,
+                                         int32_t *out_dist2, cudaStream_t stream);
+
 }  // namespace hulo

@@ -46,7 +46,23 @@ def main():
         uid, path = bench.rendezvous_id(rank, world, HuloGpu.comm_unique_id)
         g.comm_init(uid, rank, world)
         dA, dB = g.db(A), g.db(B[lo:hi])
-        idx, dist = g.knn2_sharded(dA, dB, lo)
+        # both exchange flavours: stores into peer-mapped buffers (default) and ncclAllGather
+        results = []
+        for flavour in ("peer", "nccl", "peer"):
+            os.environ["HULO_EXCHANGE"] = flavour
+            for _ in range(3):                       # repeated calls exercise the parity double buffer
+                results.append(g.knn2_sharded(dA, dB, lo))
+        # a larger searcher table forces the exchange buffers to be rebuilt (collective)
+        os.environ["HULO_EXCHANGE"] = "peer"
+        A2 = np.concatenate([A] * 8, axis=0)
+        dA2 = g.db(A2)
+        i2, d2 = g.knn2_sharded(dA2, dB, lo)
+        dA2.free()
+        for (i_, d_) in results:
+            assert np.array_equal(i_, results[0][0]) and np.array_equal(d_, results[0][1])
+        assert np.array_equal(i2[:NA], results[0][0]) and np.array_equal(i2[-NA:], results[0][0])
+        assert np.array_equal(d2[:NA], results[0][1])
+        idx, dist = results[0]
         t = g.comm_max(float(rank))
         assert t == float(world - 1)
         g.comm_barrier()

@@ -267,7 +267,40 @@ def localize_bench(g, with_cpu=True, reps=20):
                                "sample": "1 query: exact per-view 2-NN on all cores, sequential AC-RANSAC on one "
                                          "thread (as the reference runs it)",
                                "localized": bool(ro["ok"]), "inliers": int(len(ro["inliers"]))}
+        out["reference_algorithm_lsh"] = lsh_reference(sc, set(zip(m_view, m_i, m_j)))
     return out
+
+
+def lsh_reference(sc, exact_matches):
+    """The reference's own (approximate) matcher configuration, for context: cv::flann LSH index
+    (2 tables, key 20, multi-probe 2) on the query descriptors, knnSearch(k=2, checks=2) per map
+    view, float ratio test (MatchUtils.cpp:52-65, 303-355), through OpenCV's Python binding,
+    one thread (the reference spreads the views over OpenMP threads).  Reports its time and how
+    its putative matches compare with the exact matcher's.  Not the parity target."""
+    try:
+        import cv2
+    except Exception as e:                      # pragma: no cover
+        return {"unavailable": "cv2 not importable: %s" % e}
+    off = sc["seg_offsets"]
+    t0 = time.perf_counter()
+    index = cv2.flann_Index(sc["q_desc"], dict(algorithm=6, table_number=2, key_size=20, multi_probe_level=2), 9)
+    got = set()
+    for v in range(len(off) - 1):
+        a = sc["rows"][int(off[v]):int(off[v + 1])]
+        idx, dist = index.knnSearch(a, 2, params=dict(checks=2, eps=0.0, sorted=True))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            q = dist[:, 0].astype(np.float32) / dist[:, 1].astype(np.float32)
+        keep = np.nonzero((q < np.float32(0.6)) & (dist[:, 1] < 2**31 - 1))[0]
+        if len(keep) >= 16:
+            got.update((v, int(i), int(idx[i, 0])) for i in keep)
+    dt = time.perf_counter() - t0
+    both = len(got & exact_matches)
+    return {"ms_per_query_matching": dt * 1e3, "threads": 1, "putative_matches": len(got),
+            "exact_matcher_matches": len(exact_matches), "common": both,
+            "note": "approximate and indicative only: on i.i.d. synthetic descriptors the probed LSH buckets "
+                    "almost never hold a second candidate, so rows come back with d1 = INT_MAX and are rejected "
+                    "(MatchUtils.cpp:349); on real images the second candidate is whatever shares a bucket"}
+
 
 
 def workload_config(n_gpus):
@@ -315,11 +348,13 @@ def main():
             g.knn2(dA, dB, fetch=False)
 
     # ---- kernel-resident throughput: inputs already in HBM, results left in HBM
+    # the clock sampler runs from the warm-up on (same load) so that short timed regions still
+    # collect samples; nvidia-smi needs ~100 ms to deliver its first line
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_device()
     g.comm_barrier() if world > 1 else g.synchronize()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = g.launch_count
     g.timer_start()
     for _ in range(args.steps):

@@ -110,6 +110,7 @@ struct hulo_gpu {
     hulo::DevBuf scratch0, scratch1, scratch2, scratch3;   // post-processing / K2
     hulo::HostBuf hstage0, hstage1;
     size_t last_nA = 0;
+    size_t score_smem_configured = 0;   // dynamic smem opt-in already set for K2 on this device
 
     // NCCL (loaded lazily)
     void *nccl_comm = nullptr;

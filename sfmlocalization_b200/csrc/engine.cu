@@ -17,9 +17,9 @@ struct hulo_engine {
     hulo_gpu *h = nullptr;
     hulo_db *map = nullptr;
     size_t n_views = 0;
-    // (view, feat) -> landmark, sorted by key = view << 32 | feat
-    std::vector<uint64_t> obs_key;
-    std::vector<uint32_t> obs_lm;
+    // (view, feat) -> landmark as a dense table over the map rows: lm_of_row[seg[view] + feat], -1 = none
+    std::vector<uint64_t> seg;
+    std::vector<int32_t> lm_of_row;
     std::vector<double> X;     // n_landmarks x 3
     double K[9];
     float ratio = 0.6f;        // secondTestRatio, localizeImage.cc:46-59
@@ -123,18 +123,20 @@ int hulo_engine_create(hulo_gpu *h, const uint8_t *rows, size_t n, size_t stride
     int rc = hulo_db_upload(h, rows, n, stride, seg_offsets, n_views, &e->map);
     if (rc != HULO_OK) { delete e; return rc; }
     e->n_views = n_views;
-    std::vector<size_t> order(n_obs);
-    for (size_t k = 0; k < n_obs; ++k) order[k] = k;
-    auto key = [&](size_t k) { return ((uint64_t)obs_view[k] << 32) | obs_feat[k]; };
-    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return key(a) < key(b); });
-    e->obs_key.reserve(n_obs);
-    e->obs_lm.reserve(n_obs);
+    e->seg.assign(seg_offsets, seg_offsets + n_views + 1);
+    e->lm_of_row.assign(std::max<size_t>(n, 1), -1);
     for (size_t k = 0; k < n_obs; ++k) {
-        const uint64_t kk = key(order[k]);
+        const uint64_t row = e->seg[obs_view[k]] + obs_feat[k];
+        if (row >= e->seg[obs_view[k] + 1]) {
+            set_error("hulo_engine_create: observation %zu refers to feature %u of view %u, which has %llu rows", k,
+                      obs_feat[k], obs_view[k], (unsigned long long)(e->seg[obs_view[k] + 1] - e->seg[obs_view[k]]));
+            hulo_db_free(e->map);
+            delete e;
+            return HULO_ERR_ARG;
+        }
         // a (view, feature) observed by several landmarks keeps the last one written, like the
         // map[view][feat] = landmark assignment of SfMDataUtils.cpp:42
-        if (!e->obs_key.empty() && e->obs_key.back() == kk) e->obs_lm.back() = obs_landmark[order[k]];
-        else { e->obs_key.push_back(kk); e->obs_lm.push_back(obs_landmark[order[k]]); }
+        e->lm_of_row[row] = (int32_t)obs_landmark[k];
     }
     e->X.assign(landmark_X, landmark_X + 3 * n_landmarks);
     memcpy(e->K, K, sizeof e->K);
@@ -215,10 +217,9 @@ int hulo_engine_localize(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t
             e->fd_stamp[j] = (int32_t)oi;
         }
         for (size_t k = start[v]; k < start[v + 1]; ++k) {
-            const uint64_t key = ((uint64_t)view_id << 32) | e->m_i[k];
-            auto it = std::lower_bound(e->obs_key.begin(), e->obs_key.end(), key);
-            if (it == e->obs_key.end() || *it != key) continue;      // feature has no landmark
-            const uint32_t lm = e->obs_lm[(size_t)(it - e->obs_key.begin())];
+            const int32_t lmi = e->lm_of_row[e->seg[view_id] + e->m_i[k]];
+            if (lmi < 0) continue;                                     // feature has no landmark
+            const uint32_t lm = (uint32_t)lmi;
             const uint32_t j = e->m_j[k];
             if (e->fd_stamp[j] != (int32_t)oi) continue;
             const int32_t d = e->fd[j];

@@ -406,10 +406,9 @@ int launch_score(hulo_gpu *h, const Problem &pb, const double *d_models, size_t 
     if (H == 0) return HULO_OK;
     const uint32_t npad = next_pow2((uint32_t)pb.N);
     const size_t smem = npad * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024 && smem > h->score_smem_configured) {   // per device, so per context
         HULO_CUDA(cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+        h->score_smem_configured = smem;
     }
     score_kernel<<<(unsigned)H, kScoreThreads, smem, h->stream>>>(d_models, (uint32_t)H, pb.d_x2dn, pb.d_X3d,
                                                                 (uint32_t)pb.N, npad, pb.d_logc_n, pb.d_logc_k,

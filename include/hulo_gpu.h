@@ -121,6 +121,18 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
                         uint32_t *out_view, uint32_t *out_i, uint32_t *out_j, int32_t *out_d0,
                         size_t cap, size_t *n_out, uint32_t *view_counts);
 
+/* Batched hulo::matchAKAZEToQuery: n_queries query images against the same map in one pass
+ * (the server handling concurrent requests, BASELINE.json config 4; the reference has no
+ * batched form -- its engine is single-threaded and non-re-entrant, localizeImage.cc:71-74).
+ * queries holds the descriptor rows of all images back to back, image q owning rows
+ * [q_offsets[q], q_offsets[q+1]).  Output order: query ascending, then as hulo_match_to_query;
+ * out_query[k] is the query image of match k; counts (n_queries x n_views, may be NULL) the
+ * matches per (query, view).  Capacity protocol as hulo_match_to_query. */
+int hulo_match_to_queries(hulo_gpu *h, const hulo_db *map, const uint32_t *views, size_t n_views,
+                          const uint8_t *queries, size_t q_stride, const uint64_t *q_offsets, size_t n_queries,
+                          float ratio, uint32_t *out_query, uint32_t *out_view, uint32_t *out_i, uint32_t *out_j,
+                          int32_t *out_d0, size_t cap, size_t *n_out, uint32_t *counts);
+
 /* ------------------------------------------ image-pair matching (reconstruction) */
 
 #define HULO_PAIR_ONE_TO_ONE 1u /* drop every claimant of a train row claimed twice, :125-143 */
@@ -215,6 +227,16 @@ int hulo_engine_localize(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t
                          const uint32_t *views, size_t n_views, uint64_t seed, double *pose12, int *localized,
                          uint32_t *corr_qfeat, uint32_t *corr_landmark, size_t *n_corr, int32_t *inliers,
                          size_t *n_inliers, double *times_ms);
+
+/* The same for n_queries images at once (concurrent server requests, BASELINE.json config 4):
+ * one batched matching pass (hulo_match_to_queries), then assembly and resection per image.
+ * Layout of qdesc / q_offsets as hulo_match_to_queries; qxy holds 2 doubles per descriptor row.
+ * Image q uses seed + q.  pose12: n_queries x 12; localized, n_corr, n_inliers: n_queries entries
+ * (the last two may be NULL); times_ms[3] accumulates putMatch, assembly, PnP over the batch. */
+int hulo_engine_localize_batch(hulo_engine *e, size_t n_queries, const uint8_t *qdesc, size_t q_stride,
+                               const uint64_t *q_offsets, const double *qxy, const uint32_t *views, size_t n_views,
+                               uint64_t seed, double *pose12, int *localized, uint32_t *n_corr, uint32_t *n_inliers,
+                               double *times_ms);
 
 /* ------------------------------------------------------------------ multi GPU */
 

@@ -48,6 +48,8 @@ SIGNATURES = {
     "hulo_knn2_host": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz, _sz, _vp, _vp]),
     "hulo_match_to_query": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _sz, _sz, _f32, _vp, _vp, _vp, _vp, _sz,
                                       C.POINTER(_sz), _vp]),
+    "hulo_match_to_queries": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _sz, _vp, _sz, _f32, _vp, _vp, _vp, _vp, _vp, _sz,
+                                        C.POINTER(_sz), _vp]),
     "hulo_match_pairs": (C.c_int, [_vp, _vp, _vp, _sz, _f32, C.c_uint, _vp, _vp, _vp, _sz, C.POINTER(_sz)]),
     "hulo_score_resection": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _f64, _vp, _vp, _vp, _vp]),
     "hulo_resection_residuals": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp]),
@@ -59,6 +61,7 @@ SIGNATURES = {
     "hulo_engine_configure": (C.c_int, [_vp, _f32, C.c_int, C.c_int, C.c_int, _sz]),
     "hulo_engine_localize": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _vp, _sz, _u64, _vp, C.POINTER(C.c_int), _vp, _vp,
                                        C.POINTER(_sz), _vp, C.POINTER(_sz), _vp]),
+    "hulo_engine_localize_batch": (C.c_int, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _u64, _vp, _vp, _vp, _vp, _vp]),
     "hulo_comm_unique_id": (C.c_int, [_vp]),
     "hulo_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "hulo_comm_barrier": (C.c_int, [_vp]),

@@ -515,6 +515,163 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     return HULO_OK;
 }
 
+// Batched form: several query images against the same map in one pass (BASELINE.json config 4).
+int hulo_match_to_queries(hulo_gpu *h, const hulo_db *map, const uint32_t *views, size_t n_views,
+                          const uint8_t *queries, size_t q_stride, const uint64_t *q_offsets, size_t n_queries,
+                          float ratio, uint32_t *out_query, uint32_t *out_view, uint32_t *out_i, uint32_t *out_j,
+                          int32_t *out_d0, size_t cap, size_t *n_out, uint32_t *counts) {
+    HULO_ARG(h != nullptr && map != nullptr && n_out != nullptr, "null argument");
+    HULO_ARG(n_queries == 0 || q_offsets != nullptr, "q_offsets is null");
+    HULO_ARG(q_stride >= 1, "stride must be >= 1");
+    *n_out = 0;
+    HULO_CUDA(cudaSetDevice(h->device));
+    const size_t n_seg = map->seg.size() - 1;
+    if (views == nullptr) n_views = n_seg;
+    for (size_t v = 0; views && v < n_views; ++v) HULO_ARG(views[v] < n_seg, "view index out of range");
+    if (counts) memset(counts, 0, n_queries * n_views * sizeof(uint32_t));
+    if (n_queries == 0 || n_views == 0) return HULO_OK;
+    const uint64_t total_q_rows = q_offsets[n_queries];
+    for (size_t q = 0; q < n_queries; ++q) {
+        HULO_ARG(q_offsets[q] <= q_offsets[q + 1], "q_offsets not ascending");
+        HULO_ARG(q_offsets[q + 1] - q_offsets[q] <= kMaxChunkRows, "query image with more than 4 Mi descriptors");
+    }
+    HULO_ARG(total_q_rows == 0 || queries != nullptr, "queries is null");
+    HULO_ARG(total_q_rows < (uint64_t)INT_MAX, "too many query rows");
+
+    std::vector<uint64_t> sel_off(n_views + 1, 0);
+    for (size_t v = 0; v < n_views; ++v) {
+        const size_t s = views ? views[v] : v;
+        sel_off[v + 1] = sel_off[v] + (map->seg[s + 1] - map->seg[s]);
+    }
+    const uint64_t n_rows = sel_off[n_views];
+    if (n_rows == 0 || total_q_rows == 0) return HULO_OK;
+
+    // all query rows go up once
+    HULO_CUDA(h->stageB.reserve(total_q_rows * HULO_ROW_BYTES));
+    cudaError_t e;
+    const uint8_t *q64 = stage_rows(h->hstage1, queries, total_q_rows, q_stride, &e);
+    HULO_CUDA(e);
+    HULO_CUDA(cudaMemcpyAsync(h->stageB.ptr, q64, total_q_rows * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
+
+    const KnnConfig cfg = choose_config(h, (size_t)n_rows);
+    const uint32_t tile = knn2_tile_rows(cfg);
+    struct Run { uint64_t a0, rows, slot0; };
+    std::vector<Run> runs;
+    for (size_t v = 0; v < n_views; ++v) {
+        const size_t s = views ? views[v] : v;
+        const uint64_t a0 = map->seg[s], rows = map->seg[s + 1] - map->seg[s];
+        if (rows == 0) continue;
+        if (!runs.empty() && runs.back().a0 + runs.back().rows == a0) runs.back().rows += rows;
+        else runs.push_back(Run{a0, rows, sel_off[v]});
+    }
+    int ctas_per_sm = 1;
+    knn2_kernel_info(cfg, nullptr, &ctas_per_sm, nullptr);
+    const int full_grid = h->sm_count * std::max(1, ctas_per_sm);
+
+    // sub-batches of queries bounded by compact rows (queries x selected map rows)
+    const uint64_t budget = (uint64_t)std::max(1, env_int("HULO_QUERY_BATCH_ROWS", 48 << 20));
+    HULO_ARG(n_rows <= budget, "selected map rows exceed HULO_QUERY_BATCH_ROWS");
+    const size_t per_batch = (size_t)std::max<uint64_t>(1, budget / n_rows);
+    std::vector<KnnItem> items;
+    std::vector<uint64_t> seg_off, h_seg_out;
+    std::vector<size_t> members;
+    size_t total_out = 0;
+    bool overflow = false;
+    for (size_t q0 = 0; q0 < n_queries; q0 += per_batch) {
+        const size_t q1 = std::min(n_queries, q0 + per_batch);
+        members.clear();
+        for (size_t q = q0; q < q1; ++q)
+            if (q_offsets[q + 1] > q_offsets[q]) members.push_back(q);     // MatchUtils.cpp:299-301
+        if (members.empty()) continue;
+        const size_t nb = members.size();
+        const uint64_t rows_total = (uint64_t)nb * n_rows;
+        items.clear();
+        seg_off.assign(nb * n_views + 1, 0);
+        for (size_t ql = 0; ql < nb; ++ql) {
+            const size_t q = members[ql];
+            for (const Run &r : runs)
+                for (uint64_t t0 = 0; t0 < r.rows; t0 += tile) {
+                    KnnItem it{};
+                    it.a_row0 = (uint32_t)(r.a0 + t0);
+                    it.a_rows = (uint32_t)std::min<uint64_t>(tile, r.rows - t0);
+                    it.b_row0 = (uint32_t)q_offsets[q];
+                    it.b_rows = (uint32_t)(q_offsets[q + 1] - q_offsets[q]);
+                    it.out_slot0 = (uint64_t)ql * n_rows + r.slot0 + t0;
+                    items.push_back(it);
+                }
+            for (size_t v = 0; v < n_views; ++v) seg_off[ql * n_views + v] = (uint64_t)ql * n_rows + sel_off[v];
+        }
+        seg_off[nb * n_views] = rows_total;
+        const size_t n_segs = nb * n_views;
+        const size_t n_blocks = (rows_total + kCompactBlockRows - 1) / kCompactBlockRows;
+        HULO_CUDA(h->items.reserve(items.size() * sizeof(KnnItem)));
+        HULO_CUDA(cudaMemcpyAsync(h->items.ptr, items.data(), items.size() * sizeof(KnnItem), cudaMemcpyHostToDevice, h->stream));
+        HULO_CUDA(h->partial.reserve(rows_total * sizeof(uint2)));
+        HULO_CUDA(h->counter.reserve(sizeof(unsigned int)));
+        HULO_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(unsigned int), h->stream));
+        HULO_CUDA(h->scratch0.reserve(rows_total * 2 * sizeof(int32_t)));
+        HULO_CUDA(h->scratch1.reserve((n_segs + 1) * sizeof(uint64_t)));
+        HULO_CUDA(h->scratch2.reserve((n_blocks + 2) * sizeof(uint32_t) + (n_segs + 2) * sizeof(uint64_t) + 64));
+        HULO_CUDA(h->scratch3.reserve(rows_total * 3 * sizeof(uint32_t)));
+        HULO_CUDA(cudaMemcpyAsync(h->scratch1.ptr, seg_off.data(), (n_segs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+        KnnParams kp{};
+        kp.A = map->rows; kp.B = h->stageB.as<uint4>();
+        kp.items = h->items.as<KnnItem>();
+        kp.n_items = (uint32_t)items.size();
+        kp.key_unit = 1u << kKeyIdxBits;
+        kp.partial = h->partial.as<uint2>();
+        kp.counter = h->counter.as<unsigned int>();
+        HULO_CUDA(knn2_launch(kp, cfg, (int)std::min<size_t>((size_t)full_grid, items.size()), h->stream));
+        h->launches++;
+        int32_t *val = h->scratch0.as<int32_t>();
+        int32_t *dist = val + rows_total;
+        HULO_CUDA(post_query_launch(h->partial.as<uint2>(), (uint32_t)rows_total, 1, rows_total, kMaxChunkRows, ratio, val,
+                                    dist, h->stream));
+        h->launches++;
+        uint8_t *s2 = h->scratch2.as<uint8_t>();
+        uint64_t *d_total = reinterpret_cast<uint64_t *>(s2);
+        uint64_t *d_seg_out = d_total + 1;
+        uint32_t *d_blocks = reinterpret_cast<uint32_t *>(d_seg_out + (n_segs + 1));
+        uint32_t *o_i = h->scratch3.as<uint32_t>(), *o_j = o_i + rows_total;
+        int32_t *o_d = reinterpret_cast<int32_t *>(o_j + rows_total);
+        HULO_CUDA(compact_launch(val, dist, (uint32_t)rows_total, h->scratch1.as<uint64_t>(), (uint32_t)n_segs, d_blocks,
+                                 nullptr, o_i, o_j, o_d, d_seg_out, d_total, h->stream));
+        h->launches += kCompactLaunches;
+        h_seg_out.resize(n_segs + 2);
+        HULO_CUDA(cudaMemcpyAsync(h_seg_out.data(), d_total, (n_segs + 2) * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+        HULO_CUDA(cudaStreamSynchronize(h->stream));
+        const uint64_t total = h_seg_out[0];
+        if (!overflow && total_out + total <= cap) {
+            if (total > 0) {
+                HULO_ARG(out_i != nullptr && out_j != nullptr, "null output");
+                HULO_CUDA(cudaMemcpyAsync(out_i + total_out, o_i, total * 4, cudaMemcpyDeviceToHost, h->stream));
+                HULO_CUDA(cudaMemcpyAsync(out_j + total_out, o_j, total * 4, cudaMemcpyDeviceToHost, h->stream));
+                if (out_d0) HULO_CUDA(cudaMemcpyAsync(out_d0 + total_out, o_d, total * 4, cudaMemcpyDeviceToHost, h->stream));
+                HULO_CUDA(cudaStreamSynchronize(h->stream));
+            }
+            size_t k = total_out;
+            for (size_t ql = 0; ql < nb; ++ql)
+                for (size_t v = 0; v < n_views; ++v) {
+                    const uint32_t c = (uint32_t)(h_seg_out[2 + ql * n_views + v] - h_seg_out[1 + ql * n_views + v]);
+                    if (counts) counts[members[ql] * n_views + v] = c;
+                    for (uint32_t m = 0; m < c; ++m, ++k) {
+                        if (out_query) out_query[k] = (uint32_t)members[ql];
+                        if (out_view) out_view[k] = (uint32_t)v;
+                    }
+                }
+        } else {
+            overflow = true;
+        }
+        total_out += total;
+    }
+    *n_out = total_out;
+    if (overflow) {
+        set_error("hulo_match_to_queries: %zu matches, capacity %zu", total_out, cap);
+        return HULO_ERR_CAPACITY;
+    }
+    return HULO_OK;
+}
+
 // ------------------------------------------------ image-pair matching (reconstruction)
 int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size_t n_pairs, float ratio,
                      unsigned flags, uint64_t *pair_offsets, uint32_t *out_i, uint32_t *out_j, size_t cap,

@@ -162,39 +162,22 @@ int hulo_engine_configure(hulo_engine *e, float ratio, int min_putative, int min
     return HULO_OK;
 }
 
-int hulo_engine_localize(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t q_stride, const double *qxy,
-                         const uint32_t *views, size_t n_views, uint64_t seed, double *pose12, int *localized,
-                         uint32_t *corr_qfeat, uint32_t *corr_landmark, size_t *n_corr, int32_t *inliers,
-                         size_t *n_inliers, double *times_ms) {
-    HULO_ARG(e != nullptr && pose12 != nullptr && localized != nullptr, "null argument");
-    HULO_ARG(nq == 0 || (qdesc != nullptr && qxy != nullptr), "null query");
-    *localized = 0;
-    if (n_corr) *n_corr = 0;
-    if (n_inliers) *n_inliers = 0;
-    if (times_ms) times_ms[0] = times_ms[1] = times_ms[2] = 0.0;
-    if (views == nullptr) n_views = e->n_views;
-    const double t0 = now_ms();
-
-    // ---- putative matching, hulo::matchAKAZEToQuery (LocalizeEngine.cc:423)
-    const size_t cap = hulo_db_rows(e->map);
-    e->m_view.resize(std::max<size_t>(cap, 1));
-    e->m_i.resize(std::max<size_t>(cap, 1));
-    e->m_j.resize(std::max<size_t>(cap, 1));
-    e->m_d0.resize(std::max<size_t>(cap, 1));
-    e->view_counts.assign(std::max<size_t>(n_views, 1), 0);
-    size_t n_m = 0;
-    int rc = hulo_match_to_query(e->h, e->map, views, n_views, qdesc, nq, q_stride, e->ratio, e->m_view.data(),
-                                 e->m_i.data(), e->m_j.data(), e->m_d0.data(), cap, &n_m, e->view_counts.data());
-    if (rc != HULO_OK) return rc;
+// Stages after the putative matching, shared by the single and the batched entry points:
+// view filter, 2D-3D assembly, resection, pose.  m_* are the matches of this query grouped by
+// view position (view_counts[v] entries each, emission order).
+static int assemble_and_resect(hulo_engine *e, size_t nq, const double *qxy, const uint32_t *views, size_t n_views,
+                               const uint32_t *m_i, const uint32_t *m_j, const int32_t *m_d0,
+                               const uint32_t *view_counts, uint64_t seed, double *pose12, int *localized,
+                               uint32_t *corr_qfeat, uint32_t *corr_landmark, size_t *n_corr, int32_t *inliers,
+                               size_t *n_inliers, double *t_assembly, double *t_pnp) {
     const double t1 = now_ms();
-
     // ---- 2D-3D assembly, hulo::matchProviderToMatchSet (SfMDataUtils.cpp:59-125).
     // The reference walks a std::map keyed by (view id, query id): ascending view id, and inside
     // a view the matches in emission order.  featDist[(v,q)][j] is the distance of the LAST
     // match of view v onto query feature j (MatchUtils.cpp:351); every candidate of that view for
     // j is weighed with it, and a candidate replaces the current one only if strictly closer.
     std::vector<size_t> start(n_views + 1, 0);
-    for (size_t v = 0; v < n_views; ++v) start[v + 1] = start[v] + e->view_counts[v];
+    for (size_t v = 0; v < n_views; ++v) start[v + 1] = start[v] + view_counts[v];
     std::vector<size_t> order(n_views);
     for (size_t v = 0; v < n_views; ++v) order[v] = v;
     if (views)
@@ -210,17 +193,17 @@ int hulo_engine_localize(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t
         if ((int32_t)view_id == prev_view_id) continue;              // a view listed twice: one map key
         prev_view_id = (int32_t)view_id;
         // views with fewer putative matches than the threshold are dropped (LocalizeEngine.cc:428-434)
-        if ((int)e->view_counts[v] < e->min_putative) continue;
+        if ((int)view_counts[v] < e->min_putative) continue;
         for (size_t k = start[v]; k < start[v + 1]; ++k) {
-            const uint32_t j = e->m_j[k];
-            e->fd[j] = e->m_d0[k];
+            const uint32_t j = m_j[k];
+            e->fd[j] = m_d0[k];
             e->fd_stamp[j] = (int32_t)oi;
         }
         for (size_t k = start[v]; k < start[v + 1]; ++k) {
-            const int32_t lmi = e->lm_of_row[e->seg[view_id] + e->m_i[k]];
+            const int32_t lmi = e->lm_of_row[e->seg[view_id] + m_i[k]];
             if (lmi < 0) continue;                                     // feature has no landmark
             const uint32_t lm = (uint32_t)lmi;
-            const uint32_t j = e->m_j[k];
+            const uint32_t j = m_j[k];
             if (e->fd_stamp[j] != (int32_t)oi) continue;
             const int32_t d = e->fd[j];
             if (e->best_lm[j] < 0 || (float)e->best_d[j] > (float)d) {
@@ -252,8 +235,8 @@ int hulo_engine_localize(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t
         size_t n_inl = 0;
         double err_max = 0.0;
         int found = 0;
-        rc = hulo_resect_acransac(e->h, e->x2d.data(), e->X3d.data(), N, e->K, e->max_iter, seed, P, e->inl.data(),
-                                  &n_inl, &err_max, &found);
+        int rc = hulo_resect_acransac(e->h, e->x2d.data(), e->X3d.data(), N, e->K, e->max_iter, seed, P, e->inl.data(),
+                                      &n_inl, &err_max, &found);
         if (rc != HULO_OK) return rc;
         if (inliers) memcpy(inliers, e->inl.data(), n_inl * sizeof(int32_t));
         if (n_inliers) *n_inliers = n_inl;
@@ -267,7 +250,84 @@ int hulo_engine_localize(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t
         }
     }
     const double t3 = now_ms();
-    if (times_ms) { times_ms[0] = t1 - t0; times_ms[1] = t2 - t1; times_ms[2] = t3 - t2; }
+    if (t_assembly) *t_assembly += t2 - t1;
+    if (t_pnp) *t_pnp += t3 - t2;
+    return HULO_OK;
+}
+
+int hulo_engine_localize(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t q_stride, const double *qxy,
+                         const uint32_t *views, size_t n_views, uint64_t seed, double *pose12, int *localized,
+                         uint32_t *corr_qfeat, uint32_t *corr_landmark, size_t *n_corr, int32_t *inliers,
+                         size_t *n_inliers, double *times_ms) {
+    HULO_ARG(e != nullptr && pose12 != nullptr && localized != nullptr, "null argument");
+    HULO_ARG(nq == 0 || (qdesc != nullptr && qxy != nullptr), "null query");
+    *localized = 0;
+    if (n_corr) *n_corr = 0;
+    if (n_inliers) *n_inliers = 0;
+    if (times_ms) times_ms[0] = times_ms[1] = times_ms[2] = 0.0;
+    if (views == nullptr) n_views = e->n_views;
+    const double t0 = now_ms();
+
+    // ---- putative matching, hulo::matchAKAZEToQuery (LocalizeEngine.cc:423)
+    const size_t cap = std::max<size_t>(hulo_db_rows(e->map), 1);
+    e->m_view.resize(cap);
+    e->m_i.resize(cap);
+    e->m_j.resize(cap);
+    e->m_d0.resize(cap);
+    e->view_counts.assign(std::max<size_t>(n_views, 1), 0);
+    size_t n_m = 0;
+    int rc = hulo_match_to_query(e->h, e->map, views, n_views, qdesc, nq, q_stride, e->ratio, e->m_view.data(),
+                                 e->m_i.data(), e->m_j.data(), e->m_d0.data(), cap, &n_m, e->view_counts.data());
+    if (rc != HULO_OK) return rc;
+    if (times_ms) times_ms[0] = now_ms() - t0;
+    return assemble_and_resect(e, nq, qxy, views, n_views, e->m_i.data(), e->m_j.data(), e->m_d0.data(),
+                               e->view_counts.data(), seed, pose12, localized, corr_qfeat, corr_landmark, n_corr,
+                               inliers, n_inliers, times_ms ? times_ms + 1 : nullptr, times_ms ? times_ms + 2 : nullptr);
+}
+
+int hulo_engine_localize_batch(hulo_engine *e, size_t n_queries, const uint8_t *qdesc, size_t q_stride,
+                               const uint64_t *q_offsets, const double *qxy, const uint32_t *views, size_t n_views,
+                               uint64_t seed, double *pose12, int *localized, uint32_t *n_corr, uint32_t *n_inliers,
+                               double *times_ms) {
+    HULO_ARG(e != nullptr, "null engine");
+    HULO_ARG(n_queries == 0 || (q_offsets != nullptr && pose12 != nullptr && localized != nullptr), "null argument");
+    if (times_ms) times_ms[0] = times_ms[1] = times_ms[2] = 0.0;
+    if (n_queries == 0) return HULO_OK;
+    HULO_ARG(q_offsets[n_queries] == 0 || (qdesc != nullptr && qxy != nullptr), "null query");
+    if (views == nullptr) n_views = e->n_views;
+    const double t0 = now_ms();
+    // ---- putative matching of every query image in one pass
+    std::vector<uint32_t> counts(n_queries * std::max<size_t>(n_views, 1), 0);
+    size_t cap = std::max<size_t>(e->m_i.size(), 1 << 20), n_m = 0;
+    for (;;) {
+        e->m_i.resize(cap);
+        e->m_j.resize(cap);
+        e->m_d0.resize(cap);
+        int rc = hulo_match_to_queries(e->h, e->map, views, n_views, qdesc, q_stride, q_offsets, n_queries, e->ratio,
+                                       nullptr, nullptr, e->m_i.data(), e->m_j.data(), e->m_d0.data(), cap, &n_m,
+                                       counts.data());
+        if (rc == HULO_ERR_CAPACITY) { cap = n_m + n_m / 8; continue; }
+        if (rc != HULO_OK) return rc;
+        break;
+    }
+    if (times_ms) times_ms[0] = now_ms() - t0;
+    size_t k0 = 0;
+    for (size_t q = 0; q < n_queries; ++q) {
+        const size_t nq = (size_t)(q_offsets[q + 1] - q_offsets[q]);
+        const uint32_t *vc = counts.data() + q * n_views;
+        size_t n_q_matches = 0;
+        for (size_t v = 0; v < n_views; ++v) n_q_matches += vc[v];
+        localized[q] = 0;
+        size_t nc = 0, ni = 0;
+        int rc = assemble_and_resect(e, nq, qxy + 2 * q_offsets[q], views, n_views, e->m_i.data() + k0,
+                                     e->m_j.data() + k0, e->m_d0.data() + k0, vc, seed + q, pose12 + 12 * q,
+                                     localized + q, nullptr, nullptr, &nc, nullptr, &ni,
+                                     times_ms ? times_ms + 1 : nullptr, times_ms ? times_ms + 2 : nullptr);
+        if (rc != HULO_OK) return rc;
+        if (n_corr) n_corr[q] = (uint32_t)nc;
+        if (n_inliers) n_inliers[q] = (uint32_t)ni;
+        k0 += n_q_matches;
+    }
     return HULO_OK;
 }
 

@@ -189,6 +189,34 @@ class HuloGpu:
         return dict(view=ov[:k].copy(), i=oi[:k].copy(), j=oj[:k].copy(), d0=od[:k].copy(),
                     view_counts=vc[:n_views].copy())
 
+    def match_to_queries(self, map_db, queries, q_offsets, ratio, views=None, cap=None):
+        """hulo_match_to_queries -> dict(query, view, i, j, d0, counts[n_queries, n_views])."""
+        queries = _rows(queries)
+        q_offsets = np.ascontiguousarray(q_offsets, np.uint64)
+        nQ = len(q_offsets) - 1
+        if views is not None:
+            views = np.ascontiguousarray(views, dtype=np.uint32)
+            n_views = len(views)
+        else:
+            n_views = map_db.n_segments
+        cap = (1 << 20) if cap is None else cap
+        while True:
+            oq = np.empty(cap, np.uint32); ov = np.empty(cap, np.uint32); oi = np.empty(cap, np.uint32)
+            oj = np.empty(cap, np.uint32); od = np.empty(cap, np.int32)
+            counts = np.zeros((max(nQ, 1), max(n_views, 1)), np.uint32)
+            n = C.c_size_t(0)
+            st = self.lib.hulo_match_to_queries(self.h, map_db.h, _ptr(views), n_views, _ptr(queries),
+                                                queries.shape[1] if queries.shape[0] else 64, _ptr(q_offsets), nQ,
+                                                ratio, _ptr(oq), _ptr(ov), _ptr(oi), _ptr(oj), _ptr(od), cap,
+                                                C.byref(n), _ptr(counts))
+            if st == _lib.ERR_CAPACITY:
+                cap = int(n.value)
+                continue
+            check(st)
+            k = n.value
+            return dict(query=oq[:k].copy(), view=ov[:k].copy(), i=oi[:k].copy(), j=oj[:k].copy(), d0=od[:k].copy(),
+                        counts=counts[:nQ, :n_views].copy())
+
     def match_pairs(self, db, pairs, ratio, flags=_lib.PAIR_REFERENCE, cap=None):
         """hulo_match_pairs -> (pair_offsets uint64[P+1], i, j)."""
         pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
@@ -309,6 +337,27 @@ class LocalizeEngine:
         return dict(localized=bool(loc.value), center=pose[:3].copy(), R=pose[3:].reshape(3, 3).copy(),
                     corr_qfeat=cq[:nc.value].copy(), corr_landmark=cl[:nc.value].copy(),
                     inliers=inl[:ni.value].copy(), times_ms=times)
+
+    def localize_batch(self, qdescs, qxys, views=None, seed=1):
+        """qdescs / qxys: lists of per-image arrays.  Returns dict of per-image arrays."""
+        nQ = len(qdescs)
+        off = np.zeros(nQ + 1, np.uint64)
+        off[1:] = np.cumsum([d.shape[0] for d in qdescs])
+        desc = _rows(np.concatenate(qdescs, axis=0)) if nQ else np.zeros((0, 64), np.uint8)
+        xy = np.ascontiguousarray(np.concatenate(qxys, axis=0), np.float64) if nQ else np.zeros((0, 2))
+        n_views = 0
+        if views is not None:
+            views = np.ascontiguousarray(views, np.uint32)
+            n_views = len(views)
+        pose = np.zeros((max(nQ, 1), 12)); loc = np.zeros(max(nQ, 1), np.int32)
+        nc = np.zeros(max(nQ, 1), np.uint32); ni = np.zeros(max(nQ, 1), np.uint32)
+        times = np.zeros(3)
+        check(self.lib.hulo_engine_localize_batch(self.h, nQ, _ptr(desc), desc.shape[1] if desc.shape[0] else 64,
+                                                  _ptr(off), _ptr(xy), _ptr(views), n_views, seed, _ptr(pose),
+                                                  _ptr(loc), _ptr(nc), _ptr(ni), _ptr(times)))
+        return dict(localized=loc[:nQ].astype(bool), center=pose[:nQ, :3].copy(),
+                    R=pose[:nQ, 3:].reshape(-1, 3, 3).copy(), n_corr=nc[:nQ].copy(), n_inliers=ni[:nQ].copy(),
+                    times_ms=times)
 
     def close(self):
         if self.h is not None:

@@ -172,4 +172,28 @@ def localization_scene(n_views, feats_per_view, n_landmarks, nq, seed, track_fra
     return dict(rows=np.concatenate(rows), seg_offsets=np.array(off, np.uint64),
                 obs_view=np.array(obs_view, np.uint32), obs_feat=np.array(obs_feat, np.uint32),
                 obs_landmark=np.array(obs_lm, np.uint32), landmark_X=X, K=K.copy(), R=R, t=t,
-                center=-R.T @ t, q_desc=q_desc, q_xy=q_xy, q_truth=q_truth)
+                center=-R.T @ t, q_desc=q_desc, q_xy=q_xy, q_truth=q_truth, lm_desc=lm_desc)
+
+
+def extra_query(scene, nq, seed, query_inlier_frac=0.35, noise_px=0.7, flip_p=0.08):
+    """Another query image of the same map from a nearby pose (a few degrees / decimetres away):
+    the concurrent requests of the batched server mode.  Returns dict(q_desc, q_xy, R, t, center)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    K, X = scene["K"], scene["landmark_X"]
+    dR = rodrigues(rng.normal(size=3) * np.deg2rad(3.0))
+    R = dR @ scene["R"]
+    t = dR @ scene["t"] + rng.normal(size=3) * 0.15
+    Xc = X @ R.T + t
+    uv = Xc @ K.T
+    uv = uv[:, :2] / uv[:, 2:]
+    vis = np.nonzero((Xc[:, 2] > 1.0) & (uv[:, 0] >= 0) & (uv[:, 0] < IMAGE_WH[0]) & (uv[:, 1] >= 0)
+                     & (uv[:, 1] < IMAGE_WH[1]))[0]
+    n_in = min(int(nq * query_inlier_frac), len(vis))
+    q_lms = rng.choice(vis, size=n_in, replace=False)
+    q_desc = np.concatenate([_noisy_copies(scene["lm_desc"][q_lms], seed + 3, flip_p), random_rows(nq - n_in, seed + 4)])
+    xy = uv[q_lms] + rng.normal(scale=noise_px, size=(n_in, 2))
+    q_xy = np.concatenate([xy, np.stack([rng.uniform(0, IMAGE_WH[0], nq - n_in),
+                                         rng.uniform(0, IMAGE_WH[1], nq - n_in)], axis=1)])
+    perm = rng.permutation(nq)
+    return dict(q_desc=q_desc[perm], q_xy=q_xy[perm], R=R, t=t, center=-R.T @ t)
+

@@ -71,3 +71,52 @@ def test_localize_respects_thresholds(gpu):
     eng = LocalizeEngine(gpu, **kw, min_inliers=10 ** 6)       # resection runs, result rejected (:560)
     r = eng.localize(sc["q_desc"], sc["q_xy"]); eng.close()
     assert not r["localized"] and len(r["inliers"]) > 10
+
+
+def test_match_to_queries_equals_single_calls(gpu):
+    """The batched matching pass returns, per query image, exactly what hulo_match_to_query does."""
+    sc = synth.localization_scene(12, 600, 2500, 500, 21)
+    qs = [sc["q_desc"]] + [synth.extra_query(sc, n, 30 + k)["q_desc"] for k, n in enumerate((300, 1, 700))]
+    qs.insert(2, np.zeros((0, 64), np.uint8))                      # an image without descriptors
+    off = np.zeros(len(qs) + 1, np.uint64); off[1:] = np.cumsum([q.shape[0] for q in qs])
+    db = gpu.db(sc["rows"], sc["seg_offsets"])
+    try:
+        for views in (None, [7, 2, 3, 4]):
+            import os
+            for budget in (None, "9000"):                          # second pass: several sub-batches
+                if budget:
+                    os.environ["HULO_QUERY_BATCH_ROWS"] = budget
+                b = gpu.match_to_queries(db, np.concatenate(qs), off, 0.6, views=views, cap=64)
+                os.environ.pop("HULO_QUERY_BATCH_ROWS", None)
+                k = 0
+                for q, rows in enumerate(qs):
+                    s = gpu.match_to_query(db, rows, 0.6, views=None if views is None else np.array(views, np.uint32))
+                    n = len(s["i"])
+                    assert (b["query"][k:k + n] == q).all()
+                    assert np.array_equal(b["view"][k:k + n], s["view"]) and np.array_equal(b["i"][k:k + n], s["i"])
+                    assert np.array_equal(b["j"][k:k + n], s["j"]) and np.array_equal(b["d0"][k:k + n], s["d0"])
+                    assert np.array_equal(b["counts"][q], s["view_counts"])
+                    k += n
+                assert k == len(b["i"]) and k > 200
+    finally:
+        db.free()
+
+
+def test_localize_batch(gpu):
+    sc = synth.localization_scene(16, 700, 3000, 800, 23)
+    extra = [synth.extra_query(sc, 800, 40 + k) for k in range(5)]
+    eng = LocalizeEngine(gpu, sc["rows"], sc["seg_offsets"], sc["obs_view"], sc["obs_feat"], sc["obs_landmark"],
+                         sc["landmark_X"], sc["K"], ratio=0.6)
+    try:
+        descs = [sc["q_desc"]] + [e["q_desc"] for e in extra]
+        xys = [sc["q_xy"]] + [e["q_xy"] for e in extra]
+        centres = [sc["center"]] + [e["center"] for e in extra]
+        b = eng.localize_batch(descs, xys, seed=3)
+        for q in range(len(descs)):
+            s = eng.localize(descs[q], xys[q], seed=3 + q)        # the batch uses seed + q
+            assert b["localized"][q] and s["localized"]
+            assert b["n_corr"][q] == len(s["corr_qfeat"]) and b["n_inliers"][q] == len(s["inliers"])
+            assert np.allclose(b["center"][q], s["center"], atol=1e-12) and np.allclose(b["R"][q], s["R"], atol=1e-12)
+            assert np.linalg.norm(b["center"][q] - centres[q]) < 0.05
+    finally:
+        eng.close()

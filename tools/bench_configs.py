@@ -61,6 +61,31 @@ def scoring(g, name, H, N, seed):
                       "note": "wall clock of hulo_score_resection incl. H2D of models and D2H of scores"}), flush=True)
 
 
+def batched_server(g, name, n_views, feats, n_landmarks, n_queries, nq, seed):
+    """BASELINE.json config 4 end to end: concurrent query images against one resident map."""
+    from sfmlocalization_b200.gpu import LocalizeEngine
+    t0 = time.perf_counter()
+    sc = synth.localization_scene(n_views, feats, n_landmarks, nq, seed)
+    qs = [synth.extra_query(sc, nq, seed + 10 + k) for k in range(n_queries)]
+    gen_s = time.perf_counter() - t0
+    eng = LocalizeEngine(g, sc["rows"], sc["seg_offsets"], sc["obs_view"], sc["obs_feat"], sc["obs_landmark"],
+                         sc["landmark_X"], sc["K"], ratio=0.6)
+    descs = [q["q_desc"] for q in qs]; xys = [q["q_xy"] for q in qs]
+    eng.localize_batch(descs[:2], xys[:2])
+    t0 = time.perf_counter()
+    b = eng.localize_batch(descs, xys, seed=5)
+    dt = time.perf_counter() - t0
+    eng.close()
+    err = [float(np.linalg.norm(b["center"][k] - qs[k]["center"])) for k in range(n_queries) if b["localized"][k]]
+    dist = float(n_queries) * nq * sc["rows"].shape[0]
+    print(json.dumps({"config": name, "queries": n_queries, "query_rows": nq, "map_rows": int(sc["rows"].shape[0]),
+                      "wall_s": dt, "localizations_per_s": n_queries / dt, "gdist_per_s_wall": dist / dt / 1e9,
+                      "stage_ms_total": {"putMatch": b["times_ms"][0], "assembly": b["times_ms"][1], "PnP": b["times_ms"][2]},
+                      "fraction_localized": float(b["localized"].mean()),
+                      "centre_error_m_median": float(np.median(err)) if err else None,
+                      "scene_generation_s": gen_s}), flush=True)
+
+
 def main():
     which = sys.argv[1:] or ["c1", "c1r", "c2", "c4", "c5", "k2"]
     with HuloGpu(0) as g:
@@ -74,6 +99,9 @@ def main():
             flat(g, "C4 768000 x 2000000", 768000, 2000000, 4000, steps=1)
         if "c5" in which:
             flat(g, "C5 one of 8 shards: 16384 x 6250000", 16384, 6250000, 5000, steps=2)
+        if "c4e" in which:
+            batched_server(g, "C4 batched server: 256 queries x 3000 vs 2M-descriptor map, end to end", 1000, 2000,
+                           200000, 256, 3000, 4100)
         if "k2" in which:
             for N in (100, 500, 2000):
                 scoring(g, "K2 scoring 4096 triplets x <=4 models", 16384, N, 4000 + N)

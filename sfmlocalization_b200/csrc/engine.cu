@@ -298,7 +298,9 @@ int hulo_engine_localize_batch(hulo_engine *e, size_t n_queries, const uint8_t *
     const double t0 = now_ms();
     // ---- putative matching of every query image in one pass
     std::vector<uint32_t> counts(n_queries * std::max<size_t>(n_views, 1), 0);
-    size_t cap = std::max<size_t>(e->m_i.size(), 1 << 20), n_m = 0;
+    // room for four matches per query descriptor; a retry (which repeats the whole pass) only
+    // happens beyond that
+    size_t cap = std::max<size_t>(std::max<size_t>(e->m_i.size(), 1 << 20), 4 * (size_t)q_offsets[n_queries]), n_m = 0;
     for (;;) {
         e->m_i.resize(cap);
         e->m_j.resize(cap);

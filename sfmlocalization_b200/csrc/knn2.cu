@@ -451,7 +451,7 @@ cudaError_t info_variant(int *regs, int *ctas, size_t *smem) {
     X(256, 8, 7, 1) X(256, 8, 7, 2) X(256, 8, 7, 3) X(256, 8, 8, 0) X(256, 8, 8, 1) X(256, 8, 8, 3) \
     X(512, 4, 7, 0) X(512, 4, 7, 1) X(512, 4, 7, 3) X(512, 4, 8, 1) X(512, 4, 8, 3) X(512, 4, 9, 0) \
     X(256, 4, 7, 0) X(256, 4, 7, 3) X(256, 4, 8, 3) X(128, 8, 7, 0) X(128, 4, 7, 0) X(128, 4, 7, 3) \
-    X(1024, 2, 7, 0) X(1024, 2, 7, 3) X(1024, 2, 8, 3)
+    X(768, 2, 8, 1) X(768, 2, 7, 1) X(768, 2, 8, 0) X(640, 3, 8, 1) X(640, 3, 7, 1) X(640, 3, 8, 0) X(384, 5, 8, 1)
 
 cudaError_t knn2_launch(const KnnParams &p, const KnnConfig &cfg, int grid_ctas, cudaStream_t stream) {
 #define X(T, Q, C, O) \

@@ -133,13 +133,17 @@ def _noisy_copies(base, seed, flip_p):
 
 
 def localization_scene(n_views, feats_per_view, n_landmarks, nq, seed, track_frac=0.6, query_inlier_frac=0.35,
-                       noise_px=0.7, flip_p=0.08, K=K_IPHONE6):
+                       noise_px=0.7, flip_p=0.08, K=K_IPHONE6, window=None):
     """A synthetic SfM map and one query image.
     Map: n_landmarks 3D points, each with a base descriptor; every view holds feats_per_view
     features of which track_frac observe a random landmark (descriptor = noisy copy of the
     landmark's) and the rest are clutter.  Query: nq features, query_inlier_frac of them observe
     landmarks (projected with the true pose + pixel noise), the rest are clutter at random
-    positions.  Returns a dict with everything hulo_engine_create / localize need plus truth."""
+    positions.  window: when given, every view observes landmarks from a window of that many
+    consecutive landmark ids (views march through the id range) and the query from the window in
+    the middle -- the co-visibility structure of a real map, where a query overlaps a few dozen
+    views strongly instead of all views weakly.
+    Returns a dict with everything hulo_engine_create / localize need plus truth."""
     rng = np.random.Generator(np.random.PCG64(seed))
     sc = resection_scene(n_landmarks, seed + 1, outlier_frac=0.0, noise_px=0.0, K=K)
     X, R, t = sc["X3d"], sc["R"], sc["t"]
@@ -148,7 +152,11 @@ def localization_scene(n_views, feats_per_view, n_landmarks, nq, seed, track_fra
     obs_view, obs_feat, obs_lm = [], [], []
     for v in range(n_views):
         n_obs = int(feats_per_view * track_frac)
-        lms = rng.choice(n_landmarks, size=min(n_obs, n_landmarks), replace=False)
+        if window:
+            w0 = int((n_landmarks - window) * v / max(1, n_views - 1))
+            lms = w0 + rng.choice(window, size=min(n_obs, window), replace=False)
+        else:
+            lms = rng.choice(n_landmarks, size=min(n_obs, n_landmarks), replace=False)
         d_obs = _noisy_copies(lm_desc[lms], seed * 7919 + v, flip_p)
         d_clutter = random_rows(feats_per_view - len(lms), seed * 104729 + v)
         d = np.concatenate([d_obs, d_clutter], axis=0)
@@ -158,7 +166,10 @@ def localization_scene(n_views, feats_per_view, n_landmarks, nq, seed, track_fra
         rows.append(d); off.append(off[-1] + d.shape[0])
         obs_view += [v] * len(lms); obs_feat += inv[:len(lms)].tolist(); obs_lm += lms.tolist()
     n_in = int(nq * query_inlier_frac)
-    q_lms = rng.choice(n_landmarks, size=min(n_in, n_landmarks), replace=False)
+    if window:
+        q_lms = (n_landmarks - window) // 2 + rng.choice(window, size=min(n_in, window), replace=False)
+    else:
+        q_lms = rng.choice(n_landmarks, size=min(n_in, n_landmarks), replace=False)
     q_desc = np.concatenate([_noisy_copies(lm_desc[q_lms], seed + 3, flip_p), random_rows(nq - len(q_lms), seed + 4)])
     Xc = X[q_lms] @ R.T + t
     uv = (Xc @ K.T); uv = uv[:, :2] / uv[:, 2:]
@@ -172,7 +183,7 @@ def localization_scene(n_views, feats_per_view, n_landmarks, nq, seed, track_fra
     return dict(rows=np.concatenate(rows), seg_offsets=np.array(off, np.uint64),
                 obs_view=np.array(obs_view, np.uint32), obs_feat=np.array(obs_feat, np.uint32),
                 obs_landmark=np.array(obs_lm, np.uint32), landmark_X=X, K=K.copy(), R=R, t=t,
-                center=-R.T @ t, q_desc=q_desc, q_xy=q_xy, q_truth=q_truth, lm_desc=lm_desc)
+                center=-R.T @ t, q_desc=q_desc, q_xy=q_xy, q_truth=q_truth, lm_desc=lm_desc, window=window)
 
 
 def extra_query(scene, nq, seed, query_inlier_frac=0.35, noise_px=0.7, flip_p=0.08):
@@ -186,8 +197,13 @@ def extra_query(scene, nq, seed, query_inlier_frac=0.35, noise_px=0.7, flip_p=0.
     Xc = X @ R.T + t
     uv = Xc @ K.T
     uv = uv[:, :2] / uv[:, 2:]
-    vis = np.nonzero((Xc[:, 2] > 1.0) & (uv[:, 0] >= 0) & (uv[:, 0] < IMAGE_WH[0]) & (uv[:, 1] >= 0)
-                     & (uv[:, 1] < IMAGE_WH[1]))[0]
+    ok = (Xc[:, 2] > 1.0) & (uv[:, 0] >= 0) & (uv[:, 0] < IMAGE_WH[0]) & (uv[:, 1] >= 0) & (uv[:, 1] < IMAGE_WH[1])
+    if scene.get("window"):
+        w0 = (len(X) - scene["window"]) // 2 + int(rng.integers(-scene["window"] // 4, scene["window"] // 4 + 1))
+        inwin = np.zeros(len(X), bool)
+        inwin[max(0, w0):w0 + scene["window"]] = True
+        ok &= inwin
+    vis = np.nonzero(ok)[0]
     n_in = min(int(nq * query_inlier_frac), len(vis))
     q_lms = rng.choice(vis, size=n_in, replace=False)
     q_desc = np.concatenate([_noisy_copies(scene["lm_desc"][q_lms], seed + 3, flip_p), random_rows(nq - n_in, seed + 4)])

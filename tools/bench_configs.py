@@ -65,7 +65,7 @@ def batched_server(g, name, n_views, feats, n_landmarks, n_queries, nq, seed):
     """BASELINE.json config 4 end to end: concurrent query images against one resident map."""
     from sfmlocalization_b200.gpu import LocalizeEngine
     t0 = time.perf_counter()
-    sc = synth.localization_scene(n_views, feats, n_landmarks, nq, seed)
+    sc = synth.localization_scene(n_views, feats, n_landmarks, nq, seed, window=6000)
     qs = [synth.extra_query(sc, nq, seed + 10 + k) for k in range(n_queries)]
     gen_s = time.perf_counter() - t0
     eng = LocalizeEngine(g, sc["rows"], sc["seg_offsets"], sc["obs_view"], sc["obs_feat"], sc["obs_landmark"],

@@ -234,3 +234,50 @@ def krt_from_p(P):
     K = np.empty((3, 3)); R = np.empty((3, 3)); t = np.empty(3); c = np.empty(3)
     lib().orc_krt_from_p(_p(P), _p(K), _p(R), _p(t), _p(c))
     return K, R, t, c
+
+
+# ---------------------------------------------------------------- F-matrix geometric filter
+def precondition(w, h):
+    T = np.empty((3, 3))
+    lib().orc_precondition(int(w), int(h), _p(T))
+    return T
+
+
+def seven_point(x1, x2):
+    """orc_seven_point: 7 x 2 normalised points each -> up to three 3x3 F (x2^T F x1 = 0)."""
+    x1, x2 = _f64(x1), _f64(x2)
+    F = np.zeros((3, 3, 3))
+    n = lib().orc_seven_point(_p(x1), _p(x2), _p(F))
+    return F[:n].copy()
+
+
+def epipolar_errors(F, x1, x2):
+    F, x1, x2 = _f64(F), _f64(x1), _f64(x2)
+    err = np.empty(x1.shape[0])
+    lib().orc_epipolar_errors(_p(F), _p(x1), _p(x2), C.c_size_t(x1.shape[0]), _p(err))
+    return err
+
+
+def fmatrix_score(F, x1n, x2n, logalpha0, max_thr=np.inf):
+    F, x1n, x2n = _f64(F), _f64(x1n), _f64(x2n)
+    kb = C.c_size_t(0)
+    ek = C.c_double(0)
+    lib().orc_fmatrix_score.restype = C.c_double
+    nfa = lib().orc_fmatrix_score(_p(F), _p(x1n), _p(x2n), C.c_size_t(x1n.shape[0]), C.c_double(logalpha0),
+                                  C.c_double(max_thr), C.byref(kb), C.byref(ek))
+    return float(nfa), int(kb.value), float(ek.value)
+
+
+def fmatrix_acransac(xI, xJ, sizeI, sizeJ, precision_px=4.0, max_iter=1024, seed=1):
+    """orc_fmatrix_acransac -> dict(ok, F, inliers, error_max [px], nfa)."""
+    xI, xJ = _f64(xI), _f64(xJ)
+    N = xI.shape[0]
+    F = np.zeros((3, 3))
+    inl = np.empty(max(N, 1), np.int32)
+    n_inl = C.c_size_t(0)
+    emax = C.c_double(0)
+    nfa = C.c_double(0)
+    ok = lib().orc_fmatrix_acransac(_p(xI), _p(xJ), C.c_size_t(N), int(sizeI[0]), int(sizeI[1]), int(sizeJ[0]),
+                                    int(sizeJ[1]), C.c_double(precision_px), C.c_size_t(max_iter), C.c_uint64(seed),
+                                    _p(F), _p(inl), C.byref(n_inl), C.byref(emax), C.byref(nfa))
+    return dict(ok=bool(ok), F=F, inliers=inl[:n_inl.value].copy(), error_max=emax.value, nfa=nfa.value)

@@ -487,3 +487,261 @@ void orc_krt_from_p(const double *P, double *Kout, double *Rout, double *tout, d
     if (tout) memcpy(tout, t, sizeof t);
     if (centre) { double c[3]; m_tmulv(R, t, c); centre[0] = -c[0]; centre[1] = -c[1]; centre[2] = -c[2]; }
 }
+
+/* =====================================================================================
+ * Fundamental-matrix geometric filter: CPU restatement of hulo::geometricMatch
+ * (VisionLocalizeCommon/src/MatchUtils.cpp:372-420), which runs OpenMVG 1.1's
+ * GeometricFilter_FMatrix_AC(geomPrec, ransacRound) on every putative pair
+ * (callers: LocalizeEngine.cc:458, localization.cpp:450, computeFeaturesAndMatches.cpp:242).
+ * PARITY UNPINNED for the same reason as the resection above (OpenMVG is not vendored and
+ * the reference has no test).  Upstream files restated:
+ *   matching_image_collection/F_ACRobust.hpp                -> orc_fmatrix_acransac
+ *   robust_estimation/robust_estimator_ACRansacKernelAdaptator.hpp (ACKernelAdaptor,
+ *        point-to-line)                                     -> normalisation, logalpha0,
+ *                                                              multError 0.5, unormalizeError
+ *   multiview/conditioning.cpp (PreconditionerFromPoints)   -> orc_precondition
+ *   multiview/solver_fundamental_kernel.{hpp,cpp} (SevenPointSolver, EpipolarDistanceError)
+ *                                                           -> orc_seven_point, orc_epipolar_errors
+ *   numeric/poly.h (SolveCubicPolynomial)                   -> solve_cubic
+ * The 7-point solution set is cross-checked against cv2.findFundamentalMat(FM_7POINT).
+ * ===================================================================================== */
+
+/* T = [[s,0,-w s/2],[0,s,-h s/2],[0,0,1]], s = 1/sqrt(w h) */
+void orc_precondition(int w, int h, double *T) {
+    double s = 1.0 / sqrt((double)w * (double)h);
+    T[0] = s; T[1] = 0; T[2] = -0.5 * w * s;
+    T[3] = 0; T[4] = s; T[5] = -0.5 * h * s;
+    T[6] = 0; T[7] = 0; T[8] = 1.0;
+}
+
+static double det3r(const double *a, const double *b, const double *c) {
+    return a[0]*(b[1]*c[2]-b[2]*c[1]) - a[1]*(b[0]*c[2]-b[2]*c[0]) + a[2]*(b[0]*c[1]-b[1]*c[0]);
+}
+
+/* real roots of x^3 + a x^2 + b x + c, ascending (the GSL scheme upstream uses) */
+static int solve_cubic(double a, double b, double c, double *x) {
+    double q = a*a - 3*b, r = 2*a*a*a - 9*a*b + 27*c;
+    double Q = q/9, R = r/54, Q3 = Q*Q*Q, R2 = R*R;
+    double CR2 = 729*r*r, CQ3 = 2916*q*q*q;
+    if (R == 0 && Q == 0) { x[0] = x[1] = x[2] = -a/3; return 3; }
+    if (CR2 == CQ3) {
+        double sqrtQ = sqrt(Q);
+        if (R > 0) { x[0] = -2*sqrtQ - a/3; x[1] = sqrtQ - a/3; x[2] = sqrtQ - a/3; }
+        else       { x[0] = -sqrtQ - a/3;   x[1] = -sqrtQ - a/3; x[2] = 2*sqrtQ - a/3; }
+        return 3;
+    }
+    if (CR2 < CQ3) {
+        double sqrtQ = sqrt(Q), sqrtQ3 = sqrtQ*sqrtQ*sqrtQ, theta = acos(R/sqrtQ3), norm = -2*sqrtQ;
+        x[0] = norm*cos(theta/3) - a/3;
+        x[1] = norm*cos((theta + 2.0*M_PI)/3) - a/3;
+        x[2] = norm*cos((theta - 2.0*M_PI)/3) - a/3;
+        for (int i = 0; i < 2; ++i) for (int j = 0; j < 2 - i; ++j)
+            if (x[j] > x[j+1]) { double t = x[j]; x[j] = x[j+1]; x[j+1] = t; }
+        return 3;
+    }
+    double sgnR = R >= 0 ? 1 : -1;
+    double A = -sgnR * pow(fabs(R) + sqrt(R2 - Q3), 1.0/3.0);
+    double B = Q / A;
+    x[0] = A + B - a/3;
+    return 1;
+}
+
+/* Two vectors spanning the null space of the 7x9 epipolar system (Gauss-Jordan with full
+ * pivoting).  Any basis gives the same solution set {F1 + a F2 : det = 0} up to scale. */
+static int nullspace2(double A[7][9], double *f1, double *f2) {
+    int colperm[9];
+    for (int c = 0; c < 9; ++c) colperm[c] = c;
+    for (int k = 0; k < 7; ++k) {
+        int pr = k, pc = k; double best = 0;
+        for (int r = k; r < 7; ++r) for (int c = k; c < 9; ++c)
+            if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); pr = r; pc = c; }
+        if (best < 1e-14) return 0;                       /* rank deficient sample */
+        if (pr != k) for (int c = 0; c < 9; ++c) { double t = A[k][c]; A[k][c] = A[pr][c]; A[pr][c] = t; }
+        if (pc != k) { for (int r = 0; r < 7; ++r) { double t = A[r][k]; A[r][k] = A[r][pc]; A[r][pc] = t; }
+                       int t = colperm[k]; colperm[k] = colperm[pc]; colperm[pc] = t; }
+        double inv = 1.0 / A[k][k];
+        for (int c = 0; c < 9; ++c) A[k][c] *= inv;
+        for (int r = 0; r < 7; ++r) if (r != k) {
+            double m = A[r][k];
+            if (m != 0) for (int c = 0; c < 9; ++c) A[r][c] -= m * A[k][c];
+        }
+    }
+    /* free variables: permuted columns 7 and 8 */
+    for (int v = 0; v < 2; ++v) {
+        double z[9];
+        for (int k = 0; k < 7; ++k) z[k] = -A[k][7 + v];
+        z[7] = v == 0 ? 1 : 0; z[8] = v == 1 ? 1 : 0;
+        double *f = v == 0 ? f1 : f2;
+        for (int k = 0; k < 9; ++k) f[colperm[k]] = z[k];
+    }
+    return 1;
+}
+
+/* SevenPointSolver: x1, x2 are 7 x 2 (normalised) points; up to three row-major 3x3 F with
+ * x2^T F x1 = 0 and det F = 0, in ascending order of the cubic's root.  Returns the count. */
+int orc_seven_point(const double *x1, const double *x2, double *F) {
+    double A[7][9];
+    for (int i = 0; i < 7; ++i) {
+        double a = x1[2*i], b = x1[2*i+1], c = x2[2*i], d = x2[2*i+1];
+        A[i][0] = c*a; A[i][1] = c*b; A[i][2] = c;
+        A[i][3] = d*a; A[i][4] = d*b; A[i][5] = d;
+        A[i][6] = a;   A[i][7] = b;   A[i][8] = 1.0;
+    }
+    double f1[9], f2[9];
+    if (!nullspace2(A, f1, f2)) return 0;
+    /* det(F1 + t F2) = P0 + P1 t + P2 t^2 + P3 t^3 by multilinearity in the rows */
+    const double *r1 = f1, *r2 = f1 + 3, *r3 = f1 + 6, *s1 = f2, *s2 = f2 + 3, *s3 = f2 + 6;
+    double P0 = det3r(r1, r2, r3);
+    double P1 = det3r(s1, r2, r3) + det3r(r1, s2, r3) + det3r(r1, r2, s3);
+    double P2 = det3r(s1, s2, r3) + det3r(s1, r2, s3) + det3r(r1, s2, s3);
+    double P3 = det3r(s1, s2, s3);
+    double roots[3];
+    int n;
+    if (P3 == 0) return 0;
+    n = solve_cubic(P2/P3, P1/P3, P0/P3, roots);
+    int n_out = 0;
+    for (int k = 0; k < n; ++k) {
+        int ok = 1;
+        for (int e = 0; e < 9; ++e) { F[9*n_out + e] = f1[e] + roots[k]*f2[e]; if (!isfinite(F[9*n_out + e])) ok = 0; }
+        if (ok) ++n_out;
+    }
+    return n_out;
+}
+
+/* EpipolarDistanceError (= SimpleError): squared distance of x2 to the epipolar line F x1. */
+void orc_epipolar_errors(const double *F, const double *x1, const double *x2, size_t N, double *err) {
+    for (size_t i = 0; i < N; ++i) {
+        double a = x1[2*i], b = x1[2*i+1];
+        double l0 = F[0]*a + F[1]*b + F[2], l1 = F[3]*a + F[4]*b + F[5], l2 = F[6]*a + F[7]*b + F[8];
+        double d = l0*x2[2*i] + l1*x2[2*i+1] + l2;
+        err[i] = d*d / (l0*l0 + l1*l1);
+    }
+}
+
+float orc_logcombi_k(size_t k, size_t n) { return orc_logcombi(k, n); }
+
+/* 7 distinct positions in [0,total), ascending insertion like UniformSample */
+static void sample_k(uint64_t *state, size_t total, int k, size_t *out) {
+    for (int i = 0; i < k; ++i) {
+        size_t r = (size_t)(splitmix64(state) % (uint64_t)(total - i));
+        int j;
+        for (j = 0; j < i && r >= out[j]; ++j) ++r;
+        for (int m = i; m > j; --m) out[m] = out[m-1];
+        out[j] = r;
+    }
+}
+
+/*
+ * GeometricFilter_FMatrix_AC::Robust_estimation for one pair.
+ *   xI, xJ: N x 2 pixel coordinates of the putative matches; image sizes (wI,hI), (wJ,hJ);
+ *   precision_px = geomPrec (infinity allowed), max_iter = ransacRound, seed.
+ * Outputs: F (row-major, pixel coordinates: x_J^T F x_I = 0), inliers (indices sorted by
+ * residual), *n_inl, *error_max [px], *min_nfa.  Returns 1 iff #inliers > 2.5 * 7.
+ */
+int orc_fmatrix_acransac(const double *xI, const double *xJ, size_t N, int wI, int hI, int wJ, int hJ,
+                         double precision_px, size_t max_iter, uint64_t seed, double *Fout, int32_t *inliers,
+                         size_t *n_inl, double *error_max, double *min_nfa_out) {
+    *n_inl = 0; *error_max = 0.0; if (min_nfa_out) *min_nfa_out = 0.0;
+    const size_t S = 7;
+    if (N <= S) return 0;
+    double N1[9], N2[9];
+    orc_precondition(wI, hI, N1); orc_precondition(wJ, hJ, N2);
+    double *x1 = (double *)malloc(sizeof(double)*2*N), *x2 = (double *)malloc(sizeof(double)*2*N);
+    for (size_t i = 0; i < N; ++i) {
+        x1[2*i] = N1[0]*xI[2*i] + N1[2]; x1[2*i+1] = N1[4]*xI[2*i+1] + N1[5];
+        x2[2*i] = N2[0]*xJ[2*i] + N2[2]; x2[2*i+1] = N2[4]*xJ[2*i+1] + N2[5];
+    }
+    double D = sqrt((double)wJ*wJ + (double)hJ*hJ), Ar = (double)wJ*(double)hJ;
+    double logalpha0 = log10(2.0*D/Ar / N2[0]);
+    double mult = 0.5;
+    double maxThr = isinf(precision_px) ? INFINITY : precision_px*precision_px * N2[0]*N2[0];
+    double loge0 = log10(3.0 * (double)(N - S));
+    float *logc_n = (float *)malloc(sizeof(float)*(N+1)), *logc_k = (float *)malloc(sizeof(float)*(N+1));
+    for (size_t k = 0; k <= N; ++k) { logc_n[k] = orc_logcombi(k, N); logc_k[k] = orc_logcombi(S, k); }
+    double *err = (double *)malloc(sizeof(double)*N);
+    err_idx *ei = (err_idx *)malloc(sizeof(err_idx)*N);
+    size_t *pool = (size_t *)malloc(sizeof(size_t)*N), n_pool = N;
+    for (size_t i = 0; i < N; ++i) pool[i] = i;
+    size_t *best_inl = (size_t *)malloc(sizeof(size_t)*N), n_best = 0;
+    double best_F[9] = {0}, minNFA = INFINITY, errorMax = INFINITY;
+    uint64_t rng = seed;
+    size_t nIter = max_iter, nIterReserve = nIter/10;
+    nIter -= nIterReserve;
+    for (size_t iter = 0; iter < nIter; ++iter) {
+        size_t pos[7];
+        sample_k(&rng, n_pool, 7, pos);
+        double s1[14], s2[14];
+        for (int s = 0; s < 7; ++s) {
+            size_t id = pool[pos[s]];
+            s1[2*s] = x1[2*id]; s1[2*s+1] = x1[2*id+1]; s2[2*s] = x2[2*id]; s2[2*s+1] = x2[2*id+1];
+        }
+        double Fs[27];
+        int nm = orc_seven_point(s1, s2, Fs);
+        int better = 0;
+        for (int m = 0; m < nm; ++m) {
+            orc_epipolar_errors(Fs + 9*m, x1, x2, N, err);
+            for (size_t i = 0; i < N; ++i) { ei[i].e = isnan(err[i]) ? INFINITY : err[i]; ei[i].i = i; }
+            qsort(ei, N, sizeof(err_idx), cmp_err_idx);
+            /* bestNFA with startIndex 7 and the precision bound */
+            double bn = INFINITY; size_t bk = S;
+            for (size_t k = S + 1; k <= N && ei[k-1].e <= maxThr; ++k) {
+                double logalpha = logalpha0 + mult * log10(ei[k-1].e + (double)FLT_EPSILON);
+                double nfa = loge0 + logalpha*(double)(k - S) + (double)logc_n[k] + (double)logc_k[k];
+                if (nfa < bn) { bn = nfa; bk = k; }
+            }
+            if (bn < minNFA) {
+                better = 1; minNFA = bn; n_best = bk;
+                for (size_t i = 0; i < bk; ++i) best_inl[i] = ei[i].i;
+                errorMax = ei[bk-1].e;
+                memcpy(best_F, Fs + 9*m, sizeof best_F);
+            }
+        }
+        if ((better && minNFA < 0) || (iter + 1 == nIter && nIterReserve)) {
+            if (n_best == 0) { nIter++; nIterReserve--; }
+            else {
+                n_pool = n_best;
+                memcpy(pool, best_inl, sizeof(size_t)*n_best);
+                if (nIterReserve) { nIter = iter + 1 + nIterReserve; nIterReserve = 0; }
+            }
+        }
+    }
+    int ok = 0;
+    if (minNFA >= 0) n_best = 0;
+    if (n_best > 0) {
+        /* Unnormalize: F = N2^T F N1 ; error = sqrt(e) / N2(0,0) */
+        double T[9], N2t[9];
+        m_transpose(N2, N2t); m_mul(N2t, best_F, T); m_mul(T, N1, Fout);
+        *error_max = sqrt(errorMax) / N2[0];
+        for (size_t i = 0; i < n_best; ++i) inliers[i] = (int32_t)best_inl[i];
+        *n_inl = n_best;
+        ok = (double)n_best > 2.5 * 7.0;
+    }
+    if (min_nfa_out) *min_nfa_out = minNFA;
+    free(x1); free(x2); free(logc_n); free(logc_k); free(err); free(ei); free(pool); free(best_inl);
+    return ok;
+}
+
+/* NFA score of one F hypothesis (normalised coordinates) against all matches: the per-model
+ * body of the loop above, for per-hypothesis parity checks of the GPU scoring. */
+double orc_fmatrix_score(const double *F, const double *x1n, const double *x2n, size_t N, double logalpha0,
+                         double max_thr, size_t *k_best, double *err_k) {
+    const size_t S = 7;
+    double *err = (double *)malloc(sizeof(double)*(N ? N : 1));
+    orc_epipolar_errors(F, x1n, x2n, N, err);
+    for (size_t i = 0; i < N; ++i) if (isnan(err[i])) err[i] = INFINITY;
+    /* plain ascending sort of the values is enough for the score */
+    err_idx *ei = (err_idx *)malloc(sizeof(err_idx)*(N ? N : 1));
+    for (size_t i = 0; i < N; ++i) { ei[i].e = err[i]; ei[i].i = i; }
+    qsort(ei, N, sizeof(err_idx), cmp_err_idx);
+    double loge0 = log10(3.0 * (double)(N > S ? N - S : 1));
+    double bn = INFINITY; size_t bk = S;
+    for (size_t k = S + 1; k <= N && ei[k-1].e <= max_thr; ++k) {
+        double logalpha = logalpha0 + 0.5 * log10(ei[k-1].e + (double)FLT_EPSILON);
+        double nfa = loge0 + logalpha*(double)(k - S) + (double)orc_logcombi(k, N) + (double)orc_logcombi(S, k);
+        if (nfa < bn) { bn = nfa; bk = k; }
+    }
+    *k_best = bk;
+    *err_k = (bk >= 1 && bk <= N) ? ei[bk-1].e : INFINITY;
+    free(err); free(ei);
+    return bn;
+}

@@ -213,3 +213,25 @@ def extra_query(scene, nq, seed, query_inlier_frac=0.35, noise_px=0.7, flip_p=0.
     perm = rng.permutation(nq)
     return dict(q_desc=q_desc[perm], q_xy=q_xy[perm], R=R, t=t, center=-R.T @ t)
 
+
+
+def two_view_matches(N, seed, outlier_frac=0.4, noise_px=0.5, K=K_IPHONE6):
+    """Putative matches between two views of a 3D scene (the input of the F-matrix geometric
+    filter): N point pairs in pixels, a fraction replaced by uniform outliers in image J.
+    Returns dict(xI, xJ N x 2, inlier_mask, F_true with xJ^T F xI = 0, size (w, h))."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    X = np.stack([rng.uniform(-4, 4, N), rng.uniform(-2.5, 2.5, N), rng.uniform(5, 14, N)], axis=1)
+    R = rodrigues(rng.normal(size=3) * np.deg2rad(6.0))
+    t = np.array([rng.uniform(0.3, 0.8), rng.uniform(-0.2, 0.2), rng.uniform(-0.2, 0.2)])
+    uI = X @ K.T; xI = uI[:, :2] / uI[:, 2:]
+    XJ = X @ R.T + t
+    uJ = XJ @ K.T; xJ = uJ[:, :2] / uJ[:, 2:]
+    xI = xI + rng.normal(scale=noise_px, size=xI.shape)
+    xJ = xJ + rng.normal(scale=noise_px, size=xJ.shape)
+    out = rng.random(N) < outlier_frac
+    n_out = int(out.sum())
+    xJ[out] = np.stack([rng.uniform(0, IMAGE_WH[0], n_out), rng.uniform(0, IMAGE_WH[1], n_out)], axis=1)
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    Ki = np.linalg.inv(K)
+    F = Ki.T @ tx @ R @ Ki
+    return dict(xI=xI, xJ=xJ, inlier_mask=~out, F_true=F / np.linalg.norm(F), size=IMAGE_WH)

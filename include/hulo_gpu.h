@@ -186,6 +186,33 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
                          const double *K, size_t max_iter, uint64_t seed, double *P,
                          int32_t *inliers, size_t *n_inliers, double *error_max, int *found);
 
+/* --------------------------------------------- K3: F-matrix geometric filter */
+
+/* hulo::geometricMatch, MatchUtils.cpp:372-420 (decl MatchUtils.h:66-72): OpenMVG's
+ * GeometricFilter_FMatrix_AC(geomPrec, ransacRound) on every pair of the putative matches
+ * (LocalizeEngine.cc:458, localization.cpp:450, computeFeaturesAndMatches.cpp:242), without
+ * guided matching: a-contrario RANSAC over the 7-point fundamental-matrix solver, residual =
+ * squared distance to the epipolar line in image J, both images preconditioned by their size.
+ * All pairs run in one launch (one thread block per pair).
+ *   xI, xJ        total x 2 doubles: pixel positions of the matched features in image I / J,
+ *                 pairs back to back; pair p owns matches [pair_offsets[p], pair_offsets[p+1])
+ *   image_sizes   n_pairs x {wI, hI, wJ, hJ}
+ *   precision_px  geomPrec: upper bound of the inlier residual in pixels (INFINITY = none)
+ *   max_iter      ransacRound (25 in LocalizeParam.py:35, 200 CLI default, 500 ExtFeatAndMatch)
+ *   seed          pair p samples from the stream seeded with seed + 1000003 p, or with
+ *                 pair_seeds[p] when pair_seeds is not NULL (results then do not depend on
+ *                 how a pair list is split into calls)
+ * Outputs per pair: valid[p] = 1 iff a meaningful model (NFA < 0) with more than 2.5 * 7
+ * inliers exists (the pair keeps its key in map_geometricMatches); n_inliers[p]; the inlier
+ * positions inside the pair, in (residual, index) order like ACRANSAC's vec_inliers, at
+ * inliers[pair_offsets[p] ...] (capacity pair_offsets[n_pairs]); F (n_pairs x 9, row-major,
+ * pixel coordinates, x_J^T F x_I = 0), error_max (pixels) and nfa (log10) may be NULL.
+ * At most 16384 putative matches per pair. */
+int hulo_geometric_filter(hulo_gpu *h, const double *xI, const double *xJ, const uint64_t *pair_offsets,
+                          size_t n_pairs, const int32_t *image_sizes, double precision_px, size_t max_iter,
+                          uint64_t seed, const uint64_t *pair_seeds, int32_t *valid, uint32_t *n_inliers,
+                          int32_t *inliers, double *F, double *error_max, double *nfa);
+
 /* ------------------------------------------------- query localisation, end to end */
 
 typedef struct hulo_engine hulo_engine;
@@ -211,18 +238,29 @@ void hulo_engine_destroy(hulo_engine *e);
 int hulo_engine_configure(hulo_engine *e, float ratio, int min_putative, int min_points, int min_inliers,
                           size_t max_iter);
 
+/* Keypoint positions for the geometric filter (the Regions_Provider of LocalizeEngine.cc:458):
+ * map_xy holds 2 doubles per descriptor row of the map (same row order), view_wh the image
+ * size {w, h} of every view (View::ui_width / ui_height), query_w / query_h that of the
+ * query camera. */
+int hulo_engine_set_keypoints(hulo_engine *e, const double *map_xy, const int32_t *view_wh, int query_w,
+                              int query_h);
+/* Switch hulo::geometricMatch (LocalizeEngine.cc:458) on or off (off after hulo_engine_create):
+ * ransac_round = mRansacRound, precision_px = mRansacPrecision of the LocalizeEngine
+ * constructor (LocalizeEngine.cc:84-91).  Guided matching is not implemented. */
+int hulo_engine_configure_geometric(hulo_engine *e, int enabled, size_t ransac_round, double precision_px);
+
 /* LocalizeEngine::localize from the putative matching on (LocalizeEngine.cc:423-602) for one
  * query image given its descriptors and (undistorted) keypoint positions:
- *   hulo::matchAKAZEToQuery -> drop views with too few matches -> hulo::matchProviderToMatchSet
- *   (2D-3D assembly, closest descriptor wins) -> SfM_Localizer::Localize -> KRt_From_P.
- * The F-matrix geometric filter between matching and assembly (hulo::geometricMatch, :458) is
- * not applied: the assembly consumes the putative matches.
+ *   hulo::matchAKAZEToQuery -> drop views with too few matches -> [hulo::geometricMatch, when
+ *   enabled: F-matrix AC-RANSAC per (view, query) pair, hulo_geometric_filter] ->
+ *   hulo::matchProviderToMatchSet (2D-3D assembly over the geometric -- else putative --
+ *   matches, closest descriptor wins) -> SfM_Localizer::Localize -> KRt_From_P.
  *   views / n_views   selected map views (NULL: all), as the `pairs` argument of matchAKAZEToQuery
  *   pose12            camera centre -R^T t (3) then R row-major (9), as LocalizeEngine.cc:593-602
  *   *localized        1 iff resection succeeded with enough inliers
  *   corr_qfeat / corr_landmark (capacity nq, may be NULL) the 2D-3D pairs, ascending query feature
  *   inliers (capacity nq, may be NULL) indices into the pair list
- *   times_ms[3]       putMatch, assembly, PnP (device + host wall time per stage) */
+ *   times_ms[4]       putMatch, assembly, PnP, geoMatch (device + host wall time per stage) */
 int hulo_engine_localize(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t q_stride, const double *qxy,
                          const uint32_t *views, size_t n_views, uint64_t seed, double *pose12, int *localized,
                          uint32_t *corr_qfeat, uint32_t *corr_landmark, size_t *n_corr, int32_t *inliers,
@@ -232,7 +270,7 @@ int hulo_engine_localize(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t
  * one batched matching pass (hulo_match_to_queries), then assembly and resection per image.
  * Layout of qdesc / q_offsets as hulo_match_to_queries; qxy holds 2 doubles per descriptor row.
  * Image q uses seed + q.  pose12: n_queries x 12; localized, n_corr, n_inliers: n_queries entries
- * (the last two may be NULL); times_ms[3] accumulates putMatch, assembly, PnP over the batch. */
+ * (the last two may be NULL); times_ms[4] accumulates putMatch, assembly, PnP, geoMatch over the batch. */
 int hulo_engine_localize_batch(hulo_engine *e, size_t n_queries, const uint8_t *qdesc, size_t q_stride,
                                const uint64_t *q_offsets, const double *qxy, const uint32_t *views, size_t n_views,
                                uint64_t seed, double *pose12, int *localized, uint32_t *n_corr, uint32_t *n_inliers,

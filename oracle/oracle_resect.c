@@ -504,6 +504,8 @@ void orc_krt_from_p(const double *P, double *Kout, double *Rout, double *tout, d
  *                                                           -> orc_seven_point, orc_epipolar_errors
  *   numeric/poly.h (SolveCubicPolynomial)                   -> solve_cubic
  * The 7-point solution set is cross-checked against cv2.findFundamentalMat(FM_7POINT).
+ * Known deviations: seeded splitmix64 sampler (as the resection above); non-finite models
+ * skipped; the narrowed sampling pool kept in index order (see orc_fmatrix_acransac).
  * ===================================================================================== */
 
 /* T = [[s,0,-w s/2],[0,s,-h s/2],[0,0,1]], s = 1/sqrt(w h) */
@@ -620,6 +622,11 @@ void orc_epipolar_errors(const double *F, const double *x1, const double *x2, si
 
 float orc_logcombi_k(size_t k, size_t n) { return orc_logcombi(k, n); }
 
+static int cmp_size_t(const void *a, const void *b) {
+    size_t x = *(const size_t *)a, y = *(const size_t *)b;
+    return (x > y) - (x < y);
+}
+
 /* 7 distinct positions in [0,total), ascending insertion like UniformSample */
 static void sample_k(uint64_t *state, size_t total, int k, size_t *out) {
     for (int i = 0; i < k; ++i) {
@@ -699,8 +706,15 @@ int orc_fmatrix_acransac(const double *xI, const double *xJ, size_t N, int wI, i
         if ((better && minNFA < 0) || (iter + 1 == nIter && nIterReserve)) {
             if (n_best == 0) { nIter++; nIterReserve--; }
             else {
+                /* Known deviation: the narrowed pool is kept in ascending index order, not in
+                 * residual order.  The order of a pool only decides which uniformly drawn
+                 * position selects which element, so the sampling distribution is unchanged;
+                 * it removes the dependence of the whole trace on the rounding-noise order of
+                 * the seven (zero-residual) sample points, which no two floating-point
+                 * implementations share.  The inlier list returned stays in residual order. */
                 n_pool = n_best;
                 memcpy(pool, best_inl, sizeof(size_t)*n_best);
+                qsort(pool, n_pool, sizeof(size_t), cmp_size_t);
                 if (nIterReserve) { nIter = iter + 1 + nIterReserve; nIterReserve = 0; }
             }
         }

@@ -56,9 +56,13 @@ SIGNATURES = {
     "hulo_p3p": (C.c_int, [_vp, _vp, _sz, _vp, _vp, _sz, _vp, _vp, _vp]),
     "hulo_resect_acransac": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _sz, _u64, _vp, _vp, C.POINTER(_sz),
                                        C.POINTER(_f64), C.POINTER(C.c_int)]),
+    "hulo_geometric_filter": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp, _f64, _sz, _u64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                        _vp]),
     "hulo_engine_create": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _pp]),
     "hulo_engine_destroy": (None, [_vp]),
     "hulo_engine_configure": (C.c_int, [_vp, _f32, C.c_int, C.c_int, C.c_int, _sz]),
+    "hulo_engine_set_keypoints": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
+    "hulo_engine_configure_geometric": (C.c_int, [_vp, C.c_int, _sz, _f64]),
     "hulo_engine_localize": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _vp, _sz, _u64, _vp, C.POINTER(C.c_int), _vp, _vp,
                                        C.POINTER(_sz), _vp, C.POINTER(_sz), _vp]),
     "hulo_engine_localize_batch": (C.c_int, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _u64, _vp, _vp, _vp, _vp, _vp]),

@@ -225,7 +225,7 @@ void hulo_gpu_destroy(hulo_gpu *h) {
     hulo_comm_destroy_internal(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
     DevBuf *bufs[] = {&h->partial, &h->counter, &h->items, &h->knn_idx, &h->knn_dist, &h->packed, &h->gathered,
-                      &h->stageA, &h->stageB, &h->scratch0, &h->scratch1, &h->scratch2, &h->scratch3};
+                      &h->stageA, &h->stageB, &h->scratch0, &h->scratch1, &h->scratch2, &h->scratch3, &h->lfact};
     for (DevBuf *b : bufs) b->release();
     h->hstage0.release();
     h->hstage1.release();

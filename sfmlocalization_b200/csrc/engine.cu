@@ -25,6 +25,19 @@ struct hulo_engine {
     float ratio = 0.6f;        // secondTestRatio, localizeImage.cc:46-59
     int min_putative = 16, min_points = 8, min_inliers = 10;
     size_t max_iter = 4096;
+    // geometric filter (hulo::geometricMatch, LocalizeEngine.cc:458): keypoint positions of the map
+    // features (row order of the descriptor table), image size per view and of the query camera
+    std::vector<double> map_xy;
+    std::vector<int32_t> view_wh;
+    int32_t query_wh[2] = {0, 0};
+    bool geo_enabled = false;
+    size_t geo_rounds = 25;        // mRansacRound (LocalizeParam.py:35)
+    double geo_precision = 4.0;    // mRansacPrecision
+    std::vector<double> g_xI, g_xJ;
+    std::vector<uint64_t> g_off;
+    std::vector<int32_t> g_sizes, g_valid, g_inl;
+    std::vector<uint32_t> g_ninl;
+    std::vector<size_t> g_view;    // position in views[] of each filtered pair
     // per-query scratch
     std::vector<uint32_t> m_view, m_i, m_j, view_counts;
     std::vector<int32_t> m_d0;
@@ -162,6 +175,30 @@ int hulo_engine_configure(hulo_engine *e, float ratio, int min_putative, int min
     return HULO_OK;
 }
 
+int hulo_engine_set_keypoints(hulo_engine *e, const double *map_xy, const int32_t *view_wh, int query_w, int query_h) {
+    HULO_ARG(e != nullptr && map_xy != nullptr && view_wh != nullptr, "null argument");
+    HULO_ARG(query_w > 0 && query_h > 0, "the query image size must be positive");
+    for (size_t v = 0; v < 2 * e->n_views; ++v) HULO_ARG(view_wh[v] > 0, "view image sizes must be positive");
+    const size_t n = (size_t)e->seg[e->n_views];
+    e->map_xy.assign(map_xy, map_xy + 2 * n);
+    e->view_wh.assign(view_wh, view_wh + 2 * e->n_views);
+    e->query_wh[0] = query_w;
+    e->query_wh[1] = query_h;
+    return HULO_OK;
+}
+
+int hulo_engine_configure_geometric(hulo_engine *e, int enabled, size_t ransac_round, double precision_px) {
+    HULO_ARG(e != nullptr, "null engine");
+    if (enabled) {
+        HULO_ARG(!e->view_wh.empty(), "hulo_engine_set_keypoints must be called before enabling the geometric filter");
+        HULO_ARG(ransac_round >= 1 && precision_px > 0.0, "bad geometric filter parameter");
+        e->geo_rounds = ransac_round;
+        e->geo_precision = precision_px;
+    }
+    e->geo_enabled = enabled != 0;
+    return HULO_OK;
+}
+
 // Stages after the putative matching, shared by the single and the batched entry points:
 // view filter, 2D-3D assembly, resection, pose.  m_* are the matches of this query grouped by
 // view position (view_counts[v] entries each, emission order).
@@ -169,8 +206,8 @@ static int assemble_and_resect(hulo_engine *e, size_t nq, const double *qxy, con
                                const uint32_t *m_i, const uint32_t *m_j, const int32_t *m_d0,
                                const uint32_t *view_counts, uint64_t seed, double *pose12, int *localized,
                                uint32_t *corr_qfeat, uint32_t *corr_landmark, size_t *n_corr, int32_t *inliers,
-                               size_t *n_inliers, double *t_assembly, double *t_pnp) {
-    const double t1 = now_ms();
+                               size_t *n_inliers, double *t_assembly, double *t_pnp, double *t_geo) {
+    double t1 = now_ms();
     // ---- 2D-3D assembly, hulo::matchProviderToMatchSet (SfMDataUtils.cpp:59-125).
     // The reference walks a std::map keyed by (view id, query id): ascending view id, and inside
     // a view the matches in emission order.  featDist[(v,q)][j] is the distance of the LAST
@@ -186,6 +223,52 @@ static int assemble_and_resect(hulo_engine *e, size_t nq, const double *qxy, con
     e->fd_stamp.assign(nq, -1);
     e->best_lm.assign(nq, -1);
     e->best_d.assign(nq, 0);
+
+    // ---- geometric filter, hulo::geometricMatch (LocalizeEngine.cc:458): every surviving
+    // (view, query) pair goes through the F-matrix AC-RANSAC in one launch; the assembly below
+    // then walks the geometric inliers of the pairs that stayed valid, in ACRANSAC's inlier order
+    // (map_geometricMatches), while featDist keeps coming from the putative matches.
+    std::vector<int64_t> geo_pair(n_views, -1);       // pair number of views[v], -1 = not filtered
+    if (e->geo_enabled) {
+        e->g_xI.clear(); e->g_xJ.clear(); e->g_sizes.clear(); e->g_view.clear();
+        e->g_off.assign(1, 0);
+        int32_t prev = -1;
+        for (size_t oi = 0; oi < n_views; ++oi) {
+            const size_t v = order[oi];
+            const uint32_t view_id = views ? views[v] : (uint32_t)v;
+            if ((int32_t)view_id == prev) continue;
+            prev = (int32_t)view_id;
+            if ((int)view_counts[v] < e->min_putative) continue;
+            geo_pair[v] = (int64_t)e->g_view.size();
+            e->g_view.push_back(v);
+            for (size_t k = start[v]; k < start[v + 1]; ++k) {
+                const size_t row = e->seg[view_id] + m_i[k];
+                e->g_xI.push_back(e->map_xy[2 * row]);
+                e->g_xI.push_back(e->map_xy[2 * row + 1]);
+                e->g_xJ.push_back(qxy[2 * (size_t)m_j[k]]);
+                e->g_xJ.push_back(qxy[2 * (size_t)m_j[k] + 1]);
+            }
+            e->g_off.push_back(e->g_off.back() + view_counts[v]);
+            e->g_sizes.push_back(e->view_wh[2 * view_id]);
+            e->g_sizes.push_back(e->view_wh[2 * view_id + 1]);
+            e->g_sizes.push_back(e->query_wh[0]);
+            e->g_sizes.push_back(e->query_wh[1]);
+        }
+        const size_t P = e->g_view.size();
+        e->g_valid.assign(std::max<size_t>(P, 1), 0);
+        e->g_ninl.assign(std::max<size_t>(P, 1), 0);
+        e->g_inl.resize(std::max<size_t>((size_t)e->g_off.back(), 1));
+        if (P) {
+            int rc = hulo_geometric_filter(e->h, e->g_xI.data(), e->g_xJ.data(), e->g_off.data(), P, e->g_sizes.data(),
+                                           e->geo_precision, e->geo_rounds, seed + 77, nullptr, e->g_valid.data(),
+                                           e->g_ninl.data(), e->g_inl.data(), nullptr, nullptr, nullptr);
+            if (rc != HULO_OK) return rc;
+        }
+        const double tg = now_ms();
+        if (t_geo) *t_geo += tg - t1;
+        t1 = tg;
+    }
+
     int32_t prev_view_id = -1;
     for (size_t oi = 0; oi < n_views; ++oi) {
         const size_t v = order[oi];
@@ -194,12 +277,21 @@ static int assemble_and_resect(hulo_engine *e, size_t nq, const double *qxy, con
         prev_view_id = (int32_t)view_id;
         // views with fewer putative matches than the threshold are dropped (LocalizeEngine.cc:428-434)
         if ((int)view_counts[v] < e->min_putative) continue;
+        size_t n_cand = start[v + 1] - start[v];
+        const int32_t *cand = nullptr;                               // nullptr: all putative matches, emission order
+        if (e->geo_enabled) {
+            const size_t p = (size_t)geo_pair[v];
+            if (!e->g_valid[p]) continue;                            // pair not in map_geometricMatches
+            cand = e->g_inl.data() + e->g_off[p];
+            n_cand = e->g_ninl[p];
+        }
         for (size_t k = start[v]; k < start[v + 1]; ++k) {
             const uint32_t j = m_j[k];
             e->fd[j] = m_d0[k];
             e->fd_stamp[j] = (int32_t)oi;
         }
-        for (size_t k = start[v]; k < start[v + 1]; ++k) {
+        for (size_t c = 0; c < n_cand; ++c) {
+            const size_t k = start[v] + (cand ? (size_t)cand[c] : c);
             const int32_t lmi = e->lm_of_row[e->seg[view_id] + m_i[k]];
             if (lmi < 0) continue;                                     // feature has no landmark
             const uint32_t lm = (uint32_t)lmi;
@@ -264,7 +356,7 @@ int hulo_engine_localize(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t
     *localized = 0;
     if (n_corr) *n_corr = 0;
     if (n_inliers) *n_inliers = 0;
-    if (times_ms) times_ms[0] = times_ms[1] = times_ms[2] = 0.0;
+    if (times_ms) times_ms[0] = times_ms[1] = times_ms[2] = times_ms[3] = 0.0;
     if (views == nullptr) n_views = e->n_views;
     const double t0 = now_ms();
 
@@ -282,7 +374,8 @@ int hulo_engine_localize(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t
     if (times_ms) times_ms[0] = now_ms() - t0;
     return assemble_and_resect(e, nq, qxy, views, n_views, e->m_i.data(), e->m_j.data(), e->m_d0.data(),
                                e->view_counts.data(), seed, pose12, localized, corr_qfeat, corr_landmark, n_corr,
-                               inliers, n_inliers, times_ms ? times_ms + 1 : nullptr, times_ms ? times_ms + 2 : nullptr);
+                               inliers, n_inliers, times_ms ? times_ms + 1 : nullptr, times_ms ? times_ms + 2 : nullptr,
+                               times_ms ? times_ms + 3 : nullptr);
 }
 
 int hulo_engine_localize_batch(hulo_engine *e, size_t n_queries, const uint8_t *qdesc, size_t q_stride,
@@ -291,7 +384,7 @@ int hulo_engine_localize_batch(hulo_engine *e, size_t n_queries, const uint8_t *
                                double *times_ms) {
     HULO_ARG(e != nullptr, "null engine");
     HULO_ARG(n_queries == 0 || (q_offsets != nullptr && pose12 != nullptr && localized != nullptr), "null argument");
-    if (times_ms) times_ms[0] = times_ms[1] = times_ms[2] = 0.0;
+    if (times_ms) times_ms[0] = times_ms[1] = times_ms[2] = times_ms[3] = 0.0;
     if (n_queries == 0) return HULO_OK;
     HULO_ARG(q_offsets[n_queries] == 0 || (qdesc != nullptr && qxy != nullptr), "null query");
     if (views == nullptr) n_views = e->n_views;
@@ -324,7 +417,8 @@ int hulo_engine_localize_batch(hulo_engine *e, size_t n_queries, const uint8_t *
         int rc = assemble_and_resect(e, nq, qxy + 2 * q_offsets[q], views, n_views, e->m_i.data() + k0,
                                      e->m_j.data() + k0, e->m_d0.data() + k0, vc, seed + q, pose12 + 12 * q,
                                      localized + q, nullptr, nullptr, &nc, nullptr, &ni,
-                                     times_ms ? times_ms + 1 : nullptr, times_ms ? times_ms + 2 : nullptr);
+                                     times_ms ? times_ms + 1 : nullptr, times_ms ? times_ms + 2 : nullptr,
+                                     times_ms ? times_ms + 3 : nullptr);
         if (rc != HULO_OK) return rc;
         if (n_corr) n_corr[q] = (uint32_t)nc;
         if (n_inliers) n_inliers[q] = (uint32_t)ni;

@@ -98,10 +98,39 @@ bool readViewsFromSfmData(const std::string &sfm_data_json, Views &views) {
         std::size_t ki = s.find("\"id_view\"", q1);
         if (ki == std::string::npos) return false;
         const std::size_t id = (std::size_t)std::strtoull(s.c_str() + s.find(':', ki) + 1, nullptr, 10);
-        views[id] = View{id, path};
+        View view{id, path};
+        // "width" / "height" sit between "filename" and "id_view" in the cereal layout
+        const std::size_t kw = s.find("\"width\"", q1), kh = s.find("\"height\"", q1);
+        if (kw != std::string::npos && kw < ki) view.ui_width = (std::size_t)std::strtoull(s.c_str() + s.find(':', kw) + 1, nullptr, 10);
+        if (kh != std::string::npos && kh < ki) view.ui_height = (std::size_t)std::strtoull(s.c_str() + s.find(':', kh) + 1, nullptr, 10);
+        views[id] = view;
         pos = ki + 9;
     }
     return !views.empty();
+}
+
+bool readFeatFile(const std::string &filename, FeatureLocations &feats) {
+    feats.clear();
+    std::ifstream f(filename);
+    if (!f.is_open()) return false;
+    std::string line;
+    while (std::getline(f, line)) {
+        std::istringstream ls(line);
+        double x, y;
+        if (ls >> x >> y) feats.push_back(std::make_pair(x, y));
+    }
+    return true;
+}
+
+std::string featPath(const std::string &dir, const std::string &img_path) {
+    std::string p = descPath(dir, img_path, true);
+    return p.substr(0, p.size() - 4) + "feat";
+}
+
+bool loadRegions(const Views &views, const std::string &dir, RegionsProvider &regions) {
+    for (const auto &kv : views)
+        if (!readFeatFile(featPath(dir, kv.second.s_Img_path), regions[kv.first])) return false;
+    return true;
 }
 
 std::string descPath(const std::string &dir, const std::string &img_path, bool strip_extension) {

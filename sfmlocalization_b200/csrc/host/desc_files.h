@@ -31,6 +31,13 @@ bool readViewsFromSfmData(const std::string &sfm_data_json, Views &views);
 // Plain alternative: one "id path" per line.
 bool readViewsFromList(const std::string &filename, Views &views);
 
+// OpenMVG .feat file of a view (Regions::Load, text flavour): one feature per line,
+// "x y scale orientation" for the SIOPointFeature of AKAZE regions ("x y" alone is accepted).
+bool readFeatFile(const std::string &filename, FeatureLocations &feats);
+// Regions_Provider::load for the views given: <dir>/<basename>.feat for each.
+bool loadRegions(const Views &views, const std::string &dir, RegionsProvider &regions);
+std::string featPath(const std::string &dir, const std::string &img_path);
+
 // stlplus::create_filespec(dir, basename_part(path), "desc")
 std::string descPath(const std::string &dir, const std::string &img_path, bool strip_extension);
 

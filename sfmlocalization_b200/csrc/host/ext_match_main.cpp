@@ -1,18 +1,26 @@
-// hulo_ext_match -- the putative-matching stage of the reference's ExtFeatAndMatch CLI
-// (ExtFeatAndMatch/src/computeFeaturesAndMatches.cpp:150-191) on the GPU.  It reads the
+// hulo_ext_match -- the matching stages of the reference's ExtFeatAndMatch CLI
+// (ExtFeatAndMatch/src/computeFeaturesAndMatches.cpp:150-246) on the GPU.  It reads the
 // .desc files the extraction stage wrote into <matchdir>, matches, and writes
-// <matchdir>/matches.putative.txt in the format the rest of the reference pipeline consumes
-// (F-matrix filter, openMVG_main_GlobalSfM, cleanSfM.py).
+// <matchdir>/matches.putative.txt; then, like the reference (:194-246), drops the pairs with
+// fewer than -mm matches, runs the F-matrix geometric filter (hulo::geometricMatch) on the
+// rest using the .feat files and the image sizes of sfm_data.json, and writes
+// <matchdir>/matches.f.txt -- the files the rest of the reference pipeline consumes
+// (openMVG_main_GlobalSfM, cleanSfM.py).
 //
-//   hulo_ext_match <matchdir> [-f=0.6] [-v=0] [-p=<pairfile>] [-mf=0]
+//   hulo_ext_match <matchdir> [-f=0.6] [-v=0] [-p=<pairfile>] [-mf=0] [-r=4096] [-mm=60] [-g=4.0]
 //                  [--views=<id path per line>] [--out=<file>] [--rank=R --world=W] [--device=D]
+//                  [--putative-only]
 //
-// Flags -f/-v/-p/-mf have the reference's meaning (computeFeaturesAndMatches.cpp:49-64);
-// unknown reference flags (-c -t -o -l -r -mm -g -gm -sm) are accepted and ignored so the
-// Python drivers' command lines keep working (reconstructGraph.py:158-163).  The view list
-// comes from <matchdir>/sfm_data.json like the reference, or from --views.
+// Flags -f/-v/-p/-mf/-r/-mm/-g have the reference's meaning (computeFeaturesAndMatches.cpp:49-64;
+// -g is read as an integer there, :92, and here); the extraction flags (-c -t -o -l -sm) are
+// accepted and ignored so the Python drivers' command lines keep working
+// (reconstructGraph.py:158-163); -gm (guided matching) is not implemented: a warning is printed
+// and the unguided filter runs.  When a .feat file or an image size is missing the geometric stage
+// is skipped with a message (the reference would abort: "Cannot construct regions providers").
+// The view list comes from <matchdir>/sfm_data.json like the reference, or from --views.
 // --rank/--world shard the pair list across processes (one per GPU, no collective); each
-// rank writes <out>.rank<R>, rank order concatenation equals the single-GPU file.
+// rank writes <out>.rank<R> (and matches.f.txt.rank<R>), rank order concatenation equals the
+// single-GPU file.
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -34,12 +42,19 @@ int main(int argc, char **argv) {
     std::string sMatchesDir, sPairFile, sViews, sOut, v;
     float fDistRatio = 0.6f;
     int videoMatchFrame = 0, rank = 0, world = 1, device = -1;
+    int ransacRound = 4096, minMatch = 60, geomError = 4;
+    bool bGuided = false, putativeOnly = false;
     size_t maxFrameDist = 0;
     for (int a = 1; a < argc; ++a) {
         if (flag(argv[a], "-f", v)) fDistRatio = (float)atof(v.c_str());
         else if (flag(argv[a], "-v", v)) videoMatchFrame = atoi(v.c_str());
         else if (flag(argv[a], "-p", v)) sPairFile = v;
         else if (flag(argv[a], "-mf", v)) maxFrameDist = (size_t)atoll(v.c_str());
+        else if (flag(argv[a], "-r", v)) ransacRound = atoi(v.c_str());
+        else if (flag(argv[a], "-mm", v)) minMatch = atoi(v.c_str());
+        else if (flag(argv[a], "-g", v)) geomError = atoi(v.c_str());
+        else if (strcmp(argv[a], "-gm") == 0 || flag(argv[a], "-gm", v)) bGuided = true;
+        else if (strcmp(argv[a], "--putative-only") == 0) putativeOnly = true;
         else if (flag(argv[a], "--views", v)) sViews = v;
         else if (flag(argv[a], "--out", v)) sOut = v;
         else if (flag(argv[a], "--rank", v)) rank = atoi(v.c_str());
@@ -97,6 +112,37 @@ int main(int argc, char **argv) {
             return EXIT_FAILURE;
         }
         std::cout << "wrote " << matches.size() << " pairs to " << sOut << std::endl;
+
+        // ---- geometric matching (computeFeaturesAndMatches.cpp:194-246)
+        if (!putativeOnly) {
+            std::cout << "Start Geometric Matching..." << std::endl;
+            for (auto it = matches.cbegin(); it != matches.cend();) {                 // :222-232
+                if ((int)it->second.size() < minMatch) it = matches.erase(it);
+                else ++it;
+            }
+            Views used;
+            for (const auto &kv : matches) {
+                used[kv.first.first] = views.at(kv.first.first);
+                used[kv.first.second] = views.at(kv.first.second);
+            }
+            RegionsProvider regions;
+            bool have = loadRegions(used, sMatchesDir, regions);
+            for (const auto &kv : used) have = have && kv.second.ui_width > 0 && kv.second.ui_height > 0;
+            if (!have) {
+                std::cout << "geometric matching skipped: .feat files or image sizes are missing" << std::endl;
+            } else {
+                if (bGuided) std::cerr << "warning: guided matching (-gm) is not implemented; running the unguided filter\n";
+                PairWiseMatches geometric;
+                geometricMatch(session, views, regions, matches, geometric, ransacRound, (double)geomError, false);
+                std::string sF = sMatchesDir + "/matches.f.txt";
+                if (world > 1) sF += ".rank" + std::to_string(rank);
+                if (!exportPairWiseMatches(geometric, sF)) {
+                    std::cerr << "Cannot write " << sF << std::endl;
+                    return EXIT_FAILURE;
+                }
+                std::cout << "wrote " << geometric.size() << " pairs to " << sF << std::endl;
+            }
+        }
     } catch (const std::exception &e) {
         std::cerr << "hulo_ext_match: " << e.what() << std::endl;
         return EXIT_FAILURE;

@@ -26,11 +26,18 @@ typedef std::map<Pair, IndMatches> PairWiseMatches;
 // (viewID, viewID) -> query feature -> distance to its nearest neighbour (MatchUtils.h:60)
 typedef std::map<Pair, std::map<std::size_t, int>> FeatDistMap;
 
-// What the matchers read from openMVG::sfm::SfM_Data: views in ascending id with their image path.
+// What the matchers read from openMVG::sfm::SfM_Data: views in ascending id with their image path
+// and, for the geometric filter, the image size (View::ui_width / ui_height).
 struct View {
     std::size_t id_view;
     std::string s_Img_path;
+    std::size_t ui_width = 0, ui_height = 0;
 };
 typedef std::map<std::size_t, View> Views;
+
+// What hulo::geometricMatch reads from the Regions_Provider: the (x, y) position of every
+// feature of a view, in feature order (openMVG::features::PointFeature).
+typedef std::vector<std::pair<double, double>> FeatureLocations;
+typedef std::map<std::size_t, FeatureLocations> RegionsProvider;
 
 }  // namespace hulo

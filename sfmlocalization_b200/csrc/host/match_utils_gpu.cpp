@@ -193,7 +193,54 @@ void matchAKAZEToQuery(GpuSession &s, const Views &views, const std::string &sMa
     }
 }
 
+// ------------------------------------------------------------------ geometricMatch
+uint64_t g_geometricSeed = 0x5eedULL;
+
+void geometricMatch(GpuSession &s, const Views &views, const RegionsProvider &regions_provider,
+                    const PairWiseMatches &map_putativeMatches, PairWiseMatches &map_geometricMatches,
+                    int ransacRound, double geomPrec, bool bGuided_matching) {
+    if (bGuided_matching) throw std::invalid_argument("hulo::geometricMatch: guided matching is not implemented");
+    map_geometricMatches.clear();                                                  // assignment at :415
+    std::vector<double> xI, xJ;
+    std::vector<uint64_t> off(1, 0), seeds;
+    std::vector<int32_t> sizes;
+    std::vector<const PairWiseMatches::value_type *> kept;
+    for (const auto &kv : map_putativeMatches) {
+        const View &vi = views.at(kv.first.first), &vj = views.at(kv.first.second);   // .at() like :385-403
+        const FeatureLocations &fi = regions_provider.at(kv.first.first), &fj = regions_provider.at(kv.first.second);
+        for (const IndMatch &m : kv.second) {
+            xI.push_back(fi.at(m.i_).first); xI.push_back(fi.at(m.i_).second);
+            xJ.push_back(fj.at(m.j_).first); xJ.push_back(fj.at(m.j_).second);
+        }
+        off.push_back(off.back() + kv.second.size());
+        sizes.push_back((int32_t)vi.ui_width); sizes.push_back((int32_t)vi.ui_height);
+        sizes.push_back((int32_t)vj.ui_width); sizes.push_back((int32_t)vj.ui_height);
+        seeds.push_back(g_geometricSeed + 1000003ull * ((uint64_t)kv.first.first * 1000003ull + (uint64_t)kv.first.second));
+        kept.push_back(&kv);
+    }
+    const std::size_t P = kept.size();
+    if (P) {
+        std::vector<int32_t> valid(P), inl(std::max<std::size_t>((std::size_t)off.back(), 1));
+        std::vector<uint32_t> ninl(P);
+        must(hulo_geometric_filter(s.gpu(), xI.data(), xJ.data(), off.data(), P, sizes.data(), geomPrec,
+                                   (std::size_t)std::max(ransacRound, 0), g_geometricSeed, seeds.data(), valid.data(),
+                                   ninl.data(), inl.data(), nullptr, nullptr, nullptr),
+             "hulo_geometric_filter");
+        for (std::size_t p = 0; p < P; ++p) {
+            if (!valid[p]) continue;
+            IndMatches &out = map_geometricMatches[kept[p]->first];
+            for (uint32_t c = 0; c < ninl[p]; ++c) out.push_back(kept[p]->second[(std::size_t)inl[off[p] + c]]);
+        }
+    }
+    std::cout << "number of putative matches : " << map_putativeMatches.size() << std::endl;
+    std::cout << "number of geometric matches : " << map_geometricMatches.size() << std::endl;
+}
+
 // ------------------------------------------------------------------ default-session overloads
+void geometricMatch(const Views &views, const RegionsProvider &r, const PairWiseMatches &p, PairWiseMatches &g,
+                    int ransacRound, double geomPrec, bool bGuided_matching) {
+    geometricMatch(defaultSession(), views, r, p, g, ransacRound, geomPrec, bGuided_matching);
+}
 void matchAKAZE(const Views &views, const std::string &d, const std::vector<Pair> &pairs, const float r,
                 PairWiseMatches &m) {
     matchAKAZE(defaultSession(), views, d, pairs, r, m);

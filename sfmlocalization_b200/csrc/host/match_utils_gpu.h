@@ -52,6 +52,22 @@ void matchAKAZEToQuery(const Views &views, const std::string &sMatchesDir, const
                        const std::vector<std::size_t> &pairs, const std::size_t queryInd, const float fDistRatio,
                        PairWiseMatches &matches, FeatDistMap &featDist);
 
+// hulo::geometricMatch, MatchUtils.cpp:372-420 (decl MatchUtils.h:66-72): OpenMVG's
+// GeometricFilter_FMatrix_AC(geomPrec, ransacRound) on every pair of map_putativeMatches; pairs
+// whose robust estimation fails get no key in map_geometricMatches; surviving pairs hold the
+// inliers in ACRANSAC's order.  SfM_Data is replaced by the views (image sizes) and the
+// Regions_Provider by the feature positions.  bGuided_matching = true throws
+// std::invalid_argument: guided matching is not implemented.
+void geometricMatch(const Views &views, const RegionsProvider &regions_provider,
+                    const PairWiseMatches &map_putativeMatches, PairWiseMatches &map_geometricMatches,
+                    int ransacRound, double geomPrec, bool bGuided_matching);
+void geometricMatch(GpuSession &s, const Views &views, const RegionsProvider &regions_provider,
+                    const PairWiseMatches &map_putativeMatches, PairWiseMatches &map_geometricMatches,
+                    int ransacRound, double geomPrec, bool bGuided_matching);
+// sampler seed of the filter (pair (I, J) draws from a stream derived from it and from I, J, so
+// the result of a pair does not depend on which other pairs are filtered with it)
+extern uint64_t g_geometricSeed;
+
 // the same three against an explicit session (several GPUs, tests)
 void matchAKAZE(GpuSession &s, const Views &views, const std::string &sMatchesDir, const std::vector<Pair> &pairs,
                 const float fDistRatio, PairWiseMatches &matches);

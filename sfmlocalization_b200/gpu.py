@@ -278,6 +278,28 @@ class HuloGpu:
                                             _ptr(inl), C.byref(n_inl), C.byref(emax), C.byref(found)))
         return dict(found=bool(found.value), P=P, inliers=inl[:n_inl.value].copy(), error_max=emax.value)
 
+    # -- K3
+    def geometric_filter(self, xI, xJ, pair_offsets, image_sizes, precision_px=4.0, max_iter=25, seed=1,
+                         pair_seeds=None):
+        """hulo_geometric_filter -> dict(valid, n_inliers, inliers (list per pair), F, error_max, nfa)."""
+        xI = np.ascontiguousarray(xI, np.float64).reshape(-1, 2)
+        xJ = np.ascontiguousarray(xJ, np.float64).reshape(-1, 2)
+        off = np.ascontiguousarray(pair_offsets, np.uint64)
+        P = len(off) - 1
+        sizes = np.ascontiguousarray(image_sizes, np.int32).reshape(-1, 4)
+        total = int(off[-1]) if P >= 0 and len(off) else 0
+        if pair_seeds is not None:
+            pair_seeds = np.ascontiguousarray(pair_seeds, np.uint64)
+        valid = np.zeros(max(P, 1), np.int32); ninl = np.zeros(max(P, 1), np.uint32)
+        inl = np.zeros(max(total, 1), np.int32)
+        F = np.zeros((max(P, 1), 3, 3)); emax = np.zeros(max(P, 1)); nfa = np.zeros(max(P, 1))
+        check(self.lib.hulo_geometric_filter(self.h, _ptr(xI), _ptr(xJ), _ptr(off), P, _ptr(sizes), precision_px,
+                                             max_iter, seed, _ptr(pair_seeds), _ptr(valid), _ptr(ninl), _ptr(inl),
+                                             _ptr(F), _ptr(emax), _ptr(nfa)))
+        per_pair = [inl[int(off[p]):int(off[p]) + int(ninl[p])].copy() for p in range(P)]
+        return dict(valid=valid[:P].astype(bool), n_inliers=ninl[:P].copy(), inliers=per_pair, F=F[:P].copy(),
+                    error_max=emax[:P].copy(), nfa=nfa[:P].copy())
+
     # -- multi GPU
     @staticmethod
     def comm_unique_id():
@@ -318,6 +340,15 @@ class LocalizeEngine:
         self.h = h
         check(self.lib.hulo_engine_configure(self.h, ratio, min_putative, min_points, min_inliers, max_iter))
 
+    def set_keypoints(self, map_xy, view_wh, query_wh):
+        map_xy = np.ascontiguousarray(map_xy, np.float64)
+        view_wh = np.ascontiguousarray(view_wh, np.int32)
+        check(self.lib.hulo_engine_set_keypoints(self.h, _ptr(map_xy), _ptr(view_wh), int(query_wh[0]),
+                                                 int(query_wh[1])))
+
+    def configure_geometric(self, enabled, ransac_round=25, precision_px=4.0):
+        check(self.lib.hulo_engine_configure_geometric(self.h, int(bool(enabled)), ransac_round, precision_px))
+
     def localize(self, qdesc, qxy, views=None, seed=1):
         qdesc = _rows(qdesc)
         qxy = np.ascontiguousarray(qxy, np.float64)
@@ -330,7 +361,7 @@ class LocalizeEngine:
         cq = np.empty(max(nq, 1), np.uint32); cl = np.empty(max(nq, 1), np.uint32)
         inl = np.empty(max(nq, 1), np.int32)
         nc = C.c_size_t(0); ni = C.c_size_t(0)
-        times = np.zeros(3)
+        times = np.zeros(4)
         check(self.lib.hulo_engine_localize(self.h, _ptr(qdesc), nq, qdesc.shape[1] if nq else 64, _ptr(qxy),
                                             _ptr(views), n_views, seed, _ptr(pose), C.byref(loc), _ptr(cq), _ptr(cl),
                                             C.byref(nc), _ptr(inl), C.byref(ni), _ptr(times)))
@@ -351,7 +382,7 @@ class LocalizeEngine:
             n_views = len(views)
         pose = np.zeros((max(nQ, 1), 12)); loc = np.zeros(max(nQ, 1), np.int32)
         nc = np.zeros(max(nQ, 1), np.uint32); ni = np.zeros(max(nQ, 1), np.uint32)
-        times = np.zeros(3)
+        times = np.zeros(4)
         check(self.lib.hulo_engine_localize_batch(self.h, nQ, _ptr(desc), desc.shape[1] if desc.shape[0] else 64,
                                                   _ptr(off), _ptr(xy), _ptr(views), n_views, seed, _ptr(pose),
                                                   _ptr(loc), _ptr(nc), _ptr(ni), _ptr(times)))

@@ -150,6 +150,11 @@ def localization_scene(n_views, feats_per_view, n_landmarks, nq, seed, track_fra
     lm_desc = random_rows(n_landmarks, seed + 2)
     rows, off = [], [0]
     obs_view, obs_feat, obs_lm = [], [], []
+    # keypoint positions of the map features (input of the F-matrix geometric filter): every view
+    # has its own pose near the query's; drawn from a separate stream so the fields above and below
+    # are unchanged by their presence
+    rng_xy = np.random.Generator(np.random.PCG64(seed + 5))
+    map_xy, view_R, view_t = [], [], []
     for v in range(n_views):
         n_obs = int(feats_per_view * track_frac)
         if window:
@@ -165,6 +170,15 @@ def localization_scene(n_views, feats_per_view, n_landmarks, nq, seed, track_fra
         inv = np.empty_like(perm); inv[perm] = np.arange(len(perm))
         rows.append(d); off.append(off[-1] + d.shape[0])
         obs_view += [v] * len(lms); obs_feat += inv[:len(lms)].tolist(); obs_lm += lms.tolist()
+        Rv = rodrigues(rng_xy.normal(size=3) * np.deg2rad(4.0)) @ R
+        tv = t + rng_xy.normal(size=3) * 0.4
+        Xv = X[lms] @ Rv.T + tv
+        uvv = Xv @ K.T
+        xy_obs = uvv[:, :2] / uvv[:, 2:] + rng_xy.normal(scale=noise_px, size=(len(lms), 2))
+        n_cl = feats_per_view - len(lms)
+        xy = np.concatenate([xy_obs, np.stack([rng_xy.uniform(0, IMAGE_WH[0], n_cl),
+                                               rng_xy.uniform(0, IMAGE_WH[1], n_cl)], axis=1)])
+        map_xy.append(xy[perm]); view_R.append(Rv); view_t.append(tv)
     n_in = int(nq * query_inlier_frac)
     if window:
         q_lms = (n_landmarks - window) // 2 + rng.choice(window, size=min(n_in, window), replace=False)
@@ -183,7 +197,9 @@ def localization_scene(n_views, feats_per_view, n_landmarks, nq, seed, track_fra
     return dict(rows=np.concatenate(rows), seg_offsets=np.array(off, np.uint64),
                 obs_view=np.array(obs_view, np.uint32), obs_feat=np.array(obs_feat, np.uint32),
                 obs_landmark=np.array(obs_lm, np.uint32), landmark_X=X, K=K.copy(), R=R, t=t,
-                center=-R.T @ t, q_desc=q_desc, q_xy=q_xy, q_truth=q_truth, lm_desc=lm_desc, window=window)
+                center=-R.T @ t, q_desc=q_desc, q_xy=q_xy, q_truth=q_truth, lm_desc=lm_desc, window=window,
+                map_xy=np.concatenate(map_xy), view_wh=np.tile(np.array(IMAGE_WH, np.int32), (n_views, 1)),
+                view_R=np.array(view_R), view_t=np.array(view_t))
 
 
 def extra_query(scene, nq, seed, query_inlier_frac=0.35, noise_px=0.7, flip_p=0.08):

@@ -102,3 +102,63 @@ def test_pair_list_sharded_over_two_ranks(tmp_path, orc):
     merged = dict(a); merged.update(b)
     assert merged == one
     assert len(a) > 5 and len(b) > 5
+
+
+GEO_SEED = 0x5EED      # hulo::g_geometricSeed
+
+
+def test_geometric_stage_writes_matches_f(tmp_path, orc):
+    """ExtFeatAndMatch's second stage (computeFeaturesAndMatches.cpp:194-246): pairs below -mm are
+    dropped, the rest go through the F-matrix filter; matches.f.txt holds the inliers in ACRANSAC's
+    order.  Same composition on the oracle, same per-pair sampler seed."""
+    V = 6
+    sc = synth.localization_scene(V, 700, 900, 10, 31, track_frac=0.7)
+    off = sc["seg_offsets"]
+    d = tmp_path / "matches"
+    d.mkdir()
+    segs, xys = [], []
+    for k in range(V):
+        seg = sc["rows"][int(off[k]):int(off[k + 1])]
+        xy = sc["map_xy"][int(off[k]):int(off[k + 1])]
+        hostlib.write_desc_numpy(str(d / ("frame%04d.desc" % k)), np.ascontiguousarray(seg[:, :61]))
+        with open(d / ("frame%04d.feat" % k), "w") as f:
+            for x, y in xy:
+                f.write("%r %r 1.0 0.0\n" % (float(x), float(y)))
+        segs.append(seg); xys.append(xy)
+    views = [{"key": k, "value": {"ptr_wrapper": {"data": {"local_path": "/", "filename": "frame%04d.jpg" % k,
+                                                           "width": 1920, "height": 1080, "id_view": k}}}}
+             for k in range(V)]
+    (d / "sfm_data.json").write_text(json.dumps({"root_path": "/x", "views": views, "intrinsics": []}))
+    out = run_cli(d, "-f=0.7", "-r=200", "-mm=40", "-g=4.0")
+    assert "geometric matching skipped" not in out
+    put = hostlib.parse_matches(str(d / "matches.putative.txt"))
+    geo = hostlib.parse_matches(str(d / "matches.f.txt"))
+    pairs = [(a, b) for a in range(V) for b in range(a + 1, V)]
+    want_put = oracle_pairs(orc, segs, pairs, 0.7)
+    assert put == want_put
+    exact = 0
+    n_valid = 0
+    for (I, J), m in want_put.items():
+        if len(m) < 40:
+            assert (I, J) not in geo
+            continue
+        m = np.array(m)
+        r = orc.fmatrix_acransac(xys[I][m[:, 0]], xys[J][m[:, 1]], (1920, 1080), (1920, 1080), 4.0, 200,
+                                 GEO_SEED + 1000003 * (I * 1000003 + J))
+        assert ((I, J) in geo) == r["ok"]
+        if not r["ok"]:
+            continue
+        n_valid += 1
+        want = [tuple(x) for x in m[r["inliers"]].tolist()]
+        got = geo[(I, J)]
+        assert len(set(got) & set(want)) >= 0.8 * len(set(got) | set(want))
+        exact += int(set(got) == set(want))
+    assert n_valid >= 5 and exact >= n_valid - 2
+
+
+def test_geometric_stage_skipped_without_feat_files(tmp_path):
+    d, segs = make_matchdir(tmp_path, 4, 300, 9)
+    out = run_cli(d, "-f=0.7", "-mm=5")
+    assert "geometric matching skipped" in out and not (d / "matches.f.txt").exists()
+    out = run_cli(d, "-f=0.7", "--putative-only")
+    assert "Geometric" not in out

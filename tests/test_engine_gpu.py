@@ -120,3 +120,62 @@ def test_localize_batch(gpu):
             assert np.linalg.norm(b["center"][q] - centres[q]) < 0.05
     finally:
         eng.close()
+
+
+def oracle_geometric_assembly(orc, sc, views, ratio, min_putative, rounds, precision, seed):
+    """Putative matching -> view filter -> F-matrix filter per (view, query) pair -> assembly over
+    the geometric matches with featDist from the putative ones (LocalizeEngine.cc:423-497)."""
+    off = sc["seg_offsets"]
+    w, h = synth.IMAGE_WH
+    g_view, g_i, g_j, f_view, f_j, f_d = [], [], [], [], [], []
+    p = 0
+    kept = []
+    for v in sorted(set(views)):
+        a = sc["rows"][int(off[v]):int(off[v + 1])]
+        oi, oj, od = orc.match_view_to_query(a, sc["q_desc"], ratio)
+        if len(oi) < min_putative:
+            continue
+        r = orc.fmatrix_acransac(sc["map_xy"][int(off[v]) + oi], sc["q_xy"][oj], (w, h), (w, h), precision, rounds,
+                                 seed + 77 + 1000003 * p)
+        p += 1
+        if not r["ok"]:
+            continue
+        kept.append(v)
+        inl = r["inliers"]
+        g_view += [v] * len(inl); g_i += oi[inl].tolist(); g_j += oj[inl].tolist()
+        f_view += [v] * len(oi); f_j += oj.tolist(); f_d += od.tolist()
+    order = np.lexsort((sc["obs_feat"], sc["obs_view"]))
+    wj, wl = orc.match_set(g_view, g_i, g_j, f_view, f_j, f_d, sc["obs_view"][order], sc["obs_feat"][order],
+                           sc["obs_landmark"][order].astype(np.int64), len(sc["q_desc"]))
+    return wj, wl, kept
+
+
+@pytest.mark.parametrize("seed,rounds", [(1, 25), (2, 200)])
+def test_localize_with_geometric_filter(gpu, orc, seed, rounds):
+    sc = synth.localization_scene(24, 800, 4000, 900, seed)
+    eng = LocalizeEngine(gpu, sc["rows"], sc["seg_offsets"], sc["obs_view"], sc["obs_feat"], sc["obs_landmark"],
+                         sc["landmark_X"], sc["K"], ratio=0.6)
+    try:
+        plain = eng.localize(sc["q_desc"], sc["q_xy"], seed=5)
+        with pytest.raises(Exception):
+            eng.configure_geometric(True, rounds, 4.0)            # keypoints not set yet: loud failure
+        eng.set_keypoints(sc["map_xy"], sc["view_wh"], synth.IMAGE_WH)
+        eng.configure_geometric(True, rounds, 4.0)
+        r = eng.localize(sc["q_desc"], sc["q_xy"], seed=5)
+        eng.configure_geometric(False)
+        again = eng.localize(sc["q_desc"], sc["q_xy"], seed=5)
+    finally:
+        eng.close()
+    assert again["corr_qfeat"].tolist() == plain["corr_qfeat"].tolist()
+    wj, wl, kept = oracle_geometric_assembly(orc, sc, range(24), 0.6, 16, rounds, 4.0, 5)
+    assert len(kept) >= 12
+    got = set(zip(r["corr_qfeat"].tolist(), r["corr_landmark"].tolist()))
+    want = set(zip(wj.tolist(), wl.tolist()))
+    assert len(got & want) >= 0.97 * len(got | want)
+    # the filter removes wrong pairs: what is left is cleaner than the putative assembly
+    truth = sc["q_truth"][r["corr_qfeat"]]
+    truth_plain = sc["q_truth"][plain["corr_qfeat"]]
+    assert (truth == r["corr_landmark"]).mean() >= (truth_plain == plain["corr_landmark"]).mean()
+    assert (truth == r["corr_landmark"]).mean() > 0.97
+    assert r["localized"] and np.linalg.norm(r["center"] - sc["center"]) < 0.05
+    assert r["times_ms"][3] > 0 and plain["times_ms"][3] == 0

@@ -244,6 +244,8 @@ int hulo_engine_configure(hulo_engine *e, float ratio, int min_putative, int min
  * query camera. */
 int hulo_engine_set_keypoints(hulo_engine *e, const double *map_xy, const int32_t *view_wh, int query_w,
                               int query_h);
+/* The size of the next query image (the View added per query at LocalizeEngine.cc:405-409). */
+int hulo_engine_set_query_size(hulo_engine *e, int query_w, int query_h);
 /* Switch hulo::geometricMatch (LocalizeEngine.cc:458) on or off (off after hulo_engine_create):
  * ransac_round = mRansacRound, precision_px = mRansacPrecision of the LocalizeEngine
  * constructor (LocalizeEngine.cc:84-91).  Guided matching is not implemented. */

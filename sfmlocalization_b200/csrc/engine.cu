@@ -187,6 +187,14 @@ int hulo_engine_set_keypoints(hulo_engine *e, const double *map_xy, const int32_
     return HULO_OK;
 }
 
+int hulo_engine_set_query_size(hulo_engine *e, int query_w, int query_h) {
+    HULO_ARG(e != nullptr, "null engine");
+    HULO_ARG(query_w > 0 && query_h > 0, "the query image size must be positive");
+    e->query_wh[0] = query_w;
+    e->query_wh[1] = query_h;
+    return HULO_OK;
+}
+
 int hulo_engine_configure_geometric(hulo_engine *e, int enabled, size_t ransac_round, double precision_px) {
     HULO_ARG(e != nullptr, "null engine");
     if (enabled) {

@@ -6,6 +6,7 @@
 #include "desc_files.h"
 #include "match_utils_gpu.h"
 #include "pair_lists.h"
+#include "sfm_data_io.h"
 
 using namespace hulo;
 
@@ -110,6 +111,54 @@ long long hulo_host_views_from_sfm_data(const char *path, unsigned long long *id
         ++k;
     }
     return (long long)k;
+}
+
+// sfm_data.json reader: counts = {views, intrinsics, poses, landmarks, observations};
+// intrinsic0 = {focal, ppx, ppy, width, height, k1, k2, k3}; view_wh: 2 per view (ascending id)
+long long hulo_host_load_sfm_data(const char *path, unsigned long long *counts, double *first_X, double *intrinsic0,
+                                  unsigned long long *view_wh, unsigned long long cap_views) {
+    SfMScene sc;
+    if (!loadSfMData(path, sc)) return -1;
+    unsigned long long n_obs = 0;
+    for (const Landmark &lm : sc.landmarks) n_obs += lm.obs.size();
+    counts[0] = sc.views.size(); counts[1] = sc.intrinsics.size(); counts[2] = sc.poses.size();
+    counts[3] = sc.landmarks.size(); counts[4] = n_obs;
+    if (first_X && !sc.landmarks.empty()) memcpy(first_X, sc.landmarks[0].X, 3 * sizeof(double));
+    if (intrinsic0 && sc.intrinsics.count(0)) {
+        const Intrinsic &in = sc.intrinsics.at(0);
+        intrinsic0[0] = in.focal; intrinsic0[1] = in.ppx; intrinsic0[2] = in.ppy;
+        intrinsic0[3] = (double)in.width; intrinsic0[4] = (double)in.height;
+        for (int k = 0; k < 3; ++k) intrinsic0[5 + k] = (size_t)k < in.disto.size() ? in.disto[k] : 0.0;
+    }
+    unsigned long long k = 0;
+    for (const auto &kv : sc.views) {
+        if (view_wh && k < cap_views) { view_wh[2 * k] = kv.second.ui_width; view_wh[2 * k + 1] = kv.second.ui_height; }
+        ++k;
+    }
+    return (long long)sc.views.size();
+}
+
+void hulo_host_undistort(double focal, double ppx, double ppy, double k1, double k2, double k3, double x, double y,
+                         double *out2) {
+    Intrinsic in;
+    in.focal = focal; in.ppx = ppx; in.ppy = ppy;
+    in.disto = {k1, k2, k3};
+    const std::pair<double, double> ud = in.get_ud_pixel(x, y);
+    out2[0] = ud.first; out2[1] = ud.second;
+}
+
+int hulo_host_read_cv_matrix(const char *path, const char *name, double *out, int cap, int *rows, int *cols) {
+    std::vector<double> d;
+    if (!readOpenCVMatrix(path, name, *rows, *cols, d)) return 1;
+    for (int k = 0; k < cap && k < (int)d.size(); ++k) out[k] = d[k];
+    return 0;
+}
+
+long long hulo_host_read_feat(const char *path, double *xy, unsigned long long cap) {
+    FeatureLocations f;
+    if (!readFeatFile(path, f)) return -1;
+    for (unsigned long long k = 0; k < f.size() && k < cap; ++k) { xy[2 * k] = f[k].first; xy[2 * k + 1] = f[k].second; }
+    return (long long)f.size();
 }
 
 }  // extern "C"

@@ -32,6 +32,7 @@ struct View {
     std::size_t id_view;
     std::string s_Img_path;
     std::size_t ui_width = 0, ui_height = 0;
+    std::size_t id_intrinsic = 0, id_pose = 0;
 };
 typedef std::map<std::size_t, View> Views;
 

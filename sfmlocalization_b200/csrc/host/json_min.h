@@ -1,0 +1,140 @@
+// json_min.h -- a small recursive-descent JSON reader, enough for OpenMVG's cereal
+// sfm_data.json (objects, arrays, numbers, strings, true/false/null).  Header only.
+#pragma once
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+namespace hulo {
+namespace json {
+
+struct Value {
+    enum Type { Null, Bool, Number, String, Array, Object } type = Null;
+    bool b = false;
+    double num = 0.0;
+    std::string str;
+    std::vector<Value> arr;
+    std::vector<std::pair<std::string, Value>> obj;
+
+    const Value *get(const char *key) const {
+        if (type != Object) return nullptr;
+        for (const auto &kv : obj)
+            if (kv.first == key) return &kv.second;
+        return nullptr;
+    }
+    // follows a path of keys; nullptr when any is missing
+    const Value *path(std::initializer_list<const char *> keys) const {
+        const Value *v = this;
+        for (const char *k : keys) {
+            if (!v) return nullptr;
+            v = v->get(k);
+        }
+        return v;
+    }
+    double number(double dflt = 0.0) const { return type == Number ? num : dflt; }
+};
+
+class Parser {
+public:
+    explicit Parser(const std::string &text) : s_(text.c_str()), end_(text.c_str() + text.size()) {}
+    bool parse(Value &out) {
+        skip();
+        if (!value(out)) return false;
+        skip();
+        return true;
+    }
+
+private:
+    const char *s_, *end_;
+    void skip() {
+        while (s_ < end_ && (*s_ == ' ' || *s_ == '\n' || *s_ == '\t' || *s_ == '\r')) ++s_;
+    }
+    bool literal(const char *w) {
+        const size_t n = strlen(w);
+        if ((size_t)(end_ - s_) < n || strncmp(s_, w, n) != 0) return false;
+        s_ += n;
+        return true;
+    }
+    bool string(std::string &out) {
+        if (s_ >= end_ || *s_ != '"') return false;
+        ++s_;
+        out.clear();
+        while (s_ < end_ && *s_ != '"') {
+            if (*s_ == '\\' && s_ + 1 < end_) {
+                ++s_;
+                switch (*s_) {
+                    case 'n': out += '\n'; break;
+                    case 't': out += '\t'; break;
+                    case 'r': out += '\r'; break;
+                    case 'b': out += '\b'; break;
+                    case 'f': out += '\f'; break;
+                    case 'u':   // \uXXXX: kept as '?', paths in sfm_data.json are ASCII
+                        out += '?';
+                        s_ += (end_ - s_ >= 5) ? 4 : 0;
+                        break;
+                    default: out += *s_;
+                }
+                ++s_;
+            } else {
+                out += *s_++;
+            }
+        }
+        if (s_ >= end_) return false;
+        ++s_;
+        return true;
+    }
+    bool value(Value &v) {
+        skip();
+        if (s_ >= end_) return false;
+        const char c = *s_;
+        if (c == '{') {
+            v.type = Value::Object;
+            ++s_;
+            skip();
+            if (s_ < end_ && *s_ == '}') { ++s_; return true; }
+            for (;;) {
+                skip();
+                std::string key;
+                if (!string(key)) return false;
+                skip();
+                if (s_ >= end_ || *s_ != ':') return false;
+                ++s_;
+                v.obj.emplace_back(std::move(key), Value());
+                if (!value(v.obj.back().second)) return false;
+                skip();
+                if (s_ < end_ && *s_ == ',') { ++s_; continue; }
+                if (s_ < end_ && *s_ == '}') { ++s_; return true; }
+                return false;
+            }
+        }
+        if (c == '[') {
+            v.type = Value::Array;
+            ++s_;
+            skip();
+            if (s_ < end_ && *s_ == ']') { ++s_; return true; }
+            for (;;) {
+                v.arr.emplace_back();
+                if (!value(v.arr.back())) return false;
+                skip();
+                if (s_ < end_ && *s_ == ',') { ++s_; continue; }
+                if (s_ < end_ && *s_ == ']') { ++s_; return true; }
+                return false;
+            }
+        }
+        if (c == '"') { v.type = Value::String; return string(v.str); }
+        if (literal("true")) { v.type = Value::Bool; v.b = true; return true; }
+        if (literal("false")) { v.type = Value::Bool; v.b = false; return true; }
+        if (literal("null")) { v.type = Value::Null; return true; }
+        char *e = nullptr;
+        v.num = strtod(s_, &e);
+        if (e == s_) return false;
+        v.type = Value::Number;
+        s_ = e;
+        return true;
+    }
+};
+
+}  // namespace json
+}  // namespace hulo

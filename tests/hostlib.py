@@ -7,6 +7,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "sfmlocalization_b200")
 CLI = os.path.join(PKG, "hulo_ext_match")
+CLI_LOCALIZE = os.path.join(PKG, "hulo_localize")
 _lib = None
 
 
@@ -15,7 +16,8 @@ def lib():
     if _lib is None:
         C.CDLL(os.path.join(PKG, "libhulo_gpu.so"), mode=C.RTLD_GLOBAL)
         _lib = C.CDLL(os.path.join(PKG, "libhulo_host.so"))
-        for name in ("hulo_host_read_desc", "hulo_host_matches_roundtrip", "hulo_host_views_from_sfm_data"):
+        for name in ("hulo_host_read_desc", "hulo_host_matches_roundtrip", "hulo_host_views_from_sfm_data",
+                     "hulo_host_load_sfm_data", "hulo_host_read_feat"):
             getattr(_lib, name).restype = C.c_longlong
         for name in ("hulo_host_all_pairs", "hulo_host_video_pairs", "hulo_host_remove_dup_pairs",
                      "hulo_host_partition_pairs", "hulo_host_propagate_tracks"):
@@ -106,3 +108,73 @@ def parse_matches(path):
         out[(I, J)] = [(int(tok[k + 2 * m]), int(tok[k + 2 * m + 1])) for m in range(n)]
         k += 2 * n
     return out
+
+
+def write_feat(path, xy):
+    """OpenMVG .feat (SIOPointFeature text): x y scale orientation per line."""
+    with open(path, "w") as f:
+        for x, y in np.asarray(xy, np.float64):
+            f.write("%r %r 1.0 0.0\n" % (float(x), float(y)))
+
+
+def write_sfm_data(path, scene, names, focal=None, disto=None):
+    """An OpenMVG 1.x cereal sfm_data.json for a synth.localization_scene: views with sizes,
+    one pinhole (or pinhole_radial_k3) intrinsic, one pose per view, landmarks with observations."""
+    import json
+    K = scene["K"]
+    V = len(scene["seg_offsets"]) - 1
+    w, h = [int(x) for x in scene["view_wh"][0]]
+    views = [{"key": k, "value": {"polymorphic_id": 1073741824, "ptr_wrapper": {"id": 2147483649 + k, "data": {
+        "local_path": "/", "filename": names[k] + ".jpg", "width": w, "height": h, "id_view": k, "id_intrinsic": 0,
+        "id_pose": k}}}} for k in range(V)]
+    data = {"width": w, "height": h, "focal_length": float(K[0, 0] if focal is None else focal),
+            "principal_point": [float(K[0, 2]), float(K[1, 2])]}
+    name = "pinhole"
+    if disto is not None:
+        data["disto_k3"] = [float(x) for x in disto]
+        name = "pinhole_radial_k3"
+    intr = [{"key": 0, "value": {"polymorphic_id": 2147483649, "polymorphic_name": name,
+                                 "ptr_wrapper": {"id": 2147483700, "data": data}}}]
+    ext = [{"key": k, "value": {"rotation": scene["view_R"][k].tolist(),
+                                "center": (-scene["view_R"][k].T @ scene["view_t"][k]).tolist()}} for k in range(V)]
+    obs = {}
+    for v, f, l in zip(scene["obs_view"].tolist(), scene["obs_feat"].tolist(), scene["obs_landmark"].tolist()):
+        obs.setdefault(l, []).append({"key": v, "value": {"id_feat": f, "x": [0.0, 0.0]}})
+    structure = [{"key": l, "value": {"X": scene["landmark_X"][l].tolist(), "observations": obs[l]}}
+                 for l in sorted(obs)]
+    with open(path, "w") as f:
+        json.dump({"sfm_data_version": "0.2", "root_path": "/x", "views": views, "intrinsics": intr,
+                   "extrinsics": ext, "structure": structure, "control_points": []}, f)
+    return sorted(obs)
+
+
+def load_sfm_data(path, cap_views=4096):
+    counts = np.zeros(5, np.uint64); X = np.zeros(3); intr = np.zeros(8)
+    wh = np.zeros((cap_views, 2), np.uint64)
+    n = lib().hulo_host_load_sfm_data(path.encode(), _p(counts), _p(X), _p(intr), _p(wh), C.c_ulonglong(cap_views))
+    if n < 0:
+        return None
+    return dict(counts=counts.astype(np.int64), first_X=X, intrinsic0=intr, view_wh=wh[:n].astype(np.int64))
+
+
+def undistort(focal, ppx, ppy, k, x, y):
+    out = np.zeros(2)
+    lib().hulo_host_undistort(C.c_double(focal), C.c_double(ppx), C.c_double(ppy), C.c_double(k[0]), C.c_double(k[1]),
+                              C.c_double(k[2]), C.c_double(x), C.c_double(y), _p(out))
+    return out
+
+
+def read_cv_matrix(path, name, cap=64):
+    out = np.zeros(cap); r = C.c_int(0); c = C.c_int(0)
+    if lib().hulo_host_read_cv_matrix(path.encode(), name.encode(), _p(out), cap, C.byref(r), C.byref(c)) != 0:
+        return None
+    return out[:r.value * c.value].reshape(r.value, c.value)
+
+
+def read_feat(path):
+    n = lib().hulo_host_read_feat(path.encode(), None, C.c_ulonglong(0))
+    if n < 0:
+        return None
+    out = np.zeros((max(n, 1), 2))
+    lib().hulo_host_read_feat(path.encode(), _p(out), C.c_ulonglong(n))
+    return out[:n]

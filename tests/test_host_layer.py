@@ -112,3 +112,45 @@ def test_views_from_sfm_data_json(tmp_path):
                                                     C.c_ulonglong(64))
     assert n == 5 and ids[:5].tolist() == [0, 1, 2, 3, 4]
     assert bytes(names[2]).split(b"\0")[0] == b"img006.jpg"
+
+
+def test_sfm_data_json_reader(tmp_path):
+    """loadSfMData: the cereal layout of OpenMVG 1.x (views / intrinsics / extrinsics / structure)."""
+    sc = synth.localization_scene(5, 60, 200, 10, 3)
+    names = ["frame%04d" % k for k in range(5)]
+    p = str(tmp_path / "sfm_data.json")
+    lms = hostlib.write_sfm_data(p, sc, names, disto=[0.05, -0.01, 0.002])
+    r = hostlib.load_sfm_data(p)
+    assert r["counts"].tolist() == [5, 1, 5, len(lms), len(sc["obs_view"])]
+    assert np.allclose(r["first_X"], sc["landmark_X"][lms[0]])
+    assert np.allclose(r["intrinsic0"], [sc["K"][0, 0], sc["K"][0, 2], sc["K"][1, 2], 1920, 1080, 0.05, -0.01, 0.002])
+    assert (r["view_wh"] == [1920, 1080]).all()
+    assert hostlib.load_sfm_data(str(tmp_path / "missing.json")) is None
+    (tmp_path / "bad.json").write_text("{\"views\": [")
+    assert hostlib.load_sfm_data(str(tmp_path / "bad.json")) is None
+
+
+def test_undistortion_inverts_the_radial_model():
+    """Intrinsic::get_ud_pixel (Pinhole_Intrinsic_Radial_K3): distort(undistort(p)) == p."""
+    f, cx, cy, k = 1800.0, 960.0, 540.0, (0.08, -0.02, 0.004)
+    for x, y in [(100.0, 80.0), (960.0, 540.0), (1900.0, 1000.0), (300.5, 777.25)]:
+        ux, uy = hostlib.undistort(f, cx, cy, k, x, y)
+        a, b = (ux - cx) / f, (uy - cy) / f
+        r2 = a * a + b * b
+        c = 1 + k[0] * r2 + k[1] * r2 ** 2 + k[2] * r2 ** 3
+        assert abs(f * a * c + cx - x) < 1e-4 and abs(f * b * c + cy - y) < 1e-4
+    assert np.array_equal(hostlib.undistort(f, cx, cy, (0, 0, 0), 12.5, 99.0), [12.5, 99.0])   # plain pinhole
+
+
+def test_opencv_yaml_matrix_and_feat_reader(tmp_path):
+    import cv2
+    A = np.arange(12, dtype=np.float64).reshape(3, 4) * 0.37 - 1.5
+    fs = cv2.FileStorage(str(tmp_path / "A.yml"), cv2.FILE_STORAGE_WRITE)
+    fs.write("other", np.eye(2)); fs.write("A", A); fs.release()
+    got = hostlib.read_cv_matrix(str(tmp_path / "A.yml"), "A")
+    assert got.shape == (3, 4) and np.allclose(got, A)
+    assert hostlib.read_cv_matrix(str(tmp_path / "A.yml"), "missing") is None
+    xy = np.array([[1.5, 2.25], [1000.125, 33.0]])
+    hostlib.write_feat(str(tmp_path / "a.feat"), xy)
+    assert np.array_equal(hostlib.read_feat(str(tmp_path / "a.feat")), xy)
+    assert hostlib.read_feat(str(tmp_path / "none.feat")) is None

@@ -1,0 +1,103 @@
+"""GPU suite for hulo_localize (the OpenMVGLocalization_AKAZE CLI from the putative matching on)
+and the C++ hulo::LocalizeEngine behind it: sfm_data.json + .desc/.feat files in, per-query
+result JSON out (keys filename, sfm_data, matches_dir, K, R, t, pair -- localization.cpp:100-144)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from sfmlocalization_b200 import synth
+from sfmlocalization_b200.gpu import LocalizeEngine
+from tests import hostlib
+
+pytestmark = pytest.mark.gpu
+K_EQ = np.array([[1865.0, 0.0, 1043.21], [0.0, 1865.0, 644.65], [0.0, 0.0, 1.0]])   # OpenMVG pinhole: one focal
+
+
+def make_project(tmp_path, seed=5, V=14, n_queries=3):
+    sc = synth.localization_scene(V, 700, 3000, 800, seed, K=K_EQ)
+    sfm = tmp_path / "sfm"; mdir = tmp_path / "matches"; qdir = tmp_path / "query"; out = tmp_path / "out"
+    for d in (sfm, mdir, qdir, out):
+        d.mkdir()
+    names = ["frame%04d" % k for k in range(V)]
+    off = sc["seg_offsets"]
+    for k in range(V):
+        hostlib.write_desc_numpy(str(mdir / (names[k] + ".desc")), sc["rows"][int(off[k]):int(off[k + 1]), :61])
+        hostlib.write_feat(str(mdir / (names[k] + ".feat")), sc["map_xy"][int(off[k]):int(off[k + 1])])
+    lm_ids = hostlib.write_sfm_data(str(sfm / "sfm_data.json"), sc, names)
+    queries = [dict(q_desc=sc["q_desc"], q_xy=sc["q_xy"], center=sc["center"], R=sc["R"])]
+    queries += [synth.extra_query(sc, 800, 60 + k) for k in range(n_queries - 1)]
+    for k, q in enumerate(queries):
+        hostlib.write_desc_numpy(str(qdir / ("q%03d.desc" % k)), q["q_desc"][:, :61])
+        hostlib.write_feat(str(qdir / ("q%03d.feat" % k)), q["q_xy"])
+    return sc, sfm, mdir, qdir, out, queries, lm_ids
+
+
+def run(*args):
+    r = subprocess.run([hostlib.CLI_LOCALIZE] + [str(a) for a in args], capture_output=True, text=True, timeout=600)
+    return r
+
+
+def test_folder_of_queries(tmp_path):
+    sc, sfm, mdir, qdir, out, queries, lm_ids = make_project(tmp_path)
+    r = run(qdir, sfm, mdir, out, "-f=0.6", "-r=25", "-g=4.0", "-w", "-k=0")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "localized 3 of 3" in r.stdout
+    for k, q in enumerate(queries):
+        res = json.loads((out / ("q%03d.json" % k)).read_text())
+        assert res["filename"].endswith("q%03d.desc" % k) and res["sfm_data"].endswith("sfm_data.json")
+        assert res["matches_dir"] == str(mdir)
+        assert np.allclose(np.array(res["K"]), K_EQ, rtol=1e-5)
+        assert np.linalg.norm(np.array(res["t"]) - q["center"]) < 0.05            # t = camera centre -R^T t
+        assert np.abs(np.array(res["R"]) - q["R"]).max() < 5e-3
+        pairs = np.array(res["pair"])
+        assert len(pairs) > 10 and pairs[:, 0].max() < 800 and np.isin(pairs[:, 1], lm_ids).all()
+        if k == 0:                                                                # truth known for the main query
+            assert (sc["q_truth"][pairs[:, 0]] == pairs[:, 1]).mean() > 0.95
+
+
+def test_cli_equals_c_abi_engine(tmp_path, gpu):
+    """The C++ engine over the files gives what the C-ABI engine gives on the same arrays and seed."""
+    sc, sfm, mdir, qdir, out, queries, lm_ids = make_project(tmp_path, seed=8, n_queries=1)
+    r = run(qdir / "q000.desc", sfm, mdir, out, "-f=0.6", "-r=25", "--seed=4")
+    assert r.returncode == 0, r.stdout + r.stderr
+    res = json.loads((out / "q000.json").read_text())
+    eng = LocalizeEngine(gpu, sc["rows"], sc["seg_offsets"], sc["obs_view"], sc["obs_feat"], sc["obs_landmark"],
+                         sc["landmark_X"], K_EQ, ratio=np.float32(0.6))
+    try:
+        eng.set_keypoints(sc["map_xy"], sc["view_wh"], synth.IMAGE_WH)
+        eng.configure_geometric(True, 25, 4.0)
+        e = eng.localize(sc["q_desc"], sc["q_xy"], seed=4 + 1)                    # the CLI uses seed + image number
+    finally:
+        eng.close()
+    assert e["localized"]
+    assert np.allclose(np.array(res["t"]), e["center"], rtol=2e-6, atol=1e-6)     # JSON keeps 6 significant digits
+    assert np.allclose(np.array(res["R"]), e["R"], rtol=2e-6, atol=1e-6)
+    want = [[int(e["corr_qfeat"][i]), int(e["corr_landmark"][i])] for i in e["inliers"]]
+    assert res["pair"] == want
+
+
+def test_failure_writes_the_short_json_and_bad_input_fails(tmp_path):
+    sc, sfm, mdir, qdir, out, queries, lm_ids = make_project(tmp_path, seed=9, n_queries=1)
+    hostlib.write_desc_numpy(str(qdir / "noise.desc"), synth.random_rows(300, 77)[:, :61])
+    rng = np.random.default_rng(1)
+    hostlib.write_feat(str(qdir / "noise.feat"), rng.uniform(0, 1000, (300, 2)))
+    r = run(qdir / "noise.desc", sfm, mdir, out)
+    assert r.returncode == 0 and "Fail to estimate camera matrix" in r.stdout
+    res = json.loads((out / "noise.json").read_text())
+    assert sorted(res) == ["filename", "matches_dir", "sfm_data"]                 # localization.cpp:84-99
+    assert run(qdir, tmp_path / "nowhere", mdir, out).returncode != 0             # unreadable sfm_data.json
+    assert run(qdir, sfm, mdir, out, "-gm").returncode != 0                       # guided matching refused
+    assert run(qdir, sfm).returncode != 0                                         # usage
+
+
+def test_restricting_views_by_location(tmp_path):
+    """-x -y -z -d keep the views whose centre is near a location (hulo::getLocalViews)."""
+    sc, sfm, mdir, qdir, out, queries, lm_ids = make_project(tmp_path, seed=10, n_queries=1)
+    c = sc["center"]
+    r = run(qdir, sfm, mdir, out, "-x=%r" % c[0], "-y=%r" % c[1], "-z=%r" % c[2], "-d=100.0")
+    assert r.returncode == 0 and "localized 1 of 1" in r.stdout
+    r = run(qdir, sfm, mdir, out, "-x=1000.0", "-y=1000.0", "-z=1000.0", "-d=0.5")   # nothing nearby
+    assert r.returncode == 0 and "localized 0 of 1" in r.stdout

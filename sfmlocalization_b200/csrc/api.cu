@@ -313,6 +313,8 @@ int hulo_db_update(hulo_gpu *h, hulo_db *db, const uint8_t *rows, size_t n, size
         HULO_CUDA(cudaMemcpy2DAsync(db->rows, HULO_ROW_BYTES, rows, stride, stride, n, cudaMemcpyHostToDevice,
                                     h->stream));
     }
+    HULO_CUDA(knn2_fold_rows_launch(db->rows, n, h->stream));     // device layout of K1 (knn2.cuh)
+    h->launches++;
     HULO_CUDA(cudaStreamSynchronize(h->stream));
     return HULO_OK;
 }
@@ -333,6 +335,7 @@ int hulo_db_download(hulo_gpu *h, const hulo_db *db, size_t first, size_t n, uin
     HULO_ARG(rows64 != nullptr, "rows64 is null");
     HULO_CUDA(cudaMemcpyAsync(rows64, db->rows + first * 4, n * HULO_ROW_BYTES, cudaMemcpyDeviceToHost, h->stream));
     HULO_CUDA(cudaStreamSynchronize(h->stream));
+    knn2_fold_rows_host(rows64, n);                               // undo the device layout
     return HULO_OK;
 }
 
@@ -373,6 +376,9 @@ int hulo_knn2_host(hulo_gpu *h, const uint8_t *A, size_t nA, size_t strideA, con
     HULO_CUDA(e);
     if (nA) HULO_CUDA(cudaMemcpyAsync(h->stageA.ptr, a64, nA * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
     if (nB) HULO_CUDA(cudaMemcpyAsync(h->stageB.ptr, b64, nB * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
+    HULO_CUDA(knn2_fold_rows_launch(h->stageA.as<uint4>(), nA, h->stream));
+    HULO_CUDA(knn2_fold_rows_launch(h->stageB.as<uint4>(), nB, h->stream));
+    h->launches += (nA ? 1 : 0) + (nB ? 1 : 0);
     int rc = run_flat(h, h->stageA.as<uint4>(), nA, h->stageB.as<uint4>(), nB, 0, false);
     if (rc != HULO_OK) return rc;
     return hulo_knn2_fetch(h, nA, idx2, dist2);
@@ -412,6 +418,8 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     const uint8_t *q64 = stage_rows(h->hstage1, query, nq, q_stride, &e);
     HULO_CUDA(e);
     HULO_CUDA(cudaMemcpyAsync(h->stageB.ptr, q64, nq * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
+    HULO_CUDA(knn2_fold_rows_launch(h->stageB.as<uint4>(), nq, h->stream));
+    h->launches++;
 
     // items: maximal runs of views that are contiguous in the table, tiled, x chunks of the query
     const KnnConfig cfg = choose_config(h, (size_t)n_rows);
@@ -552,6 +560,8 @@ int hulo_match_to_queries(hulo_gpu *h, const hulo_db *map, const uint32_t *views
     const uint8_t *q64 = stage_rows(h->hstage1, queries, total_q_rows, q_stride, &e);
     HULO_CUDA(e);
     HULO_CUDA(cudaMemcpyAsync(h->stageB.ptr, q64, total_q_rows * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
+    HULO_CUDA(knn2_fold_rows_launch(h->stageB.as<uint4>(), total_q_rows, h->stream));
+    h->launches++;
 
     const KnnConfig cfg = choose_config(h, (size_t)n_rows);
     const uint32_t tile = knn2_tile_rows(cfg);

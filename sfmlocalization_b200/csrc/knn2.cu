@@ -55,6 +55,13 @@ __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
     asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
+// carry of a + b + c when the third operand is given as the SUM bit s = a ^ b ^ c:
+// maj(a, b, a ^ b ^ s), one LOP3 (truth table 0xD4)
+__device__ __forceinline__ uint32_t carry_from_sum(uint32_t a, uint32_t b, uint32_t s) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD4;" : "=r"(r) : "r"(a), "r"(b), "r"(s));
+    return r;
+}
 // carry-save adder: three words of weight w -> one of weight w (lo) and one of weight 2w (hi)
 #define HULO_CSA(hi, lo, a, b, c) \
     do {                          \
@@ -70,6 +77,12 @@ __device__ __forceinline__ uint32_t popc_mad(uint32_t x, uint32_t m, uint32_t ac
     return r;
 }
 
+// Rows are stored FOLDED (knn2_fold_rows): words 3i+2 (i = 0..4) hold w[3i] ^ w[3i+1] ^ w[3i+2].
+// XOR is linear, so q'[3i+2] ^ w'[3i+2] is directly the sum output of the first-level carry-save
+// adder over the triple (x[3i], x[3i+1], x[3i+2]) of the unfolded difference, and its carry follows
+// from the two plain differences and that sum in one LOP3: 4 instead of 5 LOP3 per triple, 5 fewer
+// ALU instructions per distance with bit-identical distances.
+//
 // key = base + (distance << kKeyIdxBits) for a register-resident searcher row q and a database
 // row w; distance = 512-bit Hamming.  CSA = number of carry-save adders applied before the POPCs
 // (0: plain 16 POPC).  `unit` is 1 << kKeyIdxBits held in a register so ptxas keeps the IMADs.
@@ -87,16 +100,20 @@ __device__ __forceinline__ uint32_t hamming_key(const uint32_t (&q)[16], const u
         else cnt += __popc(word);                                    \
     } while (0)
     if constexpr (CSA == 0) {
+        // plain 16 POPC baseline: undo the fold of the difference first
+#pragma unroll
+        for (int i = 0; i < 5; ++i) x[3 * i + 2] = xor3(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
 #pragma unroll
         for (int k = 0; k < 16; ++k) HULO_ACC(x[k], 1u, n1);
     } else {
-        // level 1: 15 words -> 5 sums (weight 1) + 5 carries (weight 2); x[15] left over
-        uint32_t s0, s1, s2, s3, s4, c0, c1, c2, c3, c4;
-        HULO_CSA(c0, s0, x[0], x[1], x[2]);
-        HULO_CSA(c1, s1, x[3], x[4], x[5]);
-        HULO_CSA(c2, s2, x[6], x[7], x[8]);
-        HULO_CSA(c3, s3, x[9], x[10], x[11]);
-        HULO_CSA(c4, s4, x[12], x[13], x[14]);
+        // level 1: 15 words -> 5 sums (weight 1) + 5 carries (weight 2); x[15] left over.
+        // The folded layout delivers the sums; only the carries are computed.
+        const uint32_t s0 = x[2], s1 = x[5], s2 = x[8], s3 = x[11], s4 = x[14];
+        const uint32_t c0 = carry_from_sum(x[0], x[1], s0);
+        const uint32_t c1 = carry_from_sum(x[3], x[4], s1);
+        const uint32_t c2 = carry_from_sum(x[6], x[7], s2);
+        const uint32_t c3 = carry_from_sum(x[9], x[10], s3);
+        const uint32_t c4 = carry_from_sum(x[12], x[13], s4);
         if constexpr (CSA == 5) {
             HULO_ACC(s0, 1u, n1); HULO_ACC(s1, 1u, n1); HULO_ACC(s2, 1u, n1); HULO_ACC(s3, 1u, n1);
             HULO_ACC(s4, 1u, n1); HULO_ACC(x[15], 1u, n1);
@@ -426,6 +443,20 @@ __global__ void knn2_merge_from_peers_kernel(const PeerExchange px, uint32_t nA,
     write_result(m0, m1, row, out_idx2, out_dist2, nullptr);
 }
 
+// In-place fold / unfold of 64-byte rows (an involution): w[3i+2] ^= w[3i] ^ w[3i+1], i = 0..4.
+__global__ void knn2_fold_rows_kernel(uint4 *__restrict__ rows, size_t n) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint4 *p = rows + r * 4;
+    uint4 a = p[0], b = p[1], c = p[2], d = p[3];
+    a.z ^= a.x ^ a.y;      // w2  ^= w0 ^ w1
+    b.y ^= a.w ^ b.x;      // w5  ^= w3 ^ w4
+    c.x ^= b.z ^ b.w;      // w8  ^= w6 ^ w7
+    c.w ^= c.y ^ c.z;      // w11 ^= w9 ^ w10
+    d.z ^= d.x ^ d.y;      // w14 ^= w12 ^ w13
+    p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+}
+
 template <int THREADS, int QPT, int CSA, int OPT>
 cudaError_t launch_variant(const KnnParams &p, int grid, cudaStream_t stream) {
     knn2_kernel<THREADS, QPT, CSA, OPT><<<grid, THREADS, 0, stream>>>(p);
@@ -469,6 +500,20 @@ cudaError_t knn2_kernel_info(const KnnConfig &cfg, int *regs, int *max_ctas_per_
     HULO_KNN_VARIANTS(X)
 #undef X
     return cudaErrorInvalidValue;
+}
+
+cudaError_t knn2_fold_rows_launch(uint4 *rows, size_t n, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    const int threads = 256;
+    knn2_fold_rows_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, stream>>>(rows, n);
+    return cudaGetLastError();
+}
+
+void knn2_fold_rows_host(uint8_t *rows64, size_t n) {
+    for (size_t r = 0; r < n; ++r) {
+        uint32_t *w = reinterpret_cast<uint32_t *>(rows64 + r * 64);
+        for (int i = 0; i < 5; ++i) w[3 * i + 2] ^= w[3 * i] ^ w[3 * i + 1];
+    }
 }
 
 cudaError_t knn2_merge_launch(const uint2 *partial, uint32_t nA, uint32_t n_chunks, uint64_t slot_stride,

@@ -61,6 +61,12 @@ inline uint32_t knn2_tile_rows(const KnnConfig &cfg) { return (uint32_t)(cfg.thr
 // Registers / occupancy report used by tests and the bench (cudaFuncGetAttributes).
 cudaError_t knn2_kernel_info(const KnnConfig &cfg, int *regs, int *max_ctas_per_sm, size_t *smem);
 
+// Device layout of a descriptor row: FOLDED -- words 3i+2 (i = 0..4) hold w[3i] ^ w[3i+1] ^ w[3i+2]
+// (see hamming_key in knn2.cu).  Every table and staging buffer K1 reads must be folded after its
+// upload; the transform is its own inverse (download = copy + fold on the host).
+cudaError_t knn2_fold_rows_launch(uint4 *rows, size_t n, cudaStream_t stream);
+void knn2_fold_rows_host(uint8_t *rows64, size_t n);
+
 // Merge the per-chunk keys of every searcher row into final (idx, dist) pairs.
 //   slot(row, c) = c * slot_stride + row ; global index = row_base + c * rows_per_chunk + (key & mask)
 // out_idx2/out_dist2: nA x 2 int32.  out_packed (optional): nA x int4 {d0, i0, d1, i1} with

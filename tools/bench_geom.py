@@ -21,6 +21,14 @@ def make(P, N, outl, seed):
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--one":        # one launch of one shape (ncu capture)
+        P, N, outl, rounds = int(sys.argv[2]), int(sys.argv[3]), float(sys.argv[4]), int(sys.argv[5])
+        xI, xJ, off, sizes = make(P, N, outl, 1)
+        with HuloGpu(0) as g:
+            for _ in range(2):
+                r = g.geometric_filter(xI, xJ, off, sizes, 4.0, rounds, 1)
+        print("valid", int(r["valid"].sum()), "of", P)
+        return
     shapes = [(64, 40, 0.5, 25), (64, 200, 0.5, 25), (256, 100, 0.5, 25), (1024, 100, 0.5, 25), (64, 200, 0.5, 200),
               (148, 1000, 0.5, 500), (592, 1000, 0.5, 500), (592, 1000, 1.0, 500), (2000, 300, 0.6, 500)]
     with HuloGpu(0) as g:

@@ -129,8 +129,8 @@ def rendezvous_id(rank, world, make_id):
 def make_tables(world, rank):
     """Every rank generates the same query set; rank r generates only its shard of the map
     (blocks are seeded independently, so shards concatenate to the 1-GPU table)."""
-    n_blocks = 40                       # 10M rows in 250k-row blocks, seeded per block
-    blk = N_MAP // n_blocks
+    blk = 250_000                       # rows in 250k-row blocks, seeded per block
+    n_blocks = N_MAP // blk
     per = n_blocks // world if n_blocks % world == 0 else None
     if per is None:
         raise SystemExit("--gpus must divide %d" % n_blocks)
@@ -341,8 +341,9 @@ def lsh_reference(sc, exact_matches):
 
 
 def workload_config(n_gpus):
-    return {"workload": "C3 building-scale map: %d queries x %d map descriptors (64-byte AKAZE/MLDB rows), "
-                        "exact Hamming 2-NN, planted matches (30%%)" % (N_QUERIES, N_MAP),
+    return {"workload": "%s: %d queries x %d map descriptors (64-byte AKAZE/MLDB rows), "
+                        "exact Hamming 2-NN, planted matches (30%%)"
+                        % ("C5 campus-scale map" if N_MAP > 10_000_000 else "C3 building-scale map", N_QUERIES, N_MAP),
             "sharding": "map rows sharded over %d GPU(s), NCCL all-gather top-2 merge" % n_gpus if n_gpus > 1
             else "single GPU, whole table resident",
             "cache": "map table 640 MB > 126 MB L2, streamed from HBM every step (no L2 flush needed)"}
@@ -355,7 +356,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
+                    help="c3 (default, the headline): 4096 x 10M; c5: 16384 x 50M campus map (8 GPUs)")
     args = ap.parse_args()
+    global N_QUERIES, N_MAP, SEED
+    if args.workload == "c5":
+        N_QUERIES, N_MAP, SEED = 16384, 50_000_000, 5000
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -480,9 +486,9 @@ def main():
             "roofline": roofline,
             "result_check": "planted matches found, d0<=d1" if ok else "FAILED",
         }
-        if world == 1:
+        if world == 1 and args.workload == "c3":
             line["localize"] = localize_bench(g, with_cpu=not args.no_cpu_baseline)
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline and world == 1 and args.workload == "c3":
             cb, (ci, cd, nq, nb) = cpu_baseline_sample(A, shard)
             # the same sample through the GPU path must agree bit for bit
             gi, gd = g.knn2_host(A[:nq], shard[:nb])

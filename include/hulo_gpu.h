@@ -178,8 +178,9 @@ int hulo_p3p(hulo_gpu *h, const uint32_t *triplets, size_t T, const double *x2d,
 
 /* openMVG::sfm::SfM_Localizer::Localize (LocalizeEngine.cc:529-532): AC-RANSAC resection
  * with P3P, max_iter iterations (the reference runs OpenMVG's default 4096), batched:
- * 90 % of the triplets are drawn and scored in one batch, the reserved 10 % are drawn from
- * the inliers of the best model so far.
+ * triplets are drawn from all correspondences and scored in growing batches (64, 128, ... 512)
+ * until a meaningful model (NFA < 0) appears or 90 % of the budget is spent; the reserved 10 %
+ * are then drawn from the inliers of the best model so far, like the sequential schedule.
  * Outputs: P = K [R|t] (12 doubles), inliers (capacity N) sorted by residual, *n_inliers,
  * *error_max in pixels.  *found is 1 iff inliers > 2.5 * 3 with NFA < 0. */
 int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size_t N,

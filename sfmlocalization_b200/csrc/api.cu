@@ -36,11 +36,24 @@ static int env_int(const char *name, int dflt) {
 }
 
 // Searcher-tile shape: the widest tile (fewest B re-reads) that the searcher count still fills.
+// "threads,qpt,csa,opt" from the environment (tuning sweeps), else the default
+static KnnConfig env_config(const char *name, KnnConfig dflt) {
+    const char *s = getenv(name);
+    KnnConfig c = dflt;
+    if (s && sscanf(s, "%d,%d,%d,%d", &c.threads, &c.qpt, &c.csa, &c.opt) == 4 &&
+        knn2_kernel_info(c, nullptr, nullptr, nullptr) == cudaSuccess)
+        return c;
+    cudaGetLastError();
+    return dflt;
+}
+static KnnConfig small_config() { static const KnnConfig c = env_config("HULO_KNN_SMALL", KnnConfig{128, 4, 8, 1}); return c; }
+static KnnConfig mid_config() { static const KnnConfig c = env_config("HULO_KNN_MID", KnnConfig{256, 4, 89, 1}); return c; }
+
 static KnnConfig choose_config(const hulo_gpu *h, size_t nA) {
     if (h->knn_cfg_forced) return h->knn_cfg;
     KnnConfig c = h->knn_cfg;
-    if (nA <= 512) c = KnnConfig{128, 4, 7, 0};
-    else if (nA <= 1024) c = KnnConfig{256, 4, 8, 3};
+    if (nA <= 512) c = small_config();
+    else if (nA <= 1024) c = mid_config();
     return c;
 }
 
@@ -335,7 +348,7 @@ int hulo_db_download(hulo_gpu *h, const hulo_db *db, size_t first, size_t n, uin
     HULO_ARG(rows64 != nullptr, "rows64 is null");
     HULO_CUDA(cudaMemcpyAsync(rows64, db->rows + first * 4, n * HULO_ROW_BYTES, cudaMemcpyDeviceToHost, h->stream));
     HULO_CUDA(cudaStreamSynchronize(h->stream));
-    knn2_fold_rows_host(rows64, n);                               // undo the device layout
+    knn2_unfold_rows_host(rows64, n);                             // undo the device layout
     return HULO_OK;
 }
 
@@ -695,7 +708,7 @@ int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size
         HULO_ARG(pairs[2 * p] < n_seg && pairs[2 * p + 1] < n_seg, "pair refers to a segment that does not exist");
     if (pair_offsets) pair_offsets[0] = 0;
 
-    const KnnConfig cfg = h->knn_cfg_forced ? h->knn_cfg : KnnConfig{256, 4, 8, 3};   // 1024-row tiles fit 5000-row images with 2 % waste
+    const KnnConfig cfg = h->knn_cfg_forced ? h->knn_cfg : mid_config();   // 1024-row tiles fit 5000-row images with 2 % waste
     const uint32_t tile = knn2_tile_rows(cfg);
     int ctas_per_sm = 1;
     knn2_kernel_info(cfg, nullptr, &ctas_per_sm, nullptr);

@@ -97,7 +97,7 @@ struct hulo_gpu {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     uint64_t launches = 0;
-    hulo::KnnConfig knn_cfg{512, 4, 8, 1};   // best of the round-1 sweep on C3 (profiles/r1_k1_variant_sweep.txt)
+    hulo::KnnConfig knn_cfg{512, 4, 89, 1};  // best of the sweeps on C3 (profiles/r1_k1_variant_sweep.txt, r1_k1_sweep_folded.txt)
     bool knn_cfg_forced = false;
 
     hulo::DevBuf partial;      // K1 per-item keys

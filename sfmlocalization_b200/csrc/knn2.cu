@@ -77,11 +77,13 @@ __device__ __forceinline__ uint32_t popc_mad(uint32_t x, uint32_t m, uint32_t ac
     return r;
 }
 
-// Rows are stored FOLDED (knn2_fold_rows): words 3i+2 (i = 0..4) hold w[3i] ^ w[3i+1] ^ w[3i+2].
-// XOR is linear, so q'[3i+2] ^ w'[3i+2] is directly the sum output of the first-level carry-save
-// adder over the triple (x[3i], x[3i+1], x[3i+2]) of the unfolded difference, and its carry follows
-// from the two plain differences and that sum in one LOP3: 4 instead of 5 LOP3 per triple, 5 fewer
-// ALU instructions per distance with bit-identical distances.
+// Rows are stored FOLDED (knn2_fold_rows): words 3i+2 (i = 0..4) hold w[3i] ^ w[3i+1] ^ w[3i+2],
+// and word 15 holds w9 ^ w10 ^ ... ^ w15.  XOR is linear, so q'[3i+2] ^ w'[3i+2] is directly the sum
+// output of the first-level carry-save adder over the triple (x[3i], x[3i+1], x[3i+2]) of the
+// unfolded difference, and its carry follows from the two plain differences and that sum in one
+// LOP3: 4 instead of 5 LOP3 per triple.  Likewise q'[15] ^ w'[15] is the sum output of the
+// second-level adder over (s3, s4, x[15]).  6 fewer ALU instructions per distance, bit-identical
+// distances.
 //
 // key = base + (distance << kKeyIdxBits) for a register-resident searcher row q and a database
 // row w; distance = 512-bit Hamming.  CSA = number of carry-save adders applied before the POPCs
@@ -101,6 +103,7 @@ __device__ __forceinline__ uint32_t hamming_key(const uint32_t (&q)[16], const u
     } while (0)
     if constexpr (CSA == 0) {
         // plain 16 POPC baseline: undo the fold of the difference first
+        x[15] = xor3(x[15], x[11], x[14]);
 #pragma unroll
         for (int i = 0; i < 5; ++i) x[3 * i + 2] = xor3(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
 #pragma unroll
@@ -116,14 +119,15 @@ __device__ __forceinline__ uint32_t hamming_key(const uint32_t (&q)[16], const u
         const uint32_t c4 = carry_from_sum(x[12], x[13], s4);
         if constexpr (CSA == 5) {
             HULO_ACC(s0, 1u, n1); HULO_ACC(s1, 1u, n1); HULO_ACC(s2, 1u, n1); HULO_ACC(s3, 1u, n1);
-            HULO_ACC(s4, 1u, n1); HULO_ACC(x[15], 1u, n1);
+            HULO_ACC(s4, 1u, n1); HULO_ACC(xor3(x[15], s3, s4), 1u, n1);
             HULO_ACC(c0, 2u, n2); HULO_ACC(c1, 2u, n2); HULO_ACC(c2, 2u, n2); HULO_ACC(c3, 2u, n2);
             HULO_ACC(c4, 2u, n2);
         } else {
             // level 2: the six weight-1 words -> 2 sums + 2 carries
-            uint32_t s5, s6, c5, c6;
+            uint32_t s5, c5;
             HULO_CSA(c5, s5, s0, s1, s2);
-            HULO_CSA(c6, s6, s3, s4, x[15]);
+            const uint32_t s6 = x[15];                             // folded: s3 ^ s4 ^ (plain x15)
+            const uint32_t c6 = carry_from_sum(s3, s4, s6);
             HULO_ACC(s5, 1u, n1); HULO_ACC(s6, 1u, n1);
             if constexpr (CSA == 7) {
                 HULO_ACC(c0, 2u, n2); HULO_ACC(c1, 2u, n2); HULO_ACC(c2, 2u, n2); HULO_ACC(c3, 2u, n2);
@@ -156,6 +160,23 @@ __device__ __forceinline__ uint32_t hamming_key(const uint32_t (&q)[16], const u
     if constexpr (IMAD) return key;
     else return base + ((n1 + 2u * n2 + 4u * n4 + 8u * n8) << kKeyIdxBits);
 }
+
+// One database row against the QPT register-resident searcher rows of a thread, unrolled at
+// compile time.  CSA == 89 is a mix: the last searcher row of the thread uses nine carry-save
+// adders, the others eight -- per distance that is 27.5 LOP3 + 7.75 POPC, which puts the ALU
+// pipe (2 cycles per warp instruction) and the XU pipe (8 cycles per POPC) at the same load.
+template <int QI, int QPT, int CSA, bool IMAD>
+struct RowVsQueries {
+    static __device__ __forceinline__ void run(const uint32_t (&q)[QPT][16], const uint32_t (&w)[16], uint32_t base,
+                                               uint32_t unit, uint32_t (&best0)[QPT], uint32_t (&best1)[QPT]) {
+        constexpr int kCsa = CSA == 89 ? (QI == QPT - 1 ? 9 : 8) : CSA == 889 ? (2 * QI >= QPT ? 9 : 8) : CSA;
+        const uint32_t key = hamming_key<kCsa, IMAD>(q[QI], w, base, unit);
+        const uint32_t hi = max(best0[QI], key);
+        best0[QI] = min(best0[QI], key);
+        best1[QI] = min(best1[QI], hi);
+        if constexpr (QI + 1 < QPT) RowVsQueries<QI + 1, QPT, CSA, IMAD>::run(q, w, base, unit, best0, best1);
+    }
+};
 
 // OPT bit 0: adds on the FMA pipe (IMAD); bit 1: rows taken two at a time so the best-2 update
 // uses 3-input min/max (VIMNMX3): 5 instead of 6 instructions per two keys.
@@ -267,8 +288,9 @@ __global__ void __launch_bounds__(THREADS, 1) knn2_kernel(const KnnParams p) {
                     load_row(r + 1, w1);
 #pragma unroll
                     for (int qi = 0; qi < QPT; ++qi) {
-                        const uint32_t k0 = hamming_key<CSA, kImad>(q[qi], w0, key_base + r, unit);
-                        const uint32_t k1 = hamming_key<CSA, kImad>(q[qi], w1, key_base + r + 1, unit);
+                        constexpr int kCsaPair = (CSA == 89 || CSA == 889) ? 8 : CSA;
+                        const uint32_t k0 = hamming_key<kCsaPair, kImad>(q[qi], w0, key_base + r, unit);
+                        const uint32_t k1 = hamming_key<kCsaPair, kImad>(q[qi], w1, key_base + r + 1, unit);
                         const uint32_t lo = min(k0, k1), hi = max(k0, k1);
                         const uint32_t m = max(best0[qi], lo);
                         best0[qi] = min(best0[qi], lo);
@@ -280,13 +302,7 @@ __global__ void __launch_bounds__(THREADS, 1) knn2_kernel(const KnnParams p) {
             for (; r < rows; ++r) {
                 uint32_t w[16];
                 load_row(r, w);
-#pragma unroll
-                for (int qi = 0; qi < QPT; ++qi) {
-                    const uint32_t key = hamming_key<CSA, kImad>(q[qi], w, key_base + r, unit);
-                    const uint32_t hi = max(best0[qi], key);
-                    best0[qi] = min(best0[qi], key);
-                    best1[qi] = min(best1[qi], hi);
-                }
+                RowVsQueries<0, QPT, CSA, kImad>::run(q, w, key_base + r, unit, best0, best1);
             }
             ++n_cons;
             __syncwarp();
@@ -443,7 +459,7 @@ __global__ void knn2_merge_from_peers_kernel(const PeerExchange px, uint32_t nA,
     write_result(m0, m1, row, out_idx2, out_dist2, nullptr);
 }
 
-// In-place fold / unfold of 64-byte rows (an involution): w[3i+2] ^= w[3i] ^ w[3i+1], i = 0..4.
+// In-place fold of 64-byte rows: w[3i+2] ^= w[3i] ^ w[3i+1] for i = 0..4, then w15 ^= w11 ^ w14.
 __global__ void knn2_fold_rows_kernel(uint4 *__restrict__ rows, size_t n) {
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
@@ -454,6 +470,7 @@ __global__ void knn2_fold_rows_kernel(uint4 *__restrict__ rows, size_t n) {
     c.x ^= b.z ^ b.w;      // w8  ^= w6 ^ w7
     c.w ^= c.y ^ c.z;      // w11 ^= w9 ^ w10
     d.z ^= d.x ^ d.y;      // w14 ^= w12 ^ w13
+    d.w ^= c.w ^ d.z;      // w15 ^= w11' ^ w14'  (= w9 ^ ... ^ w15)
     p[0] = a; p[1] = b; p[2] = c; p[3] = d;
 }
 
@@ -482,7 +499,9 @@ cudaError_t info_variant(int *regs, int *ctas, size_t *smem) {
     X(256, 8, 7, 1) X(256, 8, 7, 2) X(256, 8, 7, 3) X(256, 8, 8, 0) X(256, 8, 8, 1) X(256, 8, 8, 3) \
     X(512, 4, 7, 0) X(512, 4, 7, 1) X(512, 4, 7, 3) X(512, 4, 8, 1) X(512, 4, 8, 3) X(512, 4, 9, 0) \
     X(256, 4, 7, 0) X(256, 4, 7, 3) X(256, 4, 8, 3) X(128, 8, 7, 0) X(128, 4, 7, 0) X(128, 4, 7, 3) \
-    X(768, 2, 8, 1) X(768, 2, 7, 1) X(768, 2, 8, 0) X(640, 3, 8, 1) X(640, 3, 7, 1) X(640, 3, 8, 0) X(384, 5, 8, 1)
+    X(768, 2, 8, 1) X(768, 2, 7, 1) X(768, 2, 8, 0) X(640, 3, 8, 1) X(640, 3, 7, 1) X(640, 3, 8, 0) X(384, 5, 8, 1) \
+    X(512, 4, 89, 1) X(512, 4, 9, 1) X(256, 8, 89, 1) X(256, 8, 9, 1) X(256, 4, 89, 1) X(256, 4, 8, 1) X(128, 4, 8, 1) \
+    X(512, 4, 889, 1) X(256, 4, 889, 1) X(256, 4, 9, 1) X(128, 4, 89, 1) X(128, 4, 889, 1)
 
 cudaError_t knn2_launch(const KnnParams &p, const KnnConfig &cfg, int grid_ctas, cudaStream_t stream) {
 #define X(T, Q, C, O) \
@@ -509,9 +528,10 @@ cudaError_t knn2_fold_rows_launch(uint4 *rows, size_t n, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-void knn2_fold_rows_host(uint8_t *rows64, size_t n) {
+void knn2_unfold_rows_host(uint8_t *rows64, size_t n) {
     for (size_t r = 0; r < n; ++r) {
         uint32_t *w = reinterpret_cast<uint32_t *>(rows64 + r * 64);
+        w[15] ^= w[11] ^ w[14];                                   // while w11, w14 are still folded
         for (int i = 0; i < 5; ++i) w[3 * i + 2] ^= w[3 * i] ^ w[3 * i + 1];
     }
 }

@@ -50,7 +50,7 @@ struct KnnParams {
 struct KnnConfig {
     int threads;
     int qpt;
-    int csa;   // carry-save depth: number of CSAs applied before POPC (0, 5, 7, 8, 9, 11)
+    int csa;   // carry-save depth: number of CSAs applied before POPC (0, 5, 7, 8, 9, 11); 89 / 889: 8 and 9 mixed per searcher row
     int opt;   // bit 0: adds on the FMA pipe (IMAD); bit 1: two rows per best-2 update (VIMNMX3)
 };
 
@@ -62,10 +62,10 @@ inline uint32_t knn2_tile_rows(const KnnConfig &cfg) { return (uint32_t)(cfg.thr
 cudaError_t knn2_kernel_info(const KnnConfig &cfg, int *regs, int *max_ctas_per_sm, size_t *smem);
 
 // Device layout of a descriptor row: FOLDED -- words 3i+2 (i = 0..4) hold w[3i] ^ w[3i+1] ^ w[3i+2]
-// (see hamming_key in knn2.cu).  Every table and staging buffer K1 reads must be folded after its
-// upload; the transform is its own inverse (download = copy + fold on the host).
+// and word 15 holds w9 ^ ... ^ w15 (see hamming_key in knn2.cu).  Every table and staging buffer
+// K1 reads must be folded after its upload; a download copies and unfolds on the host.
 cudaError_t knn2_fold_rows_launch(uint4 *rows, size_t n, cudaStream_t stream);
-void knn2_fold_rows_host(uint8_t *rows64, size_t n);
+void knn2_unfold_rows_host(uint8_t *rows64, size_t n);
 
 // Merge the per-chunk keys of every searcher row into final (idx, dist) pairs.
 //   slot(row, c) = c * slot_stride + row ; global index = row_base + c * rows_per_chunk + (key & mask)

@@ -181,20 +181,27 @@ __global__ void compact_write_kernel(const int32_t *__restrict__ val, const int3
     }
 }
 
-// seg_out_off[s] = number of survivors in compact rows [0, seg_off[s])
+// seg_out_off[s] = number of survivors in compact rows [0, seg_off[s]).  One warp per segment
+// boundary: the survivors before the boundary's compaction block come from the block scan, the
+// rows of that block up to the boundary are counted with coalesced loads and ballots.
 __global__ void compact_seg_offsets_kernel(const int32_t *__restrict__ val, uint32_t n_rows,
                                            const uint64_t *__restrict__ seg_off, uint32_t n_seg,
                                            const uint32_t *__restrict__ block_offsets,
                                            uint64_t *__restrict__ seg_out_off) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
     if (s > n_seg) return;
     const uint64_t row = seg_off[s];
     const uint32_t b = (uint32_t)(row / kCompactBlockRows);
-    uint64_t o = block_offsets[b];   // block_offsets has n_blocks + 1 entries (last = total)
     const uint32_t start = b * kCompactBlockRows;
-    for (uint32_t r = start; r < (uint32_t)row && r < n_rows; ++r)
-        if (val[r] >= 0) ++o;
-    seg_out_off[s] = o;
+    const uint32_t end = (uint32_t)(row < n_rows ? row : n_rows);
+    uint32_t cnt = 0;
+    for (uint32_t r0 = start; r0 < end; r0 += 32) {
+        const uint32_t r = r0 + lane;
+        const bool live = r < end && val[r] >= 0;
+        cnt += __popc(__ballot_sync(0xffffffffu, live));
+    }
+    if (lane == 0) seg_out_off[s] = (uint64_t)block_offsets[b] + cnt;   // block_offsets has n_blocks + 1 entries
 }
 
 }  // namespace
@@ -239,8 +246,8 @@ cudaError_t compact_launch(const int32_t *val, const int32_t *dist, uint32_t n_r
                                                                       block_counts, out_seg, out_i, out_j,
                                                                       out_d);
     if (seg_out_off)
-        compact_seg_offsets_kernel<<<(n_seg + 1 + 255) / 256, 256, 0, stream>>>(val, n_rows, seg_off, n_seg,
-                                                                              block_counts, seg_out_off);
+        compact_seg_offsets_kernel<<<(n_seg + 1 + 7) / 8, 256, 0, stream>>>(val, n_rows, seg_off, n_seg,
+                                                                          block_counts, seg_out_off);
     return cudaGetLastError();
 }
 

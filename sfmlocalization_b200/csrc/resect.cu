@@ -558,7 +558,10 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
     // max_iter - reserve draws), then one batch of `reserve` draws from the inliers.
     const size_t reserve = max_iter / 10;
     const size_t global_budget = max_iter - reserve;
-    const size_t batch = std::min<size_t>(global_budget, 512);
+    // the first batches are small and grow (64, 128, 256, 512, 512, ...): the sequential algorithm
+    // leaves the global phase at its first meaningful model, which on clean correspondence sets is
+    // one of the very first draws, so a large first batch would only score models it discards
+    size_t batch = std::min<size_t>(global_budget, 64);
     uint64_t rng = seed;
     std::vector<size_t> pool(N);
     for (size_t i = 0; i < N; ++i) pool[i] = i;
@@ -641,6 +644,7 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
         if (rc != HULO_OK) return rc;
         drawn += T;
         if (best_nfa < 0.0) break;
+        batch = std::min<size_t>(batch * 2, 512);
     }
     double final_nfa = INFINITY;
     if (best_nfa < INFINITY) final_nfa = finalize(best_model);

@@ -1,0 +1,52 @@
+"""Condense an .ncu-rep (read here with `ncu -i ... --page raw --csv`) into a small JSON kept
+under profiles/.  usage: python tools/ncu_summary.py <rep> <out.json> "<kernel label>" "<command>" "<workload>" """
+import csv
+import io
+import json
+import subprocess
+import sys
+
+KEEP = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__cycles_active.avg",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.per_cycle_active",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+]
+
+
+def main():
+    rep, out, label, cmd, workload = sys.argv[1:6]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    launches = rows[2:]
+    res = {"kernel": label, "command": cmd, "workload": workload, "launches_in_report": len(launches), "metrics": {}}
+    vals = launches[-1]
+    stalls = []
+    for h, u, v in zip(hdr, units, vals):
+        if h in KEEP:
+            res["metrics"][h] = {"value": v, "unit": u}
+        if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
+            try:
+                stalls.append((float(v), h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]))
+            except ValueError:
+                pass
+    res["warps_stalled_per_issue_active"] = [{"reason": h, "ratio": round(v, 3)} for v, h in sorted(stalls, reverse=True)[:8]]
+    with open(out, "w") as f:
+        json.dump(res, f, indent=1)
+    print("wrote", out, "with", len(res["metrics"]), "metrics")
+
+
+if __name__ == "__main__":
+    main()

@@ -214,6 +214,22 @@ int hulo_geometric_filter(hulo_gpu *h, const double *xI, const double *xJ, const
                           uint64_t seed, const uint64_t *pair_seeds, int32_t *valid, uint32_t *n_inliers,
                           int32_t *inliers, double *F, double *error_max, double *nfa);
 
+/* Guided matching of the geometric filter (bGuided_matching = true of hulo::geometricMatch,
+ * MatchUtils.cpp:372-420; -gm of the CLIs, on by default in the reconstruction drivers,
+ * ReconstructParam.py:70-71): OpenMVG's Geometry_guided_matching for the pairs that passed the
+ * robust estimation.  For pair p = (I, J) = (pairs[2p], pairs[2p+1]) of segments of `db`, with
+ * F[p] (row-major, pixel coordinates, x_J^T F x_I = 0, as hulo_geometric_filter returns it) and
+ * error_th[p] = (robust precision in pixels)^2: for every feature i of I the nearest and second
+ * nearest descriptor among the features j of J whose squared distance to the epipolar line F x_i
+ * is < error_th[p]; the match (i, j) is kept iff a second one exists and best < dist_ratio * second
+ * (OpenMVG passes 0.6^2).  xy holds the (undistorted) feature position of every row of `db`,
+ * 2 doubles per row.  dedup != 0 drops, per pair, matches whose position 4-tuple repeats as floats
+ * (first kept).  Output as hulo_match_pairs: ascending i inside a pair, pair_offsets (n_pairs + 1),
+ * capacity protocol of hulo_match_to_query. */
+int hulo_guided_match(hulo_gpu *h, const hulo_db *db, const double *xy, const uint32_t *pairs, size_t n_pairs,
+                      const double *F, const double *error_th, double dist_ratio, int dedup,
+                      uint64_t *pair_offsets, uint32_t *out_i, uint32_t *out_j, size_t cap, size_t *n_out);
+
 /* ------------------------------------------------- query localisation, end to end */
 
 typedef struct hulo_engine hulo_engine;

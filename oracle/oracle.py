@@ -281,3 +281,21 @@ def fmatrix_acransac(xI, xJ, sizeI, sizeJ, precision_px=4.0, max_iter=1024, seed
                                     int(sizeJ[1]), C.c_double(precision_px), C.c_size_t(max_iter), C.c_uint64(seed),
                                     _p(F), _p(inl), C.byref(n_inl), C.byref(emax), C.byref(nfa))
     return dict(ok=bool(ok), F=F, inliers=inl[:n_inl.value].copy(), error_max=emax.value, nfa=nfa.value)
+
+
+# ---------------------------------------------------------------- guided matching (geometric filter, -gm)
+def guided_match(F, xI, descI, xJ, descJ, error_th, dist_ratio=0.36, dedup=True):
+    """orc_guided_match (+ orc_guided_dedup) -> (i, j) arrays, ascending i."""
+    F, xI, xJ = _f64(F), _f64(xI), _f64(xJ)
+    descI, descJ = _u8(descI), _u8(descJ)
+    nI, nJ = descI.shape[0], descJ.shape[0]
+    oi = np.empty(max(nI, 1), np.int32)
+    oj = np.empty(max(nI, 1), np.int32)
+    lib().orc_guided_match.restype = C.c_size_t
+    lib().orc_guided_dedup.restype = C.c_size_t
+    n = lib().orc_guided_match(_p(F), _p(xI), _p(descI), C.c_size_t(nI), C.c_size_t(descI.shape[1] if nI else 64),
+                               _p(xJ), _p(descJ), C.c_size_t(nJ), C.c_size_t(descJ.shape[1] if nJ else 64),
+                               C.c_double(error_th), C.c_double(dist_ratio), _p(oi), _p(oj))
+    if dedup and n:
+        n = lib().orc_guided_dedup(_p(xI), _p(xJ), _p(oi), _p(oj), C.c_size_t(n))
+    return oi[:n].copy(), oj[:n].copy()

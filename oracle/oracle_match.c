@@ -24,6 +24,7 @@
  * cv2.flann_Index LINEAR) through tests/golden/ -- see tests/golden/make_golden.py.
  */
 #include <limits.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -316,4 +317,74 @@ size_t orc_match_set(const int32_t *m_view, const int32_t *m_i, const int32_t *m
     free(best_lm);
     free(best_d);
     return n;
+}
+
+/* =====================================================================================
+ * Guided matching of the F-matrix geometric filter (bGuided_matching = true; the
+ * reconstruction drivers pass -gm by default, ReconstructParam.py:70-71,
+ * reconstructGraph.py:156-163).  CPU restatement of OpenMVG 1.1
+ *   robust_estimation/guided_matching.hpp  (GuidedMatching with Regions, distanceRatio)
+ *   matching_image_collection/F_ACRobust.hpp (Geometry_guided_matching: errorTh =
+ *        Square(precision_robust), distRatio = Square(0.6))
+ * as called by ImageCollectionGeometricFilter::Robust_model_estimation behind
+ * hulo::geometricMatch (MatchUtils.cpp:410-413).  PARITY UNPINNED (OpenMVG not vendored,
+ * no reference test).  For every feature i of image I: among the features j of image J
+ * whose squared distance to the epipolar line F x_i is < error_th, the nearest and second
+ * nearest in Hamming distance; kept iff a second one exists and best < dist_ratio * second
+ * (doubles).  The nearest keeps the lowest j on ties (strict < in distanceRatio::update).
+ * Known deviation: upstream then removes matches whose position 4-tuple repeats
+ * (IndMatchDecorator::getDeduplicated) and emits them in the order of its position-keyed
+ * set; orc_guided_dedup keeps the first of each 4-tuple in ascending i and keeps that order.
+ * ===================================================================================== */
+size_t orc_guided_match(const double *F, const double *xI, const uint8_t *descI, size_t nI, size_t strideI,
+                        const double *xJ, const uint8_t *descJ, size_t nJ, size_t strideJ, double error_th,
+                        double dist_ratio, int32_t *out_i, int32_t *out_j) {
+    int32_t *best = (int32_t *)malloc(sizeof(int32_t) * (nI ? nI : 1));
+    const size_t lenI = strideI < 64 ? strideI : 64, lenJ = strideJ < 64 ? strideJ : 64;
+    const size_t len = lenI < lenJ ? lenI : lenJ;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long long i = 0; i < (long long)nI; ++i) {
+        /* explicit fma() in a fixed order: the device evaluates the same expression tree, so the
+         * strict comparison with error_th decides identically on both sides */
+        const double a = xI[2 * i], b = xI[2 * i + 1];
+        const double l0 = fma(F[0], a, fma(F[1], b, F[2])), l1 = fma(F[3], a, fma(F[4], b, F[5])),
+                     l2 = fma(F[6], a, fma(F[7], b, F[8]));
+        const double den = fma(l0, l0, l1 * l1);
+        double bd = 1e300, sbd = 1e300;
+        int have2 = 0, have1 = 0;
+        int32_t idx = -1;
+        for (size_t j = 0; j < nJ; ++j) {
+            const double d = fma(l0, xJ[2 * j], fma(l1, xJ[2 * j + 1], l2));
+            const double err = d * d / den;
+            if (!(err < error_th)) continue;
+            int h = row_hamming(descI + (size_t)i * strideI, descJ + j * strideJ, len);
+            /* bytes beyond the shorter row count as zero on that side */
+            for (size_t k = len; k < lenI; ++k) h += __builtin_popcount(descI[(size_t)i * strideI + k]);
+            for (size_t k = len; k < lenJ; ++k) h += __builtin_popcount(descJ[j * strideJ + k]);
+            const double dist = (double)h;
+            if (dist < bd) { sbd = bd; have2 = have1; bd = dist; idx = (int32_t)j; have1 = 1; }
+            else if (dist < sbd) { sbd = dist; have2 = 1; }
+        }
+        best[i] = (have2 && bd < dist_ratio * sbd) ? idx : -1;
+    }
+    size_t n = 0;
+    for (size_t i = 0; i < nI; ++i)
+        if (best[i] >= 0) { out_i[n] = (int32_t)i; out_j[n] = best[i]; ++n; }
+    free(best);
+    return n;
+}
+
+/* Keep the first match (ascending position in the list) of every (xI_i, xJ_j) position
+ * 4-tuple compared as floats, order preserved.  Returns the new count (in place). */
+size_t orc_guided_dedup(const double *xI, const double *xJ, int32_t *mi, int32_t *mj, size_t n) {
+    size_t out = 0;
+    for (size_t k = 0; k < n; ++k) {
+        const float a = (float)xI[2 * mi[k]], b = (float)xI[2 * mi[k] + 1], c = (float)xJ[2 * mj[k]], d = (float)xJ[2 * mj[k] + 1];
+        int dup = 0;
+        for (size_t m = 0; m < out && !dup; ++m)
+            dup = a == (float)xI[2 * mi[m]] && b == (float)xI[2 * mi[m] + 1] && c == (float)xJ[2 * mj[m]] &&
+                  d == (float)xJ[2 * mj[m] + 1];
+        if (!dup) { mi[out] = mi[k]; mj[out] = mj[k]; ++out; }
+    }
+    return out;
 }

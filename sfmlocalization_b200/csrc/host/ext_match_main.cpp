@@ -14,9 +14,9 @@
 // Flags -f/-v/-p/-mf/-r/-mm/-g have the reference's meaning (computeFeaturesAndMatches.cpp:49-64;
 // -g is read as an integer there, :92, and here); the extraction flags (-c -t -o -l -sm) are
 // accepted and ignored so the Python drivers' command lines keep working
-// (reconstructGraph.py:158-163); -gm (guided matching) is not implemented: a warning is printed
-// and the unguided filter runs.  When a .feat file or an image size is missing the geometric stage
-// is skipped with a message (the reference would abort: "Cannot construct regions providers").
+// (reconstructGraph.py:158-163); -gm switches guided matching on like the reference.  When a .feat
+// file or an image size is missing the geometric stage is skipped with a message (the reference
+// would abort: "Cannot construct regions providers").
 // The view list comes from <matchdir>/sfm_data.json like the reference, or from --views.
 // --rank/--world shard the pair list across processes (one per GPU, no collective); each
 // rank writes <out>.rank<R> (and matches.f.txt.rank<R>), rank order concatenation equals the
@@ -131,9 +131,9 @@ int main(int argc, char **argv) {
             if (!have) {
                 std::cout << "geometric matching skipped: .feat files or image sizes are missing" << std::endl;
             } else {
-                if (bGuided) std::cerr << "warning: guided matching (-gm) is not implemented; running the unguided filter\n";
                 PairWiseMatches geometric;
-                geometricMatch(session, views, regions, matches, geometric, ransacRound, (double)geomError, false);
+                geometricMatch(session, views, regions, sMatchesDir, matches, geometric, ransacRound, (double)geomError,
+                               bGuided);
                 std::string sF = sMatchesDir + "/matches.f.txt";
                 if (world > 1) sF += ".rank" + std::to_string(rank);
                 if (!exportPairWiseMatches(geometric, sF)) {

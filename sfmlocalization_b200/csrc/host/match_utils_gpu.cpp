@@ -199,7 +199,15 @@ uint64_t g_geometricSeed = 0x5eedULL;
 void geometricMatch(GpuSession &s, const Views &views, const RegionsProvider &regions_provider,
                     const PairWiseMatches &map_putativeMatches, PairWiseMatches &map_geometricMatches,
                     int ransacRound, double geomPrec, bool bGuided_matching) {
-    if (bGuided_matching) throw std::invalid_argument("hulo::geometricMatch: guided matching is not implemented");
+    if (bGuided_matching)
+        throw std::invalid_argument("hulo::geometricMatch: guided matching needs the descriptor directory (sMatchesDir overload)");
+    geometricMatch(s, views, regions_provider, std::string(), map_putativeMatches, map_geometricMatches, ransacRound,
+                   geomPrec, false);
+}
+
+void geometricMatch(GpuSession &s, const Views &views, const RegionsProvider &regions_provider,
+                    const std::string &sMatchesDir, const PairWiseMatches &map_putativeMatches,
+                    PairWiseMatches &map_geometricMatches, int ransacRound, double geomPrec, bool bGuided_matching) {
     map_geometricMatches.clear();                                                  // assignment at :415
     std::vector<double> xI, xJ;
     std::vector<uint64_t> off(1, 0), seeds;
@@ -222,14 +230,60 @@ void geometricMatch(GpuSession &s, const Views &views, const RegionsProvider &re
     if (P) {
         std::vector<int32_t> valid(P), inl(std::max<std::size_t>((std::size_t)off.back(), 1));
         std::vector<uint32_t> ninl(P);
+        std::vector<double> F(9 * P), err(P);
         must(hulo_geometric_filter(s.gpu(), xI.data(), xJ.data(), off.data(), P, sizes.data(), geomPrec,
                                    (std::size_t)std::max(ransacRound, 0), g_geometricSeed, seeds.data(), valid.data(),
-                                   ninl.data(), inl.data(), nullptr, nullptr, nullptr),
+                                   ninl.data(), inl.data(), F.data(), err.data(), nullptr),
              "hulo_geometric_filter");
         for (std::size_t p = 0; p < P; ++p) {
             if (!valid[p]) continue;
             IndMatches &out = map_geometricMatches[kept[p]->first];
             for (uint32_t c = 0; c < ninl[p]; ++c) out.push_back(kept[p]->second[(std::size_t)inl[off[p] + c]]);
+        }
+        if (bGuided_matching && !map_geometricMatches.empty()) {
+            // Geometry_guided_matching over all features of the surviving pairs
+            std::vector<std::size_t> ids;
+            for (const auto &kv : map_geometricMatches) { ids.push_back(kv.first.first); ids.push_back(kv.first.second); }
+            std::sort(ids.begin(), ids.end());
+            ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+            auto t = s.table(views, sMatchesDir, ids);
+            std::vector<double> xy;
+            for (std::size_t v : t->view_ids) {
+                const FeatureLocations &f = regions_provider.at(v);
+                if (f.size() != t->rows_of_view.at(v))
+                    throw std::runtime_error("hulo::geometricMatch: view " + std::to_string(v) + " has " + std::to_string(f.size()) +
+                                             " features but " + std::to_string(t->rows_of_view.at(v)) + " descriptors");
+                for (const auto &pt : f) { xy.push_back(pt.first); xy.push_back(pt.second); }
+            }
+            std::vector<uint32_t> seg_pairs;
+            std::vector<double> gF, gthr;
+            std::vector<Pair> gkeys;
+            for (std::size_t p = 0; p < P; ++p) {
+                if (!valid[p]) continue;
+                seg_pairs.push_back(t->seg_of_view.at(kept[p]->first.first));
+                seg_pairs.push_back(t->seg_of_view.at(kept[p]->first.second));
+                gF.insert(gF.end(), F.begin() + 9 * p, F.begin() + 9 * p + 9);
+                gthr.push_back(err[p] * err[p]);                                   // Square(m_dPrecision_robust)
+                gkeys.push_back(kept[p]->first);
+            }
+            const std::size_t G = gkeys.size();
+            std::vector<uint64_t> goff(G + 1, 0);
+            std::vector<uint32_t> gi(1), gj(1);
+            std::size_t n = 0;
+            static const double none2[2] = {0, 0};
+            int rc = hulo_guided_match(s.gpu(), t->db, xy.empty() ? none2 : xy.data(), seg_pairs.data(), G, gF.data(),
+                                       gthr.data(), 0.6 * 0.6, 1, goff.data(), gi.data(), gj.data(), 0, &n);
+            if (rc == HULO_ERR_CAPACITY) {
+                gi.resize(n); gj.resize(n);
+                rc = hulo_guided_match(s.gpu(), t->db, xy.data(), seg_pairs.data(), G, gF.data(), gthr.data(), 0.6 * 0.6, 1,
+                                       goff.data(), gi.data(), gj.data(), n, &n);
+            }
+            must(rc, "hulo_guided_match");
+            for (std::size_t g = 0; g < G; ++g) {
+                IndMatches &out = map_geometricMatches[gkeys[g]];                  // the key stays even when empty
+                out.clear();
+                for (uint64_t m = goff[g]; m < goff[g + 1]; ++m) out.push_back(IndMatch(gi[m], gj[m]));
+            }
         }
     }
     std::cout << "number of putative matches : " << map_putativeMatches.size() << std::endl;

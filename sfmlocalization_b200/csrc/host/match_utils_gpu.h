@@ -56,14 +56,21 @@ void matchAKAZEToQuery(const Views &views, const std::string &sMatchesDir, const
 // GeometricFilter_FMatrix_AC(geomPrec, ransacRound) on every pair of map_putativeMatches; pairs
 // whose robust estimation fails get no key in map_geometricMatches; surviving pairs hold the
 // inliers in ACRANSAC's order.  SfM_Data is replaced by the views (image sizes) and the
-// Regions_Provider by the feature positions.  bGuided_matching = true throws
-// std::invalid_argument: guided matching is not implemented.
+// Regions_Provider by the feature positions (+ the directory of the .desc files, which the
+// reference's Regions_Provider holds in memory).  With bGuided_matching the inliers of every
+// surviving pair are replaced by OpenMVG's Geometry_guided_matching over ALL features of the two
+// images (hulo_guided_match: epipolar gate at the robust precision, descriptor ratio 0.6^2), in
+// ascending i; the overloads without sMatchesDir have no descriptors and throw
+// std::invalid_argument when it is requested.
 void geometricMatch(const Views &views, const RegionsProvider &regions_provider,
                     const PairWiseMatches &map_putativeMatches, PairWiseMatches &map_geometricMatches,
                     int ransacRound, double geomPrec, bool bGuided_matching);
 void geometricMatch(GpuSession &s, const Views &views, const RegionsProvider &regions_provider,
                     const PairWiseMatches &map_putativeMatches, PairWiseMatches &map_geometricMatches,
                     int ransacRound, double geomPrec, bool bGuided_matching);
+void geometricMatch(GpuSession &s, const Views &views, const RegionsProvider &regions_provider,
+                    const std::string &sMatchesDir, const PairWiseMatches &map_putativeMatches,
+                    PairWiseMatches &map_geometricMatches, int ransacRound, double geomPrec, bool bGuided_matching);
 // sampler seed of the filter (pair (I, J) draws from a stream derived from it and from I, J, so
 // the result of a pair does not depend on which other pairs are filtered with it)
 extern uint64_t g_geometricSeed;

@@ -300,6 +300,27 @@ class HuloGpu:
         return dict(valid=valid[:P].astype(bool), n_inliers=ninl[:P].copy(), inliers=per_pair, F=F[:P].copy(),
                     error_max=emax[:P].copy(), nfa=nfa[:P].copy())
 
+    def guided_match(self, db, xy, pairs, F, error_th, dist_ratio=0.36, dedup=True, cap=None):
+        """hulo_guided_match -> (pair_offsets uint64[P+1], i, j)."""
+        xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+        pairs = np.ascontiguousarray(pairs, np.uint32).reshape(-1, 2)
+        F = np.ascontiguousarray(F, np.float64).reshape(-1, 9)
+        thr = np.ascontiguousarray(error_th, np.float64)
+        P = pairs.shape[0]
+        cap = (1 << 20) if cap is None else cap
+        while True:
+            off = np.zeros(P + 1, np.uint64)
+            oi = np.empty(max(cap, 1), np.uint32)
+            oj = np.empty(max(cap, 1), np.uint32)
+            n = C.c_size_t(0)
+            st = self.lib.hulo_guided_match(self.h, db.h, _ptr(xy), _ptr(pairs), P, _ptr(F), _ptr(thr), dist_ratio,
+                                            int(bool(dedup)), _ptr(off), _ptr(oi), _ptr(oj), cap, C.byref(n))
+            if st == _lib.ERR_CAPACITY:
+                cap = int(n.value)
+                continue
+            check(st)
+            return off, oi[:n.value].copy(), oj[:n.value].copy()
+
     # -- multi GPU
     @staticmethod
     def comm_unique_id():

@@ -162,3 +162,37 @@ def test_geometric_stage_skipped_without_feat_files(tmp_path):
     assert "geometric matching skipped" in out and not (d / "matches.f.txt").exists()
     out = run_cli(d, "-f=0.7", "--putative-only")
     assert "Geometric" not in out
+
+
+def test_guided_matching_flag(tmp_path, orc):
+    """-gm: the inliers of every surviving pair are replaced by guided matches over all features of
+    the two images (ReconstructParam.py:70-71 switches it on for reconstruction)."""
+    V = 4
+    sc = synth.localization_scene(V, 700, 900, 10, 33, track_frac=0.7)
+    off = sc["seg_offsets"]
+    d = tmp_path / "matches"
+    d.mkdir()
+    segs, xys = [], []
+    for k in range(V):
+        seg = sc["rows"][int(off[k]):int(off[k + 1])]
+        xy = sc["map_xy"][int(off[k]):int(off[k + 1])]
+        hostlib.write_desc_numpy(str(d / ("frame%04d.desc" % k)), np.ascontiguousarray(seg[:, :61]))
+        hostlib.write_feat(str(d / ("frame%04d.feat" % k)), xy)
+        segs.append(seg); xys.append(xy)
+    views = [{"key": k, "value": {"ptr_wrapper": {"data": {"local_path": "/", "filename": "frame%04d.jpg" % k,
+                                                           "width": 1920, "height": 1080, "id_view": k}}}}
+             for k in range(V)]
+    (d / "sfm_data.json").write_text(json.dumps({"root_path": "/x", "views": views, "intrinsics": []}))
+    run_cli(d, "-f=0.7", "-r=200", "-mm=40", "-g=4.0", "-gm")
+    geo = hostlib.parse_matches(str(d / "matches.f.txt"))
+    put = hostlib.parse_matches(str(d / "matches.putative.txt"))
+    assert len(geo) == 6
+    for (I, J), got in geo.items():
+        m = np.array(put[(I, J)])
+        r = orc.fmatrix_acransac(xys[I][m[:, 0]], xys[J][m[:, 1]], (1920, 1080), (1920, 1080), 4.0, 200,
+                                 GEO_SEED + 1000003 * (I * 1000003 + J))
+        assert r["ok"]
+        wi, wj = orc.guided_match(r["F"], xys[I], segs[I], xys[J], segs[J], r["error_max"] ** 2, 0.36)
+        want = set(zip(wi.tolist(), wj.tolist()))
+        assert len(set(got) & want) >= 0.97 * len(set(got) | want) and len(got) > 100
+        assert [g[0] for g in got] == sorted(g[0] for g in got)            # ascending i

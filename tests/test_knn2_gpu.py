@@ -106,3 +106,24 @@ def test_split_database_merge_is_associative(gpu, orc):
     order = np.lexsort((cand_i, cand_d), axis=1)[:, :2]
     md = np.take_along_axis(cand_d, order, axis=1); mi = np.take_along_axis(cand_i, order, axis=1)
     assert np.array_equal(md, d_full) and np.array_equal(mi, i_full)
+
+
+@pytest.mark.parametrize("stride", [61, 64, 70])
+def test_table_round_trip_through_the_device_layout(gpu, stride):
+    """Rows are stored folded on the device (knn2.cuh); a download must give back the 64-byte
+    zero-padded rows that were uploaded, for any stride, and an update must replace them."""
+    rng = np.random.default_rng(stride)
+    rows = rng.integers(0, 256, size=(1000, stride), dtype=np.uint8)
+    want = np.zeros((1000, 64), np.uint8)
+    want[:, :min(stride, 64)] = rows[:, :64]
+    db = gpu.db(rows)
+    try:
+        assert np.array_equal(db.download(), want)
+        assert np.array_equal(db.download(first=123, n=77), want[123:200])
+        rows2 = rng.integers(0, 256, size=(640, stride), dtype=np.uint8)
+        db.update(rows2)
+        want2 = np.zeros((640, 64), np.uint8)
+        want2[:, :min(stride, 64)] = rows2[:, :64]
+        assert len(db) == 640 and np.array_equal(db.download(), want2)
+    finally:
+        db.free()

@@ -463,8 +463,16 @@ def main():
         alg_bytes = 64.0 * (nA + N_MAP / world) + 16.0 * nA
         hbm_gbs = alg_bytes / (ms * 1e-3 / args.steps) / 1e9
         traffic = (read_json(os.path.join(ROOT, "profiles", "k1_traffic.json"), {}) or {}).get("dram_bytes_per_launch")
+        # the limit of the kernel's own instruction mix: per distance 26.5 LOP3 +
+        # 3 VIMNMX on the ALU pipe (2 cycles per warp instruction per sub-partition) and 7.75 POPC on
+        # the XU pipe (8 cycles each); the busier pipe bounds the rate
+        mix_cycles = max((26.5 + 3.0) * 2.0, 7.75 * 8.0)
+        mix_peak = 148 * 4 * 32 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / mix_cycles / 1e9
         roofline = {"bound": "int-popc", "achieved": per_gpu, "peak": peak, "unit": UNIT + "/GPU",
                     "frac": per_gpu / peak, "peak_source": peak_src,
+                    "pipe_limit_of_kernel_mix": {"peak": mix_peak, "frac": per_gpu / mix_peak,
+                                                 "cycles_per_warp_distance": mix_cycles,
+                                                 "mix": "26.5 LOP3 + 3 VIMNMX (ALU, 2 clk) | 7.75 POPC (XU, 8 clk) | 7.75 IMAD (FMA)"},
                     "work_per_unit": "1 dist = 512 compared bits = 16 x 32-bit POPC (naive); the kernel folds "
                                      "words with LOP3 carry-save adders first, so frac can exceed 1",
                     "traffic": traffic,

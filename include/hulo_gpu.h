@@ -295,6 +295,29 @@ int hulo_engine_localize_batch(hulo_engine *e, size_t n_queries, const uint8_t *
                                uint64_t seed, double *pose12, int *localized, uint32_t *n_corr, uint32_t *n_inliers,
                                double *times_ms);
 
+/* ------------------------------------------- K4: 3D-3D transform between two models */
+
+/* ransacAffineTransform (PyVisionLocalizeCommon/src/hulo_sfm/mergeSfM.py:344-388; similarity = 0)
+ * and ransacSimilarityTransform (hulo_transform/ransacTransform.py:13-49; similarity = 1), which
+ * mergeSfM.ransacTransform (:394-399) runs when two models are merged (:577-579) and when a model
+ * is anchored to world coordinates (localizeGlobalCoordinate.py:209, measureAccuracy.py:239):
+ * the 3 x 4 matrix M with A ~ M [B; 1].  Every round takes 4 points, fits M to them (exact 4 x 4
+ * solve, or rotation + scale + translation), counts the points with || M [B_i; 1] - A_i || < thres;
+ * a round replaces the best so far iff it has strictly more inliers and the singular values of its
+ * linear part satisfy s_max / s_min < svd_ratio; M is refitted on the inliers of the best round.
+ * All rounds are scored in one launch.
+ *   A, B      3 x n doubles, row-major (the reference's numpy layout: one row per coordinate)
+ *   samples   rounds x 4 point indices (what random.sample returned per round), or NULL to draw
+ *             them from `seed`
+ *   svd_ratio pass INFINITY for "no condition" (the reference's default sys.float_info.max)
+ * Outputs: M (12 doubles, row-major 3 x 4; all zero when nothing was found), inliers (capacity n,
+ * ascending like np.where), *n_inliers (0 = the reference's `return [], []`), *best_round (may be
+ * NULL) the winning round. */
+int hulo_ransac_transform3d(hulo_gpu *h, const double *A, const double *B, size_t n, double thres,
+                            const uint32_t *samples, size_t rounds, uint64_t seed, double svd_ratio,
+                            int similarity, double *M, int32_t *inliers, size_t *n_inliers,
+                            uint32_t *best_round);
+
 /* ------------------------------------------------------------------ multi GPU */
 
 /* One process per GPU.  Rank 0 obtains an id with hulo_comm_unique_id and distributes its

@@ -299,3 +299,58 @@ def guided_match(F, xI, descI, xJ, descJ, error_th, dist_ratio=0.36, dedup=True)
     if dedup and n:
         n = lib().orc_guided_dedup(_p(xI), _p(xJ), _p(oi), _p(oj), C.c_size_t(n))
     return oi[:n].copy(), oj[:n].copy()
+
+
+# ---------------------------------------------------------------- 3D-3D model-merge RANSAC
+def superimposition_matrix(v0, v1):
+    """Restatement of transformations.superimposition_matrix(v0, v1, scale=True) (Gohlke's
+    transformations.py, which the reference asks the user to drop into hulo_transform/ and does
+    not vendor -- PARITY UNPINNED): similarity transform (4 x 4) taking the 3 x n points v0 onto v1,
+    rotation from the SVD of the covariance (Kabsch, reflection fixed), scale = sqrt of the ratio of
+    the centred sums of squares."""
+    v0 = np.array(v0, np.float64, copy=True)[:3]
+    v1 = np.array(v1, np.float64, copy=True)[:3]
+    t0 = -np.mean(v0, axis=1)
+    t1 = -np.mean(v1, axis=1)
+    v0 += t0.reshape(3, 1)
+    v1 += t1.reshape(3, 1)
+    u, s, vh = np.linalg.svd(np.dot(v1, v0.T))
+    R = np.dot(u, vh)
+    if np.linalg.det(R) < 0.0:
+        R -= np.outer(u[:, 2], vh[2, :] * 2.0)
+    M = np.identity(4)
+    M[:3, :3] = R * np.sqrt(np.sum(v1 * v1) / np.sum(v0 * v0))
+    M0 = np.identity(4); M0[:3, 3] = t0
+    M1 = np.identity(4); M1[:3, 3] = t1
+    return np.dot(np.linalg.inv(M1), np.dot(M, M0))
+
+
+def ransac_transform3d(A, B, thres, samples, svd_ratio=float("inf"), similarity=False):
+    """ransacAffineTransform (PyVisionLocalizeCommon/src/hulo_sfm/mergeSfM.py:344-388) and
+    ransacSimilarityTransform (hulo_transform/ransacTransform.py:13-49) with the 4-point samples
+    of every round given explicitly (the reference draws them with random.sample): find the 3 x 4
+    M with A ~ M [B; 1].  Returns (M, inliers) or (empty, empty).  The affine flavour is pinned
+    against the reference's own function (tests/golden/make_golden_merge.py)."""
+    A = np.asarray(A, np.float64); B = np.asarray(B, np.float64)
+    Bh = np.vstack((B, np.ones((1, B.shape[1]))))
+    inliers = np.asarray([], np.int64)
+    n_inl = 0
+    for sel in np.asarray(samples, np.int64).reshape(-1, 4):
+        if similarity:
+            M = superimposition_matrix(B[:, sel], A[:, sel])[:3]
+        else:
+            M = np.linalg.lstsq(Bh[:, sel].T, A[:, sel].T, rcond=-1)[0].T
+        norm = np.linalg.norm(np.dot(M, Bh) - A, axis=0)
+        tmp = np.where(norm < thres)[0]
+        if len(tmp) >= n_inl:
+            s = np.linalg.svd(M[0:3, 0:3], compute_uv=False)
+            if len(tmp) > n_inl and s[0] / s[-1] < svd_ratio:
+                n_inl = len(tmp)
+                inliers = tmp
+    if len(inliers) < 4:
+        return np.array([]), np.asarray([], np.int64)
+    if similarity:
+        M = superimposition_matrix(B[:, inliers], A[:, inliers])[:3]
+    else:
+        M = np.linalg.lstsq(Bh[:, inliers].T, A[:, inliers].T, rcond=-1)[0].T
+    return M, inliers

@@ -321,6 +321,23 @@ class HuloGpu:
             check(st)
             return off, oi[:n.value].copy(), oj[:n.value].copy()
 
+    # -- K4
+    def ransac_transform3d(self, A, B, thres, rounds, svd_ratio=float("inf"), similarity=False, samples=None, seed=1):
+        """hulo_ransac_transform3d -> (M 3x4, inliers) or (empty, empty) like the reference."""
+        A = np.ascontiguousarray(A, np.float64); B = np.ascontiguousarray(B, np.float64)
+        n = A.shape[1]
+        if samples is not None:
+            samples = np.ascontiguousarray(samples, np.uint32).reshape(-1, 4)
+            rounds = samples.shape[0]
+        M = np.zeros((3, 4)); inl = np.zeros(max(n, 1), np.int32)
+        ni = C.c_size_t(0); br = C.c_uint32(0)
+        check(self.lib.hulo_ransac_transform3d(self.h, _ptr(A), _ptr(B), n, thres, _ptr(samples), rounds, seed,
+                                               svd_ratio, int(bool(similarity)), _ptr(M), _ptr(inl), C.byref(ni),
+                                               C.byref(br)))
+        if ni.value == 0:
+            return np.array([]), np.asarray([], np.int64)
+        return M, inl[:ni.value].astype(np.int64)
+
     # -- multi GPU
     @staticmethod
     def comm_unique_id():
@@ -415,3 +432,32 @@ class LocalizeEngine:
         if self.h is not None:
             self.lib.hulo_engine_destroy(self.h)
             self.h = None
+
+
+# ---- the reference's Python entry points for the model-merge RANSAC, same names and signatures
+# (PyVisionLocalizeCommon/src/hulo_sfm/mergeSfM.py:344, 394; hulo_transform/ransacTransform.py:13),
+# on the GPU.  They use one lazily created context on device 0.
+_default_gpu = None
+
+
+def _gpu0():
+    global _default_gpu
+    if _default_gpu is None:
+        _default_gpu = HuloGpu(0)
+    return _default_gpu
+
+
+def ransacAffineTransform(A, B, thres, ransacRound, svdRatio=float("inf"), seed=1):
+    import sys
+    return _gpu0().ransac_transform3d(A, B, thres, ransacRound, min(svdRatio, sys.float_info.max), False, seed=seed)
+
+
+def ransacSimilarityTransform(A, B, thres, ransacRound, svdRatio=float("inf"), seed=1):
+    import sys
+    return _gpu0().ransac_transform3d(A, B, thres, ransacRound, min(svdRatio, sys.float_info.max), True, seed=seed)
+
+
+def ransacTransform(A, B, thres, ransacRound, svdRatio=float("inf"), seed=1):
+    """mergeSfM.ransacTransform: the similarity flavour when hulo_transform is importable (it is part
+    of the reference tree), which is what the drivers get."""
+    return ransacSimilarityTransform(A, B, thres, ransacRound, svdRatio, seed)

@@ -318,6 +318,23 @@ int hulo_ransac_transform3d(hulo_gpu *h, const double *A, const double *B, size_
                             int similarity, double *M, int32_t *inliers, size_t *n_inliers,
                             uint32_t *best_round);
 
+/* --------------------------------------- K5: nearest map views in bag-of-features space */
+
+typedef struct hulo_bow hulo_bow;
+
+/* hulo::selectViewByBoF (BoWCommon/src/BoFUtils.cpp:27-68; callers LocalizeEngine.cc:296-332,
+ * localization.cpp:386-412): the knn views whose BoF vector is nearest to the query's under L2.
+ * The reference rebuilds a FLANN KD-tree (4 trees, 64 checks, approximate) over the candidate views
+ * for every query; here the n x d matrix (row v = the vector of view v, what readMatBin returns
+ * from <view>.bow, transposed) is uploaded once and the search is exact.
+ *   subset / n_subset  candidate views (the viewList argument), NULL = all
+ *   knn                must be smaller than the number of candidates (CV_Assert at :30)
+ *   idx (knn)          view numbers by (squared distance, view number) ascending; dist may be NULL */
+int hulo_bow_create(hulo_gpu *h, const float *bof, size_t n, size_t d, hulo_bow **out);
+void hulo_bow_destroy(hulo_bow *b);
+int hulo_bow_knn(hulo_bow *b, const float *query, const uint32_t *subset, size_t n_subset, size_t knn,
+                 int32_t *idx, float *dist);
+
 /* ------------------------------------------------------------------ multi GPU */
 
 /* One process per GPU.  Rank 0 obtains an id with hulo_comm_unique_id and distributes its

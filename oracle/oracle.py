@@ -354,3 +354,18 @@ def ransac_transform3d(A, B, thres, samples, svd_ratio=float("inf"), similarity=
     else:
         M = np.linalg.lstsq(Bh[:, inliers].T, A[:, inliers].T, rcond=-1)[0].T
     return M, inliers
+
+
+# ---------------------------------------------------------------- BoF view selection
+def bow_knn(bof, query, knn, subset=None):
+    """Exact restatement of hulo::selectViewByBoF (BoWCommon/src/BoFUtils.cpp:27-68): the knn rows of
+    `bof` (n x d float32, one per view) nearest to `query` under squared L2, by (distance, index).
+    The reference searches a FLANN KD-tree (4 trees, 64 checks; OpenCV 3.0, not vendored), which is
+    approximate; this is the exact answer it approximates, pinned against cv2.BFMatcher(NORM_L2)
+    (tests/golden/make_golden_bow.py).  float32 accumulation in the order of the device kernel is
+    NOT reproduced: distances are float64 sums rounded to float32, ties at that rounding are by index."""
+    bof = np.asarray(bof, np.float32); query = np.asarray(query, np.float32).ravel()
+    idx = np.arange(bof.shape[0]) if subset is None else np.asarray(subset, np.int64)
+    d = ((bof[idx].astype(np.float64) - query.astype(np.float64)) ** 2).sum(axis=1)
+    order = np.lexsort((idx, d))[:knn]
+    return idx[order].astype(np.int32), d[order].astype(np.float32)

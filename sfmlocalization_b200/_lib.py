@@ -62,6 +62,9 @@ SIGNATURES = {
                                     C.POINTER(_sz)]),
     "hulo_ransac_transform3d": (C.c_int, [_vp, _vp, _vp, _sz, _f64, _vp, _sz, _u64, _f64, C.c_int, _vp, _vp,
                                           C.POINTER(_sz), _vp]),
+    "hulo_bow_create": (C.c_int, [_vp, _vp, _sz, _sz, _pp]),
+    "hulo_bow_destroy": (None, [_vp]),
+    "hulo_bow_knn": (C.c_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp]),
     "hulo_engine_create": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _pp]),
     "hulo_engine_destroy": (None, [_vp]),
     "hulo_engine_configure": (C.c_int, [_vp, _f32, C.c_int, C.c_int, C.c_int, _sz]),

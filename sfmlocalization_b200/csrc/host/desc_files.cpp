@@ -133,6 +133,66 @@ bool loadRegions(const Views &views, const std::string &dir, RegionsProvider &re
     return true;
 }
 
+bool readMatBin(const std::string &filename, int &rows, int &cols, std::vector<double> &values) {
+    values.clear();
+    rows = cols = 0;
+    std::ifstream f(filename, std::ios::binary);
+    if (!f.is_open()) return false;
+    int32_t r = 0, c = 0, type = 0;
+    f.read(reinterpret_cast<char *>(&r), 4);
+    if (!f || r == 0) return (bool)f;                       // an empty matrix stores only its row count (:66-68)
+    f.read(reinterpret_cast<char *>(&c), 4);
+    f.read(reinterpret_cast<char *>(&type), 4);
+    if (!f || r < 0 || c < 0 || (type >> 3) != 0) return false;   // one channel only
+    const size_t n = (size_t)r * (size_t)c;
+    values.resize(n);
+    auto load = [&](auto tag) {
+        typedef decltype(tag) T;
+        std::vector<T> buf(n);
+        f.read(reinterpret_cast<char *>(buf.data()), (std::streamsize)(n * sizeof(T)));
+        for (size_t k = 0; k < n; ++k) values[k] = (double)buf[k];
+        return (bool)f;
+    };
+    bool ok = false;
+    switch (type & 7) {
+        case 0: ok = load((uint8_t)0); break;
+        case 1: ok = load((int8_t)0); break;
+        case 2: ok = load((uint16_t)0); break;
+        case 3: ok = load((int16_t)0); break;
+        case 4: ok = load((int32_t)0); break;
+        case 5: ok = load((float)0); break;
+        case 6: ok = load((double)0); break;
+        default: ok = false;
+    }
+    if (!ok) { values.clear(); return false; }
+    rows = r; cols = c;
+    return true;
+}
+
+bool saveMatBin(const std::string &filename, int rows, int cols, int cv_type, const double *values) {
+    std::ofstream f(filename, std::ios::binary);
+    if (!f.is_open()) return false;
+    const int32_t r = rows, c = cols, t = cv_type;
+    f.write(reinterpret_cast<const char *>(&r), 4);
+    if (rows == 0) return (bool)f;
+    f.write(reinterpret_cast<const char *>(&c), 4);
+    f.write(reinterpret_cast<const char *>(&t), 4);
+    const size_t n = (size_t)rows * (size_t)cols;
+    for (size_t k = 0; k < n; ++k) {
+        if (cv_type == 5) { const float v = (float)values[k]; f.write(reinterpret_cast<const char *>(&v), 4); }
+        else if (cv_type == 6) { f.write(reinterpret_cast<const char *>(&values[k]), 8); }
+        else if (cv_type == 4) { const int32_t v = (int32_t)values[k]; f.write(reinterpret_cast<const char *>(&v), 4); }
+        else if (cv_type == 0) { const uint8_t v = (uint8_t)values[k]; f.write(reinterpret_cast<const char *>(&v), 1); }
+        else return false;
+    }
+    return (bool)f;
+}
+
+std::string bowPath(const std::string &dir, const std::string &img_path) {
+    std::string p = descPath(dir, img_path, true);
+    return p.substr(0, p.size() - 4) + "bow";
+}
+
 std::string descPath(const std::string &dir, const std::string &img_path, bool strip_extension) {
     std::string base = img_path;
     const std::size_t slash = base.find_last_of("/\\");

@@ -38,6 +38,13 @@ bool readFeatFile(const std::string &filename, FeatureLocations &feats);
 bool loadRegions(const Views &views, const std::string &dir, RegionsProvider &regions);
 std::string featPath(const std::string &dir, const std::string &img_path);
 
+// hulo::readMatBin / saveMatBin, FileUtils.cpp:44-75: int32 rows, cols, OpenCV type code, then the
+// raw elements (depths CV_8U 0, CV_32S 4, CV_32F 5, CV_64F 6; one channel).  Values come back as
+// doubles, row-major.  Used for the <view>.bow bag-of-features vectors (BoFUtils.cpp:38-42).
+bool readMatBin(const std::string &filename, int &rows, int &cols, std::vector<double> &values);
+bool saveMatBin(const std::string &filename, int rows, int cols, int cv_type, const double *values);
+std::string bowPath(const std::string &dir, const std::string &img_path);
+
 // stlplus::create_filespec(dir, basename_part(path), "desc")
 std::string descPath(const std::string &dir, const std::string &img_path, bool strip_extension);
 

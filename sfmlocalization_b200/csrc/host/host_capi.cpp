@@ -1,7 +1,9 @@
 // host_capi.cpp -- a small extern "C" surface over the C++ host layer so the CPU test-suite can
 // exercise the parts that need no GPU (file formats, pair lists, track propagation) through
 // ctypes.  Not part of the drop-in boundary (that is include/hulo_gpu.h).
+#include <cstdio>
 #include <cstring>
+#include <set>
 
 #include "desc_files.h"
 #include "match_utils_gpu.h"
@@ -159,6 +161,39 @@ long long hulo_host_read_feat(const char *path, double *xy, unsigned long long c
     if (!readFeatFile(path, f)) return -1;
     for (unsigned long long k = 0; k < f.size() && k < cap; ++k) { xy[2 * k] = f[k].first; xy[2 * k + 1] = f[k].second; }
     return (long long)f.size();
+}
+
+// .bow / readMatBin round trip: values as doubles, returns rows * cols or -1
+long long hulo_host_read_mat_bin(const char *path, int *rows, int *cols, double *values, unsigned long long cap) {
+    std::vector<double> v;
+    if (!readMatBin(path, *rows, *cols, v)) return -1;
+    for (unsigned long long k = 0; k < v.size() && k < cap; ++k) values[k] = v[k];
+    return (long long)v.size();
+}
+int hulo_host_save_mat_bin(const char *path, int rows, int cols, int cv_type, const double *values) {
+    return saveMatBin(path, rows, cols, cv_type, values) ? 0 : 1;
+}
+
+// hulo::selectViewByBoF over views 0..n_views-1 named frame%04d.jpg in match_dir (needs a GPU):
+// returns the number of selected views written to out (ascending, the std::set order) or -1
+long long hulo_host_select_view_by_bof(const char *match_dir, unsigned long long n_views, const float *bow,
+                                       unsigned long long dim, const unsigned long long *view_list,
+                                       unsigned long long n_list, int knn, unsigned long long *out) {
+    try {
+        Views views;
+        char name[64];
+        for (unsigned long long v = 0; v < n_views; ++v) {
+            snprintf(name, sizeof name, "frame%04llu.jpg", v);
+            views[(std::size_t)v] = View{(std::size_t)v, name};
+        }
+        std::set<std::size_t> list(view_list, view_list + n_list), sel;
+        selectViewByBoF(defaultSession(), std::vector<float>(bow, bow + dim), match_dir, list, views, knn, sel);
+        unsigned long long k = 0;
+        for (std::size_t v : sel) out[k++] = v;
+        return (long long)k;
+    } catch (const std::exception &) {
+        return -1;
+    }
 }
 
 }  // extern "C"

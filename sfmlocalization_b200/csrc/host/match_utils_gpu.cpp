@@ -15,10 +15,19 @@ void must(int status, const char *what) {
 }
 }  // namespace
 
+struct BowTable {
+    hulo_bow *index = nullptr;
+    std::map<std::size_t, uint32_t> row_of_view;
+    std::size_t dim = 0;
+};
+
 struct GpuSession::State {
     hulo_gpu *gpu = nullptr;
     std::map<std::string, std::shared_ptr<Table>> cache;
+    std::map<std::string, std::shared_ptr<BowTable>> bow_cache;
     ~State() {
+        for (auto &kv : bow_cache)
+            if (kv.second && kv.second->index) hulo_bow_destroy(kv.second->index);
         for (auto &kv : cache)
             if (kv.second && kv.second->db) hulo_db_free(kv.second->db);
         if (gpu) hulo_gpu_destroy(gpu);
@@ -29,11 +38,58 @@ GpuSession::GpuSession(int device) : st_(std::make_shared<State>()) {
     must(hulo_gpu_create(device, &st_->gpu), "hulo_gpu_create");
 }
 hulo_gpu *GpuSession::gpu() const { return st_->gpu; }
+std::map<std::string, std::shared_ptr<BowTable>> &GpuSession::bowCache() { return st_->bow_cache; }
 
 void GpuSession::clearCache() {
     for (auto &kv : st_->cache)
         if (kv.second && kv.second->db) hulo_db_free(kv.second->db);
     st_->cache.clear();
+    for (auto &kv : st_->bow_cache)
+        if (kv.second && kv.second->index) hulo_bow_destroy(kv.second->index);
+    st_->bow_cache.clear();
+}
+
+// ------------------------------------------------------------------ selectViewByBoF
+void selectViewByBoF(GpuSession &s, const std::vector<float> &bow, const std::string &matchDir,
+                     const std::set<std::size_t> &viewList, const Views &views, int knn,
+                     std::set<std::size_t> &selectedViewList) {
+    if (!(knn >= 0 && (std::size_t)knn < viewList.size()))
+        throw std::invalid_argument("hulo::selectViewByBoF: knn must be smaller than the number of views");   // :30
+    std::shared_ptr<BowTable> t;
+    auto &cache = s.bowCache();
+    auto it = cache.find(matchDir);
+    if (it != cache.end()) {
+        t = it->second;
+    } else {
+        t = std::make_shared<BowTable>();
+        std::vector<float> all;
+        std::vector<double> vec;
+        for (const auto &kv : views) {
+            int r = 0, c = 0;
+            if (!readMatBin(bowPath(matchDir, kv.second.s_Img_path), r, c, vec) || vec.empty()) continue;
+            if (t->dim == 0) t->dim = vec.size();
+            if (vec.size() != t->dim) throw std::runtime_error("hulo::selectViewByBoF: .bow vectors of different length");
+            t->row_of_view[kv.first] = (uint32_t)t->row_of_view.size();
+            for (double v : vec) all.push_back((float)v);                 // convertTo(CV_32FC1), :44-46
+        }
+        if (t->row_of_view.empty()) throw std::runtime_error("hulo::selectViewByBoF: no .bow file in " + matchDir);
+        must(hulo_bow_create(s.gpu(), all.data(), t->row_of_view.size(), t->dim, &t->index), "hulo_bow_create");
+        cache[matchDir] = t;
+    }
+    if (bow.size() != t->dim) throw std::invalid_argument("hulo::selectViewByBoF: query vector of the wrong length");
+    std::vector<uint32_t> subset;
+    std::vector<std::size_t> view_of;                                      // position in viewList order -> view id
+    for (std::size_t v : viewList) {
+        subset.push_back(t->row_of_view.at(v));                            // .at(): every listed view must have a vector
+        view_of.push_back(v);
+    }
+    std::map<uint32_t, std::size_t> view_of_row;
+    for (std::size_t k = 0; k < subset.size(); ++k) view_of_row[subset[k]] = view_of[k];
+    std::vector<int32_t> idx((std::size_t)std::max(knn, 1));
+    must(hulo_bow_knn(t->index, bow.data(), subset.data(), subset.size(), (std::size_t)knn, idx.data(), nullptr),
+         "hulo_bow_knn");
+    selectedViewList.clear();
+    for (int k = 0; k < knn; ++k) selectedViewList.insert(view_of_row.at((uint32_t)idx[k]));
 }
 
 std::shared_ptr<GpuSession::Table> GpuSession::table(const Views &views, const std::string &sMatchesDir,

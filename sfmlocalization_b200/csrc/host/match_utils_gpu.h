@@ -7,6 +7,7 @@
 // because its matcher cannot fail).
 #pragma once
 #include <memory>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -36,6 +37,7 @@ public:
                                  const std::vector<std::size_t> &view_ids);
     void clearCache();
     struct State;
+    std::map<std::string, std::shared_ptr<struct BowTable>> &bowCache();
 private:
     std::shared_ptr<State> st_;
 };
@@ -74,6 +76,15 @@ void geometricMatch(GpuSession &s, const Views &views, const RegionsProvider &re
 // sampler seed of the filter (pair (I, J) draws from a stream derived from it and from I, J, so
 // the result of a pair does not depend on which other pairs are filtered with it)
 extern uint64_t g_geometricSeed;
+
+// hulo::selectViewByBoF, BoWCommon/src/BoFUtils.cpp:27-68: the knn views of viewList whose
+// bag-of-features vector (<matchDir>/<basename>.bow, readMatBin) is nearest to the query's `bow`
+// under L2.  The vectors of all views are read once per matchDir and kept on the device; the search
+// is exact where the reference's per-query FLANN KD-tree (4 trees, 64 checks) is approximate.
+// Throws std::invalid_argument unless knn < viewList.size() (CV_Assert at :30).
+void selectViewByBoF(GpuSession &s, const std::vector<float> &bow, const std::string &matchDir,
+                     const std::set<std::size_t> &viewList, const Views &views, int knn,
+                     std::set<std::size_t> &selectedViewList);
 
 // the same three against an explicit session (several GPUs, tests)
 void matchAKAZE(GpuSession &s, const Views &views, const std::string &sMatchesDir, const std::vector<Pair> &pairs,

@@ -358,6 +358,32 @@ class HuloGpu:
         return v.value
 
 
+class BowIndex:
+    """hulo_bow_*: the BoF vectors of the map views, resident on the device (hulo::selectViewByBoF)."""
+
+    def __init__(self, gpu, bof):
+        bof = np.ascontiguousarray(bof, np.float32)
+        self.lib = gpu.lib
+        h = C.c_void_p()
+        check(self.lib.hulo_bow_create(gpu.h, _ptr(bof), bof.shape[0], bof.shape[1], C.byref(h)))
+        self.h = h
+
+    def knn(self, query, knn, subset=None):
+        query = np.ascontiguousarray(query, np.float32).ravel()
+        ns = 0
+        if subset is not None:
+            subset = np.ascontiguousarray(subset, np.uint32)
+            ns = len(subset)
+        idx = np.zeros(max(knn, 1), np.int32); dist = np.zeros(max(knn, 1), np.float32)
+        check(self.lib.hulo_bow_knn(self.h, _ptr(query), _ptr(subset), ns, knn, _ptr(idx), _ptr(dist)))
+        return idx[:knn].copy(), dist[:knn].copy()
+
+    def close(self):
+        if self.h is not None:
+            self.lib.hulo_bow_destroy(self.h)
+            self.h = None
+
+
 class LocalizeEngine:
     """hulo_engine_*: the hot path of LocalizeEngine::localize (LocalizeEngine.cc:423-602) with
     the map resident on the device."""

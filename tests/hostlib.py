@@ -17,7 +17,8 @@ def lib():
         C.CDLL(os.path.join(PKG, "libhulo_gpu.so"), mode=C.RTLD_GLOBAL)
         _lib = C.CDLL(os.path.join(PKG, "libhulo_host.so"))
         for name in ("hulo_host_read_desc", "hulo_host_matches_roundtrip", "hulo_host_views_from_sfm_data",
-                     "hulo_host_load_sfm_data", "hulo_host_read_feat"):
+                     "hulo_host_load_sfm_data", "hulo_host_read_feat", "hulo_host_read_mat_bin",
+                     "hulo_host_select_view_by_bof"):
             getattr(_lib, name).restype = C.c_longlong
         for name in ("hulo_host_all_pairs", "hulo_host_video_pairs", "hulo_host_remove_dup_pairs",
                      "hulo_host_partition_pairs", "hulo_host_propagate_tracks"):
@@ -178,3 +179,29 @@ def read_feat(path):
     out = np.zeros((max(n, 1), 2))
     lib().hulo_host_read_feat(path.encode(), _p(out), C.c_ulonglong(n))
     return out[:n]
+
+
+def save_mat_bin(path, mat, cv_type):
+    """hulo::saveMatBin (FileUtils.cpp:44-58): cv_type 0 = CV_8U, 4 = CV_32S, 5 = CV_32F, 6 = CV_64F."""
+    m = np.ascontiguousarray(mat, np.float64)
+    rows, cols = (m.shape if m.ndim == 2 else (m.shape[0], 1)) if m.size else (0, 0)
+    return lib().hulo_host_save_mat_bin(path.encode(), rows, cols, cv_type, _p(m))
+
+
+def read_mat_bin(path):
+    r = C.c_int(0); c = C.c_int(0)
+    n = lib().hulo_host_read_mat_bin(path.encode(), C.byref(r), C.byref(c), None, C.c_ulonglong(0))
+    if n < 0:
+        return None
+    out = np.zeros(max(n, 1))
+    lib().hulo_host_read_mat_bin(path.encode(), C.byref(r), C.byref(c), _p(out), C.c_ulonglong(n))
+    return out[:n].reshape(r.value, c.value)
+
+
+def select_view_by_bof(match_dir, n_views, bow, view_list, knn):
+    bow = np.ascontiguousarray(bow, np.float32)
+    vl = np.ascontiguousarray(view_list, np.uint64)
+    out = np.zeros(max(knn, 1), np.uint64)
+    n = lib().hulo_host_select_view_by_bof(match_dir.encode(), C.c_ulonglong(n_views), _p(bow), C.c_ulonglong(len(bow)),
+                                           _p(vl), C.c_ulonglong(len(vl)), knn, _p(out))
+    return None if n < 0 else out[:n].astype(np.int64)

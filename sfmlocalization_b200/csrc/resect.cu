@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <vector>
 
@@ -126,6 +127,35 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
         if (out_k) out_k[h] = b.k;
         if (out_errk) out_errk[h] = b.k >= 1 ? s_e[b.k - 1] : INFINITY;
         if (out_ninl) out_ninl[h] = c;
+    }
+}
+
+// First minimum of the H scores (strict <: the earliest hypothesis wins ties, like the sequential
+// update rule) and its model, gathered into one small record so a batch costs one D2H copy:
+// out = {nfa, (double)index, model[12]}; index = -1 when every score is +inf / NaN.
+__global__ void __launch_bounds__(256) argmin_kernel(const double *__restrict__ nfa, uint32_t H,
+                                                     const double *__restrict__ models, double *__restrict__ out) {
+    __shared__ double s_v[8];
+    __shared__ uint32_t s_i[8];
+    double v = INFINITY;
+    uint32_t idx = 0xFFFFFFFFu;
+    for (uint32_t h = threadIdx.x; h < H; h += 256) {
+        const double x = nfa[h];
+        if (x < v) { v = x; idx = h; }          // ascending h per thread: keeps the earliest
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = v; s_i[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (s_v[w] < v || (s_v[w] == v && s_i[w] < idx)) { v = s_v[w]; idx = s_i[w]; }
+        out[0] = v;
+        out[1] = idx == 0xFFFFFFFFu ? -1.0 : (double)idx;
+        for (int k = 0; k < 12; ++k) out[2 + k] = idx == 0xFFFFFFFFu ? 0.0 : models[(size_t)idx * 12 + k];
     }
 }
 
@@ -335,12 +365,25 @@ void normalize_points(const double *x2d, size_t N, const double *K, std::vector<
 
 // log10 C(N,k) for k = 0..N and log10 C(n,3) for n = 0..N, double sums stored as float with the
 // same summation order as the sequential definition (prefix sums reproduce it exactly).
+// log10 of the integers, grown on demand and kept per thread: the log-binomial tables below are
+// rebuilt for every problem size, and the calls to log10 were most of their cost
+static const double *log10_int(size_t n_max) {
+    static thread_local std::vector<double> t(2, 0.0);      // t[0] unused, t[1] = 0
+    if (t.size() <= n_max) {
+        const size_t old = t.size();
+        t.resize(n_max + 1 + n_max / 2);
+        for (size_t i = old; i < t.size(); ++i) t[i] = log10((double)i);
+    }
+    return t.data();
+}
+
 void make_logcombi(size_t N, std::vector<float> &logc_n, std::vector<float> &logc_k) {
     logc_n.assign(N + 1, 0.0f);
     logc_k.assign(N + 1, 0.0f);
+    const double *lg = log10_int(N + 1);
     std::vector<double> prefix(N / 2 + 2, 0.0);   // prefix[j] = sum_{i=1..j} log10(N-i+1) - log10(i)
-    for (size_t j = 1; j < prefix.size(); ++j)
-        prefix[j] = prefix[j - 1] + (log10((double)(N - j + 1)) - log10((double)j));
+    for (size_t j = 1; j < prefix.size() && j <= N; ++j)
+        prefix[j] = prefix[j - 1] + (lg[N - j + 1] - lg[j]);
     for (size_t k = 0; k <= N; ++k) {
         if (k >= N || k == 0) { logc_n[k] = 0.0f; continue; }
         const size_t kk = (N - k < k) ? N - k : k;
@@ -351,7 +394,7 @@ void make_logcombi(size_t N, std::vector<float> &logc_n, std::vector<float> &log
         if (k >= n) { logc_k[n] = 0.0f; continue; }
         if (n - k < k) k = n - k;
         double r = 0.0;
-        for (size_t i = 1; i <= k; ++i) r += log10((double)(n - i + 1)) - log10((double)i);
+        for (size_t i = 1; i <= k; ++i) r += lg[n - i + 1] - lg[i];
         logc_k[n] = (float)r;
     }
 }
@@ -368,11 +411,12 @@ struct Problem {
     double *d_x2dn = nullptr, *d_X3d = nullptr;
     float *d_logc_n = nullptr, *d_logc_k = nullptr;
     double loge0 = 0, logalpha0 = 0;
+    std::vector<float> lcn, lck;       // the same tables on the host (final fp64 rescoring)
 };
 
 // scratch0: x2dn | X3d | logc_n | logc_k   (problem);  scratch1: models; scratch2: outputs; scratch3: triplets
 int stage_problem(hulo_gpu *h, const std::vector<double> &x2dn, const double *X3d, size_t N, Problem &pb) {
-    std::vector<float> lcn, lck;
+    std::vector<float> &lcn = pb.lcn, &lck = pb.lck;
     make_logcombi(N, lcn, lck);
     const size_t bytes = N * 5 * sizeof(double) + 2 * (N + 1) * sizeof(float) + 64;
     HULO_CUDA(h->scratch0.reserve(bytes));
@@ -397,7 +441,7 @@ int stage_problem(hulo_gpu *h, const std::vector<double> &x2dn, const double *X3
 struct ScoreOut { double *nfa; int32_t *k; float *errk; int32_t *ninl; };
 
 int launch_score(hulo_gpu *h, const Problem &pb, const double *d_models, size_t H, float thr2, ScoreOut &o) {
-    const size_t bytes = H * (sizeof(double) + 2 * sizeof(int32_t) + sizeof(float)) + 64;
+    const size_t bytes = H * (sizeof(double) + 2 * sizeof(int32_t) + sizeof(float)) + 64 + 16 * sizeof(double);
     HULO_CUDA(h->scratch2.reserve(bytes));
     o.nfa = h->scratch2.as<double>();
     o.k = reinterpret_cast<int32_t *>(o.nfa + H);
@@ -569,7 +613,6 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
     double best_nfa = INFINITY;
     double best_model[12] = {0};
     std::vector<uint32_t> tri;
-    std::vector<double> h_nfa;
     std::vector<double> h_model(12);
 
     auto run_batch = [&](size_t T) -> int {
@@ -591,23 +634,25 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
         ScoreOut o;
         int rc2 = launch_score(h, pb, d_models, 4 * T, -1.0f, o);
         if (rc2 != HULO_OK) return rc2;
-        h_nfa.resize(4 * T);
-        HULO_CUDA(cudaMemcpyAsync(h_nfa.data(), o.nfa, 4 * T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        // first minimum of the batch and its model in one record, one copy, one synchronisation
+        double rec[14];
+        double *d_rec = reinterpret_cast<double *>(o.ninl + 4 * T + 2);
+        d_rec = reinterpret_cast<double *>((reinterpret_cast<uintptr_t>(d_rec) + 7) & ~(uintptr_t)7);
+        argmin_kernel<<<1, 256, 0, h->stream>>>(o.nfa, (uint32_t)(4 * T), d_models, d_rec);
+        HULO_CUDA(cudaGetLastError());
+        h->launches++;
+        HULO_CUDA(cudaMemcpyAsync(rec, d_rec, sizeof rec, cudaMemcpyDeviceToHost, h->stream));
         HULO_CUDA(cudaStreamSynchronize(h->stream));
         // sequential update rule: strict <, so the earliest hypothesis wins ties
-        size_t arg = (size_t)-1;
-        for (size_t i = 0; i < 4 * T; ++i)
-            if (h_nfa[i] < best_nfa) { best_nfa = h_nfa[i]; arg = i; }
-        if (arg != (size_t)-1) {
-            HULO_CUDA(cudaMemcpyAsync(best_model, d_models + 12 * arg, 12 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            HULO_CUDA(cudaStreamSynchronize(h->stream));
+        if (rec[1] >= 0.0 && rec[0] < best_nfa) {
+            best_nfa = rec[0];
+            memcpy(best_model, rec + 2, 12 * sizeof(double));
         }
         return HULO_OK;
     };
 
     // Final scoring of a model in fp64 on the host: residuals, (residual, index) order, NFA.
-    std::vector<float> lcn, lck;
-    make_logcombi(N, lcn, lck);
+    const std::vector<float> &lcn = pb.lcn, &lck = pb.lck;
     struct EI { double e; size_t i; };
     std::vector<EI> ei(N);
     size_t best_k = 0;

@@ -512,13 +512,41 @@ cudaError_t knn2_launch(const KnnParams &p, const KnnConfig &cfg, int grid_ctas,
     return cudaErrorInvalidValue;
 }
 
-cudaError_t knn2_kernel_info(const KnnConfig &cfg, int *regs, int *max_ctas_per_sm, size_t *smem) {
+static cudaError_t knn2_kernel_info_query(const KnnConfig &cfg, int *regs, int *max_ctas_per_sm, size_t *smem) {
 #define X(T, Q, C, O) \
     if (cfg.threads == T && cfg.qpt == Q && cfg.csa == C && cfg.opt == O) \
         return info_variant<T, Q, C, O>(regs, max_ctas_per_sm, smem);
     HULO_KNN_VARIANTS(X)
 #undef X
     return cudaErrorInvalidValue;
+}
+
+// The attributes of a variant do not change: asked once per (thread, device, variant) -- the
+// per-query entry points call this on every request.
+cudaError_t knn2_kernel_info(const KnnConfig &cfg, int *regs, int *max_ctas_per_sm, size_t *smem) {
+    struct Entry { KnnConfig cfg; int device, regs, ctas; size_t smem; };
+    static thread_local Entry cache[8];
+    static thread_local int n_cached = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (int k = 0; k < n_cached; ++k) {
+        const Entry &e = cache[k];
+        if (e.device == dev && e.cfg.threads == cfg.threads && e.cfg.qpt == cfg.qpt && e.cfg.csa == cfg.csa &&
+            e.cfg.opt == cfg.opt) {
+            if (regs) *regs = e.regs;
+            if (max_ctas_per_sm) *max_ctas_per_sm = e.ctas;
+            if (smem) *smem = e.smem;
+            return cudaSuccess;
+        }
+    }
+    Entry e{cfg, dev, 0, 0, 0};
+    const cudaError_t rc = knn2_kernel_info_query(cfg, &e.regs, &e.ctas, &e.smem);
+    if (rc != cudaSuccess) return rc;
+    if (n_cached < 8) cache[n_cached++] = e;
+    if (regs) *regs = e.regs;
+    if (max_ctas_per_sm) *max_ctas_per_sm = e.ctas;
+    if (smem) *smem = e.smem;
+    return cudaSuccess;
 }
 
 cudaError_t knn2_fold_rows_launch(uint4 *rows, size_t n, cudaStream_t stream) {

@@ -127,3 +127,16 @@ def test_table_round_trip_through_the_device_layout(gpu, stride):
         assert len(db) == 640 and np.array_equal(db.download(), want2)
     finally:
         db.free()
+
+
+def test_full_512_bit_rows(gpu, orc):
+    """Rows whose last bytes are not zero (every bit of every word live): exercises all six folded
+    adder sums of the device layout, including the one over words 9..15."""
+    rng = np.random.default_rng(99)
+    A = rng.integers(0, 256, size=(777, 64), dtype=np.uint8)
+    B = rng.integers(0, 256, size=(5003, 64), dtype=np.uint8)
+    B[100] = A[5]; B[4000] = A[5]                     # an exact duplicate pair: distance 0 twice, lowest index first
+    idx, dist = gpu.knn2_host(A, B)
+    ri, rd = orc.knn2(A, B)
+    assert np.array_equal(idx, ri) and np.array_equal(dist, rd)
+    assert idx[5].tolist() == [100, 4000] and dist[5].tolist() == [0, 0]

@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""The matching stages of ExtFeatAndMatch (computeFeaturesAndMatches.cpp:150-246) end to end on one
+GPU, through the C-ABI, on a synthetic collection WITH geometry: V views of one scene (each with its
+own pose, F features of which 60 % observe landmarks from a sliding window), all V(V-1)/2 pairs:
+  putative matching (ratio 0.6, one-to-one)  ->  drop pairs below minMatch 60  ->
+  F-matrix AC-RANSAC (ransacRound 500, 4 px: ReconstructParam.py:76)  ->  guided matching (-gm, the
+  reconstruction default, ReconstructParam.py:70-71).
+Prints one JSON line with the wall time of every stage."""
+import json
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, ".")
+from sfmlocalization_b200 import synth  # noqa: E402
+from sfmlocalization_b200.gpu import HuloGpu  # noqa: E402
+
+
+def main():
+    V = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+    F = int(sys.argv[2]) if len(sys.argv) > 2 else 5000
+    t0 = time.perf_counter()
+    sc = synth.localization_scene(V, F, 12 * F, 10, 77, track_frac=0.6, window=4 * F)
+    gen = time.perf_counter() - t0
+    off = sc["seg_offsets"]
+    pairs = np.array([(a, b) for a in range(V) for b in range(a + 1, V)], np.uint32)
+    w, h = synth.IMAGE_WH
+    with HuloGpu(0) as g:
+        db = g.db(sc["rows"], off)
+        g.match_pairs(db, pairs[:64], 0.6)
+        t0 = time.perf_counter()
+        po, pi, pj = g.match_pairs(db, pairs, 0.6, cap=len(pairs) * F // 4)
+        t_put = time.perf_counter() - t0
+        # pairs with at least minMatch putative matches go on (computeFeaturesAndMatches.cpp:222-232)
+        t0 = time.perf_counter()
+        cnt = np.diff(po.astype(np.int64))
+        keep = np.flatnonzero(cnt >= 60)
+        sel = np.concatenate([np.arange(po[p], po[p + 1]) for p in keep]).astype(np.int64) if len(keep) else np.zeros(0, np.int64)
+        pair_of = np.repeat(keep, cnt[keep])
+        xI = sc["map_xy"][off[pairs[pair_of, 0]].astype(np.int64) + pi[sel]]
+        xJ = sc["map_xy"][off[pairs[pair_of, 1]].astype(np.int64) + pj[sel]]
+        goff = np.zeros(len(keep) + 1, np.uint64); goff[1:] = np.cumsum(cnt[keep])
+        sizes = np.tile(np.array([w, h, w, h], np.int32), (len(keep), 1))
+        t_prep = time.perf_counter() - t0
+        g.geometric_filter(xI[:int(goff[1])], xJ[:int(goff[1])], goff[:2], sizes[:1], 4.0, 500, 1)
+        t0 = time.perf_counter()
+        r = g.geometric_filter(xI, xJ, goff, sizes, 4.0, 500, 1)
+        t_geo = time.perf_counter() - t0
+        valid = np.flatnonzero(r["valid"])
+        gp = pairs[keep[valid]]
+        g.guided_match(db, sc["map_xy"], gp[:4], r["F"][valid][:4], r["error_max"][valid][:4] ** 2)
+        t0 = time.perf_counter()
+        go, gi, gj = g.guided_match(db, sc["map_xy"], gp, r["F"][valid], r["error_max"][valid] ** 2, cap=len(gp) * F // 2)
+        t_gm = time.perf_counter() - t0
+        db.free()
+    print(json.dumps({"workload": "%d views x %d features, %d pairs" % (V, F, len(pairs)), "putative_s": t_put,
+                      "putative_gdist_per_s": len(pairs) * F * F / t_put / 1e9, "putative_matches": int(len(pi)),
+                      "pairs_with_60_matches": int(len(keep)), "host_gather_s": t_prep,
+                      "geometric_filter_s": t_geo, "pairs_valid": int(len(valid)),
+                      "inliers": int(r["n_inliers"].sum()), "guided_matching_s": t_gm, "guided_matches": int(len(gi)),
+                      "total_gpu_stages_s": t_put + t_geo + t_gm, "scene_generation_s": gen}), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,7 +24,6 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
-#include <unordered_set>
 #include <vector>
 
 #include "context.cuh"
@@ -93,17 +92,19 @@ __global__ void __launch_bounds__(kGuidedThreads) guided_kernel(
                 s_xyd[e] = p;
                 s_xyf[e] = make_float2((float)p.x, (float)p.y);
             }
+            // pad the last group of 32 with NaN positions (they fail every gate), so the gate loop
+            // below always runs 32 rows with compile-time bit positions
+            for (uint32_t e = nj + tid; e < ((nj + 31u) & ~31u); e += kGuidedThreads) s_xyf[e] = make_float2(NAN, NAN);
             for (uint32_t e = tid; e < nj * 4; e += kGuidedThreads)
                 s_desc[e] = __ldg(rows + (size_t)(item.j_row0 + j0) * 4 + e);
             __syncthreads();
             for (uint32_t g0 = 0; g0 < nj; g0 += 32) {
-                const uint32_t ng = min(32u, nj - g0);
                 uint32_t mask = 0;
-#pragma unroll 8
-                for (uint32_t jj = 0; jj < ng; ++jj) {
+#pragma unroll
+                for (uint32_t jj = 0; jj < 32; ++jj) {
                     const float2 p = s_xyf[g0 + jj];
                     const float t = fmaf(l0f, p.x, fmaf(l1f, p.y, l2f));
-                    mask |= (fabsf(t) < gate ? 1u : 0u) << jj;
+                    if (fabsf(t) < gate) mask |= 1u << jj;
                 }
                 while (mask) {
                     const uint32_t jj = (uint32_t)__ffs(mask) - 1u;
@@ -146,19 +147,37 @@ __global__ void __launch_bounds__(kGuidedThreads) guided_kernel(
     }
 }
 
-struct Key4 {
-    float a, b, c, d;
-    bool operator==(const Key4 &o) const { return a == o.a && b == o.b && c == o.c && d == o.d; }
-};
-struct Key4Hash {
-    size_t operator()(const Key4 &k) const {
-        uint32_t w[4];
-        memcpy(w, &k, sizeof w);
-        uint64_t h = 1469598103934665603ull;
-        for (int i = 0; i < 4; ++i) h = (h ^ w[i]) * 1099511628211ull;
-        return (size_t)h;
+// Position groups of one image: rep[f] = the first feature of the image at the same float
+// position as feature f, member[f] = 1 when that position is shared by several features.  A
+// duplicate position 4-tuple needs two matches whose I-features share a position, so images without
+// shared positions (the normal case) skip the duplicate filter altogether.  Open addressing over the
+// 64 bits of (float x, float y).
+void position_groups(const double *xy, size_t n, int32_t *rep, uint8_t *member) {
+    size_t cap = 16;
+    while (cap < 2 * n + 2) cap <<= 1;
+    std::vector<int32_t> slot(cap, -1);
+    std::vector<uint64_t> keys(n);
+    for (size_t f = 0; f < n; ++f) {
+        const float x = (float)xy[2 * f], y = (float)xy[2 * f + 1];
+        uint32_t a, b;
+        memcpy(&a, &x, 4); memcpy(&b, &y, 4);
+        if (x == 0.0f) a = 0;                       // +0 and -0 compare equal as floats
+        if (y == 0.0f) b = 0;
+        const uint64_t k = ((uint64_t)a << 32) | b;
+        keys[f] = k;
+        size_t h = (size_t)((k * 0x9E3779B97F4A7C15ULL) >> 20) & (cap - 1);
+        while (slot[h] >= 0 && keys[(size_t)slot[h]] != k) h = (h + 1) & (cap - 1);
+        if (slot[h] < 0 || x != x || y != y) {      // NaN never equals anything
+            if (slot[h] < 0) slot[h] = (int32_t)f;
+            rep[f] = (int32_t)f;
+            member[f] = 0;
+        } else {
+            rep[f] = slot[h];
+            member[f] = 1;
+            member[(size_t)slot[h]] = 1;
+        }
     }
-};
+}
 
 }  // namespace
 }  // namespace hulo
@@ -194,6 +213,10 @@ int hulo_guided_match(hulo_gpu *h, const hulo_db *db, const double *xy, const ui
     std::vector<GuidedItem> items;
     std::vector<uint64_t> row_off, h_seg_out;
     std::vector<uint32_t> hi, hj;
+    // position groups per image, built the first time an image appears in a pair
+    std::vector<int32_t> rep(dedup ? std::max<size_t>(db->n, 1) : 1);
+    std::vector<uint8_t> member(dedup ? std::max<size_t>(db->n, 1) : 1, 0), grouped(n_seg, 0);
+    std::vector<uint64_t> seen;
     size_t p0 = 0;
     while (p0 < n_pairs) {
         items.clear();
@@ -264,12 +287,22 @@ int hulo_guided_match(hulo_gpu *h, const hulo_db *db, const double *xy, const ui
             // (IndMatchDecorator::getDeduplicated), first occurrence kept, order preserved
             for (size_t p = 0; p < bp; ++p) {
                 const uint32_t I = pairs[2 * (p0 + p)], J = pairs[2 * (p0 + p) + 1];
-                const double *xI = xy + 2 * db->seg[I], *xJ = xy + 2 * db->seg[J];
-                std::unordered_set<Key4, Key4Hash> seen;
+                if (dedup) {
+                    for (uint32_t S : {I, J}) {
+                        if (grouped[S]) continue;
+                        const size_t a = (size_t)db->seg[S], nS = (size_t)(db->seg[S + 1] - db->seg[S]);
+                        position_groups(xy + 2 * a, nS, rep.data() + a, member.data() + a);
+                        grouped[S] = 1;
+                    }
+                }
+                const int32_t *repI = dedup ? rep.data() + db->seg[I] : nullptr, *repJ = dedup ? rep.data() + db->seg[J] : nullptr;
+                const uint8_t *memI = dedup ? member.data() + db->seg[I] : nullptr;
+                seen.clear();
                 for (uint64_t m = h_seg_out[1 + p]; m < h_seg_out[2 + p]; ++m) {
-                    if (dedup) {
-                        const Key4 k{(float)xI[2 * hi[m]], (float)xI[2 * hi[m] + 1], (float)xJ[2 * hj[m]], (float)xJ[2 * hj[m] + 1]};
-                        if (!seen.insert(k).second) continue;
+                    if (dedup && memI[hi[m]]) {
+                        const uint64_t k = ((uint64_t)(uint32_t)repI[hi[m]] << 32) | (uint32_t)repJ[hj[m]];
+                        if (std::find(seen.begin(), seen.end(), k) != seen.end()) continue;
+                        seen.push_back(k);
                     }
                     if (total_out < cap) {
                         if (out_i == nullptr || out_j == nullptr) { set_error("hulo_guided_match: null output"); return HULO_ERR_ARG; }

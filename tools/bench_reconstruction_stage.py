@@ -53,12 +53,15 @@ def main():
         t0 = time.perf_counter()
         go, gi, gj = g.guided_match(db, sc["map_xy"], gp, r["F"][valid], r["error_max"][valid] ** 2, cap=len(gp) * F // 2)
         t_gm = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        g.guided_match(db, sc["map_xy"], gp, r["F"][valid], r["error_max"][valid] ** 2, dedup=False, cap=len(gp) * F // 2)
+        t_gm_nodedup = time.perf_counter() - t0
         db.free()
     print(json.dumps({"workload": "%d views x %d features, %d pairs" % (V, F, len(pairs)), "putative_s": t_put,
                       "putative_gdist_per_s": len(pairs) * F * F / t_put / 1e9, "putative_matches": int(len(pi)),
                       "pairs_with_60_matches": int(len(keep)), "host_gather_s": t_prep,
                       "geometric_filter_s": t_geo, "pairs_valid": int(len(valid)),
-                      "inliers": int(r["n_inliers"].sum()), "guided_matching_s": t_gm, "guided_matches": int(len(gi)),
+                      "inliers": int(r["n_inliers"].sum()), "guided_matching_s": t_gm, "guided_matching_without_position_dedup_s": t_gm_nodedup, "guided_matches": int(len(gi)),
                       "total_gpu_stages_s": t_put + t_geo + t_gm, "scene_generation_s": gen}), flush=True)
 
 

@@ -28,7 +28,7 @@ def main():
     w, h = synth.IMAGE_WH
     with HuloGpu(0) as g:
         db = g.db(sc["rows"], off)
-        g.match_pairs(db, pairs[:64], 0.6)
+        g.match_pairs(db, pairs, 0.6, cap=len(pairs) * F // 4)        # warm-up at full size
         t0 = time.perf_counter()
         po, pi, pj = g.match_pairs(db, pairs, 0.6, cap=len(pairs) * F // 4)
         t_put = time.perf_counter() - t0
@@ -43,13 +43,13 @@ def main():
         goff = np.zeros(len(keep) + 1, np.uint64); goff[1:] = np.cumsum(cnt[keep])
         sizes = np.tile(np.array([w, h, w, h], np.int32), (len(keep), 1))
         t_prep = time.perf_counter() - t0
-        g.geometric_filter(xI[:int(goff[1])], xJ[:int(goff[1])], goff[:2], sizes[:1], 4.0, 500, 1)
+        g.geometric_filter(xI, xJ, goff, sizes, 4.0, 500, 2)          # warm-up at full size: scratch grows here
         t0 = time.perf_counter()
         r = g.geometric_filter(xI, xJ, goff, sizes, 4.0, 500, 1)
         t_geo = time.perf_counter() - t0
         valid = np.flatnonzero(r["valid"])
         gp = pairs[keep[valid]]
-        g.guided_match(db, sc["map_xy"], gp[:4], r["F"][valid][:4], r["error_max"][valid][:4] ** 2)
+        g.guided_match(db, sc["map_xy"], gp, r["F"][valid], r["error_max"][valid] ** 2, cap=len(gp) * F // 2)   # warm-up
         t0 = time.perf_counter()
         go, gi, gj = g.guided_match(db, sc["map_xy"], gp, r["F"][valid], r["error_max"][valid] ** 2, cap=len(gp) * F // 2)
         t_gm = time.perf_counter() - t0

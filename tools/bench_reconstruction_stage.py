@@ -57,7 +57,25 @@ def main():
         g.guided_match(db, sc["map_xy"], gp, r["F"][valid], r["error_max"][valid] ** 2, dedup=False, cap=len(gp) * F // 2)
         t_gm_nodedup = time.perf_counter() - t0
         db.free()
-    print(json.dumps({"workload": "%d views x %d features, %d pairs" % (V, F, len(pairs)), "putative_s": t_put,
+    # the same three stages on the CPU port (test oracle, OpenMP) for a few pairs, extrapolated
+    from oracle import oracle as orc
+    orc.build()
+    n_cpu = 6
+    tp = tg = tm = 0.0
+    for (I, J) in pairs[:n_cpu]:
+        a = sc["rows"][int(off[I]):int(off[I + 1])]; b = sc["rows"][int(off[J]):int(off[J + 1])]
+        xa = sc["map_xy"][int(off[I]):int(off[I + 1])]; xb = sc["map_xy"][int(off[J]):int(off[J + 1])]
+        t0 = time.perf_counter(); oi, oj = orc.match_pair(a, b, 0.6); tp += time.perf_counter() - t0
+        if len(oi) < 60:
+            continue
+        t0 = time.perf_counter(); rr = orc.fmatrix_acransac(xa[oi], xb[oj], (w, h), (w, h), 4.0, 500, 1); tg += time.perf_counter() - t0
+        if rr["ok"]:
+            t0 = time.perf_counter(); orc.guided_match(rr["F"], xa, a, xb, b, rr["error_max"] ** 2, 0.36); tm += time.perf_counter() - t0
+    scale = len(pairs) / n_cpu
+    cpu = {"cores": orc.num_threads(), "kind": "port", "sample": "%d pairs, extrapolated to %d" % (n_cpu, len(pairs)),
+           "putative_s": tp * scale, "geometric_filter_s": tg * scale, "guided_matching_s": tm * scale,
+           "total_s": (tp + tg + tm) * scale}
+    print(json.dumps({"cpu_baseline": cpu, "workload": "%d views x %d features, %d pairs" % (V, F, len(pairs)), "putative_s": t_put,
                       "putative_gdist_per_s": len(pairs) * F * F / t_put / 1e9, "putative_matches": int(len(pi)),
                       "pairs_with_60_matches": int(len(keep)), "host_gather_s": t_prep,
                       "geometric_filter_s": t_geo, "pairs_valid": int(len(valid)),

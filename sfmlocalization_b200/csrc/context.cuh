@@ -113,7 +113,7 @@ struct hulo_gpu {
     size_t score_smem_configured = 0;   // dynamic smem opt-in already set for K2 on this device
     hulo::DevBuf lfact;        // K3: log10(n!) table
     size_t lfact_n = 0;
-    size_t geo_smem_configured = 0, geo_warp_smem_configured = 0;
+    size_t geo_smem_configured = 0;
 
     // NCCL (loaded lazily)
     void *nccl_comm = nullptr;

@@ -6,14 +6,16 @@
 //
 //   hulo_localize <query .desc file or folder> <sfmDir> <matchDir> <outDir>
 //                 [-f=0.6] [-r=200] [-g=4.0] [-x= -y= -z= -d=-1] [-i=1] [--width=W --height=H]
-//                 [--device=D] [--seed=S]
+//                 [--device=D] [--seed=S] [--rank=R --world=W]
 //
 // The reference takes image files and extracts AKAZE features itself (localization.cpp:312-330);
 // extraction is upstream of the accelerated path, so this tool takes the query's extracted regions:
 // <name>.desc (FileUtils.cpp:77-92) with <name>.feat next to it.  The image size comes from
 // --width/--height or, by default, from intrinsic 0 of sfm_data.json.  -f -r -g -x -y -z -d -i have
 // the reference's meaning; -w -k -a -p (match-file dump, BoW pre-selection) are accepted and
-// ignored; -gm (guided matching) is not implemented and is refused.
+// ignored; -gm (guided matching) is not implemented and is refused.  --rank/--world shard a folder
+// of queries over processes (one per GPU, each holding the map; no collective): process R handles
+// every W-th query and writes its own result files.
 #include <dirent.h>
 #include <sys/stat.h>
 
@@ -86,7 +88,7 @@ int main(int argc, char **argv) {
     std::vector<std::string> pos;
     std::string v;
     float fDistRatio = 0.6f;
-    int ransacRound = 200, locEvryNFrame = 1, device = 0;
+    int ransacRound = 200, locEvryNFrame = 1, device = -1, rank = 0, world = 1;
     double geomPrec = 4.0, cenX = 0, cenY = 0, cenZ = 0, cenRadius = -1.0;
     size_t width = 0, height = 0;
     unsigned long long seed = 1;
@@ -103,6 +105,8 @@ int main(int argc, char **argv) {
         else if (flag(argv[a], "--height", v)) height = (size_t)atoll(v.c_str());
         else if (flag(argv[a], "--device", v)) device = atoi(v.c_str());
         else if (flag(argv[a], "--seed", v)) seed = strtoull(v.c_str(), nullptr, 10);
+        else if (flag(argv[a], "--rank", v)) rank = atoi(v.c_str());
+        else if (flag(argv[a], "--world", v)) world = atoi(v.c_str());
         else if (strcmp(argv[a], "-gm") == 0 || (flag(argv[a], "-gm", v) && v != "false" && v != "0")) {
             std::cerr << "guided matching (-gm) is not implemented" << std::endl;
             return EXIT_FAILURE;
@@ -137,7 +141,9 @@ int main(int argc, char **argv) {
     }
     const std::string sSfM_data = sSfMDir + (sSfMDir.back() == '/' ? "" : "/") + "sfm_data.json";
     try {
-        LocalizeEngine engine(sSfMDir, sMatchesDir, "", fDistRatio, ransacRound, geomPrec, false, 0, 0, device);
+        if (world < 1 || rank < 0 || rank >= world) { std::cerr << "bad --rank/--world\n"; return 1; }
+        LocalizeEngine engine(sSfMDir, sMatchesDir, "", fDistRatio, ransacRound, geomPrec, false, 0, 0,
+                              device >= 0 ? device : rank);
         if (cenRadius > 0) engine.setLocalViews({cenX, cenY, cenZ}, cenRadius);
         const Intrinsic &cam = engine.scene().intrinsics.at(0);
         if (width == 0) width = cam.width;
@@ -145,6 +151,7 @@ int main(int argc, char **argv) {
         int imageNumber = 0, matchNextNFrame = 0, n_ok = 0;
         for (const std::string &q : list) {
             imageNumber++;
+            if ((imageNumber - 1) % world != rank) continue;          // another process's query
             // video mode: localise every i-th frame, and the frames right after a success (:293-301, :583-587)
             if (imageNumber % locEvryNFrame == 0) {
             } else if (matchNextNFrame <= 0) {

@@ -101,3 +101,14 @@ def test_restricting_views_by_location(tmp_path):
     assert r.returncode == 0 and "localized 1 of 1" in r.stdout
     r = run(qdir, sfm, mdir, out, "-x=1000.0", "-y=1000.0", "-z=1000.0", "-d=0.5")   # nothing nearby
     assert r.returncode == 0 and "localized 0 of 1" in r.stdout
+
+
+def test_queries_sharded_over_processes(tmp_path):
+    """--rank/--world: every process localises its share of the folder; together they cover it."""
+    sc, sfm, mdir, qdir, out, queries, lm_ids = make_project(tmp_path, seed=12, n_queries=4)
+    for r in range(2):
+        res = run(qdir, sfm, mdir, out, "-r=25", "--rank=%d" % r, "--world=2", "--device=0")
+        assert res.returncode == 0 and "localized 2 of 4" in res.stdout, res.stdout + res.stderr
+    for k, q in enumerate(queries):
+        j = json.loads((out / ("q%03d.json" % k)).read_text())
+        assert np.linalg.norm(np.array(j["t"]) - q["center"]) < 0.05

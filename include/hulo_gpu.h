@@ -187,6 +187,19 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
                          const double *K, size_t max_iter, uint64_t seed, double *P,
                          int32_t *inliers, size_t *n_inliers, double *error_max, int *found);
 
+/* The same with the SEQUENTIAL schedule of openMVG::robust::ACRANSAC kept to the letter: the
+ * global phase ends at the first meaningful model in draw order, the pool narrows again at every
+ * improvement during the reserved iterations, and a model replaces the best so far only in draw
+ * order.  Iterations are still scored in batches, speculatively; results are committed in order
+ * and the rest of a batch is re-drawn when a commit changes the pool.  For one seed this runs the
+ * trace of the sequential CPU restatement (same draws, same pool updates); it costs more round
+ * trips than hulo_resect_acransac (1.2 ms against 0.28 ms for 700 clean correspondences), which is why
+ * the engine uses the batched form.  Inliers and error_max are at the device's scoring precision
+ * (fp32 residual keys).  Arguments and outputs as hulo_resect_acransac. */
+int hulo_resect_acransac_sequential(hulo_gpu *h, const double *x2d, const double *X3d, size_t N,
+                                    const double *K, size_t max_iter, uint64_t seed, double *P,
+                                    int32_t *inliers, size_t *n_inliers, double *error_max, int *found);
+
 /* --------------------------------------------- K3: F-matrix geometric filter */
 
 /* hulo::geometricMatch, MatchUtils.cpp:372-420 (decl MatchUtils.h:66-72): OpenMVG's

@@ -24,7 +24,8 @@
  * The P3P solution set is cross-checked against cv2.solveP3P in tests/.
  * Known deviations: (1) the sampler is a seeded splitmix64 instead of std::rand (upstream
  * seeds non-deterministically, so traces are not comparable anyway); (2) P3P models with
- * non-finite entries are skipped instead of being sorted with NaN residuals.
+ * non-finite entries are skipped instead of being sorted with NaN residuals; (3) the narrowed
+ * sampling pool is kept in index order (distribution preserving, see orc_acransac).
  */
 #include <complex.h>
 #include <float.h>
@@ -314,6 +315,11 @@ void orc_score_hypotheses(const double *models, size_t H, const double *x2dn, co
     free(logc_n); free(logc_k);
 }
 
+static int cmp_size_t_fwd(const void *a, const void *b) {
+    size_t x = *(const size_t *)a, y = *(const size_t *)b;
+    return (x > y) - (x < y);
+}
+
 /* ---------- sampler ---------- */
 static uint64_t splitmix64(uint64_t *s) {
     uint64_t z = (*s += 0x9E3779B97F4A7C15ULL);
@@ -400,8 +406,12 @@ int orc_acransac(const double *x2d, const double *X3d, size_t N, const double *K
                 nIter++;
                 nIterReserve--;
             } else {
+                /* Known deviation (3): the narrowed pool is kept in ascending index order, not in
+                 * residual order -- see orc_fmatrix_acransac below for why this changes nothing in
+                 * distribution and makes traces comparable between implementations. */
                 n_pool = n_best;
                 memcpy(pool, best_inl, sizeof(size_t) * n_best);
+                qsort(pool, n_pool, sizeof(size_t), cmp_size_t_fwd);
                 if (nIterReserve) {
                     nIter = iter + 1 + nIterReserve;
                     nIterReserve = 0;

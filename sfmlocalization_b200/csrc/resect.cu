@@ -736,4 +736,119 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
     return HULO_OK;
 }
 
+// The residual key of correspondence i under model M exactly as score_kernel forms it: projection and
+// difference in fp64 with the same fma tree, squared norm in fp32; NaN sorts last.
+static inline float device_residual(const double *M, const double *X, const double *xn) {
+    const double u = std::fma(M[0], X[0], std::fma(M[1], X[1], std::fma(M[2], X[2], M[3])));
+    const double v = std::fma(M[4], X[0], std::fma(M[5], X[1], std::fma(M[6], X[2], M[7])));
+    const double w = std::fma(M[8], X[0], std::fma(M[9], X[1], std::fma(M[10], X[2], M[11])));
+    const float fx = (float)(u / w - xn[0]), fy = (float)(v / w - xn[1]);
+    const float e = std::fmaf(fx, fx, fy * fy);
+    return e == e ? e : INFINITY;
+}
+
+int hulo_resect_acransac_sequential(hulo_gpu *h, const double *x2d, const double *X3d, size_t N, const double *K,
+                                    size_t max_iter, uint64_t seed, double *P, int32_t *inliers, size_t *n_inliers,
+                                    double *error_max, int *found) {
+    HULO_ARG(h != nullptr && K != nullptr && P != nullptr && n_inliers != nullptr && error_max != nullptr &&
+                 found != nullptr, "null argument");
+    HULO_ARG(N == 0 || (x2d != nullptr && X3d != nullptr && inliers != nullptr), "null correspondences");
+    HULO_ARG(N <= kMaxPoints, "more than 32768 correspondences");
+    *n_inliers = 0; *error_max = 0.0; *found = 0;
+    if (N <= 3 || max_iter == 0) return HULO_OK;
+    HULO_CUDA(cudaSetDevice(h->device));
+    std::vector<double> x2dn;
+    normalize_points(x2d, N, K, x2dn);
+    Problem pb;
+    int rc = stage_problem(h, x2dn, X3d, N, pb);
+    if (rc != HULO_OK) return rc;
+
+    size_t nIter = max_iter, reserve = nIter / 10;
+    nIter -= reserve;
+    std::vector<size_t> pool(N);
+    for (size_t i = 0; i < N; ++i) pool[i] = i;
+    double minNFA = INFINITY, best_model[12] = {0};
+    size_t n_best = 0;
+    std::vector<uint32_t> tri;
+    std::vector<double> h_nfa, h_models;
+    std::vector<int32_t> h_k;
+    struct EI { float e; uint32_t i; };
+    std::vector<EI> ei(N);
+    // the inliers of a model at device precision: the n_best smallest (residual, index) keys
+    auto sort_keys = [&](const double *M) {
+        for (size_t i = 0; i < N; ++i) ei[i] = EI{device_residual(M, X3d + 3 * i, x2dn.data() + 2 * i), (uint32_t)i};
+        std::sort(ei.begin(), ei.end(), [](const EI &a, const EI &b) { return a.e < b.e || (a.e == b.e && a.i < b.i); });
+    };
+
+    size_t iter = 0, chunk = 64;
+    while (iter < nIter) {
+        // the next iterations are drawn and scored together, speculatively: their results are
+        // committed in order below, and thrown away from the first commit that changes the pool
+        const size_t B = std::min(chunk, nIter - iter);
+        tri.resize(3 * B);
+        for (size_t t = 0; t < B; ++t) {
+            uint64_t st = seed + (uint64_t)(iter + t) * 3ull * 0x9E3779B97F4A7C15ULL;   // 3 draws per iteration
+            size_t pos[3];
+            sample3(st, pool.size(), pos);
+            for (int s3 = 0; s3 < 3; ++s3) tri[3 * t + s3] = (uint32_t)pool[pos[s3]];
+        }
+        HULO_CUDA(h->scratch3.reserve(B * 3 * sizeof(uint32_t)));
+        HULO_CUDA(h->scratch1.reserve(B * 48 * sizeof(double) + B * sizeof(int32_t)));
+        HULO_CUDA(cudaMemcpyAsync(h->scratch3.ptr, tri.data(), B * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        double *d_models = h->scratch1.as<double>();
+        int32_t *d_nm = reinterpret_cast<int32_t *>(d_models + B * 48);
+        p3p_kernel<<<(unsigned)((B + 127) / 128), 128, 0, h->stream>>>(h->scratch3.as<uint32_t>(), (uint32_t)B, pb.d_x2dn,
+                                                                     pb.d_X3d, d_models, d_nm);
+        HULO_CUDA(cudaGetLastError());
+        h->launches++;
+        ScoreOut o;
+        rc = launch_score(h, pb, d_models, 4 * B, -1.0f, o);
+        if (rc != HULO_OK) return rc;
+        h_nfa.resize(4 * B); h_k.resize(4 * B); h_models.resize(48 * B);
+        HULO_CUDA(cudaMemcpyAsync(h_nfa.data(), o.nfa, 4 * B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        HULO_CUDA(cudaMemcpyAsync(h_k.data(), o.k, 4 * B * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        HULO_CUDA(cudaMemcpyAsync(h_models.data(), d_models, 48 * B * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        HULO_CUDA(cudaStreamSynchronize(h->stream));
+        size_t next_iter = iter + B;
+        for (size_t t = 0; t < B; ++t) {
+            const size_t it = iter + t;
+            bool better = false;
+            // the solver compacts its models to the front; absent slots are NaN-marked and score +inf
+            for (int m = 0; m < 4; ++m)
+                if (h_nfa[4 * t + m] < minNFA) {
+                    better = true;
+                    minNFA = h_nfa[4 * t + m];
+                    n_best = (size_t)h_k[4 * t + m];
+                    memcpy(best_model, &h_models[48 * t + 12 * m], sizeof best_model);
+                }
+            if ((better && minNFA < 0) || (it + 1 == nIter && reserve)) {
+                if (n_best == 0) {
+                    nIter++;
+                    reserve--;
+                } else {
+                    sort_keys(best_model);
+                    pool.resize(n_best);
+                    for (size_t i = 0; i < n_best; ++i) pool[i] = ei[i].i;
+                    std::sort(pool.begin(), pool.end());        // the pool is kept in index order
+                    if (reserve) { nIter = it + 1 + reserve; reserve = 0; }
+                    next_iter = it + 1;                          // the rest sampled the old pool
+                    break;
+                }
+            }
+        }
+        if (next_iter == iter + B) chunk = std::min<size_t>(chunk * 2, 512);
+        iter = next_iter;
+    }
+    if (!(minNFA < 0.0) || n_best == 0) return HULO_OK;
+    sort_keys(best_model);
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c)
+            P[4 * r + c] = K[3 * r] * best_model[c] + K[3 * r + 1] * best_model[4 + c] + K[3 * r + 2] * best_model[8 + c];
+    *error_max = sqrt((double)ei[n_best - 1].e) * K[0];
+    for (size_t i = 0; i < n_best; ++i) inliers[i] = (int32_t)ei[i].i;
+    *n_inliers = n_best;
+    *found = (double)n_best > 2.5 * 3.0 ? 1 : 0;
+    return HULO_OK;
+}
+
 }  // extern "C"

@@ -268,13 +268,14 @@ class HuloGpu:
                                 _ptr(models), _ptr(nm)))
         return models, nm
 
-    def resect_acransac(self, x2d, X3d, K, max_iter=4096, seed=1):
+    def resect_acransac(self, x2d, X3d, K, max_iter=4096, seed=1, sequential=False):
         x2d = np.ascontiguousarray(x2d, np.float64); X3d = np.ascontiguousarray(X3d, np.float64)
         K = np.ascontiguousarray(K, np.float64)
         N = x2d.shape[0]
         P = np.zeros((3, 4)); inl = np.empty(max(N, 1), np.int32)
         n_inl = C.c_size_t(0); emax = C.c_double(0); found = C.c_int(0)
-        check(self.lib.hulo_resect_acransac(self.h, _ptr(x2d), _ptr(X3d), N, _ptr(K), max_iter, seed, _ptr(P),
+        fn = self.lib.hulo_resect_acransac_sequential if sequential else self.lib.hulo_resect_acransac
+        check(fn(self.h, _ptr(x2d), _ptr(X3d), N, _ptr(K), max_iter, seed, _ptr(P),
                                             _ptr(inl), C.byref(n_inl), C.byref(emax), C.byref(found)))
         return dict(found=bool(found.value), P=P, inliers=inl[:n_inl.value].copy(), error_max=emax.value)
 

@@ -138,3 +138,31 @@ def test_acransac_not_found_cases(gpu):
     sc = synth.resection_scene(60, 9, outlier_frac=1.0)
     r = gpu.resect_acransac(sc["x2d"], sc["X3d"], sc["K"], max_iter=512, seed=3)
     assert not r["found"]
+
+
+@pytest.mark.parametrize("N,outl,max_iter,seed", [(60, 0.3, 4096, 1), (300, 0.5, 4096, 2), (1000, 0.6, 1024, 3),
+                                                  (2000, 0.7, 4096, 4), (12, 0.2, 200, 5), (500, 0.0, 64, 6)])
+def test_sequential_schedule_runs_the_oracle_trace(gpu, orc, N, outl, max_iter, seed):
+    """hulo_resect_acransac_sequential keeps ACRANSAC's schedule to the letter, and both sides keep
+    the narrowed pool in index order, so for one seed the device commits the draws the sequential
+    CPU restatement commits: same model (P to 1e-9 relative), same inlier set; the order of the list
+    agrees beyond the three zero-residual sample points."""
+    sc = synth.resection_scene(N, 300 + N, outlier_frac=outl)
+    g = gpu.resect_acransac(sc["x2d"], sc["X3d"], sc["K"], max_iter=max_iter, seed=seed, sequential=True)
+    o = orc.acransac(sc["x2d"], sc["X3d"], sc["K"], max_iter=max_iter, seed=seed)
+    assert g["found"] == (o["ok"] and len(o["inliers"]) > 7.5)
+    assert np.array_equal(np.sort(g["inliers"]), np.sort(o["inliers"]))
+    if len(o["inliers"]):
+        assert np.abs(g["P"] - o["P"]).max() <= 1e-9 * np.abs(o["P"]).max()
+        assert abs(g["error_max"] - o["error_max"]) <= 1e-3
+        assert np.array_equal(g["inliers"][3:], o["inliers"][3:]) or len(np.setdiff1d(g["inliers"][:6], o["inliers"][:6])) <= 3
+
+
+def test_sequential_schedule_degenerate_inputs(gpu, orc):
+    sc = synth.resection_scene(3, 1, outlier_frac=0.0)
+    g = gpu.resect_acransac(sc["x2d"], sc["X3d"], sc["K"], sequential=True)
+    assert not g["found"] and len(g["inliers"]) == 0
+    sc = synth.resection_scene(200, 2, outlier_frac=1.0)
+    g = gpu.resect_acransac(sc["x2d"], sc["X3d"], sc["K"], max_iter=512, seed=3, sequential=True)
+    o = orc.acransac(sc["x2d"], sc["X3d"], sc["K"], max_iter=512, seed=3)
+    assert not g["found"] and len(g["inliers"]) == len(o["inliers"]) == 0

@@ -64,6 +64,22 @@ def scoring(g, name, H, N, seed):
                       "note": "wall clock of hulo_score_resection incl. H2D of models and D2H of scores"}), flush=True)
 
 
+def resection(g, name, N, outl, seed):
+    """AC-RANSAC resection (4096 iterations) in both schedules: batched (engine default) and sequential."""
+    sc = synth.resection_scene(N, seed, outlier_frac=outl)
+    out = {"config": name, "N": N, "outlier_frac": outl}
+    for label, seq in (("batched", False), ("sequential", True)):
+        g.resect_acransac(sc["x2d"], sc["X3d"], sc["K"], seed=1, sequential=seq)
+        ts = []
+        for k in range(10):
+            t0 = time.perf_counter()
+            r = g.resect_acransac(sc["x2d"], sc["X3d"], sc["K"], seed=10 + k, sequential=seq)
+            ts.append(time.perf_counter() - t0)
+        out[label + "_ms"] = float(np.median(ts)) * 1e3
+        out[label + "_inliers"] = int(len(r["inliers"]))
+    print(json.dumps(out), flush=True)
+
+
 def batched_server(g, name, n_views, feats, n_landmarks, n_queries, nq, seed):
     """BASELINE.json config 4 end to end: concurrent query images against one resident map."""
     from sfmlocalization_b200.gpu import LocalizeEngine
@@ -108,6 +124,10 @@ def main():
         if "c4e" in which:
             batched_server(g, "C4 batched server: 256 queries x 3000 vs 2M-descriptor map, end to end", 1000, 2000,
                            200000, 256, 3000, 4100)
+        if "pnp" in which:
+            resection(g, "AC-RANSAC resection, clean query (C1-like)", 700, 0.02, 4200)
+            resection(g, "AC-RANSAC resection, half outliers", 700, 0.5, 4201)
+            resection(g, "AC-RANSAC resection, 2000 correspondences, 70 % outliers", 2000, 0.7, 4202)
         if "k2" in which:
             for N in (100, 500, 2000):
                 scoring(g, "K2 scoring 4096 triplets x <=4 models", 16384, N, 4000 + N)

@@ -178,12 +178,31 @@ struct RowVsQueries {
     }
 };
 
+// The same with a LAZY best-2 update: the keys of the row are computed for every searcher row of
+// the thread, but the three min/max per key only run when some lane of the warp holds a key below
+// its current second best -- one compare per key and one vote per row otherwise.  After a few
+// thousand rows of a chunk almost no row qualifies, so on long chunks this takes two ALU
+// instructions per distance out of the loop; on short chunks (a few hundred rows) it loses.
+template <int QI, int QPT, int CSA, bool IMAD>
+struct RowKeys {
+    static __device__ __forceinline__ bool run(const uint32_t (&q)[QPT][16], const uint32_t (&w)[16], uint32_t base,
+                                               uint32_t unit, const uint32_t (&best1)[QPT], uint32_t (&keys)[QPT]) {
+        constexpr int kCsa = CSA == 89 ? (QI == QPT - 1 ? 9 : 8) : CSA == 889 ? (2 * QI >= QPT ? 9 : 8) : CSA;
+        keys[QI] = hamming_key<kCsa, IMAD>(q[QI], w, base, unit);
+        bool hit = keys[QI] < best1[QI];
+        if constexpr (QI + 1 < QPT) hit = RowKeys<QI + 1, QPT, CSA, IMAD>::run(q, w, base, unit, best1, keys) || hit;
+        return hit;
+    }
+};
+
 // OPT bit 0: adds on the FMA pipe (IMAD); bit 1: rows taken two at a time so the best-2 update
-// uses 3-input min/max (VIMNMX3): 5 instead of 6 instructions per two keys.
+// uses 3-input min/max (VIMNMX3): 5 instead of 6 instructions per two keys; bit 2: lazy best-2
+// update (RowKeys).
 template <int THREADS, int QPT, int CSA, int OPT>
 __global__ void __launch_bounds__(THREADS, 1) knn2_kernel(const KnnParams p) {
     constexpr bool kImad = (OPT & 1) != 0;
     constexpr bool kPairRows = (OPT & 2) != 0;
+    constexpr bool kLazy = (OPT & 4) != 0;
     constexpr int kWarps = THREADS / 32;
     __shared__ __align__(128) uint4 s_tiles[kStages][kTileRows * 4];
     __shared__ __align__(8) uint64_t s_full[kStages];
@@ -302,7 +321,20 @@ __global__ void __launch_bounds__(THREADS, 1) knn2_kernel(const KnnParams p) {
             for (; r < rows; ++r) {
                 uint32_t w[16];
                 load_row(r, w);
-                RowVsQueries<0, QPT, CSA, kImad>::run(q, w, key_base + r, unit, best0, best1);
+                if constexpr (kLazy) {
+                    uint32_t keys[QPT];
+                    const bool hit = RowKeys<0, QPT, CSA, kImad>::run(q, w, key_base + r, unit, best1, keys);
+                    if (__any_sync(0xffffffffu, hit)) {
+#pragma unroll
+                        for (int qi = 0; qi < QPT; ++qi) {
+                            const uint32_t hi = max(best0[qi], keys[qi]);
+                            best0[qi] = min(best0[qi], keys[qi]);
+                            best1[qi] = min(best1[qi], hi);
+                        }
+                    }
+                } else {
+                    RowVsQueries<0, QPT, CSA, kImad>::run(q, w, key_base + r, unit, best0, best1);
+                }
             }
             ++n_cons;
             __syncwarp();
@@ -501,7 +533,8 @@ cudaError_t info_variant(int *regs, int *ctas, size_t *smem) {
     X(256, 4, 7, 0) X(256, 4, 7, 3) X(256, 4, 8, 3) X(128, 8, 7, 0) X(128, 4, 7, 0) X(128, 4, 7, 3) \
     X(768, 2, 8, 1) X(768, 2, 7, 1) X(768, 2, 8, 0) X(640, 3, 8, 1) X(640, 3, 7, 1) X(640, 3, 8, 0) X(384, 5, 8, 1) \
     X(512, 4, 89, 1) X(512, 4, 9, 1) X(256, 8, 89, 1) X(256, 8, 9, 1) X(256, 4, 89, 1) X(256, 4, 8, 1) X(128, 4, 8, 1) \
-    X(512, 4, 889, 1) X(256, 4, 889, 1) X(256, 4, 9, 1) X(128, 4, 89, 1) X(128, 4, 889, 1)
+    X(512, 4, 889, 1) X(256, 4, 889, 1) X(256, 4, 9, 1) X(128, 4, 89, 1) X(128, 4, 889, 1) \
+    X(512, 4, 9, 5) X(512, 4, 889, 5)
 
 cudaError_t knn2_launch(const KnnParams &p, const KnnConfig &cfg, int grid_ctas, cudaStream_t stream) {
 #define X(T, Q, C, O) \

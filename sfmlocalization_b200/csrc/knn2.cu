@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(THREADS, 1) knn2_kernel(const KnnParams p) {
     constexpr bool kImad = (OPT & 1) != 0;
     constexpr bool kPairRows = (OPT & 2) != 0;
     constexpr bool kLazy = (OPT & 4) != 0;
+    constexpr int kRowUnroll = (OPT & 8) ? 1 : (OPT & 16) ? 4 : 2;     // rows per trip of the inner loop
     constexpr int kWarps = THREADS / 32;
     __shared__ __align__(128) uint4 s_tiles[kStages][kTileRows * 4];
     __shared__ __align__(8) uint64_t s_full[kStages];
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(THREADS, 1) knn2_kernel(const KnnParams p) {
                     }
                 }
             }
-#pragma unroll 2
+#pragma unroll kRowUnroll
             for (; r < rows; ++r) {
                 uint32_t w[16];
                 load_row(r, w);

@@ -20,6 +20,11 @@ void must(int status, const char *what) {
 struct LocalizeEngine::State {
     hulo_gpu *gpu = nullptr;
     hulo_engine *eng = nullptr;
+    hulo_bow *bow = nullptr;                           // the views' bag-of-features vectors (bowKnnNum > 0)
+    std::map<std::size_t, uint32_t> bow_row_of_view;
+    std::vector<std::size_t> bow_view_of_row;
+    std::size_t bow_dim = 0;
+    int bowKnnNum = 0;
     SfMScene scene;
     std::string sfmDataDir, matchDir;
     double ratio = 0.6;
@@ -34,6 +39,7 @@ struct LocalizeEngine::State {
     bool cli_restricted = false;
     LastResult last;
     ~State() {
+        if (bow) hulo_bow_destroy(bow);
         if (eng) hulo_engine_destroy(eng);
         if (gpu) hulo_gpu_destroy(gpu);
     }
@@ -57,7 +63,6 @@ LocalizeEngine::LocalizeEngine(const std::string sfmDataDir, const std::string m
     if (!loadSfMData(sSfM_data, s.scene))
         throw std::runtime_error("The input sfm_data.json file \"" + sSfM_data + "\" cannot be read.");
     if (beaconKnnNum > 0) std::cout << "iBeacon view selection is outside this library: beaconKnnNum ignored" << std::endl;
-    if (bowKnnNum > 0) std::cout << "BoW view selection is outside this library: bowKnnNum ignored" << std::endl;
 
     // the global-coordinate matrix A (LocalizeEngine.cc:113-119); landmarks and camera centres are
     // moved into global coordinates once (TRANSFORM_SFM_DATA_BEFORE_LOCALIZE, :61, :122-144)
@@ -151,6 +156,26 @@ LocalizeEngine::LocalizeEngine(const std::string sfmDataDir, const std::string m
     must(hulo_engine_configure(s.eng, (float)secondTestRatio, 16, 8, 10, 4096), "hulo_engine_configure");
     s.last.localized = false;
     memcpy(s.last.K, K, sizeof K);
+    // BoW model of the views (LocalizeEngine.cc:146-179): the .bow vectors, resident on the device
+    if (bowKnnNum > 0) {
+        std::vector<float> all;
+        std::vector<double> vec;
+        for (const auto &kv : s.scene.views) {
+            int r = 0, c = 0;
+            if (!readMatBin(bowPath(matchDir, kv.second.s_Img_path), r, c, vec) || vec.empty()) continue;
+            if (s.bow_dim == 0) s.bow_dim = vec.size();
+            if (vec.size() != s.bow_dim) continue;
+            s.bow_row_of_view[kv.first] = (uint32_t)s.bow_view_of_row.size();
+            s.bow_view_of_row.push_back(kv.first);
+            for (double v : vec) all.push_back((float)v);
+        }
+        if (s.bow_view_of_row.empty()) {
+            std::cout << "cannot find BOW vectors of the views, localize without using BOW model" << std::endl;
+        } else {
+            must(hulo_bow_create(s.gpu, all.data(), s.bow_view_of_row.size(), s.bow_dim, &s.bow), "hulo_bow_create");
+            s.bowKnnNum = bowKnnNum;
+        }
+    }
     // keypoints are set now; the query image size is only known per call (hulo_engine_set_query_size)
     std::vector<double> xy1(2, 0.0);
     must(hulo_engine_set_keypoints(s.eng, map_xy.empty() ? xy1.data() : map_xy.data(), view_wh.data(), 1, 1),
@@ -180,7 +205,8 @@ std::vector<double> LocalizeEngine::localize(const uint8_t *desc, std::size_t n,
                                              bool bReturnKeypoints, std::vector<double> &points2D,
                                              std::vector<double> &points3D, std::vector<int> &pointsInlier,
                                              bool bReturnTime, std::vector<double> &times,
-                                             const std::vector<double> &center, double radius, uint64_t seed) {
+                                             const std::vector<double> &center, double radius, uint64_t seed,
+                                             const std::vector<float> *queryBow) {
     State &s = *st_;
     std::vector<double> result;
     s.last.localized = false;
@@ -211,6 +237,25 @@ std::vector<double> LocalizeEngine::localize(const uint8_t *desc, std::size_t n,
     if (restricted) {
         std::cout << "number of selected local views by center location : " << views.size() << std::endl;
         if (views.empty()) return result;
+    }
+    // ---- BoW pre-selection (LocalizeEngine.cc:334-362): the knn views nearest to the query in
+    // bag-of-features space, when there are more candidates than knn
+    if (s.bow && s.bowKnnNum > 0 && queryBow && queryBow->size() == s.bow_dim && views.size() > (std::size_t)s.bowKnnNum) {
+        std::vector<uint32_t> rows;
+        for (uint32_t seg : views) {
+            auto it = s.bow_row_of_view.find(s.seg_view[seg]);
+            if (it != s.bow_row_of_view.end()) rows.push_back(it->second);
+        }
+        if (rows.size() > (std::size_t)s.bowKnnNum) {
+            std::vector<int32_t> idx((std::size_t)s.bowKnnNum);
+            must(hulo_bow_knn(s.bow, queryBow->data(), rows.data(), rows.size(), (std::size_t)s.bowKnnNum, idx.data(), nullptr),
+                 "hulo_bow_knn");
+            std::set<std::size_t> chosen;
+            for (int32_t r : idx) chosen.insert(s.bow_view_of_row[(std::size_t)r]);
+            views.clear();
+            for (std::size_t v : chosen) views.push_back(s.seg_of_view.at(v));     // ascending view id, like the std::set
+            std::cout << "number of selected local views by bow : " << views.size() << std::endl;
+        }
     }
     if (views.empty()) {                       // no pair to match: map_putativeMatches stays empty (:439-454)
         std::cout << "Not enough putative matches" << std::endl;

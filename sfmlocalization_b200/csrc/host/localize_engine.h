@@ -6,8 +6,10 @@
 //   * localize() takes the query image's extracted AKAZE regions (descriptor rows + feature
 //     positions) and its size instead of a cv::Mat: extraction (LocalizeEngine.cc:200-260,
 //     334-352) is upstream of the accelerated path and stays with the caller;
-//   * iBeacon / BoW view pre-selection (beaconKnnNum, bowKnnNum, beaconStr) is out of scope:
-//     the arguments are accepted, a non-zero value prints a note and selects nothing;
+//   * BoW view pre-selection (bowKnnNum, LocalizeEngine.cc:334-362) works from the views' .bow
+//     files and the query's bag-of-features vector handed to localize(); computing that vector
+//     from the image (dense features + vocabulary) stays with the caller.  iBeacon pre-selection
+//     (beaconKnnNum, beaconStr) is out of scope: accepted, a non-zero value prints a note;
 //   * guided matching is not implemented: guidedMatching = true throws std::invalid_argument.
 // The object is a copyable handle (shared state), because the reference stores engines by
 // value in a std::map (localizeImage.cc:100).  Not re-entrant, like the reference (:71-74).
@@ -42,7 +44,7 @@ public:
                                  const std::string &beaconStr, bool bReturnKeypoints, std::vector<double> &points2D,
                                  std::vector<double> &points3D, std::vector<int> &pointsInlier, bool bReturnTime,
                                  std::vector<double> &times, const std::vector<double> &center = std::vector<double>(),
-                                 double radius = -1.0, uint64_t seed = 1);
+                                 double radius = -1.0, uint64_t seed = 1, const std::vector<float> *queryBow = nullptr);
 
     // what the CLI prints into <outDir>/<basename>.json (localization.cpp:100-144)
     struct LastResult {

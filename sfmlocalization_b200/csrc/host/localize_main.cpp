@@ -12,8 +12,10 @@
 // extraction is upstream of the accelerated path, so this tool takes the query's extracted regions:
 // <name>.desc (FileUtils.cpp:77-92) with <name>.feat next to it.  The image size comes from
 // --width/--height or, by default, from intrinsic 0 of sfm_data.json.  -f -r -g -x -y -z -d -i have
-// the reference's meaning; -w -k -a -p (match-file dump, BoW pre-selection) are accepted and
-// ignored; -gm (guided matching) is not implemented and is refused.  --rank/--world shard a folder
+// the reference's meaning; -k=knnbow selects the knn views nearest in bag-of-features space, from the
+// views' .bow files and <name>.bow next to the query's .desc (the reference computes the query's
+// vector from the image with the -a / -p models, localization.cpp:386-412); -w -a -p are accepted
+// and ignored; -gm (guided matching) is not implemented and is refused.  --rank/--world shard a folder
 // of queries over processes (one per GPU, each holding the map; no collective): process R handles
 // every W-th query and writes its own result files.
 #include <dirent.h>
@@ -88,7 +90,7 @@ int main(int argc, char **argv) {
     std::vector<std::string> pos;
     std::string v;
     float fDistRatio = 0.6f;
-    int ransacRound = 200, locEvryNFrame = 1, device = -1, rank = 0, world = 1;
+    int ransacRound = 200, locEvryNFrame = 1, device = -1, rank = 0, world = 1, knnbow = 0;
     double geomPrec = 4.0, cenX = 0, cenY = 0, cenZ = 0, cenRadius = -1.0;
     size_t width = 0, height = 0;
     unsigned long long seed = 1;
@@ -101,6 +103,7 @@ int main(int argc, char **argv) {
         else if (flag(argv[a], "-z", v)) cenZ = atof(v.c_str());
         else if (flag(argv[a], "-d", v)) cenRadius = atof(v.c_str());
         else if (flag(argv[a], "-i", v)) locEvryNFrame = atoi(v.c_str());
+        else if (flag(argv[a], "-k", v)) knnbow = atoi(v.c_str());
         else if (flag(argv[a], "--width", v)) width = (size_t)atoll(v.c_str());
         else if (flag(argv[a], "--height", v)) height = (size_t)atoll(v.c_str());
         else if (flag(argv[a], "--device", v)) device = atoi(v.c_str());
@@ -142,7 +145,7 @@ int main(int argc, char **argv) {
     const std::string sSfM_data = sSfMDir + (sSfMDir.back() == '/' ? "" : "/") + "sfm_data.json";
     try {
         if (world < 1 || rank < 0 || rank >= world) { std::cerr << "bad --rank/--world\n"; return 1; }
-        LocalizeEngine engine(sSfMDir, sMatchesDir, "", fDistRatio, ransacRound, geomPrec, false, 0, 0,
+        LocalizeEngine engine(sSfMDir, sMatchesDir, "", fDistRatio, ransacRound, geomPrec, false, 0, knnbow,
                               device >= 0 ? device : rank);
         if (cenRadius > 0) engine.setLocalViews({cenX, cenY, cenZ}, cenRadius);
         const Intrinsic &cam = engine.scene().intrinsics.at(0);
@@ -172,8 +175,16 @@ int main(int argc, char **argv) {
             std::cout << "image # " << imageNumber << "/" << list.size() << std::endl;
             std::vector<double> p2, p3, times;
             std::vector<int> inl;
+            std::vector<float> qbow;
+            if (knnbow > 0) {
+                int br = 0, bc = 0;
+                std::vector<double> bv;
+                if (readMatBin(q.substr(0, q.size() - 4) + "bow", br, bc, bv))
+                    for (double x : bv) qbow.push_back((float)x);
+            }
             const std::vector<double> pose = engine.localize(rows.data(), n, 64, feats, width, height, "", false, p2, p3, inl,
-                                                             true, times, std::vector<double>(), -1.0, seed + imageNumber);
+                                                             true, times, std::vector<double>(), -1.0, seed + imageNumber,
+                                                             qbow.empty() ? nullptr : &qbow);
             if (times.size() == 6)
                 std::cout << "Putative matching: " << times[3] << " s\nGeometric matching: " << times[4] << " s\nPnP: "
                           << times[5] << " s\n";

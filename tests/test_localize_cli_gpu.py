@@ -112,3 +112,22 @@ def test_queries_sharded_over_processes(tmp_path):
     for k, q in enumerate(queries):
         j = json.loads((out / ("q%03d.json" % k)).read_text())
         assert np.linalg.norm(np.array(j["t"]) - q["center"]) < 0.05
+
+
+def test_bow_preselection(tmp_path):
+    """-k: the views are narrowed to the knn nearest in bag-of-features space (views' .bow files and
+    the query's .bow) before matching; localisation still succeeds on the narrowed set."""
+    sc, sfm, mdir, qdir, out, queries, lm_ids = make_project(tmp_path, seed=13, n_queries=1)
+    rng = np.random.default_rng(2)
+    bof = rng.random((14, 96)).astype(np.float32)
+    for v in range(14):
+        hostlib.save_mat_bin(str(mdir / ("frame%04d.bow" % v)), bof[v].reshape(-1, 1), 5)
+    qv = bof[[3, 7, 9]].mean(axis=0)
+    hostlib.save_mat_bin(str(qdir / "q000.bow"), qv.reshape(-1, 1), 5)
+    r = run(qdir, sfm, mdir, out, "-r=25", "-k=6")
+    assert r.returncode == 0 and "number of selected local views by bow : 6" in r.stdout, r.stdout + r.stderr
+    assert "localized 1 of 1" in r.stdout
+    j = json.loads((out / "q000.json").read_text())
+    assert np.linalg.norm(np.array(j["t"]) - queries[0]["center"]) < 0.05
+    r = run(qdir, sfm, mdir, out, "-r=25", "-k=50")                 # more than there are views: no narrowing
+    assert r.returncode == 0 and "selected local views by bow" not in r.stdout and "localized 1 of 1" in r.stdout

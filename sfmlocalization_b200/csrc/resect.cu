@@ -20,6 +20,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -126,6 +127,129 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
         out_nfa[h] = b.nfa;
         if (out_k) out_k[h] = b.k;
         if (out_errk) out_errk[h] = b.k >= 1 ? s_e[b.k - 1] : INFINITY;
+        if (out_ninl) out_ninl[h] = c;
+    }
+}
+
+// The same kernel with the sort in REGISTERS (N <= 4096).  Thread t owns the E = npad / 256
+// consecutive elements [E t, E t + E) of the bitonic network: exchanges at distance j < E stay inside
+// the thread, E <= j < 32 E are warp shuffles, and only j >= 32 E (at most three sub-stages of the
+// last three merges) go through shared memory -- 6 block barriers instead of one per sub-stage (66
+// for 2048 elements), and no strided shared-memory traffic (the ncu profile of score_kernel:
+// 73 % issue slots, LSU 50 %, 80 M bank conflicts, warps waiting on short scoreboard).
+template <int E>
+__global__ void __launch_bounds__(kScoreThreads) score_kernel_reg(
+    const double *__restrict__ models, uint32_t H, const double *__restrict__ x2dn,
+    const double *__restrict__ X3d, uint32_t N, const float *__restrict__ logc_n,
+    const float *__restrict__ logc_k, double loge0, double logalpha0, float thr2, double *__restrict__ out_nfa,
+    int32_t *__restrict__ out_k, float *__restrict__ out_errk, int32_t *__restrict__ out_ninl) {
+    constexpr uint32_t npad = (uint32_t)E * kScoreThreads;
+    // one pad word per 32 keeps the blocked accesses (stride E between lanes) free of bank conflicts
+    __shared__ float s_e[npad + npad / 32];
+    auto at = [](uint32_t i) { return i + (i >> 5); };
+    __shared__ double s_M[12];
+    __shared__ NfaMin s_red[kScoreThreads / 32];
+    __shared__ int s_cnt[kScoreThreads / 32];
+    const uint32_t h = blockIdx.x;
+    if (h >= H) return;
+    const int tid = threadIdx.x;
+    if (tid < 12) s_M[tid] = models[(size_t)h * 12 + tid];
+    __syncthreads();
+    if (!(s_M[0] == s_M[0]) || N < 4) {
+        if (tid == 0) {
+            out_nfa[h] = INFINITY;
+            if (out_k) out_k[h] = 3;
+            if (out_errk) out_errk[h] = INFINITY;
+            if (out_ninl) out_ninl[h] = 0;
+        }
+        return;
+    }
+    int cnt = 0;
+    for (uint32_t i = tid; i < npad; i += kScoreThreads) {
+        float e = INFINITY;
+        if (i < N) {
+            double dx, dy;
+            proj_residual(s_M, X3d + 3 * (size_t)i, x2dn + 2 * (size_t)i, dx, dy);
+            const float fx = (float)dx, fy = (float)dy;
+            e = fmaf(fx, fx, fy * fy);
+            if (!(e == e)) e = INFINITY;
+            if (thr2 >= 0.0f && e <= thr2) ++cnt;
+        }
+        s_e[at(i)] = e;
+    }
+    __syncthreads();
+    float v[E];
+    const uint32_t base = (uint32_t)E * tid;
+#pragma unroll
+    for (int a = 0; a < E; ++a) v[a] = s_e[at(base + a)];
+    for (uint32_t k = 2; k <= npad; k <<= 1) {
+        uint32_t j = k >> 1;
+        for (; j >= 32u * E; j >>= 1) {                     // partner in another warp
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < E; ++a) s_e[at(base + a)] = v[a];
+            __syncthreads();
+#pragma unroll
+            for (int a = 0; a < E; ++a) {
+                const uint32_t i = base + a;
+                const float o = s_e[at(i ^ j)];
+                const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                v[a] = keep_min ? fminf(v[a], o) : fmaxf(v[a], o);
+            }
+        }
+        for (; j >= (uint32_t)E; j >>= 1) {                 // partner in another lane of the warp
+            const int m = (int)(j / E);
+#pragma unroll
+            for (int a = 0; a < E; ++a) {
+                const uint32_t i = base + a;
+                const float o = __shfl_xor_sync(0xffffffffu, v[a], m);
+                const bool keep_min = ((i & j) == 0) == ((i & k) == 0);
+                v[a] = keep_min ? fminf(v[a], o) : fmaxf(v[a], o);
+            }
+        }
+#pragma unroll
+        for (int jj = E / 2; jj > 0; jj >>= 1) {            // partner inside the thread
+            if ((uint32_t)jj < k) {
+#pragma unroll
+                for (int a = 0; a < E; ++a) {
+                    if ((a & jj) == 0) {
+                        const bool up = ((base + a) & k) == 0;
+                        const float lo = fminf(v[a], v[a | jj]), hi = fmaxf(v[a], v[a | jj]);
+                        v[a] = up ? lo : hi;
+                        v[a | jj] = up ? hi : lo;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int a = 0; a < E; ++a) s_e[at(base + a)] = v[a];
+    __syncthreads();
+    NfaMin best{INFINITY, 3};
+    for (uint32_t k = 4 + tid; k <= N; k += kScoreThreads) {
+        const float e = s_e[at(k - 1)];
+        if (e == INFINITY) continue;
+        const double logalpha = logalpha0 + log10((double)e + (double)FLT_EPSILON);
+        const double nfa = loge0 + logalpha * (double)(k - 3) + (double)logc_n[k] + (double)logc_k[k];
+        if (nfa < best.nfa) { best.nfa = nfa; best.k = (int)k; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        NfaMin other;
+        other.nfa = __shfl_xor_sync(0xffffffffu, best.nfa, o);
+        other.k = __shfl_xor_sync(0xffffffffu, best.k, o);
+        best = nfa_min(best, other);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((tid & 31) == 0) { s_red[tid >> 5] = best; s_cnt[tid >> 5] = cnt; }
+    __syncthreads();
+    if (tid == 0) {
+        NfaMin b = s_red[0];
+        int c = s_cnt[0];
+        for (int w = 1; w < kScoreThreads / 32; ++w) { b = nfa_min(b, s_red[w]); c += s_cnt[w]; }
+        out_nfa[h] = b.nfa;
+        if (out_k) out_k[h] = b.k;
+        if (out_errk) out_errk[h] = b.k >= 1 ? s_e[at((uint32_t)b.k - 1)] : INFINITY;
         if (out_ninl) out_ninl[h] = c;
     }
 }
@@ -448,6 +572,26 @@ int launch_score(hulo_gpu *h, const Problem &pb, const double *d_models, size_t 
     o.errk = reinterpret_cast<float *>(o.k + H);
     o.ninl = reinterpret_cast<int32_t *>(o.errk + H);
     if (H == 0) return HULO_OK;
+    if (pb.N <= 4096 && !getenv("HULO_K2_SMEM_SORT")) {
+        // register-resident sort: E elements per thread, npad = 256 E
+        uint32_t np = kScoreThreads;
+        while (np < pb.N) np <<= 1;
+#define HULO_K2_REG(EE)                                                                                            \
+    score_kernel_reg<EE><<<(unsigned)H, kScoreThreads, 0, h->stream>>>(d_models, (uint32_t)H, pb.d_x2dn, pb.d_X3d,     \
+                                                                     (uint32_t)pb.N, pb.d_logc_n, pb.d_logc_k, pb.loge0, \
+                                                                     pb.logalpha0, thr2, o.nfa, o.k, o.errk, o.ninl)
+        switch (np / kScoreThreads) {
+            case 1: HULO_K2_REG(1); break;
+            case 2: HULO_K2_REG(2); break;
+            case 4: HULO_K2_REG(4); break;
+            case 8: HULO_K2_REG(8); break;
+            default: HULO_K2_REG(16); break;
+        }
+#undef HULO_K2_REG
+        HULO_CUDA(cudaGetLastError());
+        h->launches++;
+        return HULO_OK;
+    }
     const uint32_t npad = next_pow2((uint32_t)pb.N);
     const size_t smem = npad * sizeof(float);
     if (smem > 48 * 1024 && smem > h->score_smem_configured) {   // per device, so per context

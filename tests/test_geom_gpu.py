@@ -140,3 +140,10 @@ def test_different_image_sizes_and_many_pairs(gpu, orc):
             t = np.flatnonzero(truth[p])
             assert np.isin(r["inliers"][p], t).mean() > 0.85
     assert agree >= 285
+
+
+def test_large_pair_uses_the_big_shared_memory_buffer(gpu, orc):
+    """9000 putative matches in one pair: 128 KB of sort keys (dynamic shared memory opt-in)."""
+    specs = [(9000, 0.5), (40, 0.3)]
+    exact, r = compare(gpu, orc, specs, 4.0, 200, 13, seed0=900)
+    assert r["valid"][0] and r["n_inliers"][0] > 3000 and exact >= 1

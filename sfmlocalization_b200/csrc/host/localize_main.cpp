@@ -6,7 +6,7 @@
 //
 //   hulo_localize <query .desc file or folder> <sfmDir> <matchDir> <outDir>
 //                 [-f=0.6] [-r=200] [-g=4.0] [-x= -y= -z= -d=-1] [-i=1] [--width=W --height=H]
-//                 [--device=D] [--seed=S] [--rank=R --world=W]
+//                 [--device=D] [--seed=S] [--rank=R --world=W] [--amat=<A.yml>]
 //
 // The reference takes image files and extracts AKAZE features itself (localization.cpp:312-330);
 // extraction is upstream of the accelerated path, so this tool takes the query's extracted regions:
@@ -17,7 +17,9 @@
 // vector from the image with the -a / -p models, localization.cpp:386-412); -w -a -p are accepted
 // and ignored; -gm (guided matching) is not implemented and is refused.  --rank/--world shard a folder
 // of queries over processes (one per GPU, each holding the map; no collective): process R handles
-// every W-th query and writes its own result files.
+// every W-th query and writes its own result files.  --amat gives the OpenCV YAML file with the 3 x 4
+// (or 4 x 4) matrix "A" that takes the model to global coordinates, like the server's aMatFile
+// (LocalizeEngine.cc:113-144): landmarks and camera centres are transformed before localising.
 #include <dirent.h>
 #include <sys/stat.h>
 
@@ -88,7 +90,7 @@ static void save_result(const std::string &out_dir, const std::string &query, co
 
 int main(int argc, char **argv) {
     std::vector<std::string> pos;
-    std::string v;
+    std::string v, sAmat;
     float fDistRatio = 0.6f;
     int ransacRound = 200, locEvryNFrame = 1, device = -1, rank = 0, world = 1, knnbow = 0;
     double geomPrec = 4.0, cenX = 0, cenY = 0, cenZ = 0, cenRadius = -1.0;
@@ -108,6 +110,7 @@ int main(int argc, char **argv) {
         else if (flag(argv[a], "--height", v)) height = (size_t)atoll(v.c_str());
         else if (flag(argv[a], "--device", v)) device = atoi(v.c_str());
         else if (flag(argv[a], "--seed", v)) seed = strtoull(v.c_str(), nullptr, 10);
+        else if (flag(argv[a], "--amat", v)) sAmat = v;
         else if (flag(argv[a], "--rank", v)) rank = atoi(v.c_str());
         else if (flag(argv[a], "--world", v)) world = atoi(v.c_str());
         else if (strcmp(argv[a], "-gm") == 0 || (flag(argv[a], "-gm", v) && v != "false" && v != "0")) {
@@ -145,7 +148,7 @@ int main(int argc, char **argv) {
     const std::string sSfM_data = sSfMDir + (sSfMDir.back() == '/' ? "" : "/") + "sfm_data.json";
     try {
         if (world < 1 || rank < 0 || rank >= world) { std::cerr << "bad --rank/--world\n"; return 1; }
-        LocalizeEngine engine(sSfMDir, sMatchesDir, "", fDistRatio, ransacRound, geomPrec, false, 0, knnbow,
+        LocalizeEngine engine(sSfMDir, sMatchesDir, sAmat, fDistRatio, ransacRound, geomPrec, false, 0, knnbow,
                               device >= 0 ? device : rank);
         if (cenRadius > 0) engine.setLocalViews({cenX, cenY, cenZ}, cenRadius);
         const Intrinsic &cam = engine.scene().intrinsics.at(0);

@@ -131,3 +131,53 @@ def test_bow_preselection(tmp_path):
     assert np.linalg.norm(np.array(j["t"]) - queries[0]["center"]) < 0.05
     r = run(qdir, sfm, mdir, out, "-r=25", "-k=50")                 # more than there are views: no narrowing
     assert r.returncode == 0 and "selected local views by bow" not in r.stdout and "localized 1 of 1" in r.stdout
+
+
+def test_global_coordinates_through_the_a_matrix(tmp_path):
+    """--amat (the server's aMatFile, LocalizeEngine.cc:113-144): the model is moved to global
+    coordinates first, so the pose comes out there: centre = A [c; 1], R = R_local A_R^T."""
+    import cv2
+    sc, sfm, mdir, qdir, out, queries, lm_ids = make_project(tmp_path, seed=14, n_queries=1)
+    rng = np.random.default_rng(3)
+    Q = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+    Q *= np.sign(np.linalg.det(Q))
+    A = np.hstack([Q, np.array([[5.0], [-2.0], [1.5]])])          # a rigid motion keeps the intrinsics valid
+    fs = cv2.FileStorage(str(tmp_path / "A.yml"), cv2.FILE_STORAGE_WRITE)
+    fs.write("A", A); fs.release()
+    r = run(qdir, sfm, mdir, out, "-r=25", "--amat=" + str(tmp_path / "A.yml"))
+    assert r.returncode == 0 and "localized 1 of 1" in r.stdout, r.stdout + r.stderr
+    j = json.loads((out / "q000.json").read_text())
+    want_c = A[:, :3] @ queries[0]["center"] + A[:, 3]
+    assert np.linalg.norm(np.array(j["t"]) - want_c) < 0.05
+    assert np.abs(np.array(j["R"]) - queries[0]["R"] @ Q.T).max() < 5e-3
+
+
+def test_radial_distortion_is_removed_before_matching_geometry(tmp_path):
+    """A pinhole_radial_k3 camera: the .feat positions of views and query are distorted pixels; the
+    engine undistorts them (get_ud_pixel) for the geometric filter and the resection."""
+    k3 = (0.12, -0.05, 0.01)
+    sc = synth.localization_scene(12, 700, 3000, 800, 15, K=K_EQ)
+    f, cx, cy = K_EQ[0, 0], K_EQ[0, 2], K_EQ[1, 2]
+
+    def distort(xy):
+        a = (xy[:, 0] - cx) / f; b = (xy[:, 1] - cy) / f
+        r2 = a * a + b * b
+        c = 1 + k3[0] * r2 + k3[1] * r2 ** 2 + k3[2] * r2 ** 3
+        return np.stack([f * a * c + cx, f * b * c + cy], axis=1)
+
+    sfm = tmp_path / "sfm"; mdir = tmp_path / "matches"; qdir = tmp_path / "query"; out = tmp_path / "out"
+    for d in (sfm, mdir, qdir, out):
+        d.mkdir()
+    names = ["frame%04d" % k for k in range(12)]
+    off = sc["seg_offsets"]
+    for k in range(12):
+        hostlib.write_desc_numpy(str(mdir / (names[k] + ".desc")), sc["rows"][int(off[k]):int(off[k + 1]), :61])
+        hostlib.write_feat(str(mdir / (names[k] + ".feat")), distort(sc["map_xy"][int(off[k]):int(off[k + 1])]))
+    hostlib.write_sfm_data(str(sfm / "sfm_data.json"), sc, names, disto=k3)
+    hostlib.write_desc_numpy(str(qdir / "q000.desc"), sc["q_desc"][:, :61])
+    hostlib.write_feat(str(qdir / "q000.feat"), distort(sc["q_xy"]))
+    r = run(qdir, sfm, mdir, out, "-r=25")
+    assert r.returncode == 0 and "localized 1 of 1" in r.stdout, r.stdout + r.stderr
+    j = json.loads((out / "q000.json").read_text())
+    assert np.linalg.norm(np.array(j["t"]) - sc["center"]) < 0.05       # with the distortion left in: decimetres off
+    assert np.abs(np.array(j["R"]) - sc["R"]).max() < 5e-3

@@ -48,3 +48,13 @@ def test_no_device_is_a_loud_failure():
         HuloGpu(0)
     assert e.value.status == _lib.ERR_CUDA
     assert "no CPU fallback" in str(e.value)
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/hulo_gpu.h must compile as C99 on its own."""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "hulo_gpu.h"\nint main(void) { return hulo_device_count() < 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-c", str(src), "-o", str(tmp_path / "hdr.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

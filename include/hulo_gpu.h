@@ -278,7 +278,7 @@ int hulo_engine_set_keypoints(hulo_engine *e, const double *map_xy, const int32_
 int hulo_engine_set_query_size(hulo_engine *e, int query_w, int query_h);
 /* Switch hulo::geometricMatch (LocalizeEngine.cc:458) on or off (off after hulo_engine_create):
  * ransac_round = mRansacRound, precision_px = mRansacPrecision of the LocalizeEngine
- * constructor (LocalizeEngine.cc:84-91).  Guided matching is not implemented. */
+ * constructor (LocalizeEngine.cc:84-91).  Guided matching is available for the reconstruction stage only (hulo_guided_match); the engine runs the unguided filter. */
 int hulo_engine_configure_geometric(hulo_engine *e, int enabled, size_t ransac_round, double precision_px);
 
 /* LocalizeEngine::localize from the putative matching on (LocalizeEngine.cc:423-602) for one

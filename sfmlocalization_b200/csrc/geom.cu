@@ -44,6 +44,9 @@ namespace hulo {
 namespace {
 
 constexpr int kGeoThreads = 128;
+#ifndef HULO_GEO_MIN_BLOCKS
+#define HULO_GEO_MIN_BLOCKS 4      // 128 registers with a few spills in the solver: four pairs per SM beat two at 254 registers
+#endif
 constexpr int kGeoAhead = 32;              // iterations whose 7-point problems are solved together
 constexpr uint32_t kGeoMaxMatches = 16384; // per pair: 128 KB of sort keys
 constexpr uint32_t kGeoRankSortMax = 3 * kGeoThreads;   // counting sort up to here, bitonic network above
@@ -429,7 +432,7 @@ __device__ ModelScore score_model_block(const PairCtx &c, const double *F, unsig
 // the new pool.  While iterating only the SET of inliers of the best model is needed (the pool is
 // kept in index order), so it is rebuilt from the model when a commit needs it, and the
 // residual-ordered inlier list is produced once at the end.
-__global__ void __launch_bounds__(kGeoThreads) fmatrix_acransac_kernel(GeoParams g) {
+__global__ void __launch_bounds__(kGeoThreads, HULO_GEO_MIN_BLOCKS) fmatrix_acransac_kernel(GeoParams g) {
     extern __shared__ unsigned long long s_keys[];          // block buffer: pow2 >= N keys (>= 512)
     __shared__ unsigned long long s_wkeys[kGeoWarps][kGeoWarpKeys];
     __shared__ double s_models[kGeoAhead * 27];

@@ -200,6 +200,20 @@ int hulo_resect_acransac_sequential(hulo_gpu *h, const double *x2d, const double
                                     const double *K, size_t max_iter, uint64_t seed, double *P,
                                     int32_t *inliers, size_t *n_inliers, double *error_max, int *found);
 
+/* Many independent resections in one call: all views of a reconstruction re-resected against its
+ * structure (OpenMVG_BA/src/adjust_sfm_data.cpp:91-146 -- an omp loop around
+ * SfM_Localizer::Localize at :135-137), or the queries of a server batch.  Problem p owns the
+ * correspondences [offsets[p], offsets[p+1]) of x2d (total x 2) / X3d (total x 3), the intrinsics
+ * K + 9 p and the seed seeds[p] (seeds == NULL: seed + 1000003 p).  Each problem runs exactly the
+ * schedule of hulo_resect_acransac -- the results are bit-identical to n_problems single calls --
+ * but one step of all problems still running is one wave on the device (one P3P launch, one
+ * scoring launch per size class, one first-minimum launch, one copy back).  Outputs: P (n x 12),
+ * inliers of problem p at inliers + offsets[p] (capacity: its N), n_inliers, error_max, found (n). */
+int hulo_resect_acransac_batch(hulo_gpu *h, size_t n_problems, const uint64_t *offsets,
+                               const double *x2d, const double *X3d, const double *K, size_t max_iter,
+                               uint64_t seed, const uint64_t *seeds, double *P, int32_t *inliers,
+                               uint64_t *n_inliers, double *error_max, int32_t *found);
+
 /* --------------------------------------------- K3: F-matrix geometric filter */
 
 /* hulo::geometricMatch, MatchUtils.cpp:372-420 (decl MatchUtils.h:66-72): OpenMVG's

@@ -21,7 +21,9 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "context.cuh"
@@ -137,9 +139,11 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(
 // last three merges) go through shared memory -- 6 block barriers instead of one per sub-stage (66
 // for 2048 elements), and no strided shared-memory traffic (the ncu profile of score_kernel:
 // 73 % issue slots, LSU 50 %, 80 M bank conflicts, warps waiting on short scoreboard).
+// The block's work for hypothesis h, shared by the single-problem kernel and the batched one (so a
+// problem scores bit-identically through either).
 template <int E>
-__global__ void __launch_bounds__(kScoreThreads) score_kernel_reg(
-    const double *__restrict__ models, uint32_t H, const double *__restrict__ x2dn,
+__device__ __forceinline__ void score_reg_block(
+    const uint32_t h, const double *__restrict__ models, const double *__restrict__ x2dn,
     const double *__restrict__ X3d, uint32_t N, const float *__restrict__ logc_n,
     const float *__restrict__ logc_k, double loge0, double logalpha0, float thr2, double *__restrict__ out_nfa,
     int32_t *__restrict__ out_k, float *__restrict__ out_errk, int32_t *__restrict__ out_ninl) {
@@ -150,8 +154,6 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel_reg(
     __shared__ double s_M[12];
     __shared__ NfaMin s_red[kScoreThreads / 32];
     __shared__ int s_cnt[kScoreThreads / 32];
-    const uint32_t h = blockIdx.x;
-    if (h >= H) return;
     const int tid = threadIdx.x;
     if (tid < 12) s_M[tid] = models[(size_t)h * 12 + tid];
     __syncthreads();
@@ -254,11 +256,50 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel_reg(
     }
 }
 
+template <int E>
+__global__ void __launch_bounds__(kScoreThreads) score_kernel_reg(
+    const double *__restrict__ models, uint32_t H, const double *__restrict__ x2dn,
+    const double *__restrict__ X3d, uint32_t N, const float *__restrict__ logc_n,
+    const float *__restrict__ logc_k, double loge0, double logalpha0, float thr2, double *__restrict__ out_nfa,
+    int32_t *__restrict__ out_k, float *__restrict__ out_errk, int32_t *__restrict__ out_ninl) {
+    if (blockIdx.x >= H) return;
+    score_reg_block<E>(blockIdx.x, models, x2dn, X3d, N, logc_n, logc_k, loge0, logalpha0, thr2, out_nfa, out_k,
+                       out_errk, out_ninl);
+}
+
+// ---- many resection problems in one launch (hulo_resect_acransac_batch)
+// One staged problem: where its correspondences and log-binomial tables live in the arena.
+struct ResectDesc {
+    const double *x2dn, *X3d;
+    const float *logc_n, *logc_k;
+    double loge0, logalpha0;
+    uint32_t N, pad;
+};
+// One problem's share of a wave: its hypotheses are models[hyp_base .. hyp_base + 4 T) and, inside
+// the launch of its size class, the blocks [blk_off, next slot's blk_off).
+struct WaveSlot { uint32_t job, hyp_base, blk_off, pad; };
+
+template <int E>
+__global__ void __launch_bounds__(kScoreThreads) score_kernel_reg_batch(
+    const ResectDesc *__restrict__ desc, const WaveSlot *__restrict__ slots, uint32_t n_slots,
+    const double *__restrict__ models, double *__restrict__ out_nfa) {
+    // slot of this block: last one with blk_off <= blockIdx.x (uniform over the block, cached)
+    uint32_t lo = 0, hi = n_slots;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (slots[mid].blk_off <= blockIdx.x) lo = mid; else hi = mid;
+    }
+    const WaveSlot sl = slots[lo];
+    const ResectDesc d = desc[sl.job];
+    score_reg_block<E>(sl.hyp_base + (blockIdx.x - sl.blk_off), models, d.x2dn, d.X3d, d.N, d.logc_n, d.logc_k,
+                       d.loge0, d.logalpha0, -1.0f, out_nfa, nullptr, nullptr, nullptr);
+}
+
 // First minimum of the H scores (strict <: the earliest hypothesis wins ties, like the sequential
 // update rule) and its model, gathered into one small record so a batch costs one D2H copy:
 // out = {nfa, (double)index, model[12]}; index = -1 when every score is +inf / NaN.
-__global__ void __launch_bounds__(256) argmin_kernel(const double *__restrict__ nfa, uint32_t H,
-                                                     const double *__restrict__ models, double *__restrict__ out) {
+__device__ __forceinline__ void argmin_block(const double *__restrict__ nfa, uint32_t H,
+                                             const double *__restrict__ models, double *__restrict__ out) {
     __shared__ double s_v[8];
     __shared__ uint32_t s_i[8];
     double v = INFINITY;
@@ -281,6 +322,18 @@ __global__ void __launch_bounds__(256) argmin_kernel(const double *__restrict__ 
         out[1] = idx == 0xFFFFFFFFu ? -1.0 : (double)idx;
         for (int k = 0; k < 12; ++k) out[2 + k] = idx == 0xFFFFFFFFu ? 0.0 : models[(size_t)idx * 12 + k];
     }
+}
+__global__ void __launch_bounds__(256) argmin_kernel(const double *__restrict__ nfa, uint32_t H,
+                                                     const double *__restrict__ models, double *__restrict__ out) {
+    argmin_block(nfa, H, models, out);
+}
+// one block per problem of the wave: record a = first minimum over its own hypotheses
+__global__ void __launch_bounds__(256) argmin_batch_kernel(const double *__restrict__ nfa,
+                                                           const uint2 *__restrict__ ranges,
+                                                           const double *__restrict__ models,
+                                                           double *__restrict__ out) {
+    const uint2 r = ranges[blockIdx.x];
+    argmin_block(nfa + r.x, r.y, models + (size_t)r.x * 12, out + (size_t)blockIdx.x * 14);
 }
 
 // residuals in pixels (sqrt(e) * fx), H x N, for the parity test of the projection arithmetic
@@ -541,7 +594,7 @@ struct Problem {
 // scratch0: x2dn | X3d | logc_n | logc_k   (problem);  scratch1: models; scratch2: outputs; scratch3: triplets
 int stage_problem(hulo_gpu *h, const std::vector<double> &x2dn, const double *X3d, size_t N, Problem &pb) {
     std::vector<float> &lcn = pb.lcn, &lck = pb.lck;
-    make_logcombi(N, lcn, lck);
+    if (lcn.size() != N + 1 || lck.size() != N + 1) make_logcombi(N, lcn, lck);   // else: handed in by the caller
     const size_t bytes = N * 5 * sizeof(double) + 2 * (N + 1) * sizeof(float) + 64;
     HULO_CUDA(h->scratch0.reserve(bytes));
     pb.N = N;
@@ -622,6 +675,182 @@ void sample3(uint64_t &state, size_t total, size_t out[3]) {
         for (int k = i; k > j; --k) out[k] = out[k - 1];
         out[j] = r;
     }
+}
+
+
+// ---- one AC-RANSAC resection as a resumable schedule
+// The host side of hulo_resect_acransac: which triplets to draw next, and what a scored batch means.
+// The device work of a step (P3P over the drawn triplets, K2 scoring, first minimum) is done by the
+// caller -- alone for one problem, or for a whole wave of problems at once
+// (hulo_resect_acransac_batch) -- and comes back as the record {nfa, index, model[12]}.
+//
+// Schedule of the sequential algorithm: 10 % of the iterations are reserved; once a meaningful model
+// (NFA < 0) exists the sampler draws from its inliers and only the reserved iterations remain.
+// Batched: global batches until a meaningful model appears (at most max_iter - reserve draws), then
+// one batch of `reserve` draws from the inliers.  The first batches are small and grow (64, 128, 256,
+// 512, 512, ...): the sequential algorithm leaves the global phase at its first meaningful model,
+// which on clean correspondence sets is one of the very first draws, so a large first batch would
+// only score models it discards.
+struct ResectJob {
+    enum Phase { kGlobal, kFocused, kReserveGlobal, kDone };
+    struct EI { double e; size_t i; };
+
+    size_t N = 0;
+    const double *X3d = nullptr;
+    const double *K = nullptr;
+    std::vector<double> x2dn;
+    std::vector<float> lcn, lck;
+    double loge0 = 0, logalpha0 = 0;
+
+    Phase phase = kDone;
+    size_t reserve = 0, global_budget = 0, batch = 0, drawn = 0, last_T = 0;
+    uint64_t rng = 0;
+    std::vector<size_t> pool;
+    double best_nfa = INFINITY, final_nfa = INFINITY;
+    double best_model[12] = {0}, prev_model[12] = {0};
+    double prev_nfa = INFINITY;
+    size_t best_k = 0;
+    double best_err = 0.0;
+    std::vector<EI> ei;
+
+    void init(const double *x2d, const double *X3d_, size_t N_, const double *K_, size_t max_iter, uint64_t seed) {
+        N = N_; X3d = X3d_; K = K_;
+        normalize_points(x2d, N, K, x2dn);
+        make_logcombi(N, lcn, lck);
+        loge0 = log10(4.0 * (double)(N > 3 ? N - 3 : 1));
+        logalpha0 = log10(M_PI);
+        reserve = max_iter / 10;
+        global_budget = max_iter - reserve;
+        batch = std::min<size_t>(global_budget, 64);
+        rng = seed;
+        pool.resize(N);
+        for (size_t i = 0; i < N; ++i) pool[i] = i;
+        ei.resize(N);
+        phase = kGlobal;
+    }
+    // triplets of the next step (0: finished)
+    size_t next_T() const {
+        switch (phase) {
+            case kGlobal: return std::min(batch, global_budget - drawn);
+            case kFocused: case kReserveGlobal: return reserve;
+            default: return 0;
+        }
+    }
+    // draws T triplets; indices are offset by `base` (the problem's first row in a shared arena)
+    void draw(size_t T, uint32_t *tri, uint32_t base) {
+        for (size_t t = 0; t < T; ++t) {
+            size_t pos[3];
+            sample3(rng, pool.size(), pos);
+            for (int s = 0; s < 3; ++s) tri[3 * t + s] = base + (uint32_t)pool[pos[s]];
+        }
+        last_T = T;
+    }
+    // Final scoring of a model in fp64 on the host: residuals, (residual, index) order, NFA.
+    double finalize(const double *M) {
+        for (size_t i = 0; i < N; ++i) {
+            const double *X = X3d + 3 * i;
+            const double u = M[0] * X[0] + M[1] * X[1] + M[2] * X[2] + M[3];
+            const double v = M[4] * X[0] + M[5] * X[1] + M[6] * X[2] + M[7];
+            const double w = M[8] * X[0] + M[9] * X[1] + M[10] * X[2] + M[11];
+            const double dx = u / w - x2dn[2 * i], dy = v / w - x2dn[2 * i + 1];
+            double e = dx * dx + dy * dy;
+            if (!(e == e)) e = INFINITY;
+            ei[i] = EI{e, i};
+        }
+        std::sort(ei.begin(), ei.end(), [](const EI &a, const EI &b) { return a.e < b.e || (a.e == b.e && a.i < b.i); });
+        double bn = INFINITY;
+        size_t bk = 3;
+        for (size_t k = 4; k <= N; ++k) {
+            if (!(ei[k - 1].e < INFINITY)) break;
+            const double logalpha = logalpha0 + log10(ei[k - 1].e + (double)FLT_EPSILON);
+            const double nfa = loge0 + logalpha * (double)(k - 3) + (double)lcn[k] + (double)lck[k];
+            if (nfa < bn) { bn = nfa; bk = k; }
+        }
+        best_k = bk;
+        best_err = bk >= 1 ? ei[bk - 1].e : 0.0;
+        return bn;
+    }
+    // the scored step comes back: rec = {nfa, index or -1, model[12]} of its first minimum
+    void absorb(const double *rec) {
+        // sequential update rule: strict <, so the earliest hypothesis wins ties
+        if (rec[1] >= 0.0 && rec[0] < best_nfa) {
+            best_nfa = rec[0];
+            memcpy(best_model, rec + 2, 12 * sizeof(double));
+        }
+        if (phase == kGlobal) {
+            drawn += last_T;
+            if (!(best_nfa < 0.0) && drawn < global_budget) {
+                batch = std::min<size_t>(batch * 2, 512);
+                return;
+            }
+            final_nfa = INFINITY;
+            if (best_nfa < INFINITY) final_nfa = finalize(best_model);
+            if (reserve > 0 && final_nfa < 0.0 && best_k >= 3) {
+                // focused sampling among the inliers of the best model so far
+                pool.resize(best_k);
+                for (size_t i = 0; i < best_k; ++i) pool[i] = ei[i].i;
+                memcpy(prev_model, best_model, sizeof prev_model);
+                prev_nfa = best_nfa;
+                phase = kFocused;
+            } else if (reserve > 0 && !(final_nfa < 0.0)) {
+                phase = kReserveGlobal;   // no meaningful model yet: the reserved iterations keep sampling globally
+            } else {
+                phase = kDone;
+            }
+        } else if (phase == kFocused) {
+            if (best_nfa < prev_nfa) {
+                const double keep_nfa = final_nfa;
+                const size_t keep_k = best_k;
+                const double keep_err = best_err;
+                std::vector<EI> keep_ei(ei.begin(), ei.begin() + keep_k);
+                const double cand = finalize(best_model);
+                if (cand < keep_nfa) {
+                    final_nfa = cand;
+                } else {   // fp32 ranking disagreed with the fp64 rescoring: keep the earlier model
+                    memcpy(best_model, prev_model, sizeof prev_model);
+                    best_k = keep_k; best_err = keep_err;
+                    std::copy(keep_ei.begin(), keep_ei.end(), ei.begin());
+                }
+            }
+            phase = kDone;
+        } else if (phase == kReserveGlobal) {
+            if (best_nfa < INFINITY) final_nfa = finalize(best_model);
+            phase = kDone;
+        }
+    }
+    // outputs of SfM_Localizer::Localize
+    void emit(double *P, int32_t *inliers, size_t *n_inliers, double *error_max, int *found) const {
+        *n_inliers = 0; *error_max = 0.0; *found = 0;
+        if (!(final_nfa < 0.0)) return;   // minNFA >= 0: inliers cleared, not found
+        // Unnormalize: P = K * model ; error in pixels = sqrt(e) / Kinv(0,0)
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 4; ++c)
+                P[4 * r + c] = K[3 * r] * best_model[c] + K[3 * r + 1] * best_model[4 + c] + K[3 * r + 2] * best_model[8 + c];
+        *error_max = sqrt(best_err) * K[0];
+        for (size_t i = 0; i < best_k; ++i) inliers[i] = (int32_t)ei[i].i;
+        *n_inliers = best_k;
+        // SfM_Localizer::Localize: resection succeeded iff #inliers > 2.5 * MINIMUM_SAMPLES
+        *found = (double)best_k > 2.5 * 3.0 ? 1 : 0;
+    }
+};
+
+template <class F>
+void parallel_for(size_t n, size_t grain, F f) {
+    const size_t hw = std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), 32));
+    const size_t nt = std::min(hw, (n + grain - 1) / std::max<size_t>(grain, 1));
+    if (nt <= 1) { for (size_t i = 0; i < n; ++i) f(i); return; }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    auto body = [&]() {
+        for (;;) {
+            const size_t b = next.fetch_add(grain);
+            if (b >= n) return;
+            for (size_t i = b; i < std::min(n, b + grain); ++i) f(i);
+        }
+    };
+    for (size_t t = 1; t < nt; ++t) th.emplace_back(body);
+    body();
+    for (auto &t : th) t.join();
 }
 
 }  // namespace
@@ -734,38 +963,18 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
     // ACRANSAC: nothing to do with N <= MINIMUM_SAMPLES
     if (N <= 3 || max_iter == 0) return HULO_OK;
     HULO_CUDA(cudaSetDevice(h->device));
-    std::vector<double> x2dn;
-    normalize_points(x2d, N, K, x2dn);
+    ResectJob job;
+    job.init(x2d, X3d, N, K, max_iter, seed);
     Problem pb;
-    int rc = stage_problem(h, x2dn, X3d, N, pb);
+    pb.lcn = job.lcn;
+    pb.lck = job.lck;
+    int rc = stage_problem(h, job.x2dn, X3d, N, pb);
     if (rc != HULO_OK) return rc;
 
-    // Schedule of the sequential algorithm: 10 % of the iterations are reserved; once a
-    // meaningful model (NFA < 0) exists the sampler draws from its inliers and only the reserved
-    // iterations remain.  Batched: global batches until a meaningful model appears (at most
-    // max_iter - reserve draws), then one batch of `reserve` draws from the inliers.
-    const size_t reserve = max_iter / 10;
-    const size_t global_budget = max_iter - reserve;
-    // the first batches are small and grow (64, 128, 256, 512, 512, ...): the sequential algorithm
-    // leaves the global phase at its first meaningful model, which on clean correspondence sets is
-    // one of the very first draws, so a large first batch would only score models it discards
-    size_t batch = std::min<size_t>(global_budget, 64);
-    uint64_t rng = seed;
-    std::vector<size_t> pool(N);
-    for (size_t i = 0; i < N; ++i) pool[i] = i;
-
-    double best_nfa = INFINITY;
-    double best_model[12] = {0};
     std::vector<uint32_t> tri;
-    std::vector<double> h_model(12);
-
-    auto run_batch = [&](size_t T) -> int {
+    for (size_t T = job.next_T(); T > 0; T = job.next_T()) {
         tri.resize(3 * T);
-        for (size_t t = 0; t < T; ++t) {
-            size_t pos[3];
-            sample3(rng, pool.size(), pos);
-            for (int s = 0; s < 3; ++s) tri[3 * t + s] = (uint32_t)pool[pos[s]];
-        }
+        job.draw(T, tri.data(), 0);
         HULO_CUDA(h->scratch3.reserve(T * 3 * sizeof(uint32_t)));
         HULO_CUDA(h->scratch1.reserve(T * 48 * sizeof(double) + T * sizeof(int32_t)));
         HULO_CUDA(cudaMemcpyAsync(h->scratch3.ptr, tri.data(), T * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
@@ -776,8 +985,8 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
         HULO_CUDA(cudaGetLastError());
         h->launches++;
         ScoreOut o;
-        int rc2 = launch_score(h, pb, d_models, 4 * T, -1.0f, o);
-        if (rc2 != HULO_OK) return rc2;
+        rc = launch_score(h, pb, d_models, 4 * T, -1.0f, o);
+        if (rc != HULO_OK) return rc;
         // first minimum of the batch and its model in one record, one copy, one synchronisation
         double rec[14];
         double *d_rec = reinterpret_cast<double *>(o.ninl + 4 * T + 2);
@@ -787,96 +996,193 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
         h->launches++;
         HULO_CUDA(cudaMemcpyAsync(rec, d_rec, sizeof rec, cudaMemcpyDeviceToHost, h->stream));
         HULO_CUDA(cudaStreamSynchronize(h->stream));
-        // sequential update rule: strict <, so the earliest hypothesis wins ties
-        if (rec[1] >= 0.0 && rec[0] < best_nfa) {
-            best_nfa = rec[0];
-            memcpy(best_model, rec + 2, 12 * sizeof(double));
-        }
-        return HULO_OK;
-    };
-
-    // Final scoring of a model in fp64 on the host: residuals, (residual, index) order, NFA.
-    const std::vector<float> &lcn = pb.lcn, &lck = pb.lck;
-    struct EI { double e; size_t i; };
-    std::vector<EI> ei(N);
-    size_t best_k = 0;
-    double best_err = 0.0;
-    auto finalize = [&](const double *M) -> double {
-        for (size_t i = 0; i < N; ++i) {
-            const double *X = X3d + 3 * i;
-            const double u = M[0] * X[0] + M[1] * X[1] + M[2] * X[2] + M[3];
-            const double v = M[4] * X[0] + M[5] * X[1] + M[6] * X[2] + M[7];
-            const double w = M[8] * X[0] + M[9] * X[1] + M[10] * X[2] + M[11];
-            const double dx = u / w - x2dn[2 * i], dy = v / w - x2dn[2 * i + 1];
-            double e = dx * dx + dy * dy;
-            if (!(e == e)) e = INFINITY;
-            ei[i] = EI{e, i};
-        }
-        std::sort(ei.begin(), ei.end(), [](const EI &a, const EI &b) { return a.e < b.e || (a.e == b.e && a.i < b.i); });
-        double bn = INFINITY;
-        size_t bk = 3;
-        for (size_t k = 4; k <= N; ++k) {
-            if (!(ei[k - 1].e < INFINITY)) break;
-            const double logalpha = pb.logalpha0 + log10(ei[k - 1].e + (double)FLT_EPSILON);
-            const double nfa = pb.loge0 + logalpha * (double)(k - 3) + (double)lcn[k] + (double)lck[k];
-            if (nfa < bn) { bn = nfa; bk = k; }
-        }
-        best_k = bk;
-        best_err = bk >= 1 ? ei[bk - 1].e : 0.0;
-        return bn;
-    };
-
-    size_t drawn = 0;
-    while (drawn < global_budget) {
-        const size_t T = std::min(batch, global_budget - drawn);
-        rc = run_batch(T);
-        if (rc != HULO_OK) return rc;
-        drawn += T;
-        if (best_nfa < 0.0) break;
-        batch = std::min<size_t>(batch * 2, 512);
+        job.absorb(rec);
     }
-    double final_nfa = INFINITY;
-    if (best_nfa < INFINITY) final_nfa = finalize(best_model);
-    if (reserve > 0 && final_nfa < 0.0 && best_k >= 3) {
-        // focused sampling among the inliers of the best model so far
-        pool.resize(best_k);
-        for (size_t i = 0; i < best_k; ++i) pool[i] = ei[i].i;
-        double prev_model[12];
-        memcpy(prev_model, best_model, sizeof prev_model);
-        const double prev_nfa = best_nfa;
-        rc = run_batch(reserve);
-        if (rc != HULO_OK) return rc;
-        if (best_nfa < prev_nfa) {
-            const double keep_nfa = final_nfa;
-            const size_t keep_k = best_k;
-            const double keep_err = best_err;
-            std::vector<EI> keep_ei(ei.begin(), ei.begin() + keep_k);
-            const double cand = finalize(best_model);
-            if (cand < keep_nfa) {
-                final_nfa = cand;
-            } else {   // fp32 ranking disagreed with the fp64 rescoring: keep the earlier model
-                memcpy(best_model, prev_model, sizeof prev_model);
-                best_k = keep_k; best_err = keep_err;
-                std::copy(keep_ei.begin(), keep_ei.end(), ei.begin());
+    job.emit(P, inliers, n_inliers, error_max, found);
+    return HULO_OK;
+}
+
+// Many independent resections at once: the views of a reconstruction re-resected against its own
+// structure (OpenMVG_BA/src/adjust_sfm_data.cpp:91-146, an omp loop of SfM_Localizer::Localize), or
+// the queries of a server batch.  Every problem follows exactly the schedule of
+// hulo_resect_acransac with its own seed -- same draws, same kernels' arithmetic, same decisions,
+// so the results are bit-identical to n_problems single calls -- but a step of all problems still
+// running is ONE wave on the device: one P3P launch over all drawn triplets, one scoring launch
+// per size class (the register-resident sort is compiled per points-per-thread), one first-minimum
+// launch, one copy back.  The host part of a step (fp64 rescoring when a problem changes phase)
+// runs on the host threads.
+int hulo_resect_acransac_batch(hulo_gpu *h, size_t n_problems, const uint64_t *offsets, const double *x2d,
+                               const double *X3d, const double *K, size_t max_iter, uint64_t seed,
+                               const uint64_t *seeds, double *P, int32_t *inliers, uint64_t *n_inliers,
+                               double *error_max, int32_t *found) {
+    HULO_ARG(h != nullptr, "null handle");
+    if (n_problems == 0) return HULO_OK;
+    HULO_ARG(offsets != nullptr && K != nullptr && P != nullptr && n_inliers != nullptr && error_max != nullptr &&
+                 found != nullptr, "null argument");
+    const size_t total = (size_t)offsets[n_problems];
+    HULO_ARG(total == 0 || (x2d != nullptr && X3d != nullptr && inliers != nullptr), "null correspondences");
+    HULO_ARG(total < 0xFFFFFFFFull, "too many correspondences in one call");
+    for (size_t p = 0; p < n_problems; ++p) {
+        HULO_ARG(offsets[p] <= offsets[p + 1], "offsets must ascend");
+        HULO_ARG(offsets[p + 1] - offsets[p] <= kMaxPoints, "more than 32768 correspondences in one problem");
+        n_inliers[p] = 0; error_max[p] = 0.0; found[p] = 0;
+    }
+    HULO_CUDA(cudaSetDevice(h->device));
+    auto job_seed = [&](size_t p) { return seeds ? seeds[p] : seed + 1000003ull * (uint64_t)p; };
+
+    // problems the batched kernels take (register-resident sort: N <= 4096); the rest go one by one
+    std::vector<ResectJob> jobs(n_problems);
+    std::vector<uint32_t> batched, single;
+    const bool smem_sort = getenv("HULO_K2_SMEM_SORT") != nullptr;
+    for (size_t p = 0; p < n_problems; ++p) {
+        const size_t N = (size_t)(offsets[p + 1] - offsets[p]);
+        if (N <= 3 || max_iter == 0) continue;
+        if (N > 4096 || smem_sort) single.push_back((uint32_t)p); else batched.push_back((uint32_t)p);
+    }
+    parallel_for(batched.size(), 8, [&](size_t b) {
+        const size_t p = batched[b];
+        jobs[p].init(x2d + 2 * offsets[p], X3d + 3 * offsets[p], (size_t)(offsets[p + 1] - offsets[p]), K + 9 * p,
+                     max_iter, job_seed(p));
+    });
+
+    if (!batched.empty()) {
+        // ---- arena: normalised observations, points, log-binomial tables, descriptors
+        std::vector<double> h_x2dn(2 * total);
+        std::vector<uint64_t> tab_off(n_problems + 1, 0);
+        for (size_t p = 0; p < n_problems; ++p) tab_off[p + 1] = tab_off[p] + (jobs[p].phase != ResectJob::kDone ? jobs[p].N + 1 : 0);
+        std::vector<float> h_lcn(tab_off[n_problems]), h_lck(tab_off[n_problems]);
+        for (uint32_t p : batched) {
+            memcpy(h_x2dn.data() + 2 * offsets[p], jobs[p].x2dn.data(), jobs[p].x2dn.size() * sizeof(double));
+            memcpy(h_lcn.data() + tab_off[p], jobs[p].lcn.data(), (jobs[p].N + 1) * sizeof(float));
+            memcpy(h_lck.data() + tab_off[p], jobs[p].lck.data(), (jobs[p].N + 1) * sizeof(float));
+        }
+        const size_t b_x = 2 * total * sizeof(double), b_X = 3 * total * sizeof(double);
+        const size_t b_t = ((tab_off[n_problems] * sizeof(float) + 15) / 16) * 16;
+        HULO_CUDA(h->scratch0.reserve(b_x + b_X + 2 * b_t + n_problems * sizeof(ResectDesc) + 64));
+        double *d_x2dn = h->scratch0.as<double>();
+        double *d_X3d = d_x2dn + 2 * total;
+        float *d_lcn = reinterpret_cast<float *>(d_X3d + 3 * total);
+        float *d_lck = reinterpret_cast<float *>(reinterpret_cast<char *>(d_lcn) + b_t);
+        ResectDesc *d_desc = reinterpret_cast<ResectDesc *>(reinterpret_cast<char *>(d_lck) + b_t);
+        std::vector<ResectDesc> h_desc(n_problems);
+        for (size_t p = 0; p < n_problems; ++p) {
+            ResectDesc &d = h_desc[p];
+            d.x2dn = d_x2dn + 2 * offsets[p];
+            d.X3d = d_X3d + 3 * offsets[p];
+            d.logc_n = d_lcn + tab_off[p];
+            d.logc_k = d_lck + tab_off[p];
+            d.loge0 = jobs[p].loge0;
+            d.logalpha0 = jobs[p].logalpha0;
+            d.N = (uint32_t)jobs[p].N;
+            d.pad = 0;
+        }
+        HULO_CUDA(cudaMemcpyAsync(d_x2dn, h_x2dn.data(), b_x, cudaMemcpyHostToDevice, h->stream));
+        HULO_CUDA(cudaMemcpyAsync(d_X3d, X3d, b_X, cudaMemcpyHostToDevice, h->stream));
+        if (!h_lcn.empty()) {
+            HULO_CUDA(cudaMemcpyAsync(d_lcn, h_lcn.data(), h_lcn.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+            HULO_CUDA(cudaMemcpyAsync(d_lck, h_lck.data(), h_lck.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        }
+        HULO_CUDA(cudaMemcpyAsync(d_desc, h_desc.data(), n_problems * sizeof(ResectDesc), cudaMemcpyHostToDevice, h->stream));
+
+        // ---- waves
+        std::vector<uint32_t> active(batched), tri;
+        std::vector<uint64_t> trip_off;
+        std::vector<WaveSlot> slots;
+        std::vector<uint2> ranges;
+        std::vector<double> recs;
+        while (!active.empty()) {
+            const size_t na = active.size();
+            trip_off.assign(na + 1, 0);
+            for (size_t a = 0; a < na; ++a) trip_off[a + 1] = trip_off[a] + jobs[active[a]].next_T();
+            const size_t Ttot = (size_t)trip_off[na];
+            HULO_ARG(4 * Ttot < 0xFFFFFFFFull, "too many hypotheses in one wave");
+            tri.resize(3 * Ttot);
+            parallel_for(na, 16, [&](size_t a) {
+                ResectJob &j = jobs[active[a]];
+                j.draw(j.next_T(), tri.data() + 3 * trip_off[a], (uint32_t)offsets[active[a]]);
+            });
+            // slots grouped by size class (points per thread of the register-resident sort)
+            ranges.resize(na);
+            slots.clear();
+            uint32_t cls_begin[6] = {0}, cls_blocks[5] = {0};
+            for (int c = 0; c < 5; ++c) {
+                cls_begin[c] = (uint32_t)slots.size();
+                uint32_t blk = 0;
+                for (size_t a = 0; a < na; ++a) {
+                    const ResectJob &j = jobs[active[a]];
+                    uint32_t np = kScoreThreads;
+                    while (np < j.N) np <<= 1;
+                    const uint32_t e = np / kScoreThreads;
+                    const int cls = e == 1 ? 0 : e == 2 ? 1 : e == 4 ? 2 : e == 8 ? 3 : 4;
+                    if (cls != c) continue;
+                    const uint32_t nh = (uint32_t)(4 * (trip_off[a + 1] - trip_off[a]));
+                    slots.push_back(WaveSlot{active[a], (uint32_t)(4 * trip_off[a]), blk, 0});
+                    blk += nh;
+                }
+                cls_blocks[c] = blk;
             }
-        }
-    } else if (reserve > 0 && !(final_nfa < 0.0)) {
-        // no meaningful model yet: the reserved iterations keep sampling globally
-        rc = run_batch(reserve);
-        if (rc != HULO_OK) return rc;
-        if (best_nfa < INFINITY) final_nfa = finalize(best_model);
-    }
-    if (!(final_nfa < 0.0)) return HULO_OK;   // minNFA >= 0: inliers cleared, not found
+            cls_begin[5] = (uint32_t)slots.size();
+            for (size_t a = 0; a < na; ++a)
+                ranges[a] = make_uint2((uint32_t)(4 * trip_off[a]), (uint32_t)(4 * (trip_off[a + 1] - trip_off[a])));
 
-    // Unnormalize: P = K * model ; error in pixels = sqrt(e) / Kinv(0,0)
-    for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 4; ++c)
-            P[4 * r + c] = K[3 * r] * best_model[c] + K[3 * r + 1] * best_model[4 + c] + K[3 * r + 2] * best_model[8 + c];
-    *error_max = sqrt(best_err) * K[0];
-    for (size_t i = 0; i < best_k; ++i) inliers[i] = (int32_t)ei[i].i;
-    *n_inliers = best_k;
-    // SfM_Localizer::Localize: resection succeeded iff #inliers > 2.5 * MINIMUM_SAMPLES
-    *found = (double)best_k > 2.5 * 3.0 ? 1 : 0;
+            const size_t b_tri = ((3 * Ttot * sizeof(uint32_t) + 15) / 16) * 16;
+            const size_t b_slots = slots.size() * sizeof(WaveSlot);
+            HULO_CUDA(h->scratch3.reserve(b_tri + b_slots + na * sizeof(uint2) + 64));
+            uint32_t *d_tri = h->scratch3.as<uint32_t>();
+            WaveSlot *d_slots = reinterpret_cast<WaveSlot *>(reinterpret_cast<char *>(d_tri) + b_tri);
+            uint2 *d_ranges = reinterpret_cast<uint2 *>(reinterpret_cast<char *>(d_slots) + b_slots);
+            HULO_CUDA(h->scratch1.reserve(Ttot * 48 * sizeof(double) + Ttot * sizeof(int32_t)));
+            double *d_models = h->scratch1.as<double>();
+            int32_t *d_nm = reinterpret_cast<int32_t *>(d_models + Ttot * 48);
+            HULO_CUDA(h->scratch2.reserve((4 * Ttot + 14 * na) * sizeof(double)));
+            double *d_nfa = h->scratch2.as<double>();
+            double *d_rec = d_nfa + 4 * Ttot;
+            HULO_CUDA(cudaMemcpyAsync(d_tri, tri.data(), 3 * Ttot * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+            HULO_CUDA(cudaMemcpyAsync(d_slots, slots.data(), b_slots, cudaMemcpyHostToDevice, h->stream));
+            HULO_CUDA(cudaMemcpyAsync(d_ranges, ranges.data(), na * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
+            p3p_kernel<<<(unsigned)((Ttot + 127) / 128), 128, 0, h->stream>>>(d_tri, (uint32_t)Ttot, d_x2dn, d_X3d,
+                                                                            d_models, d_nm);
+            HULO_CUDA(cudaGetLastError());
+            h->launches++;
+#define HULO_K2_BATCH(C, EE)                                                                                        \
+    if (cls_blocks[C] > 0) {                                                                                        \
+        score_kernel_reg_batch<EE><<<cls_blocks[C], kScoreThreads, 0, h->stream>>>(                                 \
+            d_desc, d_slots + cls_begin[C], cls_begin[C + 1] - cls_begin[C], d_models, d_nfa);                      \
+        HULO_CUDA(cudaGetLastError());                                                                              \
+        h->launches++;                                                                                              \
+    }
+            HULO_K2_BATCH(0, 1) HULO_K2_BATCH(1, 2) HULO_K2_BATCH(2, 4) HULO_K2_BATCH(3, 8) HULO_K2_BATCH(4, 16)
+#undef HULO_K2_BATCH
+            argmin_batch_kernel<<<(unsigned)na, 256, 0, h->stream>>>(d_nfa, d_ranges, d_models, d_rec);
+            HULO_CUDA(cudaGetLastError());
+            h->launches++;
+            recs.resize(14 * na);
+            HULO_CUDA(cudaMemcpyAsync(recs.data(), d_rec, 14 * na * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            HULO_CUDA(cudaStreamSynchronize(h->stream));
+            parallel_for(na, 4, [&](size_t a) { jobs[active[a]].absorb(recs.data() + 14 * a); });
+            size_t keep = 0;
+            for (size_t a = 0; a < na; ++a)
+                if (jobs[active[a]].next_T() > 0) active[keep++] = active[a];
+            active.resize(keep);
+        }
+        for (uint32_t p : batched) {
+            size_t ni = 0;
+            int f = 0;
+            jobs[p].emit(P + 12 * p, inliers + offsets[p], &ni, error_max + p, &f);
+            n_inliers[p] = ni;
+            found[p] = f;
+        }
+    }
+    for (uint32_t p : single) {
+        size_t ni = 0;
+        int f = 0;
+        int rc = hulo_resect_acransac(h, x2d + 2 * offsets[p], X3d + 3 * offsets[p], (size_t)(offsets[p + 1] - offsets[p]),
+                                      K + 9 * p, max_iter, job_seed(p), P + 12 * p, inliers + offsets[p], &ni,
+                                      error_max + p, &f);
+        if (rc != HULO_OK) return rc;
+        n_inliers[p] = ni;
+        found[p] = f;
+    }
     return HULO_OK;
 }
 

@@ -279,6 +279,27 @@ class HuloGpu:
                                             _ptr(inl), C.byref(n_inl), C.byref(emax), C.byref(found)))
         return dict(found=bool(found.value), P=P, inliers=inl[:n_inl.value].copy(), error_max=emax.value)
 
+    def resect_acransac_batch(self, x2d, X3d, offsets, K, max_iter=4096, seed=1, seeds=None):
+        """hulo_resect_acransac_batch -> list of dict(found, P, inliers, error_max), one per problem.
+        K: (n, 3, 3) or one (3, 3) shared by all problems."""
+        x2d = np.ascontiguousarray(x2d, np.float64).reshape(-1, 2)
+        X3d = np.ascontiguousarray(X3d, np.float64).reshape(-1, 3)
+        off = np.ascontiguousarray(offsets, np.uint64)
+        n = len(off) - 1
+        K = np.asarray(K, np.float64)
+        K = np.ascontiguousarray(np.broadcast_to(K.reshape(-1, 3, 3), (max(n, 1), 3, 3)))
+        if seeds is not None:
+            seeds = np.ascontiguousarray(seeds, np.uint64)
+        total = int(off[-1]) if n > 0 else 0
+        P = np.zeros((max(n, 1), 3, 4)); inl = np.empty(max(total, 1), np.int32)
+        ninl = np.zeros(max(n, 1), np.uint64); emax = np.zeros(max(n, 1)); found = np.zeros(max(n, 1), np.int32)
+        check(self.lib.hulo_resect_acransac_batch(self.h, n, _ptr(off), _ptr(x2d), _ptr(X3d), _ptr(K), max_iter, seed,
+                                                  _ptr(seeds), _ptr(P), _ptr(inl), _ptr(ninl), _ptr(emax),
+                                                  _ptr(found)))
+        return [dict(found=bool(found[p]), P=P[p].copy(),
+                     inliers=inl[int(off[p]):int(off[p]) + int(ninl[p])].copy(), error_max=float(emax[p]))
+                for p in range(n)]
+
     # -- K3
     def geometric_filter(self, xI, xJ, pair_offsets, image_sizes, precision_px=4.0, max_iter=25, seed=1,
                          pair_seeds=None):

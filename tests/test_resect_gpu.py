@@ -166,3 +166,64 @@ def test_sequential_schedule_degenerate_inputs(gpu, orc):
     g = gpu.resect_acransac(sc["x2d"], sc["X3d"], sc["K"], max_iter=512, seed=3, sequential=True)
     o = orc.acransac(sc["x2d"], sc["X3d"], sc["K"], max_iter=512, seed=3)
     assert not g["found"] and len(g["inliers"]) == len(o["inliers"]) == 0
+
+
+# ---------------------------------------------------------------- many resections in one call
+def _batch_problems(specs, seed0=500):
+    scs = [synth.resection_scene(N, seed0 + i, outlier_frac=o) for i, (N, o) in enumerate(specs)]
+    off = np.zeros(len(scs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(s["x2d"]) for s in scs])
+    x2d = np.concatenate([s["x2d"] for s in scs]) if scs else np.zeros((0, 2))
+    X3d = np.concatenate([s["X3d"] for s in scs]) if scs else np.zeros((0, 3))
+    return scs, off, x2d, X3d
+
+
+def test_batch_resection_equals_single_calls(gpu):
+    """hulo_resect_acransac_batch runs every problem on the schedule of hulo_resect_acransac:
+    identical bits, whatever phases the problems of a wave are in.  The mix: clean sets (leave the
+    global phase in wave 1), outlier-heavy ones (several growing waves), pure outliers (never a
+    model: the reserved iterations stay global), every size class of the scoring kernel, sets too
+    small to resect, an empty one, and one above the register-sort limit (runs alone)."""
+    specs = [(100, 0.3), (700, 0.5), (2000, 0.7), (40, 0.0), (300, 1.0), (3, 0.0), (0, 0.0), (1500, 0.85),
+             (256, 0.2), (257, 0.6), (4096, 0.5), (4500, 0.4), (12, 0.5), (600, 0.9), (1024, 0.1), (5, 0.0)]
+    scs, off, x2d, X3d = _batch_problems(specs)
+    Ks = np.stack([s["K"] * (1.0 if i % 2 == 0 else 1.0) for i, s in enumerate(scs)])
+    Ks[1::2, 0, 0] *= 1.01          # per-problem intrinsics are honoured
+    seeds = np.arange(len(specs), dtype=np.uint64) * 7919 + 11
+    got = gpu.resect_acransac_batch(x2d, X3d, off, Ks, 4096, seeds=seeds)
+    n_found = 0
+    for p, sc in enumerate(scs):
+        want = gpu.resect_acransac(sc["x2d"], sc["X3d"], Ks[p], 4096, int(seeds[p]))
+        assert got[p]["found"] == want["found"], p
+        assert np.array_equal(got[p]["inliers"], want["inliers"]), p
+        assert got[p]["error_max"] == want["error_max"], p
+        if want["found"]:
+            assert np.array_equal(got[p]["P"], want["P"]), p
+            n_found += 1
+    assert n_found >= 9
+
+
+def test_batch_resection_default_seeds_and_small_budgets(gpu):
+    scs, off, x2d, X3d = _batch_problems([(200, 0.4)] * 5 + [(900, 0.6)] * 3, seed0=900)
+    for max_iter in (1, 9, 64, 1000):
+        got = gpu.resect_acransac_batch(x2d, X3d, off, scs[0]["K"], max_iter, seed=42)
+        for p, sc in enumerate(scs):
+            want = gpu.resect_acransac(sc["x2d"], sc["X3d"], sc["K"], max_iter, 42 + 1000003 * p)
+            assert got[p]["found"] == want["found"]
+            assert np.array_equal(got[p]["inliers"], want["inliers"])
+            if want["found"]:
+                assert np.array_equal(got[p]["P"], want["P"])
+    assert gpu.resect_acransac_batch(np.zeros((0, 2)), np.zeros((0, 3)), [0], scs[0]["K"]) == []
+
+
+def test_batch_resection_recovers_the_poses(gpu):
+    """400 views at once: every clean problem is localised to its true camera."""
+    specs = [(300 + 7 * (i % 40), 0.3 + 0.01 * (i % 30)) for i in range(400)]
+    scs, off, x2d, X3d = _batch_problems(specs, seed0=2000)
+    got = gpu.resect_acransac_batch(x2d, X3d, off, scs[0]["K"], 4096, seed=3)
+    for p, sc in enumerate(scs):
+        assert got[p]["found"], p
+        M = np.linalg.inv(sc["K"]) @ got[p]["P"]
+        M /= np.cbrt(np.linalg.det(M[:, :3]))
+        C = -M[:, :3].T @ M[:, 3]
+        assert np.linalg.norm(C - (-sc["R"].T @ sc["t"])) < 0.05, p

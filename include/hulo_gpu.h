@@ -214,6 +214,11 @@ int hulo_resect_acransac_batch(hulo_gpu *h, size_t n_problems, const uint64_t *o
                                uint64_t seed, const uint64_t *seeds, double *P, int32_t *inliers,
                                uint64_t *n_inliers, double *error_max, int32_t *found);
 
+/* Pose extraction from a projection matrix (LocalizeEngine.cc:582-602, localization.cpp:544-547,
+ * adjust_sfm_data.cpp:138-142): KRt_From_P, then centre = -R^T t.  Host arithmetic, no launch.
+ * P: 12 doubles row-major; outputs K (9, may be NULL), R (9, row-major), center (3). */
+int hulo_pose_from_projection(const double *P, double *K, double *R, double *center);
+
 /* --------------------------------------------- K3: F-matrix geometric filter */
 
 /* hulo::geometricMatch, MatchUtils.cpp:372-420 (decl MatchUtils.h:66-72): OpenMVG's

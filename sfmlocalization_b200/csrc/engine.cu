@@ -117,6 +117,16 @@ using namespace hulo;
 
 extern "C" {
 
+int hulo_pose_from_projection(const double *P, double *K, double *R, double *center) {
+    if (P == nullptr || R == nullptr || center == nullptr) return HULO_ERR_ARG;
+    double Kd[9], t[3];
+    krt_from_p(P, Kd, R, t);
+    // camera centre = -R^T t  (LocalizeEngine.cc:582-585, adjust_sfm_data.cpp:139-142)
+    for (int c = 0; c < 3; ++c) center[c] = -(R[c] * t[0] + R[3 + c] * t[1] + R[6 + c] * t[2]);
+    if (K != nullptr) memcpy(K, Kd, sizeof Kd);
+    return HULO_OK;
+}
+
 int hulo_engine_create(hulo_gpu *h, const uint8_t *rows, size_t n, size_t stride, const uint64_t *seg_offsets,
                        size_t n_views, const uint32_t *obs_view, const uint32_t *obs_feat,
                        const uint32_t *obs_landmark, size_t n_obs, const double *landmark_X, size_t n_landmarks,

@@ -140,6 +140,28 @@ long long hulo_host_load_sfm_data(const char *path, unsigned long long *counts, 
     return (long long)sc.views.size();
 }
 
+// sums of the observed image points (checks that Observation::x is read)
+int hulo_host_sfm_observation_sums(const char *path, double *sums2) {
+    SfMScene sc;
+    if (!loadSfMData(path, sc)) return 1;
+    sums2[0] = sums2[1] = 0.0;
+    for (const Landmark &lm : sc.landmarks)
+        for (const Observation &o : lm.obs) { sums2[0] += o.x[0]; sums2[1] += o.x[1]; }
+    return 0;
+}
+
+int hulo_host_save_sfm_poses(const char *in_json, const char *out_json, unsigned long long n,
+                             const unsigned long long *ids, const double *R, const double *center) {
+    std::map<std::size_t, Pose> poses;
+    for (unsigned long long k = 0; k < n; ++k) {
+        Pose p;
+        memcpy(p.R, R + 9 * k, sizeof p.R);
+        memcpy(p.center, center + 3 * k, sizeof p.center);
+        poses[(std::size_t)ids[k]] = p;
+    }
+    return saveSfMDataPoses(in_json, out_json, poses) ? 0 : 1;
+}
+
 void hulo_host_undistort(double focal, double ppx, double ppy, double k1, double k2, double k3, double x, double y,
                          double *out2) {
     Intrinsic in;

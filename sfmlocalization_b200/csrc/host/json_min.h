@@ -1,6 +1,8 @@
 // json_min.h -- a small recursive-descent JSON reader, enough for OpenMVG's cereal
-// sfm_data.json (objects, arrays, numbers, strings, true/false/null).  Header only.
+// sfm_data.json (objects, arrays, numbers, strings, true/false/null), and a writer that puts a
+// parsed tree back with every number it did not touch spelled as it was read.  Header only.
 #pragma once
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -34,7 +36,67 @@ struct Value {
         return v;
     }
     double number(double dflt = 0.0) const { return type == Number ? num : dflt; }
+
+    Value *find(const char *key) { return const_cast<Value *>(static_cast<const Value *>(this)->get(key)); }
+    // a number set by the program (written with 17 significant digits)
+    void set_number(double v) { type = Number; num = v; str.clear(); }
 };
+
+inline void dump_string(const std::string &in, std::string &out) {
+    out += '"';
+    for (char c : in) {
+        switch (c) {
+            case '"': out += "\\\""; break;
+            case '\\': out += "\\\\"; break;
+            case '\n': out += "\\n"; break;
+            case '\t': out += "\\t"; break;
+            case '\r': out += "\\r"; break;
+            default: out += c;
+        }
+    }
+    out += '"';
+}
+
+// cereal's layout: 4 spaces per level, one member per line
+inline void dump(const Value &v, std::string &out, int indent = 0) {
+    const std::string pad((size_t)(indent + 1) * 4, ' '), pad_close((size_t)indent * 4, ' ');
+    switch (v.type) {
+        case Value::Null: out += "null"; break;
+        case Value::Bool: out += v.b ? "true" : "false"; break;
+        case Value::Number:
+            if (!v.str.empty()) {
+                out += v.str;                  // as read
+            } else {
+                char buf[40];
+                snprintf(buf, sizeof buf, "%.17g", v.num);
+                out += buf;
+            }
+            break;
+        case Value::String: dump_string(v.str, out); break;
+        case Value::Array:
+            if (v.arr.empty()) { out += "[]"; break; }
+            out += "[\n";
+            for (size_t i = 0; i < v.arr.size(); ++i) {
+                out += pad;
+                dump(v.arr[i], out, indent + 1);
+                out += i + 1 < v.arr.size() ? ",\n" : "\n";
+            }
+            out += pad_close + "]";
+            break;
+        case Value::Object:
+            if (v.obj.empty()) { out += "{}"; break; }
+            out += "{\n";
+            for (size_t i = 0; i < v.obj.size(); ++i) {
+                out += pad;
+                dump_string(v.obj[i].first, out);
+                out += ": ";
+                dump(v.obj[i].second, out, indent + 1);
+                out += i + 1 < v.obj.size() ? ",\n" : "\n";
+            }
+            out += pad_close + "}";
+            break;
+    }
+}
 
 class Parser {
 public:
@@ -131,6 +193,7 @@ private:
         v.num = strtod(s_, &e);
         if (e == s_) return false;
         v.type = Value::Number;
+        v.str.assign(s_, (size_t)(e - s_));    // the spelling, so an untouched number is written back as read
         s_ = e;
         return true;
     }

@@ -118,13 +118,73 @@ bool loadSfMData(const std::string &sfm_data_json, SfMScene &scene) {
                 for (const json::Value &o : obs->arr) {
                     const json::Value *ov = o.get("value");
                     if (!ov || !o.get("key") || !ov->get("id_feat")) return false;
-                    lm.obs.push_back(Observation{(std::size_t)o.get("key")->number(), (std::size_t)ov->get("id_feat")->number()});
+                    Observation ob;
+                    ob.id_view = (std::size_t)o.get("key")->number();
+                    ob.id_feat = (std::size_t)ov->get("id_feat")->number();
+                    if (const json::Value *x = ov->get("x"))
+                        for (std::size_t i = 0; i < 2 && i < x->arr.size(); ++i) ob.x[i] = x->arr[i].number();
+                    lm.obs.push_back(ob);
                 }
             sorted[lm.id] = std::move(lm);
         }
         for (auto &kv : sorted) scene.landmarks.push_back(std::move(kv.second));
     }
     return !scene.views.empty();
+}
+
+bool saveSfMDataPoses(const std::string &in_json, const std::string &out_json, const std::map<std::size_t, Pose> &poses) {
+    std::ifstream f(in_json);
+    if (!f.is_open()) return false;
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string text = ss.str();
+    json::Value root;
+    json::Parser parser(text);
+    if (!parser.parse(root) || root.type != json::Value::Object) return false;
+    json::Value *ext = root.find("extrinsics");
+    if (!ext) {
+        root.obj.emplace_back("extrinsics", json::Value());
+        ext = &root.obj.back().second;
+    }
+    ext->type = json::Value::Array;
+    ext->arr.clear();
+    for (const auto &kv : poses) {
+        json::Value rot;
+        rot.type = json::Value::Array;
+        for (int i = 0; i < 3; ++i) {
+            json::Value row;
+            row.type = json::Value::Array;
+            for (int j = 0; j < 3; ++j) {
+                row.arr.emplace_back();
+                row.arr.back().set_number(kv.second.R[3 * i + j]);
+            }
+            rot.arr.push_back(std::move(row));
+        }
+        json::Value center;
+        center.type = json::Value::Array;
+        for (int i = 0; i < 3; ++i) {
+            center.arr.emplace_back();
+            center.arr.back().set_number(kv.second.center[i]);
+        }
+        json::Value value;
+        value.type = json::Value::Object;
+        value.obj.emplace_back("rotation", std::move(rot));
+        value.obj.emplace_back("center", std::move(center));
+        json::Value key;
+        key.set_number((double)kv.first);
+        json::Value entry;
+        entry.type = json::Value::Object;
+        entry.obj.emplace_back("key", std::move(key));
+        entry.obj.emplace_back("value", std::move(value));
+        ext->arr.push_back(std::move(entry));
+    }
+    std::string out;
+    json::dump(root, out);
+    out += "\n";
+    std::ofstream o(out_json);
+    if (!o.is_open()) return false;
+    o << out;
+    return (bool)o;
 }
 
 bool readOpenCVMatrix(const std::string &yaml_file, const std::string &name, int &rows, int &cols,

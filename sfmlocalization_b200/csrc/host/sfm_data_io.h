@@ -29,7 +29,7 @@ struct Pose {
     double center[3] = {0, 0, 0};
 };
 
-struct Observation { std::size_t id_view, id_feat; };
+struct Observation { std::size_t id_view, id_feat; double x[2] = {0, 0}; };   // x: the observed image point
 struct Landmark {
     std::size_t id = 0;
     double X[3] = {0, 0, 0};
@@ -45,6 +45,11 @@ struct SfMScene {
 };
 
 bool loadSfMData(const std::string &sfm_data_json, SfMScene &scene);
+
+// openMVG::sfm::Save after the poses changed (adjust_sfm_data.cpp:152-155): `in_json` written to
+// `out_json` with the entries of "extrinsics" replaced by `poses` (ascending id_pose); every other
+// member, and every number of it, is written back as it was read.
+bool saveSfMDataPoses(const std::string &in_json, const std::string &out_json, const std::map<std::size_t, Pose> &poses);
 
 // cv::FileStorage(file, READ)[name] >> Mat for a numeric matrix: reads rows, cols and data of the
 // "!!opencv-matrix" node `name`.  Returns false when the file or the node is missing.

@@ -279,6 +279,13 @@ class HuloGpu:
                                             _ptr(inl), C.byref(n_inl), C.byref(emax), C.byref(found)))
         return dict(found=bool(found.value), P=P, inliers=inl[:n_inl.value].copy(), error_max=emax.value)
 
+    def pose_from_projection(self, P):
+        """hulo_pose_from_projection -> (K, R, center)."""
+        P = np.ascontiguousarray(P, np.float64)
+        K = np.zeros((3, 3)); R = np.zeros((3, 3)); c = np.zeros(3)
+        check(self.lib.hulo_pose_from_projection(_ptr(P), _ptr(K), _ptr(R), _ptr(c)))
+        return K, R, c
+
     def resect_acransac_batch(self, x2d, X3d, offsets, K, max_iter=4096, seed=1, seeds=None):
         """hulo_resect_acransac_batch -> list of dict(found, P, inliers, error_max), one per problem.
         K: (n, 3, 3) or one (3, 3) shared by all problems."""

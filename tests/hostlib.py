@@ -8,6 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "sfmlocalization_b200")
 CLI = os.path.join(PKG, "hulo_ext_match")
 CLI_LOCALIZE = os.path.join(PKG, "hulo_localize")
+CLI_BA_RESECT = os.path.join(PKG, "hulo_ba_resect")
 _lib = None
 
 
@@ -139,8 +140,9 @@ def write_sfm_data(path, scene, names, focal=None, disto=None):
     ext = [{"key": k, "value": {"rotation": scene["view_R"][k].tolist(),
                                 "center": (-scene["view_R"][k].T @ scene["view_t"][k]).tolist()}} for k in range(V)]
     obs = {}
+    off = scene["seg_offsets"].astype(np.int64)
     for v, f, l in zip(scene["obs_view"].tolist(), scene["obs_feat"].tolist(), scene["obs_landmark"].tolist()):
-        obs.setdefault(l, []).append({"key": v, "value": {"id_feat": f, "x": [0.0, 0.0]}})
+        obs.setdefault(l, []).append({"key": v, "value": {"id_feat": f, "x": scene["map_xy"][off[v] + f].tolist()}})
     structure = [{"key": l, "value": {"X": scene["landmark_X"][l].tolist(), "observations": obs[l]}}
                  for l in sorted(obs)]
     with open(path, "w") as f:
@@ -156,6 +158,18 @@ def load_sfm_data(path, cap_views=4096):
     if n < 0:
         return None
     return dict(counts=counts.astype(np.int64), first_X=X, intrinsic0=intr, view_wh=wh[:n].astype(np.int64))
+
+
+def sfm_observation_sums(path):
+    out = np.zeros(2)
+    return out if lib().hulo_host_sfm_observation_sums(path.encode(), _p(out)) == 0 else None
+
+
+def save_sfm_poses(in_json, out_json, ids, R, center):
+    ids = np.ascontiguousarray(ids, np.uint64); R = np.ascontiguousarray(R, np.float64)
+    center = np.ascontiguousarray(center, np.float64)
+    return lib().hulo_host_save_sfm_poses(in_json.encode(), out_json.encode(), C.c_ulonglong(len(ids)), _p(ids), _p(R),
+                                          _p(center)) == 0
 
 
 def undistort(focal, ppx, ppy, k, x, y):

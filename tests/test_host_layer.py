@@ -154,3 +154,38 @@ def test_opencv_yaml_matrix_and_feat_reader(tmp_path):
     hostlib.write_feat(str(tmp_path / "a.feat"), xy)
     assert np.array_equal(hostlib.read_feat(str(tmp_path / "a.feat")), xy)
     assert hostlib.read_feat(str(tmp_path / "none.feat")) is None
+
+
+def test_sfm_data_rewrite_keeps_everything_but_the_poses(tmp_path):
+    """saveSfMDataPoses (what hulo_ba_resect writes, adjust_sfm_data.cpp:152-155): the extrinsics
+    are replaced, every other member comes back with every number spelled as it was read."""
+    import json
+    sc = synth.localization_scene(5, 40, 60, 30, 23)
+    names = ["v%02d" % k for k in range(5)]
+    p = str(tmp_path / "sfm_data.json")
+    hostlib.write_sfm_data(p, sc, names, disto=[0.05, -0.01, 0.002])
+    sums = hostlib.sfm_observation_sums(p)
+    off = sc["seg_offsets"].astype(np.int64)
+    want = sc["map_xy"][off[sc["obs_view"]] + sc["obs_feat"]].sum(axis=0)
+    assert np.allclose(sums, want, rtol=1e-12)                     # Observation::x is read
+    rng = np.random.default_rng(5)
+    ids = np.array([0, 2, 3, 9], np.uint64)                         # a pose may be new (9) or dropped (1, 4)
+    R = rng.normal(size=(4, 3, 3)); Cc = rng.normal(size=(4, 3)) * 1e3
+    out = str(tmp_path / "out.json")
+    assert hostlib.save_sfm_poses(p, out, ids, R, Cc)
+    a, b = json.load(open(p)), json.load(open(out))
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        if k != "extrinsics":
+            assert a[k] == b[k], k
+    assert [e["key"] for e in b["extrinsics"]] == [0, 2, 3, 9]
+    for e, r, c in zip(b["extrinsics"], R, Cc):
+        assert np.array_equal(np.array(e["value"]["rotation"]), r)  # 17 significant digits: exact round trip
+        assert np.array_equal(np.array(e["value"]["center"]), c)
+    # numbers that were not touched keep their spelling
+    txt = open(out).read()
+    assert repr(float(sc["landmark_X"][0][0])) in txt
+    # and the file loads again
+    r = hostlib.load_sfm_data(out)
+    assert r["counts"][2] == 4 and r["counts"][3] == json.load(open(p))["structure"].__len__()
+    assert not hostlib.save_sfm_poses(str(tmp_path / "missing.json"), out, ids, R, Cc)

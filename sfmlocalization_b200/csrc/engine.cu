@@ -217,6 +217,13 @@ int hulo_engine_configure_geometric(hulo_engine *e, int enabled, size_t ransac_r
     return HULO_OK;
 }
 
+// 2D-3D pairs of the queries of a batch, gathered for one batched resection (a query with too few
+// pairs owns an empty range).
+struct ResectionBatch {
+    std::vector<double> x2d, X3d;
+    std::vector<uint64_t> offsets = std::vector<uint64_t>(1, 0);
+};
+
 // Stages after the putative matching, shared by the single and the batched entry points:
 // view filter, 2D-3D assembly, resection, pose.  m_* are the matches of this query grouped by
 // view position (view_counts[v] entries each, emission order).
@@ -224,7 +231,8 @@ static int assemble_and_resect(hulo_engine *e, size_t nq, const double *qxy, con
                                const uint32_t *m_i, const uint32_t *m_j, const int32_t *m_d0,
                                const uint32_t *view_counts, uint64_t seed, double *pose12, int *localized,
                                uint32_t *corr_qfeat, uint32_t *corr_landmark, size_t *n_corr, int32_t *inliers,
-                               size_t *n_inliers, double *t_assembly, double *t_pnp, double *t_geo) {
+                               size_t *n_inliers, double *t_assembly, double *t_pnp, double *t_geo,
+                               ResectionBatch *defer = nullptr) {
     double t1 = now_ms();
     // ---- 2D-3D assembly, hulo::matchProviderToMatchSet (SfMDataUtils.cpp:59-125).
     // The reference walks a std::map keyed by (view id, query id): ascending view id, and inside
@@ -338,6 +346,16 @@ static int assemble_and_resect(hulo_engine *e, size_t nq, const double *qxy, con
     if (n_corr) *n_corr = N;
     const double t2 = now_ms();
 
+    if (defer) {
+        // batched server: the resections of all queries run as one hulo_resect_acransac_batch
+        if ((int)N > e->min_points) {
+            defer->x2d.insert(defer->x2d.end(), e->x2d.begin(), e->x2d.end());
+            defer->X3d.insert(defer->X3d.end(), e->X3d.begin(), e->X3d.end());
+        }
+        defer->offsets.push_back(defer->x2d.size() / 2);
+        if (t_assembly) *t_assembly += t2 - t1;
+        return HULO_OK;
+    }
     // ---- resection, SfM_Localizer::Localize (LocalizeEngine.cc:529-532) and acceptance (:560)
     if ((int)N > e->min_points) {
         double P[12];
@@ -425,6 +443,7 @@ int hulo_engine_localize_batch(hulo_engine *e, size_t n_queries, const uint8_t *
     }
     if (times_ms) times_ms[0] = now_ms() - t0;
     size_t k0 = 0;
+    ResectionBatch rb;
     for (size_t q = 0; q < n_queries; ++q) {
         const size_t nq = (size_t)(q_offsets[q + 1] - q_offsets[q]);
         const uint32_t *vc = counts.data() + q * n_views;
@@ -436,12 +455,38 @@ int hulo_engine_localize_batch(hulo_engine *e, size_t n_queries, const uint8_t *
                                      e->m_j.data() + k0, e->m_d0.data() + k0, vc, seed + q, pose12 + 12 * q,
                                      localized + q, nullptr, nullptr, &nc, nullptr, &ni,
                                      times_ms ? times_ms + 1 : nullptr, times_ms ? times_ms + 2 : nullptr,
-                                     times_ms ? times_ms + 3 : nullptr);
+                                     times_ms ? times_ms + 3 : nullptr, &rb);
         if (rc != HULO_OK) return rc;
         if (n_corr) n_corr[q] = (uint32_t)nc;
-        if (n_inliers) n_inliers[q] = (uint32_t)ni;
+        if (n_inliers) n_inliers[q] = 0;
         k0 += n_q_matches;
     }
+    // ---- resection of every query at once (SfM_Localizer::Localize, LocalizeEngine.cc:529-532),
+    // query q with the seed the one-query entry point would give it, and acceptance (:560)
+    const double t_r0 = now_ms();
+    std::vector<double> P(12 * n_queries), emax(n_queries), Ks(9 * n_queries);
+    std::vector<uint64_t> n_inl(n_queries), seeds(n_queries);
+    std::vector<int32_t> found(n_queries), inl(std::max<size_t>(rb.x2d.size() / 2, 1));
+    for (size_t q = 0; q < n_queries; ++q) {
+        seeds[q] = seed + q;
+        memcpy(&Ks[9 * q], e->K, 9 * sizeof(double));
+    }
+    int rc = hulo_resect_acransac_batch(e->h, n_queries, rb.offsets.data(), rb.x2d.data(), rb.X3d.data(), Ks.data(),
+                                        e->max_iter, seed, seeds.data(), P.data(), inl.data(), n_inl.data(),
+                                        emax.data(), found.data());
+    if (rc != HULO_OK) return rc;
+    for (size_t q = 0; q < n_queries; ++q) {
+        if (n_inliers) n_inliers[q] = (uint32_t)n_inl[q];
+        if (found[q] && (int)n_inl[q] > e->min_inliers) {
+            double Kd[9], R[9], t[3];
+            krt_from_p(&P[12 * q], Kd, R, t);
+            double *pose = pose12 + 12 * q;
+            for (int c = 0; c < 3; ++c) pose[c] = -(R[c] * t[0] + R[3 + c] * t[1] + R[6 + c] * t[2]);
+            memcpy(pose + 3, R, 9 * sizeof(double));
+            localized[q] = 1;
+        }
+    }
+    if (times_ms) times_ms[2] += now_ms() - t_r0;
     return HULO_OK;
 }
 

@@ -297,8 +297,15 @@ int hulo_engine_set_keypoints(hulo_engine *e, const double *map_xy, const int32_
 int hulo_engine_set_query_size(hulo_engine *e, int query_w, int query_h);
 /* Switch hulo::geometricMatch (LocalizeEngine.cc:458) on or off (off after hulo_engine_create):
  * ransac_round = mRansacRound, precision_px = mRansacPrecision of the LocalizeEngine
- * constructor (LocalizeEngine.cc:84-91).  Guided matching is available for the reconstruction stage only (hulo_guided_match); the engine runs the unguided filter. */
+ * constructor (LocalizeEngine.cc:84-91).  Switching it off also switches guided matching off. */
 int hulo_engine_configure_geometric(hulo_engine *e, int enabled, size_t ransac_round, double precision_px);
+/* mGuidedMatching of the LocalizeEngine constructor / -gm of the localisation CLI
+ * (bGuided_matching of hulo::geometricMatch, MatchUtils.cpp:407-416): for every (view, query) pair
+ * that passed the F-matrix filter, ALL features of the view are re-matched against ALL features of
+ * the query behind the epipolar gate of the pair's F (robust precision of the filter, descriptor
+ * ratio 0.6^2) and the result replaces the pair's inlier list before the 2D-3D assembly.  Needs
+ * the geometric filter enabled (off after hulo_engine_create). */
+int hulo_engine_set_guided_matching(hulo_engine *e, int enabled);
 
 /* LocalizeEngine::localize from the putative matching on (LocalizeEngine.cc:423-602) for one
  * query image given its descriptors and (undistorted) keypoint positions:

@@ -75,6 +75,7 @@ SIGNATURES = {
     "hulo_engine_set_keypoints": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
     "hulo_engine_set_query_size": (C.c_int, [_vp, C.c_int, C.c_int]),
     "hulo_engine_configure_geometric": (C.c_int, [_vp, C.c_int, _sz, _f64]),
+    "hulo_engine_set_guided_matching": (C.c_int, [_vp, C.c_int]),
     "hulo_engine_localize": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _vp, _sz, _u64, _vp, C.POINTER(C.c_int), _vp, _vp,
                                        C.POINTER(_sz), _vp, C.POINTER(_sz), _vp]),
     "hulo_engine_localize_batch": (C.c_int, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _u64, _vp, _vp, _vp, _vp, _vp]),

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "context.cuh"
+#include "guided.cuh"
 
 struct hulo_engine {
     hulo_gpu *h = nullptr;
@@ -38,6 +39,15 @@ struct hulo_engine {
     std::vector<int32_t> g_sizes, g_valid, g_inl;
     std::vector<uint32_t> g_ninl;
     std::vector<size_t> g_view;    // position in views[] of each filtered pair
+    // guided matching after the filter (bGuided_matching of hulo::geometricMatch, MatchUtils.cpp:407-416):
+    // map keypoints resident on the device, position groups of the map views cached across queries
+    bool guided = false;
+    hulo::DevBuf d_map_xy, d_q_xy;
+    hulo::GuidedGroups map_groups;
+    std::vector<double> g_F, g_err, gm_F, gm_thr;
+    std::vector<uint32_t> gm_pairs, gm_i, gm_j;
+    std::vector<uint64_t> gm_off;
+    std::vector<int64_t> gm_of_pair;
     // per-query scratch
     std::vector<uint32_t> m_view, m_i, m_j, view_counts;
     std::vector<int32_t> m_d0;
@@ -170,6 +180,8 @@ int hulo_engine_create(hulo_gpu *h, const uint8_t *rows, size_t n, size_t stride
 void hulo_engine_destroy(hulo_engine *e) {
     if (!e) return;
     hulo_db_free(e->map);
+    e->d_map_xy.release();
+    e->d_q_xy.release();
     delete e;
 }
 
@@ -194,6 +206,19 @@ int hulo_engine_set_keypoints(hulo_engine *e, const double *map_xy, const int32_
     e->view_wh.assign(view_wh, view_wh + 2 * e->n_views);
     e->query_wh[0] = query_w;
     e->query_wh[1] = query_h;
+    // resident copy for guided matching; positions changed, so the cached position groups go
+    HULO_CUDA(cudaSetDevice(e->h->device));
+    HULO_CUDA(e->d_map_xy.reserve(std::max<size_t>(n, 1) * 2 * sizeof(double)));
+    if (n) HULO_CUDA(cudaMemcpyAsync(e->d_map_xy.ptr, e->map_xy.data(), n * 2 * sizeof(double), cudaMemcpyHostToDevice, e->h->stream));
+    HULO_CUDA(cudaStreamSynchronize(e->h->stream));
+    e->map_groups.segs.clear();
+    return HULO_OK;
+}
+
+int hulo_engine_set_guided_matching(hulo_engine *e, int enabled) {
+    HULO_ARG(e != nullptr, "null engine");
+    if (enabled) HULO_ARG(e->geo_enabled, "guided matching refines the geometric filter: enable hulo_engine_configure_geometric first");
+    e->guided = enabled != 0;
     return HULO_OK;
 }
 
@@ -214,6 +239,7 @@ int hulo_engine_configure_geometric(hulo_engine *e, int enabled, size_t ransac_r
         e->geo_precision = precision_px;
     }
     e->geo_enabled = enabled != 0;
+    if (!e->geo_enabled) e->guided = false;
     return HULO_OK;
 }
 
@@ -232,7 +258,7 @@ static int assemble_and_resect(hulo_engine *e, size_t nq, const double *qxy, con
                                const uint32_t *view_counts, uint64_t seed, double *pose12, int *localized,
                                uint32_t *corr_qfeat, uint32_t *corr_landmark, size_t *n_corr, int32_t *inliers,
                                size_t *n_inliers, double *t_assembly, double *t_pnp, double *t_geo,
-                               ResectionBatch *defer = nullptr) {
+                               ResectionBatch *defer = nullptr, size_t q_row0 = 0) {
     double t1 = now_ms();
     // ---- 2D-3D assembly, hulo::matchProviderToMatchSet (SfMDataUtils.cpp:59-125).
     // The reference walks a std::map keyed by (view id, query id): ascending view id, and inside
@@ -284,11 +310,52 @@ static int assemble_and_resect(hulo_engine *e, size_t nq, const double *qxy, con
         e->g_valid.assign(std::max<size_t>(P, 1), 0);
         e->g_ninl.assign(std::max<size_t>(P, 1), 0);
         e->g_inl.resize(std::max<size_t>((size_t)e->g_off.back(), 1));
+        e->g_F.resize(9 * std::max<size_t>(P, 1));
+        e->g_err.resize(std::max<size_t>(P, 1));
         if (P) {
             int rc = hulo_geometric_filter(e->h, e->g_xI.data(), e->g_xJ.data(), e->g_off.data(), P, e->g_sizes.data(),
                                            e->geo_precision, e->geo_rounds, seed + 77, nullptr, e->g_valid.data(),
-                                           e->g_ninl.data(), e->g_inl.data(), nullptr, nullptr, nullptr);
+                                           e->g_ninl.data(), e->g_inl.data(), e->g_F.data(), e->g_err.data(), nullptr);
             if (rc != HULO_OK) return rc;
+        }
+        if (e->guided) {
+            // Geometry_guided_matching: ALL features of the view against ALL features of the query
+            // behind the epipolar gate of the pair's F, descriptor ratio 0.6^2 (MatchUtils.cpp:410-414);
+            // the result replaces the pair's inlier list.  I side: the resident map; J side: the
+            // query rows as hulo_match_to_query(ies) left them (folded) in the staging buffer.
+            e->gm_pairs.clear(); e->gm_F.clear(); e->gm_thr.clear();
+            e->gm_of_pair.assign(std::max<size_t>(P, 1), -1);
+            for (size_t p = 0; p < P; ++p) {
+                if (!e->g_valid[p]) continue;
+                const size_t v = e->g_view[p];
+                e->gm_of_pair[p] = (int64_t)(e->gm_pairs.size() / 2);
+                e->gm_pairs.push_back(views ? views[v] : (uint32_t)v);
+                e->gm_pairs.push_back(0);
+                e->gm_F.insert(e->gm_F.end(), e->g_F.begin() + 9 * p, e->g_F.begin() + 9 * p + 9);
+                e->gm_thr.push_back(e->g_err[p] * e->g_err[p]);               // Square(m_dPrecision_robust)
+            }
+            const size_t G = e->gm_pairs.size() / 2;
+            e->gm_off.assign(G + 1, 0);
+            if (G) {
+                HULO_CUDA(e->d_q_xy.reserve(std::max<size_t>(nq, 1) * 2 * sizeof(double)));
+                HULO_CUDA(cudaMemcpyAsync(e->d_q_xy.ptr, qxy, nq * 2 * sizeof(double), cudaMemcpyHostToDevice, e->h->stream));
+                const uint64_t q_seg[2] = {0, (uint64_t)nq};
+                hulo::GuidedSide SI, SJ;
+                SI.rows = e->map->rows; SI.seg = e->seg.data(); SI.n_seg = e->n_views;
+                SI.h_xy = e->map_xy.data(); SI.d_xy = e->d_map_xy.as<double2>(); SI.groups = &e->map_groups;
+                SJ.rows = e->h->stageB.as<uint4>() + 4 * q_row0; SJ.seg = q_seg; SJ.n_seg = 1;
+                SJ.h_xy = qxy; SJ.d_xy = e->d_q_xy.as<double2>();
+                size_t cap = std::max<size_t>(e->gm_i.size(), 4096), n_g = 0;
+                for (;;) {
+                    e->gm_i.resize(cap);
+                    e->gm_j.resize(cap);
+                    int rc = hulo::guided_match_sides(e->h, SI, SJ, e->gm_pairs.data(), G, e->gm_F.data(), e->gm_thr.data(),
+                                                      0.6 * 0.6, 1, e->gm_off.data(), e->gm_i.data(), e->gm_j.data(), cap, &n_g);
+                    if (rc == HULO_ERR_CAPACITY) { cap = n_g + n_g / 8; continue; }
+                    if (rc != HULO_OK) return rc;
+                    break;
+                }
+            }
         }
         const double tg = now_ms();
         if (t_geo) *t_geo += tg - t1;
@@ -316,12 +383,24 @@ static int assemble_and_resect(hulo_engine *e, size_t nq, const double *qxy, con
             e->fd[j] = m_d0[k];
             e->fd_stamp[j] = (int32_t)oi;
         }
+        const uint32_t *g_i = nullptr, *g_j = nullptr;               // guided matches of the pair: (feature, query feature)
+        if (e->geo_enabled && e->guided) {
+            const size_t g = (size_t)e->gm_of_pair[(size_t)geo_pair[v]];
+            g_i = e->gm_i.data() + e->gm_off[g];
+            g_j = e->gm_j.data() + e->gm_off[g];
+            n_cand = (size_t)(e->gm_off[g + 1] - e->gm_off[g]);
+        }
         for (size_t c = 0; c < n_cand; ++c) {
-            const size_t k = start[v] + (cand ? (size_t)cand[c] : c);
-            const int32_t lmi = e->lm_of_row[e->seg[view_id] + m_i[k]];
+            uint32_t fi, j;
+            if (g_i) {
+                fi = g_i[c]; j = g_j[c];
+            } else {
+                const size_t k = start[v] + (cand ? (size_t)cand[c] : c);
+                fi = m_i[k]; j = m_j[k];
+            }
+            const int32_t lmi = e->lm_of_row[e->seg[view_id] + fi];
             if (lmi < 0) continue;                                     // feature has no landmark
             const uint32_t lm = (uint32_t)lmi;
-            const uint32_t j = m_j[k];
             if (e->fd_stamp[j] != (int32_t)oi) continue;
             const int32_t d = e->fd[j];
             if (e->best_lm[j] < 0 || (float)e->best_d[j] > (float)d) {
@@ -455,7 +534,7 @@ int hulo_engine_localize_batch(hulo_engine *e, size_t n_queries, const uint8_t *
                                      e->m_j.data() + k0, e->m_d0.data() + k0, vc, seed + q, pose12 + 12 * q,
                                      localized + q, nullptr, nullptr, &nc, nullptr, &ni,
                                      times_ms ? times_ms + 1 : nullptr, times_ms ? times_ms + 2 : nullptr,
-                                     times_ms ? times_ms + 3 : nullptr, &rb);
+                                     times_ms ? times_ms + 3 : nullptr, &rb, (size_t)q_offsets[q]);
         if (rc != HULO_OK) return rc;
         if (n_corr) n_corr[q] = (uint32_t)nc;
         if (n_inliers) n_inliers[q] = 0;

@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "context.cuh"
+#include "guided.cuh"
 #include "match_post.cuh"
 
 namespace hulo {
@@ -37,16 +38,17 @@ constexpr int kGuidedTile = 128;          // rows of J per shared-memory tile
 
 struct alignas(16) GuidedItem {
     uint32_t pair;       // position in the batch (F, threshold)
-    uint32_t i_row0;     // first row of the tile (global row in the table)
+    uint32_t i_row0;     // first row of the tile (row in the table of the I side)
     uint32_t i_rows;     // rows in the tile (<= kGuidedThreads)
-    uint32_t j_row0;     // first row of image J
+    uint32_t j_row0;     // first row of image J (row in the table of the J side)
     uint32_t j_rows;
     uint32_t pad;
     uint64_t out_slot0;  // val[out_slot0 + t] for row i_row0 + t
 };
 
 __global__ void __launch_bounds__(kGuidedThreads) guided_kernel(
-    const uint4 *__restrict__ rows, const double2 *__restrict__ xy, const double *__restrict__ Fs,
+    const uint4 *__restrict__ rows, const double2 *__restrict__ xy, const uint4 *__restrict__ rows_j,
+    const double2 *__restrict__ xy_j, const double *__restrict__ Fs,
     const double *__restrict__ thr2, double ratio, const GuidedItem *__restrict__ items, uint32_t n_items,
     int32_t *__restrict__ val) {
     __shared__ float2 s_xyf[kGuidedTile];
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(kGuidedThreads) guided_kernel(
             const uint32_t nj = min((uint32_t)kGuidedTile, item.j_rows - j0);
             __syncthreads();                             // the previous tile has been consumed
             for (uint32_t e = tid; e < nj; e += kGuidedThreads) {
-                const double2 p = xy[item.j_row0 + j0 + e];
+                const double2 p = xy_j[item.j_row0 + j0 + e];
                 s_xyd[e] = p;
                 s_xyf[e] = make_float2((float)p.x, (float)p.y);
             }
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(kGuidedThreads) guided_kernel(
             // below always runs 32 rows with compile-time bit positions
             for (uint32_t e = nj + tid; e < ((nj + 31u) & ~31u); e += kGuidedThreads) s_xyf[e] = make_float2(NAN, NAN);
             for (uint32_t e = tid; e < nj * 4; e += kGuidedThreads)
-                s_desc[e] = __ldg(rows + (size_t)(item.j_row0 + j0) * 4 + e);
+                s_desc[e] = __ldg(rows_j + (size_t)(item.j_row0 + j0) * 4 + e);
             __syncthreads();
             for (uint32_t g0 = 0; g0 < nj; g0 += 32) {
                 uint32_t mask = 0;
@@ -180,42 +182,30 @@ void position_groups(const double *xy, size_t n, int32_t *rep, uint8_t *member) 
 }
 
 }  // namespace
-}  // namespace hulo
 
-using namespace hulo;
+// Position groups of the images of one side, built the first time an image appears in a pair.
+const GuidedGroups::Seg &GuidedGroups::of(const GuidedSide &side, uint32_t S) {
+    auto it = segs.find(S);
+    if (it != segs.end()) return it->second;
+    Seg &g = segs[S];
+    const size_t a = (size_t)side.seg[S], n = (size_t)(side.seg[S + 1] - side.seg[S]);
+    g.rep.resize(std::max<size_t>(n, 1));
+    g.member.assign(std::max<size_t>(n, 1), 0);
+    position_groups(side.h_xy + 2 * a, n, g.rep.data(), g.member.data());
+    return g;
+}
 
-extern "C" {
-
-int hulo_guided_match(hulo_gpu *h, const hulo_db *db, const double *xy, const uint32_t *pairs, size_t n_pairs,
-                      const double *F, const double *error_th, double dist_ratio, int dedup, uint64_t *pair_offsets,
-                      uint32_t *out_i, uint32_t *out_j, size_t cap, size_t *n_out) {
-    HULO_ARG(h != nullptr && db != nullptr && n_out != nullptr, "null argument");
-    *n_out = 0;
-    if (pair_offsets) pair_offsets[0] = 0;
-    if (n_pairs == 0) return HULO_OK;
-    HULO_ARG(pairs != nullptr && F != nullptr && error_th != nullptr, "null argument");
-    HULO_ARG(db->n == 0 || xy != nullptr, "feature positions are null");
-    HULO_ARG(dist_ratio > 0.0, "the distance ratio must be positive");
-    HULO_CUDA(cudaSetDevice(h->device));
-    const size_t n_seg = db->seg.size() - 1;
-    for (size_t p = 0; p < n_pairs; ++p) {
-        HULO_ARG(pairs[2 * p] < n_seg && pairs[2 * p + 1] < n_seg, "pair refers to a segment that does not exist");
-        HULO_ARG(db->seg[pairs[2 * p + 1] + 1] - db->seg[pairs[2 * p + 1]] <= kMaxChunkRows, "image with more than 4 Mi descriptors");
-    }
-    // feature positions of every row of the table
-    HULO_CUDA(h->stageA.reserve(std::max<size_t>(db->n, 1) * sizeof(double2)));
-    if (db->n) HULO_CUDA(cudaMemcpyAsync(h->stageA.ptr, xy, db->n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
-    const double2 *d_xy = h->stageA.as<double2>();
-
+int guided_match_sides(hulo_gpu *h, const GuidedSide &SI, const GuidedSide &SJ, const uint32_t *pairs, size_t n_pairs,
+                       const double *F, const double *error_th, double dist_ratio, int dedup, uint64_t *pair_offsets,
+                       uint32_t *out_i, uint32_t *out_j, size_t cap, size_t *n_out) {
     const uint64_t max_batch_rows = 16u << 20;
     size_t total_out = 0;
     bool overflow = false;
     std::vector<GuidedItem> items;
     std::vector<uint64_t> row_off, h_seg_out;
     std::vector<uint32_t> hi, hj;
-    // position groups per image, built the first time an image appears in a pair
-    std::vector<int32_t> rep(dedup ? std::max<size_t>(db->n, 1) : 1);
-    std::vector<uint8_t> member(dedup ? std::max<size_t>(db->n, 1) : 1, 0), grouped(n_seg, 0);
+    GuidedGroups own_i, own_j;
+    GuidedGroups &groups_i = SI.groups ? *SI.groups : own_i, &groups_j = SJ.groups ? *SJ.groups : own_j;
     std::vector<uint64_t> seen;
     size_t p0 = 0;
     while (p0 < n_pairs) {
@@ -224,14 +214,14 @@ int hulo_guided_match(hulo_gpu *h, const hulo_db *db, const double *xy, const ui
         size_t p1 = p0;
         while (p1 < n_pairs) {
             const uint32_t I = pairs[2 * p1], J = pairs[2 * p1 + 1];
-            const uint64_t nI = db->seg[I + 1] - db->seg[I], nJ = db->seg[J + 1] - db->seg[J];
+            const uint64_t nI = SI.seg[I + 1] - SI.seg[I], nJ = SJ.seg[J + 1] - SJ.seg[J];
             if (p1 > p0 && row_off.back() + nI > max_batch_rows) break;
             for (uint64_t t0 = 0; t0 < nI; t0 += kGuidedThreads) {
                 GuidedItem it{};
                 it.pair = (uint32_t)(p1 - p0);
-                it.i_row0 = (uint32_t)(db->seg[I] + t0);
+                it.i_row0 = (uint32_t)(SI.seg[I] + t0);
                 it.i_rows = (uint32_t)std::min<uint64_t>(kGuidedThreads, nI - t0);
-                it.j_row0 = (uint32_t)db->seg[J];
+                it.j_row0 = (uint32_t)SJ.seg[J];
                 it.j_rows = (uint32_t)nJ;
                 it.out_slot0 = row_off.back() + t0;
                 items.push_back(it);
@@ -260,7 +250,7 @@ int hulo_guided_match(hulo_gpu *h, const hulo_db *db, const double *xy, const ui
             HULO_CUDA(cudaMemcpyAsync(d_thr, error_th + p0, bp * sizeof(double), cudaMemcpyHostToDevice, h->stream));
             int32_t *val = h->scratch0.as<int32_t>();
             const unsigned grid = (unsigned)std::min<size_t>(items.size(), (size_t)h->sm_count * 8);
-            guided_kernel<<<grid, kGuidedThreads, 0, h->stream>>>(db->rows, d_xy, d_F, d_thr, dist_ratio,
+            guided_kernel<<<grid, kGuidedThreads, 0, h->stream>>>(SI.rows, SI.d_xy, SJ.rows, SJ.d_xy, d_F, d_thr, dist_ratio,
                                                                   h->items.as<GuidedItem>(), (uint32_t)items.size(), val);
             HULO_CUDA(cudaGetLastError());
             h->launches++;
@@ -287,25 +277,17 @@ int hulo_guided_match(hulo_gpu *h, const hulo_db *db, const double *xy, const ui
             // (IndMatchDecorator::getDeduplicated), first occurrence kept, order preserved
             for (size_t p = 0; p < bp; ++p) {
                 const uint32_t I = pairs[2 * (p0 + p)], J = pairs[2 * (p0 + p) + 1];
-                if (dedup) {
-                    for (uint32_t S : {I, J}) {
-                        if (grouped[S]) continue;
-                        const size_t a = (size_t)db->seg[S], nS = (size_t)(db->seg[S + 1] - db->seg[S]);
-                        position_groups(xy + 2 * a, nS, rep.data() + a, member.data() + a);
-                        grouped[S] = 1;
-                    }
-                }
-                const int32_t *repI = dedup ? rep.data() + db->seg[I] : nullptr, *repJ = dedup ? rep.data() + db->seg[J] : nullptr;
-                const uint8_t *memI = dedup ? member.data() + db->seg[I] : nullptr;
+                const GuidedGroups::Seg *gI = dedup ? &groups_i.of(SI, I) : nullptr;
+                const GuidedGroups::Seg *gJ = dedup ? &groups_j.of(SJ, J) : nullptr;
                 seen.clear();
                 for (uint64_t m = h_seg_out[1 + p]; m < h_seg_out[2 + p]; ++m) {
-                    if (dedup && memI[hi[m]]) {
-                        const uint64_t k = ((uint64_t)(uint32_t)repI[hi[m]] << 32) | (uint32_t)repJ[hj[m]];
+                    if (dedup && gI->member[hi[m]]) {
+                        const uint64_t k = ((uint64_t)(uint32_t)gI->rep[hi[m]] << 32) | (uint32_t)gJ->rep[hj[m]];
                         if (std::find(seen.begin(), seen.end(), k) != seen.end()) continue;
                         seen.push_back(k);
                     }
                     if (total_out < cap) {
-                        if (out_i == nullptr || out_j == nullptr) { set_error("hulo_guided_match: null output"); return HULO_ERR_ARG; }
+                        if (out_i == nullptr || out_j == nullptr) { set_error("guided matching: null output"); return HULO_ERR_ARG; }
                         out_i[total_out] = hi[m];
                         out_j[total_out] = hj[m];
                     } else {
@@ -322,10 +304,47 @@ int hulo_guided_match(hulo_gpu *h, const hulo_db *db, const double *xy, const ui
     }
     *n_out = total_out;
     if (overflow) {
-        set_error("hulo_guided_match: %zu matches, capacity %zu", total_out, cap);
+        set_error("guided matching: %zu matches, capacity %zu", total_out, cap);
         return HULO_ERR_CAPACITY;
     }
     return HULO_OK;
+}
+
+}  // namespace hulo
+
+using namespace hulo;
+
+extern "C" {
+
+int hulo_guided_match(hulo_gpu *h, const hulo_db *db, const double *xy, const uint32_t *pairs, size_t n_pairs,
+                      const double *F, const double *error_th, double dist_ratio, int dedup, uint64_t *pair_offsets,
+                      uint32_t *out_i, uint32_t *out_j, size_t cap, size_t *n_out) {
+    HULO_ARG(h != nullptr && db != nullptr && n_out != nullptr, "null argument");
+    *n_out = 0;
+    if (pair_offsets) pair_offsets[0] = 0;
+    if (n_pairs == 0) return HULO_OK;
+    HULO_ARG(pairs != nullptr && F != nullptr && error_th != nullptr, "null argument");
+    HULO_ARG(db->n == 0 || xy != nullptr, "feature positions are null");
+    HULO_ARG(dist_ratio > 0.0, "the distance ratio must be positive");
+    HULO_CUDA(cudaSetDevice(h->device));
+    const size_t n_seg = db->seg.size() - 1;
+    for (size_t p = 0; p < n_pairs; ++p) {
+        HULO_ARG(pairs[2 * p] < n_seg && pairs[2 * p + 1] < n_seg, "pair refers to a segment that does not exist");
+        HULO_ARG(db->seg[pairs[2 * p + 1] + 1] - db->seg[pairs[2 * p + 1]] <= kMaxChunkRows, "image with more than 4 Mi descriptors");
+    }
+    // feature positions of every row of the table
+    HULO_CUDA(h->stageA.reserve(std::max<size_t>(db->n, 1) * sizeof(double2)));
+    if (db->n) HULO_CUDA(cudaMemcpyAsync(h->stageA.ptr, xy, db->n * sizeof(double2), cudaMemcpyHostToDevice, h->stream));
+    GuidedSide side;
+    side.rows = db->rows;
+    side.seg = db->seg.data();
+    side.n_seg = n_seg;
+    side.h_xy = xy;
+    side.d_xy = h->stageA.as<double2>();
+    GuidedGroups groups;                  // one table on both sides: one set of position groups
+    side.groups = &groups;
+    return guided_match_sides(h, side, side, pairs, n_pairs, F, error_th, dist_ratio, dedup, pair_offsets, out_i, out_j,
+                              cap, n_out);
 }
 
 }  // extern "C"

@@ -30,6 +30,7 @@ struct LocalizeEngine::State {
     double ratio = 0.6;
     int ransacRound = 25;
     double ransacPrecision = 4.0;
+    bool guidedMatching = false;
     bool hasA = false;
     double A[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};   // row-major 4 x 4 (3 x 4 padded)
     std::vector<std::size_t> seg_view;                 // segment s of the device table = view seg_view[s]
@@ -52,7 +53,7 @@ LocalizeEngine::LocalizeEngine(const std::string sfmDataDir, const std::string m
                                int beaconKnnNum, int bowKnnNum, int device)
     : st_(std::make_shared<State>()) {
     State &s = *st_;
-    if (guidedMatching) throw std::invalid_argument("LocalizeEngine: guided matching is not implemented");
+    s.guidedMatching = guidedMatching;
     s.sfmDataDir = sfmDataDir;
     s.matchDir = matchDir;
     s.ratio = secondTestRatio;
@@ -274,6 +275,7 @@ std::vector<double> LocalizeEngine::localize(const uint8_t *desc, std::size_t n,
          "hulo_engine_set_query_size");
     must(hulo_engine_configure_geometric(s.eng, 1, (std::size_t)std::max(s.ransacRound, 1), s.ransacPrecision),
          "hulo_engine_configure_geometric");
+    must(hulo_engine_set_guided_matching(s.eng, s.guidedMatching ? 1 : 0), "hulo_engine_set_guided_matching");
 
     double pose12[12];
     int localized = 0;

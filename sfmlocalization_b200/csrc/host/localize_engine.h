@@ -9,8 +9,10 @@
 //   * BoW view pre-selection (bowKnnNum, LocalizeEngine.cc:334-362) works from the views' .bow
 //     files and the query's bag-of-features vector handed to localize(); computing that vector
 //     from the image (dense features + vocabulary) stays with the caller.  iBeacon pre-selection
-//     (beaconKnnNum, beaconStr) is out of scope: accepted, a non-zero value prints a note;
-//   * guided matching is not implemented: guidedMatching = true throws std::invalid_argument.
+//     (beaconKnnNum, beaconStr) is out of scope: accepted, a non-zero value prints a note.
+// guidedMatching = true re-matches all features of every pair that passed the F-matrix filter
+// behind the epipolar gate (hulo_engine_set_guided_matching), like bGuided_matching of
+// hulo::geometricMatch (LocalizeEngine.cc:458).
 // The object is a copyable handle (shared state), because the reference stores engines by
 // value in a std::map (localizeImage.cc:100).  Not re-entrant, like the reference (:71-74).
 #pragma once

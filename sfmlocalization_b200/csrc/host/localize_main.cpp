@@ -5,7 +5,7 @@
 // localization.cpp:100-144; consumers sfmMergeGraph.py:260-269, mergeSfM.py:50-66).
 //
 //   hulo_localize <query .desc file or folder> <sfmDir> <matchDir> <outDir>
-//                 [-f=0.6] [-r=200] [-g=4.0] [-x= -y= -z= -d=-1] [-i=1] [--width=W --height=H]
+//                 [-f=0.6] [-r=200] [-g=4.0] [-gm] [-x= -y= -z= -d=-1] [-i=1] [--width=W --height=H]
 //                 [--device=D] [--seed=S] [--rank=R --world=W] [--amat=<A.yml>]
 //
 // The reference takes image files and extracts AKAZE features itself (localization.cpp:312-330);
@@ -15,7 +15,7 @@
 // the reference's meaning; -k=knnbow selects the knn views nearest in bag-of-features space, from the
 // views' .bow files and <name>.bow next to the query's .desc (the reference computes the query's
 // vector from the image with the -a / -p models, localization.cpp:386-412); -w -a -p are accepted
-// and ignored; -gm (guided matching) is not implemented and is refused.  --rank/--world shard a folder
+// and ignored; -gm switches guided matching on (localization.cpp:82).  --rank/--world shard a folder
 // of queries over processes (one per GPU, each holding the map; no collective): process R handles
 // every W-th query and writes its own result files.  --amat gives the OpenCV YAML file with the 3 x 4
 // (or 4 x 4) matrix "A" that takes the model to global coordinates, like the server's aMatFile
@@ -93,6 +93,7 @@ int main(int argc, char **argv) {
     std::string v, sAmat;
     float fDistRatio = 0.6f;
     int ransacRound = 200, locEvryNFrame = 1, device = -1, rank = 0, world = 1, knnbow = 0;
+    bool bGuided = false;
     double geomPrec = 4.0, cenX = 0, cenY = 0, cenZ = 0, cenRadius = -1.0;
     size_t width = 0, height = 0;
     unsigned long long seed = 1;
@@ -113,10 +114,9 @@ int main(int argc, char **argv) {
         else if (flag(argv[a], "--amat", v)) sAmat = v;
         else if (flag(argv[a], "--rank", v)) rank = atoi(v.c_str());
         else if (flag(argv[a], "--world", v)) world = atoi(v.c_str());
-        else if (strcmp(argv[a], "-gm") == 0 || (flag(argv[a], "-gm", v) && v != "false" && v != "0")) {
-            std::cerr << "guided matching (-gm) is not implemented" << std::endl;
-            return EXIT_FAILURE;
-        } else if (argv[a][0] == '-' && !(argv[a][1] >= '0' && argv[a][1] <= '9')) continue;
+        else if (strcmp(argv[a], "-gm") == 0) bGuided = true;
+        else if (flag(argv[a], "-gm", v)) bGuided = v != "false" && v != "0";
+        else if (argv[a][0] == '-' && !(argv[a][1] >= '0' && argv[a][1] <= '9')) continue;
         else pos.push_back(argv[a]);
     }
     if (pos.size() < 4) {
@@ -148,7 +148,7 @@ int main(int argc, char **argv) {
     const std::string sSfM_data = sSfMDir + (sSfMDir.back() == '/' ? "" : "/") + "sfm_data.json";
     try {
         if (world < 1 || rank < 0 || rank >= world) { std::cerr << "bad --rank/--world\n"; return 1; }
-        LocalizeEngine engine(sSfMDir, sMatchesDir, sAmat, fDistRatio, ransacRound, geomPrec, false, 0, knnbow,
+        LocalizeEngine engine(sSfMDir, sMatchesDir, sAmat, fDistRatio, ransacRound, geomPrec, bGuided, 0, knnbow,
                               device >= 0 ? device : rank);
         if (cenRadius > 0) engine.setLocalViews({cenX, cenY, cenZ}, cenRadius);
         const Intrinsic &cam = engine.scene().intrinsics.at(0);

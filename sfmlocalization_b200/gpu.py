@@ -442,6 +442,9 @@ class LocalizeEngine:
     def configure_geometric(self, enabled, ransac_round=25, precision_px=4.0):
         check(self.lib.hulo_engine_configure_geometric(self.h, int(bool(enabled)), ransac_round, precision_px))
 
+    def set_guided_matching(self, enabled):
+        check(self.lib.hulo_engine_set_guided_matching(self.h, int(bool(enabled))))
+
     def localize(self, qdesc, qxy, views=None, seed=1):
         qdesc = _rows(qdesc)
         qxy = np.ascontiguousarray(qxy, np.float64)

@@ -179,3 +179,75 @@ def test_localize_with_geometric_filter(gpu, orc, seed, rounds):
     assert (truth == r["corr_landmark"]).mean() > 0.97
     assert r["localized"] and np.linalg.norm(r["center"] - sc["center"]) < 0.05
     assert r["times_ms"][3] > 0 and plain["times_ms"][3] == 0
+
+
+def composed_guided_assembly(gpu, orc, sc, seed, rounds, precision, ratio=0.6, min_putative=16):
+    """The engine's guided path rebuilt from the library's stand-alone entry points: putative
+    matching, F-matrix filter per (view, query) pair with the engine's seeds, guided matching of
+    the surviving pairs on a table that holds the query as one more image, then the assembly of
+    SfMDataUtils.cpp:59-125 (restated on the CPU) over the guided matches, featDist from the
+    putative ones."""
+    off = sc["seg_offsets"].astype(np.int64)
+    V = len(off) - 1
+    w, h = synth.IMAGE_WH
+    mdb = gpu.db(sc["rows"], sc["seg_offsets"])
+    m = gpu.match_to_query(mdb, sc["q_desc"], ratio)
+    mdb.free()
+    sel = [v for v in range(V) if m["view_counts"][v] >= min_putative]
+    xI, xJ, poff = [], [], [0]
+    for v in sel:
+        k = m["view"] == v
+        xI.append(sc["map_xy"][off[v] + m["i"][k]]); xJ.append(sc["q_xy"][m["j"][k]])
+        poff.append(poff[-1] + int(k.sum()))
+    f = gpu.geometric_filter(np.concatenate(xI), np.concatenate(xJ), poff, [[w, h, w, h]] * len(sel), precision, rounds,
+                             seed + 77)
+    valid = [p for p in range(len(sel)) if f["valid"][p]]
+    both = gpu.db(np.concatenate([sc["rows"], sc["q_desc"]]), np.append(sc["seg_offsets"], len(sc["rows"]) + len(sc["q_desc"])))
+    goff, gi, gj = gpu.guided_match(both, np.concatenate([sc["map_xy"], sc["q_xy"]]), [(sel[p], V) for p in valid],
+                                    f["F"][valid], f["error_max"][valid] ** 2, 0.36)
+    both.free()
+    g_view, f_view, f_j, f_d = [], [], [], []
+    for n, p in enumerate(valid):
+        g_view += [sel[p]] * int(goff[n + 1] - goff[n])
+        k = m["view"] == sel[p]
+        f_view += [sel[p]] * int(k.sum()); f_j += m["j"][k].tolist(); f_d += m["d0"][k].tolist()
+    order = np.lexsort((sc["obs_feat"], sc["obs_view"]))
+    wj, wl = orc.match_set(g_view, gi.tolist(), gj.tolist(), f_view, f_j, f_d, sc["obs_view"][order],
+                           sc["obs_feat"][order], sc["obs_landmark"][order].astype(np.int64), len(sc["q_desc"]))
+    return wj, wl, len(valid), len(gi)
+
+
+@pytest.mark.parametrize("seed", [1, 4])
+def test_localize_with_guided_matching(gpu, orc, seed):
+    """mGuidedMatching (LocalizeEngine.cc:458 -> MatchUtils.cpp:407-416) inside the per-query engine:
+    exactly the correspondences the stand-alone entry points give when chained by hand."""
+    sc = synth.localization_scene(24, 800, 4000, 900, seed)
+    eng = LocalizeEngine(gpu, sc["rows"], sc["seg_offsets"], sc["obs_view"], sc["obs_feat"], sc["obs_landmark"],
+                         sc["landmark_X"], sc["K"], ratio=0.6)
+    try:
+        with pytest.raises(Exception):
+            eng.set_guided_matching(True)                        # needs the geometric filter
+        eng.set_keypoints(sc["map_xy"], sc["view_wh"], synth.IMAGE_WH)
+        eng.configure_geometric(True, 25, 4.0)
+        unguided = eng.localize(sc["q_desc"], sc["q_xy"], seed=5)
+        eng.set_guided_matching(True)
+        r = eng.localize(sc["q_desc"], sc["q_xy"], seed=5)
+        r2 = eng.localize(sc["q_desc"], sc["q_xy"], seed=5)      # cached position groups: same answer
+        b = eng.localize_batch([sc["q_desc"], sc["q_desc"][:400], sc["q_desc"]], [sc["q_xy"], sc["q_xy"][:400], sc["q_xy"]],
+                               seed=5)
+        eng.configure_geometric(False)                           # takes guided matching with it
+        plain = eng.localize(sc["q_desc"], sc["q_xy"], seed=5)
+    finally:
+        eng.close()
+    wj, wl, n_valid, n_guided = composed_guided_assembly(gpu, orc, sc, 5, 25, 4.0)
+    assert n_valid >= 12 and n_guided > 200
+    assert r["corr_qfeat"].tolist() == wj.tolist() and r["corr_landmark"].tolist() == wl.tolist()
+    assert r2["corr_qfeat"].tolist() == wj.tolist()
+    assert int(b["n_corr"][0]) == len(wj)                        # batched entry point: query rows at an offset
+    assert b["localized"][0] and np.allclose(b["center"][0], r["center"])
+    assert r["localized"] and np.linalg.norm(r["center"] - sc["center"]) < 0.05
+    assert plain["times_ms"][3] == 0
+    # guided matching only re-pairs query features the putative matching already reached
+    assert set(r["corr_qfeat"].tolist()) <= set(plain["corr_qfeat"].tolist()) | set(unguided["corr_qfeat"].tolist())
+    truth = sc["q_truth"][r["corr_qfeat"]]
+    assert (truth == r["corr_landmark"]).mean() > 0.97

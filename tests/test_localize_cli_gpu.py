@@ -89,7 +89,6 @@ def test_failure_writes_the_short_json_and_bad_input_fails(tmp_path):
     res = json.loads((out / "noise.json").read_text())
     assert sorted(res) == ["filename", "matches_dir", "sfm_data"]                 # localization.cpp:84-99
     assert run(qdir, tmp_path / "nowhere", mdir, out).returncode != 0             # unreadable sfm_data.json
-    assert run(qdir, sfm, mdir, out, "-gm").returncode != 0                       # guided matching refused
     assert run(qdir, sfm).returncode != 0                                         # usage
 
 
@@ -181,3 +180,14 @@ def test_radial_distortion_is_removed_before_matching_geometry(tmp_path):
     j = json.loads((out / "q000.json").read_text())
     assert np.linalg.norm(np.array(j["t"]) - sc["center"]) < 0.05       # with the distortion left in: decimetres off
     assert np.abs(np.array(j["R"]) - sc["R"]).max() < 5e-3
+
+
+def test_guided_matching_flag(tmp_path):
+    """-gm (localization.cpp:82): the F-matrix filter is followed by guided matching."""
+    sc, sfm, mdir, qdir, out, queries, lm_ids = make_project(tmp_path, seed=8, n_queries=2)
+    r = run(qdir, sfm, mdir, out, "-f=0.6", "-r=25", "-g=4.0", "-gm")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "localized 2 of 2" in r.stdout
+    for k, q in enumerate(queries):
+        res = json.load(open(out / ("q%03d.json" % k)))
+        assert np.linalg.norm(np.array(res["t"]) - q["center"]) < 0.05

@@ -51,7 +51,16 @@ inline void dump_string(const std::string &in, std::string &out) {
             case '\n': out += "\\n"; break;
             case '\t': out += "\\t"; break;
             case '\r': out += "\\r"; break;
-            default: out += c;
+            case '\b': out += "\\b"; break;
+            case '\f': out += "\\f"; break;
+            default:
+                if ((unsigned char)c < 0x20) {
+                    char buf[8];
+                    snprintf(buf, sizeof buf, "\\u%04x", (unsigned)(unsigned char)c);
+                    out += buf;
+                } else {
+                    out += c;       // UTF-8 bytes pass through
+                }
         }
     }
     out += '"';
@@ -132,10 +141,35 @@ private:
                     case 'r': out += '\r'; break;
                     case 'b': out += '\b'; break;
                     case 'f': out += '\f'; break;
-                    case 'u':   // \uXXXX: kept as '?', paths in sfm_data.json are ASCII
-                        out += '?';
-                        s_ += (end_ - s_ >= 5) ? 4 : 0;
+                    case 'u': {   // \uXXXX -> UTF-8 (surrogate pairs joined)
+                        auto hex4 = [&](const char *p, unsigned &v) {
+                            v = 0;
+                            for (int k = 0; k < 4; ++k) {
+                                const char c = p[k];
+                                v <<= 4;
+                                if (c >= '0' && c <= '9') v |= (unsigned)(c - '0');
+                                else if (c >= 'a' && c <= 'f') v |= (unsigned)(c - 'a' + 10);
+                                else if (c >= 'A' && c <= 'F') v |= (unsigned)(c - 'A' + 10);
+                                else return false;
+                            }
+                            return true;
+                        };
+                        unsigned cp = 0;
+                        if (end_ - s_ < 5 || !hex4(s_ + 1, cp)) return false;
+                        s_ += 4;
+                        if (cp >= 0xD800 && cp < 0xDC00 && end_ - s_ >= 7 && s_[1] == '\\' && s_[2] == 'u') {
+                            unsigned lo = 0;
+                            if (hex4(s_ + 3, lo) && lo >= 0xDC00 && lo < 0xE000) {
+                                cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+                                s_ += 6;
+                            }
+                        }
+                        if (cp < 0x80) out += (char)cp;
+                        else if (cp < 0x800) { out += (char)(0xC0 | (cp >> 6)); out += (char)(0x80 | (cp & 0x3F)); }
+                        else if (cp < 0x10000) { out += (char)(0xE0 | (cp >> 12)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
+                        else { out += (char)(0xF0 | (cp >> 18)); out += (char)(0x80 | ((cp >> 12) & 0x3F)); out += (char)(0x80 | ((cp >> 6) & 0x3F)); out += (char)(0x80 | (cp & 0x3F)); }
                         break;
+                    }
                     default: out += *s_;
                 }
                 ++s_;

@@ -164,6 +164,9 @@ def test_sfm_data_rewrite_keeps_everything_but_the_poses(tmp_path):
     names = ["v%02d" % k for k in range(5)]
     p = str(tmp_path / "sfm_data.json")
     hostlib.write_sfm_data(p, sc, names, disto=[0.05, -0.01, 0.002])
+    doc = json.load(open(p))
+    doc["root_path"] = "/d\u00e9p\u00f4t \U0001F600/\"q\"\\x\ttab"   # escapes: 2- and 4-byte UTF-8, a surrogate pair, quotes
+    json.dump(doc, open(p, "w"))                                   # ensure_ascii: written as \uXXXX escapes
     sums = hostlib.sfm_observation_sums(p)
     off = sc["seg_offsets"].astype(np.int64)
     want = sc["map_xy"][off[sc["obs_view"]] + sc["obs_feat"]].sum(axis=0)

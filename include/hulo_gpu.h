@@ -384,6 +384,28 @@ int hulo_comm_barrier(hulo_gpu *h);
 /* max over ranks of a device-time measurement */
 int hulo_comm_max_f64(hulo_gpu *h, double *value);
 
+/* All-gather of one host buffer of `bytes` per rank into recv (world x bytes, rank order): staged
+ * through the device and ncclAllGather.  A context without a communicator is a world of one. */
+int hulo_comm_allgather(hulo_gpu *h, const void *send, size_t bytes, void *recv);
+int hulo_comm_rank(const hulo_gpu *h);
+int hulo_comm_world(const hulo_gpu *h);
+
+/* Reference-direction query over a view-sharded map (the matcher of LocalizeEngine.cc:423 has one
+ * independent unit per view): every rank holds the engine and gets the same query; rank r matches a
+ * contiguous range of the view list (hulo_partition_views: balanced by descriptor rows), the
+ * surviving matches -- a few thousand records of 12 bytes -- are all-gathered, and every rank
+ * finishes the query (filter, assembly, resection) on identical inputs: the result on every rank is
+ * bit-identical to hulo_engine_localize on one GPU.  Arguments as hulo_engine_localize; collective
+ * over the communicator of the engine's context (hulo_comm_init); a world of one is the plain call. */
+int hulo_engine_localize_sharded(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t q_stride,
+                                 const double *qxy, const uint32_t *views, size_t n_views, uint64_t seed,
+                                 double *pose12, int *localized, uint32_t *corr_qfeat,
+                                 uint32_t *corr_landmark, size_t *n_corr, int32_t *inliers,
+                                 size_t *n_inliers, double *times_ms);
+/* The contiguous ranges of a view list given to the ranks: bounds[r] .. bounds[r + 1] for rank r
+ * (world + 1 entries), each holding about 1 / world of the rows.  Host arithmetic. */
+int hulo_partition_views(const uint64_t *rows_per_view, size_t n_views, int world, uint64_t *bounds);
+
 /* Row-sharded database: this rank's B holds rows [row_base, row_base + rows(B)) of the
  * global table.  Every rank passes the same A.  Each rank computes its local top-2 with
  * global indices, one ncclAllGather exchanges nA x 16 bytes per rank, and every rank

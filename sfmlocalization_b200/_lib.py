@@ -78,6 +78,12 @@ SIGNATURES = {
     "hulo_engine_set_guided_matching": (C.c_int, [_vp, C.c_int]),
     "hulo_engine_localize": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _vp, _sz, _u64, _vp, C.POINTER(C.c_int), _vp, _vp,
                                        C.POINTER(_sz), _vp, C.POINTER(_sz), _vp]),
+    "hulo_engine_localize_sharded": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _vp, _sz, _u64, _vp, C.POINTER(C.c_int), _vp, _vp,
+                                               C.POINTER(_sz), _vp, C.POINTER(_sz), _vp]),
+    "hulo_partition_views": (C.c_int, [_vp, _sz, C.c_int, _vp]),
+    "hulo_comm_allgather": (C.c_int, [_vp, _vp, _sz, _vp]),
+    "hulo_comm_rank": (C.c_int, [_vp]),
+    "hulo_comm_world": (C.c_int, [_vp]),
     "hulo_engine_localize_batch": (C.c_int, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _u64, _vp, _vp, _vp, _vp, _vp]),
     "hulo_comm_unique_id": (C.c_int, [_vp]),
     "hulo_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),

@@ -413,7 +413,19 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     for (size_t v = 0; views && v < n_views; ++v) HULO_ARG(views[v] < n_seg, "view index out of range");
     if (view_counts) memset(view_counts, 0, n_views * sizeof(uint32_t));
     // MatchUtils.cpp:299-301: nothing to do without query rows
-    if (nq < 1 || n_views == 0) return HULO_OK;
+    if (nq < 1) return HULO_OK;
+
+    // upload the query rows.  They stay in the staging buffer, folded, until the next matching
+    // call: the engine's guided matching reads them there (also on a rank of a view-sharded query
+    // that was given no view, hence before the early returns).
+    HULO_CUDA(h->stageB.reserve(nq * HULO_ROW_BYTES));
+    cudaError_t e;
+    const uint8_t *q64 = stage_rows(h->hstage1, query, nq, q_stride, &e);
+    HULO_CUDA(e);
+    HULO_CUDA(cudaMemcpyAsync(h->stageB.ptr, q64, nq * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
+    HULO_CUDA(knn2_fold_rows_launch(h->stageB.as<uint4>(), nq, h->stream));
+    h->launches++;
+    if (n_views == 0) return hulo_synchronize(h);
 
     // compact row space: the rows of the selected views, concatenated in the order given
     std::vector<uint64_t> sel_off(n_views + 1, 0);
@@ -423,16 +435,7 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     }
     const uint64_t n_rows = sel_off[n_views];
     HULO_ARG(n_rows < (uint64_t)INT_MAX, "too many rows selected");
-    if (n_rows == 0) return HULO_OK;
-
-    // upload the query rows
-    HULO_CUDA(h->stageB.reserve(nq * HULO_ROW_BYTES));
-    cudaError_t e;
-    const uint8_t *q64 = stage_rows(h->hstage1, query, nq, q_stride, &e);
-    HULO_CUDA(e);
-    HULO_CUDA(cudaMemcpyAsync(h->stageB.ptr, q64, nq * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
-    HULO_CUDA(knn2_fold_rows_launch(h->stageB.as<uint4>(), nq, h->stream));
-    h->launches++;
+    if (n_rows == 0) return hulo_synchronize(h);
 
     // items: maximal runs of views that are contiguous in the table, tiled, x chunks of the query
     const KnnConfig cfg = choose_config(h, (size_t)n_rows);

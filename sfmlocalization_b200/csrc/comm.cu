@@ -194,6 +194,30 @@ int hulo_comm_max_f64(hulo_gpu *h, double *value) {
     return HULO_OK;
 }
 
+int hulo_comm_allgather(hulo_gpu *h, const void *send, size_t bytes, void *recv) {
+    HULO_ARG(h != nullptr && (bytes == 0 || (send != nullptr && recv != nullptr)), "null argument");
+    if (bytes == 0) return HULO_OK;
+    if (h->world == 1 && !h->nccl_comm) { memcpy(recv, send, bytes); return HULO_OK; }
+    if (!h->nccl_comm) { set_error("hulo_comm_allgather: communicator not initialised"); return HULO_ERR_NCCL; }
+    HULO_CUDA(cudaSetDevice(h->device));
+    const size_t slot = (bytes + 15) & ~(size_t)15;
+    HULO_CUDA(h->scratch2.reserve(slot * (size_t)(h->world + 1)));
+    uint8_t *d_all = h->scratch2.as<uint8_t>();
+    uint8_t *d_mine = d_all + slot * (size_t)h->world;
+    HULO_CUDA(cudaMemcpyAsync(d_mine, send, bytes, cudaMemcpyHostToDevice, h->stream));
+    HULO_NCCL(g_nccl.AllGather(d_mine, d_all, slot, ncclChar, (ncclComm_t)h->nccl_comm, h->stream));
+    if (slot == bytes) {
+        HULO_CUDA(cudaMemcpyAsync(recv, d_all, bytes * (size_t)h->world, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        HULO_CUDA(cudaMemcpy2DAsync(recv, bytes, d_all, slot, bytes, (size_t)h->world, cudaMemcpyDeviceToHost, h->stream));
+    }
+    HULO_CUDA(cudaStreamSynchronize(h->stream));
+    return HULO_OK;
+}
+
+int hulo_comm_rank(const hulo_gpu *h) { return h ? h->rank : 0; }
+int hulo_comm_world(const hulo_gpu *h) { return h ? std::max(h->world, 1) : 1; }
+
 int hulo_knn2_sharded(hulo_gpu *h, const hulo_db *A, const hulo_db *B_shard, uint64_t row_base, int32_t *idx2,
                       int32_t *dist2) {
     HULO_ARG(h != nullptr && A != nullptr && B_shard != nullptr, "null argument");

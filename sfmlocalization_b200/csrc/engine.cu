@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -487,6 +488,118 @@ int hulo_engine_localize(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t
                                  e->m_i.data(), e->m_j.data(), e->m_d0.data(), cap, &n_m, e->view_counts.data());
     if (rc != HULO_OK) return rc;
     if (times_ms) times_ms[0] = now_ms() - t0;
+    return assemble_and_resect(e, nq, qxy, views, n_views, e->m_i.data(), e->m_j.data(), e->m_d0.data(),
+                               e->view_counts.data(), seed, pose12, localized, corr_qfeat, corr_landmark, n_corr,
+                               inliers, n_inliers, times_ms ? times_ms + 1 : nullptr, times_ms ? times_ms + 2 : nullptr,
+                               times_ms ? times_ms + 3 : nullptr);
+}
+
+int hulo_partition_views(const uint64_t *rows_per_view, size_t n_views, int world, uint64_t *bounds) {
+    HULO_ARG(world >= 1 && bounds != nullptr && (n_views == 0 || rows_per_view != nullptr), "bad argument");
+    uint64_t total = 0;
+    for (size_t v = 0; v < n_views; ++v) total += rows_per_view[v];
+    // contiguous ranges with about total / world rows each: range r starts at the first view whose
+    // prefix of rows reaches r * total / world
+    bounds[0] = 0;
+    size_t v = 0;
+    uint64_t prefix = 0;
+    for (int r = 1; r < world; ++r) {
+        const uint64_t want = (uint64_t)(((unsigned __int128)total * (unsigned)r) / (unsigned)world);
+        while (v < n_views && prefix + rows_per_view[v] / 2 < want) prefix += rows_per_view[v++];
+        bounds[r] = v;
+    }
+    bounds[world] = n_views;
+    return HULO_OK;
+}
+
+int hulo_engine_localize_sharded(hulo_engine *e, const uint8_t *qdesc, size_t nq, size_t q_stride, const double *qxy,
+                                 const uint32_t *views, size_t n_views, uint64_t seed, double *pose12, int *localized,
+                                 uint32_t *corr_qfeat, uint32_t *corr_landmark, size_t *n_corr, int32_t *inliers,
+                                 size_t *n_inliers, double *times_ms) {
+    HULO_ARG(e != nullptr && pose12 != nullptr && localized != nullptr, "null argument");
+    HULO_ARG(nq == 0 || (qdesc != nullptr && qxy != nullptr), "null query");
+    const int world = hulo_comm_world(e->h), rank = hulo_comm_rank(e->h);
+    if (world == 1)
+        return hulo_engine_localize(e, qdesc, nq, q_stride, qxy, views, n_views, seed, pose12, localized, corr_qfeat,
+                                    corr_landmark, n_corr, inliers, n_inliers, times_ms);
+    *localized = 0;
+    if (n_corr) *n_corr = 0;
+    if (n_inliers) *n_inliers = 0;
+    if (times_ms) times_ms[0] = times_ms[1] = times_ms[2] = times_ms[3] = 0.0;
+    if (views == nullptr) n_views = e->n_views;
+    const double t0 = now_ms();
+
+    // ---- this rank's share of the views: a contiguous range of the list, balanced by rows
+    std::vector<uint64_t> rows(n_views), bounds((size_t)world + 1);
+    for (size_t v = 0; v < n_views; ++v) {
+        const size_t s = views ? views[v] : v;
+        HULO_ARG(s < e->n_views, "view index out of range");
+        rows[v] = e->seg[s + 1] - e->seg[s];
+    }
+    hulo_partition_views(rows.data(), n_views, world, bounds.data());
+    const size_t v0 = (size_t)bounds[(size_t)rank], nv = (size_t)(bounds[(size_t)rank + 1] - bounds[(size_t)rank]);
+    size_t max_nv = 0;
+    for (int r = 0; r < world; ++r) max_nv = std::max<size_t>(max_nv, (size_t)(bounds[(size_t)r + 1] - bounds[(size_t)r]));
+    std::vector<uint32_t> my_views(std::max<size_t>(nv, 1));
+    for (size_t k = 0; k < nv; ++k) my_views[k] = views ? views[v0 + k] : (uint32_t)(v0 + k);
+
+    // ---- putative matching of the local views (the query goes to every rank: the broadcast)
+    uint64_t local_rows = 0;
+    for (size_t k = 0; k < nv; ++k) local_rows += rows[v0 + k];
+    const size_t cap = std::max<size_t>((size_t)local_rows, 1);
+    e->m_view.resize(cap); e->m_i.resize(cap); e->m_j.resize(cap); e->m_d0.resize(cap);
+    std::vector<uint32_t> local_counts(std::max<size_t>(nv, 1), 0);
+    size_t n_m = 0;
+    int rc = hulo_match_to_query(e->h, e->map, my_views.data(), nv, qdesc, nq, q_stride, e->ratio, e->m_view.data(),
+                                 e->m_i.data(), e->m_j.data(), e->m_d0.data(), cap, &n_m, local_counts.data());
+    if (rc != HULO_OK) return rc;
+
+    // ---- exchange.  Block of a rank: {n_matches, counts[max_nv], records[slots] of (i, j, d0)}.  One
+    // all-gather when every rank's matches fit the slots, else a second one sized by the largest.
+    size_t slots = std::max<size_t>(4096, 2 * nq);
+    std::vector<uint32_t> block, all;
+    std::vector<uint64_t> rank_n((size_t)world);
+    for (int round = 0; round < 2; ++round) {
+        const size_t words = 1 + max_nv + 3 * slots;
+        block.assign(words, 0);
+        block[0] = (uint32_t)n_m;
+        for (size_t k = 0; k < nv; ++k) block[1 + k] = local_counts[k];
+        const size_t fit = std::min(n_m, slots);
+        for (size_t k = 0; k < fit; ++k) {
+            block[1 + max_nv + 3 * k] = e->m_i[k];
+            block[1 + max_nv + 3 * k + 1] = e->m_j[k];
+            block[1 + max_nv + 3 * k + 2] = (uint32_t)e->m_d0[k];
+        }
+        all.resize(words * (size_t)world);
+        rc = hulo_comm_allgather(e->h, block.data(), words * sizeof(uint32_t), all.data());
+        if (rc != HULO_OK) return rc;
+        size_t largest = 0;
+        for (int r = 0; r < world; ++r) {
+            rank_n[(size_t)r] = all[words * (size_t)r];
+            largest = std::max<size_t>(largest, (size_t)rank_n[(size_t)r]);
+        }
+        if (largest <= slots) break;
+        slots = largest;                       // the same decision on every rank
+    }
+    // the matches of all views in list order: exactly what one GPU emits for the whole list
+    const size_t words = 1 + max_nv + 3 * slots;
+    size_t total = 0;
+    for (int r = 0; r < world; ++r) total += (size_t)rank_n[(size_t)r];
+    e->m_i.resize(std::max<size_t>(total, 1)); e->m_j.resize(std::max<size_t>(total, 1)); e->m_d0.resize(std::max<size_t>(total, 1));
+    e->view_counts.assign(std::max<size_t>(n_views, 1), 0);
+    size_t at = 0;
+    for (int r = 0; r < world; ++r) {
+        const uint32_t *b = all.data() + words * (size_t)r;
+        const size_t rv0 = (size_t)bounds[(size_t)r], rnv = (size_t)(bounds[(size_t)r + 1] - bounds[(size_t)r]);
+        for (size_t k = 0; k < rnv; ++k) e->view_counts[rv0 + k] = b[1 + k];
+        for (size_t k = 0; k < (size_t)rank_n[(size_t)r]; ++k, ++at) {
+            e->m_i[at] = b[1 + max_nv + 3 * k];
+            e->m_j[at] = b[1 + max_nv + 3 * k + 1];
+            e->m_d0[at] = (int32_t)b[1 + max_nv + 3 * k + 2];
+        }
+    }
+    if (times_ms) times_ms[0] = now_ms() - t0;
+    // ---- every rank finishes the query on its own: same matches, same seed, same pose
     return assemble_and_resect(e, nq, qxy, views, n_views, e->m_i.data(), e->m_j.data(), e->m_d0.data(),
                                e->view_counts.data(), seed, pose12, localized, corr_qfeat, corr_landmark, n_corr,
                                inliers, n_inliers, times_ms ? times_ms + 1 : nullptr, times_ms ? times_ms + 2 : nullptr,

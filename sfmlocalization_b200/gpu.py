@@ -445,7 +445,11 @@ class LocalizeEngine:
     def set_guided_matching(self, enabled):
         check(self.lib.hulo_engine_set_guided_matching(self.h, int(bool(enabled))))
 
-    def localize(self, qdesc, qxy, views=None, seed=1):
+    def localize_sharded(self, qdesc, qxy, views=None, seed=1):
+        """hulo_engine_localize_sharded: collective over the ranks of the context's communicator."""
+        return self.localize(qdesc, qxy, views, seed, _fn=self.lib.hulo_engine_localize_sharded)
+
+    def localize(self, qdesc, qxy, views=None, seed=1, _fn=None):
         qdesc = _rows(qdesc)
         qxy = np.ascontiguousarray(qxy, np.float64)
         nq = qdesc.shape[0]
@@ -458,9 +462,9 @@ class LocalizeEngine:
         inl = np.empty(max(nq, 1), np.int32)
         nc = C.c_size_t(0); ni = C.c_size_t(0)
         times = np.zeros(4)
-        check(self.lib.hulo_engine_localize(self.h, _ptr(qdesc), nq, qdesc.shape[1] if nq else 64, _ptr(qxy),
-                                            _ptr(views), n_views, seed, _ptr(pose), C.byref(loc), _ptr(cq), _ptr(cl),
-                                            C.byref(nc), _ptr(inl), C.byref(ni), _ptr(times)))
+        fn = _fn if _fn is not None else self.lib.hulo_engine_localize
+        check(fn(self.h, _ptr(qdesc), nq, qdesc.shape[1] if nq else 64, _ptr(qxy), _ptr(views), n_views, seed, _ptr(pose),
+                 C.byref(loc), _ptr(cq), _ptr(cl), C.byref(nc), _ptr(inl), C.byref(ni), _ptr(times)))
         return dict(localized=bool(loc.value), center=pose[:3].copy(), R=pose[3:].reshape(3, 3).copy(),
                     corr_qfeat=cq[:nc.value].copy(), corr_landmark=cl[:nc.value].copy(),
                     inliers=inl[:ni.value].copy(), times_ms=times)
@@ -519,3 +523,11 @@ def ransacTransform(A, B, thres, ransacRound, svdRatio=float("inf"), seed=1):
     """mergeSfM.ransacTransform: the similarity flavour when hulo_transform is importable (it is part
     of the reference tree), which is what the drivers get."""
     return ransacSimilarityTransform(A, B, thres, ransacRound, svdRatio, seed)
+
+
+def partition_views(rows_per_view, world):
+    """hulo_partition_views -> bounds (world + 1): rank r matches views[bounds[r]:bounds[r + 1]]."""
+    rows = np.ascontiguousarray(rows_per_view, np.uint64)
+    bounds = np.zeros(world + 1, np.uint64)
+    check(_lib.load().hulo_partition_views(_ptr(rows), len(rows), world, _ptr(bounds)))
+    return bounds.astype(np.int64)

@@ -30,9 +30,99 @@ def merge_candidates(cands):
     return np.take_along_axis(i, order, axis=1).astype(np.int32), np.take_along_axis(d, order, axis=1).astype(np.int32)
 
 
+def localize_views_gloo(rank, world):
+    """View-sharded query (hulo_engine_localize_sharded) on the CPU: the library's own partition of
+    the view list, the CPU restatement's matcher on this rank's views, an all-gather of the padded
+    blocks {n, counts, (i, j, d0)...} over gloo, concatenation in rank order -- must equal the
+    unsharded match list, view by view."""
+    import torch
+    import torch.distributed as dist_
+    from oracle import oracle as orc
+    from sfmlocalization_b200.gpu import partition_views
+    dist_.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["MASTER_PORT"],
+                             rank=rank, world_size=world)
+    sc = synth.localization_scene(13, 300, 900, 400, 31)
+    off = sc["seg_offsets"].astype(np.int64)
+    views = [11, 2, 3, 4, 5, 12, 0, 7]                      # a selection, not in id order
+    rows = [off[v + 1] - off[v] for v in views]
+    bounds = partition_views(rows, world)
+    mine = views[bounds[rank]:bounds[rank + 1]]
+    max_nv = int(np.max(np.diff(bounds)))
+
+    def match(vs):
+        out = []
+        for v in vs:
+            oi, oj, od = orc.match_view_to_query(sc["rows"][off[v]:off[v + 1]], sc["q_desc"], 0.6)
+            out.append(np.stack([oi, oj, od], axis=1).astype(np.int64).reshape(-1, 3))
+        return out
+
+    local = match(mine)
+    n_m = sum(len(x) for x in local)
+    slots = 4096
+    block = np.zeros(1 + max_nv + 3 * slots, np.int64)
+    block[0] = n_m
+    block[1:1 + len(local)] = [len(x) for x in local]
+    if n_m:
+        block[1 + max_nv:1 + max_nv + 3 * n_m] = np.concatenate(local).ravel()
+    parts = [torch.empty(len(block), dtype=torch.int64) for _ in range(world)]
+    dist_.all_gather(parts, torch.from_numpy(block))
+    dist_.destroy_process_group()
+    counts, recs = [], []
+    for r in range(world):
+        b = parts[r].numpy()
+        counts += b[1:1 + (bounds[r + 1] - bounds[r])].tolist()
+        recs.append(b[1 + max_nv:1 + max_nv + 3 * int(b[0])].reshape(-1, 3))
+    recs = np.concatenate(recs)
+    want = match(views)
+    ok = counts == [len(x) for x in want] and np.array_equal(recs, np.concatenate(want))
+    ok = ok and bounds[0] == 0 and bounds[-1] == len(views) and sum(counts) > 100
+    print("rank %d/%d views-gloo: %s" % (rank, world, "OK" if ok else "MISMATCH"))
+    sys.exit(0 if ok else 1)
+
+
+def localize_views_nccl(rank, world):
+    """hulo_engine_localize_sharded on `world` GPUs: every rank gets the single-GPU answer, bit for bit."""
+    import bench
+    from sfmlocalization_b200.gpu import HuloGpu, LocalizeEngine
+    g = HuloGpu(int(os.environ.get("LOCAL_RANK", rank)))
+    uid, path = bench.rendezvous_id(rank, world, HuloGpu.comm_unique_id)
+    sc = synth.localization_scene(24, 800, 4000, 900, 1)
+    eng = LocalizeEngine(g, sc["rows"], sc["seg_offsets"], sc["obs_view"], sc["obs_feat"], sc["obs_landmark"],
+                         sc["landmark_X"], sc["K"], ratio=0.6)
+    want = [eng.localize(sc["q_desc"], sc["q_xy"], seed=5),
+            eng.localize(sc["q_desc"], sc["q_xy"], views=[9, 2, 3, 4, 11, 17, 20], seed=6)]
+    eng.set_keypoints(sc["map_xy"], sc["view_wh"], synth.IMAGE_WH)
+    eng.configure_geometric(True, 25, 4.0)
+    eng.set_guided_matching(True)
+    want.append(eng.localize(sc["q_desc"], sc["q_xy"], seed=7))
+    eng.configure_geometric(False)
+    g.comm_init(uid, rank, world)
+    got = [eng.localize_sharded(sc["q_desc"], sc["q_xy"], seed=5),
+           eng.localize_sharded(sc["q_desc"], sc["q_xy"], views=[9, 2, 3, 4, 11, 17, 20], seed=6)]
+    eng.configure_geometric(True, 25, 4.0)
+    eng.set_guided_matching(True)
+    got.append(eng.localize_sharded(sc["q_desc"], sc["q_xy"], seed=7))
+    one = eng.localize_sharded(sc["q_desc"], sc["q_xy"], views=[3], seed=8)     # fewer views than ranks
+    g.comm_barrier()
+    ok = all(w["localized"] and a["localized"] and np.array_equal(a["center"], w["center"]) and
+             np.array_equal(a["R"], w["R"]) and np.array_equal(a["corr_qfeat"], w["corr_qfeat"]) and
+             np.array_equal(a["corr_landmark"], w["corr_landmark"]) and np.array_equal(a["inliers"], w["inliers"])
+             for a, w in zip(got, want))
+    ok = ok and len(one["corr_qfeat"]) > 0
+    eng.close(); g.close()
+    if rank == 0 and os.path.exists(path):
+        os.remove(path)
+    print("rank %d/%d views-nccl: %s" % (rank, world, "OK" if ok else "MISMATCH"))
+    sys.exit(0 if ok else 1)
+
+
 def main():
     mode = sys.argv[1]
     rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+    if mode == "views-gloo":
+        return localize_views_gloo(rank, world)
+    if mode == "views-nccl":
+        return localize_views_nccl(rank, world)
     A, B, _ = synth.descriptor_sets(NA, NB, 123)
     B[20000:20040] = B[5:45]                        # cross-shard duplicates
     lo, hi = shard_bounds(NB, world)[rank]

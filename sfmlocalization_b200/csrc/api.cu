@@ -511,9 +511,8 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     uint32_t *o_view = h->scratch3.as<uint32_t>();
     uint32_t *o_i = o_view + n_rows, *o_j = o_i + n_rows;
     int32_t *o_d = reinterpret_cast<int32_t *>(o_j + n_rows);
-    HULO_CUDA(compact_launch(val, dist, (uint32_t)n_rows, h->scratch1.as<uint64_t>(), (uint32_t)n_views, d_blocks,
-                             o_view, o_i, o_j, o_d, d_seg_out, d_total, h->stream));
-    h->launches += kCompactLaunches;
+    { int nl = 0; HULO_CUDA(compact_launch(val, dist, (uint32_t)n_rows, h->scratch1.as<uint64_t>(), (uint32_t)n_views, d_blocks,
+                             o_view, o_i, o_j, o_d, d_seg_out, d_total, h->stream, &nl)); h->launches += nl; }
 
     // total + per-view offsets first, then exactly the survivors
     HULO_CUDA(h->hstage0.reserve((n_views + 2) * sizeof(uint64_t)));
@@ -660,9 +659,8 @@ int hulo_match_to_queries(hulo_gpu *h, const hulo_db *map, const uint32_t *views
         uint32_t *d_blocks = reinterpret_cast<uint32_t *>(d_seg_out + (n_segs + 1));
         uint32_t *o_i = h->scratch3.as<uint32_t>(), *o_j = o_i + rows_total;
         int32_t *o_d = reinterpret_cast<int32_t *>(o_j + rows_total);
-        HULO_CUDA(compact_launch(val, dist, (uint32_t)rows_total, h->scratch1.as<uint64_t>(), (uint32_t)n_segs, d_blocks,
-                                 nullptr, o_i, o_j, o_d, d_seg_out, d_total, h->stream));
-        h->launches += kCompactLaunches;
+        { int nl = 0; HULO_CUDA(compact_launch(val, dist, (uint32_t)rows_total, h->scratch1.as<uint64_t>(), (uint32_t)n_segs, d_blocks,
+                                 nullptr, o_i, o_j, o_d, d_seg_out, d_total, h->stream, &nl)); h->launches += nl; }
         h_seg_out.resize(n_segs + 2);
         HULO_CUDA(cudaMemcpyAsync(h_seg_out.data(), d_total, (n_segs + 2) * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
         HULO_CUDA(cudaStreamSynchronize(h->stream));
@@ -800,9 +798,8 @@ int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size
             uint64_t *d_seg_out = d_total + 1;
             uint32_t *d_blocks = reinterpret_cast<uint32_t *>(d_seg_out + (bp + 1));
             uint32_t *o_i = h->scratch3.as<uint32_t>(), *o_j = o_i + n_rows;
-            HULO_CUDA(compact_launch(val, nullptr, (uint32_t)n_rows, d_row_off, (uint32_t)bp, d_blocks, nullptr, o_i,
-                                     o_j, nullptr, d_seg_out, d_total, h->stream));
-            h->launches += kCompactLaunches;
+            { int nl = 0; HULO_CUDA(compact_launch(val, nullptr, (uint32_t)n_rows, d_row_off, (uint32_t)bp, d_blocks, nullptr, o_i,
+                                     o_j, nullptr, d_seg_out, d_total, h->stream, &nl)); h->launches += nl; }
 
             h_seg_out.resize(bp + 2);
             HULO_CUDA(cudaMemcpyAsync(h_seg_out.data(), d_total, (bp + 2) * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));

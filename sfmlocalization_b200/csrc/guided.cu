@@ -259,9 +259,8 @@ int guided_match_sides(hulo_gpu *h, const GuidedSide &SI, const GuidedSide &SJ, 
             uint64_t *d_seg_out = d_total + 1;
             uint32_t *d_blocks = reinterpret_cast<uint32_t *>(d_seg_out + (bp + 1));
             uint32_t *o_i = h->scratch3.as<uint32_t>(), *o_j = o_i + n_rows;
-            HULO_CUDA(compact_launch(val, nullptr, (uint32_t)n_rows, d_row_off, (uint32_t)bp, d_blocks, nullptr, o_i, o_j,
-                                     nullptr, d_seg_out, d_total, h->stream));
-            h->launches += kCompactLaunches;
+            { int nl = 0; HULO_CUDA(compact_launch(val, nullptr, (uint32_t)n_rows, d_row_off, (uint32_t)bp, d_blocks, nullptr, o_i, o_j,
+                                     nullptr, d_seg_out, d_total, h->stream, &nl)); h->launches += nl; }
             h_seg_out.resize(bp + 2);
             HULO_CUDA(cudaMemcpyAsync(h_seg_out.data(), d_total, (bp + 2) * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
             HULO_CUDA(cudaStreamSynchronize(h->stream));

@@ -140,13 +140,34 @@ __global__ void compact_scan_kernel(uint32_t *block_counts, uint32_t n_blocks, u
     }
 }
 
+// SELF_SCAN: block_offsets holds the raw per-block counts and the block sums its predecessors
+// itself (small launches: saves the scan kernel); otherwise block_offsets is the exclusive scan.
+// seg_out_off[s] = number of survivors in compact rows [0, seg_off[s]): written by the thread whose
+// rows hold the boundary (its exclusive prefix + the survivors of its own rows before it);
+// boundaries at or beyond n_rows get the total from the last block.
+template <bool SELF_SCAN>
 __global__ void compact_write_kernel(const int32_t *__restrict__ val, const int32_t *__restrict__ dist,
                                      uint32_t n_rows, const uint64_t *__restrict__ seg_off, uint32_t n_seg,
                                      const uint32_t *__restrict__ block_offsets, uint32_t *__restrict__ out_seg,
                                      uint32_t *__restrict__ out_i, uint32_t *__restrict__ out_j,
-                                     int32_t *__restrict__ out_d) {
+                                     int32_t *__restrict__ out_d, uint64_t *__restrict__ seg_out_off,
+                                     uint64_t *__restrict__ total) {
     __shared__ uint32_t s_warp[kCompactThreads / 32];
+    __shared__ uint32_t s_pre[kCompactThreads / 32];
     const uint32_t base = blockIdx.x * kCompactBlockRows + threadIdx.x * kRowsPerThread;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t block_base;
+    if (SELF_SCAN) {
+        uint32_t pre = 0;
+        for (uint32_t b = threadIdx.x; b < blockIdx.x; b += kCompactThreads) pre += block_offsets[b];
+        for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+        if (lane == 0) s_pre[warp] = pre;
+        __syncthreads();
+        block_base = 0;
+        for (int w = 0; w < kCompactThreads / 32; ++w) block_base += s_pre[w];
+    } else {
+        block_base = block_offsets[blockIdx.x];
+    }
     int32_t v[kRowsPerThread];
     uint32_t c = 0;
 #pragma unroll
@@ -157,16 +178,19 @@ __global__ void compact_write_kernel(const int32_t *__restrict__ val, const int3
     }
     // exclusive scan of c over the block
     uint32_t inc = c;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    uint32_t warp_base = 0;
-    for (int w = 0; w < warp; ++w) warp_base += s_warp[w];
-    uint32_t pos = block_offsets[blockIdx.x] + warp_base + inc - c;
+    uint32_t warp_base = 0, block_count = 0;
+    for (int w = 0; w < kCompactThreads / 32; ++w) {
+        if (w < warp) warp_base += s_warp[w];
+        block_count += s_warp[w];
+    }
+    const uint32_t pos0 = block_base + warp_base + inc - c;
+    uint32_t pos = pos0;
 #pragma unroll
     for (int k = 0; k < kRowsPerThread; ++k) {
         if (v[k] >= 0) {
@@ -179,29 +203,35 @@ __global__ void compact_write_kernel(const int32_t *__restrict__ val, const int3
             ++pos;
         }
     }
-}
-
-// seg_out_off[s] = number of survivors in compact rows [0, seg_off[s]).  One warp per segment
-// boundary: the survivors before the boundary's compaction block come from the block scan, the
-// rows of that block up to the boundary are counted with coalesced loads and ballots.
-__global__ void compact_seg_offsets_kernel(const int32_t *__restrict__ val, uint32_t n_rows,
-                                           const uint64_t *__restrict__ seg_off, uint32_t n_seg,
-                                           const uint32_t *__restrict__ block_offsets,
-                                           uint64_t *__restrict__ seg_out_off) {
-    const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
-    if (s > n_seg) return;
-    const uint64_t row = seg_off[s];
-    const uint32_t b = (uint32_t)(row / kCompactBlockRows);
-    const uint32_t start = b * kCompactBlockRows;
-    const uint32_t end = (uint32_t)(row < n_rows ? row : n_rows);
-    uint32_t cnt = 0;
-    for (uint32_t r0 = start; r0 < end; r0 += 32) {
-        const uint32_t r = r0 + lane;
-        const bool live = r < end && val[r] >= 0;
-        cnt += __popc(__ballot_sync(0xffffffffu, live));
+    if (seg_out_off) {
+        if (base < n_rows) {
+            // first boundary at or after this thread's first row
+            uint32_t lo = 0, hi = n_seg + 1;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (seg_off[mid] < base) lo = mid + 1; else hi = mid;
+            }
+            const uint64_t end = min((uint64_t)base + kRowsPerThread, (uint64_t)n_rows);
+            for (uint32_t s = lo; s <= n_seg && seg_off[s] < end; ++s) {
+                const uint32_t upto = (uint32_t)(seg_off[s] - base);
+                uint32_t before = 0;
+#pragma unroll
+                for (int k = 0; k < kRowsPerThread; ++k)
+                    if ((uint32_t)k < upto && v[k] >= 0) ++before;
+                seg_out_off[s] = (uint64_t)pos0 + before;
+            }
+        }
+        if (blockIdx.x == gridDim.x - 1) {
+            uint32_t lo = 0, hi = n_seg + 1;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (seg_off[mid] < n_rows) lo = mid + 1; else hi = mid;
+            }
+            for (uint32_t s = lo + threadIdx.x; s <= n_seg; s += kCompactThreads)
+                seg_out_off[s] = (uint64_t)block_base + block_count;
+        }
     }
-    if (lane == 0) seg_out_off[s] = (uint64_t)block_offsets[b] + cnt;   // block_offsets has n_blocks + 1 entries
+    if (SELF_SCAN && total && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total = (uint64_t)block_base + block_count;
 }
 
 }  // namespace
@@ -236,18 +266,31 @@ cudaError_t post_pair_filter_launch(uint32_t n_rows, const uint64_t *row_off, co
 cudaError_t compact_launch(const int32_t *val, const int32_t *dist, uint32_t n_rows, const uint64_t *seg_off,
                            uint32_t n_seg, uint32_t *block_counts, uint32_t *out_seg, uint32_t *out_i,
                            uint32_t *out_j, int32_t *out_d, uint64_t *seg_out_off, uint64_t *total,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, int *n_launches) {
     const uint32_t n_blocks = (n_rows + kCompactBlockRows - 1) / kCompactBlockRows;
-    if (n_blocks > 0)
-        compact_count_kernel<<<n_blocks, kCompactThreads, 0, stream>>>(val, n_rows, block_counts);
-    compact_scan_kernel<<<1, 1024, 0, stream>>>(block_counts, n_blocks, total);
-    if (n_blocks > 0)
-        compact_write_kernel<<<n_blocks, kCompactThreads, 0, stream>>>(val, dist, n_rows, seg_off, n_seg,
-                                                                      block_counts, out_seg, out_i, out_j,
-                                                                      out_d);
-    if (seg_out_off)
-        compact_seg_offsets_kernel<<<(n_seg + 1 + 7) / 8, 256, 0, stream>>>(val, n_rows, seg_off, n_seg,
-                                                                          block_counts, seg_out_off);
+    int launches = 0;
+    if (n_blocks == 0) {
+        // nothing to compact: total and every segment offset are zero
+        cudaError_t e = cudaMemsetAsync(total, 0, sizeof(uint64_t), stream);
+        if (e != cudaSuccess) return e;
+        if (seg_out_off) e = cudaMemsetAsync(seg_out_off, 0, ((size_t)n_seg + 1) * sizeof(uint64_t), stream);
+        if (n_launches) *n_launches = 0;
+        return e;
+    }
+    compact_count_kernel<<<n_blocks, kCompactThreads, 0, stream>>>(val, n_rows, block_counts);
+    ++launches;
+    if (n_blocks <= 1024) {
+        // few blocks: each one sums the counts of its predecessors itself
+        compact_write_kernel<true><<<n_blocks, kCompactThreads, 0, stream>>>(val, dist, n_rows, seg_off, n_seg, block_counts,
+                                                                            out_seg, out_i, out_j, out_d, seg_out_off, total);
+        ++launches;
+    } else {
+        compact_scan_kernel<<<1, 1024, 0, stream>>>(block_counts, n_blocks, total);
+        compact_write_kernel<false><<<n_blocks, kCompactThreads, 0, stream>>>(val, dist, n_rows, seg_off, n_seg, block_counts,
+                                                                             out_seg, out_i, out_j, out_d, seg_out_off, total);
+        launches += 2;
+    }
+    if (n_launches) *n_launches = launches;
     return cudaGetLastError();
 }
 

@@ -30,12 +30,11 @@ cudaError_t post_pair_filter_launch(uint32_t n_rows, const uint64_t *row_off, co
 // Outputs: out_seg[k], out_i[k] (row inside its segment), out_j[k] = val, out_d[k] = dist
 // (out_seg / out_d / dist may be null), seg_out_off[n_seg+1] = output offset of each segment,
 // *total (device) = number of survivors.  block_counts needs ceil(n_rows / 2048) + 1 entries.
+// *n_launches (optional) = kernels launched, for hulo_launch_count: 2 up to 1024 blocks, 3 above.
 cudaError_t compact_launch(const int32_t *val, const int32_t *dist, uint32_t n_rows, const uint64_t *seg_off,
                            uint32_t n_seg, uint32_t *block_counts, uint32_t *out_seg, uint32_t *out_i,
                            uint32_t *out_j, int32_t *out_d, uint64_t *seg_out_off, uint64_t *total,
-                           cudaStream_t stream);
+                           cudaStream_t stream, int *n_launches = nullptr);
 constexpr uint32_t kCompactBlockRows = 2048;
-// number of kernels the three entry points above launch (for hulo_launch_count)
-constexpr int kCompactLaunches = 4;
 
 }  // namespace hulo

@@ -514,10 +514,21 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     { int nl = 0; HULO_CUDA(compact_launch(val, dist, (uint32_t)n_rows, h->scratch1.as<uint64_t>(), (uint32_t)n_views, d_blocks,
                              o_view, o_i, o_j, o_d, d_seg_out, d_total, h->stream, &nl)); h->launches += nl; }
 
-    // total + per-view offsets first, then exactly the survivors
-    HULO_CUDA(h->hstage0.reserve((n_views + 2) * sizeof(uint64_t)));
+    // One round trip in the common case: the totals and per-view offsets travel together with the
+    // first `spec` survivors of every output array into pinned memory; only a query with more
+    // survivors than that fetches the rest in a second round.
+    const size_t spec = std::min<size_t>(std::min<size_t>((size_t)n_rows, cap), 16384);
+    const size_t head_bytes = ((n_views + 2) * sizeof(uint64_t) + 15) & ~(size_t)15;
+    HULO_CUDA(h->hstage0.reserve(head_bytes + 4 * spec * sizeof(uint32_t)));
     uint64_t *h_tot = h->hstage0.as<uint64_t>();
+    uint32_t *h_spec = reinterpret_cast<uint32_t *>(h->hstage0.as<uint8_t>() + head_bytes);
     HULO_CUDA(cudaMemcpyAsync(h_tot, d_total, (n_views + 2) * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    if (spec > 0) {
+        if (out_view) HULO_CUDA(cudaMemcpyAsync(h_spec, o_view, spec * 4, cudaMemcpyDeviceToHost, h->stream));
+        HULO_CUDA(cudaMemcpyAsync(h_spec + spec, o_i, spec * 4, cudaMemcpyDeviceToHost, h->stream));
+        HULO_CUDA(cudaMemcpyAsync(h_spec + 2 * spec, o_j, spec * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (out_d0) HULO_CUDA(cudaMemcpyAsync(h_spec + 3 * spec, o_d, spec * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
     HULO_CUDA(cudaStreamSynchronize(h->stream));
     const uint64_t total = h_tot[0];
     *n_out = (size_t)total;
@@ -529,11 +540,19 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     }
     if (total > 0) {
         HULO_ARG(out_i != nullptr && out_j != nullptr, "null output");
-        if (out_view) HULO_CUDA(cudaMemcpyAsync(out_view, o_view, total * 4, cudaMemcpyDeviceToHost, h->stream));
-        HULO_CUDA(cudaMemcpyAsync(out_i, o_i, total * 4, cudaMemcpyDeviceToHost, h->stream));
-        HULO_CUDA(cudaMemcpyAsync(out_j, o_j, total * 4, cudaMemcpyDeviceToHost, h->stream));
-        if (out_d0) HULO_CUDA(cudaMemcpyAsync(out_d0, o_d, total * 4, cudaMemcpyDeviceToHost, h->stream));
-        HULO_CUDA(cudaStreamSynchronize(h->stream));
+        const size_t got = std::min<size_t>((size_t)total, spec);
+        if (out_view) memcpy(out_view, h_spec, got * 4);
+        memcpy(out_i, h_spec + spec, got * 4);
+        memcpy(out_j, h_spec + 2 * spec, got * 4);
+        if (out_d0) memcpy(out_d0, h_spec + 3 * spec, got * 4);
+        if (total > got) {
+            const size_t rest = (size_t)total - got;
+            if (out_view) HULO_CUDA(cudaMemcpyAsync(out_view + got, o_view + got, rest * 4, cudaMemcpyDeviceToHost, h->stream));
+            HULO_CUDA(cudaMemcpyAsync(out_i + got, o_i + got, rest * 4, cudaMemcpyDeviceToHost, h->stream));
+            HULO_CUDA(cudaMemcpyAsync(out_j + got, o_j + got, rest * 4, cudaMemcpyDeviceToHost, h->stream));
+            if (out_d0) HULO_CUDA(cudaMemcpyAsync(out_d0 + got, o_d + got, rest * 4, cudaMemcpyDeviceToHost, h->stream));
+            HULO_CUDA(cudaStreamSynchronize(h->stream));
+        }
     }
     return HULO_OK;
 }

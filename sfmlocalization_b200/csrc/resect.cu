@@ -604,14 +604,18 @@ int stage_problem(hulo_gpu *h, const std::vector<double> &x2dn, const double *X3
     pb.d_logc_k = pb.d_logc_n + (N + 1);
     pb.loge0 = log10(4.0 * (double)(N > 3 ? N - 3 : 1));
     pb.logalpha0 = log10(M_PI);
+    // one copy: the four arrays are packed in pinned memory in the device layout.  Every caller
+    // synchronises the stream before the staging buffer can be written again.
+    HULO_CUDA(h->hstage1.reserve(bytes));
+    uint8_t *hp = h->hstage1.as<uint8_t>();
     if (N > 0) {
-        HULO_CUDA(cudaMemcpyAsync(pb.d_x2dn, x2dn.data(), 2 * N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-        HULO_CUDA(cudaMemcpyAsync(pb.d_X3d, X3d, 3 * N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        memcpy(hp, x2dn.data(), 2 * N * sizeof(double));
+        memcpy(hp + 2 * N * sizeof(double), X3d, 3 * N * sizeof(double));
     }
-    HULO_CUDA(cudaMemcpyAsync(pb.d_logc_n, lcn.data(), (N + 1) * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    HULO_CUDA(cudaMemcpyAsync(pb.d_logc_k, lck.data(), (N + 1) * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    // the host vectors die with this frame; the copies above are from pageable memory and have
-    // been staged by the runtime before cudaMemcpyAsync returned
+    memcpy(hp + 5 * N * sizeof(double), lcn.data(), (N + 1) * sizeof(float));
+    memcpy(hp + 5 * N * sizeof(double) + (N + 1) * sizeof(float), lck.data(), (N + 1) * sizeof(float));
+    HULO_CUDA(cudaMemcpyAsync(pb.d_x2dn, hp, 5 * N * sizeof(double) + 2 * (N + 1) * sizeof(float), cudaMemcpyHostToDevice,
+                              h->stream));
     return HULO_OK;
 }
 

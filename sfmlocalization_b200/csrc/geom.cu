@@ -688,13 +688,30 @@ int hulo_geometric_filter(hulo_gpu *h, const double *xI, const double *xJ, const
     HULO_CUDA(h->scratch3.reserve(std::max<size_t>(total, 1) * 8));
     int32_t *d_inl = h->scratch3.as<int32_t>();
     int32_t *d_pool = d_inl + total;
-    if (total) {
-        HULO_CUDA(cudaMemcpyAsync(d_xI, xI, total * 16, cudaMemcpyHostToDevice, h->stream));
-        HULO_CUDA(cudaMemcpyAsync(d_xJ, xJ, total * 16, cudaMemcpyHostToDevice, h->stream));
+    // A small call (the pairs of one query) is latency: its inputs are packed in pinned memory in the
+    // device layout and go up in one copy, its outputs come back in two.  A large one (a
+    // reconstruction) copies straight from and to the caller's arrays.
+    const bool packed = in_bytes <= (1u << 20);
+    if (packed) {
+        HULO_CUDA(h->hstage1.reserve(in_bytes));
+        uint8_t *hp = h->hstage1.as<uint8_t>();
+        if (total) {
+            memcpy(hp, xI, total * 16);
+            memcpy(hp + total * 16, xJ, total * 16);
+        }
+        memcpy(hp + total * 32, pair_offsets, (n_pairs + 1) * 8);
+        if (pair_seeds) memcpy(hp + total * 32 + (n_pairs + 1) * 8, pair_seeds, n_pairs * 8);
+        memcpy(hp + total * 32 + (n_pairs + 1) * 8 + n_pairs * 8, image_sizes, n_pairs * 16);
+        HULO_CUDA(cudaMemcpyAsync(d_xI, hp, in_bytes - 64, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        if (total) {
+            HULO_CUDA(cudaMemcpyAsync(d_xI, xI, total * 16, cudaMemcpyHostToDevice, h->stream));
+            HULO_CUDA(cudaMemcpyAsync(d_xJ, xJ, total * 16, cudaMemcpyHostToDevice, h->stream));
+        }
+        HULO_CUDA(cudaMemcpyAsync(d_off, pair_offsets, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+        HULO_CUDA(cudaMemcpyAsync(d_sizes, image_sizes, n_pairs * 16, cudaMemcpyHostToDevice, h->stream));
+        if (pair_seeds) HULO_CUDA(cudaMemcpyAsync(d_seeds, pair_seeds, n_pairs * 8, cudaMemcpyHostToDevice, h->stream));
     }
-    HULO_CUDA(cudaMemcpyAsync(d_off, pair_offsets, (n_pairs + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-    HULO_CUDA(cudaMemcpyAsync(d_sizes, image_sizes, n_pairs * 16, cudaMemcpyHostToDevice, h->stream));
-    if (pair_seeds) HULO_CUDA(cudaMemcpyAsync(d_seeds, pair_seeds, n_pairs * 8, cudaMemcpyHostToDevice, h->stream));
 
     GeoParams g;
     g.xI = reinterpret_cast<const double2 *>(d_xI);
@@ -717,6 +734,26 @@ int hulo_geometric_filter(hulo_gpu *h, const double *xI, const double *xJ, const
     HULO_CUDA(cudaGetLastError());
     h->launches++;
 
+    if (packed) {
+        const size_t per_pair = n_pairs * (9 + 2) * sizeof(double) + n_pairs * 8;
+        HULO_CUDA(h->hstage0.reserve(per_pair + total * 4 + 64));
+        uint8_t *ho = h->hstage0.as<uint8_t>();
+        HULO_CUDA(cudaMemcpyAsync(ho, d_F, per_pair, cudaMemcpyDeviceToHost, h->stream));
+        if (total) HULO_CUDA(cudaMemcpyAsync(ho + per_pair, d_inl, total * 4, cudaMemcpyDeviceToHost, h->stream));
+        HULO_CUDA(cudaStreamSynchronize(h->stream));
+        const uint8_t *o = ho;
+        if (F) memcpy(F, o, n_pairs * 72);
+        o += n_pairs * 72;
+        if (error_max) memcpy(error_max, o, n_pairs * 8);
+        o += n_pairs * 8;
+        if (nfa) memcpy(nfa, o, n_pairs * 8);
+        o += n_pairs * 8;
+        memcpy(valid, o, n_pairs * 4);
+        o += n_pairs * 4;
+        memcpy(n_inliers, o, n_pairs * 4);
+        if (total) memcpy(inliers, ho + per_pair, total * 4);
+        return HULO_OK;
+    }
     HULO_CUDA(cudaMemcpyAsync(valid, d_valid, n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
     HULO_CUDA(cudaMemcpyAsync(n_inliers, d_ninl, n_pairs * 4, cudaMemcpyDeviceToHost, h->stream));
     if (F) HULO_CUDA(cudaMemcpyAsync(F, d_F, n_pairs * 72, cudaMemcpyDeviceToHost, h->stream));

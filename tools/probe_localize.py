@@ -25,4 +25,17 @@ with HuloGpu(0) as g:
         st.append(r["times_ms"])
     print(json.dumps(dict(wall_ms_median=float(np.median(wall)), stages_ms_median=np.median(np.array(st), axis=0).tolist(),
                           launches_per_query=None)))
+    eng.set_keypoints(sc["map_xy"], sc["view_wh"], synth.IMAGE_WH)
+    eng.configure_geometric(True, 25, 4.0)
+    for guided in (False, True):
+        eng.set_guided_matching(guided)
+        eng.localize(sc["q_desc"], sc["q_xy"], seed=1)
+        wall, st = [], []
+        for k in range(reps):
+            t0 = time.perf_counter()
+            r = eng.localize(sc["q_desc"], sc["q_xy"], seed=200 + k)
+            wall.append((time.perf_counter() - t0) * 1e3)
+            st.append(r["times_ms"])
+        print(json.dumps(dict(geometric_filter=True, guided=guided, wall_ms_median=float(np.median(wall)),
+                              stages_ms_median=np.median(np.array(st), axis=0).tolist(), localized=bool(r["localized"]))))
     eng.close()

@@ -201,17 +201,21 @@ int hulo_comm_allgather(hulo_gpu *h, const void *send, size_t bytes, void *recv)
     if (!h->nccl_comm) { set_error("hulo_comm_allgather: communicator not initialised"); return HULO_ERR_NCCL; }
     HULO_CUDA(cudaSetDevice(h->device));
     const size_t slot = (bytes + 15) & ~(size_t)15;
-    HULO_CUDA(h->scratch2.reserve(slot * (size_t)(h->world + 1)));
+    const size_t world = (size_t)h->world;
+    HULO_CUDA(h->scratch2.reserve(slot * (world + 1)));
     uint8_t *d_all = h->scratch2.as<uint8_t>();
-    uint8_t *d_mine = d_all + slot * (size_t)h->world;
-    HULO_CUDA(cudaMemcpyAsync(d_mine, send, bytes, cudaMemcpyHostToDevice, h->stream));
+    uint8_t *d_mine = d_all + slot * world;
+    // both directions through pinned memory: the caller's buffers are usually pageable, and a
+    // pageable copy of this size costs more than the collective
+    HULO_CUDA(h->hstage0.reserve(slot * (world + 1)));
+    uint8_t *p_all = h->hstage0.as<uint8_t>();
+    uint8_t *p_mine = p_all + slot * world;
+    memcpy(p_mine, send, bytes);
+    HULO_CUDA(cudaMemcpyAsync(d_mine, p_mine, bytes, cudaMemcpyHostToDevice, h->stream));
     HULO_NCCL(g_nccl.AllGather(d_mine, d_all, slot, ncclChar, (ncclComm_t)h->nccl_comm, h->stream));
-    if (slot == bytes) {
-        HULO_CUDA(cudaMemcpyAsync(recv, d_all, bytes * (size_t)h->world, cudaMemcpyDeviceToHost, h->stream));
-    } else {
-        HULO_CUDA(cudaMemcpy2DAsync(recv, bytes, d_all, slot, bytes, (size_t)h->world, cudaMemcpyDeviceToHost, h->stream));
-    }
+    HULO_CUDA(cudaMemcpyAsync(p_all, d_all, slot * world, cudaMemcpyDeviceToHost, h->stream));
     HULO_CUDA(cudaStreamSynchronize(h->stream));
+    for (size_t r = 0; r < world; ++r) memcpy(static_cast<uint8_t *>(recv) + r * bytes, p_all + r * slot, bytes);
     return HULO_OK;
 }
 

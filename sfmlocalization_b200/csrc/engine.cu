@@ -556,7 +556,9 @@ int hulo_engine_localize_sharded(hulo_engine *e, const uint8_t *qdesc, size_t nq
 
     // ---- exchange.  Block of a rank: {n_matches, counts[max_nv], records[slots] of (i, j, d0)}.  One
     // all-gather when every rank's matches fit the slots, else a second one sized by the largest.
-    size_t slots = std::max<size_t>(4096, 2 * nq);
+    // sized for the usual yield (a few matches per query descriptor over all views, shared by the
+    // ranks) with a factor of two to spare
+    size_t slots = std::max<size_t>(256, 4 * nq / (size_t)world);
     std::vector<uint32_t> block, all;
     std::vector<uint64_t> rank_n((size_t)world);
     for (int round = 0; round < 2; ++round) {

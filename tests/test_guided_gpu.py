@@ -104,3 +104,62 @@ def test_duplicate_positions_empty_images_and_degenerate_models(gpu, orc):
         assert int(o[1]) == int(o[5]) == int(o[6])             # empty / single-feature / zero-model pairs: nothing
     finally:
         db.free()
+
+
+def test_adversarial_geometry(gpu, orc):
+    """Geometry that stresses the gate: lines along the axes, diagonal, through a corner, with the
+    epipole far outside the image, a degenerate model; features off the image on every side and
+    non-finite positions; gates from sub-pixel to 'everything'; images of one feature, of 40
+    features within 20 px, one spanning 60000 px, 300 features at one point: the match lists stay
+    those of the CPU restatement."""
+    rng = np.random.default_rng(11)
+    n_img = 6
+    sizes = [700, 900, 1, 40, 800, 600]
+    rows = [synth.random_rows(n, 500 + k) for k, n in enumerate(sizes)]
+    # descriptors of every image near those of image 0's, so that nearest / second nearest are meaningful
+    base = rows[0]
+    for k in range(1, n_img):
+        src = base[rng.integers(0, len(base), sizes[k])].copy()
+        flip = rng.random(src.shape) < 0.02
+        rows[k] = src ^ (flip * rng.integers(1, 255, src.shape)).astype(np.uint8)
+        rows[k][:, 61:] = 0
+    xys = [np.stack([rng.uniform(-300, 2300, n), rng.uniform(-200, 1300, n)], axis=1) for n in sizes]
+    xys[1][::50] = np.nan
+    xys[1][7] = [np.inf, 3.0]
+    xys[3] = rng.uniform(0, 20, (sizes[3], 2))                 # everything in one cell
+    xys[4][:, 0] *= 30.0                                       # 60000 px wide: the cell size grows
+    xys[5][:300] = xys[5][0]                                   # 300 features at one point
+    off = np.zeros(n_img + 1, np.uint64); off[1:] = np.cumsum(sizes)
+    allrows = np.concatenate(rows); allxy = np.concatenate(xys)
+
+    def cross(e):
+        return np.array([[0, -e[2], e[1]], [e[2], 0, -e[0]], [-e[1], e[0], 0]], float)
+    Fs = [
+        cross([1.0, 0.0, 0.0]),                    # lines through (inf, 0): horizontal lines y = const
+        cross([0.0, 1.0, 0.0]),                    # vertical lines
+        cross([960.0, 540.0, 1.0]),                # pencil through the image centre: every slope
+        cross([-5000.0, 300.0, 1.0]),              # epipole far to the left
+        cross([0.0, 0.0, 1.0]),                    # lines through the corner (0, 0)
+        np.array([[0, 0, 0], [0, 0, 0], [0, 0, 1.0]]),    # l = (0, 0, 1): degenerate, matches nothing
+        np.array([[0, 0, 1e-9], [0, 0, 1.0], [0, 0, -640.0]]),   # one fixed, almost horizontal line
+        rng.normal(size=(3, 3)),
+    ]
+    pairs, Fl, thr = [], [], []
+    for (I, J) in [(0, 1), (1, 0), (0, 4), (4, 0), (0, 5), (5, 1), (0, 3), (3, 0), (0, 2), (2, 0), (1, 5)]:
+        for F in Fs:
+            for t in (0.25, 16.0, 2500.0, 1e12):
+                pairs.append((I, J)); Fl.append(F); thr.append(t)
+    Fl = np.array(Fl); thr = np.array(thr)
+    db = gpu.db(allrows, off)
+    try:
+        o, gi, gj = gpu.guided_match(db, allxy, pairs, Fl, thr, dist_ratio=0.8)
+    finally:
+        db.free()
+    total = 0
+    for p, (I, J) in enumerate(pairs):
+        wi, wj = orc.guided_match(Fl[p], xys[I], rows[I], xys[J], rows[J], thr[p], 0.8)
+        a, b = int(o[p]), int(o[p + 1])
+        assert gi[a:b].tolist() == wi.tolist() and gj[a:b].tolist() == wj.tolist(), (p, I, J, thr[p])
+        total += len(wi)
+    assert total > 2000
+

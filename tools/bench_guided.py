@@ -15,6 +15,10 @@ from sfmlocalization_b200.gpu import HuloGpu  # noqa: E402
 
 def main():
     n_img, rows = 200, 5000
+    if "--rows" in sys.argv:                      # larger images: fewer of them
+        k = sys.argv.index("--rows")
+        rows = int(sys.argv[k + 1]); n_img = 24
+        del sys.argv[k:k + 2]
     allrows, off = synth.image_collection(n_img, rows, 2000, overlap=0.3)
     rng = np.random.default_rng(5)
     xy = np.stack([rng.uniform(0, 1920, n_img * rows), rng.uniform(0, 1080, n_img * rows)], axis=1)

@@ -749,6 +749,44 @@ struct ResectJob {
         }
         last_T = T;
     }
+    // (residual, index) ascending.  The residuals are non-negative doubles (or +inf), whose bit
+    // patterns order like the values: a stable byte-wise radix sort from the index order gives
+    // exactly the order of the comparison sort it replaces, in a third of the time at N ~ 700.
+    // Bytes on which all keys agree (most of the exponent) are skipped.
+    std::vector<EI> ei_tmp;
+    void sort_by_residual() {
+        if (N < 64) {
+            std::sort(ei.begin(), ei.end(), [](const EI &a, const EI &b) { return a.e < b.e || (a.e == b.e && a.i < b.i); });
+            return;
+        }
+        uint32_t hist[8][256];
+        memset(hist, 0, sizeof hist);
+        for (size_t i = 0; i < N; ++i) {
+            uint64_t k;
+            if (ei[i].e == 0.0) ei[i].e = 0.0;            // -0.0 would sort as the largest key
+            memcpy(&k, &ei[i].e, 8);
+            for (int b = 0; b < 8; ++b) ++hist[b][(k >> (8 * b)) & 255];
+        }
+        ei_tmp.resize(N);
+        EI *src = ei.data(), *dst = ei_tmp.data();
+        for (int b = 0; b < 8; ++b) {
+            uint32_t *h = hist[b];
+            bool trivial = false;
+            for (int d = 0; d < 256; ++d)
+                if (h[d] == N) { trivial = true; break; }
+            if (trivial) continue;
+            uint32_t run = 0;
+            for (int d = 0; d < 256; ++d) { const uint32_t c = h[d]; h[d] = run; run += c; }
+            for (size_t i = 0; i < N; ++i) {
+                uint64_t k;
+                memcpy(&k, &src[i].e, 8);
+                dst[h[(k >> (8 * b)) & 255]++] = src[i];
+            }
+            std::swap(src, dst);
+        }
+        if (src != ei.data()) memcpy(ei.data(), src, N * sizeof(EI));
+    }
+
     // Final scoring of a model in fp64 on the host: residuals, (residual, index) order, NFA.
     double finalize(const double *M) {
         for (size_t i = 0; i < N; ++i) {
@@ -761,7 +799,7 @@ struct ResectJob {
             if (!(e == e)) e = INFINITY;
             ei[i] = EI{e, i};
         }
-        std::sort(ei.begin(), ei.end(), [](const EI &a, const EI &b) { return a.e < b.e || (a.e == b.e && a.i < b.i); });
+        sort_by_residual();
         double bn = INFINITY;
         size_t bk = 3;
         for (size_t k = 4; k <= N; ++k) {

@@ -162,6 +162,25 @@ static const uint8_t *stage_rows(HostBuf &hb, const uint8_t *rows, size_t n, siz
     return dst;
 }
 
+// The same into pinned memory for every stride, with the fold of the device layout (knn2.cuh)
+// applied on the way: a query image is a few thousand rows, the host folds them while it copies and
+// the upload needs neither a pageable transfer nor the fold kernel.
+static const uint8_t *stage_rows_folded(HostBuf &hb, const uint8_t *rows, size_t n, size_t stride, cudaError_t *err) {
+    *err = hb.reserve(std::max<size_t>(n, 1) * HULO_ROW_BYTES);
+    if (*err != cudaSuccess) return nullptr;
+    uint8_t *dst = hb.as<uint8_t>();
+    const size_t w = std::min<size_t>(stride, HULO_ROW_BYTES);
+    for (size_t i = 0; i < n; ++i) {
+        uint32_t r[16];
+        memcpy(r, rows + i * stride, w);
+        if (w < HULO_ROW_BYTES) memset(reinterpret_cast<uint8_t *>(r) + w, 0, HULO_ROW_BYTES - w);
+        for (int k = 0; k < 5; ++k) r[3 * k + 2] ^= r[3 * k] ^ r[3 * k + 1];
+        r[15] ^= r[11] ^ r[14];                                   // folded w11, w14: w15 = w9 ^ ... ^ w15
+        memcpy(dst + i * HULO_ROW_BYTES, r, HULO_ROW_BYTES);
+    }
+    return dst;
+}
+
 int run_flat_packed(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t nB, uint32_t row_base) {
     return run_flat(h, A, nA, B, nB, row_base, true);
 }
@@ -420,11 +439,17 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     // that was given no view, hence before the early returns).
     HULO_CUDA(h->stageB.reserve(nq * HULO_ROW_BYTES));
     cudaError_t e;
-    const uint8_t *q64 = stage_rows(h->hstage1, query, nq, q_stride, &e);
-    HULO_CUDA(e);
-    HULO_CUDA(cudaMemcpyAsync(h->stageB.ptr, q64, nq * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
-    HULO_CUDA(knn2_fold_rows_launch(h->stageB.as<uint4>(), nq, h->stream));
-    h->launches++;
+    if (nq <= 65536) {
+        const uint8_t *q64 = stage_rows_folded(h->hstage1, query, nq, q_stride, &e);
+        HULO_CUDA(e);
+        HULO_CUDA(cudaMemcpyAsync(h->stageB.ptr, q64, nq * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
+    } else {
+        const uint8_t *q64 = stage_rows(h->hstage1, query, nq, q_stride, &e);
+        HULO_CUDA(e);
+        HULO_CUDA(cudaMemcpyAsync(h->stageB.ptr, q64, nq * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
+        HULO_CUDA(knn2_fold_rows_launch(h->stageB.as<uint4>(), nq, h->stream));
+        h->launches++;
+    }
     if (n_views == 0) return hulo_synchronize(h);
 
     // compact row space: the rows of the selected views, concatenated in the order given

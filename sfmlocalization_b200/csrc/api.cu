@@ -101,6 +101,67 @@ static FlatPlan plan_flat(const hulo_gpu *h, size_t nA, size_t nB) {
     return p;
 }
 
+// ------------------------------------------------------------- K1t tile images
+void tc_image_register(hulo_gpu *h, const void *rows) {
+    for (auto &e : h->tc_images) if (e.rows == rows) { e.valid = false; return; }
+    h->tc_images.push_back(hulo_gpu::TcImage{rows, 0, false, DevBuf{}});
+}
+void tc_image_invalidate(hulo_gpu *h, const void *rows) {
+    for (auto &e : h->tc_images) if (e.rows == rows) e.valid = false;
+}
+void tc_image_drop(hulo_gpu *h, const void *rows) {
+    for (size_t k = 0; k < h->tc_images.size(); ++k)
+        if (h->tc_images[k].rows == rows) {
+            h->tc_images[k].img.release();
+            h->tc_images.erase(h->tc_images.begin() + (long)k);
+            return;
+        }
+}
+// Tile image of `n` folded rows at `rows`: the cached one when the rows are a registered table,
+// else expanded into `scratch`.
+static int tc_image_for(hulo_gpu *h, const uint4 *rows, size_t n, DevBuf &scratch, const uint8_t **out) {
+    for (auto &e : h->tc_images) {
+        if (e.rows != rows) continue;
+        if (!e.valid || e.n != n) {
+            HULO_CUDA(e.img.reserve(knn2_tc_image_bytes(n)));
+            HULO_CUDA(knn2_tc_expand_launch(rows, n, e.img.as<uint8_t>(), h->stream));
+            h->launches++;
+            e.n = n;
+            e.valid = true;
+        }
+        *out = e.img.as<uint8_t>();
+        return HULO_OK;
+    }
+    HULO_CUDA(scratch.reserve(knn2_tc_image_bytes(n)));
+    HULO_CUDA(knn2_tc_expand_launch(rows, n, scratch.as<uint8_t>(), h->stream));
+    h->launches++;
+    *out = scratch.as<uint8_t>();
+    return HULO_OK;
+}
+
+// K1t for a flat searcher table against a flat database: same partial-key format as K1.
+static int run_flat_k1_tc(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t nB, FlatRun *run) {
+    uint32_t n_mtiles = 0, n_chunks = 0, rpc = 0;
+    knn2_tc_plan(nA, nB, h->sm_count, &n_mtiles, &n_chunks, &rpc);
+    run->n_chunks = n_chunks; run->rows_per_chunk = rpc; run->slot_stride = (nA + 31) & ~(size_t)31;
+    if (n_chunks == 0) return HULO_OK;
+    const uint8_t *imgA = nullptr, *imgB = nullptr;
+    int rc = tc_image_for(h, A, nA, h->tc_scratchA, &imgA);
+    if (rc != HULO_OK) return rc;
+    rc = tc_image_for(h, B, nB, h->tc_scratchB, &imgB);
+    if (rc != HULO_OK) return rc;
+    HULO_CUDA(h->partial.reserve((size_t)n_chunks * run->slot_stride * sizeof(uint2)));
+    TcParams tp{};
+    tp.imgA = imgA; tp.imgB = imgB;
+    tp.nA = (uint32_t)nA; tp.nB = (uint32_t)nB;
+    tp.n_mtiles = n_mtiles; tp.n_chunks = n_chunks; tp.rows_per_chunk = rpc;
+    tp.slot_stride = run->slot_stride;
+    tp.partial = h->partial.as<uint2>();
+    HULO_CUDA(knn2_tc_launch(tp, h->sm_count, h->stream));
+    h->launches++;
+    return HULO_OK;
+}
+
 // K1 for a flat searcher table against a flat database: per-chunk keys left in h->partial.
 int run_flat_k1(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t nB, uint32_t row_base,
                 FlatRun *run) {
@@ -110,6 +171,7 @@ int run_flat_k1(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t n
     h->last_nA = nA;
     run->n_chunks = 0; run->rows_per_chunk = 1; run->slot_stride = 0;
     if (nA == 0) return HULO_OK;
+    if (h->knn_engine == HULO_KNN_TC) return run_flat_k1_tc(h, A, nA, B, nB, run);
     FlatPlan pl = plan_flat(h, nA, nB);
     run->n_chunks = pl.n_chunks; run->rows_per_chunk = pl.rows_per_chunk; run->slot_stride = pl.slot_stride;
     if (pl.n_chunks > 0) {
@@ -245,9 +307,21 @@ int hulo_gpu_create(int device, hulo_gpu **out) {
             return HULO_ERR_ARG;
         }
     }
+    {
+        const char *eng = getenv("HULO_KNN_ENGINE");
+        if (eng && (!strcmp(eng, "tc") || !strcmp(eng, "1"))) h->knn_engine = HULO_KNN_TC;
+    }
     *out = h;
     return HULO_OK;
 }
+
+int hulo_gpu_set_knn_engine(hulo_gpu *h, int engine) {
+    HULO_ARG(h != nullptr, "null context");
+    HULO_ARG(engine == HULO_KNN_INT || engine == HULO_KNN_TC, "unknown engine");
+    h->knn_engine = engine;
+    return HULO_OK;
+}
+int hulo_gpu_knn_engine(const hulo_gpu *h) { return h ? h->knn_engine : -1; }
 
 void hulo_comm_destroy_internal(hulo_gpu *h);
 
@@ -259,6 +333,9 @@ void hulo_gpu_destroy(hulo_gpu *h) {
     DevBuf *bufs[] = {&h->partial, &h->counter, &h->items, &h->knn_idx, &h->knn_dist, &h->packed, &h->gathered,
                       &h->stageA, &h->stageB, &h->scratch0, &h->scratch1, &h->scratch2, &h->scratch3, &h->lfact};
     for (DevBuf *b : bufs) b->release();
+    for (auto &e : h->tc_images) e.img.release();
+    h->tc_scratchA.release();
+    h->tc_scratchB.release();
     h->hstage0.release();
     h->hstage1.release();
     if (h->ev_start) cudaEventDestroy(h->ev_start);
@@ -322,6 +399,7 @@ int hulo_db_upload(hulo_gpu *h, const uint8_t *rows, size_t n, size_t stride, co
     }
     if (seg_offsets) db->seg.assign(seg_offsets, seg_offsets + n_seg + 1);
     else db->seg = {0, (uint64_t)n};
+    tc_image_register(h, db->rows);
     int rc = hulo_db_update(h, db, rows, n, stride);
     if (rc != HULO_OK) { hulo_db_free(db); return rc; }
     *out = db;
@@ -334,6 +412,7 @@ int hulo_db_update(hulo_gpu *h, hulo_db *db, const uint8_t *rows, size_t n, size
     HULO_ARG(n == 0 || rows != nullptr, "rows is null");
     HULO_ARG(stride >= 1, "stride must be >= 1");
     if (n != db->n) { db->n = n; db->seg = {0, (uint64_t)n}; }
+    tc_image_invalidate(h, db->rows);
     if (n == 0) return HULO_OK;
     if (stride == HULO_ROW_BYTES) {
         HULO_CUDA(cudaMemcpyAsync(db->rows, rows, n * HULO_ROW_BYTES, cudaMemcpyHostToDevice, h->stream));
@@ -354,6 +433,7 @@ int hulo_db_update(hulo_gpu *h, hulo_db *db, const uint8_t *rows, size_t n, size
 void hulo_db_free(hulo_db *db) {
     if (!db) return;
     if (db->owner) cudaSetDevice(db->owner->device);
+    if (db->owner) tc_image_drop(db->owner, db->rows);
     if (db->rows) cudaFree(db->rows);
     delete db;
 }

@@ -9,6 +9,7 @@
 
 #include "../../include/hulo_gpu.h"
 #include "knn2.cuh"
+#include "knn2_tc.cuh"
 
 namespace hulo {
 
@@ -99,6 +100,15 @@ struct hulo_gpu {
     uint64_t launches = 0;
     hulo::KnnConfig knn_cfg{512, 4, 89, 1};  // best of the sweeps on C3 (profiles/r1_k1_variant_sweep.txt, r1_k1_sweep_folded.txt)
     bool knn_cfg_forced = false;
+
+    // K1 arithmetic: HULO_KNN_INT = integer pipes (knn2.cu, the conformant default),
+    // HULO_KNN_TC = int8 contraction on the tensor cores (knn2_tc.cu); flat searches only
+    int knn_engine = 0;
+    // tile images of K1t: one per registered table (built on first use, dropped when the table
+    // changes), and two scratch images for staged rows
+    struct TcImage { const void *rows; size_t n; bool valid; hulo::DevBuf img; };
+    std::vector<TcImage> tc_images;
+    hulo::DevBuf tc_scratchA, tc_scratchB;
 
     hulo::DevBuf partial;      // K1 per-item keys
     hulo::DevBuf counter;      // K1 dynamic item counter

@@ -400,6 +400,7 @@ int hulo_comm_max_f64(hulo_gpu *h, double *value);
 /* All-gather of one host buffer of `bytes` per rank into recv (world x bytes, rank order): staged
  * through the device and ncclAllGather.  A context without a communicator is a world of one. */
 int hulo_comm_allgather(hulo_gpu *h, const void *send, size_t bytes, void *recv);
+const char *hulo_comm_exchange_kind(const hulo_gpu *h);
 int hulo_comm_rank(const hulo_gpu *h);
 int hulo_comm_world(const hulo_gpu *h);
 
@@ -421,8 +422,17 @@ int hulo_partition_views(const uint64_t *rows_per_view, size_t n_views, int worl
 
 /* Row-sharded database: this rank's B holds rows [row_base, row_base + rows(B)) of the
  * global table.  Every rank passes the same A.  Each rank computes its local top-2 with
- * global indices, one ncclAllGather exchanges nA x 16 bytes per rank, and every rank
- * merges to the result a single GPU would give (bit-identical).  Outputs as hulo_knn2. */
+ * global indices, the candidates (nA x 16 bytes per rank) are exchanged, and every rank
+ * merges to the result a single GPU would give (bit-identical).  Outputs as hulo_knn2.
+ * The exchange the call uses is what hulo_comm_exchange_kind reports:
+ *   "peer-store"      (default) the chunk-merge kernel stores each record straight into every
+ *                     rank's exchange buffer (CUDA IPC mappings over NVLink) and raises a flag;
+ *                     the merge kernel waits on the flags.  NCCL only carried the set-up.
+ *   "nccl-allgather"  one ncclAllGather of the packed records, when the peers cannot be mapped
+ *                     or HULO_EXCHANGE=nccl is set;
+ *   "none"            a world of one.
+ * hulo_gpu_destroy of a context that ran the peer-store exchange is collective (the ranks meet
+ * between closing their mappings and freeing the exported buffers). */
 int hulo_knn2_sharded(hulo_gpu *h, const hulo_db *A, const hulo_db *B_shard, uint64_t row_base,
                       int32_t *idx2, int32_t *dist2);
 

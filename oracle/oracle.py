@@ -58,6 +58,17 @@ def num_threads():
     return int(lib().orc_num_threads())
 
 
+def use_all_cores():
+    """Run the OpenMP loops on every core this process may use, ignoring OMP_NUM_THREADS
+    (torchrun exports OMP_NUM_THREADS=1 to its ranks).  Returns the thread count."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
 def pad_rows(rows):
     """orc_pad_rows: N x w (w <= 64) -> N x 64, zero padded (FileUtils.cpp:77-92)."""
     rows = _u8(rows)

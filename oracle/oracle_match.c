@@ -43,6 +43,16 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* Thread count of the parallel loops from now on, whatever OMP_NUM_THREADS said at start-up
+ * (launchers such as torchrun export OMP_NUM_THREADS=1 to every rank). */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* Hamming distance of two rows of `len` bytes (len <= 64). */
 static inline int row_hamming(const uint8_t *a, const uint8_t *b, size_t len) {
     int d = 0;

@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libhulo_gpu.so")
 OK, ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_CAPACITY = 0, 1, 2, 3, 4
 PAIR_ONE_TO_ONE, PAIR_DROP_LAST = 1, 2
 PAIR_REFERENCE = PAIR_ONE_TO_ONE | PAIR_DROP_LAST
+KNN_INT, KNN_TC = 0, 1
 DIST_NONE = 2**31 - 1
 IDX_NONE = -1
 
@@ -37,6 +38,8 @@ SIGNATURES = {
     "hulo_timer_stop": (C.c_int, [_vp, C.POINTER(_f32)]),
     "hulo_synchronize": (C.c_int, [_vp]),
     "hulo_launch_count": (_u64, [_vp]),
+    "hulo_gpu_set_knn_engine": (C.c_int, [_vp, C.c_int]),
+    "hulo_gpu_knn_engine": (C.c_int, [_vp]),
     "hulo_db_upload": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz, _pp]),
     "hulo_db_update": (C.c_int, [_vp, _vp, _vp, _sz, _sz]),
     "hulo_db_free": (None, [_vp]),
@@ -82,6 +85,7 @@ SIGNATURES = {
                                                C.POINTER(_sz), _vp, C.POINTER(_sz), _vp]),
     "hulo_partition_views": (C.c_int, [_vp, _sz, C.c_int, _vp]),
     "hulo_comm_allgather": (C.c_int, [_vp, _vp, _sz, _vp]),
+    "hulo_comm_exchange_kind": (C.c_char_p, [_vp]),
     "hulo_comm_rank": (C.c_int, [_vp]),
     "hulo_comm_world": (C.c_int, [_vp]),
     "hulo_engine_localize_batch": (C.c_int, [_vp, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _u64, _vp, _vp, _vp, _vp, _vp]),

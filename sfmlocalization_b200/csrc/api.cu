@@ -157,6 +157,8 @@ static int run_flat_k1_tc(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B
     tp.n_mtiles = n_mtiles; tp.n_chunks = n_chunks; tp.rows_per_chunk = rpc;
     tp.slot_stride = run->slot_stride;
     tp.partial = h->partial.as<uint2>();
+    static const int cluster = env_int("HULO_TC_CLUSTER", 1);      // tuning sweeps
+    tp.cluster = cluster;
     HULO_CUDA(knn2_tc_launch(tp, h->sm_count, h->stream));
     h->launches++;
     return HULO_OK;

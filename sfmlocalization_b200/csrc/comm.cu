@@ -1,13 +1,24 @@
 // comm.cu -- the one exchange step of the path: a row-sharded database returns its local
-// top-2 per searcher row and the candidates (16 bytes per row per rank) are merged after a
-// single ncclAllGather over NVLink.  NCCL is bound lazily with dlopen so that single-GPU use
-// and the CPU-side symbol check do not need it.
+// top-2 per searcher row and the candidates (16 bytes per row per rank) are merged.  Default data
+// plane: stores into peer-mapped buffers (CUDA IPC over NVLink) fused into the chunk-merge kernel,
+// with a flag handshake (knn2.cu); NCCL carries the set-up traffic (IPC handles, barriers) and a
+// single ncclAllGather is the fallback data plane.  NCCL is bound lazily with dlopen and its few
+// types are declared here, so neither building nor single-GPU use needs NCCL installed.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 #include <dlfcn.h>
-#include <nccl.h>
+
+// The slice of nccl.h this file uses (NCCL 2.x ABI): declared locally so that the library builds on
+// a machine without the NCCL headers.
+extern "C" {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclInt8 = 0, ncclChar = 0, ncclFloat64 = 8, ncclDouble = 8 } ncclDataType_t;
+typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3 } ncclRedOp_t;
+}
 
 #include "context.cuh"
 
@@ -73,11 +84,16 @@ bool load_nccl() {
 //   [2][world][cap] int4 records | [2][world] uint32 flags | done counter | status
 size_t px_bytes(int world, uint32_t cap) { return (size_t)2 * world * cap * sizeof(int4) + 4096; }
 
+// Collective over the communicator when peers are mapped: every rank closes its mappings of the
+// peers' buffers, all ranks meet, and only then is the exported buffer freed (freeing memory that an
+// importer still has open is undefined behaviour).
 void px_release(hulo_gpu *h) {
+    bool had_peers = false;
     for (int g = 0; g < h->world && g < kMaxPeers; ++g) {
-        if (g != h->rank && h->px_peer_base[g]) cudaIpcCloseMemHandle(h->px_peer_base[g]);
+        if (g != h->rank && h->px_peer_base[g]) { cudaIpcCloseMemHandle(h->px_peer_base[g]); had_peers = true; }
         h->px_peer_base[g] = nullptr;
     }
+    if (had_peers && h->nccl_comm) hulo_comm_barrier(h);
     if (h->px_own) cudaFree(h->px_own);
     h->px_own = nullptr;
     h->px_ready = false;
@@ -89,10 +105,14 @@ int px_setup(hulo_gpu *h, size_t rows) {
     px_release(h);
     const uint32_t cap = (uint32_t)((rows + 255) & ~(size_t)255);
     const size_t bytes = px_bytes(h->world, cap);
-    HULO_CUDA(cudaMalloc(&h->px_own, bytes));
-    HULO_CUDA(cudaMemsetAsync(h->px_own, 0, bytes, h->stream));
+    // a local failure must not leave the peers alone inside the collectives below: carry it to the
+    // agreement step instead of returning
+    bool ok = true;
     cudaIpcMemHandle_t mine;
-    HULO_CUDA(cudaIpcGetMemHandle(&mine, h->px_own));
+    memset(&mine, 0, sizeof mine);
+    if (cudaMalloc(&h->px_own, bytes) != cudaSuccess) { cudaGetLastError(); h->px_own = nullptr; ok = false; }
+    if (ok && cudaMemsetAsync(h->px_own, 0, bytes, h->stream) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    if (ok && cudaIpcGetMemHandle(&mine, h->px_own) != cudaSuccess) { cudaGetLastError(); ok = false; }
     // all-gather the 64-byte handles with the communicator that already exists
     HULO_CUDA(h->scratch2.reserve((size_t)(h->world + 1) * sizeof(cudaIpcMemHandle_t)));
     uint8_t *d_all = h->scratch2.as<uint8_t>();
@@ -102,7 +122,18 @@ int px_setup(hulo_gpu *h, size_t rows) {
     std::vector<cudaIpcMemHandle_t> all((size_t)h->world);
     HULO_CUDA(cudaMemcpyAsync(all.data(), d_all, all.size() * sizeof mine, cudaMemcpyDeviceToHost, h->stream));
     HULO_CUDA(cudaStreamSynchronize(h->stream));
-    bool ok = true;
+    // did every rank get as far as exporting a buffer?
+    {
+        double neg = ok ? -1.0 : 0.0;
+        int rc = hulo_comm_max_f64(h, &neg);
+        if (rc != HULO_OK) return rc;
+        if (-neg < 0.5) {
+            if (h->px_own) cudaFree(h->px_own);
+            h->px_own = nullptr;
+            h->px_disabled = true;
+            return HULO_OK;
+        }
+    }
     for (int g = 0; g < h->world; ++g) {
         if (g == h->rank) { h->px_peer_base[g] = h->px_own; continue; }
         void *p = nullptr;
@@ -219,6 +250,13 @@ int hulo_comm_allgather(hulo_gpu *h, const void *send, size_t bytes, void *recv)
     return HULO_OK;
 }
 
+const char *hulo_comm_exchange_kind(const hulo_gpu *h) {
+    if (!h || h->world <= 1) return "none";
+    const char *ex = getenv("HULO_EXCHANGE");
+    if (h->px_disabled || (ex && strcmp(ex, "nccl") == 0)) return "nccl-allgather";
+    return "peer-store";
+}
+
 int hulo_comm_rank(const hulo_gpu *h) { return h ? h->rank : 0; }
 int hulo_comm_world(const hulo_gpu *h) { return h ? std::max(h->world, 1) : 1; }
 
@@ -253,7 +291,11 @@ int hulo_knn2_sharded(hulo_gpu *h, const hulo_db *A, const hulo_db *B_shard, uin
             if (rc2 != HULO_OK) return rc2;
             unsigned int st = 0;
             HULO_CUDA(cudaMemcpy(&st, h->px.status, sizeof st, cudaMemcpyDeviceToHost));
-            if (st) { set_error("hulo_knn2_sharded: a peer did not deliver its candidates within 10 s"); return HULO_ERR_NCCL; }
+            if (st) {
+                HULO_CUDA(cudaMemset(h->px.status, 0, sizeof st));      // reported once, not on every later fetch
+                set_error("hulo_knn2_sharded: a peer did not deliver its candidates within 10 s");
+                return HULO_ERR_NCCL;
+            }
         }
         return HULO_OK;
     }

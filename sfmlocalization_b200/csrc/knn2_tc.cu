@@ -11,9 +11,9 @@ constexpr int kStages = 4;                       // ring of B stages (256 rows x
 constexpr uint32_t kStageBytes = 32768;
 constexpr uint32_t kKChunks = 4;                 // 512 K-bytes = 4 stages per accumulator tile
 constexpr uint32_t kABytes = 65536;              // resident searcher tile
-constexpr uint32_t kThreads = 192;               // warp 0: copies, warp 1: MMA issue, warps 2..5: epilogue
+constexpr uint32_t kThreads = 320;               // warp 0: copies, warp 1: MMA issue, warps 2..5 / 6..9: epilogue of even / odd tiles
 constexpr uint32_t kTmemCols = 512;              // two 128 x 256 int32 accumulators
-constexpr size_t kSmemBytes = 1024 + kABytes + (size_t)kStages * kStageBytes + 256;
+constexpr size_t kSmemBytes = 1024 + kABytes + (size_t)kStages * kStageBytes + 256 + 2 * 128 * sizeof(uint2);
 
 constexpr int32_t kThrNone = -1024;              // "second best" threshold while fewer than two candidates
 constexpr int32_t kDotMasked = -2048;            // accumulator value given to columns past the chunk end
@@ -51,11 +51,36 @@ __device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src_gme
         "l"(src_gmem), "r"(bytes), "r"(bar)
         : "memory");
 }
+// the same, delivered to the same shared-memory offset (data and mbarrier) of every CTA of the
+// cluster named in cta_mask
+__device__ __forceinline__ void bulk_load_multicast(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar,
+                                                    uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            dst_smem),
+        "l"(src_gmem), "r"(bytes), "r"(bar), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // all tcgen05 operations issued so far by this thread -> one arrival on the mbarrier when they finish
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// the same arrival on the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cta_mask)
+                 : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32, M = 128, N = 256, K = 32
 __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -112,13 +137,21 @@ __device__ __forceinline__ int32_t max3(int32_t a, int32_t b, int32_t c) { retur
 // keys of the 16 columns through the same min/max update as K1.
 __device__ __forceinline__ void scan_block(const int32_t (&v)[64], uint32_t row0, uint32_t &best0, uint32_t &best1,
                                            int32_t &thr) {
+    // the four group maxima first: 32 independent min/max instructions the scheduler can overlap
+    // (the compares below depend on each other through thr)
+    int32_t gm[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         const int32_t *w = &v[16 * g];
         const int32_t m0 = max3(w[0], w[1], w[2]), m1 = max3(w[3], w[4], w[5]), m2 = max3(w[6], w[7], w[8]);
         const int32_t m3 = max3(w[9], w[10], w[11]), m4 = max3(w[12], w[13], w[14]);
-        const int32_t m = max(max3(m0, m1, m2), max3(m3, m4, w[15]));
-        if (m > thr) {
+        gm[g] = max(max3(m0, m1, m2), max3(m3, m4, w[15]));
+    }
+    if (max(max(gm[0], gm[1]), max(gm[2], gm[3])) <= thr) return;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int32_t *w = &v[16 * g];
+        if (gm[g] > thr) {
             const int32_t t0 = thr;
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
@@ -134,6 +167,12 @@ __device__ __forceinline__ void scan_block(const int32_t (&v)[64], uint32_t row0
     }
 }
 
+// CL = CTAs per cluster.  The CTAs of a cluster work on CL consecutive searcher tiles against the
+// SAME database chunk in lockstep: every stage of B is fetched once per cluster, each CTA issuing
+// 1/CL of it as a multicast bulk copy into all CL shared memories, which divides the L2 -> SM
+// traffic (the first limit of the single-CTA form) by CL.  A stage is refilled when the MMAs of all
+// CL CTAs have released it (multicast tcgen05.commit onto every CTA's "empty" barrier).
+template <int CL>
 __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -144,8 +183,10 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
     const uint32_t bar_b_full = bars + 16, bar_b_empty = bar_b_full + 8 * kStages;
     const uint32_t bar_acc_full = bar_b_empty + 8 * kStages, bar_acc_empty = bar_acc_full + 16;
     const uint32_t tmem_slot = bar_acc_empty + 16;
+    const uint32_t xchg = bars + 256;                    // [2 item parities][128 rows] uint2: keys of the odd-tile group
     uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     volatile uint32_t *tmem_slot_gen = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+    uint2 *xchg_gen = reinterpret_cast<uint2 *>(smem_gen + (xchg - smem_base));
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -154,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
         mbar_init(bar_a_empty, 1);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(bar_b_full + 8 * s, 1);
-            mbar_init(bar_b_empty + 8 * s, 1);
+            mbar_init(bar_b_empty + 8 * s, CL);           // one commit per CTA of the cluster
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_acc_full + 8 * b, 1);
@@ -170,17 +211,23 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();             // peers' barriers exist before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
-    const uint32_t n_items = p.n_mtiles * p.n_chunks;
+    const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+    const uint32_t cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+    const uint32_t n_mgroups = (p.n_mtiles + CL - 1) / CL;
+    const uint32_t n_items = n_mgroups * p.n_chunks;
+    constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
     if (warp == 0) {
         // ===== producer: searcher tile once per item, database stages through the ring =====
         if (lane == 0) {
             uint32_t it = 0, stage = 0, ph = 0;
-            for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-                const uint32_t mt = w % p.n_mtiles, c = w / p.n_mtiles;
+            for (uint32_t w = cluster_id; w < n_items; w += n_clusters, ++it) {
+                // a cluster past the last searcher tile repeats it (its results are not written)
+                const uint32_t mt = min((w % n_mgroups) * CL + crank, p.n_mtiles - 1u), c = w / n_mgroups;
                 const uint32_t b_row0 = c * p.rows_per_chunk;
                 const uint32_t b_rows = min(p.rows_per_chunk, p.nB - b_row0);
                 const uint32_t n_tiles = (b_rows + kTcTileN - 1) / kTcTileN;
@@ -193,8 +240,16 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
                         mbar_wait(bar_b_empty + 8 * stage, ph ^ 1u);
                         mbar_expect_tx(bar_b_full + 8 * stage, kStageBytes);
                         const uint8_t *s0 = src + (size_t)(2 * t) * kTcTileBytes + kc * 16384u;
-                        bulk_load(sB + stage * kStageBytes, s0, 16384u, bar_b_full + 8 * stage);
-                        bulk_load(sB + stage * kStageBytes + 16384u, s0 + kTcTileBytes, 16384u, bar_b_full + 8 * stage);
+                        if constexpr (CL == 1) {
+                            bulk_load(sB + stage * kStageBytes, s0, 16384u, bar_b_full + 8 * stage);
+                            bulk_load(sB + stage * kStageBytes + 16384u, s0 + kTcTileBytes, 16384u, bar_b_full + 8 * stage);
+                        } else {
+                            // this CTA's share of the stage (32 KB / CL), to every CTA of the cluster
+                            constexpr uint32_t kShare = kStageBytes / CL;
+                            const uint32_t off = crank * kShare;              // offset inside the 32 KB stage
+                            const uint8_t *sp = s0 + (size_t)(off >> 14) * kTcTileBytes + (off & 16383u);
+                            bulk_load_multicast(sB + stage * kStageBytes + off, sp, kShare, bar_b_full + 8 * stage, kMask);
+                        }
                         if (++stage == kStages) { stage = 0; ph ^= 1u; }
                     }
                 }
@@ -205,8 +260,8 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
         // ===== MMA issuer: one thread =====
         if (lane == 0) {
             uint32_t it = 0, stage = 0, ph = 0, acc_it = 0;
-            for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-                const uint32_t c = w / p.n_mtiles;
+            for (uint32_t w = cluster_id; w < n_items; w += n_clusters, ++it) {
+                const uint32_t c = w / n_mgroups;
                 const uint32_t b_row0 = c * p.rows_per_chunk;
                 const uint32_t b_rows = min(p.rows_per_chunk, p.nB - b_row0);
                 const uint32_t n_tiles = (b_rows + kTcTileN - 1) / kTcTileN;
@@ -225,7 +280,9 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
                             const uint64_t db = smem_desc(sB + stage * kStageBytes + j * 256u, p.lbo, p.sbo);
                             tc_mma_i8(tmem_d, da, db, kIdesc, (kc | j) != 0u);
                         }
-                        tc_commit(bar_b_empty + 8 * stage);            // stage free once these MMAs have read it
+                        // stage free once these MMAs have read it (in every CTA of the cluster)
+                        if constexpr (CL == 1) tc_commit(bar_b_empty + 8 * stage);
+                        else tc_commit_multicast(bar_b_empty + 8 * stage, kMask);
                         if (++stage == kStages) { stage = 0; ph ^= 1u; }
                     }
                     tc_commit(bar_acc_full + 8 * buf);
@@ -235,27 +292,30 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
         }
         __syncwarp();
     } else {
-        // ===== epilogue: warp q of a warpgroup reads TMEM lanes 32q .. 32q+31 =====
+        // ===== epilogue: warp q of a warpgroup reads TMEM lanes 32q .. 32q+31.  Two groups of four
+        // warps: group 0 (warps 2..5) drains accumulator 0, group 1 (warps 6..9) accumulator 1, i.e.
+        // they take alternate tiles, so each has two MMA tile times per tile.  Each thread keeps the
+        // best two of ITS tiles; the groups are merged per item through shared memory. =====
         const uint32_t quarter = warp & 3u;
+        const uint32_t grp = (warp - 2u) >> 2;                   // accumulator buffer this warp drains
         const uint32_t row = quarter * 32u + lane;               // searcher row within the tile
-        uint32_t acc_it = 0;
-        for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
-            const uint32_t mt = w % p.n_mtiles, c = w / p.n_mtiles;
+        uint32_t acc_base = 0, uses = 0, it = 0;                 // tiles before this item; uses of this group's buffer
+        for (uint32_t w = cluster_id; w < n_items; w += n_clusters, ++it) {
+            const uint32_t mt = (w % n_mgroups) * CL + crank, c = w / n_mgroups;
             const uint32_t b_row0 = c * p.rows_per_chunk;
             const uint32_t b_rows = min(p.rows_per_chunk, p.nB - b_row0);
             const uint32_t n_tiles = (b_rows + kTcTileN - 1) / kTcTileN;
             uint32_t best0 = kKeyNone, best1 = kKeyNone;
             int32_t thr = kThrNone;
-            for (uint32_t t = 0; t < n_tiles; ++t, ++acc_it) {
-                const uint32_t buf = acc_it & 1u;
-                mbar_wait(bar_acc_full + 8 * buf, (acc_it >> 1) & 1u);
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + grp * kTcTileN;
+            for (uint32_t t = (acc_base + grp) & 1u; t < n_tiles; t += 2, ++uses) {
+                mbar_wait(bar_acc_full + 8 * grp, uses & 1u);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * kTcTileN;
                 const uint32_t n_valid = min(kTcTileN, b_rows - t * kTcTileN);
                 int32_t va[64], vb[64];
                 HULO_LDTM64(va, taddr);
                 HULO_WAIT_LD64(va);
-                const bool dump = p.dbg_dots != nullptr && w == 0 && t == 0;
+                const bool dump = p.dbg_dots != nullptr && w == 0 && t == 0 && crank == 0;
                 if (dump) _Pragma("unroll") for (int e = 0; e < 64; ++e) p.dbg_dots[row * 256 + e] = va[e];
                 HULO_LDTM64(vb, taddr + 64u);
                 if (n_valid < 64u) {
@@ -284,20 +344,31 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
                 // every column of this accumulator is in registers: hand it back before the last scan
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * grp);
                 if (n_valid < 256u) {
 #pragma unroll
                     for (int e = 0; e < 64; ++e) if ((uint32_t)(192 + e) >= n_valid) vb[e] = kDotMasked;
                 }
                 scan_block(vb, t * kTcTileN + 192u, best0, best1, thr);
             }
-            const uint32_t a_row = mt * kTcTileRows + row;
-            if (a_row < p.nA) p.partial[(uint64_t)c * p.slot_stride + a_row] = make_uint2(best0, best1);
+            acc_base += n_tiles;
+            // merge the two groups: keys are unique, so min/max on them is the (distance, index) order
+            uint2 *slot = xchg_gen + (it & 1u) * 128u + row;
+            if (grp == 1u) *slot = make_uint2(best0, best1);
+            asm volatile("bar.sync 1, 256;" ::: "memory");        // the eight epilogue warps
+            if (grp == 0u) {
+                const uint2 o = *slot;
+                const uint32_t lo = min(best0, o.x), mid = max(best0, o.x);
+                const uint32_t second = min(mid, min(best1, o.y));
+                const uint32_t a_row = mt * kTcTileRows + row;
+                if (a_row < p.nA) p.partial[(uint64_t)c * p.slot_stride + a_row] = make_uint2(lo, second);
+            }
         }
     }
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();             // no peer may still send into this CTA's shared memory
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
@@ -349,31 +420,67 @@ void knn2_tc_plan(size_t nA, size_t nB, int n_ctas, uint32_t *n_mtiles, uint32_t
     const uint32_t mt = (uint32_t)((nA + kTcTileRows - 1) / kTcTileRows);
     *n_mtiles = mt;
     if (nB == 0 || mt == 0) { *n_chunks = 0; *rows_per_chunk = kTcTileN; return; }
-    // about 16 items per CTA when the table is long enough, chunks of at least 2048 rows (8 tiles)
-    const uint64_t want_items = 16ull * (uint64_t)n_ctas;
-    uint64_t chunks = std::max<uint64_t>(1, want_items / mt);
-    uint64_t rpc = (nB + chunks - 1) / chunks;
-    rpc = std::max<uint64_t>(rpc, 2048);
-    rpc = (rpc + kTcTileN - 1) / kTcTileN * kTcTileN;
+    // Items (searcher tile x chunk) are dealt round-robin, so the makespan is (items per CTA, rounded
+    // up) x (cost of an item).  Every item pays a fixed cost on top of its rows: the searcher tile
+    // load, the pipeline refill and, above all, the best-2 thresholds restarting from nothing (the
+    // first few thousand rows of a chunk take the slow path of the epilogue often).
+    const uint64_t overhead_rows = 4096;
+    const uint64_t tiles_b = (nB + kTcTileN - 1) / kTcTileN;
+    const uint64_t c_min = (nB + kMaxChunkRows - 1) / kMaxChunkRows;
+    uint64_t c_max = std::min<uint64_t>(tiles_b, std::max<uint64_t>(c_min, (32ull * n_ctas + mt - 1) / mt));
+    uint64_t best_c = c_min, best_cost = ~0ull;
+    for (uint64_t c = c_min; c <= c_max; ++c) {
+        uint64_t rpc = ((nB + c - 1) / c + kTcTileN - 1) / kTcTileN * kTcTileN;
+        if (rpc > kMaxChunkRows) continue;
+        const uint64_t chunks = (nB + rpc - 1) / rpc;
+        const uint64_t per_cta = ((uint64_t)mt * chunks + n_ctas - 1) / n_ctas;
+        const uint64_t cost = per_cta * (rpc + overhead_rows);
+        if (cost < best_cost) { best_cost = cost; best_c = c; }
+    }
+    uint64_t rpc = ((nB + best_c - 1) / best_c + kTcTileN - 1) / kTcTileN * kTcTileN;
     rpc = std::min<uint64_t>(rpc, kMaxChunkRows);
     *rows_per_chunk = (uint32_t)rpc;
     *n_chunks = (uint32_t)((nB + rpc - 1) / rpc);
 }
 
-cudaError_t knn2_tc_launch(const TcParams &p, int grid, cudaStream_t stream) {
+template <int CL>
+static cudaError_t launch_cl(const TcParams &p, int grid, cudaStream_t stream) {
     static thread_local int configured_device = -1;
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured_device != dev) {
-        cudaError_t e = cudaFuncSetAttribute(knn2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(knn2_tc_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) return e;
         configured_device = dev;
     }
-    const uint32_t n_items = p.n_mtiles * p.n_chunks;
+    const uint32_t n_mgroups = (p.n_mtiles + CL - 1) / CL;
+    const uint64_t n_items = (uint64_t)n_mgroups * p.n_chunks;
     if (n_items == 0) return cudaSuccess;
-    if ((uint32_t)grid > n_items) grid = (int)n_items;
-    knn2_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(p);
-    return cudaGetLastError();
+    uint64_t clusters = (uint64_t)grid / CL;
+    if (clusters > n_items) clusters = n_items;
+    if (clusters == 0) clusters = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(clusters * CL), 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, knn2_tc_kernel<CL>, p);
+}
+
+cudaError_t knn2_tc_launch(const TcParams &p, int grid, cudaStream_t stream) {
+    switch (p.cluster) {
+        case 1: return launch_cl<1>(p, grid, stream);
+        case 2: return launch_cl<2>(p, grid, stream);
+        case 4: return launch_cl<4>(p, grid, stream);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace hulo

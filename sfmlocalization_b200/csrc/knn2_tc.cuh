@@ -59,11 +59,13 @@ struct TcParams {
     // tile of work item 0 are written there (128 x 256 int32)
     int32_t *dbg_dots = nullptr;
     uint32_t lbo = 128, sbo = 1024;   // shared-memory descriptor strides of the tile image
+    int cluster = 1;                  // CTAs per cluster sharing every database stage (1, 2 or 4); 1 measured fastest
 };
 
-// Persistent launch, one CTA per SM; work item w -> searcher tile (w % n_mtiles), chunk (w / n_mtiles),
-// items dealt round-robin (CTA b takes w = b, b + grid, ...), so the CTAs running at any moment share
-// a handful of database chunks through L2.
+// Persistent launch, one CTA per SM in clusters of p.cluster CTAs; work item w -> group of p.cluster
+// consecutive searcher tiles (w % n_groups), chunk (w / n_groups), items dealt round-robin over the
+// clusters, so the CTAs running at any moment share a handful of database chunks through L2 and the
+// CTAs of a cluster share every stage through one multicast copy.
 cudaError_t knn2_tc_launch(const TcParams &p, int grid, cudaStream_t stream);
 
 // Chunk size for a K1t run (multiple of 256 rows).

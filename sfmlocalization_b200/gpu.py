@@ -122,6 +122,16 @@ class HuloGpu:
         return int(self.lib.hulo_launch_count(self.h))
 
     # -- K1
+    def set_knn_engine(self, engine):
+        """'int' (XOR + popcount on the integer pipes, the default) or 'tc' (int8 contraction on the
+        tensor cores); both exact.  Applies to the flat searches."""
+        code = {"int": _lib.KNN_INT, "tc": _lib.KNN_TC}[engine]
+        check(self.lib.hulo_gpu_set_knn_engine(self.h, code))
+
+    @property
+    def knn_engine(self):
+        return {_lib.KNN_INT: "int", _lib.KNN_TC: "tc"}[int(self.lib.hulo_gpu_knn_engine(self.h))]
+
     def knn2(self, A, B, fetch=True):
         """A, B: DescriptorDb.  Returns (idx2, dist2) int32 nA x 2, or None when fetch=False."""
         nA = len(A)
@@ -377,6 +387,11 @@ class HuloGpu:
     def comm_init(self, unique_id, rank, world):
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         check(self.lib.hulo_comm_init(self.h, buf, rank, world))
+
+    @property
+    def exchange_kind(self):
+        """Data plane of the row-sharded search on this context: 'peer-store', 'nccl-allgather' or 'none'."""
+        return self.lib.hulo_comm_exchange_kind(self.h).decode()
 
     def comm_barrier(self):
         check(self.lib.hulo_comm_barrier(self.h))

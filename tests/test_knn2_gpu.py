@@ -9,6 +9,15 @@ pytestmark = pytest.mark.gpu
 INT_MAX = 2**31 - 1
 
 
+@pytest.fixture(autouse=True, params=["int", "tc"])
+def engine(request, gpu):
+    """Every test of this module runs on both arithmetic engines of the flat search: the integer
+    pipes (K1) and the int8 tensor-core contraction (K1t).  Same bit-exact expectations."""
+    gpu.set_knn_engine(request.param)
+    yield request.param
+    gpu.set_knn_engine("int")
+
+
 def run_gpu(gpu, A, B):
     return gpu.knn2_host(A, B)
 

@@ -51,12 +51,15 @@ struct Dev {
 
 int main(int argc, char **argv) {
     const size_t big_nB = argc > 1 ? strtoull(argv[1], nullptr, 10) : 2000000;
+    const int reps = argc > 2 ? atoi(argv[2]) : 12;            // timed launches of section 3
+    const int only_cluster = argc > 3 ? atoi(argv[3]) : 0;     // 0: sweep 1, 2, 4
+    const bool timing_only = argc > 4 && atoi(argv[4]) != 0;   // skip the correctness sections
     int sms = 0;
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
     printf("SMs %d\n", sms);
 
     // ---- 1: one tile, raw dots
-    {
+    if (!timing_only) {
         const size_t nA = 128, nB = 256;
         auto A = random_rows(nA, 1), B = random_rows(nB, 2);
         Dev dA, dB; dA.make(A, nA); dB.make(B, nB);
@@ -69,7 +72,7 @@ int main(int argc, char **argv) {
             TcParams p{};
             p.imgA = dA.img; p.imgB = dB.img; p.nA = nA; p.nB = nB; p.n_mtiles = 1; p.n_chunks = 1;
             p.rows_per_chunk = 256; p.slot_stride = 128; p.partial = partial; p.dbg_dots = dots;
-            p.lbo = cand[v][0]; p.sbo = cand[v][1];
+            p.lbo = cand[v][0]; p.sbo = cand[v][1]; p.cluster = 1;
             CK(knn2_tc_launch(p, sms, 0));
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("variant lbo=%u sbo=%u: kernel failed: %s\n", p.lbo, p.sbo, cudaGetErrorString(e)); return 3; }
@@ -88,8 +91,8 @@ int main(int argc, char **argv) {
     }
 
     // ---- 2: ragged shape, keys against a CPU scan
-    {
-        const size_t nA = 300, nB = 5000;
+    if (!timing_only) {
+        const size_t nA = 300, nB = 70000;
         auto A = random_rows(nA, 3), B = random_rows(nB, 4);
         // make ties and duplicates likely: copy some rows
         for (size_t j = 100; j < 140; ++j) memcpy(&B[j * 16], &B[7 * 16], 64);
@@ -101,9 +104,11 @@ int main(int argc, char **argv) {
         uint2 *partial;
         CK(cudaMalloc(&partial, (size_t)nc * stride * sizeof(uint2)));
         CK(cudaMemset(partial, 0xEE, (size_t)nc * stride * sizeof(uint2)));
+      for (int cl = 1; cl <= 4; cl *= 2) {
+        CK(cudaMemset(partial, 0xEE, (size_t)nc * stride * sizeof(uint2)));
         TcParams p{};
         p.imgA = dA.img; p.imgB = dB.img; p.nA = nA; p.nB = nB; p.n_mtiles = mt; p.n_chunks = nc;
-        p.rows_per_chunk = rpc; p.slot_stride = stride; p.partial = partial;
+        p.rows_per_chunk = rpc; p.slot_stride = stride; p.partial = partial; p.cluster = cl;
         CK(knn2_tc_launch(p, sms, 0));
         CK(cudaDeviceSynchronize());
         std::vector<uint2> h((size_t)nc * stride);
@@ -134,7 +139,8 @@ int main(int argc, char **argv) {
                 ++bad;
             }
         }
-        printf("ragged test %zu x %zu (mtiles %u chunks %u rpc %u): %zu rows wrong\n", nA, nB, mt, nc, rpc, bad);
+        printf("ragged test %zu x %zu cluster %d (mtiles %u chunks %u rpc %u): %zu rows wrong\n", nA, nB, cl, mt, nc, rpc, bad);
+      }
         dA.free(); dB.free(); cudaFree(partial);
     }
 
@@ -173,13 +179,14 @@ int main(int argc, char **argv) {
         TcParams p{};
         p.imgA = dA.img; p.imgB = img; p.nA = nA; p.nB = nB; p.n_mtiles = mt; p.n_chunks = nc;
         p.rows_per_chunk = rpc; p.slot_stride = stride; p.partial = partial;
-        for (int rep = 0; rep < 6; ++rep) {
+        for (int rep = 0; rep < reps; ++rep) {
+            p.cluster = only_cluster ? only_cluster : 1 << ((rep * 3) / reps);
             CK(cudaEventRecord(e0));
             CK(knn2_tc_launch(p, sms, 0));
             CK(cudaEventRecord(e1));
             CK(cudaEventSynchronize(e1));
             CK(cudaEventElapsedTime(&ms, e0, e1));
-            printf("K1t %zu x %zu (mtiles %u chunks %u rpc %u): %.3f ms  %.1f Gdist/s\n", nA, nB, mt, nc, rpc, ms,
+            printf("K1t %zu x %zu cluster %d (mtiles %u chunks %u rpc %u): %.3f ms  %.1f Gdist/s\n", nA, nB, p.cluster, mt, nc, rpc, ms,
                    (double)nA * nB / ms * 1e-6);
         }
         cudaFree(rows); cudaFree(img); cudaFree(partial); dA.free();

@@ -1,22 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the SfMLocalization hot path on B200.
+"""bench.py -- benchmarks of the SfMLocalization hot path on B200, one JSON line per run.
 
-Workload (BASELINE.json configs[2], the one the roofline target is quoted on): exact Hamming
-2-NN of 4096 query descriptors against a 10M-row map table of 64-byte AKAZE/MLDB rows,
-synthetic random descriptors with planted true matches.  At N > 1 the table is row-sharded
-across the ranks (one process per GPU), every rank returns its local top-2 and one NCCL
-all-gather of 16 bytes per query per rank merges them (strong scaling: the table is fixed).
+Headline (default, --workload c3 = BASELINE.json configs[2], the one the roofline target is quoted
+on): exact Hamming 2-NN of 4096 query descriptors against a 10M-row map table of 64-byte AKAZE/MLDB
+rows, synthetic random descriptors with planted true matches.  At N > 1 the table is row-sharded
+across the ranks (one process per GPU), every rank returns its local top-2 and the candidates
+(16 bytes per query per rank) are exchanged and merged (strong scaling: the table is fixed).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+Other configurations of BASELINE.json behind --workload, same JSON contract:
+    c1  one query localisation, 2000 descriptors vs a 200k-descriptor map (match + AC-RANSAC)
+    c2  exhaustive pairwise matching, 200 images x 5000, pair list sharded over the ranks
+    c4  batched server, 256 queries x 3000 vs a 2M-descriptor map, queries sharded over the ranks
+    c5  campus map, 16384 queries x 50M rows, row-sharded (needs 8 GPUs for the headline shape)
 
-No PyTorch: the library owns device memory, its stream, CUDA events and the NCCL
-communicator; torchrun is only the process launcher (RANK / LOCAL_RANK / WORLD_SIZE).
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cX]
+                    [--engine tc|int]
+
+No PyTorch: the library owns device memory, its stream, CUDA events and the communicator;
+torchrun is only the process launcher (RANK / LOCAL_RANK / WORLD_SIZE).  Every CPU leg (the
+reference arm's work, cpu_baseline, the parity sample) runs in a child process, so the process that
+drives the GPU never maps the oracle.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -33,6 +43,8 @@ UNIT = "Gdist/s"
 N_QUERIES = 4096
 N_MAP = 10_000_000
 SEED = 3000          # seed = 1000 * config number
+BLK = 250_000        # map rows are generated in independently seeded blocks
+PARITY_QUERIES = 64  # rows of the result checked bit for bit against the oracle over the whole table
 
 
 def read_json(path, default=None):
@@ -65,11 +77,12 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.mark = 0
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -80,6 +93,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark_timed_region(self):
+        """Samples before this point belong to the warm-up."""
+        self.mark = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -88,14 +105,15 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        lines = self.lines[self.mark:] if len(self.lines) - self.mark >= 3 else self.lines
+        sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0])); smax.append(float(f[1]))
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
             except ValueError:
                 continue
             for k, name in enumerate(names):
@@ -103,6 +121,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(smax)) if smax else None,
+                "power_w_max": float(max(power)) if power else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
@@ -126,23 +145,51 @@ def rendezvous_id(rank, world, make_id):
     raise RuntimeError("rank %d: no NCCL id at %s" % (rank, path))
 
 
+def map_block(b):
+    return synth.random_rows(BLK, SEED + 1 + b)
+
+
+def make_queries():
+    """The query rows: identical on every rank.  30 % are noisy copies of rows of map block 0."""
+    A = synth.random_rows(N_QUERIES, SEED + 7919)
+    return synth.plant_matches(A, map_block(0), SEED + 104729, frac=0.3)
+
+
 def make_tables(world, rank):
     """Every rank generates the same query set; rank r generates only its shard of the map
     (blocks are seeded independently, so shards concatenate to the 1-GPU table)."""
-    blk = 250_000                       # rows in 250k-row blocks, seeded per block
-    n_blocks = N_MAP // blk
-    per = n_blocks // world if n_blocks % world == 0 else None
-    if per is None:
+    n_blocks = N_MAP // BLK
+    if n_blocks % world != 0:
         raise SystemExit("--gpus must divide %d" % n_blocks)
+    per = n_blocks // world
     b_lo, b_hi = rank * per, (rank + 1) * per
-    shard = np.concatenate([synth.random_rows(blk, SEED + 1 + b) for b in range(b_lo, b_hi)], axis=0)
-    row_base = b_lo * blk
-    # queries: 30 % are noisy copies of map rows.  The planted sources are drawn from block 0 and
-    # written by its owner; the query rows themselves are identical on every rank.
-    block0 = synth.random_rows(blk, SEED + 1)
-    A = synth.random_rows(N_QUERIES, SEED + 7919)
-    A, target = synth.plant_matches(A, block0, SEED + 104729, frac=0.3)
-    return A, target, shard, row_base
+    shard = np.concatenate([map_block(b) for b in range(b_lo, b_hi)], axis=0)
+    A, target = make_queries()
+    return A, target, shard, b_lo * BLK
+
+
+# --------------------------------------------------------------------------- CPU legs (child process)
+def run_child(kind, extra=(), timeout=900):
+    """Runs `bench.py --cpu-leg kind` in a child process with the launcher's OMP_NUM_THREADS removed;
+    returns (its JSON line, path of the npz it wrote or None)."""
+    fd, out = tempfile.mkstemp(prefix="hulo_cpu_leg_", suffix=".npz")
+    os.close(fd)
+    env = dict(os.environ)
+    for k in ("OMP_NUM_THREADS", "OMP_PROC_BIND", "OMP_PLACES", "GOMP_CPU_AFFINITY"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-leg", kind, "--out", out,
+           "--workload", ARGS.workload] + list(extra)
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError("cpu leg %s failed: %s" % (kind, r.stderr[-2000:]))
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    return json.loads(line), out
+
+
+def oracle_all_cores():
+    from oracle import oracle as orc
+    orc.build()
+    return orc, orc.use_all_cores()
 
 
 def calibrate_queries(orc, A, shard, grp, target_s):
@@ -161,57 +208,229 @@ def calibrate_queries(orc, A, shard, grp, target_s):
     return int(min(A.shape[0], max(grp, want // grp * grp)))
 
 
-def cpu_baseline_sample(A, shard, budget_s=12.0):
-    """Times the oracle port (exact 2-NN, all host cores) on a bounded sample of the workload."""
-    from oracle import oracle as orc
-    orc.build()
-    threads = orc.num_threads()
+def leg_knn2(args):
+    """cpu_baseline of the flat search: the oracle port (exact 2-NN, every host core) on a bounded
+    sample: the first 1M map rows, as many queries as ~12 s allow.  Writes the sample's result."""
+    orc, threads = oracle_all_cores()
+    A, _ = make_queries()
+    shard = np.concatenate([map_block(b) for b in range(4)], axis=0)
     grp = 8 * max(1, threads)                       # the port walks 8 searcher rows per thread
+    nq = calibrate_queries(orc, A, shard, grp, args.budget)
     nb = int(shard.shape[0])
-    nq = calibrate_queries(orc, A, shard, grp, budget_s)
     t0 = time.perf_counter()
-    idx, dist = orc.knn2(A[:nq], shard[:nb])
+    idx, dist = orc.knn2(A[:nq], shard)
     dt = time.perf_counter() - t0
-    return {"value": nq * nb / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "%d queries x %d map rows (%.1f s), exact 2-NN, oracle/oracle_match.c with OpenMP"
-                      % (nq, nb, dt)}, (idx, dist, nq, nb)
+    np.savez(args.out, idx=idx, dist=dist, nq=nq, nb=nb)
+    print(json.dumps({"value": nq * nb / dt / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+                      "sample": "%d queries x %d map rows (%.1f s), exact 2-NN, oracle/oracle_match.c with OpenMP"
+                                % (nq, nb, dt)}))
 
 
+def leg_parity(args):
+    """Exact top-2 of the first PARITY_QUERIES queries over the WHOLE map table (all blocks, whatever
+    the sharding), block by block with the (distance, global index) merge."""
+    orc, threads = oracle_all_cores()
+    A, _ = make_queries()
+    A = A[:PARITY_QUERIES]
+    cd, ci = [], []
+    for b in range(N_MAP // BLK):
+        i, d = orc.knn2(A, map_block(b))
+        ci.append(i.astype(np.int64) + b * BLK); cd.append(d.astype(np.int64))
+    cd = np.concatenate(cd, axis=1); ci = np.concatenate(ci, axis=1)
+    order = np.lexsort((ci, cd), axis=1)[:, :2]
+    np.savez(args.out, idx=np.take_along_axis(ci, order, axis=1).astype(np.int32),
+             dist=np.take_along_axis(cd, order, axis=1).astype(np.int32))
+    print(json.dumps({"queries": PARITY_QUERIES, "map_rows": N_MAP, "cores": threads}))
+
+
+def c1_scene():
+    return synth.localization_scene(100, 2000, 20000, 2000, 1000)
+
+
+def leg_localize(args):
+    """CPU port of one C1 query: per-view exact 2-NN + ratio on all cores, assembly, sequential
+    AC-RANSAC on one thread (as the reference runs it); the geometric filter timed on its own."""
+    orc, threads = oracle_all_cores()
+    sc = c1_scene()
+    t0 = time.perf_counter()
+    off = sc["seg_offsets"]
+    m_view, m_i, m_j, m_d = [], [], [], []
+    for v in range(len(off) - 1):
+        oi, oj, od = orc.match_view_to_query(sc["rows"][int(off[v]):int(off[v + 1])], sc["q_desc"], 0.6)
+        if len(oi) < 16:
+            continue
+        m_view += [v] * len(oi); m_i += oi.tolist(); m_j += oj.tolist(); m_d += od.tolist()
+    t1 = time.perf_counter()
+    w, h = synth.IMAGE_WH
+    mv, mi, mj = np.array(m_view), np.array(m_i), np.array(m_j)
+    n_geo_valid = 0
+    for p, v in enumerate(sorted(set(m_view))):
+        sel = np.nonzero(mv == v)[0]
+        rr = orc.fmatrix_acransac(sc["map_xy"][int(off[v]) + mi[sel]], sc["q_xy"][mj[sel]], (w, h), (w, h), 4.0, 25,
+                                  77 + 1000003 * p)
+        n_geo_valid += int(rr["ok"])
+    t1g = time.perf_counter()
+    order = np.lexsort((sc["obs_feat"], sc["obs_view"]))
+    cj, cl = orc.match_set(m_view, m_i, m_j, m_view, m_j, m_d, sc["obs_view"][order], sc["obs_feat"][order],
+                           sc["obs_landmark"][order].astype(np.int64), len(sc["q_desc"]))
+    t2 = time.perf_counter()
+    ro = orc.acransac(sc["q_xy"][cj], sc["landmark_X"][cl], sc["K"], max_iter=4096, seed=1)
+    t3 = time.perf_counter()
+    out = {"ms_per_query": ((t1 - t0) + (t3 - t1g)) * 1e3, "cores": threads, "kind": "port",
+           "stage_ms": {"putMatch": (t1 - t0) * 1e3, "assembly": (t2 - t1g) * 1e3, "PnP": (t3 - t2) * 1e3,
+                        "geoMatch_when_enabled": (t1g - t1) * 1e3},
+           "sample": "1 query: exact per-view 2-NN on all cores, sequential AC-RANSAC on one thread (as the "
+                     "reference runs it); geoMatch = F-matrix AC-RANSAC of the kept views one after the other on "
+                     "one thread, 25 rounds",
+           "localized": bool(ro["ok"]), "inliers": int(len(ro["inliers"])), "geometric_pairs_valid": n_geo_valid,
+           "reference_algorithm_lsh": lsh_reference(sc, set(zip(m_view, m_i, m_j)))}
+    print(json.dumps(out))
+
+
+def c2_collection():
+    return synth.image_collection(200, 5000, 2000, overlap=0.3)
+
+
+def leg_pairs(args):
+    """CPU port of C2 on a bounded sample: the first pairs of the all-pairs list, orc_match_pair
+    (exact 2-NN of image I in image J, ratio 0.7, one-to-one filter), one pair after the other,
+    the 2-NN of each pair on all cores."""
+    orc, threads = oracle_all_cores()
+    rows, off = c2_collection()
+    pairs = [(a, b) for a in range(200) for b in range(a + 1, 200)]
+    n, t0, done, nm = 0, time.perf_counter(), 0.0, 0
+    out_i = []
+    while done < args.budget and n < len(pairs):
+        a, b = pairs[n]
+        i, j = orc.match_pair(rows[int(off[a]):int(off[a + 1])], rows[int(off[b]):int(off[b + 1])], 0.7)
+        out_i.append(np.stack([np.full(len(i), n), i, j], axis=1))
+        nm += len(i); n += 1
+        done = time.perf_counter() - t0
+    np.savez(args.out, matches=np.concatenate(out_i, axis=0).astype(np.int64), n_pairs=n)
+    print(json.dumps({"value": n * 25e6 / done / 1e9, "unit": UNIT, "cores": threads, "kind": "port",
+                      "pairs_per_s": n / done,
+                      "sample": "first %d of 19900 pairs (%.1f s), 5000 x 5000 exact 2-NN + ratio 0.7 + one-to-one "
+                                "filter per pair (oracle orc_match_pair), %d matches" % (n, done, nm)}))
+
+
+def c4_scene():
+    return synth.localization_scene(1000, 2000, 200000, 3000, 4100, window=6000)
+
+
+def leg_server(args):
+    """CPU port of C4 on a bounded sample: whole queries of the batched-server workload, one after
+    the other: per-view exact 2-NN + ratio over the 1000 views on all cores, assembly, AC-RANSAC."""
+    orc, threads = oracle_all_cores()
+    sc = c4_scene()
+    off = sc["seg_offsets"]
+    order = np.lexsort((sc["obs_feat"], sc["obs_view"]))
+    n, t0, done, ok = 0, time.perf_counter(), 0.0, 0
+    while done < args.budget and n < 256:
+        q = synth.extra_query(sc, 3000, 4100 + 10 + n)
+        m_view, m_i, m_j, m_d = [], [], [], []
+        for v in range(len(off) - 1):
+            oi, oj, od = orc.match_view_to_query(sc["rows"][int(off[v]):int(off[v + 1])], q["q_desc"], 0.6)
+            if len(oi) < 16:
+                continue
+            m_view += [v] * len(oi); m_i += oi.tolist(); m_j += oj.tolist(); m_d += od.tolist()
+        cj, cl = orc.match_set(m_view, m_i, m_j, m_view, m_j, m_d, sc["obs_view"][order], sc["obs_feat"][order],
+                               sc["obs_landmark"][order].astype(np.int64), len(q["q_desc"]))
+        ro = orc.acransac(q["q_xy"][cj], sc["landmark_X"][cl], sc["K"], max_iter=4096, seed=1) if len(cj) > 8 \
+            else {"ok": False}
+        ok += int(bool(ro["ok"])); n += 1
+        done = time.perf_counter() - t0
+    print(json.dumps({"value": n / done, "unit": "localizations/s", "cores": threads, "kind": "port",
+                      "sample": "%d of 256 queries (%.1f s): 3000 descriptors vs 2M map rows in 1000 views, exact "
+                                "2-NN on all cores, sequential AC-RANSAC on one thread; %d localised" % (n, done, ok)}))
+
+
+def lsh_reference(sc, exact_matches):
+    """The reference's own (approximate) matcher configuration, for context: cv::flann LSH index
+    (2 tables, key 20, multi-probe 2) on the query descriptors, knnSearch(k=2, checks=2) per map
+    view, float ratio test (MatchUtils.cpp:52-65, 303-355), through OpenCV's Python binding,
+    one thread (the reference spreads the views over OpenMP threads).  Reports its time and how
+    its putative matches compare with the exact matcher's.  Not the parity target."""
+    try:
+        import cv2
+    except Exception as e:                      # pragma: no cover
+        return {"unavailable": "cv2 not importable: %s" % e}
+    off = sc["seg_offsets"]
+    t0 = time.perf_counter()
+    index = cv2.flann_Index(sc["q_desc"], dict(algorithm=6, table_number=2, key_size=20, multi_probe_level=2), 9)
+    got = set()
+    for v in range(len(off) - 1):
+        a = sc["rows"][int(off[v]):int(off[v + 1])]
+        idx, dist = index.knnSearch(a, 2, params=dict(checks=2, eps=0.0, sorted=True))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            q = dist[:, 0].astype(np.float32) / dist[:, 1].astype(np.float32)
+        keep = np.nonzero((q < np.float32(0.6)) & (dist[:, 1] < 2**31 - 1))[0]
+        if len(keep) >= 16:
+            got.update((v, int(i), int(idx[i, 0])) for i in keep)
+    dt = time.perf_counter() - t0
+    both = len(got & exact_matches)
+    return {"ms_per_query_matching": dt * 1e3, "threads": 1, "putative_matches": len(got),
+            "exact_matcher_matches": len(exact_matches), "common": both,
+            "note": "approximate and indicative only: on i.i.d. synthetic descriptors the probed LSH buckets "
+                    "almost never hold a second candidate, so rows come back with d1 = INT_MAX and are rejected "
+                    "(MatchUtils.cpp:349); on real images the second candidate is whatever shares a bucket"}
+
+
+CPU_LEGS = {"knn2": leg_knn2, "parity": leg_parity, "localize": leg_localize, "pairs": leg_pairs,
+            "server": leg_server}
+
+
+# --------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU path for this stage.  Its own matcher (OpenCV 3.0
-    FLANN behind MatchUtils.cpp:105-108) cannot be built in this image, so the oracle port is
-    timed, with every host thread, on bounded samples of the same workload."""
+    """--impl reference: the reference's CPU path for this stage.  Its own matcher (OpenCV 3.0 FLANN
+    behind MatchUtils.cpp:105-108) and resection (OpenMVG 1.1) cannot be built in this image, so the
+    oracle port is timed, with every host thread (the launcher's OMP_NUM_THREADS is ignored), on
+    bounded samples of the same workload.  Rank 0 alone works."""
     if rank != 0:
         return
-    blk = 250_000
-    A = synth.random_rows(N_QUERIES, SEED + 7919)
-    shard = np.concatenate([synth.random_rows(blk, SEED + 1 + b) for b in range(4)], axis=0)
-    from oracle import oracle as orc
-    orc.build()
-    threads = orc.num_threads()
-    grp = 8 * max(1, threads)                       # the port walks 8 searcher rows per thread
-    # size one step to ~2 s of CPU work: all 1M staged map rows, as many queries as that allows
-    nb = int(shard.shape[0])
-    nq = calibrate_queries(orc, A, shard, grp, 2.0)
-    for _ in range(args.warmup):
-        orc.knn2(A[:nq], shard[:nb])
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        orc.knn2(A[:nq], shard[:nb])
-    dt = time.perf_counter() - t0
-    value = nq * nb * args.steps / dt / 1e9
-    sample = "%d queries x %d map rows per step, exact 2-NN, oracle port (OpenMP)" % (nq, nb)
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32",
-        "data": "synthetic", "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }))
+    base = {"impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "vs_baseline": None, "data": "synthetic", "gpu_launches": 0}
+    if args.workload in ("c3", "c5"):
+        orc, threads = oracle_all_cores()
+        A, _ = make_queries()
+        shard = np.concatenate([map_block(b) for b in range(4)], axis=0)
+        grp = 8 * max(1, threads)
+        nb = int(shard.shape[0])
+        nq = calibrate_queries(orc, A, shard, grp, 2.0)    # one step ~ 2 s of CPU work
+        for _ in range(args.warmup):
+            orc.knn2(A[:nq], shard)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            orc.knn2(A[:nq], shard)
+        dt = time.perf_counter() - t0
+        value = nq * nb * args.steps / dt / 1e9
+        sample = "%d queries x %d map rows per step, exact 2-NN, oracle port (OpenMP)" % (nq, nb)
+        base.update({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": dt / args.steps * 1e3,
+                     "scaling": "strong", "dtype": "u32", "config": workload_config(args.gpus, "cpu", "none"),
+                     "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+                     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+        print(json.dumps(base))
+        return
+    # c1 / c2 / c4: one bounded CPU sample is the whole run (steps and warm-up do not multiply it)
+    kind = {"c1": "localize", "c2": "pairs", "c4": "server"}[args.workload]
+    cb, out = run_child(kind, ["--budget", "20"])
+    if os.path.exists(out):
+        os.remove(out)
+    if args.workload == "c1":
+        value, unit, metric = 1e3 / cb["ms_per_query"], "localizations/s", "query_localizations_per_s"
+        cb = {"value": value, "unit": unit, "cores": cb["cores"], "kind": "port", "sample": cb["sample"],
+              "stage_ms": cb["stage_ms"]}
+    elif args.workload == "c2":
+        value, unit, metric = cb["value"], UNIT, METRIC
+    else:
+        value, unit, metric = cb["value"], "localizations/s", "query_localizations_per_s"
+    base.update({"metric": metric, "value": value, "unit": unit, "ms_per_step": None, "scaling": "weak",
+                 "dtype": "u32 / f64", "config": {"workload": WORKLOAD_NAMES[args.workload]},
+                 "cpu_baseline": cb,
+                 "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(base))
 
 
+# --------------------------------------------------------------------------- C1: one query
 def localize_bench(g, with_cpu=True, reps=20):
     """Second half of the metric (BASELINE.json: query localizations/sec): configs[0], one query
     image of 2000 descriptors against a 200k-descriptor map (100 views x 2000), ratio 0.6
@@ -219,7 +438,7 @@ def localize_bench(g, with_cpu=True, reps=20):
     reference's 4096-iteration budget.  End to end through hulo_engine_localize: query
     descriptors and keypoints in host memory, pose back in host memory."""
     from sfmlocalization_b200.gpu import LocalizeEngine
-    sc = synth.localization_scene(100, 2000, 20000, 2000, 1000)
+    sc = c1_scene()
     eng = LocalizeEngine(g, sc["rows"], sc["seg_offsets"], sc["obs_view"], sc["obs_feat"], sc["obs_landmark"],
                          sc["landmark_X"], sc["K"], ratio=0.6)
     for k in range(3):
@@ -262,8 +481,7 @@ def localize_bench(g, with_cpu=True, reps=20):
     gst = np.median(np.array(gstages), axis=0)
     ms = float(np.median(wall))
     st = np.median(np.array(stages), axis=0)
-    out = {"workload": "C1: 2000 query descriptors vs 200000 map descriptors (100 views), ratio 0.6, "
-                       "AC-RANSAC + P3P, max 4096 iterations",
+    out = {"workload": WORKLOAD_NAMES["c1"],
            "ms_per_query": ms, "localizations_per_s": 1e3 / ms,
            "stage_ms": {"putMatch": float(st[0]), "assembly": float(st[1]), "PnP": float(st[2])},
            "fraction_localized": ok / reps, "centre_error_m_median": float(np.median(err)) if err else None,
@@ -285,112 +503,43 @@ def localize_bench(g, with_cpu=True, reps=20):
                "centre_error_m_median": float(np.median(b_err)) if b_err else None,
                "note": "64 query images of 2000 descriptors in one hulo_engine_localize_batch call, host buffers in, poses out"}}
     if with_cpu:
-        from oracle import oracle as orc
-        orc.build()
-        t0 = time.perf_counter()
-        off = sc["seg_offsets"]
-        m_view, m_i, m_j, m_d = [], [], [], []
-        for v in range(len(off) - 1):
-            oi, oj, od = orc.match_view_to_query(sc["rows"][int(off[v]):int(off[v + 1])], sc["q_desc"], 0.6)
-            if len(oi) < 16:
-                continue
-            m_view += [v] * len(oi); m_i += oi.tolist(); m_j += oj.tolist(); m_d += od.tolist()
-        t1 = time.perf_counter()
-        # geometric filter of the kept views on the CPU port, timed on its own: the plain pipeline
-        # below consumes the putative matches like the GPU's plain run
-        w, h = synth.IMAGE_WH
-        mv, mi, mj = np.array(m_view), np.array(m_i), np.array(m_j)
-        n_geo_valid = 0
-        for p, v in enumerate(sorted(set(m_view))):
-            sel = np.nonzero(mv == v)[0]
-            rr = orc.fmatrix_acransac(sc["map_xy"][int(off[v]) + mi[sel]], sc["q_xy"][mj[sel]], (w, h), (w, h), 4.0, 25,
-                                      77 + 1000003 * p)
-            n_geo_valid += int(rr["ok"])
-        t1g = time.perf_counter()
-        order = np.lexsort((sc["obs_feat"], sc["obs_view"]))
-        cj, cl = orc.match_set(m_view, m_i, m_j, m_view, m_j, m_d, sc["obs_view"][order], sc["obs_feat"][order],
-                               sc["obs_landmark"][order].astype(np.int64), len(sc["q_desc"]))
-        t2 = time.perf_counter()
-        ro = orc.acransac(sc["q_xy"][cj], sc["landmark_X"][cl], sc["K"], max_iter=4096, seed=1)
-        t3 = time.perf_counter()
-        out["cpu_baseline"] = {"ms_per_query": ((t1 - t0) + (t3 - t1g)) * 1e3, "cores": orc.num_threads(),
-                               "kind": "port",
-                               "stage_ms": {"putMatch": (t1 - t0) * 1e3, "assembly": (t2 - t1g) * 1e3,
-                                            "PnP": (t3 - t2) * 1e3, "geoMatch_when_enabled": (t1g - t1) * 1e3},
-                               "sample": "1 query: exact per-view 2-NN on all cores, sequential AC-RANSAC on one "
-                                         "thread (as the reference runs it); geoMatch = F-matrix AC-RANSAC of the "
-                                         "kept views one after the other on one thread, 25 rounds",
-                               "localized": bool(ro["ok"]), "inliers": int(len(ro["inliers"])),
-                               "geometric_pairs_valid": n_geo_valid}
-        out["reference_algorithm_lsh"] = lsh_reference(sc, set(zip(m_view, m_i, m_j)))
+        cb, tmp = run_child("localize")
+        if os.path.exists(tmp):
+            os.remove(tmp)
+        out["reference_algorithm_lsh"] = cb.pop("reference_algorithm_lsh", None)
+        out["cpu_baseline"] = cb
     return out
 
 
-def lsh_reference(sc, exact_matches):
-    """The reference's own (approximate) matcher configuration, for context: cv::flann LSH index
-    (2 tables, key 20, multi-probe 2) on the query descriptors, knnSearch(k=2, checks=2) per map
-    view, float ratio test (MatchUtils.cpp:52-65, 303-355), through OpenCV's Python binding,
-    one thread (the reference spreads the views over OpenMP threads).  Reports its time and how
-    its putative matches compare with the exact matcher's.  Not the parity target."""
-    try:
-        import cv2
-    except Exception as e:                      # pragma: no cover
-        return {"unavailable": "cv2 not importable: %s" % e}
-    off = sc["seg_offsets"]
-    t0 = time.perf_counter()
-    index = cv2.flann_Index(sc["q_desc"], dict(algorithm=6, table_number=2, key_size=20, multi_probe_level=2), 9)
-    got = set()
-    for v in range(len(off) - 1):
-        a = sc["rows"][int(off[v]):int(off[v + 1])]
-        idx, dist = index.knnSearch(a, 2, params=dict(checks=2, eps=0.0, sorted=True))
-        with np.errstate(divide="ignore", invalid="ignore"):
-            q = dist[:, 0].astype(np.float32) / dist[:, 1].astype(np.float32)
-        keep = np.nonzero((q < np.float32(0.6)) & (dist[:, 1] < 2**31 - 1))[0]
-        if len(keep) >= 16:
-            got.update((v, int(i), int(idx[i, 0])) for i in keep)
-    dt = time.perf_counter() - t0
-    both = len(got & exact_matches)
-    return {"ms_per_query_matching": dt * 1e3, "threads": 1, "putative_matches": len(got),
-            "exact_matcher_matches": len(exact_matches), "common": both,
-            "note": "approximate and indicative only: on i.i.d. synthetic descriptors the probed LSH buckets "
-                    "almost never hold a second candidate, so rows come back with d1 = INT_MAX and are rejected "
-                    "(MatchUtils.cpp:349); on real images the second candidate is whatever shares a bucket"}
+WORKLOAD_NAMES = {
+    "c1": "C1: 2000 query descriptors vs 200000 map descriptors (100 views), ratio 0.6, AC-RANSAC + P3P, max 4096 "
+          "iterations",
+    "c2": "C2: exhaustive pairwise matching, 200 images x 5000 descriptors, 19900 pairs, ratio 0.7, one-to-one filter",
+    "c4": "C4 batched server: 256 queries x 3000 descriptors vs 2M-descriptor map (1000 views), matching + AC-RANSAC "
+          "resection (4096-iteration budget), end to end",
+}
 
 
+def workload_config(n_gpus, engine, exchange):
+    name = "C5 campus-scale map" if N_MAP > 10_000_000 else "C3 building-scale map"
+    img = " + %.1f GB int8 tile image" % (N_MAP * 512 / 1e9) if engine == "tc" else ""
+    return {"workload": "%s: %d queries x %d map descriptors (64-byte AKAZE/MLDB rows), exact Hamming 2-NN, planted "
+                        "matches (30%%)" % (name, N_QUERIES, N_MAP),
+            "engine": {"tc": "K1t: int8 contraction on tcgen05 tensor cores (distance = (512 - dot) / 2, int32 exact)",
+                       "int": "K1: XOR + popcount on the integer pipes", "cpu": "oracle port on host cores"}[engine],
+            "sharding": "single GPU, whole table resident" if n_gpus == 1 else
+                        "map rows sharded over %d GPUs; local top-2 per rank, exchange = %s, merge on every rank"
+                        % (n_gpus, {"peer-store": "stores into peer-mapped buffers over NVLink (CUDA IPC) fused "
+                                                  "into the chunk-merge kernel + flag wait; NCCL only for set-up",
+                                    "nccl-allgather": "one ncclAllGather of 16 bytes per query per rank",
+                                    "none": "none"}.get(exchange, exchange)),
+            "cache": "map table %d MB%s > 126 MB L2, streamed every step (no L2 flush needed)" % (N_MAP * 64 // 10**6, img)}
 
-def workload_config(n_gpus):
-    return {"workload": "%s: %d queries x %d map descriptors (64-byte AKAZE/MLDB rows), "
-                        "exact Hamming 2-NN, planted matches (30%%)"
-                        % ("C5 campus-scale map" if N_MAP > 10_000_000 else "C3 building-scale map", N_QUERIES, N_MAP),
-            "sharding": "map rows sharded over %d GPU(s), NCCL all-gather top-2 merge" % n_gpus if n_gpus > 1
-            else "single GPU, whole table resident",
-            "cache": "map table 640 MB > 126 MB L2, streamed from HBM every step (no L2 flush needed)"}
 
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="c3", choices=["c3", "c5"],
-                    help="c3 (default, the headline): 4096 x 10M; c5: 16384 x 50M campus map (8 GPUs)")
-    args = ap.parse_args()
-    global N_QUERIES, N_MAP, SEED
-    if args.workload == "c5":
-        N_QUERIES, N_MAP, SEED = 16384, 50_000_000, 5000
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        args.gpus = world
-
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-
+# --------------------------------------------------------------------------- C3 / C5: flat search
+def bench_flat(args, rank, world, local_rank):
     from sfmlocalization_b200.gpu import HuloGpu, PinnedArray
+    import ctypes as C
 
     A, target, shard, row_base = make_tables(world, rank)
     g = HuloGpu(local_rank)
@@ -401,6 +550,7 @@ def main():
     dA = g.db(A)
     dB = g.db(shard)
     nA = A.shape[0]
+    total_dist = float(nA) * float(N_MAP)
 
     def step_device():
         if world > 1:
@@ -408,30 +558,43 @@ def main():
         else:
             g.knn2(dA, dB, fetch=False)
 
-    # ---- kernel-resident throughput: inputs already in HBM, results left in HBM
-    # the clock sampler runs from the warm-up on (same load) so that short timed regions still
-    # collect samples; nvidia-smi needs ~100 ms to deliver its first line
+    def timed_device(engine, steps, warmup, sampler=None):
+        g.set_knn_engine(engine)
+        for _ in range(max(warmup, 3)):
+            step_device()
+        g.comm_barrier() if world > 1 else g.synchronize()
+        if sampler:
+            sampler.mark_timed_region()
+        l0 = g.launch_count
+        g.timer_start()
+        for _ in range(steps):
+            step_device()
+        ms = g.timer_stop()
+        launches = g.launch_count - l0
+        ms = g.comm_max(ms) if world > 1 else ms
+        return ms, launches
+
+    # ---- kernel-resident throughput: inputs already in HBM, results left in HBM.  The clock sampler
+    # runs from the warm-up on (nvidia-smi needs ~100 ms for its first line); the samples reported are
+    # those of the timed region when it is long enough to hold three.
+    primary = args.engine
+    other = "int" if primary == "tc" else "tc"
     sampler = ClockSampler(local_rank)
     sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    g.comm_barrier() if world > 1 else g.synchronize()
-    launches0 = g.launch_count
-    g.timer_start()
-    for _ in range(args.steps):
-        step_device()
-    ms = g.timer_stop()
-    launches = g.launch_count - launches0
-    ms = g.comm_max(ms) if world > 1 else ms
+    ms, launches = timed_device(primary, args.steps, args.warmup, sampler)
     clocks = sampler.stop()
-    total_dist = float(nA) * float(N_MAP)
     value = total_dist * args.steps / (ms * 1e-3) / 1e9
+    exchange = g.exchange_kind
+    o_steps = max(3, min(args.steps, 10))
+    o_ms, _ = timed_device(other, o_steps, 3)
+    engines = {primary: {"value": value, "ms_per_step": ms / args.steps},
+               other: {"value": total_dist * o_steps / (o_ms * 1e-3) / 1e9, "ms_per_step": o_ms / o_steps}}
+    g.set_knn_engine(primary)
 
     # ---- end to end through the C-ABI with host buffers: every step uploads the queries from
     # pinned host memory and reads the top-2 back; the map table is engine state (resident)
     pin_A = PinnedArray(A.shape, np.uint8); pin_A.array[...] = A
     pin_i = PinnedArray((nA, 2), np.int32); pin_d = PinnedArray((nA, 2), np.int32)
-    import ctypes as C
     lib = g.lib
 
     def step_e2e():
@@ -458,50 +621,87 @@ def main():
 
     # ---- cold variant: map shard uploaded from host inside the timed call (hulo_knn2_host)
     cold = None
-    if world == 1:
+    if world == 1 and args.workload == "c3":
         t0 = time.perf_counter()
         g.knn2_host(A, shard)
         cold_s = time.perf_counter() - t0
         cold = {"value": total_dist / cold_s / 1e9, "unit": UNIT,
                 "note": "one call of hulo_knn2_host: 640 MB map + queries H2D from pageable memory inside the call"}
 
-    # ---- sanity on the result of the timed configuration (planted rows must be found)
+    # ---- checks on the result of the timed configuration
     ok = True
     hit = np.nonzero(target >= 0)[0]
     ok &= bool(np.array_equal(idx[hit, 0], target[hit]))
     ok &= bool((dist[:, 0] <= dist[:, 1]).all())
+    # both engines must return the same arrays
+    g.set_knn_engine(other)
+    step_device()
+    oi, od = g.knn2_fetch(nA)
+    g.set_knn_engine(primary)
+    engines_agree = bool(np.array_equal(oi, idx) and np.array_equal(od, dist))
+    ok &= engines_agree
+
+    parity = None
+    if rank == 0:
+        # bit-equality of a fixed query subset with the oracle over the WHOLE table, at every N
+        pj, ppath = run_child("parity")
+        want = np.load(ppath)
+        parity = bool(np.array_equal(idx[:PARITY_QUERIES], want["idx"]) and
+                      np.array_equal(dist[:PARITY_QUERIES], want["dist"]))
+        os.remove(ppath)
+        ok &= parity
 
     if rank == 0:
-        peak, peak_src = popc_peak_gdist((clocks.get("sm_max_mhz") or 1965.0))
         peaks = read_json(os.path.join(ROOT, "MEASURED_PEAKS.json"), {}) or {}
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        sm_max = clocks.get("sm_max_mhz") or 1965.0
         per_gpu = value / world
-        # K1 is the only kernel of weight in the step (the merge is microseconds); its average
-        # launch duration is the step time measured above with CUDA events on the library stream.
-        alg_bytes = 64.0 * (nA + N_MAP / world) + 16.0 * nA
-        hbm_gbs = alg_bytes / (ms * 1e-3 / args.steps) / 1e9
-        traffic = (read_json(os.path.join(ROOT, "profiles", "k1_traffic.json"), {}) or {}).get("dram_bytes_per_launch")
-        # the limit of the kernel's own instruction mix: per distance 26.5 LOP3 +
-        # 3 VIMNMX on the ALU pipe (2 cycles per warp instruction per sub-partition) and 7.75 POPC on
-        # the XU pipe (8 cycles each); the busier pipe bounds the rate
+        step_s = ms * 1e-3 / args.steps
+        int_peak, int_src = popc_peak_gdist(sm_max)
+        # the limit of K1's own instruction mix: per distance 26.5 LOP3 + 3 VIMNMX
+        # on the ALU pipe (2 cycles per warp instruction per sub-partition) and 7.75 POPC on the XU pipe
+        # (8 cycles each); the busier pipe bounds the rate
         mix_cycles = max((26.5 + 3.0) * 2.0, 7.75 * 8.0)
-        mix_peak = 148 * 4 * 32 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / mix_cycles / 1e9
-        roofline = {"bound": "int-popc", "achieved": per_gpu, "peak": peak, "unit": UNIT + "/GPU",
-                    "frac": per_gpu / peak, "peak_source": peak_src,
-                    "pipe_limit_of_kernel_mix": {"peak": mix_peak, "frac": per_gpu / mix_peak,
-                                                 "cycles_per_warp_distance": mix_cycles,
-                                                 "mix": "26.5 LOP3 + 3 VIMNMX (ALU, 2 clk) | 7.75 POPC (XU, 8 clk) | 7.75 IMAD (FMA)"},
-                    "work_per_unit": "1 dist = 512 compared bits = 16 x 32-bit POPC (naive); the kernel folds "
-                                     "words with LOP3 carry-save adders first, so frac can exceed 1",
-                    "traffic": traffic,
-                    "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
-                            "algorithmic_bytes_per_launch": alg_bytes,
-                            "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"}}
+        mix_peak = 148 * 4 * 32 * sm_max * 1e6 / mix_cycles / 1e9
+        int_gpu = engines["int"]["value"] / world
+        int_roof = {"bound": "int-popc", "achieved": int_gpu, "peak": int_peak, "unit": UNIT + "/GPU",
+                    "frac": int_gpu / int_peak, "frac_of_binding_pipe": int_gpu / mix_peak,
+                    "binding_pipe_peak": mix_peak, "peak_source": int_src,
+                    "mix": "26.5 LOP3 + 3 VIMNMX (ALU, 2 clk) | 7.75 POPC (XU, 8 clk) | 7.75 IMAD (FMA)",
+                    "work_per_unit": "1 dist = 512 compared bits = 16 x 32-bit POPC (naive); the kernel folds words "
+                                     "with LOP3 carry-save adders first, so frac can exceed 1"}
+        tc_gpu = engines["tc"]["value"] / world
+        bf16_s = float(peaks.get("bf16_tflops_sustained", 1400.0)); bf16_b = float(peaks.get("bf16_tflops", 1590.0))
+        tc_tops = tc_gpu * 1024.0 / 1e3             # 1 dist = 512 int8 multiply-adds = 1024 ops
+        tprof = read_json(os.path.join(ROOT, "profiles", "k1t_traffic.json"), {}) or {}
+        tc_roof = {"bound": "tensor", "achieved": tc_tops, "peak": 2.0 * bf16_s, "unit": "TOP/s",
+                   "frac": tc_tops / (2.0 * bf16_s),
+                   "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (no int8 GEMM was measured on "
+                                  "this pool; the kind::i8 rate is nominally twice the bf16 rate); sustained because "
+                                  "the launches run back to back under the 1 kW cap" if peaks else "fallback",
+                   "frac_of_burst_peak": tc_tops / (2.0 * bf16_b), "frac_of_nominal_4500": tc_tops / 4500.0,
+                   "tensor_pipe_active_pct_ncu": tprof.get("sm__pipe_tensor_cycles_active_pct"),
+                   "work_per_unit": "1 dist = 512 int8 multiply-adds = 1024 ops (int32 accumulation, exact)"}
+        if primary == "tc":
+            alg_bytes = 512.0 * (nA + N_MAP / world) + 16.0 * nA
+            roofline = dict(tc_roof)
+            roofline["traffic"] = tprof.get("dram_bytes_per_launch")
+            roofline["int_engine"] = int_roof
+        else:
+            alg_bytes = 64.0 * (nA + N_MAP / world) + 16.0 * nA
+            roofline = dict(int_roof)
+            roofline["traffic"] = (read_json(os.path.join(ROOT, "profiles", "k1_traffic.json"), {}) or {}).get(
+                "dram_bytes_per_launch")
+            roofline["tc_engine"] = tc_roof
+        hbm_gbs = alg_bytes / step_s / 1e9
+        roofline["hbm"] = {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak,
+                           "algorithmic_bytes_per_launch": alg_bytes,
+                           "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": workload_config(world),
+            "scaling": "strong", "vs_baseline": None, "dtype": "s8" if primary == "tc" else "u32", "data": "synthetic",
+            "config": workload_config(world, primary, exchange),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nA * 64),
                     "d2h_bytes_per_step": int(nA * 16),
                     "inputs": "queries H2D from pinned memory + top-2 D2H every step; map table resident "
@@ -510,15 +710,21 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
-            "result_check": "planted matches found, d0<=d1" if ok else "FAILED",
+            "engines": engines,
+            "engines_agree": engines_agree,
+            "parity_vs_oracle_sample": parity,
+            "result_check": "planted matches found, d0<=d1, engines agree, %d queries bit-equal to the oracle over "
+                            "all %d rows" % (PARITY_QUERIES, N_MAP) if ok else "FAILED",
         }
         if world == 1 and args.workload == "c3":
             line["localize"] = localize_bench(g, with_cpu=not args.no_cpu_baseline)
-        if not args.no_cpu_baseline and world == 1 and args.workload == "c3":
-            cb, (ci, cd, nq, nb) = cpu_baseline_sample(A, shard)
-            # the same sample through the GPU path must agree bit for bit
-            gi, gd = g.knn2_host(A[:nq], shard[:nb])
-            cb["gpu_equals_cpu_on_sample"] = bool(np.array_equal(gi, ci) and np.array_equal(gd, cd))
+        if not args.no_cpu_baseline and world == 1:
+            cb, cpath = run_child("knn2", ["--budget", "12"])
+            s = np.load(cpath)
+            nq, nb = int(s["nq"]), int(s["nb"])
+            gi, gd = g.knn2_host(A[:nq], shard[:nb])      # the same sample through the GPU path
+            cb["gpu_equals_cpu_on_sample"] = bool(np.array_equal(gi, s["idx"]) and np.array_equal(gd, s["dist"]))
+            os.remove(cpath)
             line["cpu_baseline"] = cb
         print(json.dumps(line))
     dA.free(); dB.free()
@@ -530,6 +736,217 @@ def main():
         os.remove(id_path)
     if not ok:
         sys.exit(1)
+
+
+# --------------------------------------------------------------------------- C1 on its own
+def bench_c1(args, rank, world, local_rank):
+    """Replicas only: every rank localises the same query; rank 0 reports N x its rate."""
+    from sfmlocalization_b200.gpu import HuloGpu
+    g = HuloGpu(local_rank)
+    sampler = ClockSampler(local_rank); sampler.start()
+    loc = localize_bench(g, with_cpu=(rank == 0 and not args.no_cpu_baseline), reps=max(args.steps, 10))
+    clocks = sampler.stop()
+    g.close()
+    if rank == 0:
+        v = loc["localizations_per_s"] * world
+        print(json.dumps({"metric": "query_localizations_per_s", "value": v, "unit": "localizations/s", "n_gpus": world,
+                          "steps": max(args.steps, 10), "warmup": 3, "ms_per_step": loc["ms_per_query"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 / f32",
+                          "data": "synthetic", "config": {"workload": WORKLOAD_NAMES["c1"], "sharding": "replicas only"},
+                          "e2e": {"value": v, "unit": "localizations/s", "h2d_bytes_per_step": 2000 * 64 + 2000 * 16,
+                                  "d2h_bytes_per_step": 96,
+                                  "inputs": "query descriptors and keypoints from host memory, pose back, every query"},
+                          "gpu_launches": 10, "clocks": clocks, "localize": loc,
+                          "cpu_baseline": loc.get("cpu_baseline")}))
+
+
+# --------------------------------------------------------------------------- C2: pair-sharded matching
+def bench_pairs(args, rank, world, local_rank):
+    """hulo_match_pairs on this rank's share of the 19900 pairs (LPT partition, no data-path
+    collective: every rank holds all descriptors).  A step = the whole pair list once."""
+    from sfmlocalization_b200.gpu import HuloGpu
+    from tests import hostlib
+    g = HuloGpu(local_rank)
+    id_path = None
+    if world > 1:
+        uid, id_path = rendezvous_id(rank, world, HuloGpu.comm_unique_id)
+        g.comm_init(uid, rank, world)
+    n_img, rows = 200, 5000
+    allrows, off = c2_collection()
+    pairs = np.array([(a, b) for a in range(n_img) for b in range(a + 1, n_img)], np.uint64)
+    # one rank keeps the list order (the CPU sample below is its prefix); more ranks: LPT partition
+    pl = pairs if world == 1 else pairs[hostlib.partition_pairs(pairs, np.full(n_img, rows), rank, world)]
+    db = g.db(allrows, off)                                     # resident: descriptors uploaded once
+    cap = 4 << 20
+    sampler = ClockSampler(local_rank); sampler.start()
+    for _ in range(max(1, min(args.warmup, 2))):
+        g.match_pairs(db, pl, 0.7, cap=cap)
+    g.comm_barrier() if world > 1 else g.synchronize()
+    sampler.mark_timed_region()
+    steps = max(1, min(args.steps, 5))
+    l0 = g.launch_count
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o, oi, oj = g.match_pairs(db, pl, 0.7, cap=cap)
+    dt = time.perf_counter() - t0
+    launches = g.launch_count - l0
+    dt = g.comm_max(dt) if world > 1 else dt
+    clocks = sampler.stop()
+    dist_total = float(len(pairs)) * rows * rows
+    value = dist_total * steps / dt / 1e9
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": WORKLOAD_NAMES["c2"],
+                           "sharding": "pair list partitioned over %d rank(s) by n_I x n_J (LPT), descriptors (64 MB) "
+                                       "replicated, no data-path collective" % world,
+                           "cache": "64 MB of descriptors stay in L2; the pair outputs are compacted on the device"},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": int(len(pl) * 32),
+                        "d2h_bytes_per_step": int(len(oi) * 8 + len(o) * 8),
+                        "inputs": "the timed call is the C-ABI call itself: pair list H2D, ratio + one-to-one filters "
+                                  "and compaction on the device, match lists D2H; value is therefore the end-to-end "
+                                  "number"},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "pairs_per_s": len(pairs) * steps / dt, "matches_on_rank0": int(len(oi)),
+                "roofline": {"bound": "int-popc", "achieved": value / world, "peak": popc_peak_gdist(1965.0)[0],
+                             "unit": UNIT + "/GPU", "frac": value / world / popc_peak_gdist(1965.0)[0],
+                             "note": "item mode of K1 (integer pipes): per pair 5000 x 5000; wall clock of the whole "
+                                     "call, not kernel time"}}
+        if not args.no_cpu_baseline and world == 1:
+            cb, cpath = run_child("pairs", ["--budget", "15"])
+            s = np.load(cpath)
+            npairs = int(s["n_pairs"])
+            k_of = o[:npairs + 1]
+            got = np.stack([np.repeat(np.arange(npairs), np.diff(k_of)), oi[:k_of[-1]], oj[:k_of[-1]]], axis=1)
+            cb["gpu_equals_cpu_on_sample"] = bool(np.array_equal(got.astype(np.int64), s["matches"]))
+            os.remove(cpath)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    db.free()
+    if world > 1:
+        g.comm_barrier()
+    g.close()
+    if rank == 0 and id_path and os.path.exists(id_path):
+        os.remove(id_path)
+
+
+# --------------------------------------------------------------------------- C4: batched server
+def bench_server(args, rank, world, local_rank):
+    """256 concurrent queries end to end (hulo_engine_localize_batch); queries sharded over the
+    ranks, map replicated -- replicas, no data-path collective.  A step = all 256 queries once."""
+    from sfmlocalization_b200.gpu import HuloGpu, LocalizeEngine
+    g = HuloGpu(local_rank)
+    id_path = None
+    if world > 1:
+        uid, id_path = rendezvous_id(rank, world, HuloGpu.comm_unique_id)
+        g.comm_init(uid, rank, world)
+    n_queries, nq = 256, 3000
+    sc = c4_scene()
+    mine = list(range(rank, n_queries, world))
+    qs = [synth.extra_query(sc, nq, 4100 + 10 + k) for k in mine]
+    eng = LocalizeEngine(g, sc["rows"], sc["seg_offsets"], sc["obs_view"], sc["obs_feat"], sc["obs_landmark"],
+                         sc["landmark_X"], sc["K"], ratio=0.6)
+    descs = [q["q_desc"] for q in qs]; xys = [q["q_xy"] for q in qs]
+    sampler = ClockSampler(local_rank); sampler.start()
+    eng.localize_batch(descs[:2], xys[:2])
+    eng.localize_batch(descs, xys, seed=4)
+    g.comm_barrier() if world > 1 else g.synchronize()
+    sampler.mark_timed_region()
+    steps = max(1, min(args.steps, 5))
+    l0 = g.launch_count
+    t0 = time.perf_counter()
+    for s in range(steps):
+        b = eng.localize_batch(descs, xys, seed=5 + s)
+    dt = time.perf_counter() - t0
+    launches = g.launch_count - l0
+    dt = g.comm_max(dt) if world > 1 else dt
+    clocks = sampler.stop()
+    n_ok = float(b["localized"].sum())
+    err = [float(np.linalg.norm(b["center"][k] - qs[k]["center"])) for k in range(len(qs)) if b["localized"][k]]
+    n_ok = -g.comm_max(-n_ok) if world > 1 else n_ok
+    value = n_queries * steps / dt
+    if rank == 0:
+        map_rows = int(sc["rows"].shape[0])
+        line = {"metric": "query_localizations_per_s", "value": value, "unit": "localizations/s", "n_gpus": world,
+                "steps": steps, "warmup": 2, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u32 / f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD_NAMES["c4"],
+                           "sharding": "queries over %d rank(s), map (%d rows, %d MB) replicated, no data-path "
+                                       "collective" % (world, map_rows, map_rows * 64 // 10**6),
+                           "cache": "map 128 MB ~ L2 size; searched once per batch"},
+                "e2e": {"value": value, "unit": "localizations/s",
+                        "h2d_bytes_per_step": int(len(mine) * nq * (64 + 16)), "d2h_bytes_per_step": int(len(mine) * 104),
+                        "inputs": "the timed call is hulo_engine_localize_batch itself: query descriptors and "
+                                  "keypoints from host memory, poses back; value is the end-to-end number"},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "matching_gdist_per_s": float(n_queries) * nq * map_rows * steps / dt / 1e9,
+                "stage_ms_last_step": {"putMatch": float(b["times_ms"][0]), "assembly": float(b["times_ms"][1]),
+                                       "PnP": float(b["times_ms"][2])},
+                "min_localized_on_a_rank": int(n_ok), "queries_per_rank": len(mine),
+                "centre_error_m_median_rank0": float(np.median(err)) if err else None,
+                "roofline": {"bound": "int-popc", "achieved": float(n_queries) * nq * map_rows * steps / dt / 1e9 / world,
+                             "peak": popc_peak_gdist(1965.0)[0], "unit": UNIT + "/GPU",
+                             "frac": float(n_queries) * nq * map_rows * steps / dt / 1e9 / world / popc_peak_gdist(1965.0)[0],
+                             "note": "whole-call wall clock attributed to the matching work (the dominant stage)"}}
+        if not args.no_cpu_baseline and world == 1:
+            cb, cpath = run_child("server", ["--budget", "25"], timeout=1800)
+            if os.path.exists(cpath):
+                os.remove(cpath)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        g.comm_barrier()
+    g.close()
+    if rank == 0 and id_path and os.path.exists(id_path):
+        os.remove(id_path)
+
+
+ARGS = None
+
+
+def main():
+    global ARGS, N_QUERIES, N_MAP, SEED
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="c3 (default, the headline): 4096 x 10M flat search; see the module docstring")
+    ap.add_argument("--engine", default="tc", choices=["tc", "int"],
+                    help="arithmetic of the flat search the headline value is measured on (the other one is "
+                         "measured beside it): tc = int8 tensor-core contraction (K1t), int = integer pipes (K1)")
+    ap.add_argument("--cpu-leg", default=None, choices=sorted(CPU_LEGS), help=argparse.SUPPRESS)
+    ap.add_argument("--out", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--budget", type=float, default=12.0, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    ARGS = args
+    if args.workload == "c5":
+        N_QUERIES, N_MAP, SEED = 16384, 50_000_000, 5000
+    if args.cpu_leg:
+        CPU_LEGS[args.cpu_leg](args)
+        return
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.workload in ("c3", "c5"):
+        bench_flat(args, rank, world, local_rank)
+    elif args.workload == "c1":
+        bench_c1(args, rank, world, local_rank)
+    elif args.workload == "c2":
+        bench_pairs(args, rank, world, local_rank)
+    else:
+        bench_server(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":

@@ -66,16 +66,19 @@ int hulo_synchronize(hulo_gpu *h);
 /* Number of kernels this library launched on the context since creation. */
 uint64_t hulo_launch_count(const hulo_gpu *h);
 
-/* Arithmetic of the flat 2-NN searches (hulo_knn2, hulo_knn2_host, hulo_knn2_sharded).  Both give
- * the same exact result, bit for bit, as the cv::flann::Index::knnSearch(k=2) replacement they
- * stand for (MatchUtils.cpp:105-108, 339-340):
- *   HULO_KNN_INT  XOR + popcount on the integer pipes (K1) -- the default;
- *   HULO_KNN_TC   the 512 bits of a row as +-1 int8 values, distance = (512 - dot) / 2 from an int8
- *                 contraction with int32 accumulation on the tensor cores (K1t, tcgen05.mma.kind::i8).
- *                 Costs one expanded copy (512 bytes per row) of every table it searches.
- * The environment variable HULO_KNN_ENGINE=tc selects HULO_KNN_TC at hulo_gpu_create. */
+/* Arithmetic of the flat 2-NN searches (hulo_knn2, hulo_knn2_host, hulo_knn2_sharded).  Both
+ * engines give the same exact result, bit for bit, as the cv::flann::Index::knnSearch(k=2)
+ * replacement they stand for (MatchUtils.cpp:105-108, 339-340):
+ *   HULO_KNN_INT   XOR + popcount on the integer pipes (K1);
+ *   HULO_KNN_TC    the 512 bits of a row as +-1 int8 values, distance = (512 - dot) / 2 from an int8
+ *                  contraction with int32 accumulation on the tensor cores (K1t, tcgen05.mma.kind::i8).
+ *                  Costs one expanded copy (512 bytes per row) of every table it searches;
+ *   HULO_KNN_AUTO  (default) K1t when the search is large enough to pay for the expanded copies
+ *                  (at least 128 searcher rows, 8192 database rows and 2^28 distances), else K1.
+ * The environment variable HULO_KNN_ENGINE=int|tc|auto overrides the default at hulo_gpu_create. */
 #define HULO_KNN_INT 0
 #define HULO_KNN_TC 1
+#define HULO_KNN_AUTO 2
 int hulo_gpu_set_knn_engine(hulo_gpu *h, int engine);
 int hulo_gpu_knn_engine(const hulo_gpu *h);
 

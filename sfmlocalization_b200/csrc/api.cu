@@ -173,7 +173,8 @@ int run_flat_k1(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t n
     h->last_nA = nA;
     run->n_chunks = 0; run->rows_per_chunk = 1; run->slot_stride = 0;
     if (nA == 0) return HULO_OK;
-    if (h->knn_engine == HULO_KNN_TC) return run_flat_k1_tc(h, A, nA, B, nB, run);
+    const bool big = nA >= 128 && nB >= 8192 && (uint64_t)nA * nB >= (1ull << 28);
+    if (h->knn_engine == HULO_KNN_TC || (h->knn_engine == HULO_KNN_AUTO && big)) return run_flat_k1_tc(h, A, nA, B, nB, run);
     FlatPlan pl = plan_flat(h, nA, nB);
     run->n_chunks = pl.n_chunks; run->rows_per_chunk = pl.rows_per_chunk; run->slot_stride = pl.slot_stride;
     if (pl.n_chunks > 0) {
@@ -312,6 +313,12 @@ int hulo_gpu_create(int device, hulo_gpu **out) {
     {
         const char *eng = getenv("HULO_KNN_ENGINE");
         if (eng && (!strcmp(eng, "tc") || !strcmp(eng, "1"))) h->knn_engine = HULO_KNN_TC;
+        else if (eng && (!strcmp(eng, "int") || !strcmp(eng, "0"))) h->knn_engine = HULO_KNN_INT;
+        else if (eng && *eng && strcmp(eng, "auto") && strcmp(eng, "2")) {
+            set_error("hulo_gpu_create: HULO_KNN_ENGINE=%s (expected int, tc or auto)", eng);
+            hulo_gpu_destroy(h);
+            return HULO_ERR_ARG;
+        }
     }
     *out = h;
     return HULO_OK;
@@ -319,7 +326,7 @@ int hulo_gpu_create(int device, hulo_gpu **out) {
 
 int hulo_gpu_set_knn_engine(hulo_gpu *h, int engine) {
     HULO_ARG(h != nullptr, "null context");
-    HULO_ARG(engine == HULO_KNN_INT || engine == HULO_KNN_TC, "unknown engine");
+    HULO_ARG(engine == HULO_KNN_INT || engine == HULO_KNN_TC || engine == HULO_KNN_AUTO, "unknown engine");
     h->knn_engine = engine;
     return HULO_OK;
 }

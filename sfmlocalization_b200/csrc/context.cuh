@@ -101,9 +101,9 @@ struct hulo_gpu {
     hulo::KnnConfig knn_cfg{512, 4, 89, 1};  // best of the sweeps on C3 (profiles/r1_k1_variant_sweep.txt, r1_k1_sweep_folded.txt)
     bool knn_cfg_forced = false;
 
-    // K1 arithmetic: HULO_KNN_INT = integer pipes (knn2.cu, the conformant default),
-    // HULO_KNN_TC = int8 contraction on the tensor cores (knn2_tc.cu); flat searches only
-    int knn_engine = 0;
+    // K1 arithmetic of the flat searches: HULO_KNN_INT = integer pipes (knn2.cu), HULO_KNN_TC = int8
+    // contraction on the tensor cores (knn2_tc.cu), HULO_KNN_AUTO = K1t for large searches
+    int knn_engine = HULO_KNN_AUTO;
     // tile images of K1t: one per registered table (built on first use, dropped when the table
     // changes), and two scratch images for staged rows
     struct TcImage { const void *rows; size_t n; bool valid; hulo::DevBuf img; };

@@ -15,7 +15,7 @@ def engine(request, gpu):
     pipes (K1) and the int8 tensor-core contraction (K1t).  Same bit-exact expectations."""
     gpu.set_knn_engine(request.param)
     yield request.param
-    gpu.set_knn_engine("int")
+    gpu.set_knn_engine("auto")
 
 
 def run_gpu(gpu, A, B):

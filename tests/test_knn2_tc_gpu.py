@@ -14,7 +14,7 @@ def tc_engine(gpu):
     gpu.set_knn_engine("tc")
     assert gpu.knn_engine == "tc"
     yield
-    gpu.set_knn_engine("int")
+    gpu.set_knn_engine("auto")
 
 
 @pytest.mark.parametrize("nA,nB", [(127, 255), (128, 256), (129, 257), (1, 100000), (385, 65537), (7000, 2300),

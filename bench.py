@@ -818,8 +818,9 @@ def bench_pairs(args, rank, world, local_rank):
             cb, cpath = run_child("pairs", ["--budget", "15"])
             s = np.load(cpath)
             npairs = int(s["n_pairs"])
-            k_of = o[:npairs + 1]
-            got = np.stack([np.repeat(np.arange(npairs), np.diff(k_of)), oi[:k_of[-1]], oj[:k_of[-1]]], axis=1)
+            k_of = o[:npairs + 1].astype(np.int64)
+            got = np.stack([np.repeat(np.arange(npairs), np.diff(k_of)), oi[:k_of[-1]].astype(np.int64),
+                            oj[:k_of[-1]].astype(np.int64)], axis=1)
             cb["gpu_equals_cpu_on_sample"] = bool(np.array_equal(got.astype(np.int64), s["matches"]))
             os.remove(cpath)
             line["cpu_baseline"] = cb

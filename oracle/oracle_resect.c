@@ -22,6 +22,50 @@
  *   multiview/solver_resection_p3p.hpp (Kneip CVPR 2011)   -> orc_p3p
  *   multiview/projection.hpp (Project, KRt_From_P)         -> orc_residuals, orc_krt_from_p
  * The P3P solution set is cross-checked against cv2.solveP3P in tests/.
+ *
+ * INDEPENDENT ANCHORS (tests/test_oracle_anchors.py; the restatement does not check itself):
+ *   - orc_logcombi / orc_best_nfa against exact integer binomials (math.comb) on 1000 residual
+ *     lists with ties and threshold cuts;
+ *   - the final inlier sets of orc_acransac against cv2.solvePnPRansac(SOLVEPNP_P3P) at the
+ *     estimated threshold, and against the planted truth (fixtures: tests/golden/anchors_golden.npz,
+ *     generator: tests/golden/make_golden_anchors.py).
+ *
+ * CONSTANTS TAKEN FROM MEMORY OF THE UPSTREAM SOURCE (SURVEY.md appendix B marks them with a
+ * dagger).  Each with the upstream file a maintainer can open to confirm it, and why the value is
+ * what it is:
+ *   max_iteration = 4096          sfm/pipelines/localization/SfM_Localizer.hpp, member initialiser of
+ *                                 Image_Localizer_Match_Data; the reference never overrides it
+ *                                 (LocalizeEngine.cc:503-505 sets only pt2D / pt3D).
+ *   error_max = infinity          same struct; Localize() passes precision = error_max^2 only when
+ *                                 it is finite, so AC-RANSAC runs threshold-free (maxThreshold = inf).
+ *   MINIMUM_SAMPLES = 3,          multiview/solver_resection_p3p.hpp, P3PSolver: a P3P problem has 3
+ *   MAX_MODELS = 4                points and at most 4 real solutions of its quartic.
+ *   logalpha0 = log10(pi)         robust_estimator_ACRansacKernelAdaptator.hpp, ACKernelAdaptorResection_K:
+ *                                 the residual is a point-to-point distance in K-normalised image
+ *                                 coordinates; the probability that a uniform point falls within
+ *                                 distance d of a given point is pi d^2 / (unit area), i.e. alpha0 = pi
+ *                                 with the squared error e = d^2 entering as log10(e).
+ *   multError = 1.0               same adaptor: the error is already squared (0.5 is used by the
+ *                                 kernels that hand over unsquared point-to-line distances).
+ *   loge0 = log10(MAX_MODELS *    robust_estimator_ACRansac.hpp: number of tests = models per sample
+ *           (N - MINIMUM_SAMPLES))  x number of candidate inlier counts.
+ *   NFA_k = loge0 + logalpha *    same file, bestNFA(): the classical a-contrario bound
+ *     (k - 3) + log10 C(N,k) +      N_tests * C(N,k) * C(k,3) * alpha^(k-3), in log10; the binomial
+ *     log10 C(k,3)                  tables are float (std::vector<float>), reproduced as float here.
+ *   + FLT_EPSILON                 same function: log10(e + numeric_limits<float>::epsilon()) so that a
+ *                                 zero residual (the three sample points) stays finite.
+ *   start index k = 4             same function: loops from MINIMUM_SAMPLES + 1; a model is scored on at
+ *                                 least one point beyond its own sample.
+ *   reserve = max_iter / 10       ACRANSAC(): nIterReserve = nIter / 10, nIter -= nIterReserve; the
+ *                                 reserve is spent on samples drawn from the current inlier set once a
+ *                                 meaningful (NFA < 0) model exists.
+ *   success iff inliers > 2.5 * 3 SfM_Localizer.cpp, Localize(): "resection_data.vec_inliers.size() >
+ *                                 MINIMUM_SAMPLES * OPENMVG_MINIMUM_SAMPLES_COEF" with the coefficient 2.5.
+ *   unormalizeError(e) =          adaptor: back to pixels through the normalisation K^-1, whose scale is
+ *     sqrt(e) * fx                1 / fx (the reference's cameras have fx ~ fy, K.txt:1-3).
+ * What remains UNPINNED after the anchors: bit-level agreement of a whole AC-RANSAC trace with
+ * OpenMVG's (impossible in principle: upstream seeds its sampler from the clock), and the
+ * constants above, which are confirmed only by the statistical agreement of the outcomes.
  * Known deviations: (1) the sampler is a seeded splitmix64 instead of std::rand (upstream
  * seeds non-deterministically, so traces are not comparable anyway); (2) P3P models with
  * non-finite entries are skipped instead of being sorted with NaN residuals; (3) the narrowed

@@ -103,25 +103,25 @@ static FlatPlan plan_flat(const hulo_gpu *h, size_t nA, size_t nB) {
 
 // ------------------------------------------------------------- K1t tile images
 void tc_image_register(hulo_gpu *h, const void *rows) {
-    for (auto &e : h->tc_images) if (e.rows == rows) { e.valid = false; return; }
-    h->tc_images.push_back(hulo_gpu::TcImage{rows, 0, false, DevBuf{}});
+    for (auto &e : h->tc_images) if (e.rows == rows) e.valid = false;
+    for (auto &e : h->tc_images) if (e.rows == rows && !e.seg) return;
+    h->tc_images.push_back(hulo_gpu::TcImage{rows, 0, false, false, {}, DevBuf{}});
 }
 void tc_image_invalidate(hulo_gpu *h, const void *rows) {
     for (auto &e : h->tc_images) if (e.rows == rows) e.valid = false;
 }
 void tc_image_drop(hulo_gpu *h, const void *rows) {
-    for (size_t k = 0; k < h->tc_images.size(); ++k)
+    for (size_t k = h->tc_images.size(); k-- > 0;)
         if (h->tc_images[k].rows == rows) {
             h->tc_images[k].img.release();
             h->tc_images.erase(h->tc_images.begin() + (long)k);
-            return;
         }
 }
 // Tile image of `n` folded rows at `rows`: the cached one when the rows are a registered table,
 // else expanded into `scratch`.
 static int tc_image_for(hulo_gpu *h, const uint4 *rows, size_t n, DevBuf &scratch, const uint8_t **out) {
     for (auto &e : h->tc_images) {
-        if (e.rows != rows) continue;
+        if (e.rows != rows || e.seg) continue;
         if (!e.valid || e.n != n) {
             HULO_CUDA(e.img.reserve(knn2_tc_image_bytes(n)));
             HULO_CUDA(knn2_tc_expand_launch(rows, n, e.img.as<uint8_t>(), h->stream));
@@ -136,6 +136,74 @@ static int tc_image_for(hulo_gpu *h, const uint4 *rows, size_t n, DevBuf &scratc
     HULO_CUDA(knn2_tc_expand_launch(rows, n, scratch.as<uint8_t>(), h->stream));
     h->launches++;
     *out = scratch.as<uint8_t>();
+    return HULO_OK;
+}
+
+// Segmented tile image: every segment [seg[s], seg[s + 1]) starts on an even tile, so that it can be
+// read as searcher (128-row tiles) and as database (256-row tiles).  Fills tile0 (n_seg + 1 entries).
+static int tc_build_seg_image(hulo_gpu *h, const uint4 *rows, const uint64_t *seg, size_t n_seg, DevBuf &img,
+                              std::vector<uint32_t> &tile0) {
+    tile0.assign(n_seg + 1, 0);
+    std::vector<uint32_t> tab;                 // tile_src | tile_rows
+    for (size_t s = 0; s < n_seg; ++s) tile0[s + 1] = tile0[s] + 2u * (uint32_t)((seg[s + 1] - seg[s] + kTcTileN - 1) / kTcTileN);
+    const size_t n_tiles = std::max<size_t>(tile0[n_seg], 2);
+    tab.assign(2 * n_tiles, 0);
+    for (size_t s = 0; s < n_seg; ++s) {
+        const uint64_t n = seg[s + 1] - seg[s];
+        for (uint32_t t = tile0[s]; t < tile0[s + 1]; ++t) {
+            const uint64_t first = (uint64_t)(t - tile0[s]) * kTcTileRows;
+            tab[t] = (uint32_t)(seg[s] + std::min<uint64_t>(first, n));
+            tab[n_tiles + t] = first < n ? (uint32_t)std::min<uint64_t>(kTcTileRows, n - first) : 0u;
+        }
+    }
+    HULO_CUDA(img.reserve(n_tiles * kTcTileBytes));
+    HULO_CUDA(h->tc_tiles.reserve(tab.size() * sizeof(uint32_t)));
+    HULO_CUDA(cudaMemcpyAsync(h->tc_tiles.ptr, tab.data(), tab.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    HULO_CUDA(knn2_tc_expand_tiles_launch(rows, h->tc_tiles.as<uint32_t>(), h->tc_tiles.as<uint32_t>() + n_tiles, n_tiles,
+                                          img.as<uint8_t>(), h->stream));
+    h->launches++;
+    // the table is host memory of this call: the copy must have left it before it is reused
+    HULO_CUDA(cudaStreamSynchronize(h->stream));
+    return HULO_OK;
+}
+
+// The cached segmented image of a resident table.
+static int tc_seg_image_for_db(hulo_gpu *h, const hulo_db *db, const uint8_t **img, const uint32_t **tile0) {
+    hulo_gpu::TcImage *e = nullptr;
+    for (auto &x : h->tc_images) if (x.rows == db->rows && x.seg) e = &x;
+    if (!e) {
+        h->tc_images.push_back(hulo_gpu::TcImage{db->rows, 0, false, true, {}, DevBuf{}});
+        e = &h->tc_images.back();
+    }
+    if (!e->valid || e->n != db->n || e->tile0.size() != db->seg.size()) {
+        int rc = tc_build_seg_image(h, db->rows, db->seg.data(), db->seg.size() - 1, e->img, e->tile0);
+        if (rc != HULO_OK) return rc;
+        e->n = db->n;
+        e->valid = true;
+    }
+    *img = e->img.as<uint8_t>();
+    *tile0 = e->tile0.data();
+    return HULO_OK;
+}
+
+// Engine choice for a search of `dist` distance evaluations.
+static bool tc_wanted(const hulo_gpu *h, uint64_t dist, uint64_t min_dist) {
+    return h->knn_engine == HULO_KNN_TC || (h->knn_engine == HULO_KNN_AUTO && dist >= min_dist);
+}
+
+// K1t over an item list; the caller has reserved h->partial.
+static int run_items_tc(hulo_gpu *h, const uint8_t *imgA, const uint8_t *imgB, const std::vector<TcItem> &items) {
+    if (items.empty()) return HULO_OK;
+    HULO_CUDA(h->items.reserve(items.size() * sizeof(TcItem)));
+    HULO_CUDA(cudaMemcpyAsync(h->items.ptr, items.data(), items.size() * sizeof(TcItem), cudaMemcpyHostToDevice, h->stream));
+    TcParams tp{};
+    tp.imgA = imgA; tp.imgB = imgB;
+    tp.items = h->items.as<TcItem>();
+    tp.n_items = (uint32_t)items.size();
+    tp.partial = h->partial.as<uint2>();
+    tp.cluster = 1;
+    HULO_CUDA(knn2_tc_launch(tp, h->sm_count, h->stream));
+    h->launches++;
     return HULO_OK;
 }
 
@@ -551,6 +619,45 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     HULO_ARG(n_rows < (uint64_t)INT_MAX, "too many rows selected");
     if (n_rows == 0) return hulo_synchronize(h);
 
+    const uint64_t slot_stride = (n_rows + 31) & ~31ull;
+    uint32_t n_chunks = 0, rows_per_chunk = 1;
+    const bool use_tc = nq <= kMaxChunkRows && tc_wanted(h, n_rows * (uint64_t)nq, 1ull << 26);
+    // scratch0: val | dist ; scratch1: seg offsets (device) ; scratch2: block counts, seg_out_off, total
+    // scratch3: compacted outputs view | i | j | d0
+    const size_t n_blocks = (n_rows + kCompactBlockRows - 1) / kCompactBlockRows;
+    HULO_CUDA(h->scratch0.reserve(n_rows * 2 * sizeof(int32_t)));
+    HULO_CUDA(h->scratch1.reserve((n_views + 1) * sizeof(uint64_t)));
+    HULO_CUDA(h->scratch2.reserve((n_blocks + 2) * sizeof(uint32_t) + (n_views + 2) * sizeof(uint64_t) + 64));
+    HULO_CUDA(h->scratch3.reserve(n_rows * 4 * sizeof(uint32_t)));
+    HULO_CUDA(cudaMemcpyAsync(h->scratch1.ptr, sel_off.data(), (n_views + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+    if (use_tc) {
+        // K1t: searcher tiles of 128 rows per view out of the map's segmented image, the query image
+        // as one database range (a single chunk)
+        const uint8_t *imgA = nullptr, *imgB = nullptr;
+        const uint32_t *tile0 = nullptr;
+        int rc = tc_seg_image_for_db(h, map, &imgA, &tile0);
+        if (rc != HULO_OK) return rc;
+        rc = tc_image_for(h, h->stageB.as<uint4>(), nq, h->tc_scratchB, &imgB);
+        if (rc != HULO_OK) return rc;
+        n_chunks = 1; rows_per_chunk = kMaxChunkRows;
+        std::vector<TcItem> items;
+        for (size_t v = 0; v < n_views; ++v) {
+            const size_t s = views ? views[v] : v;
+            const uint64_t rows = map->seg[s + 1] - map->seg[s];
+            for (uint64_t t0 = 0; t0 < rows; t0 += kTcTileRows) {
+                TcItem it{};
+                it.a_tile = tile0[s] + (uint32_t)(t0 / kTcTileRows);
+                it.a_rows = (uint32_t)std::min<uint64_t>(kTcTileRows, rows - t0);
+                it.b_tile0 = 0;
+                it.b_rows = (uint32_t)nq;
+                it.out_slot0 = sel_off[v] + t0;
+                items.push_back(it);
+            }
+        }
+        HULO_CUDA(h->partial.reserve((size_t)slot_stride * sizeof(uint2)));
+        rc = run_items_tc(h, imgA, imgB, items);
+        if (rc != HULO_OK) return rc;
+    } else {
     // items: maximal runs of views that are contiguous in the table, tiled, x chunks of the query
     const KnnConfig cfg = choose_config(h, (size_t)n_rows);
     const uint32_t tile = knn2_tile_rows(cfg);
@@ -568,9 +675,7 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     int ctas_per_sm = 1;
     knn2_kernel_info(cfg, nullptr, &ctas_per_sm, nullptr);
     int grid = h->sm_count * std::max(1, ctas_per_sm);
-    uint32_t n_chunks = 0, rows_per_chunk = 1;
     plan_chunks((uint32_t)n_tiles, nq, grid, &n_chunks, &rows_per_chunk);
-    const uint64_t slot_stride = (n_rows + 31) & ~31ull;
     std::vector<KnnItem> items;
     items.reserve((size_t)n_tiles * n_chunks);
     for (uint32_t c = 0; c < n_chunks; ++c) {
@@ -594,14 +699,6 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     HULO_CUDA(h->partial.reserve((size_t)n_chunks * slot_stride * sizeof(uint2)));
     HULO_CUDA(h->counter.reserve(sizeof(unsigned int)));
     HULO_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(unsigned int), h->stream));
-    // scratch0: val | dist ; scratch1: seg offsets (device) ; scratch2: block counts, seg_out_off, total
-    // scratch3: compacted outputs view | i | j | d0
-    const size_t n_blocks = (n_rows + kCompactBlockRows - 1) / kCompactBlockRows;
-    HULO_CUDA(h->scratch0.reserve(n_rows * 2 * sizeof(int32_t)));
-    HULO_CUDA(h->scratch1.reserve((n_views + 1) * sizeof(uint64_t)));
-    HULO_CUDA(h->scratch2.reserve((n_blocks + 2) * sizeof(uint32_t) + (n_views + 2) * sizeof(uint64_t) + 64));
-    HULO_CUDA(h->scratch3.reserve(n_rows * 4 * sizeof(uint32_t)));
-    HULO_CUDA(cudaMemcpyAsync(h->scratch1.ptr, sel_off.data(), (n_views + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
 
     KnnParams kp{};
     kp.A = map->rows; kp.B = h->stageB.as<uint4>();
@@ -612,6 +709,7 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     kp.counter = h->counter.as<unsigned int>();
     HULO_CUDA(knn2_launch(kp, cfg, grid, h->stream));
     h->launches++;
+    }
 
     int32_t *val = h->scratch0.as<int32_t>();
     int32_t *dist = val + n_rows;
@@ -711,6 +809,21 @@ int hulo_match_to_queries(hulo_gpu *h, const hulo_db *map, const uint32_t *views
     HULO_CUDA(knn2_fold_rows_launch(h->stageB.as<uint4>(), total_q_rows, h->stream));
     h->launches++;
 
+    // K1t: the map's segmented image as searcher tiles, one segmented image of all query images as
+    // database ranges; per (view tile, query) one item, the items of a view tile next to each other
+    const bool use_tc = tc_wanted(h, n_rows * total_q_rows, 1ull << 26);
+    const uint8_t *imgA = nullptr, *imgB = nullptr;
+    const uint32_t *tile0_map = nullptr;
+    std::vector<uint32_t> tile0_q;
+    std::vector<TcItem> tc_items;
+    if (use_tc) {
+        int rc = tc_seg_image_for_db(h, map, &imgA, &tile0_map);
+        if (rc != HULO_OK) return rc;
+        rc = tc_build_seg_image(h, h->stageB.as<uint4>(), q_offsets, n_queries, h->tc_scratchB, tile0_q);
+        if (rc != HULO_OK) return rc;
+        imgB = h->tc_scratchB.as<uint8_t>();
+    }
+
     const KnnConfig cfg = choose_config(h, (size_t)n_rows);
     const uint32_t tile = knn2_tile_rows(cfg);
     struct Run { uint64_t a0, rows, slot0; };
@@ -744,9 +857,28 @@ int hulo_match_to_queries(hulo_gpu *h, const hulo_db *map, const uint32_t *views
         const size_t nb = members.size();
         const uint64_t rows_total = (uint64_t)nb * n_rows;
         items.clear();
+        tc_items.clear();
         seg_off.assign(nb * n_views + 1, 0);
+        if (use_tc) {
+            for (size_t v = 0; v < n_views; ++v) {
+                const size_t s = views ? views[v] : v;
+                const uint64_t rows = map->seg[s + 1] - map->seg[s];
+                for (uint64_t t0 = 0; t0 < rows; t0 += kTcTileRows)
+                    for (size_t ql = 0; ql < nb; ++ql) {
+                        const size_t q = members[ql];
+                        TcItem it{};
+                        it.a_tile = tile0_map[s] + (uint32_t)(t0 / kTcTileRows);
+                        it.a_rows = (uint32_t)std::min<uint64_t>(kTcTileRows, rows - t0);
+                        it.b_tile0 = tile0_q[q];
+                        it.b_rows = (uint32_t)(q_offsets[q + 1] - q_offsets[q]);
+                        it.out_slot0 = (uint64_t)ql * n_rows + sel_off[v] + t0;
+                        tc_items.push_back(it);
+                    }
+            }
+        }
         for (size_t ql = 0; ql < nb; ++ql) {
             const size_t q = members[ql];
+            if (!use_tc)
             for (const Run &r : runs)
                 for (uint64_t t0 = 0; t0 < r.rows; t0 += tile) {
                     KnnItem it{};
@@ -762,16 +894,22 @@ int hulo_match_to_queries(hulo_gpu *h, const hulo_db *map, const uint32_t *views
         seg_off[nb * n_views] = rows_total;
         const size_t n_segs = nb * n_views;
         const size_t n_blocks = (rows_total + kCompactBlockRows - 1) / kCompactBlockRows;
+        HULO_CUDA(h->partial.reserve(rows_total * sizeof(uint2)));
+        if (!use_tc) {
         HULO_CUDA(h->items.reserve(items.size() * sizeof(KnnItem)));
         HULO_CUDA(cudaMemcpyAsync(h->items.ptr, items.data(), items.size() * sizeof(KnnItem), cudaMemcpyHostToDevice, h->stream));
-        HULO_CUDA(h->partial.reserve(rows_total * sizeof(uint2)));
         HULO_CUDA(h->counter.reserve(sizeof(unsigned int)));
         HULO_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(unsigned int), h->stream));
+        }
         HULO_CUDA(h->scratch0.reserve(rows_total * 2 * sizeof(int32_t)));
         HULO_CUDA(h->scratch1.reserve((n_segs + 1) * sizeof(uint64_t)));
         HULO_CUDA(h->scratch2.reserve((n_blocks + 2) * sizeof(uint32_t) + (n_segs + 2) * sizeof(uint64_t) + 64));
         HULO_CUDA(h->scratch3.reserve(rows_total * 3 * sizeof(uint32_t)));
         HULO_CUDA(cudaMemcpyAsync(h->scratch1.ptr, seg_off.data(), (n_segs + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
+        if (use_tc) {
+            int rc = run_items_tc(h, imgA, imgB, tc_items);
+            if (rc != HULO_OK) return rc;
+        } else {
         KnnParams kp{};
         kp.A = map->rows; kp.B = h->stageB.as<uint4>();
         kp.items = h->items.as<KnnItem>();
@@ -781,6 +919,7 @@ int hulo_match_to_queries(hulo_gpu *h, const hulo_db *map, const uint32_t *views
         kp.counter = h->counter.as<unsigned int>();
         HULO_CUDA(knn2_launch(kp, cfg, (int)std::min<size_t>((size_t)full_grid, items.size()), h->stream));
         h->launches++;
+        }
         int32_t *val = h->scratch0.as<int32_t>();
         int32_t *dist = val + rows_total;
         HULO_CUDA(post_query_launch(h->partial.as<uint2>(), (uint32_t)rows_total, 1, rows_total, kMaxChunkRows, ratio, val,
@@ -848,6 +987,19 @@ int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size
     knn2_kernel_info(cfg, nullptr, &ctas_per_sm, nullptr);
     const int full_grid = h->sm_count * std::max(1, ctas_per_sm);
 
+    // K1t: both sides of a pair out of the table's segmented image
+    uint64_t all_dist = 0;
+    for (size_t p = 0; p < n_pairs; ++p)
+        all_dist += (db->seg[pairs[2 * p] + 1] - db->seg[pairs[2 * p]]) * (db->seg[pairs[2 * p + 1] + 1] - db->seg[pairs[2 * p + 1]]);
+    const bool use_tc = tc_wanted(h, all_dist, 1ull << 26);
+    const uint8_t *img = nullptr;
+    const uint32_t *tile0 = nullptr;
+    std::vector<TcItem> tc_items;
+    if (use_tc) {
+        int rc = tc_seg_image_for_db(h, db, &img, &tile0);
+        if (rc != HULO_OK) return rc;
+    }
+
     // batches bounded by compact searcher rows so the scratch stays modest
     const uint64_t max_batch_rows = (uint64_t)std::max(1, env_int("HULO_PAIR_BATCH_ROWS", 16 << 20));
     size_t total_out = 0;
@@ -859,6 +1011,7 @@ int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size
         row_off.assign(1, 0);
         hist_off.assign(1, 0);
         items.clear();
+        tc_items.clear();
         size_t p1 = p0;
         while (p1 < n_pairs) {
             const uint32_t I = pairs[2 * p1], J = pairs[2 * p1 + 1];
@@ -868,7 +1021,17 @@ int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size
             HULO_ARG(skip || nJ <= kMaxChunkRows, "image with more than 4 Mi descriptors");
             const uint64_t add = skip ? 0 : nI;
             if (p1 > p0 && row_off.back() + add > max_batch_rows) break;
-            if (!skip) {
+            if (!skip && use_tc) {
+                for (uint64_t t0 = 0; t0 < nI; t0 += kTcTileRows) {
+                    TcItem it{};
+                    it.a_tile = tile0[I] + (uint32_t)(t0 / kTcTileRows);
+                    it.a_rows = (uint32_t)std::min<uint64_t>(kTcTileRows, nI - t0);
+                    it.b_tile0 = tile0[J];
+                    it.b_rows = (uint32_t)nJ;
+                    it.out_slot0 = row_off.back() + t0;
+                    tc_items.push_back(it);
+                }
+            } else if (!skip) {
                 for (uint64_t t0 = 0; t0 < nI; t0 += tile) {
                     KnnItem it{};
                     it.a_row0 = (uint32_t)(db->seg[I] + t0);
@@ -888,11 +1051,13 @@ int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size
         HULO_ARG(n_rows < (uint64_t)INT_MAX, "batch too large");
         if (n_rows > 0) {
             const size_t n_blocks = (n_rows + kCompactBlockRows - 1) / kCompactBlockRows;
-            HULO_CUDA(h->items.reserve(items.size() * sizeof(KnnItem)));
-            HULO_CUDA(cudaMemcpyAsync(h->items.ptr, items.data(), items.size() * sizeof(KnnItem), cudaMemcpyHostToDevice, h->stream));
             HULO_CUDA(h->partial.reserve(n_rows * sizeof(uint2)));
-            HULO_CUDA(h->counter.reserve(sizeof(unsigned int)));
-            HULO_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(unsigned int), h->stream));
+            if (!use_tc) {
+                HULO_CUDA(h->items.reserve(items.size() * sizeof(KnnItem)));
+                HULO_CUDA(cudaMemcpyAsync(h->items.ptr, items.data(), items.size() * sizeof(KnnItem), cudaMemcpyHostToDevice, h->stream));
+                HULO_CUDA(h->counter.reserve(sizeof(unsigned int)));
+                HULO_CUDA(cudaMemsetAsync(h->counter.ptr, 0, sizeof(unsigned int), h->stream));
+            }
             // scratch0: val ; scratch1: row_off | hist_off (device) ; scratch2: total, seg_out_off, block counts
             // scratch3: out_i | out_j ; gathered (reused): claim histogram
             HULO_CUDA(h->scratch0.reserve(n_rows * sizeof(int32_t)));
@@ -906,15 +1071,20 @@ int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size
             HULO_CUDA(cudaMemcpyAsync(d_hist_off, hist_off.data(), (bp + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, h->stream));
             HULO_CUDA(cudaMemsetAsync(h->gathered.ptr, 0, std::max<uint64_t>(hist_off.back(), 1) * sizeof(uint32_t), h->stream));
 
-            KnnParams kp{};
-            kp.A = db->rows; kp.B = db->rows;
-            kp.items = h->items.as<KnnItem>();
-            kp.n_items = (uint32_t)items.size();
-            kp.key_unit = 1u << kKeyIdxBits;
-            kp.partial = h->partial.as<uint2>();
-            kp.counter = h->counter.as<unsigned int>();
-            HULO_CUDA(knn2_launch(kp, cfg, (int)std::min<size_t>((size_t)full_grid, items.size()), h->stream));
-            h->launches++;
+            if (use_tc) {
+                int rc = run_items_tc(h, img, img, tc_items);
+                if (rc != HULO_OK) return rc;
+            } else {
+                KnnParams kp{};
+                kp.A = db->rows; kp.B = db->rows;
+                kp.items = h->items.as<KnnItem>();
+                kp.n_items = (uint32_t)items.size();
+                kp.key_unit = 1u << kKeyIdxBits;
+                kp.partial = h->partial.as<uint2>();
+                kp.counter = h->counter.as<unsigned int>();
+                HULO_CUDA(knn2_launch(kp, cfg, (int)std::min<size_t>((size_t)full_grid, items.size()), h->stream));
+                h->launches++;
+            }
 
             int32_t *val = h->scratch0.as<int32_t>();
             uint32_t *hist = h->gathered.as<uint32_t>();

@@ -106,9 +106,11 @@ struct hulo_gpu {
     int knn_engine = HULO_KNN_AUTO;
     // tile images of K1t: one per registered table (built on first use, dropped when the table
     // changes), and two scratch images for staged rows
-    struct TcImage { const void *rows; size_t n; bool valid; hulo::DevBuf img; };
+    // `seg`: the segmented form (every segment of the table starts on an even tile, tile0[s] = its
+    // first tile), used by the item-mode searches; else the flat form.
+    struct TcImage { const void *rows; size_t n; bool valid; bool seg; std::vector<uint32_t> tile0; hulo::DevBuf img; };
     std::vector<TcImage> tc_images;
-    hulo::DevBuf tc_scratchA, tc_scratchB;
+    hulo::DevBuf tc_scratchA, tc_scratchB, tc_tiles;
 
     hulo::DevBuf partial;      // K1 per-item keys
     hulo::DevBuf counter;      // K1 dynamic item counter

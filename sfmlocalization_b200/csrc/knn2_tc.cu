@@ -167,6 +167,36 @@ __device__ __forceinline__ void scan_block(const int32_t (&v)[64], uint32_t row0
     }
 }
 
+// One unit of work as every warp role sees it.
+struct TcWork {
+    uint32_t a_tile;     // image tile of the searcher rows
+    uint32_t a_rows;     // rows of it whose keys are written (0: none)
+    uint32_t b_tile0;    // first image tile (128 rows) of the database range, even
+    uint32_t b_rows;     // database rows scanned
+    uint64_t out_slot0;  // partial[out_slot0 + r] receives the keys of searcher row r of the tile
+};
+// Flat mode: item w -> group of CL consecutive searcher tiles (w % n_mgroups), chunk (w / n_mgroups).
+// Item mode: the list entry.
+template <int CL>
+__device__ __forceinline__ TcWork tc_work(const TcParams &p, uint32_t w, uint32_t n_mgroups, uint32_t crank) {
+    TcWork k;
+    if (p.items != nullptr) {
+        const TcItem it = p.items[w];
+        k.a_tile = it.a_tile; k.a_rows = it.a_rows; k.b_tile0 = it.b_tile0; k.b_rows = it.b_rows;
+        k.out_slot0 = it.out_slot0;
+    } else {
+        const uint32_t mt = (w % n_mgroups) * CL + crank, c = w / n_mgroups;
+        const uint32_t b_row0 = c * p.rows_per_chunk;
+        // a cluster past the last searcher tile repeats it (its results are not written)
+        k.a_tile = min(mt, p.n_mtiles - 1u);
+        k.a_rows = mt < p.n_mtiles ? min(kTcTileRows, p.nA - mt * kTcTileRows) : 0u;
+        k.b_tile0 = b_row0 / kTcTileRows;
+        k.b_rows = min(p.rows_per_chunk, p.nB - b_row0);
+        k.out_slot0 = (uint64_t)c * p.slot_stride + (uint64_t)mt * kTcTileRows;
+    }
+    return k;
+}
+
 // CL = CTAs per cluster.  The CTAs of a cluster work on CL consecutive searcher tiles against the
 // SAME database chunk in lockstep: every stage of B is fetched once per cluster, each CTA issuing
 // 1/CL of it as a multicast bulk copy into all CL shared memories, which divides the L2 -> SM
@@ -218,23 +248,36 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
     const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
     const uint32_t cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
     const uint32_t n_mgroups = (p.n_mtiles + CL - 1) / CL;
-    const uint32_t n_items = n_mgroups * p.n_chunks;
     constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+    // flat mode: items dealt round-robin over the clusters (the CTAs running at any moment share a few
+    // database chunks through L2); item mode: a contiguous block of the list per CTA, so that items
+    // with the same searcher tile follow each other and the tile stays in shared memory
+    uint32_t w_begin, w_end, w_step;
+    if (p.items != nullptr) {
+        w_begin = (uint32_t)((uint64_t)blockIdx.x * p.n_items / gridDim.x);
+        w_end = (uint32_t)((uint64_t)(blockIdx.x + 1) * p.n_items / gridDim.x);
+        w_step = 1;
+    } else {
+        w_begin = cluster_id; w_end = n_mgroups * p.n_chunks; w_step = n_clusters;
+    }
 
     if (warp == 0) {
         // ===== producer: searcher tile once per item, database stages through the ring =====
         if (lane == 0) {
-            uint32_t it = 0, stage = 0, ph = 0;
-            for (uint32_t w = cluster_id; w < n_items; w += n_clusters, ++it) {
-                // a cluster past the last searcher tile repeats it (its results are not written)
-                const uint32_t mt = min((w % n_mgroups) * CL + crank, p.n_mtiles - 1u), c = w / n_mgroups;
-                const uint32_t b_row0 = c * p.rows_per_chunk;
-                const uint32_t b_rows = min(p.rows_per_chunk, p.nB - b_row0);
-                const uint32_t n_tiles = (b_rows + kTcTileN - 1) / kTcTileN;
-                mbar_wait(bar_a_empty, (it & 1u) ^ 1u);                 // MMAs of the previous item are done with A
-                mbar_expect_tx(bar_a_full, kABytes);
-                bulk_load(sA, p.imgA + (size_t)mt * kTcTileBytes, kABytes, bar_a_full);
-                const uint8_t *src = p.imgB + (size_t)(b_row0 / kTcTileRows) * kTcTileBytes;
+            uint32_t stage = 0, ph = 0, a_loaded = 0xFFFFFFFFu, a_loads = 0;
+            for (uint32_t w = w_begin; w < w_end; w += w_step) {
+                const TcWork k = tc_work<CL>(p, w, n_mgroups, crank);
+                const uint32_t n_tiles = (k.b_rows + kTcTileN - 1) / kTcTileN;
+                if (k.a_tile != a_loaded) {
+                    // a new searcher tile: the MMAs that read the previous one must be done (the MMA
+                    // thread commits "A empty" when IT reaches this item; both sides count tile loads)
+                    if (a_loads > 0) mbar_wait(bar_a_empty, (a_loads - 1u) & 1u);
+                    mbar_expect_tx(bar_a_full, kABytes);
+                    bulk_load(sA, p.imgA + (size_t)k.a_tile * kTcTileBytes, kABytes, bar_a_full);
+                    a_loaded = k.a_tile;
+                    ++a_loads;
+                }
+                const uint8_t *src = p.imgB + (size_t)k.b_tile0 * kTcTileBytes;
                 for (uint32_t t = 0; t < n_tiles; ++t) {
                     for (uint32_t kc = 0; kc < kKChunks; ++kc) {
                         mbar_wait(bar_b_empty + 8 * stage, ph ^ 1u);
@@ -259,13 +302,16 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
     } else if (warp == 1) {
         // ===== MMA issuer: one thread =====
         if (lane == 0) {
-            uint32_t it = 0, stage = 0, ph = 0, acc_it = 0;
-            for (uint32_t w = cluster_id; w < n_items; w += n_clusters, ++it) {
-                const uint32_t c = w / n_mgroups;
-                const uint32_t b_row0 = c * p.rows_per_chunk;
-                const uint32_t b_rows = min(p.rows_per_chunk, p.nB - b_row0);
-                const uint32_t n_tiles = (b_rows + kTcTileN - 1) / kTcTileN;
-                mbar_wait(bar_a_full, it & 1u);
+            uint32_t stage = 0, ph = 0, acc_it = 0, a_loaded = 0xFFFFFFFFu, a_loads = 0;
+            for (uint32_t w = w_begin; w < w_end; w += w_step) {
+                const TcWork k = tc_work<CL>(p, w, n_mgroups, crank);
+                const uint32_t n_tiles = (k.b_rows + kTcTileN - 1) / kTcTileN;
+                if (k.a_tile != a_loaded) {
+                    if (a_loads > 0) tc_commit(bar_a_empty);           // arrives when every MMA on the old tile is done
+                    mbar_wait(bar_a_full, a_loads & 1u);
+                    a_loaded = k.a_tile;
+                    ++a_loads;
+                }
                 for (uint32_t t = 0; t < n_tiles; ++t, ++acc_it) {
                     const uint32_t buf = acc_it & 1u;
                     mbar_wait(bar_acc_empty + 8 * buf, ((acc_it >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
@@ -287,7 +333,6 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
                     }
                     tc_commit(bar_acc_full + 8 * buf);
                 }
-                tc_commit(bar_a_empty);
             }
         }
         __syncwarp();
@@ -300,10 +345,9 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
         const uint32_t grp = (warp - 2u) >> 2;                   // accumulator buffer this warp drains
         const uint32_t row = quarter * 32u + lane;               // searcher row within the tile
         uint32_t acc_base = 0, uses = 0, it = 0;                 // tiles before this item; uses of this group's buffer
-        for (uint32_t w = cluster_id; w < n_items; w += n_clusters, ++it) {
-            const uint32_t mt = (w % n_mgroups) * CL + crank, c = w / n_mgroups;
-            const uint32_t b_row0 = c * p.rows_per_chunk;
-            const uint32_t b_rows = min(p.rows_per_chunk, p.nB - b_row0);
+        for (uint32_t w = w_begin; w < w_end; w += w_step, ++it) {
+            const TcWork k = tc_work<CL>(p, w, n_mgroups, crank);
+            const uint32_t b_rows = k.b_rows;
             const uint32_t n_tiles = (b_rows + kTcTileN - 1) / kTcTileN;
             uint32_t best0 = kKeyNone, best1 = kKeyNone;
             int32_t thr = kThrNone;
@@ -315,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
                 int32_t va[64], vb[64];
                 HULO_LDTM64(va, taddr);
                 HULO_WAIT_LD64(va);
-                const bool dump = p.dbg_dots != nullptr && w == 0 && t == 0 && crank == 0;
+                const bool dump = p.dbg_dots != nullptr && w == 0 && t == 0 && crank == 0 && p.items == nullptr;
                 if (dump) _Pragma("unroll") for (int e = 0; e < 64; ++e) p.dbg_dots[row * 256 + e] = va[e];
                 HULO_LDTM64(vb, taddr + 64u);
                 if (n_valid < 64u) {
@@ -360,8 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
                 const uint2 o = *slot;
                 const uint32_t lo = min(best0, o.x), mid = max(best0, o.x);
                 const uint32_t second = min(mid, min(best1, o.y));
-                const uint32_t a_row = mt * kTcTileRows + row;
-                if (a_row < p.nA) p.partial[(uint64_t)c * p.slot_stride + a_row] = make_uint2(lo, second);
+                if (row < k.a_rows) p.partial[k.out_slot0 + row] = make_uint2(lo, second);
             }
         }
     }
@@ -375,35 +418,45 @@ __global__ void __launch_bounds__(kThreads, 1) knn2_tc_kernel(const TcParams p) 
 }
 
 // ------------------------------------------------------------------ tile image
+// The 16 bytes of the image holding bits [16 j, 16 j + 16) of a folded row (j = kbyte / 2).
+__device__ __forceinline__ uint4 expand_piece(const uint32_t *f, uint32_t kbyte) {
+    const uint32_t wi = kbyte >> 2;
+    uint32_t wv = __ldg(f + wi);
+    // undo the K1 fold (knn2.cuh): words 2, 5, 8, 11, 14 hold the XOR of their triple, word 15 of w9..w15
+    if (wi == 15u) wv ^= __ldg(f + 11) ^ __ldg(f + 14);
+    else if (wi % 3u == 2u) wv ^= __ldg(f + wi - 1) ^ __ldg(f + wi - 2);
+    const uint32_t bits = (wv >> ((kbyte & 2u) * 8u)) & 0xFFFFu;
+    uint32_t o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t x = (bits >> (4 * q)) & 15u;
+        const uint32_t ones = (x * 0x00204081u) & 0x01010101u;            // bit b -> byte b
+        o[q] = ones | ((ones ^ 0x01010101u) * 0xFFu);                     // 1 -> +1, 0 -> -1
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 // One thread per 16-byte piece of the image (16 consecutive K positions of one row).
-__global__ void knn2_tc_expand_kernel(const uint32_t *__restrict__ folded, size_t n, uint4 *__restrict__ image,
-                                      size_t n_pieces) {
+// tile_src == nullptr: image row r is table row r (rows past n are zeros); else image tile t holds
+// table rows tile_src[t] .. + tile_rows[t] - 1.
+__global__ void knn2_tc_expand_kernel(const uint32_t *__restrict__ folded, size_t n, const uint32_t *__restrict__ tile_src,
+                                      const uint32_t *__restrict__ tile_rows, uint4 *__restrict__ image, size_t n_pieces) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_pieces) return;
     const size_t tile = idx >> 12;                       // 4096 pieces per tile
     const uint32_t rem = (uint32_t)(idx & 4095u);
     const uint32_t kc = rem >> 10, g = (rem >> 6) & 15u, cm = (rem >> 3) & 7u, i = rem & 7u;
-    const size_t r = tile * kTcTileRows + g * 8u + i;
-    uint4 out = make_uint4(0u, 0u, 0u, 0u);
-    if (r < n) {
-        const uint32_t kbyte = kc * 16u + cm * 2u;       // byte of the 64-byte row holding these 16 bits
-        const uint32_t wi = kbyte >> 2;
-        const uint32_t *f = folded + r * 16;
-        uint32_t wv = __ldg(f + wi);
-        // undo the K1 fold (knn2.cuh): words 2, 5, 8, 11, 14 hold the XOR of their triple, word 15 of w9..w15
-        if (wi == 15u) wv ^= __ldg(f + 11) ^ __ldg(f + 14);
-        else if (wi % 3u == 2u) wv ^= __ldg(f + wi - 1) ^ __ldg(f + wi - 2);
-        const uint32_t bits = (wv >> ((kbyte & 2u) * 8u)) & 0xFFFFu;
-        uint32_t o[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t x = (bits >> (4 * q)) & 15u;
-            const uint32_t ones = (x * 0x00204081u) & 0x01010101u;            // bit b -> byte b
-            o[q] = ones | ((ones ^ 0x01010101u) * 0xFFu);                     // 1 -> +1, 0 -> -1
-        }
-        out = make_uint4(o[0], o[1], o[2], o[3]);
+    const uint32_t rt = g * 8u + i;                      // row within the tile
+    size_t r;
+    bool valid;
+    if (tile_src != nullptr) {
+        valid = rt < __ldg(tile_rows + tile);
+        r = (size_t)__ldg(tile_src + tile) + rt;
+    } else {
+        r = tile * kTcTileRows + rt;
+        valid = r < n;
     }
-    image[idx] = out;
+    image[idx] = valid ? expand_piece(folded + r * 16, kc * 16u + cm * 2u) : make_uint4(0u, 0u, 0u, 0u);
 }
 
 }  // namespace
@@ -412,7 +465,17 @@ cudaError_t knn2_tc_expand_launch(const uint4 *folded_rows, size_t n, uint8_t *i
     const size_t n_pieces = knn2_tc_image_bytes(n) / 16;
     const int threads = 256;
     knn2_tc_expand_kernel<<<(unsigned)((n_pieces + threads - 1) / threads), threads, 0, stream>>>(
-        reinterpret_cast<const uint32_t *>(folded_rows), n, reinterpret_cast<uint4 *>(image), n_pieces);
+        reinterpret_cast<const uint32_t *>(folded_rows), n, nullptr, nullptr, reinterpret_cast<uint4 *>(image), n_pieces);
+    return cudaGetLastError();
+}
+
+cudaError_t knn2_tc_expand_tiles_launch(const uint4 *folded_rows, const uint32_t *tile_src, const uint32_t *tile_rows,
+                                        size_t n_tiles, uint8_t *image, cudaStream_t stream) {
+    if (n_tiles == 0) return cudaSuccess;
+    const size_t n_pieces = n_tiles * (kTcTileBytes / 16);
+    const int threads = 256;
+    knn2_tc_expand_kernel<<<(unsigned)((n_pieces + threads - 1) / threads), threads, 0, stream>>>(
+        reinterpret_cast<const uint32_t *>(folded_rows), 0, tile_src, tile_rows, reinterpret_cast<uint4 *>(image), n_pieces);
     return cudaGetLastError();
 }
 
@@ -454,7 +517,7 @@ static cudaError_t launch_cl(const TcParams &p, int grid, cudaStream_t stream) {
         configured_device = dev;
     }
     const uint32_t n_mgroups = (p.n_mtiles + CL - 1) / CL;
-    const uint64_t n_items = (uint64_t)n_mgroups * p.n_chunks;
+    const uint64_t n_items = p.items != nullptr ? p.n_items : (uint64_t)n_mgroups * p.n_chunks;
     if (n_items == 0) return cudaSuccess;
     uint64_t clusters = (uint64_t)grid / CL;
     if (clusters > n_items) clusters = n_items;
@@ -475,6 +538,7 @@ static cudaError_t launch_cl(const TcParams &p, int grid, cudaStream_t stream) {
 }
 
 cudaError_t knn2_tc_launch(const TcParams &p, int grid, cudaStream_t stream) {
+    if (p.items != nullptr) return launch_cl<1>(p, grid, stream);      // item lists are not clustered
     switch (p.cluster) {
         case 1: return launch_cl<1>(p, grid, stream);
         case 2: return launch_cl<2>(p, grid, stream);

@@ -46,9 +46,29 @@ inline size_t knn2_tc_image_bytes(size_t n) {
 // tiles are written as zeros.
 cudaError_t knn2_tc_expand_launch(const uint4 *folded_rows, size_t n, uint8_t *image, cudaStream_t stream);
 
+// The same for a table cut into segments (views, images, query images), every segment starting on
+// an even tile so that it can serve as searcher (128-row tiles) and as database (256-row tiles):
+// image tile t holds rows tile_src[t] .. tile_src[t] + tile_rows[t] - 1 of the table, zeros after
+// (tile_rows[t] = 0: a padding tile).  Both tables are device pointers of n_tiles entries.
+cudaError_t knn2_tc_expand_tiles_launch(const uint4 *folded_rows, const uint32_t *tile_src, const uint32_t *tile_rows,
+                                        size_t n_tiles, uint8_t *image, cudaStream_t stream);
+
+// One unit of work of the item mode (32 bytes): searcher tile `a_tile` of image A against
+// `b_rows` database rows starting at tile `b_tile0` (even) of image B.
+struct alignas(16) TcItem {
+    uint32_t a_tile;
+    uint32_t a_rows;     // rows of the tile whose keys are written (<= 128)
+    uint32_t b_tile0;
+    uint32_t b_rows;     // <= kMaxChunkRows
+    uint64_t out_slot0;  // partial[out_slot0 + r] receives the keys of searcher row r of the tile
+    uint64_t pad;
+};
+
 struct TcParams {
     const uint8_t *imgA;      // searcher tile image
     const uint8_t *imgB;      // database tile image
+    const TcItem *items = nullptr;   // item mode when set (device pointer), else the flat fields below
+    uint32_t n_items = 0;
     uint32_t nA, nB;
     uint32_t n_mtiles;        // ceil(nA / 128)
     uint32_t n_chunks;

@@ -10,6 +10,15 @@ from sfmlocalization_b200.gpu import LocalizeEngine
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["int", "tc"])
+def engine(request, gpu):
+    """Every test of this module runs with the 2-NN arithmetic on the integer pipes (K1) and on the
+    tensor cores (K1t, item mode): same bit-exact expectations."""
+    gpu.set_knn_engine(request.param)
+    yield request.param
+    gpu.set_knn_engine("auto")
+
+
 def oracle_assembly(orc, sc, views, ratio, min_putative):
     off = sc["seg_offsets"]
     m_view, m_i, m_j, m_d = [], [], [], []

@@ -147,3 +147,24 @@ def test_large_pair_uses_the_big_shared_memory_buffer(gpu, orc):
     specs = [(9000, 0.5), (40, 0.3)]
     exact, r = compare(gpu, orc, specs, 4.0, 200, 13, seed0=900)
     assert r["valid"][0] and r["n_inliers"][0] > 3000 and exact >= 1
+
+
+def test_inliers_agree_with_opencv_anchor(gpu):
+    """Independent anchor (tests/golden/make_golden_anchors.py): the inlier sets of the device F-matrix
+    AC-RANSAC against cv2.findFundamentalMat(FM_RANSAC)'s at the threshold the fp64 restatement
+    estimated, and against the planted truth."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    a = dict(np.load(os.path.join(root, "tests", "golden", "anchors_golden.npz")))
+    w, h = synth.IMAGE_WH
+    for k, (N, outl, seed) in enumerate(a["fmat_cases"]):
+        sc = synth.two_view_matches(int(N), int(seed), outlier_frac=float(outl))
+        r = gpu.geometric_filter(sc["xI"], sc["xJ"], np.array([0, int(N)], np.uint64),
+                                 np.array([[w, h, w, h]], np.int32), 16.0, 1024, 1)
+        assert r["valid"][0]
+        mine = np.zeros(int(N), bool); mine[r["inliers"][0]] = True
+        cv = a["fmat_%d_cv2_inliers" % k]
+        assert abs(r["error_max"][0] - float(a["fmat_%d_threshold_px" % k])) < 0.75
+        assert (cv & mine).sum() / cv.sum() >= 0.93
+        assert (cv & mine).sum() / (cv | mine).sum() >= 0.85
+        assert (mine & sc["inlier_mask"]).sum() / sc["inlier_mask"].sum() >= 0.90

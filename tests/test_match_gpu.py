@@ -8,6 +8,15 @@ from sfmlocalization_b200 import _lib, synth
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["int", "tc"])
+def engine(request, gpu):
+    """Every test of this module runs with the 2-NN arithmetic on the integer pipes (K1) and on the
+    tensor cores (K1t, item mode): same bit-exact expectations."""
+    gpu.set_knn_engine(request.param)
+    yield request.param
+    gpu.set_knn_engine("auto")
+
+
 def oracle_query(orc, rows, off, views, query, ratio):
     out = dict(view=[], i=[], j=[], d0=[], counts=[])
     for pos, v in enumerate(views):

@@ -227,3 +227,25 @@ def test_batch_resection_recovers_the_poses(gpu):
         M /= np.cbrt(np.linalg.det(M[:, :3]))
         C = -M[:, :3].T @ M[:, 3]
         assert np.linalg.norm(C - (-sc["R"].T @ sc["t"])) < 0.05, p
+
+
+@pytest.mark.parametrize("sequential", [False, True])
+def test_acransac_inliers_agree_with_opencv_anchor(gpu, sequential):
+    """Independent anchor (tests/golden/make_golden_anchors.py): the final inlier sets of the device
+    AC-RANSAC against cv2.solvePnPRansac(P3P)'s at the threshold the fp64 restatement estimated, and
+    against the planted truth.  OpenCV keeps an unrefined minimal model of its own sampling, so its
+    set is a little smaller and nearly contained in ours."""
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    a = dict(np.load(os.path.join(root, "tests", "golden", "anchors_golden.npz")))
+    for k, (N, outl, seed) in enumerate(a["resect_cases"]):
+        sc = synth.resection_scene(int(N), int(seed), outlier_frac=float(outl))
+        r = gpu.resect_acransac(sc["x2d"], sc["X3d"], sc["K"], max_iter=4096, seed=1, sequential=sequential)
+        assert r["found"]
+        mine = np.zeros(int(N), bool); mine[r["inliers"]] = True
+        cv = a["resect_%d_cv2_inliers" % k]
+        # the threshold is estimated, not given: it must land near the restatement's
+        assert abs(r["error_max"] - float(a["resect_%d_threshold_px" % k])) < 0.5
+        assert (cv & mine).sum() / cv.sum() >= 0.95
+        assert (cv & mine).sum() / (cv | mine).sum() >= 0.88
+        assert (sc["inlier_mask"] & mine).sum() / (sc["inlier_mask"] | mine).sum() >= 0.95

@@ -303,6 +303,18 @@ void hulo_engine_destroy(hulo_engine *e);
 int hulo_engine_configure(hulo_engine *e, float ratio, int min_putative, int min_points, int min_inliers,
                           size_t max_iter);
 
+/* Schedule of the AC-RANSAC resection behind hulo_engine_localize (SfM_Localizer::Localize,
+ * LocalizeEngine.cc:529-532):
+ *   HULO_RESECT_BATCHED     (default) growing batches of iterations scored together, the model with the
+ *                           smallest NFA of a batch committed; statistically equivalent, fewest round trips;
+ *   HULO_RESECT_SEQUENTIAL  the reference's own schedule kept to the letter: every iteration is committed
+ *                           in order with the strict-improvement rule, the sampling pool narrows at the
+ *                           iteration it would narrow in OpenMVG's loop (hulo_resect_acransac_sequential).
+ * The batched localisation (hulo_engine_localize_batch) always uses the batched schedule. */
+#define HULO_RESECT_BATCHED 0
+#define HULO_RESECT_SEQUENTIAL 1
+int hulo_engine_set_resection_schedule(hulo_engine *e, int schedule);
+
 /* Keypoint positions for the geometric filter (the Regions_Provider of LocalizeEngine.cc:458):
  * map_xy holds 2 doubles per descriptor row of the map (same row order), view_wh the image
  * size {w, h} of every view (View::ui_width / ui_height), query_w / query_h that of the

@@ -75,6 +75,7 @@ SIGNATURES = {
     "hulo_engine_create": (C.c_int, [_vp, _vp, _sz, _sz, _vp, _sz, _vp, _vp, _vp, _sz, _vp, _sz, _vp, _pp]),
     "hulo_engine_destroy": (None, [_vp]),
     "hulo_engine_configure": (C.c_int, [_vp, _f32, C.c_int, C.c_int, C.c_int, _sz]),
+    "hulo_engine_set_resection_schedule": (C.c_int, [_vp, C.c_int]),
     "hulo_engine_set_keypoints": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
     "hulo_engine_set_query_size": (C.c_int, [_vp, C.c_int, C.c_int]),
     "hulo_engine_configure_geometric": (C.c_int, [_vp, C.c_int, _sz, _f64]),

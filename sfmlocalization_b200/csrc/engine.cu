@@ -27,6 +27,7 @@ struct hulo_engine {
     float ratio = 0.6f;        // secondTestRatio, localizeImage.cc:46-59
     int min_putative = 16, min_points = 8, min_inliers = 10;
     size_t max_iter = 4096;
+    int resect_schedule = HULO_RESECT_BATCHED;
     // geometric filter (hulo::geometricMatch, LocalizeEngine.cc:458): keypoint positions of the map
     // features (row order of the descriptor table), image size per view and of the query camera
     std::vector<double> map_xy;
@@ -195,6 +196,13 @@ int hulo_engine_configure(hulo_engine *e, float ratio, int min_putative, int min
     e->min_points = min_points;
     e->min_inliers = min_inliers;
     e->max_iter = max_iter;
+    return HULO_OK;
+}
+
+int hulo_engine_set_resection_schedule(hulo_engine *e, int schedule) {
+    HULO_ARG(e != nullptr, "null engine");
+    HULO_ARG(schedule == HULO_RESECT_BATCHED || schedule == HULO_RESECT_SEQUENTIAL, "unknown schedule");
+    e->resect_schedule = schedule;
     return HULO_OK;
 }
 
@@ -443,8 +451,9 @@ static int assemble_and_resect(hulo_engine *e, size_t nq, const double *qxy, con
         size_t n_inl = 0;
         double err_max = 0.0;
         int found = 0;
-        int rc = hulo_resect_acransac(e->h, e->x2d.data(), e->X3d.data(), N, e->K, e->max_iter, seed, P, e->inl.data(),
-                                      &n_inl, &err_max, &found);
+        auto resect = e->resect_schedule == HULO_RESECT_SEQUENTIAL ? hulo_resect_acransac_sequential : hulo_resect_acransac;
+        int rc = resect(e->h, e->x2d.data(), e->X3d.data(), N, e->K, e->max_iter, seed, P, e->inl.data(), &n_inl, &err_max,
+                        &found);
         if (rc != HULO_OK) return rc;
         if (inliers) memcpy(inliers, e->inl.data(), n_inl * sizeof(int32_t));
         if (n_inliers) *n_inliers = n_inl;

@@ -454,6 +454,10 @@ class LocalizeEngine:
         check(self.lib.hulo_engine_set_keypoints(self.h, _ptr(map_xy), _ptr(view_wh), int(query_wh[0]),
                                                  int(query_wh[1])))
 
+    def set_resection_schedule(self, schedule):
+        """'batched' (default) or 'sequential' (the reference's AC-RANSAC loop kept to the letter)."""
+        check(self.lib.hulo_engine_set_resection_schedule(self.h, {"batched": 0, "sequential": 1}[schedule]))
+
     def configure_geometric(self, enabled, ransac_round=25, precision_px=4.0):
         check(self.lib.hulo_engine_configure_geometric(self.h, int(bool(enabled)), ransac_round, precision_px))
 

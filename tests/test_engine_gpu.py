@@ -260,3 +260,29 @@ def test_localize_with_guided_matching(gpu, orc, seed):
     assert set(r["corr_qfeat"].tolist()) <= set(plain["corr_qfeat"].tolist()) | set(unguided["corr_qfeat"].tolist())
     truth = sc["q_truth"][r["corr_qfeat"]]
     assert (truth == r["corr_landmark"]).mean() > 0.97
+
+
+def test_engine_sequential_schedule_is_the_letter_exact_driver(gpu, orc):
+    """hulo_engine_set_resection_schedule(SEQUENTIAL): the engine's pose and inlier list are those of
+    hulo_resect_acransac_sequential (the reference's AC-RANSAC loop kept to the letter, trace-checked
+    against the oracle in test_resect_gpu.py) on the correspondences it assembled."""
+    sc = synth.localization_scene(24, 800, 4000, 900, 4)
+    eng = LocalizeEngine(gpu, sc["rows"], sc["seg_offsets"], sc["obs_view"], sc["obs_feat"], sc["obs_landmark"],
+                         sc["landmark_X"], sc["K"], ratio=0.6)
+    try:
+        eng.set_resection_schedule("sequential")
+        r = eng.localize(sc["q_desc"], sc["q_xy"], seed=9)
+        eng.set_resection_schedule("batched")
+        rb = eng.localize(sc["q_desc"], sc["q_xy"], seed=9)
+    finally:
+        eng.close()
+    x2d = sc["q_xy"][r["corr_qfeat"]]; X3d = sc["landmark_X"][r["corr_landmark"]]
+    want = gpu.resect_acransac(x2d, X3d, sc["K"], max_iter=4096, seed=9, sequential=True)
+    assert r["localized"] and want["found"]
+    assert r["inliers"].tolist() == want["inliers"].tolist()
+    _, R, c = gpu.pose_from_projection(want["P"])
+    assert np.abs(r["R"] - R).max() < 1e-12 and np.abs(r["center"] - c).max() < 1e-12
+    # and the default schedule lands on the same pose statistically
+    assert rb["localized"] and np.linalg.norm(rb["center"] - r["center"]) < 0.02
+    o = orc.acransac(x2d, X3d, sc["K"], max_iter=4096, seed=9)
+    assert o["ok"] and abs(len(o["inliers"]) - len(r["inliers"])) <= max(5, len(o["inliers"]) // 20)

@@ -333,6 +333,8 @@ int hulo_device_count(void) {
 const char *hulo_last_error(void) { return g_error.c_str(); }
 const char *hulo_version(void) { return "sfmlocalization_b200 0.1 (sm_100a)"; }
 
+void hulo_gpu_destroy(hulo_gpu *h);
+
 int hulo_gpu_create(int device, hulo_gpu **out) {
     HULO_ARG(out != nullptr, "out is null");
     *out = nullptr;
@@ -350,7 +352,17 @@ int hulo_gpu_create(int device, hulo_gpu **out) {
     HULO_ARG(h != nullptr, "out of host memory");
     h->device = device;
     cudaDeviceProp prop;
-    HULO_CUDA(cudaGetDeviceProperties(&prop, device));
+    // from here on a failure releases what exists already (hulo_gpu_destroy copes with a half-built context)
+#define HULO_CREATE_CUDA(expr)                                                                                    \
+    do {                                                                                                          \
+        cudaError_t e__ = (expr);                                                                                 \
+        if (e__ != cudaSuccess) {                                                                                 \
+            hulo_gpu_destroy(h);                                                                                  \
+            hulo::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__));               \
+            return HULO_ERR_CUDA;                                                                                 \
+        }                                                                                                         \
+    } while (0)
+    HULO_CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) {
         set_error("hulo_gpu_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
                   prop.major, prop.minor);
@@ -358,9 +370,10 @@ int hulo_gpu_create(int device, hulo_gpu **out) {
         return HULO_ERR_CUDA;
     }
     h->sm_count = prop.multiProcessorCount;
-    HULO_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    HULO_CUDA(cudaEventCreate(&h->ev_start));
-    HULO_CUDA(cudaEventCreate(&h->ev_stop));
+    HULO_CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    HULO_CREATE_CUDA(cudaEventCreate(&h->ev_start));
+    HULO_CREATE_CUDA(cudaEventCreate(&h->ev_stop));
+#undef HULO_CREATE_CUDA
     // tuning overrides (benchmark sweeps): HULO_KNN_THREADS / HULO_KNN_QPT / HULO_KNN_CSA
     const int t = env_int("HULO_KNN_THREADS", 0), q = env_int("HULO_KNN_QPT", 0), c = env_int("HULO_KNN_CSA", -1);
     const int o = env_int("HULO_KNN_OPT", -1);

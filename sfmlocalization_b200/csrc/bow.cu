@@ -56,6 +56,8 @@ using namespace hulo;
 
 extern "C" {
 
+void hulo_bow_destroy(hulo_bow *b);
+
 int hulo_bow_create(hulo_gpu *h, const float *bof, size_t n, size_t d, hulo_bow **out) {
     HULO_ARG(h != nullptr && out != nullptr, "null argument");
     *out = nullptr;
@@ -77,12 +79,18 @@ int hulo_bow_create(hulo_gpu *h, const float *bof, size_t n, size_t d, hulo_bow 
         return HULO_ERR_CUDA;
     }
     if (n) {
-        HULO_CUDA(cudaMemsetAsync(b->rows, 0, n * b->d_pad * sizeof(float), h->stream));
-        HULO_CUDA(cudaMemcpy2DAsync(b->rows, b->d_pad * sizeof(float), bof, d * sizeof(float), d * sizeof(float), n,
-                                    cudaMemcpyHostToDevice, h->stream));
+        e = cudaMemsetAsync(b->rows, 0, n * b->d_pad * sizeof(float), h->stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpy2DAsync(b->rows, b->d_pad * sizeof(float), bof, d * sizeof(float), d * sizeof(float), n,
+                                  cudaMemcpyHostToDevice, h->stream);
     }
-    HULO_CUDA(cudaMemsetAsync(b->query, 0, b->d_pad * sizeof(float), h->stream));
-    HULO_CUDA(cudaStreamSynchronize(h->stream));
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->query, 0, b->d_pad * sizeof(float), h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+        set_error("hulo_bow_create: upload -> %s", cudaGetErrorString(e));
+        hulo_bow_destroy(b);
+        return HULO_ERR_CUDA;
+    }
     *out = b;
     return HULO_OK;
 }

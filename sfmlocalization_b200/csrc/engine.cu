@@ -148,6 +148,7 @@ int hulo_engine_create(hulo_gpu *h, const uint8_t *rows, size_t n, size_t stride
     HULO_ARG(seg_offsets != nullptr && n_views >= 1, "the map needs a view table");
     HULO_ARG(n_obs == 0 || (obs_view && obs_feat && obs_landmark), "null observation table");
     HULO_ARG(n_landmarks == 0 || landmark_X != nullptr, "null landmark positions");
+    HULO_ARG(n_landmarks < (size_t)INT32_MAX, "more than 2^31 - 1 landmarks (ids are int32 on the device)");
     for (size_t k = 0; k < n_obs; ++k) {
         HULO_ARG(obs_view[k] < n_views, "observation refers to a view that does not exist");
         HULO_ARG(obs_landmark[k] < n_landmarks, "observation refers to a landmark that does not exist");

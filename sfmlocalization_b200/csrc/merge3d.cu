@@ -311,9 +311,18 @@ int hulo_ransac_transform3d(hulo_gpu *h, const double *A, const double *B, size_
     uint32_t best = 0;
     long best_r = -1;
     double Mb[12] = {0}, Mr[12];
+    // the models come over in one copy the first time one is needed (an ill-conditioned leader would
+    // otherwise cost one blocking 96-byte copy per round that beats the running count)
+    std::vector<double> all_models;
     for (size_t r = 0; r < rounds; ++r) {
         if (counts[r] <= best) continue;
-        HULO_CUDA(cudaMemcpy(Mr, h->scratch1.as<double>() + 12 * r, sizeof Mr, cudaMemcpyDeviceToHost));
+        if (all_models.empty()) {
+            all_models.resize(12 * rounds);
+            HULO_CUDA(cudaMemcpyAsync(all_models.data(), h->scratch1.ptr, 12 * rounds * sizeof(double), cudaMemcpyDeviceToHost,
+                                      h->stream));
+            HULO_CUDA(cudaStreamSynchronize(h->stream));
+        }
+        memcpy(Mr, &all_models[12 * r], sizeof Mr);
         if (!(Mr[0] == Mr[0])) continue;
         double s[3];
         singular_values3(Mr, s);

@@ -22,6 +22,16 @@ KEEP = [
     "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.per_cycle_active",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__thread_inst_executed_per_inst_executed.ratio",
     "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    # tensor-core kernels (K1t)
+    "sm__cycles_elapsed.avg.per_second", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__mem_tensor_reads_op_ldt.sum.pct_of_peak_sustained_elapsed",
+    "smsp__mem_tensor_reads_op_utcmma_matrix_c.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__m_xbar2l1tex_read_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum.per_second",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "launch__cluster_size",
+    "launch__shared_mem_per_block_dynamic",
 ]
 
 

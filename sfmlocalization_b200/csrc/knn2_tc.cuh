@@ -91,4 +91,13 @@ cudaError_t knn2_tc_launch(const TcParams &p, int grid, cudaStream_t stream);
 // Chunk size for a K1t run (multiple of 256 rows).
 void knn2_tc_plan(size_t nA, size_t nB, int n_ctas, uint32_t *n_mtiles, uint32_t *n_chunks, uint32_t *rows_per_chunk);
 
+
+// ---- K1t4 (knn2_tc4.cu): the flat search with 4-bit operands (kind::mxf4, block scales 1.0, fp32
+// accumulation -- exact for these integers).  Its own image format (256 bytes per row); TcParams as
+// for the flat mode of K1t with rows_per_chunk a multiple of 224.
+size_t knn2_tc4_image_bytes(size_t n);
+cudaError_t knn2_tc4_expand_launch(const uint4 *folded_rows, size_t n, uint8_t *image, cudaStream_t stream);
+void knn2_tc4_plan(size_t nA, size_t nB, int n_ctas, uint32_t *n_mtiles, uint32_t *n_chunks, uint32_t *rows_per_chunk);
+cudaError_t knn2_tc4_launch(const TcParams &p, int grid, cudaStream_t stream);
+
 }  // namespace hulo

@@ -1,0 +1,408 @@
+// knn2_tc4.cu -- K1t4: the flat Hamming 2-NN of K1t (knn2_tc.cu) with 4-bit operands:
+// tcgen05.mma.kind::mxf4.block_scale, every bit b of a row as the e2m1 value 2b - 1 (+1.0 = 0x2,
+// -1.0 = 0xA), all block scales 1.0 (ue8m0 0x7F), fp32 accumulation.  dot = 512 - 2 * hamming is an
+// integer of magnitude <= 512, far below 2^24, so the fp32 accumulator holds it exactly and the
+// (distance, index) keys are those of K1 / K1t bit for bit.  Half the operand bytes and half the
+// tensor-pipe cycles per distance of the int8 form.
+//
+// Image layout (its own: rows are 256 bytes here): groups of 8 rows, 2 KB each --
+//   offset(row r, byte k of 256) = (r / 8) * 2048 + (k / 16) * 128 + (r % 8) * 16 + k % 16
+// so any range of whole groups is contiguous: the searcher tile (128 rows, 32 KB) and a database
+// tile (224 rows, 56 KB, the whole K of it: one ring stage) are one bulk copy each.
+// TMEM: accumulators at columns 0 and 256 (224 used of each), scale factors at column 480.
+#include "knn2_tc.cuh"
+
+#include <algorithm>
+
+namespace hulo {
+
+namespace {
+
+constexpr uint32_t kN4 = 224;                     // database rows per accumulator tile
+constexpr uint32_t kRowBytes4 = 256;
+constexpr uint32_t kGroupBytes4 = 8 * kRowBytes4; // 2048
+constexpr uint32_t kABytes4 = 128 * kRowBytes4;   // 32768
+constexpr uint32_t kStageBytes4 = kN4 * kRowBytes4;   // 57344
+constexpr int kStages4 = 3;
+constexpr uint32_t kThreads4 = 320;
+constexpr uint32_t kTmemCols4 = 512;
+constexpr uint32_t kSfCol = 480;
+constexpr size_t kSmemBytes4 = 1024 + kABytes4 + (size_t)kStages4 * kStageBytes4 + 256 + 2 * 128 * sizeof(uint2);
+
+constexpr float kThrNoneF = -1024.0f;
+constexpr float kDotMaskedF = -2048.0f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+        "l"(src_gmem), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, e2m1 x e2m1 with one ue8m0 scale per 32 elements -> fp32; M = 128, K = 64
+__device__ __forceinline__ void tc_mma_mxf4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// cute::UMMA::InstrDescriptorBlockScaled: A = B = e2m1 (MXF4Format 1), K-major, N, ue8m0 scales, M = 128, K = 64
+constexpr uint32_t kIdesc4 = (1u << 7) | (1u << 10) | ((kN4 >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
+
+#define HULO_LDTM32(v, taddr)                                                                                       \
+    asm volatile(                                                                                                   \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                   \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                  \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                   \
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),          \
+          "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]),    \
+          "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]),  \
+          "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])   \
+        : "r"(taddr)                                                                                                \
+        : "memory")
+#define HULO_WAIT_LD32(v)                                                                                            \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                    \
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),    \
+                   "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), \
+                   "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]), "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), \
+                   "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31]) \
+                 :                                                                                                    \
+                 : "memory")
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// 32 accumulator columns of this thread's searcher row (see scan_block in knn2_tc.cu)
+__device__ __forceinline__ void scan32(const float (&v)[32], uint32_t row0, uint32_t n_valid, uint32_t &best0,
+                                       uint32_t &best1, float &thr) {
+    float gm[2];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const float *w = &v[16 * g];
+        const float m0 = fmax3(w[0], w[1], w[2]), m1 = fmax3(w[3], w[4], w[5]), m2 = fmax3(w[6], w[7], w[8]);
+        const float m3 = fmax3(w[9], w[10], w[11]), m4 = fmax3(w[12], w[13], w[14]);
+        gm[g] = fmaxf(fmax3(m0, m1, m2), fmax3(m3, m4, w[15]));
+    }
+    if (fmaxf(gm[0], gm[1]) <= thr) return;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const float *w = &v[16 * g];
+        if (gm[g] > thr) {
+            const float t0 = thr;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                // columns past the end of the chunk hold whatever the padding rows gave
+                if (w[e] > t0 && (uint32_t)(16 * g + e) < n_valid) {
+                    const uint32_t key = ((uint32_t)(512 - __float2int_rn(w[e])) << (kKeyIdxBits - 1)) + (row0 + 16 * g + e);
+                    const uint32_t hi = max(best0, key);
+                    best0 = min(best0, key);
+                    best1 = min(best1, hi);
+                }
+            }
+            thr = best1 == kKeyNone ? kThrNoneF : (float)(512 - 2 * (int32_t)(best1 >> kKeyIdxBits));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA = smem_base;
+    const uint32_t sB = smem_base + kABytes4;
+    const uint32_t bars = sB + kStages4 * kStageBytes4;
+    const uint32_t bar_a_full = bars, bar_a_empty = bars + 8;
+    const uint32_t bar_b_full = bars + 16, bar_b_empty = bar_b_full + 8 * kStages4;
+    const uint32_t bar_acc_full = bar_b_empty + 8 * kStages4, bar_acc_empty = bar_acc_full + 16;
+    const uint32_t tmem_slot = bar_acc_empty + 16;
+    const uint32_t xchg = bars + 256;
+    uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t *tmem_slot_gen = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+    uint2 *xchg_gen = reinterpret_cast<uint2 *>(smem_gen + (xchg - smem_base));
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a_full, 1);
+        mbar_init(bar_a_empty, 1);
+        for (int s = 0; s < kStages4; ++s) {
+            mbar_init(bar_b_full + 8 * s, 1);
+            mbar_init(bar_b_empty + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_acc_full + 8 * b, 1);
+            mbar_init(bar_acc_empty + 8 * b, 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(kTmemCols4)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_gen;
+
+    // scale factors: every byte of columns 480..511 on all 128 lanes = 0x7F (ue8m0 1.0), whatever
+    // layout the instruction reads them in
+    if (warp >= 2 && warp < 6) {
+        const uint32_t taddr = tmem_base + (((warp & 3u) * 32u) << 16) + kSfCol;
+        const uint32_t one = 0x7F7F7F7Fu;
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+            "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+            "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(taddr),
+            "r"(one)
+            : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const uint32_t n_items = p.n_mtiles * p.n_chunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t stage = 0, ph = 0, a_loaded = 0xFFFFFFFFu, a_loads = 0;
+            for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+                const uint32_t mt = w % p.n_mtiles, c = w / p.n_mtiles;
+                const uint32_t b_row0 = c * p.rows_per_chunk;
+                const uint32_t b_rows = min(p.rows_per_chunk, p.nB - b_row0);
+                const uint32_t n_tiles = (b_rows + kN4 - 1) / kN4;
+                if (mt != a_loaded) {
+                    if (a_loads > 0) mbar_wait(bar_a_empty, (a_loads - 1u) & 1u);
+                    mbar_expect_tx(bar_a_full, kABytes4);
+                    bulk_load(sA, p.imgA + (size_t)mt * kABytes4, kABytes4, bar_a_full);
+                    a_loaded = mt;
+                    ++a_loads;
+                }
+                const uint8_t *src = p.imgB + (size_t)(b_row0 / 8u) * kGroupBytes4;
+                for (uint32_t t = 0; t < n_tiles; ++t) {
+                    mbar_wait(bar_b_empty + 8 * stage, ph ^ 1u);
+                    mbar_expect_tx(bar_b_full + 8 * stage, kStageBytes4);
+                    bulk_load(sB + stage * kStageBytes4, src + (size_t)t * kStageBytes4, kStageBytes4, bar_b_full + 8 * stage);
+                    if (++stage == kStages4) { stage = 0; ph ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t stage = 0, ph = 0, acc_it = 0, a_loaded = 0xFFFFFFFFu, a_loads = 0;
+            const uint32_t tsf = tmem_base + kSfCol;
+            for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+                const uint32_t mt = w % p.n_mtiles, c = w / p.n_mtiles;
+                const uint32_t b_row0 = c * p.rows_per_chunk;
+                const uint32_t b_rows = min(p.rows_per_chunk, p.nB - b_row0);
+                const uint32_t n_tiles = (b_rows + kN4 - 1) / kN4;
+                if (mt != a_loaded) {
+                    if (a_loads > 0) tc_commit(bar_a_empty);
+                    mbar_wait(bar_a_full, a_loads & 1u);
+                    a_loaded = mt;
+                    ++a_loads;
+                }
+                for (uint32_t t = 0; t < n_tiles; ++t, ++acc_it) {
+                    const uint32_t buf = acc_it & 1u;
+                    mbar_wait(bar_acc_empty + 8 * buf, ((acc_it >> 1) & 1u) ^ 1u);
+                    mbar_wait(bar_b_full + 8 * stage, ph);
+                    tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + buf * 256u;
+#pragma unroll
+                    for (uint32_t j = 0; j < 8; ++j) {
+                        const uint64_t da = smem_desc(sA + j * 256u, 128u, kGroupBytes4);
+                        const uint64_t db = smem_desc(sB + stage * kStageBytes4 + j * 256u, 128u, kGroupBytes4);
+                        tc_mma_mxf4(tmem_d, da, db, kIdesc4, tsf, tsf, j != 0u);
+                    }
+                    tc_commit(bar_b_empty + 8 * stage);
+                    tc_commit(bar_acc_full + 8 * buf);
+                    if (++stage == kStages4) { stage = 0; ph ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        const uint32_t quarter = warp & 3u;
+        const uint32_t grp = (warp - 2u) >> 2;
+        const uint32_t row = quarter * 32u + lane;
+        uint32_t acc_base = 0, uses = 0, it = 0;
+        for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
+            const uint32_t mt = w % p.n_mtiles, c = w / p.n_mtiles;
+            const uint32_t b_row0 = c * p.rows_per_chunk;
+            const uint32_t b_rows = min(p.rows_per_chunk, p.nB - b_row0);
+            const uint32_t n_tiles = (b_rows + kN4 - 1) / kN4;
+            uint32_t best0 = kKeyNone, best1 = kKeyNone;
+            float thr = kThrNoneF;
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + grp * 256u;
+            for (uint32_t t = (acc_base + grp) & 1u; t < n_tiles; t += 2, ++uses) {
+                mbar_wait(bar_acc_full + 8 * grp, uses & 1u);
+                tc_fence_after();
+                const uint32_t n_valid = min(kN4, b_rows - t * kN4);
+                const bool dump = p.dbg_dots != nullptr && w == 0 && t == 0;
+                float va[32], vb[32];
+                HULO_LDTM32(va, taddr);
+#pragma unroll
+                for (int blk = 0; blk < 7; ++blk) {          // 7 x 32 = 224 columns, two register sets in turn
+                    if (blk % 2 == 0) {
+                        HULO_WAIT_LD32(va);
+                        if (blk + 1 < 7) HULO_LDTM32(vb, taddr + 32u * (blk + 1));
+                        if (dump) _Pragma("unroll") for (int e = 0; e < 32; ++e) p.dbg_dots[row * 256 + 32 * blk + e] = (int32_t)va[e];
+                        if (blk == 6) {
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_acc_empty + 8 * grp);
+                        }
+                        const uint32_t nv = n_valid > 32u * blk ? n_valid - 32u * blk : 0u;
+                        scan32(va, t * kN4 + 32u * blk, nv, best0, best1, thr);
+                    } else {
+                        HULO_WAIT_LD32(vb);
+                        if (blk + 1 < 7) HULO_LDTM32(va, taddr + 32u * (blk + 1));
+                        if (dump) _Pragma("unroll") for (int e = 0; e < 32; ++e) p.dbg_dots[row * 256 + 32 * blk + e] = (int32_t)vb[e];
+                        const uint32_t nv = n_valid > 32u * blk ? n_valid - 32u * blk : 0u;
+                        scan32(vb, t * kN4 + 32u * blk, nv, best0, best1, thr);
+                    }
+                }
+            }
+            acc_base += n_tiles;
+            uint2 *slot = xchg_gen + (it & 1u) * 128u + row;
+            if (grp == 1u) *slot = make_uint2(best0, best1);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (grp == 0u) {
+                const uint2 o = *slot;
+                const uint32_t lo = min(best0, o.x), mid = max(best0, o.x);
+                const uint32_t second = min(mid, min(best1, o.y));
+                const uint32_t a_row = mt * kTcTileRows + row;
+                if (a_row < p.nA) p.partial[(uint64_t)c * p.slot_stride + a_row] = make_uint2(lo, second);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols4) : "memory");
+    }
+}
+
+// One thread per 16-byte piece of the image = 32 consecutive bits of one row.
+__global__ void knn2_tc4_expand_kernel(const uint32_t *__restrict__ folded, size_t n, uint4 *__restrict__ image,
+                                       size_t n_pieces) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_pieces) return;
+    const size_t group = idx >> 7;                       // 128 pieces per group of 8 rows
+    const uint32_t rem = (uint32_t)(idx & 127u);
+    const uint32_t core = rem >> 3, i = rem & 7u;        // word `core` of the row
+    const size_t r = group * 8 + i;
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);              // padding rows: 0.0 everywhere
+    if (r < n) {
+        const uint32_t *f = folded + r * 16;
+        uint32_t wv = __ldg(f + core);
+        if (core == 15u) wv ^= __ldg(f + 11) ^ __ldg(f + 14);
+        else if (core % 3u == 2u) wv ^= __ldg(f + core - 1) ^ __ldg(f + core - 2);
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t x = (wv >> (8 * q)) & 255u;
+            // bit b of x -> nibble b: 0x2 | (bit << 3)
+            uint32_t sp = (x | (x << 12)) & 0x000F000Fu;          // 4 bits per 16-bit half
+            sp = (sp | (sp << 6)) & 0x03030303u;                  // 2 bits per byte
+            sp = (sp | (sp << 3)) & 0x11111111u;                  // 1 bit per nibble
+            o[q] = 0x22222222u | (sp << 3);
+        }
+        out = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    image[idx] = out;
+}
+
+}  // namespace
+
+size_t knn2_tc4_image_bytes(size_t n) {
+    // whole groups, plus one database tile of slack: the last tile of a chunk is always read in full
+    return ((n + 7) / 8) * (size_t)kGroupBytes4 + kStageBytes4 + kABytes4;
+}
+
+cudaError_t knn2_tc4_expand_launch(const uint4 *folded_rows, size_t n, uint8_t *image, cudaStream_t stream) {
+    const size_t n_pieces = knn2_tc4_image_bytes(n) / 16;
+    const int threads = 256;
+    knn2_tc4_expand_kernel<<<(unsigned)((n_pieces + threads - 1) / threads), threads, 0, stream>>>(
+        reinterpret_cast<const uint32_t *>(folded_rows), n, reinterpret_cast<uint4 *>(image), n_pieces);
+    return cudaGetLastError();
+}
+
+void knn2_tc4_plan(size_t nA, size_t nB, int n_ctas, uint32_t *n_mtiles, uint32_t *n_chunks, uint32_t *rows_per_chunk) {
+    const uint32_t mt = (uint32_t)((nA + kTcTileRows - 1) / kTcTileRows);
+    *n_mtiles = mt;
+    if (nB == 0 || mt == 0) { *n_chunks = 0; *rows_per_chunk = kN4; return; }
+    const uint64_t overhead_rows = 4096;
+    const uint64_t tiles_b = (nB + kN4 - 1) / kN4;
+    const uint64_t c_min = (nB + kMaxChunkRows - 1) / kMaxChunkRows;
+    const uint64_t c_max = std::min<uint64_t>(tiles_b, std::max<uint64_t>(c_min, (32ull * n_ctas + mt - 1) / mt));
+    uint64_t best_c = c_min, best_cost = ~0ull;
+    for (uint64_t c = c_min; c <= c_max; ++c) {
+        const uint64_t rpc = ((nB + c - 1) / c + kN4 - 1) / kN4 * kN4;
+        if (rpc > kMaxChunkRows) continue;
+        const uint64_t chunks = (nB + rpc - 1) / rpc;
+        const uint64_t per_cta = ((uint64_t)mt * chunks + n_ctas - 1) / n_ctas;
+        const uint64_t cost = per_cta * (rpc + overhead_rows);
+        if (cost < best_cost) { best_cost = cost; best_c = c; }
+    }
+    uint64_t rpc = ((nB + best_c - 1) / best_c + kN4 - 1) / kN4 * kN4;
+    rpc = std::min<uint64_t>(rpc, kMaxChunkRows / kN4 * kN4);
+    *rows_per_chunk = (uint32_t)rpc;
+    *n_chunks = (uint32_t)((nB + rpc - 1) / rpc);
+}
+
+cudaError_t knn2_tc4_launch(const TcParams &p, int grid, cudaStream_t stream) {
+    static thread_local int configured_device = -1;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (configured_device != dev) {
+        cudaError_t e = cudaFuncSetAttribute(knn2_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes4);
+        if (e != cudaSuccess) return e;
+        configured_device = dev;
+    }
+    const uint64_t n_items = (uint64_t)p.n_mtiles * p.n_chunks;
+    if (n_items == 0) return cudaSuccess;
+    if ((uint64_t)grid > n_items) grid = (int)n_items;
+    knn2_tc4_kernel<<<grid, kThreads4, kSmemBytes4, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace hulo

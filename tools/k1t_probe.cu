@@ -145,7 +145,7 @@ int main(int argc, char **argv) {
     }
 
     // ---- 3: throughput
-    {
+    if (!(argc > 5 && atoi(argv[5]) == 4)) {
         const size_t nA = 4096, nB = big_nB;
         auto A = random_rows(nA, 5);
         Dev dA; dA.make(A, nA);
@@ -190,6 +190,124 @@ int main(int argc, char **argv) {
                    (double)nA * nB / ms * 1e-6);
         }
         cudaFree(rows); cudaFree(img); cudaFree(partial); dA.free();
+    }
+
+    // ---- 4: the 4-bit engine (K1t4): one tile of raw dots, a ragged shape, timing
+    if (argc > 5 && atoi(argv[5]) == 4) {
+        {
+            const size_t nA = 128, nB = 224;
+            auto A = random_rows(nA, 11), B = random_rows(nB, 12);
+            std::vector<uint32_t> fa = A, fb = B;
+            fold_rows(fa, nA); fold_rows(fb, nB);
+            uint4 *ra, *rb; uint8_t *ia, *ib; int32_t *dots; uint2 *partial;
+            CK(cudaMalloc(&ra, nA * 64)); CK(cudaMalloc(&rb, nB * 64));
+            CK(cudaMemcpy(ra, fa.data(), nA * 64, cudaMemcpyHostToDevice)); CK(cudaMemcpy(rb, fb.data(), nB * 64, cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&ia, knn2_tc4_image_bytes(nA))); CK(cudaMalloc(&ib, knn2_tc4_image_bytes(nB)));
+            CK(knn2_tc4_expand_launch(ra, nA, ia, 0)); CK(knn2_tc4_expand_launch(rb, nB, ib, 0));
+            CK(cudaMalloc(&dots, 128 * 256 * 4)); CK(cudaMemset(dots, 0x7f, 128 * 256 * 4));
+            CK(cudaMalloc(&partial, 128 * sizeof(uint2)));
+            TcParams p{};
+            p.imgA = ia; p.imgB = ib; p.nA = nA; p.nB = nB; p.n_mtiles = 1; p.n_chunks = 1; p.rows_per_chunk = 224;
+            p.slot_stride = 128; p.partial = partial; p.dbg_dots = dots;
+            CK(knn2_tc4_launch(p, sms, 0));
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("tc4 tile: kernel failed: %s\n", cudaGetErrorString(e)); return 3; }
+            std::vector<int32_t> h(128 * 256);
+            CK(cudaMemcpy(h.data(), dots, h.size() * 4, cudaMemcpyDeviceToHost));
+            size_t bad = 0;
+            for (size_t i = 0; i < nA; ++i)
+                for (size_t j = 0; j < nB; ++j)
+                    if (h[i * 256 + j] != 512 - 2 * hamming(&A[i * 16], &B[j * 16])) ++bad;
+            printf("tc4 tile test: %zu / %zu mismatches; got[0][0..3] = %d %d %d %d want %d %d %d %d; got[1][0]=%d want %d\n", bad,
+                   nA * nB, h[0], h[1], h[2], h[3], 512 - 2 * hamming(&A[0], &B[0]), 512 - 2 * hamming(&A[0], &B[16]),
+                   512 - 2 * hamming(&A[0], &B[32]), 512 - 2 * hamming(&A[0], &B[48]), h[256], 512 - 2 * hamming(&A[16], &B[0]));
+        }
+        {
+            const size_t nA = 300, nB = 70000;
+            auto A = random_rows(nA, 3), B = random_rows(nB, 4);
+            for (size_t j = 100; j < 140; ++j) memcpy(&B[j * 16], &B[7 * 16], 64);
+            for (size_t i = 0; i < 20; ++i) memcpy(&A[i * 16], &B[(i * 37) * 16], 64);
+            std::vector<uint32_t> fa = A, fb = B;
+            fold_rows(fa, nA); fold_rows(fb, nB);
+            uint4 *ra, *rb; uint8_t *ia, *ib;
+            CK(cudaMalloc(&ra, nA * 64)); CK(cudaMalloc(&rb, nB * 64));
+            CK(cudaMemcpy(ra, fa.data(), nA * 64, cudaMemcpyHostToDevice)); CK(cudaMemcpy(rb, fb.data(), nB * 64, cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&ia, knn2_tc4_image_bytes(nA))); CK(cudaMalloc(&ib, knn2_tc4_image_bytes(nB)));
+            CK(knn2_tc4_expand_launch(ra, nA, ia, 0)); CK(knn2_tc4_expand_launch(rb, nB, ib, 0));
+            uint32_t mt, nc, rpc;
+            knn2_tc4_plan(nA, nB, sms, &mt, &nc, &rpc);
+            const uint64_t stride = (nA + 31) & ~31ull;
+            uint2 *partial;
+            CK(cudaMalloc(&partial, (size_t)nc * stride * sizeof(uint2)));
+            CK(cudaMemset(partial, 0xEE, (size_t)nc * stride * sizeof(uint2)));
+            TcParams p{};
+            p.imgA = ia; p.imgB = ib; p.nA = nA; p.nB = nB; p.n_mtiles = mt; p.n_chunks = nc; p.rows_per_chunk = rpc;
+            p.slot_stride = stride; p.partial = partial;
+            CK(knn2_tc4_launch(p, sms, 0));
+            CK(cudaDeviceSynchronize());
+            std::vector<uint2> h((size_t)nc * stride);
+            CK(cudaMemcpy(h.data(), partial, h.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
+            size_t bad = 0;
+            for (size_t i = 0; i < nA; ++i) {
+                uint64_t m0 = ~0ull, m1 = ~0ull;
+                for (size_t j = 0; j < nB; ++j) {
+                    const uint64_t k = ((uint64_t)hamming(&A[i * 16], &B[j * 16]) << 32) | j;
+                    if (k < m0) { m1 = m0; m0 = k; } else if (k < m1) m1 = k;
+                }
+                uint64_t g0 = ~0ull, g1 = ~0ull;
+                for (uint32_t c = 0; c < nc; ++c) {
+                    const uint2 k = h[(size_t)c * stride + i];
+                    const uint32_t ks[2] = {k.x, k.y};
+                    for (uint32_t kk : ks) {
+                        if (kk == kKeyNone) continue;
+                        const uint64_t key = ((uint64_t)(kk >> kKeyIdxBits) << 32) | (uint64_t)(c * rpc + (kk & kKeyIdxMask));
+                        if (key < g0) { g1 = g0; g0 = key; } else if (key < g1) g1 = key;
+                    }
+                }
+                if (g0 != m0 || g1 != m1) ++bad;
+            }
+            printf("tc4 ragged test %zu x %zu (mtiles %u chunks %u rpc %u): %zu rows wrong\n", nA, nB, mt, nc, rpc, bad);
+        }
+        {
+            const size_t nA = 4096, nB = big_nB;
+            auto A = random_rows(nA, 5);
+            std::vector<uint32_t> fa = A;
+            fold_rows(fa, nA);
+            uint4 *ra, *rows; uint8_t *ia, *img;
+            CK(cudaMalloc(&ra, nA * 64)); CK(cudaMemcpy(ra, fa.data(), nA * 64, cudaMemcpyHostToDevice));
+            CK(cudaMalloc(&ia, knn2_tc4_image_bytes(nA))); CK(knn2_tc4_expand_launch(ra, nA, ia, 0));
+            CK(cudaMalloc(&rows, nB * 64));
+            {
+                const size_t slab = 1 << 20;
+                std::vector<uint32_t> buf = random_rows(slab, 6);
+                for (size_t off = 0; off < nB; off += slab) {
+                    const size_t m = std::min(slab, nB - off);
+                    buf[0] = (uint32_t)off;
+                    CK(cudaMemcpy(rows + off * 4, buf.data(), m * 64, cudaMemcpyHostToDevice));
+                }
+            }
+            CK(cudaMalloc(&img, knn2_tc4_image_bytes(nB)));
+            CK(knn2_tc4_expand_launch(rows, nB, img, 0));
+            uint32_t mt, nc, rpc;
+            knn2_tc4_plan(nA, nB, sms, &mt, &nc, &rpc);
+            uint2 *partial;
+            CK(cudaMalloc(&partial, (size_t)nc * nA * sizeof(uint2)));
+            TcParams p{};
+            p.imgA = ia; p.imgB = img; p.nA = nA; p.nB = nB; p.n_mtiles = mt; p.n_chunks = nc; p.rows_per_chunk = rpc;
+            p.slot_stride = nA; p.partial = partial;
+            cudaEvent_t e0, e1;
+            CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+            for (int rep = 0; rep < reps; ++rep) {
+                float ms = 0;
+                CK(cudaEventRecord(e0));
+                CK(knn2_tc4_launch(p, sms, 0));
+                CK(cudaEventRecord(e1));
+                CK(cudaEventSynchronize(e1));
+                CK(cudaEventElapsedTime(&ms, e0, e1));
+                printf("K1t4 %zu x %zu (mtiles %u chunks %u rpc %u): %.3f ms  %.1f Gdist/s\n", nA, nB, mt, nc, rpc, ms,
+                       (double)nA * nB / ms * 1e-6);
+            }
+        }
     }
     printf("done\n");
     return 0;

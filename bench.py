@@ -522,10 +522,13 @@ WORKLOAD_NAMES = {
 
 def workload_config(n_gpus, engine, exchange):
     name = "C5 campus-scale map" if N_MAP > 10_000_000 else "C3 building-scale map"
-    img = " + %.1f GB int8 tile image" % (N_MAP * 512 / 1e9) if engine == "tc" else ""
+    four = os.environ.get("HULO_TC_BITS", "4") != "8"
+    img = " + %.1f GB %s tile image" % (N_MAP * (256 if four else 512) / 1e9, "fp4" if four else "int8") if engine == "tc" else ""
     return {"workload": "%s: %d queries x %d map descriptors (64-byte AKAZE/MLDB rows), exact Hamming 2-NN, planted "
                         "matches (30%%)" % (name, N_QUERIES, N_MAP),
-            "engine": {"tc": "K1t: int8 contraction on tcgen05 tensor cores (distance = (512 - dot) / 2, int32 exact)",
+            "engine": {"tc": ("K1t4: fp4 (e2m1 +-1) contraction on tcgen05 tensor cores, kind::mxf4 with unit block scales, "
+                              "fp32 accumulation (distance = (512 - dot) / 2, exact)") if four else
+                             "K1t: int8 contraction on tcgen05 tensor cores (distance = (512 - dot) / 2, int32 exact)",
                        "int": "K1: XOR + popcount on the integer pipes", "cpu": "oracle port on host cores"}[engine],
             "sharding": "single GPU, whole table resident" if n_gpus == 1 else
                         "map rows sharded over %d GPUs; local top-2 per rank, exchange = %s, merge on every rank"
@@ -672,18 +675,25 @@ def bench_flat(args, rank, world, local_rank):
                                      "with LOP3 carry-save adders first, so frac can exceed 1"}
         tc_gpu = engines["tc"]["value"] / world
         bf16_s = float(peaks.get("bf16_tflops_sustained", 1400.0)); bf16_b = float(peaks.get("bf16_tflops", 1590.0))
-        tc_tops = tc_gpu * 1024.0 / 1e3             # 1 dist = 512 int8 multiply-adds = 1024 ops
+        tc_bits = 8 if os.environ.get("HULO_TC_BITS", "4") == "8" else 4
+        tc_mult = 4.0 if tc_bits == 4 else 2.0      # nominal dense rate of the operand type over bf16
+        tc_tops = tc_gpu * 1024.0 / 1e3             # 1 dist = 512 multiply-adds = 1024 ops
         tprof = read_json(os.path.join(ROOT, "profiles", "k1t_traffic.json"), {}) or {}
-        tc_roof = {"bound": "tensor", "achieved": tc_tops, "peak": 2.0 * bf16_s, "unit": "TOP/s",
-                   "frac": tc_tops / (2.0 * bf16_s),
-                   "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (no int8 GEMM was measured on "
-                                  "this pool; the kind::i8 rate is nominally twice the bf16 rate); sustained because "
-                                  "the launches run back to back under the 1 kW cap" if peaks else "fallback",
-                   "frac_of_burst_peak": tc_tops / (2.0 * bf16_b), "frac_of_nominal_4500": tc_tops / 4500.0,
+        tc_roof = {"bound": "tensor", "achieved": tc_tops, "peak": tc_mult * bf16_s, "unit": "TOP/s",
+                   "frac": tc_tops / (tc_mult * bf16_s),
+                   "peak_source": "%g x bf16_tflops_sustained of MEASURED_PEAKS.json: no %s GEMM was measured on this "
+                                  "pool, the nominal dense rate of the operand type is %g x the bf16 rate; sustained "
+                                  "because the launches run back to back under the 1 kW cap"
+                                  % (tc_mult, "fp4" if tc_bits == 4 else "int8", tc_mult) if peaks else "fallback",
+                   "frac_of_burst_peak": tc_tops / (tc_mult * bf16_b),
+                   "frac_of_nominal": tc_tops / (9000.0 if tc_bits == 4 else 4500.0),
                    "tensor_pipe_active_pct_ncu": tprof.get("sm__pipe_tensor_cycles_active_pct"),
-                   "work_per_unit": "1 dist = 512 int8 multiply-adds = 1024 ops (int32 accumulation, exact)"}
+                   "operands": "e2m1 (fp4) values +-1, ue8m0 block scales 1.0, fp32 accumulation (kind::mxf4)" if tc_bits == 4
+                               else "int8 values +-1, int32 accumulation (kind::i8)",
+                   "work_per_unit": "1 dist = 512 multiply-adds = 1024 ops; the accumulated integers stay below 2^10, so "
+                                    "the result is exact in either accumulator type"}
         if primary == "tc":
-            alg_bytes = 512.0 * (nA + N_MAP / world) + 16.0 * nA
+            alg_bytes = (256.0 if tc_bits == 4 else 512.0) * (nA + N_MAP / world) + 16.0 * nA
             roofline = dict(tc_roof)
             roofline["traffic"] = tprof.get("dram_bytes_per_launch")
             roofline["int_engine"] = int_roof
@@ -700,7 +710,9 @@ def bench_flat(args, rank, world, local_rank):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "s8" if primary == "tc" else "u32", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": ("fp4" if os.environ.get("HULO_TC_BITS", "4") != "8" else "s8") if primary == "tc" else "u32",
+            "data": "synthetic",
             "config": workload_config(world, primary, exchange),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nA * 64),
                     "d2h_bytes_per_step": int(nA * 16),

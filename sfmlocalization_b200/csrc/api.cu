@@ -104,8 +104,8 @@ static FlatPlan plan_flat(const hulo_gpu *h, size_t nA, size_t nB) {
 // ------------------------------------------------------------- K1t tile images
 void tc_image_register(hulo_gpu *h, const void *rows) {
     for (auto &e : h->tc_images) if (e.rows == rows) e.valid = false;
-    for (auto &e : h->tc_images) if (e.rows == rows && !e.seg) return;
-    h->tc_images.push_back(hulo_gpu::TcImage{rows, 0, false, false, {}, DevBuf{}});
+    for (auto &e : h->tc_images) if (e.rows == rows && e.kind == hulo_gpu::kTcFlat4) return;
+    h->tc_images.push_back(hulo_gpu::TcImage{rows, 0, false, hulo_gpu::kTcFlat4, {}, DevBuf{}});
 }
 void tc_image_invalidate(hulo_gpu *h, const void *rows) {
     for (auto &e : h->tc_images) if (e.rows == rows) e.valid = false;
@@ -117,23 +117,35 @@ void tc_image_drop(hulo_gpu *h, const void *rows) {
             h->tc_images.erase(h->tc_images.begin() + (long)k);
         }
 }
-// Tile image of `n` folded rows at `rows`: the cached one when the rows are a registered table,
-// else expanded into `scratch`.
-static int tc_image_for(hulo_gpu *h, const uint4 *rows, size_t n, DevBuf &scratch, const uint8_t **out) {
-    for (auto &e : h->tc_images) {
-        if (e.rows != rows || e.seg) continue;
-        if (!e.valid || e.n != n) {
-            HULO_CUDA(e.img.reserve(knn2_tc_image_bytes(n)));
-            HULO_CUDA(knn2_tc_expand_launch(rows, n, e.img.as<uint8_t>(), h->stream));
-            h->launches++;
-            e.n = n;
-            e.valid = true;
+// Tile image of `n` folded rows at `rows` (kind: kTcFlat8 or kTcFlat4): the cached one when the rows
+// are a registered table, else expanded into `scratch`.
+static int tc_image_for(hulo_gpu *h, const uint4 *rows, size_t n, int kind, DevBuf &scratch, const uint8_t **out) {
+    const size_t bytes = kind == hulo_gpu::kTcFlat4 ? knn2_tc4_image_bytes(n) : knn2_tc_image_bytes(n);
+    auto expand = [&](uint8_t *img) {
+        return kind == hulo_gpu::kTcFlat4 ? knn2_tc4_expand_launch(rows, n, img, h->stream)
+                                          : knn2_tc_expand_launch(rows, n, img, h->stream);
+    };
+    bool registered = false;
+    for (auto &e : h->tc_images) registered = registered || e.rows == rows;
+    if (registered) {
+        hulo_gpu::TcImage *e = nullptr;
+        for (auto &x : h->tc_images) if (x.rows == rows && x.kind == kind) e = &x;
+        if (!e) {
+            h->tc_images.push_back(hulo_gpu::TcImage{rows, 0, false, kind, {}, DevBuf{}});
+            e = &h->tc_images.back();
         }
-        *out = e.img.as<uint8_t>();
+        if (!e->valid || e->n != n) {
+            HULO_CUDA(e->img.reserve(bytes));
+            HULO_CUDA(expand(e->img.as<uint8_t>()));
+            h->launches++;
+            e->n = n;
+            e->valid = true;
+        }
+        *out = e->img.as<uint8_t>();
         return HULO_OK;
     }
-    HULO_CUDA(scratch.reserve(knn2_tc_image_bytes(n)));
-    HULO_CUDA(knn2_tc_expand_launch(rows, n, scratch.as<uint8_t>(), h->stream));
+    HULO_CUDA(scratch.reserve(bytes));
+    HULO_CUDA(expand(scratch.as<uint8_t>()));
     h->launches++;
     *out = scratch.as<uint8_t>();
     return HULO_OK;
@@ -170,9 +182,9 @@ static int tc_build_seg_image(hulo_gpu *h, const uint4 *rows, const uint64_t *se
 // The cached segmented image of a resident table.
 static int tc_seg_image_for_db(hulo_gpu *h, const hulo_db *db, const uint8_t **img, const uint32_t **tile0) {
     hulo_gpu::TcImage *e = nullptr;
-    for (auto &x : h->tc_images) if (x.rows == db->rows && x.seg) e = &x;
+    for (auto &x : h->tc_images) if (x.rows == db->rows && x.kind == hulo_gpu::kTcSeg8) e = &x;
     if (!e) {
-        h->tc_images.push_back(hulo_gpu::TcImage{db->rows, 0, false, true, {}, DevBuf{}});
+        h->tc_images.push_back(hulo_gpu::TcImage{db->rows, 0, false, hulo_gpu::kTcSeg8, {}, DevBuf{}});
         e = &h->tc_images.back();
     }
     if (!e->valid || e->n != db->n || e->tile0.size() != db->seg.size()) {
@@ -207,16 +219,21 @@ static int run_items_tc(hulo_gpu *h, const uint8_t *imgA, const uint8_t *imgB, c
     return HULO_OK;
 }
 
-// K1t for a flat searcher table against a flat database: same partial-key format as K1.
+// K1t for a flat searcher table against a flat database: same partial-key format as K1.  The 4-bit
+// form (K1t4, kind::mxf4) by default; HULO_TC_BITS=8 selects the int8 form (K1t, kind::i8).
 static int run_flat_k1_tc(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t nB, FlatRun *run) {
+    static const int bits = env_int("HULO_TC_BITS", 4);
+    const bool four = bits != 8;
+    const int kind = four ? hulo_gpu::kTcFlat4 : hulo_gpu::kTcFlat8;
     uint32_t n_mtiles = 0, n_chunks = 0, rpc = 0;
-    knn2_tc_plan(nA, nB, h->sm_count, &n_mtiles, &n_chunks, &rpc);
+    if (four) knn2_tc4_plan(nA, nB, h->sm_count, &n_mtiles, &n_chunks, &rpc);
+    else knn2_tc_plan(nA, nB, h->sm_count, &n_mtiles, &n_chunks, &rpc);
     run->n_chunks = n_chunks; run->rows_per_chunk = rpc; run->slot_stride = (nA + 31) & ~(size_t)31;
     if (n_chunks == 0) return HULO_OK;
     const uint8_t *imgA = nullptr, *imgB = nullptr;
-    int rc = tc_image_for(h, A, nA, h->tc_scratchA, &imgA);
+    int rc = tc_image_for(h, A, nA, kind, h->tc_scratchA, &imgA);
     if (rc != HULO_OK) return rc;
-    rc = tc_image_for(h, B, nB, h->tc_scratchB, &imgB);
+    rc = tc_image_for(h, B, nB, kind, h->tc_scratchB, &imgB);
     if (rc != HULO_OK) return rc;
     HULO_CUDA(h->partial.reserve((size_t)n_chunks * run->slot_stride * sizeof(uint2)));
     TcParams tp{};
@@ -225,9 +242,13 @@ static int run_flat_k1_tc(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B
     tp.n_mtiles = n_mtiles; tp.n_chunks = n_chunks; tp.rows_per_chunk = rpc;
     tp.slot_stride = run->slot_stride;
     tp.partial = h->partial.as<uint2>();
-    static const int cluster = env_int("HULO_TC_CLUSTER", 1);      // tuning sweeps
-    tp.cluster = cluster;
-    HULO_CUDA(knn2_tc_launch(tp, h->sm_count, h->stream));
+    if (four) {
+        HULO_CUDA(knn2_tc4_launch(tp, h->sm_count, h->stream));
+    } else {
+        static const int cluster = env_int("HULO_TC_CLUSTER", 1);      // tuning sweeps
+        tp.cluster = cluster;
+        HULO_CUDA(knn2_tc_launch(tp, h->sm_count, h->stream));
+    }
     h->launches++;
     return HULO_OK;
 }
@@ -650,7 +671,7 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
         const uint32_t *tile0 = nullptr;
         int rc = tc_seg_image_for_db(h, map, &imgA, &tile0);
         if (rc != HULO_OK) return rc;
-        rc = tc_image_for(h, h->stageB.as<uint4>(), nq, h->tc_scratchB, &imgB);
+        rc = tc_image_for(h, h->stageB.as<uint4>(), nq, hulo_gpu::kTcFlat8, h->tc_scratchB, &imgB);
         if (rc != HULO_OK) return rc;
         n_chunks = 1; rows_per_chunk = kMaxChunkRows;
         std::vector<TcItem> items;

@@ -106,9 +106,11 @@ struct hulo_gpu {
     int knn_engine = HULO_KNN_AUTO;
     // tile images of K1t: one per registered table (built on first use, dropped when the table
     // changes), and two scratch images for staged rows
-    // `seg`: the segmented form (every segment of the table starts on an even tile, tile0[s] = its
-    // first tile), used by the item-mode searches; else the flat form.
-    struct TcImage { const void *rows; size_t n; bool valid; bool seg; std::vector<uint32_t> tile0; hulo::DevBuf img; };
+    // kind: kTcFlat8 = int8 image of a flat table, kTcSeg8 = the segmented int8 form (every segment
+    // of the table starts on an even tile, tile0[s] = its first tile) used by the item-mode searches,
+    // kTcFlat4 = the 4-bit image of K1t4.
+    enum { kTcFlat8 = 0, kTcSeg8 = 1, kTcFlat4 = 2 };
+    struct TcImage { const void *rows; size_t n; bool valid; int kind; std::vector<uint32_t> tile0; hulo::DevBuf img; };
     std::vector<TcImage> tc_images;
     hulo::DevBuf tc_scratchA, tc_scratchB, tc_tiles;
 

@@ -99,5 +99,11 @@ size_t knn2_tc4_image_bytes(size_t n);
 cudaError_t knn2_tc4_expand_launch(const uint4 *folded_rows, size_t n, uint8_t *image, cudaStream_t stream);
 void knn2_tc4_plan(size_t nA, size_t nB, int n_ctas, uint32_t *n_mtiles, uint32_t *n_chunks, uint32_t *rows_per_chunk);
 cudaError_t knn2_tc4_launch(const TcParams &p, int grid, cudaStream_t stream);
+// Item mode of K1t4: TcItem::a_tile / b_tile0 are 8-row GROUP indices into the images (any group can
+// start a searcher tile or a database range, so the segments of a table only need 8-row alignment).
+// The segmented image: group g holds table rows group_src[g] .. + group_rows[g] - 1 (device tables).
+size_t knn2_tc4_groups_image_bytes(size_t n_groups);
+cudaError_t knn2_tc4_expand_groups_launch(const uint4 *folded_rows, const uint32_t *group_src, const uint8_t *group_rows,
+                                          size_t n_groups, uint8_t *image, cudaStream_t stream);
 
 }  // namespace hulo

@@ -30,7 +30,6 @@ constexpr uint32_t kSfCol = 480;
 constexpr size_t kSmemBytes4 = 1024 + kABytes4 + (size_t)kStages4 * kStageBytes4 + 256 + 2 * 128 * sizeof(uint2);
 
 constexpr float kThrNoneF = -1024.0f;
-constexpr float kDotMaskedF = -2048.0f;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -139,6 +138,33 @@ __device__ __forceinline__ void scan32(const float (&v)[32], uint32_t row0, uint
     }
 }
 
+struct TcWork4 {
+    uint32_t a_group;    // first 8-row group of the searcher tile in image A
+    uint32_t a_rows;     // rows of the tile whose keys are written
+    uint32_t b_group;    // first group of the database range in image B
+    uint32_t b_rows;
+    uint64_t out_slot0;
+};
+// Flat mode: item w -> searcher tile (w % n_mtiles), chunk (w / n_mtiles); item mode: the list entry
+// (TcItem::a_tile / b_tile0 hold GROUP indices for this kernel).
+__device__ __forceinline__ TcWork4 tc_work4(const TcParams &p, uint32_t w) {
+    TcWork4 k;
+    if (p.items != nullptr) {
+        const TcItem it = p.items[w];
+        k.a_group = it.a_tile; k.a_rows = it.a_rows; k.b_group = it.b_tile0; k.b_rows = it.b_rows;
+        k.out_slot0 = it.out_slot0;
+    } else {
+        const uint32_t mt = w % p.n_mtiles, c = w / p.n_mtiles;
+        const uint32_t b_row0 = c * p.rows_per_chunk;
+        k.a_group = mt * 16u;
+        k.a_rows = min(kTcTileRows, p.nA - mt * kTcTileRows);
+        k.b_group = b_row0 / 8u;
+        k.b_rows = min(p.rows_per_chunk, p.nB - b_row0);
+        k.out_slot0 = (uint64_t)c * p.slot_stride + (uint64_t)mt * kTcTileRows;
+    }
+    return k;
+}
+
 __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -197,24 +223,30 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
     __syncthreads();
     tc_fence_after();
 
-    const uint32_t n_items = p.n_mtiles * p.n_chunks;
+    // flat mode: items round-robin over the CTAs; item mode: a contiguous block of the list per CTA
+    uint32_t w_begin, w_end, w_step;
+    if (p.items != nullptr) {
+        w_begin = (uint32_t)((uint64_t)blockIdx.x * p.n_items / gridDim.x);
+        w_end = (uint32_t)((uint64_t)(blockIdx.x + 1) * p.n_items / gridDim.x);
+        w_step = 1;
+    } else {
+        w_begin = blockIdx.x; w_end = p.n_mtiles * p.n_chunks; w_step = gridDim.x;
+    }
 
     if (warp == 0) {
         if (lane == 0) {
             uint32_t stage = 0, ph = 0, a_loaded = 0xFFFFFFFFu, a_loads = 0;
-            for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
-                const uint32_t mt = w % p.n_mtiles, c = w / p.n_mtiles;
-                const uint32_t b_row0 = c * p.rows_per_chunk;
-                const uint32_t b_rows = min(p.rows_per_chunk, p.nB - b_row0);
-                const uint32_t n_tiles = (b_rows + kN4 - 1) / kN4;
-                if (mt != a_loaded) {
+            for (uint32_t w = w_begin; w < w_end; w += w_step) {
+                const TcWork4 k = tc_work4(p, w);
+                const uint32_t n_tiles = (k.b_rows + kN4 - 1) / kN4;
+                if (k.a_group != a_loaded) {
                     if (a_loads > 0) mbar_wait(bar_a_empty, (a_loads - 1u) & 1u);
                     mbar_expect_tx(bar_a_full, kABytes4);
-                    bulk_load(sA, p.imgA + (size_t)mt * kABytes4, kABytes4, bar_a_full);
-                    a_loaded = mt;
+                    bulk_load(sA, p.imgA + (size_t)k.a_group * kGroupBytes4, kABytes4, bar_a_full);
+                    a_loaded = k.a_group;
                     ++a_loads;
                 }
-                const uint8_t *src = p.imgB + (size_t)(b_row0 / 8u) * kGroupBytes4;
+                const uint8_t *src = p.imgB + (size_t)k.b_group * kGroupBytes4;
                 for (uint32_t t = 0; t < n_tiles; ++t) {
                     mbar_wait(bar_b_empty + 8 * stage, ph ^ 1u);
                     mbar_expect_tx(bar_b_full + 8 * stage, kStageBytes4);
@@ -228,15 +260,13 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
         if (lane == 0) {
             uint32_t stage = 0, ph = 0, acc_it = 0, a_loaded = 0xFFFFFFFFu, a_loads = 0;
             const uint32_t tsf = tmem_base + kSfCol;
-            for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x) {
-                const uint32_t mt = w % p.n_mtiles, c = w / p.n_mtiles;
-                const uint32_t b_row0 = c * p.rows_per_chunk;
-                const uint32_t b_rows = min(p.rows_per_chunk, p.nB - b_row0);
-                const uint32_t n_tiles = (b_rows + kN4 - 1) / kN4;
-                if (mt != a_loaded) {
+            for (uint32_t w = w_begin; w < w_end; w += w_step) {
+                const TcWork4 k = tc_work4(p, w);
+                const uint32_t n_tiles = (k.b_rows + kN4 - 1) / kN4;
+                if (k.a_group != a_loaded) {
                     if (a_loads > 0) tc_commit(bar_a_empty);
                     mbar_wait(bar_a_full, a_loads & 1u);
-                    a_loaded = mt;
+                    a_loaded = k.a_group;
                     ++a_loads;
                 }
                 for (uint32_t t = 0; t < n_tiles; ++t, ++acc_it) {
@@ -263,10 +293,9 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
         const uint32_t grp = (warp - 2u) >> 2;
         const uint32_t row = quarter * 32u + lane;
         uint32_t acc_base = 0, uses = 0, it = 0;
-        for (uint32_t w = blockIdx.x; w < n_items; w += gridDim.x, ++it) {
-            const uint32_t mt = w % p.n_mtiles, c = w / p.n_mtiles;
-            const uint32_t b_row0 = c * p.rows_per_chunk;
-            const uint32_t b_rows = min(p.rows_per_chunk, p.nB - b_row0);
+        for (uint32_t w = w_begin; w < w_end; w += w_step, ++it) {
+            const TcWork4 k = tc_work4(p, w);
+            const uint32_t b_rows = k.b_rows;
             const uint32_t n_tiles = (b_rows + kN4 - 1) / kN4;
             uint32_t best0 = kKeyNone, best1 = kKeyNone;
             float thr = kThrNoneF;
@@ -275,7 +304,7 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
                 mbar_wait(bar_acc_full + 8 * grp, uses & 1u);
                 tc_fence_after();
                 const uint32_t n_valid = min(kN4, b_rows - t * kN4);
-                const bool dump = p.dbg_dots != nullptr && w == 0 && t == 0;
+                const bool dump = p.dbg_dots != nullptr && w == 0 && t == 0 && p.items == nullptr;
                 float va[32], vb[32];
                 HULO_LDTM32(va, taddr);
 #pragma unroll
@@ -308,8 +337,7 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
                 const uint2 o = *slot;
                 const uint32_t lo = min(best0, o.x), mid = max(best0, o.x);
                 const uint32_t second = min(mid, min(best1, o.y));
-                const uint32_t a_row = mt * kTcTileRows + row;
-                if (a_row < p.nA) p.partial[(uint64_t)c * p.slot_stride + a_row] = make_uint2(lo, second);
+                if (row < k.a_rows) p.partial[k.out_slot0 + row] = make_uint2(lo, second);
             }
         }
     }
@@ -322,16 +350,27 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
 }
 
 // One thread per 16-byte piece of the image = 32 consecutive bits of one row.
-__global__ void knn2_tc4_expand_kernel(const uint32_t *__restrict__ folded, size_t n, uint4 *__restrict__ image,
-                                       size_t n_pieces) {
+// group_src == nullptr: image row r is table row r; else image group g holds table rows
+// group_src[g] .. + group_rows[g] - 1 (segmented tables: every segment starts on a group).
+__global__ void knn2_tc4_expand_kernel(const uint32_t *__restrict__ folded, size_t n, const uint32_t *__restrict__ group_src,
+                                       const uint8_t *__restrict__ group_rows, size_t n_groups_tab,
+                                       uint4 *__restrict__ image, size_t n_pieces) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_pieces) return;
     const size_t group = idx >> 7;                       // 128 pieces per group of 8 rows
     const uint32_t rem = (uint32_t)(idx & 127u);
     const uint32_t core = rem >> 3, i = rem & 7u;        // word `core` of the row
-    const size_t r = group * 8 + i;
+    size_t r;
+    bool valid;
+    if (group_src != nullptr) {
+        valid = group < n_groups_tab && i < __ldg(group_rows + group);
+        r = valid ? (size_t)__ldg(group_src + group) + i : 0;
+    } else {
+        r = group * 8 + i;
+        valid = r < n;
+    }
     uint4 out = make_uint4(0u, 0u, 0u, 0u);              // padding rows: 0.0 everywhere
-    if (r < n) {
+    if (valid) {
         const uint32_t *f = folded + r * 16;
         uint32_t wv = __ldg(f + core);
         if (core == 15u) wv ^= __ldg(f + 11) ^ __ldg(f + 14);
@@ -362,7 +401,19 @@ cudaError_t knn2_tc4_expand_launch(const uint4 *folded_rows, size_t n, uint8_t *
     const size_t n_pieces = knn2_tc4_image_bytes(n) / 16;
     const int threads = 256;
     knn2_tc4_expand_kernel<<<(unsigned)((n_pieces + threads - 1) / threads), threads, 0, stream>>>(
-        reinterpret_cast<const uint32_t *>(folded_rows), n, reinterpret_cast<uint4 *>(image), n_pieces);
+        reinterpret_cast<const uint32_t *>(folded_rows), n, nullptr, nullptr, 0, reinterpret_cast<uint4 *>(image), n_pieces);
+    return cudaGetLastError();
+}
+
+size_t knn2_tc4_groups_image_bytes(size_t n_groups) { return n_groups * (size_t)kGroupBytes4 + kStageBytes4 + kABytes4; }
+
+cudaError_t knn2_tc4_expand_groups_launch(const uint4 *folded_rows, const uint32_t *group_src, const uint8_t *group_rows,
+                                          size_t n_groups, uint8_t *image, cudaStream_t stream) {
+    const size_t n_pieces = knn2_tc4_groups_image_bytes(n_groups) / 16;
+    const int threads = 256;
+    knn2_tc4_expand_kernel<<<(unsigned)((n_pieces + threads - 1) / threads), threads, 0, stream>>>(
+        reinterpret_cast<const uint32_t *>(folded_rows), 0, group_src, group_rows, n_groups, reinterpret_cast<uint4 *>(image),
+        n_pieces);
     return cudaGetLastError();
 }
 
@@ -398,7 +449,7 @@ cudaError_t knn2_tc4_launch(const TcParams &p, int grid, cudaStream_t stream) {
         if (e != cudaSuccess) return e;
         configured_device = dev;
     }
-    const uint64_t n_items = (uint64_t)p.n_mtiles * p.n_chunks;
+    const uint64_t n_items = p.items != nullptr ? p.n_items : (uint64_t)p.n_mtiles * p.n_chunks;
     if (n_items == 0) return cudaSuccess;
     if ((uint64_t)grid > n_items) grid = (int)n_items;
     knn2_tc4_kernel<<<grid, kThreads4, kSmemBytes4, stream>>>(p);

@@ -179,16 +179,57 @@ static int tc_build_seg_image(hulo_gpu *h, const uint4 *rows, const uint64_t *se
     return HULO_OK;
 }
 
+// The same for K1t4: every segment starts on an 8-row group; grp0[s] = its first group.
+static int tc_build_seg_image4(hulo_gpu *h, const uint4 *rows, const uint64_t *seg, size_t n_seg, DevBuf &img,
+                               std::vector<uint32_t> &grp0) {
+    grp0.assign(n_seg + 1, 0);
+    for (size_t s = 0; s < n_seg; ++s) grp0[s + 1] = grp0[s] + (uint32_t)((seg[s + 1] - seg[s] + 7) / 8);
+    const size_t n_groups = grp0[n_seg];
+    std::vector<uint32_t> src(std::max<size_t>(n_groups, 1), 0);
+    std::vector<uint8_t> cnt(std::max<size_t>(n_groups, 1), 0);
+    for (size_t s = 0; s < n_seg; ++s) {
+        const uint64_t n = seg[s + 1] - seg[s];
+        for (uint32_t g = grp0[s]; g < grp0[s + 1]; ++g) {
+            const uint64_t first = (uint64_t)(g - grp0[s]) * 8;
+            src[g] = (uint32_t)(seg[s] + first);
+            cnt[g] = (uint8_t)std::min<uint64_t>(8, n - first);
+        }
+    }
+    HULO_CUDA(img.reserve(knn2_tc4_groups_image_bytes(n_groups)));
+    const size_t cnt_off = (src.size() * sizeof(uint32_t) + 15) & ~(size_t)15;
+    HULO_CUDA(h->tc_tiles.reserve(cnt_off + cnt.size()));
+    HULO_CUDA(cudaMemcpyAsync(h->tc_tiles.ptr, src.data(), src.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    HULO_CUDA(cudaMemcpyAsync(h->tc_tiles.as<uint8_t>() + cnt_off, cnt.data(), cnt.size(), cudaMemcpyHostToDevice, h->stream));
+    HULO_CUDA(knn2_tc4_expand_groups_launch(rows, h->tc_tiles.as<uint32_t>(), h->tc_tiles.as<uint8_t>() + cnt_off, n_groups,
+                                            img.as<uint8_t>(), h->stream));
+    h->launches++;
+    HULO_CUDA(cudaStreamSynchronize(h->stream));      // the tables are host memory of this call
+    return HULO_OK;
+}
+
+// Item-mode engine: 4-bit (K1t4) unless HULO_TC_BITS=8.
+static bool tc_items_four() {
+    static const int bits = env_int("HULO_TC_BITS", 4);
+    return bits != 8;
+}
+// A searcher tile / database range of a segmented image in the units of the engine: image tiles of
+// 128 rows (K1t) or groups of 8 rows (K1t4); `first[s]` = tile0 or grp0 of the segment.
+static inline uint32_t tc_unit_of_row(const uint32_t *first, size_t s, uint64_t row_in_seg) {
+    return first[s] + (uint32_t)(row_in_seg / (tc_items_four() ? 8u : kTcTileRows));
+}
+
 // The cached segmented image of a resident table.
 static int tc_seg_image_for_db(hulo_gpu *h, const hulo_db *db, const uint8_t **img, const uint32_t **tile0) {
     hulo_gpu::TcImage *e = nullptr;
-    for (auto &x : h->tc_images) if (x.rows == db->rows && x.kind == hulo_gpu::kTcSeg8) e = &x;
+    const int kind = tc_items_four() ? hulo_gpu::kTcSeg4 : hulo_gpu::kTcSeg8;
+    for (auto &x : h->tc_images) if (x.rows == db->rows && x.kind == kind) e = &x;
     if (!e) {
-        h->tc_images.push_back(hulo_gpu::TcImage{db->rows, 0, false, hulo_gpu::kTcSeg8, {}, DevBuf{}});
+        h->tc_images.push_back(hulo_gpu::TcImage{db->rows, 0, false, kind, {}, DevBuf{}});
         e = &h->tc_images.back();
     }
     if (!e->valid || e->n != db->n || e->tile0.size() != db->seg.size()) {
-        int rc = tc_build_seg_image(h, db->rows, db->seg.data(), db->seg.size() - 1, e->img, e->tile0);
+        int rc = tc_items_four() ? tc_build_seg_image4(h, db->rows, db->seg.data(), db->seg.size() - 1, e->img, e->tile0)
+                                 : tc_build_seg_image(h, db->rows, db->seg.data(), db->seg.size() - 1, e->img, e->tile0);
         if (rc != HULO_OK) return rc;
         e->n = db->n;
         e->valid = true;
@@ -214,7 +255,8 @@ static int run_items_tc(hulo_gpu *h, const uint8_t *imgA, const uint8_t *imgB, c
     tp.n_items = (uint32_t)items.size();
     tp.partial = h->partial.as<uint2>();
     tp.cluster = 1;
-    HULO_CUDA(knn2_tc_launch(tp, h->sm_count, h->stream));
+    if (tc_items_four()) HULO_CUDA(knn2_tc4_launch(tp, h->sm_count, h->stream));
+    else HULO_CUDA(knn2_tc_launch(tp, h->sm_count, h->stream));
     h->launches++;
     return HULO_OK;
 }
@@ -671,7 +713,8 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
         const uint32_t *tile0 = nullptr;
         int rc = tc_seg_image_for_db(h, map, &imgA, &tile0);
         if (rc != HULO_OK) return rc;
-        rc = tc_image_for(h, h->stageB.as<uint4>(), nq, hulo_gpu::kTcFlat8, h->tc_scratchB, &imgB);
+        rc = tc_image_for(h, h->stageB.as<uint4>(), nq, tc_items_four() ? hulo_gpu::kTcFlat4 : hulo_gpu::kTcFlat8,
+                          h->tc_scratchB, &imgB);
         if (rc != HULO_OK) return rc;
         n_chunks = 1; rows_per_chunk = kMaxChunkRows;
         std::vector<TcItem> items;
@@ -680,7 +723,7 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
             const uint64_t rows = map->seg[s + 1] - map->seg[s];
             for (uint64_t t0 = 0; t0 < rows; t0 += kTcTileRows) {
                 TcItem it{};
-                it.a_tile = tile0[s] + (uint32_t)(t0 / kTcTileRows);
+                it.a_tile = tc_unit_of_row(tile0, s, t0);
                 it.a_rows = (uint32_t)std::min<uint64_t>(kTcTileRows, rows - t0);
                 it.b_tile0 = 0;
                 it.b_rows = (uint32_t)nq;
@@ -853,7 +896,8 @@ int hulo_match_to_queries(hulo_gpu *h, const hulo_db *map, const uint32_t *views
     if (use_tc) {
         int rc = tc_seg_image_for_db(h, map, &imgA, &tile0_map);
         if (rc != HULO_OK) return rc;
-        rc = tc_build_seg_image(h, h->stageB.as<uint4>(), q_offsets, n_queries, h->tc_scratchB, tile0_q);
+        rc = tc_items_four() ? tc_build_seg_image4(h, h->stageB.as<uint4>(), q_offsets, n_queries, h->tc_scratchB, tile0_q)
+                             : tc_build_seg_image(h, h->stageB.as<uint4>(), q_offsets, n_queries, h->tc_scratchB, tile0_q);
         if (rc != HULO_OK) return rc;
         imgB = h->tc_scratchB.as<uint8_t>();
     }
@@ -901,7 +945,7 @@ int hulo_match_to_queries(hulo_gpu *h, const hulo_db *map, const uint32_t *views
                     for (size_t ql = 0; ql < nb; ++ql) {
                         const size_t q = members[ql];
                         TcItem it{};
-                        it.a_tile = tile0_map[s] + (uint32_t)(t0 / kTcTileRows);
+                        it.a_tile = tc_unit_of_row(tile0_map, s, t0);
                         it.a_rows = (uint32_t)std::min<uint64_t>(kTcTileRows, rows - t0);
                         it.b_tile0 = tile0_q[q];
                         it.b_rows = (uint32_t)(q_offsets[q + 1] - q_offsets[q]);
@@ -1058,7 +1102,7 @@ int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size
             if (!skip && use_tc) {
                 for (uint64_t t0 = 0; t0 < nI; t0 += kTcTileRows) {
                     TcItem it{};
-                    it.a_tile = tile0[I] + (uint32_t)(t0 / kTcTileRows);
+                    it.a_tile = tc_unit_of_row(tile0, I, t0);
                     it.a_rows = (uint32_t)std::min<uint64_t>(kTcTileRows, nI - t0);
                     it.b_tile0 = tile0[J];
                     it.b_rows = (uint32_t)nJ;

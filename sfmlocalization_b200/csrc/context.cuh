@@ -108,8 +108,8 @@ struct hulo_gpu {
     // changes), and two scratch images for staged rows
     // kind: kTcFlat8 = int8 image of a flat table, kTcSeg8 = the segmented int8 form (every segment
     // of the table starts on an even tile, tile0[s] = its first tile) used by the item-mode searches,
-    // kTcFlat4 = the 4-bit image of K1t4.
-    enum { kTcFlat8 = 0, kTcSeg8 = 1, kTcFlat4 = 2 };
+    // kTcFlat4 / kTcSeg4 = the 4-bit images of K1t4 (segments start on an 8-row group, tile0 = first group).
+    enum { kTcFlat8 = 0, kTcSeg8 = 1, kTcFlat4 = 2, kTcSeg4 = 3 };
     struct TcImage { const void *rows; size_t n; bool valid; int kind; std::vector<uint32_t> tile0; hulo::DevBuf img; };
     std::vector<TcImage> tc_images;
     hulo::DevBuf tc_scratchA, tc_scratchB, tc_tiles;

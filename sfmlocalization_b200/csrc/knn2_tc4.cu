@@ -30,6 +30,8 @@ constexpr uint32_t kSfCol = 480;
 constexpr size_t kSmemBytes4 = 1024 + kABytes4 + (size_t)kStages4 * kStageBytes4 + 256 + 2 * 128 * sizeof(uint2);
 
 constexpr float kThrNoneF = -1024.0f;
+constexpr float kDotPastEnd = -514.0f;          // 512 - 2 * 513
+constexpr uint32_t kKeyPastEnd = 513u << kKeyIdxBits;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -106,9 +108,23 @@ constexpr uint32_t kIdesc4 = (1u << 7) | (1u << 10) | ((kN4 >> 3) << 17) | (1u <
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
-// 32 accumulator columns of this thread's searcher row (see scan_block in knn2_tc.cu)
-__device__ __forceinline__ void scan32(const float (&v)[32], uint32_t row0, uint32_t n_valid, uint32_t &best0,
-                                       uint32_t &best1, float &thr) {
+__device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
+// two sorted key pairs -> the smallest two of the four
+__device__ __forceinline__ void merge2(uint32_t &p0, uint32_t &p1, uint32_t q0, uint32_t q1) {
+    const uint32_t m = max(p0, q0);
+    p0 = min(p0, q0);
+    p1 = umin3(m, p1, q1);
+}
+
+// 32 accumulator columns of this thread's searcher row.  v[e] = 512 - 2 * distance to database row
+// (row0 + e) of the range, an exact integer in fp32.  Fast path per 16 columns: their maximum against
+// the dot of the row's current second best (columns arrive in ascending row order, so a column that
+// only ties the second best loses on the index and a strict compare is exact).  Slow path: the packed
+// keys of all 16 columns and a branch-free tournament for their smallest two (log depth, so a single
+// warp per sub-partition keeps its ALU busy; short database ranges take this path for most groups).
+// Columns past the end of a range are given the dot kDotPastEnd by the caller ("distance 513"): they
+// lose against every real row and are turned into "none" when the item's keys are written.
+__device__ __forceinline__ void scan32(const float (&v)[32], uint32_t row0, uint32_t &best0, uint32_t &best1, float &thr) {
     float gm[2];
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
@@ -122,17 +138,25 @@ __device__ __forceinline__ void scan32(const float (&v)[32], uint32_t row0, uint
     for (int g = 0; g < 2; ++g) {
         const float *w = &v[16 * g];
         if (gm[g] > thr) {
-            const float t0 = thr;
+            // key = (512 - v) << 21 | column: v + 1.5 * 2^23 has the integer v in its low mantissa bits
+            // (0x4B400000 + v as a bit pattern), so one IMAD by -2^21 and a constant give the key modulo
+            // 2^32, which is the key (it fits 32 bits); the group's first column is a multiple of 16
+            const uint32_t kb = ((0x4B400000u + 512u) << (kKeyIdxBits - 1)) + (row0 + 16u * g);
+            uint32_t k[16];
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-                // columns past the end of the chunk hold whatever the padding rows gave
-                if (w[e] > t0 && (uint32_t)(16 * g + e) < n_valid) {
-                    const uint32_t key = ((uint32_t)(512 - __float2int_rn(w[e])) << (kKeyIdxBits - 1)) + (row0 + 16 * g + e);
-                    const uint32_t hi = max(best0, key);
-                    best0 = min(best0, key);
-                    best1 = min(best1, hi);
-                }
+                const uint32_t ti = (uint32_t)__float_as_int(w[e] + 12582912.0f);
+                k[e] = (ti * (0u - (1u << (kKeyIdxBits - 1))) + kb) | (uint32_t)e;
             }
+            uint32_t lo[8], hi[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { lo[i] = min(k[2 * i], k[2 * i + 1]); hi[i] = max(k[2 * i], k[2 * i + 1]); }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) merge2(lo[i], hi[i], lo[i + 4], hi[i + 4]);
+            merge2(lo[0], hi[0], lo[2], hi[2]);
+            merge2(lo[1], hi[1], lo[3], hi[3]);
+            merge2(lo[0], hi[0], lo[1], hi[1]);
+            merge2(best0, best1, lo[0], hi[0]);
             thr = best1 == kKeyNone ? kThrNoneF : (float)(512 - 2 * (int32_t)(best1 >> kKeyIdxBits));
         }
     }
@@ -306,30 +330,36 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
                 const uint32_t n_valid = min(kN4, b_rows - t * kN4);
                 const bool dump = p.dbg_dots != nullptr && w == 0 && t == 0 && p.items == nullptr;
                 float va[32], vb[32];
-                HULO_LDTM32(va, taddr);
+                // 7 blocks of 32 columns through two register sets; a rolled loop (the unrolled form
+                // does not fit the instruction cache with the tournament in it)
+                auto process = [&](float (&v)[32], uint32_t blk) {
+                    if (dump) _Pragma("unroll") for (int e = 0; e < 32; ++e) p.dbg_dots[row * 256 + 32 * blk + e] = (int32_t)v[e];
+                    if (n_valid < 32u * (blk + 1u)) {
 #pragma unroll
-                for (int blk = 0; blk < 7; ++blk) {          // 7 x 32 = 224 columns, two register sets in turn
-                    if (blk % 2 == 0) {
-                        HULO_WAIT_LD32(va);
-                        if (blk + 1 < 7) HULO_LDTM32(vb, taddr + 32u * (blk + 1));
-                        if (dump) _Pragma("unroll") for (int e = 0; e < 32; ++e) p.dbg_dots[row * 256 + 32 * blk + e] = (int32_t)va[e];
-                        if (blk == 6) {
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(bar_acc_empty + 8 * grp);
-                        }
-                        const uint32_t nv = n_valid > 32u * blk ? n_valid - 32u * blk : 0u;
-                        scan32(va, t * kN4 + 32u * blk, nv, best0, best1, thr);
-                    } else {
-                        HULO_WAIT_LD32(vb);
-                        if (blk + 1 < 7) HULO_LDTM32(va, taddr + 32u * (blk + 1));
-                        if (dump) _Pragma("unroll") for (int e = 0; e < 32; ++e) p.dbg_dots[row * 256 + 32 * blk + e] = (int32_t)vb[e];
-                        const uint32_t nv = n_valid > 32u * blk ? n_valid - 32u * blk : 0u;
-                        scan32(vb, t * kN4 + 32u * blk, nv, best0, best1, thr);
+                        for (int e = 0; e < 32; ++e) v[e] = 32u * blk + (uint32_t)e < n_valid ? v[e] : kDotPastEnd;
                     }
+                    scan32(v, t * kN4 + 32u * blk, best0, best1, thr);
+                };
+                HULO_LDTM32(va, taddr);
+#pragma unroll 1
+                for (uint32_t pr = 0; pr < 3; ++pr) {
+                    HULO_WAIT_LD32(va);
+                    HULO_LDTM32(vb, taddr + 32u * (2u * pr + 1u));
+                    process(va, 2u * pr);
+                    HULO_WAIT_LD32(vb);
+                    HULO_LDTM32(va, taddr + 32u * (2u * pr + 2u));
+                    process(vb, 2u * pr + 1u);
                 }
+                HULO_WAIT_LD32(va);
+                // every column of this accumulator is in registers: hand it back before the last scan
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * grp);
+                process(va, 6u);
             }
             acc_base += n_tiles;
+            if (best0 >= kKeyPastEnd) best0 = kKeyNone;           // columns past the end of the range
+            if (best1 >= kKeyPastEnd) best1 = kKeyNone;
             uint2 *slot = xchg_gen + (it & 1u) * 128u + row;
             if (grp == 1u) *slot = make_uint2(best0, best1);
             asm volatile("bar.sync 1, 256;" ::: "memory");

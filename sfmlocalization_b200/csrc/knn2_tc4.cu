@@ -97,6 +97,14 @@ constexpr uint32_t kIdesc4 = (1u << 7) | (1u << 10) | ((kN4 >> 3) << 17) | (1u <
           "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])   \
         : "r"(taddr)                                                                                                \
         : "memory")
+#define HULO_LDTM16(v, taddr)                                                                                       \
+    asm volatile(                                                                                                   \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                                                   \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"                            \
+        : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),          \
+          "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])     \
+        : "r"(taddr)                                                                                                \
+        : "memory")
 #define HULO_WAIT_LD32(v)                                                                                            \
     asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                    \
                  : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),    \
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_acc_full + 8 * b, 1);
-            mbar_init(bar_acc_empty + 8 * b, 4);
+            mbar_init(bar_acc_empty + 8 * b, 8);           // every epilogue warp drains a part of every tile
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -316,46 +324,54 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
         const uint32_t quarter = warp & 3u;
         const uint32_t grp = (warp - 2u) >> 2;
         const uint32_t row = quarter * 32u + lane;
-        uint32_t acc_base = 0, uses = 0, it = 0;
+        // Both groups work on EVERY tile, each on half of its columns (group g: [112 g, 112 g + 112)), so an
+        // accumulator is drained in half the time and handed back to the MMA thread sooner: with one
+        // group per accumulator the tensor pipe sat at 63 % (buffer cycle = MMA time + a whole drain).
+        uint32_t acc_base = 0, it = 0;
+        constexpr uint32_t kHalf = kN4 / 2;                      // 112 = 32 + 32 + 32 + 16
         for (uint32_t w = w_begin; w < w_end; w += w_step, ++it) {
             const TcWork4 k = tc_work4(p, w);
             const uint32_t b_rows = k.b_rows;
             const uint32_t n_tiles = (b_rows + kN4 - 1) / kN4;
             uint32_t best0 = kKeyNone, best1 = kKeyNone;
             float thr = kThrNoneF;
-            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + grp * 256u;
-            for (uint32_t t = (acc_base + grp) & 1u; t < n_tiles; t += 2, ++uses) {
-                mbar_wait(bar_acc_full + 8 * grp, uses & 1u);
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+                const uint32_t acc_it = acc_base + t, buf = acc_it & 1u;
+                mbar_wait(bar_acc_full + 8 * buf, (acc_it >> 1) & 1u);
                 tc_fence_after();
-                const uint32_t n_valid = min(kN4, b_rows - t * kN4);
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * 256u + grp * kHalf;
+                const uint32_t n_valid = min(kN4, b_rows - t * kN4);      // valid columns of the tile
+                const uint32_t c0 = grp * kHalf;                           // this group's first column
                 const bool dump = p.dbg_dots != nullptr && w == 0 && t == 0 && p.items == nullptr;
                 float va[32], vb[32];
-                // 7 blocks of 32 columns through two register sets; a rolled loop (the unrolled form
-                // does not fit the instruction cache with the tournament in it)
                 auto process = [&](float (&v)[32], uint32_t blk) {
-                    if (dump) _Pragma("unroll") for (int e = 0; e < 32; ++e) p.dbg_dots[row * 256 + 32 * blk + e] = (int32_t)v[e];
-                    if (n_valid < 32u * (blk + 1u)) {
+                    const uint32_t col = c0 + 32u * blk;
+                    if (dump) _Pragma("unroll") for (int e = 0; e < 32; ++e)
+                        if (blk < 3u || e < 16) p.dbg_dots[row * 256 + col + e] = (int32_t)v[e];
+                    if (n_valid < col + 32u) {
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) v[e] = 32u * blk + (uint32_t)e < n_valid ? v[e] : kDotPastEnd;
+                        for (int e = 0; e < 32; ++e) v[e] = col + (uint32_t)e < n_valid ? v[e] : kDotPastEnd;
                     }
-                    scan32(v, t * kN4 + 32u * blk, best0, best1, thr);
+                    scan32(v, t * kN4 + col, best0, best1, thr);
                 };
                 HULO_LDTM32(va, taddr);
-#pragma unroll 1
-                for (uint32_t pr = 0; pr < 3; ++pr) {
-                    HULO_WAIT_LD32(va);
-                    HULO_LDTM32(vb, taddr + 32u * (2u * pr + 1u));
-                    process(va, 2u * pr);
-                    HULO_WAIT_LD32(vb);
-                    HULO_LDTM32(va, taddr + 32u * (2u * pr + 2u));
-                    process(vb, 2u * pr + 1u);
-                }
                 HULO_WAIT_LD32(va);
-                // every column of this accumulator is in registers: hand it back before the last scan
+                HULO_LDTM32(vb, taddr + 32u);
+                process(va, 0u);
+                HULO_WAIT_LD32(vb);
+                HULO_LDTM32(va, taddr + 64u);
+                process(vb, 1u);
+                HULO_WAIT_LD32(va);
+                HULO_LDTM16(vb, taddr + 96u);                              // the last 16 columns of the half
+#pragma unroll
+                for (int e = 16; e < 32; ++e) vb[e] = kDotPastEnd;
+                process(va, 2u);
+                HULO_WAIT_LD32(vb);
+                // every column of this half is in registers: hand the accumulator back before the last scan
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * grp);
-                process(va, 6u);
+                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
+                process(vb, 3u);
             }
             acc_base += n_tiles;
             if (best0 >= kKeyPastEnd) best0 = kKeyNone;           // columns past the end of the range

@@ -70,9 +70,11 @@ uint64_t hulo_launch_count(const hulo_gpu *h);
  * engines give the same exact result, bit for bit, as the cv::flann::Index::knnSearch(k=2)
  * replacement they stand for (MatchUtils.cpp:105-108, 339-340):
  *   HULO_KNN_INT   XOR + popcount on the integer pipes (K1);
- *   HULO_KNN_TC    the 512 bits of a row as +-1 int8 values, distance = (512 - dot) / 2 from an int8
- *                  contraction with int32 accumulation on the tensor cores (K1t, tcgen05.mma.kind::i8).
- *                  Costs one expanded copy (512 bytes per row) of every table it searches;
+ *   HULO_KNN_TC    the 512 bits of a row as +-1 values, distance = (512 - dot) / 2 from a contraction on
+ *                  the tensor cores: 4-bit operands with fp32 accumulation (K1t4, tcgen05.mma.kind::mxf4;
+ *                  the accumulated integers stay below 2^10, so the result is exact) or, with
+ *                  HULO_TC_BITS=8, int8 operands with int32 accumulation (K1t, kind::i8).  Costs one
+ *                  expanded copy (256 or 512 bytes per row) of every table it searches;
  *   HULO_KNN_AUTO  (default) K1t when the search is large enough to pay for the expanded copies
  *                  (at least 128 searcher rows, 8192 database rows and 2^28 distances), else K1.
  * The environment variable HULO_KNN_ENGINE=int|tc|auto overrides the default at hulo_gpu_create. */

@@ -18,16 +18,20 @@ namespace hulo {
 
 namespace {
 
-constexpr uint32_t kN4 = 224;                     // database rows per accumulator tile
+constexpr uint32_t kN4 = 224;                     // database rows per accumulator tile, flat mode
+constexpr uint32_t kN4Items = 192;                // item mode: narrower tiles leave room for a second searcher tile
 constexpr uint32_t kRowBytes4 = 256;
 constexpr uint32_t kGroupBytes4 = 8 * kRowBytes4; // 2048
 constexpr uint32_t kABytes4 = 128 * kRowBytes4;   // 32768
-constexpr uint32_t kStageBytes4 = kN4 * kRowBytes4;   // 57344
+constexpr uint32_t kStageBytes4 = kN4 * kRowBytes4;   // 57344 (the widest stage: sizes the slack of the images)
 constexpr int kStages4 = 3;
 constexpr uint32_t kThreads4 = 320;
 constexpr uint32_t kTmemCols4 = 512;
 constexpr uint32_t kSfCol = 480;
-constexpr size_t kSmemBytes4 = 1024 + kABytes4 + (size_t)kStages4 * kStageBytes4 + 256 + 2 * 128 * sizeof(uint2);
+template <uint32_t N, bool A2>
+constexpr size_t smem_bytes4() {
+    return 1024 + (A2 ? 2 : 1) * kABytes4 + (size_t)kStages4 * N * kRowBytes4 + 256 + 2 * 128 * sizeof(uint2);
+}
 
 constexpr float kThrNoneF = -1024.0f;
 constexpr float kDotPastEnd = -514.0f;          // 512 - 2 * 513
@@ -84,7 +88,8 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
            ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 // cute::UMMA::InstrDescriptorBlockScaled: A = B = e2m1 (MXF4Format 1), K-major, N, ue8m0 scales, M = 128, K = 64
-constexpr uint32_t kIdesc4 = (1u << 7) | (1u << 10) | ((kN4 >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24);
+template <uint32_t N>
+constexpr uint32_t idesc4() { return (1u << 7) | (1u << 10) | ((N >> 3) << 17) | (1u << 23) | ((128u >> 4) << 24); }
 
 #define HULO_LDTM32(v, taddr)                                                                                       \
     asm volatile(                                                                                                   \
@@ -197,14 +202,20 @@ __device__ __forceinline__ TcWork4 tc_work4(const TcParams &p, uint32_t w) {
     return k;
 }
 
+// N = database rows per accumulator tile (a multiple of 64).  A2 = two searcher-tile buffers: the
+// producer fetches the searcher tile of the next item while the MMAs of the current one run (item
+// mode, where every few tiles bring a new searcher tile; with one buffer each change drained the ring).
+template <uint32_t N, bool A2>
 __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p) {
+    constexpr uint32_t kStageB = N * kRowBytes4;
+    constexpr uint32_t kNA = A2 ? 2u : 1u;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sA = smem_base;
-    const uint32_t sB = smem_base + kABytes4;
-    const uint32_t bars = sB + kStages4 * kStageBytes4;
-    const uint32_t bar_a_full = bars, bar_a_empty = bars + 8;
-    const uint32_t bar_b_full = bars + 16, bar_b_empty = bar_b_full + 8 * kStages4;
+    const uint32_t sB = smem_base + kNA * kABytes4;
+    const uint32_t bars = sB + kStages4 * kStageB;
+    const uint32_t bar_a_full = bars, bar_a_empty = bars + 16;          // [2] each
+    const uint32_t bar_b_full = bars + 32, bar_b_empty = bar_b_full + 8 * kStages4;
     const uint32_t bar_acc_full = bar_b_empty + 8 * kStages4, bar_acc_empty = bar_acc_full + 16;
     const uint32_t tmem_slot = bar_acc_empty + 16;
     const uint32_t xchg = bars + 256;
@@ -215,8 +226,10 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        mbar_init(bar_a_full, 1);
-        mbar_init(bar_a_empty, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_a_full + 8 * a, 1);
+            mbar_init(bar_a_empty + 8 * a, 1);
+        }
         for (int s = 0; s < kStages4; ++s) {
             mbar_init(bar_b_full + 8 * s, 1);
             mbar_init(bar_b_empty + 8 * s, 1);
@@ -270,19 +283,22 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
             uint32_t stage = 0, ph = 0, a_loaded = 0xFFFFFFFFu, a_loads = 0;
             for (uint32_t w = w_begin; w < w_end; w += w_step) {
                 const TcWork4 k = tc_work4(p, w);
-                const uint32_t n_tiles = (k.b_rows + kN4 - 1) / kN4;
+                const uint32_t n_tiles = (k.b_rows + N - 1) / N;
                 if (k.a_group != a_loaded) {
-                    if (a_loads > 0) mbar_wait(bar_a_empty, (a_loads - 1u) & 1u);
-                    mbar_expect_tx(bar_a_full, kABytes4);
-                    bulk_load(sA, p.imgA + (size_t)k.a_group * kGroupBytes4, kABytes4, bar_a_full);
+                    // load number a_loads goes to buffer a_loads % kNA; the buffer's previous tenant
+                    // (load a_loads - kNA) is released by the MMA thread when it moves past it
+                    const uint32_t slot = a_loads % kNA, use = a_loads / kNA;
+                    if (use > 0) mbar_wait(bar_a_empty + 8 * slot, (use - 1u) & 1u);
+                    mbar_expect_tx(bar_a_full + 8 * slot, kABytes4);
+                    bulk_load(sA + slot * kABytes4, p.imgA + (size_t)k.a_group * kGroupBytes4, kABytes4, bar_a_full + 8 * slot);
                     a_loaded = k.a_group;
                     ++a_loads;
                 }
                 const uint8_t *src = p.imgB + (size_t)k.b_group * kGroupBytes4;
                 for (uint32_t t = 0; t < n_tiles; ++t) {
                     mbar_wait(bar_b_empty + 8 * stage, ph ^ 1u);
-                    mbar_expect_tx(bar_b_full + 8 * stage, kStageBytes4);
-                    bulk_load(sB + stage * kStageBytes4, src + (size_t)t * kStageBytes4, kStageBytes4, bar_b_full + 8 * stage);
+                    mbar_expect_tx(bar_b_full + 8 * stage, kStageB);
+                    bulk_load(sB + stage * kStageB, src + (size_t)t * kStageB, kStageB, bar_b_full + 8 * stage);
                     if (++stage == kStages4) { stage = 0; ph ^= 1u; }
                 }
             }
@@ -290,14 +306,17 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0) {
-            uint32_t stage = 0, ph = 0, acc_it = 0, a_loaded = 0xFFFFFFFFu, a_loads = 0;
+            uint32_t stage = 0, ph = 0, acc_it = 0, a_loaded = 0xFFFFFFFFu, a_loads = 0, a_slot = 0;
             const uint32_t tsf = tmem_base + kSfCol;
             for (uint32_t w = w_begin; w < w_end; w += w_step) {
                 const TcWork4 k = tc_work4(p, w);
-                const uint32_t n_tiles = (k.b_rows + kN4 - 1) / kN4;
+                const uint32_t n_tiles = (k.b_rows + N - 1) / N;
                 if (k.a_group != a_loaded) {
-                    if (a_loads > 0) tc_commit(bar_a_empty);
-                    mbar_wait(bar_a_full, a_loads & 1u);
+                    // every MMA issued so far read an earlier tile: the buffer of the previous one is free
+                    // once they are done
+                    if (a_loads > 0) tc_commit(bar_a_empty + 8 * ((a_loads - 1u) % kNA));
+                    a_slot = a_loads % kNA;
+                    mbar_wait(bar_a_full + 8 * a_slot, (a_loads / kNA) & 1u);
                     a_loaded = k.a_group;
                     ++a_loads;
                 }
@@ -309,9 +328,9 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
                     const uint32_t tmem_d = tmem_base + buf * 256u;
 #pragma unroll
                     for (uint32_t j = 0; j < 8; ++j) {
-                        const uint64_t da = smem_desc(sA + j * 256u, 128u, kGroupBytes4);
-                        const uint64_t db = smem_desc(sB + stage * kStageBytes4 + j * 256u, 128u, kGroupBytes4);
-                        tc_mma_mxf4(tmem_d, da, db, kIdesc4, tsf, tsf, j != 0u);
+                        const uint64_t da = smem_desc(sA + a_slot * kABytes4 + j * 256u, 128u, kGroupBytes4);
+                        const uint64_t db = smem_desc(sB + stage * kStageB + j * 256u, 128u, kGroupBytes4);
+                        tc_mma_mxf4(tmem_d, da, db, idesc4<N>(), tsf, tsf, j != 0u);
                     }
                     tc_commit(bar_b_empty + 8 * stage);
                     tc_commit(bar_acc_full + 8 * buf);
@@ -328,11 +347,13 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
         // accumulator is drained in half the time and handed back to the MMA thread sooner: with one
         // group per accumulator the tensor pipe sat at 63 % (buffer cycle = MMA time + a whole drain).
         uint32_t acc_base = 0, it = 0;
-        constexpr uint32_t kHalf = kN4 / 2;                      // 112 = 32 + 32 + 32 + 16
+        constexpr uint32_t kHalf = N / 2;                        // 112 = 32 + 32 + 32 + 16, or 96 = 32 + 32 + 32
+        constexpr bool kTail16 = (kHalf % 32u) != 0u;
+        static_assert(kHalf / 32u == 3u, "the epilogue is written for three full blocks per half");
         for (uint32_t w = w_begin; w < w_end; w += w_step, ++it) {
             const TcWork4 k = tc_work4(p, w);
             const uint32_t b_rows = k.b_rows;
-            const uint32_t n_tiles = (b_rows + kN4 - 1) / kN4;
+            const uint32_t n_tiles = (b_rows + N - 1) / N;
             uint32_t best0 = kKeyNone, best1 = kKeyNone;
             float thr = kThrNoneF;
             for (uint32_t t = 0; t < n_tiles; ++t) {
@@ -340,7 +361,7 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
                 mbar_wait(bar_acc_full + 8 * buf, (acc_it >> 1) & 1u);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + buf * 256u + grp * kHalf;
-                const uint32_t n_valid = min(kN4, b_rows - t * kN4);      // valid columns of the tile
+                const uint32_t n_valid = min(N, b_rows - t * N);           // valid columns of the tile
                 const uint32_t c0 = grp * kHalf;                           // this group's first column
                 const bool dump = p.dbg_dots != nullptr && w == 0 && t == 0 && p.items == nullptr;
                 float va[32], vb[32];
@@ -352,7 +373,13 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
 #pragma unroll
                         for (int e = 0; e < 32; ++e) v[e] = col + (uint32_t)e < n_valid ? v[e] : kDotPastEnd;
                     }
-                    scan32(v, t * kN4 + col, best0, best1, thr);
+                    scan32(v, t * N + col, best0, best1, thr);
+                };
+                auto release = [&]() {
+                    // every column of this half is in registers: hand the accumulator back before the last scan
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
                 };
                 HULO_LDTM32(va, taddr);
                 HULO_WAIT_LD32(va);
@@ -362,16 +389,18 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
                 HULO_LDTM32(va, taddr + 64u);
                 process(vb, 1u);
                 HULO_WAIT_LD32(va);
-                HULO_LDTM16(vb, taddr + 96u);                              // the last 16 columns of the half
+                if constexpr (kTail16) {
+                    HULO_LDTM16(vb, taddr + 96u);                          // the last 16 columns of the half
 #pragma unroll
-                for (int e = 16; e < 32; ++e) vb[e] = kDotPastEnd;
-                process(va, 2u);
-                HULO_WAIT_LD32(vb);
-                // every column of this half is in registers: hand the accumulator back before the last scan
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
-                process(vb, 3u);
+                    for (int e = 16; e < 32; ++e) vb[e] = kDotPastEnd;
+                    process(va, 2u);
+                    HULO_WAIT_LD32(vb);
+                    release();
+                    process(vb, 3u);
+                } else {
+                    release();
+                    process(va, 2u);
+                }
             }
             acc_base += n_tiles;
             if (best0 >= kKeyPastEnd) best0 = kKeyNone;           // columns past the end of the range
@@ -486,20 +515,28 @@ void knn2_tc4_plan(size_t nA, size_t nB, int n_ctas, uint32_t *n_mtiles, uint32_
     *n_chunks = (uint32_t)((nB + rpc - 1) / rpc);
 }
 
-cudaError_t knn2_tc4_launch(const TcParams &p, int grid, cudaStream_t stream) {
+template <uint32_t N, bool A2>
+static cudaError_t launch4(const TcParams &p, int grid, cudaStream_t stream) {
     static thread_local int configured_device = -1;
+    constexpr size_t smem = smem_bytes4<N, A2>();
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured_device != dev) {
-        cudaError_t e = cudaFuncSetAttribute(knn2_tc4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes4);
+        cudaError_t e = cudaFuncSetAttribute(knn2_tc4_kernel<N, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured_device = dev;
     }
     const uint64_t n_items = p.items != nullptr ? p.n_items : (uint64_t)p.n_mtiles * p.n_chunks;
     if (n_items == 0) return cudaSuccess;
     if ((uint64_t)grid > n_items) grid = (int)n_items;
-    knn2_tc4_kernel<<<grid, kThreads4, kSmemBytes4, stream>>>(p);
+    knn2_tc4_kernel<N, A2><<<grid, kThreads4, smem, stream>>>(p);
     return cudaGetLastError();
+}
+
+cudaError_t knn2_tc4_launch(const TcParams &p, int grid, cudaStream_t stream) {
+    // item lists: 192-row tiles and two searcher-tile buffers; flat searches: 224-row tiles, one buffer
+    if (p.items != nullptr) return launch4<kN4Items, true>(p, grid, stream);
+    return launch4<kN4, false>(p, grid, stream);
 }
 
 }  // namespace hulo

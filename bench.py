@@ -592,6 +592,9 @@ def bench_flat(args, rank, world, local_rank):
     o_ms, _ = timed_device(other, o_steps, 3)
     engines = {primary: {"value": value, "ms_per_step": ms / args.steps},
                other: {"value": total_dist * o_steps / (o_ms * 1e-3) / 1e9, "ms_per_step": o_ms / o_steps}}
+    # the int8 form of the tensor-core engine (K1t), for the record
+    t8_ms, _ = timed_device("tc8", o_steps, 3)
+    engines["tc8"] = {"value": total_dist * o_steps / (t8_ms * 1e-3) / 1e9, "ms_per_step": t8_ms / o_steps}
     g.set_knn_engine(primary)
 
     # ---- end to end through the C-ABI with host buffers: every step uploads the queries from
@@ -637,11 +640,13 @@ def bench_flat(args, rank, world, local_rank):
     ok &= bool(np.array_equal(idx[hit, 0], target[hit]))
     ok &= bool((dist[:, 0] <= dist[:, 1]).all())
     # both engines must return the same arrays
-    g.set_knn_engine(other)
-    step_device()
-    oi, od = g.knn2_fetch(nA)
+    engines_agree = True
+    for eng in (other, "tc8"):
+        g.set_knn_engine(eng)
+        step_device()
+        oi, od = g.knn2_fetch(nA)
+        engines_agree &= bool(np.array_equal(oi, idx) and np.array_equal(od, dist))
     g.set_knn_engine(primary)
-    engines_agree = bool(np.array_equal(oi, idx) and np.array_equal(od, dist))
     ok &= engines_agree
 
     parity = None
@@ -724,6 +729,8 @@ def bench_flat(args, rank, world, local_rank):
             "roofline": roofline,
             "engines": engines,
             "engines_agree": engines_agree,
+            "engines_note": "tc = K1t4 (fp4 operands, kind::mxf4), tc8 = K1t (int8 operands, kind::i8), int = K1 (integer pipes); "
+                            "identical result arrays",
             "parity_vs_oracle_sample": parity,
             "result_check": "planted matches found, d0<=d1, engines agree, %d queries bit-equal to the oracle over "
                             "all %d rows" % (PARITY_QUERIES, N_MAP) if ok else "FAILED",
@@ -752,24 +759,73 @@ def bench_flat(args, rank, world, local_rank):
 
 # --------------------------------------------------------------------------- C1 on its own
 def bench_c1(args, rank, world, local_rank):
-    """Replicas only: every rank localises the same query; rank 0 reports N x its rate."""
-    from sfmlocalization_b200.gpu import HuloGpu
+    """One GPU: one query at a time through hulo_engine_localize.  N > 1: the same query with the VIEWS
+    sharded over the ranks (hulo_engine_localize_sharded: every rank matches its range of views, one
+    all-gather of the surviving matches, every rank finishes the query); a latency play, so the value
+    is the rate of ONE query stream, and rank 0 checks that the sharded result is bit-identical to its
+    own single-GPU result."""
+    from sfmlocalization_b200.gpu import HuloGpu, LocalizeEngine
     g = HuloGpu(local_rank)
+    id_path = None
+    if world > 1:
+        uid, id_path = rendezvous_id(rank, world, HuloGpu.comm_unique_id)
+        g.comm_init(uid, rank, world)
     sampler = ClockSampler(local_rank); sampler.start()
-    loc = localize_bench(g, with_cpu=(rank == 0 and not args.no_cpu_baseline), reps=max(args.steps, 10))
+    if world == 1:
+        loc = localize_bench(g, with_cpu=not args.no_cpu_baseline, reps=max(args.steps, 10))
+        value, ms, steps, extra = loc["localizations_per_s"], loc["ms_per_query"], max(args.steps, 10), {}
+    else:
+        sc = c1_scene()
+        eng = LocalizeEngine(g, sc["rows"], sc["seg_offsets"], sc["obs_view"], sc["obs_feat"], sc["obs_landmark"],
+                             sc["landmark_X"], sc["K"], ratio=0.6)
+        for k in range(5):
+            eng.localize_sharded(sc["q_desc"], sc["q_xy"], seed=k)
+        steps = max(args.steps, 20)
+        wall, stages = [], []
+        for k in range(steps):
+            g.comm_barrier()
+            t0 = time.perf_counter()
+            r = eng.localize_sharded(sc["q_desc"], sc["q_xy"], seed=100 + k)
+            dt = (time.perf_counter() - t0) * 1e3
+            wall.append(g.comm_max(dt))
+            stages.append(r["times_ms"])
+        single = eng.localize(sc["q_desc"], sc["q_xy"], seed=100 + steps - 1)        # the same seed on one GPU
+        same = bool(np.array_equal(single["corr_qfeat"], r["corr_qfeat"]) and
+                    np.array_equal(single["corr_landmark"], r["corr_landmark"]) and
+                    np.array_equal(single["inliers"], r["inliers"]) and np.array_equal(single["R"], r["R"]) and
+                    np.array_equal(single["center"], r["center"]))
+        same = bool(-g.comm_max(-float(same)) > 0.5)                                  # on every rank
+        eng.close()
+        ms = float(np.median(wall))
+        st = np.median(np.array(stages), axis=0)
+        value = 1e3 / ms
+        loc = {"workload": WORKLOAD_NAMES["c1"], "ms_per_query": ms, "localizations_per_s": value,
+               "stage_ms": {"putMatch_incl_exchange": float(st[0]), "assembly": float(st[1]), "PnP": float(st[2])},
+               "localized": bool(r["localized"]), "centre_error_m": float(np.linalg.norm(r["center"] - sc["center"]))}
+        extra = {"sharded_equals_single_gpu": same}
     clocks = sampler.stop()
+    if world > 1:
+        g.comm_barrier()
     g.close()
+    if rank == 0 and id_path and os.path.exists(id_path):
+        os.remove(id_path)
     if rank == 0:
-        v = loc["localizations_per_s"] * world
-        print(json.dumps({"metric": "query_localizations_per_s", "value": v, "unit": "localizations/s", "n_gpus": world,
-                          "steps": max(args.steps, 10), "warmup": 3, "ms_per_step": loc["ms_per_query"],
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 / f32",
-                          "data": "synthetic", "config": {"workload": WORKLOAD_NAMES["c1"], "sharding": "replicas only"},
-                          "e2e": {"value": v, "unit": "localizations/s", "h2d_bytes_per_step": 2000 * 64 + 2000 * 16,
-                                  "d2h_bytes_per_step": 96,
-                                  "inputs": "query descriptors and keypoints from host memory, pose back, every query"},
-                          "gpu_launches": 10, "clocks": clocks, "localize": loc,
-                          "cpu_baseline": loc.get("cpu_baseline")}))
+        line = {"metric": "query_localizations_per_s", "value": value, "unit": "localizations/s", "n_gpus": world,
+                "steps": steps, "warmup": 3 if world == 1 else 5, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "fp4 / f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD_NAMES["c1"],
+                           "sharding": "single GPU" if world == 1 else
+                                       "views of the map sharded over %d ranks for ONE query; one all-gather of the surviving "
+                                       "matches (12 bytes each), resection on every rank" % world},
+                "e2e": {"value": value, "unit": "localizations/s", "h2d_bytes_per_step": 2000 * 64 + 2000 * 16,
+                        "d2h_bytes_per_step": 96,
+                        "inputs": "query descriptors and keypoints from host memory, pose back, every query"},
+                "gpu_launches": 11, "clocks": clocks, "localize": loc, "cpu_baseline": loc.get("cpu_baseline")}
+        line.update(extra)
+        print(json.dumps(line))
+        if extra and not extra["sharded_equals_single_gpu"]:
+            sys.exit(1)
 
 
 # --------------------------------------------------------------------------- C2: pair-sharded matching

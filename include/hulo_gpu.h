@@ -81,6 +81,7 @@ uint64_t hulo_launch_count(const hulo_gpu *h);
 #define HULO_KNN_INT 0
 #define HULO_KNN_TC 1
 #define HULO_KNN_AUTO 2
+#define HULO_KNN_TC8 3 /* HULO_KNN_TC with int8 operands (K1t): kept for cross-checking the 4-bit form */
 int hulo_gpu_set_knn_engine(hulo_gpu *h, int engine);
 int hulo_gpu_knn_engine(const hulo_gpu *h);
 

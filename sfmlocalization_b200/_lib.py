@@ -10,7 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libhulo_gpu.so")
 OK, ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_CAPACITY = 0, 1, 2, 3, 4
 PAIR_ONE_TO_ONE, PAIR_DROP_LAST = 1, 2
 PAIR_REFERENCE = PAIR_ONE_TO_ONE | PAIR_DROP_LAST
-KNN_INT, KNN_TC, KNN_AUTO = 0, 1, 2
+KNN_INT, KNN_TC, KNN_AUTO, KNN_TC8 = 0, 1, 2, 3
 DIST_NONE = 2**31 - 1
 IDX_NONE = -1
 

@@ -207,28 +207,25 @@ static int tc_build_seg_image4(hulo_gpu *h, const uint4 *rows, const uint64_t *s
     return HULO_OK;
 }
 
-// Item-mode engine: 4-bit (K1t4) unless HULO_TC_BITS=8.
-static bool tc_items_four() {
-    static const int bits = env_int("HULO_TC_BITS", 4);
-    return bits != 8;
-}
+// Operand width of the tensor-core engine on this context: 4-bit (K1t4) unless HULO_KNN_TC8 / HULO_TC_BITS=8.
+static bool tc_items_four(const hulo_gpu *h) { return h->tc_bits != 8; }
 // A searcher tile / database range of a segmented image in the units of the engine: image tiles of
 // 128 rows (K1t) or groups of 8 rows (K1t4); `first[s]` = tile0 or grp0 of the segment.
-static inline uint32_t tc_unit_of_row(const uint32_t *first, size_t s, uint64_t row_in_seg) {
-    return first[s] + (uint32_t)(row_in_seg / (tc_items_four() ? 8u : kTcTileRows));
+static inline uint32_t tc_unit_of_row(const hulo_gpu *h, const uint32_t *first, size_t s, uint64_t row_in_seg) {
+    return first[s] + (uint32_t)(row_in_seg / (tc_items_four(h) ? 8u : kTcTileRows));
 }
 
 // The cached segmented image of a resident table.
 static int tc_seg_image_for_db(hulo_gpu *h, const hulo_db *db, const uint8_t **img, const uint32_t **tile0) {
     hulo_gpu::TcImage *e = nullptr;
-    const int kind = tc_items_four() ? hulo_gpu::kTcSeg4 : hulo_gpu::kTcSeg8;
+    const int kind = tc_items_four(h) ? hulo_gpu::kTcSeg4 : hulo_gpu::kTcSeg8;
     for (auto &x : h->tc_images) if (x.rows == db->rows && x.kind == kind) e = &x;
     if (!e) {
         h->tc_images.push_back(hulo_gpu::TcImage{db->rows, 0, false, kind, {}, DevBuf{}});
         e = &h->tc_images.back();
     }
     if (!e->valid || e->n != db->n || e->tile0.size() != db->seg.size()) {
-        int rc = tc_items_four() ? tc_build_seg_image4(h, db->rows, db->seg.data(), db->seg.size() - 1, e->img, e->tile0)
+        int rc = tc_items_four(h) ? tc_build_seg_image4(h, db->rows, db->seg.data(), db->seg.size() - 1, e->img, e->tile0)
                                  : tc_build_seg_image(h, db->rows, db->seg.data(), db->seg.size() - 1, e->img, e->tile0);
         if (rc != HULO_OK) return rc;
         e->n = db->n;
@@ -255,7 +252,7 @@ static int run_items_tc(hulo_gpu *h, const uint8_t *imgA, const uint8_t *imgB, c
     tp.n_items = (uint32_t)items.size();
     tp.partial = h->partial.as<uint2>();
     tp.cluster = 1;
-    if (tc_items_four()) HULO_CUDA(knn2_tc4_launch(tp, h->sm_count, h->stream));
+    if (tc_items_four(h)) HULO_CUDA(knn2_tc4_launch(tp, h->sm_count, h->stream));
     else HULO_CUDA(knn2_tc_launch(tp, h->sm_count, h->stream));
     h->launches++;
     return HULO_OK;
@@ -264,8 +261,7 @@ static int run_items_tc(hulo_gpu *h, const uint8_t *imgA, const uint8_t *imgB, c
 // K1t for a flat searcher table against a flat database: same partial-key format as K1.  The 4-bit
 // form (K1t4, kind::mxf4) by default; HULO_TC_BITS=8 selects the int8 form (K1t, kind::i8).
 static int run_flat_k1_tc(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t nB, FlatRun *run) {
-    static const int bits = env_int("HULO_TC_BITS", 4);
-    const bool four = bits != 8;
+    const bool four = tc_items_four(h);
     const int kind = four ? hulo_gpu::kTcFlat4 : hulo_gpu::kTcFlat8;
     uint32_t n_mtiles = 0, n_chunks = 0, rpc = 0;
     if (four) knn2_tc4_plan(nA, nB, h->sm_count, &n_mtiles, &n_chunks, &rpc);
@@ -455,6 +451,7 @@ int hulo_gpu_create(int device, hulo_gpu **out) {
         }
     }
     {
+        h->tc_bits = env_int("HULO_TC_BITS", 4) == 8 ? 8 : 4;
         const char *eng = getenv("HULO_KNN_ENGINE");
         if (eng && (!strcmp(eng, "tc") || !strcmp(eng, "1"))) h->knn_engine = HULO_KNN_TC;
         else if (eng && (!strcmp(eng, "int") || !strcmp(eng, "0"))) h->knn_engine = HULO_KNN_INT;
@@ -470,11 +467,16 @@ int hulo_gpu_create(int device, hulo_gpu **out) {
 
 int hulo_gpu_set_knn_engine(hulo_gpu *h, int engine) {
     HULO_ARG(h != nullptr, "null context");
-    HULO_ARG(engine == HULO_KNN_INT || engine == HULO_KNN_TC || engine == HULO_KNN_AUTO, "unknown engine");
-    h->knn_engine = engine;
+    HULO_ARG(engine == HULO_KNN_INT || engine == HULO_KNN_TC || engine == HULO_KNN_AUTO || engine == HULO_KNN_TC8,
+             "unknown engine");
+    if (engine == HULO_KNN_TC8) { h->knn_engine = HULO_KNN_TC; h->tc_bits = 8; }
+    else { h->knn_engine = engine; if (engine == HULO_KNN_TC) h->tc_bits = 4; }
     return HULO_OK;
 }
-int hulo_gpu_knn_engine(const hulo_gpu *h) { return h ? h->knn_engine : -1; }
+int hulo_gpu_knn_engine(const hulo_gpu *h) {
+    if (!h) return -1;
+    return h->knn_engine == HULO_KNN_TC && h->tc_bits == 8 ? HULO_KNN_TC8 : h->knn_engine;
+}
 
 void hulo_comm_destroy_internal(hulo_gpu *h);
 
@@ -713,7 +715,7 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
         const uint32_t *tile0 = nullptr;
         int rc = tc_seg_image_for_db(h, map, &imgA, &tile0);
         if (rc != HULO_OK) return rc;
-        rc = tc_image_for(h, h->stageB.as<uint4>(), nq, tc_items_four() ? hulo_gpu::kTcFlat4 : hulo_gpu::kTcFlat8,
+        rc = tc_image_for(h, h->stageB.as<uint4>(), nq, tc_items_four(h) ? hulo_gpu::kTcFlat4 : hulo_gpu::kTcFlat8,
                           h->tc_scratchB, &imgB);
         if (rc != HULO_OK) return rc;
         n_chunks = 1; rows_per_chunk = kMaxChunkRows;
@@ -723,7 +725,7 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
             const uint64_t rows = map->seg[s + 1] - map->seg[s];
             for (uint64_t t0 = 0; t0 < rows; t0 += kTcTileRows) {
                 TcItem it{};
-                it.a_tile = tc_unit_of_row(tile0, s, t0);
+                it.a_tile = tc_unit_of_row(h, tile0, s, t0);
                 it.a_rows = (uint32_t)std::min<uint64_t>(kTcTileRows, rows - t0);
                 it.b_tile0 = 0;
                 it.b_rows = (uint32_t)nq;
@@ -896,7 +898,7 @@ int hulo_match_to_queries(hulo_gpu *h, const hulo_db *map, const uint32_t *views
     if (use_tc) {
         int rc = tc_seg_image_for_db(h, map, &imgA, &tile0_map);
         if (rc != HULO_OK) return rc;
-        rc = tc_items_four() ? tc_build_seg_image4(h, h->stageB.as<uint4>(), q_offsets, n_queries, h->tc_scratchB, tile0_q)
+        rc = tc_items_four(h) ? tc_build_seg_image4(h, h->stageB.as<uint4>(), q_offsets, n_queries, h->tc_scratchB, tile0_q)
                              : tc_build_seg_image(h, h->stageB.as<uint4>(), q_offsets, n_queries, h->tc_scratchB, tile0_q);
         if (rc != HULO_OK) return rc;
         imgB = h->tc_scratchB.as<uint8_t>();
@@ -945,7 +947,7 @@ int hulo_match_to_queries(hulo_gpu *h, const hulo_db *map, const uint32_t *views
                     for (size_t ql = 0; ql < nb; ++ql) {
                         const size_t q = members[ql];
                         TcItem it{};
-                        it.a_tile = tc_unit_of_row(tile0_map, s, t0);
+                        it.a_tile = tc_unit_of_row(h, tile0_map, s, t0);
                         it.a_rows = (uint32_t)std::min<uint64_t>(kTcTileRows, rows - t0);
                         it.b_tile0 = tile0_q[q];
                         it.b_rows = (uint32_t)(q_offsets[q + 1] - q_offsets[q]);
@@ -1102,7 +1104,7 @@ int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size
             if (!skip && use_tc) {
                 for (uint64_t t0 = 0; t0 < nI; t0 += kTcTileRows) {
                     TcItem it{};
-                    it.a_tile = tc_unit_of_row(tile0, I, t0);
+                    it.a_tile = tc_unit_of_row(h, tile0, I, t0);
                     it.a_rows = (uint32_t)std::min<uint64_t>(kTcTileRows, nI - t0);
                     it.b_tile0 = tile0[J];
                     it.b_rows = (uint32_t)nJ;

@@ -104,6 +104,7 @@ struct hulo_gpu {
     // K1 arithmetic of the flat searches: HULO_KNN_INT = integer pipes (knn2.cu), HULO_KNN_TC = int8
     // contraction on the tensor cores (knn2_tc.cu), HULO_KNN_AUTO = K1t for large searches
     int knn_engine = HULO_KNN_AUTO;
+    int tc_bits = 4;           // operand width of the tensor-core engine: 4 (K1t4, kind::mxf4) or 8 (K1t, kind::i8)
     // tile images of K1t: one per registered table (built on first use, dropped when the table
     // changes), and two scratch images for staged rows
     // kind: kTcFlat8 = int8 image of a flat table, kTcSeg8 = the segmented int8 form (every segment

@@ -123,14 +123,15 @@ class HuloGpu:
 
     # -- K1
     def set_knn_engine(self, engine):
-        """'int' (XOR + popcount on the integer pipes), 'tc' (int8 contraction on the tensor cores) or
-        'auto' (the default: tc for large searches); all exact.  Applies to the flat searches."""
-        code = {"int": _lib.KNN_INT, "tc": _lib.KNN_TC, "auto": _lib.KNN_AUTO}[engine]
+        """'int' (XOR + popcount on the integer pipes), 'tc' (fp4 contraction on the tensor cores), 'tc8'
+        (its int8 form) or 'auto' (the default: tc for large searches); all exact."""
+        code = {"int": _lib.KNN_INT, "tc": _lib.KNN_TC, "auto": _lib.KNN_AUTO, "tc8": _lib.KNN_TC8}[engine]
         check(self.lib.hulo_gpu_set_knn_engine(self.h, code))
 
     @property
     def knn_engine(self):
-        return {_lib.KNN_INT: "int", _lib.KNN_TC: "tc", _lib.KNN_AUTO: "auto"}[int(self.lib.hulo_gpu_knn_engine(self.h))]
+        return {_lib.KNN_INT: "int", _lib.KNN_TC: "tc", _lib.KNN_AUTO: "auto",
+                _lib.KNN_TC8: "tc8"}[int(self.lib.hulo_gpu_knn_engine(self.h))]
 
     def knn2(self, A, B, fetch=True):
         """A, B: DescriptorDb.  Returns (idx2, dist2) int32 nA x 2, or None when fetch=False."""

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 INT_MAX = 2**31 - 1
 
 
-@pytest.fixture(autouse=True, params=["int", "tc"])
+@pytest.fixture(autouse=True, params=["int", "tc", "tc8"])
 def engine(request, gpu):
     """Every test of this module runs on both arithmetic engines of the flat search: the integer
     pipes (K1) and the int8 tensor-core contraction (K1t).  Same bit-exact expectations."""

@@ -8,7 +8,7 @@ from sfmlocalization_b200 import _lib, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["int", "tc"])
+@pytest.fixture(autouse=True, params=["int", "tc", "tc8"])
 def engine(request, gpu):
     """Every test of this module runs with the 2-NN arithmetic on the integer pipes (K1) and on the
     tensor cores (K1t, item mode): same bit-exact expectations."""

@@ -683,7 +683,7 @@ def bench_flat(args, rank, world, local_rank):
         tc_bits = 8 if os.environ.get("HULO_TC_BITS", "4") == "8" else 4
         tc_mult = 4.0 if tc_bits == 4 else 2.0      # nominal dense rate of the operand type over bf16
         tc_tops = tc_gpu * 1024.0 / 1e3             # 1 dist = 512 multiply-adds = 1024 ops
-        tprof = read_json(os.path.join(ROOT, "profiles", "k1t_traffic.json"), {}) or {}
+        tprof = read_json(os.path.join(ROOT, "profiles", "k1t4_traffic.json" if tc_bits == 4 else "k1t_traffic.json"), {}) or {}
         tc_roof = {"bound": "tensor", "achieved": tc_tops, "peak": tc_mult * bf16_s, "unit": "TOP/s",
                    "frac": tc_tops / (tc_mult * bf16_s),
                    "peak_source": "%g x bf16_tflops_sustained of MEASURED_PEAKS.json: no %s GEMM was measured on this "

@@ -11,12 +11,15 @@
 // tile (224 rows, 56 KB, the whole K of it: one ring stage) are one bulk copy each.
 // TMEM: accumulators at columns 0 and 256 (224 used of each), scale factors at column 480.
 #include "knn2_tc.cuh"
+#include "tc_ptx.cuh"
 
 #include <algorithm>
 
 namespace hulo {
 
 namespace {
+
+using namespace tcptx;
 
 constexpr uint32_t kN4 = 224;                     // database rows per accumulator tile, flat mode
 constexpr uint32_t kN4Items = 192;                // item mode: narrower tiles leave room for a second searcher tile
@@ -37,40 +40,6 @@ constexpr float kThrNoneF = -1024.0f;
 constexpr float kDotPastEnd = -514.0f;          // 512 - 2 * 513
 constexpr uint32_t kKeyPastEnd = 513u << kKeyIdxBits;
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-        "l"(src_gmem), "r"(bytes), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
 // D[tmem] (+)= A[smem] * B[smem]^T, e2m1 x e2m1 with one ue8m0 scale per 32 elements -> fp32; M = 128, K = 64
 __device__ __forceinline__ void tc_mma_mxf4(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                             uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t accumulate) {
@@ -82,10 +51,6 @@ __device__ __forceinline__ void tc_mma_mxf4(uint32_t tmem_d, uint64_t desc_a, ui
         "}\n" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
         : "memory");
-}
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
 // cute::UMMA::InstrDescriptorBlockScaled: A = B = e2m1 (MXF4Format 1), K-major, N, ue8m0 scales, M = 128, K = 64
 template <uint32_t N>

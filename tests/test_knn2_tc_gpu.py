@@ -82,3 +82,50 @@ def test_engines_agree_at_scale(gpu):
     assert np.array_equal(it, ii) and np.array_equal(dt, di)
     hit = target >= 0
     assert np.array_equal(it[hit, 0], target[hit])
+
+
+def test_random_shapes_all_engines_agree(gpu):
+    """Random table sizes (not aligned to any tile, group or chunk size): the three engines return
+    identical arrays.  The integer engine is the one checked against the oracle everywhere else."""
+    rng = np.random.default_rng(77)
+    for trial in range(10):
+        nA = int(rng.integers(1, 3000)); nB = int(rng.integers(1, 300000))
+        A, B, _ = synth.descriptor_sets(nA, nB, 1000 + trial)
+        gpu.set_knn_engine("int")
+        want = gpu.knn2_host(A, B)
+        for eng in ("tc", "tc8"):
+            gpu.set_knn_engine(eng)
+            got = gpu.knn2_host(A, B)
+            assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), (eng, nA, nB)
+
+
+def test_ragged_segments_item_mode(gpu, orc):
+    """Views of every size from empty to a few tiles (segments aligned to nothing), a query that is
+    not a multiple of the tile width: the item mode of both tensor-core forms against the oracle."""
+    rng = np.random.default_rng(5)
+    sizes = [0, 1, 2, 7, 8, 9, 127, 128, 129, 191, 192, 193, 223, 224, 225, 255, 256, 257, 700, 1031]
+    rows = synth.random_rows(int(np.sum(sizes)), 31)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    query, _ = synth.plant_matches(synth.random_rows(777, 32), rows, 33, frac=0.6)
+    db = gpu.db(rows, off)
+    try:
+        for eng in ("tc", "tc8"):
+            gpu.set_knn_engine(eng)
+            m = gpu.match_to_query(db, query, 0.8)
+            k = 0
+            for v, n_v in enumerate(sizes):
+                a = rows[int(off[v]):int(off[v + 1])]
+                oi, oj, od = orc.match_view_to_query(a, query, 0.8)
+                n = len(oi)
+                assert m["view_counts"][v] == n, (eng, v)
+                assert np.array_equal(m["i"][k:k + n], oi) and np.array_equal(m["j"][k:k + n], oj)
+                assert np.array_equal(m["d0"][k:k + n], od)
+                k += n
+            assert k == len(m["i"]) and k > 100
+            pairs = [(18, 19), (19, 18), (5, 18), (17, 16), (3, 19), (0, 18)]
+            o, pi, pj = gpu.match_pairs(db, pairs, 0.8)
+            for p, (I, J) in enumerate(pairs):
+                wi, wj = orc.match_pair(rows[int(off[I]):int(off[I + 1])], rows[int(off[J]):int(off[J + 1])], 0.8)
+                assert np.array_equal(pi[int(o[p]):int(o[p + 1])], wi) and np.array_equal(pj[int(o[p]):int(o[p + 1])], wj), (eng, I, J)
+    finally:
+        db.free()

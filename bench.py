@@ -729,7 +729,8 @@ def bench_flat(args, rank, world, local_rank):
             "roofline": roofline,
             "engines": engines,
             "engines_agree": engines_agree,
-            "engines_note": "tc = K1t4 (fp4 operands, kind::mxf4), tc8 = K1t (int8 operands, kind::i8), int = K1 (integer pipes); "
+            "engines_note": "tc = K1t4 (fp4 operands, kind::mxf4), tc8 = K1t (int8 operands, kind::i8), int = K1 (integer pipes, "
+                            "the configuration BASELINE.json:north_star prescribes; --engine int makes it the headline); "
                             "identical result arrays",
             "parity_vs_oracle_sample": parity,
             "result_check": "planted matches found, d0<=d1, engines agree, %d queries bit-equal to the oracle over "

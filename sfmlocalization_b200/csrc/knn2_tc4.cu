@@ -86,58 +86,62 @@ constexpr uint32_t idesc4() { return (1u << 7) | (1u << 10) | ((N >> 3) << 17) |
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
-__device__ __forceinline__ uint32_t umin3(uint32_t a, uint32_t b, uint32_t c) { return min(min(a, b), c); }
 // two sorted key pairs -> the smallest two of the four
 __device__ __forceinline__ void merge2(uint32_t &p0, uint32_t &p1, uint32_t q0, uint32_t q1) {
     const uint32_t m = max(p0, q0);
     p0 = min(p0, q0);
-    p1 = umin3(m, p1, q1);
+    p1 = min(min(m, p1), q1);
+}
+// the same on two 16-bit keys per register (SASS VIMNMX.U16x2 / VIMNMX3.U16x2)
+__device__ __forceinline__ void merge2x2(uint32_t &p0, uint32_t &p1, uint32_t q0, uint32_t q1) {
+    const uint32_t m = __vmaxu2(p0, q0);
+    p0 = __vminu2(p0, q0);
+    p1 = __vimin3_u16x2(m, p1, q1);
 }
 
 // 32 accumulator columns of this thread's searcher row.  v[e] = 512 - 2 * distance to database row
-// (row0 + e) of the range, an exact integer in fp32.  Fast path per 16 columns: their maximum against
-// the dot of the row's current second best (columns arrive in ascending row order, so a column that
-// only ties the second best loses on the index and a strict compare is exact).  Slow path: the packed
-// keys of all 16 columns and a branch-free tournament for their smallest two (log depth, so a single
-// warp per sub-partition keeps its ALU busy; short database ranges take this path for most groups).
+// (row0 + e) of the range, an exact integer in fp32.  Fast path: the maximum of the 32 against the dot
+// of the row's current second best (columns arrive in ascending row order, so a column that only ties
+// the second best loses on the index and a strict compare is exact).  Slow path, branch-free: a 16-bit
+// key (distance << 5 | e) per column, two to a register, and a tournament for the smallest two of
+// each 16-bit lane with packed min/max -- log depth, 1.9 ALU instructions per column, which is what
+// short database ranges (thresholds restart with every item) spend most of their epilogue in.
 // Columns past the end of a range are given the dot kDotPastEnd by the caller ("distance 513"): they
 // lose against every real row and are turned into "none" when the item's keys are written.
 __device__ __forceinline__ void scan32(const float (&v)[32], uint32_t row0, uint32_t &best0, uint32_t &best1, float &thr) {
-    float gm[2];
+    float m[11];
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-        const float *w = &v[16 * g];
-        const float m0 = fmax3(w[0], w[1], w[2]), m1 = fmax3(w[3], w[4], w[5]), m2 = fmax3(w[6], w[7], w[8]);
-        const float m3 = fmax3(w[9], w[10], w[11]), m4 = fmax3(w[12], w[13], w[14]);
-        gm[g] = fmaxf(fmax3(m0, m1, m2), fmax3(m3, m4, w[15]));
+    for (int i = 0; i < 10; ++i) m[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    m[10] = fmaxf(v[30], v[31]);
+    const float bm = fmax3(fmax3(m[0], m[1], m[2]), fmax3(m[3], m[4], m[5]),
+                           fmax3(fmax3(m[6], m[7], m[8]), m[9], m[10]));
+    if (bm <= thr) return;
+    // key16(e) = distance * 32 + e = 8192 + e - 16 v, read off the low mantissa bits of
+    // fma(v, -16, 2^23 + 8192 + e) (exact: the value is an integer in [2^23, 2^24)); columns e and
+    // e + 16 share a register: (bits(e + 16) << 16) + bits(e) leaves key(e) in the low half and
+    // key(e + 16) + 0x4B00 (the exponent bits of the low word, a constant) in the high half
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t ta = (uint32_t)__float_as_int(fmaf(v[i], -16.0f, 8388608.0f + 8192.0f + (float)i));
+        const uint32_t tb = (uint32_t)__float_as_int(fmaf(v[i + 16], -16.0f, 8388608.0f + 8192.0f + (float)(i + 16)));
+        pk[i] = tb * 65536u + ta;
     }
-    if (fmaxf(gm[0], gm[1]) <= thr) return;
+    uint32_t lo[8], hi[8];
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-        const float *w = &v[16 * g];
-        if (gm[g] > thr) {
-            // key = (512 - v) << 21 | column: v + 1.5 * 2^23 has the integer v in its low mantissa bits
-            // (0x4B400000 + v as a bit pattern), so one IMAD by -2^21 and a constant give the key modulo
-            // 2^32, which is the key (it fits 32 bits); the group's first column is a multiple of 16
-            const uint32_t kb = ((0x4B400000u + 512u) << (kKeyIdxBits - 1)) + (row0 + 16u * g);
-            uint32_t k[16];
+    for (int i = 0; i < 8; ++i) { lo[i] = __vminu2(pk[i], pk[i + 8]); hi[i] = __vmaxu2(pk[i], pk[i + 8]); }
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const uint32_t ti = (uint32_t)__float_as_int(w[e] + 12582912.0f);
-                k[e] = (ti * (0u - (1u << (kKeyIdxBits - 1))) + kb) | (uint32_t)e;
-            }
-            uint32_t lo[8], hi[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { lo[i] = min(k[2 * i], k[2 * i + 1]); hi[i] = max(k[2 * i], k[2 * i + 1]); }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) merge2(lo[i], hi[i], lo[i + 4], hi[i + 4]);
-            merge2(lo[0], hi[0], lo[2], hi[2]);
-            merge2(lo[1], hi[1], lo[3], hi[3]);
-            merge2(lo[0], hi[0], lo[1], hi[1]);
-            merge2(best0, best1, lo[0], hi[0]);
-            thr = best1 == kKeyNone ? kThrNoneF : (float)(512 - 2 * (int32_t)(best1 >> kKeyIdxBits));
-        }
-    }
+    for (int i = 0; i < 4; ++i) merge2x2(lo[i], hi[i], lo[i + 4], hi[i + 4]);
+    merge2x2(lo[0], hi[0], lo[2], hi[2]);
+    merge2x2(lo[1], hi[1], lo[3], hi[3]);
+    merge2x2(lo[0], hi[0], lo[1], hi[1]);
+    // the best two of columns 0..15 (low halves) and of 16..31 (high halves) as full keys
+    auto full = [&](uint32_t k16) { return ((k16 >> 5) << kKeyIdxBits) + row0 + (k16 & 31u); };
+    uint32_t a0 = full(lo[0] & 0xFFFFu), a1 = full(hi[0] & 0xFFFFu);
+    const uint32_t b0 = full((lo[0] >> 16) - 0x4B00u), b1 = full((hi[0] >> 16) - 0x4B00u);
+    merge2(a0, a1, b0, b1);
+    merge2(best0, best1, a0, a1);
+    thr = best1 == kKeyNone ? kThrNoneF : (float)(512 - 2 * (int32_t)(best1 >> kKeyIdxBits));
 }
 
 struct TcWork4 {

@@ -588,17 +588,9 @@ def bench_flat(args, rank, world, local_rank):
     clocks = sampler.stop()
     value = total_dist * args.steps / (ms * 1e-3) / 1e9
     exchange = g.exchange_kind
-    o_steps = max(3, min(args.steps, 10))
-    o_ms, _ = timed_device(other, o_steps, 3)
-    engines = {primary: {"value": value, "ms_per_step": ms / args.steps},
-               other: {"value": total_dist * o_steps / (o_ms * 1e-3) / 1e9, "ms_per_step": o_ms / o_steps}}
-    # the int8 form of the tensor-core engine (K1t), for the record
-    t8_ms, _ = timed_device("tc8", o_steps, 3)
-    engines["tc8"] = {"value": total_dist * o_steps / (t8_ms * 1e-3) / 1e9, "ms_per_step": t8_ms / o_steps}
-    g.set_knn_engine(primary)
-
     # ---- end to end through the C-ABI with host buffers: every step uploads the queries from
-    # pinned host memory and reads the top-2 back; the map table is engine state (resident)
+    # pinned host memory and reads the top-2 back; the map table is engine state (resident).  Timed
+    # right after the device-resident loop, before the other engines heat the board
     pin_A = PinnedArray(A.shape, np.uint8); pin_A.array[...] = A
     pin_i = PinnedArray((nA, 2), np.int32); pin_d = PinnedArray((nA, 2), np.int32)
     lib = g.lib
@@ -616,14 +608,26 @@ def bench_flat(args, rank, world, local_rank):
 
     step_e2e()
     g.comm_barrier() if world > 1 else g.synchronize()
+    e2e_sampler = ClockSampler(local_rank)
+    e2e_sampler.start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
     g.synchronize()
     e2e_s = time.perf_counter() - t0
+    e2e_clocks = e2e_sampler.stop()
     e2e_s = g.comm_max(e2e_s) if world > 1 else e2e_s
     e2e_value = total_dist * args.steps / e2e_s / 1e9
     idx, dist = pin_i.array.copy(), pin_d.array.copy()
+
+    o_steps = max(3, min(args.steps, 10))
+    o_ms, _ = timed_device(other, o_steps, 3)
+    engines = {primary: {"value": value, "ms_per_step": ms / args.steps},
+               other: {"value": total_dist * o_steps / (o_ms * 1e-3) / 1e9, "ms_per_step": o_ms / o_steps}}
+    # the int8 form of the tensor-core engine (K1t), for the record
+    t8_ms, _ = timed_device("tc8", o_steps, 3)
+    engines["tc8"] = {"value": total_dist * o_steps / (t8_ms * 1e-3) / 1e9, "ms_per_step": t8_ms / o_steps}
+    g.set_knn_engine(primary)
 
     # ---- cold variant: map shard uploaded from host inside the timed call (hulo_knn2_host)
     cold = None
@@ -720,9 +724,12 @@ def bench_flat(args, rank, world, local_rank):
             "data": "synthetic",
             "config": workload_config(world, primary, exchange),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(nA * 64),
-                    "d2h_bytes_per_step": int(nA * 16),
+                    "d2h_bytes_per_step": int(nA * 16), "clocks": e2e_clocks,
                     "inputs": "queries H2D from pinned memory + top-2 D2H every step; map table resident "
-                              "(uploaded once at engine construction, as LocalizeEngine loads its map once)"},
+                              "(uploaded once at engine construction, as LocalizeEngine loads its map once)",
+                    "note": "wall clock around the C-ABI calls.  With the tensor-core engine the board sits at its "
+                            "1 kW cap, and the copies and synchronisations between steps are idle time the next "
+                            "launch gets back as clock, so this rate can exceed the back-to-back device-resident one"},
             "e2e_cold": cold,
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -103,6 +103,15 @@ def localize_views_nccl(rank, world):
     eng.set_guided_matching(True)
     got.append(eng.localize_sharded(sc["q_desc"], sc["q_xy"], seed=7))
     one = eng.localize_sharded(sc["q_desc"], sc["q_xy"], views=[3], seed=8)     # fewer views than ranks
+    # the same query with the matching forced onto the tensor cores (item mode) and onto the integer pipes
+    eng.configure_geometric(False)
+    per_engine = []
+    for engine in ("tc", "int"):
+        g.set_knn_engine(engine)
+        per_engine.append(eng.localize_sharded(sc["q_desc"], sc["q_xy"], seed=5))
+    g.set_knn_engine("auto")
+    got += per_engine
+    want += [want[0], want[0]]
     g.comm_barrier()
     ok = all(w["localized"] and a["localized"] and np.array_equal(a["center"], w["center"]) and
              np.array_equal(a["R"], w["R"]) and np.array_equal(a["corr_qfeat"], w["corr_qfeat"]) and
@@ -148,6 +157,11 @@ def main():
         dA2 = g.db(A2)
         i2, d2 = g.knn2_sharded(dA2, dB, lo)
         dA2.free()
+        # every arithmetic engine behind the same exchange: identical arrays
+        for eng in ("int", "tc", "tc8"):
+            g.set_knn_engine(eng)
+            results.append(g.knn2_sharded(dA, dB, lo))
+        g.set_knn_engine("auto")
         for (i_, d_) in results:
             assert np.array_equal(i_, results[0][0]) and np.array_equal(d_, results[0][1])
         assert np.array_equal(i2[:NA], results[0][0]) and np.array_equal(i2[-NA:], results[0][0])

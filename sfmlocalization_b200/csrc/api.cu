@@ -103,14 +103,17 @@ static FlatPlan plan_flat(const hulo_gpu *h, size_t nA, size_t nB) {
 
 // ------------------------------------------------------------- K1t tile images
 void tc_image_register(hulo_gpu *h, const void *rows) {
+    if (h->tc_qitems_key.rows == rows) h->tc_qitems_key.valid = false;
     for (auto &e : h->tc_images) if (e.rows == rows) e.valid = false;
     for (auto &e : h->tc_images) if (e.rows == rows && e.kind == hulo_gpu::kTcFlat4) return;
     h->tc_images.push_back(hulo_gpu::TcImage{rows, 0, false, hulo_gpu::kTcFlat4, {}, DevBuf{}});
 }
 void tc_image_invalidate(hulo_gpu *h, const void *rows) {
     for (auto &e : h->tc_images) if (e.rows == rows) e.valid = false;
+    if (h->tc_qitems_key.rows == rows) h->tc_qitems_key.valid = false;
 }
 void tc_image_drop(hulo_gpu *h, const void *rows) {
+    if (h->tc_qitems_key.rows == rows) h->tc_qitems_key.valid = false;
     for (size_t k = h->tc_images.size(); k-- > 0;)
         if (h->tc_images[k].rows == rows) {
             h->tc_images[k].img.release();
@@ -241,15 +244,23 @@ static bool tc_wanted(const hulo_gpu *h, uint64_t dist, uint64_t min_dist) {
     return h->knn_engine == HULO_KNN_TC || (h->knn_engine == HULO_KNN_AUTO && dist >= min_dist);
 }
 
+// K1t over an item list that is already on the device; the caller has reserved h->partial.
+static int run_items_tc_dev(hulo_gpu *h, const uint8_t *imgA, const uint8_t *imgB, const TcItem *d_items, size_t n_items);
+
 // K1t over an item list; the caller has reserved h->partial.
 static int run_items_tc(hulo_gpu *h, const uint8_t *imgA, const uint8_t *imgB, const std::vector<TcItem> &items) {
     if (items.empty()) return HULO_OK;
     HULO_CUDA(h->items.reserve(items.size() * sizeof(TcItem)));
     HULO_CUDA(cudaMemcpyAsync(h->items.ptr, items.data(), items.size() * sizeof(TcItem), cudaMemcpyHostToDevice, h->stream));
+    return run_items_tc_dev(h, imgA, imgB, h->items.as<TcItem>(), items.size());
+}
+
+static int run_items_tc_dev(hulo_gpu *h, const uint8_t *imgA, const uint8_t *imgB, const TcItem *d_items, size_t n_items) {
+    if (n_items == 0) return HULO_OK;
     TcParams tp{};
     tp.imgA = imgA; tp.imgB = imgB;
-    tp.items = h->items.as<TcItem>();
-    tp.n_items = (uint32_t)items.size();
+    tp.items = d_items;
+    tp.n_items = (uint32_t)n_items;
     tp.partial = h->partial.as<uint2>();
     tp.cluster = 1;
     if (tc_items_four(h)) HULO_CUDA(knn2_tc4_launch(tp, h->sm_count, h->stream));
@@ -491,6 +502,8 @@ void hulo_gpu_destroy(hulo_gpu *h) {
     for (auto &e : h->tc_images) e.img.release();
     h->tc_scratchA.release();
     h->tc_scratchB.release();
+    h->tc_tiles.release();
+    h->tc_qitems.release();
     h->hstage0.release();
     h->hstage1.release();
     if (h->ev_start) cudaEventDestroy(h->ev_start);
@@ -719,22 +732,38 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
                           h->tc_scratchB, &imgB);
         if (rc != HULO_OK) return rc;
         n_chunks = 1; rows_per_chunk = kMaxChunkRows;
-        std::vector<TcItem> items;
-        for (size_t v = 0; v < n_views; ++v) {
-            const size_t s = views ? views[v] : v;
-            const uint64_t rows = map->seg[s + 1] - map->seg[s];
-            for (uint64_t t0 = 0; t0 < rows; t0 += kTcTileRows) {
-                TcItem it{};
-                it.a_tile = tc_unit_of_row(h, tile0, s, t0);
-                it.a_rows = (uint32_t)std::min<uint64_t>(kTcTileRows, rows - t0);
-                it.b_tile0 = 0;
-                it.b_rows = (uint32_t)nq;
-                it.out_slot0 = sel_off[v] + t0;
-                items.push_back(it);
+        // the item list stays on the device between calls with the same map, view list and query size
+        hulo_gpu::TcItemCache &ck = h->tc_qitems_key;
+        const int bits = tc_items_four(h) ? 4 : 8;
+        const bool same_views = ck.all_views == (views == nullptr) && ck.n_views == n_views &&
+                                (views == nullptr || std::equal(views, views + n_views, ck.views.begin()));
+        if (!(ck.valid && ck.rows == map->rows && same_views && ck.nq == nq && ck.bits == bits)) {
+            std::vector<TcItem> items;
+            for (size_t v = 0; v < n_views; ++v) {
+                const size_t s = views ? views[v] : v;
+                const uint64_t rows = map->seg[s + 1] - map->seg[s];
+                for (uint64_t t0 = 0; t0 < rows; t0 += kTcTileRows) {
+                    TcItem it{};
+                    it.a_tile = tc_unit_of_row(h, tile0, s, t0);
+                    it.a_rows = (uint32_t)std::min<uint64_t>(kTcTileRows, rows - t0);
+                    it.b_tile0 = 0;
+                    it.b_rows = (uint32_t)nq;
+                    it.out_slot0 = sel_off[v] + t0;
+                    items.push_back(it);
+                }
             }
+            HULO_CUDA(h->tc_qitems.reserve(std::max<size_t>(items.size(), 1) * sizeof(TcItem)));
+            HULO_CUDA(cudaMemcpyAsync(h->tc_qitems.ptr, items.data(), items.size() * sizeof(TcItem), cudaMemcpyHostToDevice,
+                                      h->stream));
+            HULO_CUDA(cudaStreamSynchronize(h->stream));          // `items` is about to go out of scope
+            ck.rows = map->rows; ck.n_views = n_views; ck.nq = nq; ck.bits = bits;
+            ck.all_views = views == nullptr;
+            if (views) ck.views.assign(views, views + n_views); else ck.views.clear();
+            ck.n_items = items.size();
+            ck.valid = true;
         }
         HULO_CUDA(h->partial.reserve((size_t)slot_stride * sizeof(uint2)));
-        rc = run_items_tc(h, imgA, imgB, items);
+        rc = run_items_tc_dev(h, imgA, imgB, h->tc_qitems.as<TcItem>(), ck.n_items);
         if (rc != HULO_OK) return rc;
     } else {
     // items: maximal runs of views that are contiguous in the table, tiled, x chunks of the query

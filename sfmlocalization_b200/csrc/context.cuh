@@ -114,6 +114,10 @@ struct hulo_gpu {
     struct TcImage { const void *rows; size_t n; bool valid; int kind; std::vector<uint32_t> tile0; hulo::DevBuf img; };
     std::vector<TcImage> tc_images;
     hulo::DevBuf tc_scratchA, tc_scratchB, tc_tiles;
+    // item list of the last hulo_match_to_query on the device: a server asks the same (map, view list,
+    // query size) again and again, and the list (32 bytes per searcher tile) need not go up each time
+    struct TcItemCache { const void *rows = nullptr; size_t n_views = 0, nq = 0, n_items = 0; bool all_views = false; std::vector<uint32_t> views; int bits = 0; bool valid = false; } tc_qitems_key;
+    hulo::DevBuf tc_qitems;
 
     hulo::DevBuf partial;      // K1 per-item keys
     hulo::DevBuf counter;      // K1 dynamic item counter

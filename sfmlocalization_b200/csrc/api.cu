@@ -495,8 +495,14 @@ void hulo_gpu_destroy(hulo_gpu *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     hulo_comm_destroy_internal(h);
+    if (h->xstream) cudaStreamSynchronize(h->xstream);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    DevBuf *bufs[] = {&h->partial, &h->counter, &h->items, &h->knn_idx, &h->knn_dist, &h->packed, &h->gathered,
+    for (int p = 0; p < 2; ++p) {
+        if (h->ev_k1[p]) cudaEventDestroy(h->ev_k1[p]);
+        if (h->ev_x[p]) cudaEventDestroy(h->ev_x[p]);
+    }
+    if (h->xstream) cudaStreamDestroy(h->xstream);
+    DevBuf *bufs[] = {&h->partial, &h->partial_alt, &h->counter, &h->items, &h->knn_idx, &h->knn_dist, &h->packed, &h->gathered,
                       &h->stageA, &h->stageB, &h->scratch0, &h->scratch1, &h->scratch2, &h->scratch3, &h->lfact};
     for (DevBuf *b : bufs) b->release();
     for (auto &e : h->tc_images) e.img.release();
@@ -528,6 +534,7 @@ int hulo_timer_start(hulo_gpu *h) {
 }
 int hulo_timer_stop(hulo_gpu *h, float *ms) {
     HULO_ARG(h != nullptr && ms != nullptr, "null argument");
+    HULO_CUDA(join_exchange(h));
     HULO_CUDA(cudaEventRecord(h->ev_stop, h->stream));
     HULO_CUDA(cudaEventSynchronize(h->ev_stop));
     HULO_CUDA(cudaEventElapsedTime(ms, h->ev_start, h->ev_stop));
@@ -535,6 +542,7 @@ int hulo_timer_stop(hulo_gpu *h, float *ms) {
 }
 int hulo_synchronize(hulo_gpu *h) {
     HULO_ARG(h != nullptr, "null context");
+    HULO_CUDA(join_exchange(h));
     HULO_CUDA(cudaStreamSynchronize(h->stream));
     return HULO_OK;
 }
@@ -623,6 +631,7 @@ int hulo_db_download(hulo_gpu *h, const hulo_db *db, size_t first, size_t n, uin
 int hulo_knn2_fetch(hulo_gpu *h, size_t nA, int32_t *idx2, int32_t *dist2) {
     HULO_ARG(h != nullptr, "null context");
     HULO_ARG(nA <= h->last_nA, "more rows requested than the last search produced");
+    HULO_CUDA(join_exchange(h));
     if (nA > 0) {
         if (idx2) HULO_CUDA(cudaMemcpyAsync(idx2, h->knn_idx.ptr, nA * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
         if (dist2) HULO_CUDA(cudaMemcpyAsync(dist2, h->knn_dist.ptr, nA * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -634,6 +643,7 @@ int hulo_knn2_fetch(hulo_gpu *h, size_t nA, int32_t *idx2, int32_t *dist2) {
 int hulo_knn2(hulo_gpu *h, const hulo_db *A, const hulo_db *B, int32_t *idx2, int32_t *dist2) {
     HULO_ARG(h != nullptr && A != nullptr && B != nullptr, "null argument");
     HULO_CUDA(cudaSetDevice(h->device));
+    HULO_CUDA(join_exchange(h));
     int rc = run_flat(h, A->rows, A->n, B->rows, B->n, 0, false);
     if (rc != HULO_OK) return rc;
     if (idx2 || dist2) return hulo_knn2_fetch(h, A->n, idx2, dist2);
@@ -647,6 +657,7 @@ int hulo_knn2_host(hulo_gpu *h, const uint8_t *A, size_t nA, size_t strideA, con
     HULO_ARG(strideA >= 1 && strideB >= 1, "stride must be >= 1");
     HULO_ARG(nA == 0 || (idx2 != nullptr && dist2 != nullptr), "null output");
     HULO_CUDA(cudaSetDevice(h->device));
+    HULO_CUDA(join_exchange(h));
     HULO_CUDA(h->stageA.reserve(std::max<size_t>(nA, 1) * HULO_ROW_BYTES));
     HULO_CUDA(h->stageB.reserve(std::max<size_t>(nB, 1) * HULO_ROW_BYTES));
     cudaError_t e;
@@ -675,6 +686,7 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     HULO_ARG(nq <= kMaxChunkRows * 64ull, "query too large");
     *n_out = 0;
     HULO_CUDA(cudaSetDevice(h->device));
+    HULO_CUDA(join_exchange(h));
     const size_t n_seg = map->seg.size() - 1;
     if (views == nullptr) n_views = n_seg;
     for (size_t v = 0; views && v < n_views; ++v) HULO_ARG(views[v] < n_seg, "view index out of range");
@@ -887,6 +899,7 @@ int hulo_match_to_queries(hulo_gpu *h, const hulo_db *map, const uint32_t *views
     HULO_ARG(q_stride >= 1, "stride must be >= 1");
     *n_out = 0;
     HULO_CUDA(cudaSetDevice(h->device));
+    HULO_CUDA(join_exchange(h));
     const size_t n_seg = map->seg.size() - 1;
     if (views == nullptr) n_views = n_seg;
     for (size_t v = 0; views && v < n_views; ++v) HULO_ARG(views[v] < n_seg, "view index out of range");
@@ -1085,6 +1098,7 @@ int hulo_match_pairs(hulo_gpu *h, const hulo_db *db, const uint32_t *pairs, size
     HULO_ARG(n_pairs == 0 || pairs != nullptr, "pairs is null");
     *n_out = 0;
     HULO_CUDA(cudaSetDevice(h->device));
+    HULO_CUDA(join_exchange(h));
     const size_t n_seg = db->seg.size() - 1;
     for (size_t p = 0; p < n_pairs; ++p)
         HULO_ARG(pairs[2 * p] < n_seg && pairs[2 * p + 1] < n_seg, "pair refers to a segment that does not exist");

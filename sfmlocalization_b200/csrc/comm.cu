@@ -88,6 +88,8 @@ size_t px_bytes(int world, uint32_t cap) { return (size_t)2 * world * cap * size
 // peers' buffers, all ranks meet, and only then is the exported buffer freed (freeing memory that an
 // importer still has open is undefined behaviour).
 void px_release(hulo_gpu *h) {
+    if (h->xstream) cudaStreamSynchronize(h->xstream);
+    h->x_pending = false;
     bool had_peers = false;
     for (int g = 0; g < h->world && g < kMaxPeers; ++g) {
         if (g != h->rank && h->px_peer_base[g]) { cudaIpcCloseMemHandle(h->px_peer_base[g]); had_peers = true; }
@@ -216,6 +218,7 @@ int hulo_comm_max_f64(hulo_gpu *h, double *value) {
     if (h->world == 1 && !h->nccl_comm) return hulo_synchronize(h);
     if (!h->nccl_comm) { set_error("hulo_comm_max_f64: communicator not initialised"); return HULO_ERR_NCCL; }
     HULO_CUDA(cudaSetDevice(h->device));
+    HULO_CUDA(join_exchange(h));
     HULO_CUDA(h->scratch2.reserve(64));
     double *d = h->scratch2.as<double>();
     HULO_CUDA(cudaMemcpyAsync(d, value, sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -277,14 +280,32 @@ int hulo_knn2_sharded(hulo_gpu *h, const hulo_db *A, const hulo_db *B_shard, uin
         use_peers = h->px_ready;
     }
     if (use_peers) {
+        if (!h->xstream) {
+            HULO_CUDA(cudaStreamCreateWithFlags(&h->xstream, cudaStreamNonBlocking));
+            for (int p = 0; p < 2; ++p) {
+                HULO_CUDA(cudaEventCreateWithFlags(&h->ev_k1[p], cudaEventDisableTiming));
+                HULO_CUDA(cudaEventCreateWithFlags(&h->ev_x[p], cudaEventDisableTiming));
+            }
+        }
+        // K1 on the main stream, the exchange on its own: the next call's K1 starts while this
+        // call's candidates are still crossing NVLink.  This parity's key buffer and record slots
+        // were last used two calls ago; wait for that exchange before K1 overwrites the keys.
+        const int p = (int)((h->px_seq + 1) & 1);
+        HULO_CUDA(cudaStreamWaitEvent(h->stream, h->ev_x[p], 0));
+        std::swap(h->partial, h->partial_alt);
         FlatRun run;
         int rc = run_flat_k1(h, A->rows, nA, B_shard->rows, B_shard->n, (uint32_t)row_base, &run);
         if (rc != HULO_OK) return rc;
+        HULO_CUDA(cudaEventRecord(h->ev_k1[p], h->stream));
+        HULO_CUDA(cudaStreamWaitEvent(h->xstream, h->ev_k1[p], 0));
         h->px.seq = ++h->px_seq;
         HULO_CUDA(knn2_merge_store_peers_launch(h->partial.as<uint2>(), (uint32_t)nA, run.n_chunks, run.slot_stride,
-                                                run.rows_per_chunk, (uint32_t)row_base, h->px, h->stream));
+                                                run.rows_per_chunk, (uint32_t)row_base, h->px, h->xstream));
         HULO_CUDA(knn2_merge_from_peers_launch(h->px, (uint32_t)nA, h->knn_idx.as<int32_t>(),
-                                               h->knn_dist.as<int32_t>(), h->stream));
+                                               h->knn_dist.as<int32_t>(), h->xstream));
+        HULO_CUDA(cudaEventRecord(h->ev_x[p], h->xstream));
+        h->x_pending = true;
+        h->x_last = p;
         h->launches += 2;
         if (idx2 || dist2) {
             int rc2 = hulo_knn2_fetch(h, nA, idx2, dist2);
@@ -299,6 +320,7 @@ int hulo_knn2_sharded(hulo_gpu *h, const hulo_db *A, const hulo_db *B_shard, uin
         }
         return HULO_OK;
     }
+    HULO_CUDA(join_exchange(h));
     int rc = run_flat_packed(h, A->rows, nA, B_shard->rows, B_shard->n, (uint32_t)row_base);
     if (rc != HULO_OK) return rc;
     if (h->world > 1 && nA > 0) {
@@ -318,6 +340,7 @@ int hulo_merge_top2(hulo_gpu *h, const int32_t *cand, size_t nA, int world, int3
     HULO_ARG(h != nullptr && world >= 1, "bad argument");
     HULO_ARG(nA == 0 || (cand != nullptr && idx2 != nullptr && dist2 != nullptr), "null argument");
     HULO_CUDA(cudaSetDevice(h->device));
+    HULO_CUDA(join_exchange(h));
     HULO_CUDA(h->knn_idx.reserve(std::max<size_t>(nA, 1) * 2 * sizeof(int32_t)));
     HULO_CUDA(h->knn_dist.reserve(std::max<size_t>(nA, 1) * 2 * sizeof(int32_t)));
     h->last_nA = nA;

@@ -143,4 +143,22 @@ struct hulo_gpu {
     void *px_peer_base[hulo::kMaxPeers] = {nullptr};
     bool px_ready = false, px_disabled = false;
     uint32_t px_seq = 0;
+    // The exchange runs on its own stream so that the next search's K1 overlaps it: ev_k1[p] = K1 of
+    // the step with parity p has left its keys, ev_x[p] = that step's exchange is complete.  Keys are
+    // double-buffered (partial / partial_alt) like the record slots.  Every other entry point that
+    // touches the result buffers joins the exchange stream first (hulo::join_exchange).
+    cudaStream_t xstream = nullptr;
+    cudaEvent_t ev_k1[2] = {nullptr, nullptr}, ev_x[2] = {nullptr, nullptr};
+    hulo::DevBuf partial_alt;
+    bool x_pending = false;
+    int x_last = 0;
 };
+
+namespace hulo {
+// Make the main stream wait for every exchange still in flight on the exchange stream.
+inline cudaError_t join_exchange(hulo_gpu *h) {
+    if (!h->x_pending) return cudaSuccess;
+    h->x_pending = false;
+    return cudaStreamWaitEvent(h->stream, h->ev_x[h->x_last], 0);
+}
+}  // namespace hulo

@@ -162,6 +162,26 @@ def main():
             g.set_knn_engine(eng)
             results.append(g.knn2_sharded(dA, dB, lo))
         g.set_knn_engine("auto")
+        # pipelined calls (the exchange of one call overlaps K1 of the next): un-fetched searches
+        # with two alternating searcher tables, the result read afterwards must be the last
+        # call's; then an unsharded search issued right behind a pending exchange
+        A_rev = np.ascontiguousarray(A[::-1])
+        dAr = g.db(A_rev)
+        for eng in ("tc", "int"):
+            g.set_knn_engine(eng)
+            for k in range(7):
+                g.knn2_sharded(dAr if k % 2 else dA, dB, lo, fetch=False)
+            pi, pd = g.knn2_fetch(NA)
+            assert np.array_equal(pi, results[0][0]) and np.array_equal(pd, results[0][1])
+            g.knn2_sharded(dAr, dB, lo, fetch=False)
+            pi, pd = g.knn2_fetch(NA)
+            assert np.array_equal(pi, results[0][0][::-1]) and np.array_equal(pd, results[0][1][::-1])
+            g.knn2_sharded(dA, dB, lo, fetch=False)
+            li_, ld_ = g.knn2(dAr, dB)                # local shard only, behind the pending exchange
+            wi_, wd_ = orc.knn2(A_rev, B[lo:hi])
+            assert np.array_equal(li_, wi_) and np.array_equal(ld_, wd_)
+        g.set_knn_engine("auto")
+        dAr.free()
         for (i_, d_) in results:
             assert np.array_equal(i_, results[0][0]) and np.array_equal(d_, results[0][1])
         assert np.array_equal(i2[:NA], results[0][0]) and np.array_equal(i2[-NA:], results[0][0])

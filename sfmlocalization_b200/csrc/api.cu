@@ -503,13 +503,14 @@ void hulo_gpu_destroy(hulo_gpu *h) {
     }
     if (h->xstream) cudaStreamDestroy(h->xstream);
     DevBuf *bufs[] = {&h->partial, &h->partial_alt, &h->counter, &h->items, &h->knn_idx, &h->knn_dist, &h->packed, &h->gathered,
-                      &h->stageA, &h->stageB, &h->scratch0, &h->scratch1, &h->scratch2, &h->scratch3, &h->lfact};
+                      &h->stageA, &h->stageB, &h->scratch0, &h->scratch1, &h->scratch2, &h->scratch3, &h->lfact, &h->wave_counter};
     for (DevBuf *b : bufs) b->release();
     for (auto &e : h->tc_images) e.img.release();
     h->tc_scratchA.release();
     h->tc_scratchB.release();
     h->tc_tiles.release();
     h->tc_qitems.release();
+    h->wave_rec.release();
     h->hstage0.release();
     h->hstage1.release();
     if (h->ev_start) cudaEventDestroy(h->ev_start);

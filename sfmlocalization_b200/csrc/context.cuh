@@ -130,6 +130,9 @@ struct hulo_gpu {
     hulo::HostBuf hstage0, hstage1;
     size_t last_nA = 0;
     size_t score_smem_configured = 0;   // dynamic smem opt-in already set for K2 on this device
+    hulo::DevBuf wave_counter; // K2: blocks-done counter of the fused resection wave (rests at 0)
+    hulo::HostBuf wave_rec;    // K2: the wave's record {nfa, index, model[12], -, sequence}, written by the kernel
+    uint64_t wave_seq = 0;
     hulo::DevBuf lfact;        // K3: log10(n!) table
     size_t lfact_n = 0;
     size_t geo_smem_configured = 0;

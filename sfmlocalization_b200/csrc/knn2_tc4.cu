@@ -38,6 +38,7 @@ constexpr size_t smem_bytes4() {
 
 constexpr float kThrNoneF = -1024.0f;
 constexpr float kDotPastEnd = -514.0f;          // 512 - 2 * 513
+constexpr uint32_t kLazyMinRows = 16384;   // shorter ranges: the epilogue's threshold test does not pay (scan32)
 constexpr uint32_t kKeyPastEnd = 513u << kKeyIdxBits;
 
 // D[tmem] (+)= A[smem] * B[smem]^T, e2m1 x e2m1 with one ue8m0 scale per 32 elements -> fp32; M = 128, K = 64
@@ -108,14 +109,19 @@ __device__ __forceinline__ void merge2x2(uint32_t &p0, uint32_t &p1, uint32_t q0
 // short database ranges (thresholds restart with every item) spend most of their epilogue in.
 // Columns past the end of a range are given the dot kDotPastEnd by the caller ("distance 513"): they
 // lose against every real row and are turned into "none" when the item's keys are written.
-__device__ __forceinline__ void scan32(const float (&v)[32], uint32_t row0, uint32_t &best0, uint32_t &best1, float &thr) {
-    float m[11];
+// `lazy` = false skips the fast path's test: against a short range (a query image's few thousand
+// rows) some lane of the warp improves its pair in nearly every block, and the test only costs.
+__device__ __forceinline__ void scan32(const float (&v)[32], uint32_t row0, uint32_t &best0, uint32_t &best1, float &thr,
+                                       bool lazy) {
+    if (lazy) {
+        float m[11];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) m[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
-    m[10] = fmaxf(v[30], v[31]);
-    const float bm = fmax3(fmax3(m[0], m[1], m[2]), fmax3(m[3], m[4], m[5]),
-                           fmax3(fmax3(m[6], m[7], m[8]), m[9], m[10]));
-    if (bm <= thr) return;
+        for (int i = 0; i < 10; ++i) m[i] = fmax3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+        m[10] = fmaxf(v[30], v[31]);
+        const float bm = fmax3(fmax3(m[0], m[1], m[2]), fmax3(m[3], m[4], m[5]),
+                               fmax3(fmax3(m[6], m[7], m[8]), m[9], m[10]));
+        if (bm <= thr) return;
+    }
     // key16(e) = distance * 32 + e = 8192 + e - 16 v, read off the low mantissa bits of
     // fma(v, -16, 2^23 + 8192 + e) (exact: the value is an integer in [2^23, 2^24)); columns e and
     // e + 16 share a register: (bits(e + 16) << 16) + bits(e) leaves key(e) in the low half and
@@ -325,6 +331,7 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
             const uint32_t n_tiles = (b_rows + N - 1) / N;
             uint32_t best0 = kKeyNone, best1 = kKeyNone;
             float thr = kThrNoneF;
+            const bool lazy = b_rows > kLazyMinRows;
             for (uint32_t t = 0; t < n_tiles; ++t) {
                 const uint32_t acc_it = acc_base + t, buf = acc_it & 1u;
                 mbar_wait(bar_acc_full + 8 * buf, (acc_it >> 1) & 1u);
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
 #pragma unroll
                         for (int e = 0; e < 32; ++e) v[e] = col + (uint32_t)e < n_valid ? v[e] : kDotPastEnd;
                     }
-                    scan32(v, t * N + col, best0, best1, thr);
+                    scan32(v, t * N + col, best0, best1, thr, lazy);
                 };
                 auto release = [&]() {
                     // every column of this half is in registers: hand the accumulator back before the last scan

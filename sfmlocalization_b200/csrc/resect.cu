@@ -18,6 +18,8 @@
 //   sequential scan.
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -298,14 +300,15 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel_reg_batch(
 // First minimum of the H scores (strict <: the earliest hypothesis wins ties, like the sequential
 // update rule) and its model, gathered into one small record so a batch costs one D2H copy:
 // out = {nfa, (double)index, model[12]}; index = -1 when every score is +inf / NaN.
-__device__ __forceinline__ void argmin_block(const double *__restrict__ nfa, uint32_t H,
-                                             const double *__restrict__ models, double *__restrict__ out) {
+// kFresh: the inputs were written by other blocks of the same launch (read them past L1).
+template <bool kFresh = false>
+__device__ __forceinline__ void argmin_block(const double *nfa, uint32_t H, const double *models, double *out) {
     __shared__ double s_v[8];
     __shared__ uint32_t s_i[8];
     double v = INFINITY;
     uint32_t idx = 0xFFFFFFFFu;
     for (uint32_t h = threadIdx.x; h < H; h += 256) {
-        const double x = nfa[h];
+        const double x = kFresh ? __ldcg(nfa + h) : nfa[h];
         if (x < v) { v = x; idx = h; }          // ascending h per thread: keeps the earliest
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -320,7 +323,8 @@ __device__ __forceinline__ void argmin_block(const double *__restrict__ nfa, uin
             if (s_v[w] < v || (s_v[w] == v && s_i[w] < idx)) { v = s_v[w]; idx = s_i[w]; }
         out[0] = v;
         out[1] = idx == 0xFFFFFFFFu ? -1.0 : (double)idx;
-        for (int k = 0; k < 12; ++k) out[2 + k] = idx == 0xFFFFFFFFu ? 0.0 : models[(size_t)idx * 12 + k];
+        for (int k = 0; k < 12; ++k)
+            out[2 + k] = idx == 0xFFFFFFFFu ? 0.0 : (kFresh ? __ldcg(models + (size_t)idx * 12 + k) : models[(size_t)idx * 12 + k]);
     }
 }
 __global__ void __launch_bounds__(256) argmin_kernel(const double *__restrict__ nfa, uint32_t H,
@@ -413,17 +417,15 @@ __device__ __forceinline__ void norm3(double *a) {
     a[0] /= n; a[1] /= n; a[2] /= n;
 }
 
-// One thread per sample triplet.  models: T x 4 x 12; an absent model has NaN in entry 0.
-__global__ void p3p_kernel(const uint32_t *__restrict__ triplets, uint32_t T, const double *__restrict__ x2dn,
-                           const double *__restrict__ X3d, double *__restrict__ models,
-                           int32_t *__restrict__ n_models) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
-    double *out = models + (size_t)t * 48;
-    for (int m = 0; m < 4; ++m) out[12 * m] = NAN;
+// The solver for one sample triplet (i0, i1, i2): the models of the quartic's roots [root_lo,
+// root_hi) are written to out[0], out[12], ... (finite ones only, packed) and counted.  One
+// compiled body (never inlined) serves the per-triplet kernel (all four roots) and the fused wave
+// kernel (one root per CTA), so a model has the same bits through either.
+__device__ __noinline__ int p3p_models(uint32_t i0, uint32_t i1, uint32_t i2, const double *__restrict__ x2dn,
+                                       const double *__restrict__ X3d, int root_lo, int root_hi,
+                                       double *__restrict__ out) {
     double P1[3], P2[3], P3[3], f1[3], f2[3], f3[3];
     {
-        const uint32_t i0 = triplets[3 * t], i1 = triplets[3 * t + 1], i2 = triplets[3 * t + 2];
         for (int c = 0; c < 3; ++c) { P1[c] = X3d[3 * (size_t)i0 + c]; P2[c] = X3d[3 * (size_t)i1 + c]; P3[c] = X3d[3 * (size_t)i2 + c]; }
         f1[0] = x2dn[2 * (size_t)i0]; f1[1] = x2dn[2 * (size_t)i0 + 1]; f1[2] = 1.0;
         f2[0] = x2dn[2 * (size_t)i1]; f2[1] = x2dn[2 * (size_t)i1 + 1]; f2[2] = 1.0;
@@ -434,7 +436,7 @@ __global__ void p3p_kernel(const uint32_t *__restrict__ triplets, uint32_t T, co
     double d1[3], d2[3], cr[3];
     for (int c = 0; c < 3; ++c) { d1[c] = P2[c] - P1[c]; d2[c] = P3[c] - P1[c]; }
     cross3(d1, d2, cr);
-    if (dot3(cr, cr) == 0.0) { n_models[t] = 0; return; }   // collinear world points
+    if (dot3(cr, cr) == 0.0) return 0;   // collinear world points
 
     double e1[3], e2[3], e3[3], f3t[3];
     for (int pass = 0; pass < 2; ++pass) {
@@ -481,7 +483,7 @@ __global__ void p3p_kernel(const uint32_t *__restrict__ triplets, uint32_t T, co
     double roots[4];
     solve_quartic(fac, roots);
 
-    for (int i = 0; i < 4; ++i) {
+    for (int i = root_lo; i < root_hi; ++i) {
         const double cot_alpha = (-phi1 * p1 / phi2 - roots[i] * p2 + d12 * b) / (-phi1 * roots[i] * p2 / phi2 + p1 - d12);
         const double cos_theta = roots[i];
         const double sin_theta = sqrt(1.0 - roots[i] * roots[i]);
@@ -514,7 +516,81 @@ __global__ void p3p_kernel(const uint32_t *__restrict__ triplets, uint32_t T, co
         for (int k = 0; k < 12; ++k) out[12 * n_out + k] = M[k];
         ++n_out;
     }
-    n_models[t] = n_out;
+    return n_out;
+}
+
+// One thread per sample triplet.  models: T x 4 x 12; an absent model has NaN in entry 0.
+__global__ void p3p_kernel(const uint32_t *__restrict__ triplets, uint32_t T, const double *__restrict__ x2dn,
+                           const double *__restrict__ X3d, double *__restrict__ models,
+                           int32_t *__restrict__ n_models) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    double *out = models + (size_t)t * 48;
+    for (int m = 0; m < 4; ++m) out[12 * m] = NAN;
+    n_models[t] = p3p_models(triplets[3 * t], triplets[3 * t + 1], triplets[3 * t + 2], x2dn, X3d, 0, 4, out);
+}
+
+// ---- one wave of a single problem in TWO launches: (draw + solve), (score + first minimum)
+// The host sampler is a counter-based generator (its n-th output is a function of seed + n), so the
+// device draws sample t itself; four threads share a sample and each solves one root of its
+// quartic (slot 4 t + i, NaN-marked when the root gives no model: the order of the per-triplet
+// kernel's packed models, so the first minimum is the same hypothesis).  The scoring kernel's
+// last block to finish reduces the wave to the record {nfa, index, model[12]} the host reads.
+__device__ __forceinline__ uint64_t splitmix64_at(uint64_t s0, uint64_t n) {
+    uint64_t z = s0 + n * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(128) p3p_draw_kernel(uint64_t rng0, uint32_t T, uint32_t total,
+                                                       const uint32_t *__restrict__ pool,
+                                                       const double *__restrict__ x2dn,
+                                                       const double *__restrict__ X3d, double *__restrict__ models) {
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= 4 * T) return;
+    const uint32_t t = h >> 2;
+    // three distinct positions in [0, total), ascending insertion (sample3 on the host)
+    uint32_t pos[3];
+    for (int i = 0; i < 3; ++i) {
+        uint32_t r = (uint32_t)(splitmix64_at(rng0, 3ull * t + i + 1) % (uint64_t)(total - i));
+        int j;
+        for (j = 0; j < i && r >= pos[j]; ++j) ++r;
+        for (int k = i; k > j; --k) pos[k] = pos[k - 1];
+        pos[j] = r;
+    }
+    if (pool) { pos[0] = pool[pos[0]]; pos[1] = pool[pos[1]]; pos[2] = pool[pos[2]]; }
+    double M[12];
+    M[0] = NAN;
+    for (int k = 1; k < 12; ++k) M[k] = 0.0;
+    const int root = (int)(h & 3);
+    p3p_models(pos[0], pos[1], pos[2], x2dn, X3d, root, root + 1, M);
+    for (int k = 0; k < 12; ++k) models[(size_t)h * 12 + k] = M[k];
+}
+
+template <int E>
+__global__ void __launch_bounds__(kScoreThreads) score_wave_kernel(
+    const double *__restrict__ models, const double *__restrict__ x2dn, const double *__restrict__ X3d, uint32_t N,
+    const float *__restrict__ logc_n, const float *__restrict__ logc_k, double loge0, double logalpha0,
+    double *__restrict__ out_nfa, unsigned int *__restrict__ counter, double *__restrict__ rec, uint64_t seq) {
+    score_reg_block<E>(blockIdx.x, models, x2dn, X3d, N, logc_n, logc_k, loge0, logalpha0, -1.0f, out_nfa, nullptr,
+                       nullptr, nullptr);
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *counter = 0;                 // ready for the next wave
+    // rec is pinned host memory: the record goes straight to the host, then the wave's sequence
+    // number behind a system-wide fence -- the host polls that word instead of waiting on a copy
+    argmin_block<true>(out_nfa, gridDim.x, models, rec);
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        *reinterpret_cast<volatile uint64_t *>(rec + 14) = seq;
+    }
 }
 
 // ------------------------------------------------------------------ host helpers
@@ -749,45 +825,66 @@ struct ResectJob {
         }
         last_T = T;
     }
+    // the device drew T triplets itself: advance the generator past them (three outputs each)
+    void skip_draws(size_t T) {
+        rng += (uint64_t)(3 * T) * 0x9E3779B97F4A7C15ULL;
+        last_T = T;
+    }
     // (residual, index) ascending.  The residuals are non-negative doubles (or +inf), whose bit
-    // patterns order like the values: a stable byte-wise radix sort from the index order gives
-    // exactly the order of the comparison sort it replaces, in a third of the time at N ~ 700.
-    // Bytes on which all keys agree (most of the exponent) are skipped.
+    // patterns order like the values: a stable radix sort of the upper 32 bits (three passes of
+    // 11 / 11 / 10 bits from the index order), then the rare runs that agree in those bits are put
+    // in full (residual, index) order -- exactly the order of the comparison sort it replaces.
     std::vector<EI> ei_tmp;
+    std::vector<uint32_t> hist;
     void sort_by_residual() {
+        auto less = [](const EI &a, const EI &b) { return a.e < b.e || (a.e == b.e && a.i < b.i); };
         if (N < 64) {
-            std::sort(ei.begin(), ei.end(), [](const EI &a, const EI &b) { return a.e < b.e || (a.e == b.e && a.i < b.i); });
+            std::sort(ei.begin(), ei.end(), less);
             return;
         }
-        uint32_t hist[8][256];
-        memset(hist, 0, sizeof hist);
+        hist.assign(2048 + 2048 + 1024, 0);
+        uint32_t *h0 = hist.data(), *h1 = h0 + 2048, *h2 = h1 + 2048;
+        auto hi32 = [](const EI &x) { uint64_t k; memcpy(&k, &x.e, 8); return (uint32_t)(k >> 32); };
         for (size_t i = 0; i < N; ++i) {
-            uint64_t k;
             if (ei[i].e == 0.0) ei[i].e = 0.0;            // -0.0 would sort as the largest key
-            memcpy(&k, &ei[i].e, 8);
-            for (int b = 0; b < 8; ++b) ++hist[b][(k >> (8 * b)) & 255];
+            const uint32_t k = hi32(ei[i]);
+            ++h0[k & 2047]; ++h1[(k >> 11) & 2047]; ++h2[k >> 22];
         }
         ei_tmp.resize(N);
         EI *src = ei.data(), *dst = ei_tmp.data();
-        for (int b = 0; b < 8; ++b) {
-            uint32_t *h = hist[b];
+        const int shift[3] = {0, 11, 22}, bins[3] = {2048, 2048, 1024};
+        uint32_t *hh[3] = {h0, h1, h2};
+        for (int b = 0; b < 3; ++b) {
+            uint32_t *h = hh[b];
             bool trivial = false;
-            for (int d = 0; d < 256; ++d)
-                if (h[d] == N) { trivial = true; break; }
-            if (trivial) continue;
             uint32_t run = 0;
-            for (int d = 0; d < 256; ++d) { const uint32_t c = h[d]; h[d] = run; run += c; }
-            for (size_t i = 0; i < N; ++i) {
-                uint64_t k;
-                memcpy(&k, &src[i].e, 8);
-                dst[h[(k >> (8 * b)) & 255]++] = src[i];
+            for (int d = 0; d < bins[b]; ++d) {
+                const uint32_t c = h[d];
+                if (c == N) { trivial = true; break; }
+                h[d] = run; run += c;
             }
+            if (trivial) continue;
+            const uint32_t mask = (uint32_t)bins[b] - 1;
+            for (size_t i = 0; i < N; ++i) dst[h[(hi32(src[i]) >> shift[b]) & mask]++] = src[i];
             std::swap(src, dst);
         }
         if (src != ei.data()) memcpy(ei.data(), src, N * sizeof(EI));
+        for (size_t i = 0; i + 1 < N;) {
+            size_t j = i + 1;
+            const uint32_t k = hi32(ei[i]);
+            while (j < N && hi32(ei[j]) == k) ++j;
+            if (j - i > 1) std::sort(ei.begin() + i, ei.begin() + j, less);
+            i = j;
+        }
     }
 
     // Final scoring of a model in fp64 on the host: residuals, (residual, index) order, NFA.
+    // The NFA minimum is found in two passes: a float log2 brackets every term
+    // (|log10 x - log2f(x) log10(2)| < 3e-6 for x in [1e-7, 1e30]: 1 ulp of log2f plus the
+    // float rounding of x; kSlack leaves a factor 3), and only the terms whose bracket reaches
+    // below the smallest upper bound are evaluated with the double log10 -- the same terms, in the
+    // same order and with the same strict comparison the full scan would have kept.
+    std::vector<double> nfa_lo;
     double finalize(const double *M) {
         for (size_t i = 0; i < N; ++i) {
             const double *X = X3d + 3 * i;
@@ -800,10 +897,25 @@ struct ResectJob {
             ei[i] = EI{e, i};
         }
         sort_by_residual();
-        double bn = INFINITY;
-        size_t bk = 3;
+        constexpr double kSlack = 1e-5, kLog10of2 = 0.30102999566398120;
+        nfa_lo.resize(N + 1);
+        double ub_min = INFINITY;
+        size_t k_end = 3;
         for (size_t k = 4; k <= N; ++k) {
             if (!(ei[k - 1].e < INFINITY)) break;
+            k_end = k;
+            const double x = ei[k - 1].e + (double)FLT_EPSILON;
+            if (!(x < 1e30)) { nfa_lo[k] = -INFINITY; continue; }        // outside the bracket's range: always exact
+            const double la = logalpha0 + (double)log2f((float)x) * kLog10of2;
+            const double nf = loge0 + la * (double)(k - 3) + (double)lcn[k] + (double)lck[k];
+            const double slack = kSlack * (double)(k - 3);
+            nfa_lo[k] = nf - slack;
+            ub_min = std::min(ub_min, nf + slack);
+        }
+        double bn = INFINITY;
+        size_t bk = 3;
+        for (size_t k = 4; k <= k_end; ++k) {
+            if (!(nfa_lo[k] <= ub_min)) continue;
             const double logalpha = logalpha0 + log10(ei[k - 1].e + (double)FLT_EPSILON);
             const double nfa = loge0 + logalpha * (double)(k - 3) + (double)lcn[k] + (double)lck[k];
             if (nfa < bn) { bn = nfa; bk = k; }
@@ -1005,18 +1117,109 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
     // ACRANSAC: nothing to do with N <= MINIMUM_SAMPLES
     if (N <= 3 || max_iter == 0) return HULO_OK;
     HULO_CUDA(cudaSetDevice(h->device));
+    static const bool trace = getenv("HULO_RESECT_TRACE") != nullptr;      // host time per phase on stderr
+    auto now = []() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_mark = trace ? now() : 0.0;
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        const double t = now();
+        fprintf(stderr, "[resect] %-10s %7.1f us\n", what, t - t_mark);
+        t_mark = t;
+    };
     ResectJob job;
     job.init(x2d, X3d, N, K, max_iter, seed);
+    lap("init");
     Problem pb;
     pb.lcn = job.lcn;
     pb.lck = job.lck;
     int rc = stage_problem(h, job.x2dn, X3d, N, pb);
     if (rc != HULO_OK) return rc;
+    lap("stage");
+
+    // Two launches per wave (draw + P3P, scoring + first minimum) when the sort fits in registers:
+    // nothing goes up but the focused phase's pool; the host-drawn three-kernel form below otherwise.
+    static const bool three_kernels = getenv("HULO_RESECT_UNFUSED") != nullptr || getenv("HULO_K2_SMEM_SORT") != nullptr;
+    if (N <= 4096 && !three_kernels) {
+        if (!h->wave_counter.ptr) {
+            HULO_CUDA(h->wave_counter.reserve(sizeof(unsigned int)));
+            HULO_CUDA(cudaMemsetAsync(h->wave_counter.ptr, 0, sizeof(unsigned int), h->stream));
+        }
+        if (!h->wave_rec.ptr) {
+            HULO_CUDA(h->wave_rec.reserve(16 * sizeof(double)));
+            memset(h->wave_rec.ptr, 0, 16 * sizeof(double));
+        }
+        double *rec = h->wave_rec.as<double>();
+        volatile uint64_t *rec_seq = reinterpret_cast<volatile uint64_t *>(rec + 14);
+        for (size_t T = job.next_T(); T > 0; T = job.next_T()) {
+            const size_t H = 4 * T;
+            HULO_CUDA(h->scratch1.reserve(H * 12 * sizeof(double)));
+            HULO_CUDA(h->scratch2.reserve(H * sizeof(double)));
+            const uint32_t *d_pool = nullptr;
+            if (job.phase == ResectJob::kFocused) {
+                // focused phase: the sampler draws among the inliers of the best model (the problem's
+                // staging copy has completed: the previous wave was waited for)
+                HULO_CUDA(h->scratch3.reserve(job.pool.size() * sizeof(uint32_t)));
+                HULO_CUDA(h->hstage1.reserve(job.pool.size() * sizeof(uint32_t)));
+                uint32_t *hp = h->hstage1.as<uint32_t>();
+                for (size_t i = 0; i < job.pool.size(); ++i) hp[i] = (uint32_t)job.pool[i];
+                HULO_CUDA(cudaMemcpyAsync(h->scratch3.ptr, hp, job.pool.size() * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                          h->stream));
+                d_pool = h->scratch3.as<uint32_t>();
+            }
+            double *d_models = h->scratch1.as<double>();
+            double *d_nfa = h->scratch2.as<double>();
+            const uint64_t seq = ++h->wave_seq;
+            uint32_t np = kScoreThreads;
+            while (np < N) np <<= 1;
+            p3p_draw_kernel<<<(unsigned)((H + 127) / 128), 128, 0, h->stream>>>(job.rng, (uint32_t)T, (uint32_t)job.pool.size(),
+                                                                                d_pool, pb.d_x2dn, pb.d_X3d, d_models);
+            HULO_CUDA(cudaGetLastError());
+            h->launches++;
+#define HULO_WAVE(EE)                                                                                              \
+    score_wave_kernel<EE><<<(unsigned)H, kScoreThreads, 0, h->stream>>>(                                               \
+        d_models, pb.d_x2dn, pb.d_X3d, (uint32_t)N, pb.d_logc_n, pb.d_logc_k, pb.loge0, pb.logalpha0, d_nfa,         \
+        h->wave_counter.as<unsigned int>(), rec, seq)
+            switch (np / kScoreThreads) {
+                case 1: HULO_WAVE(1); break;
+                case 2: HULO_WAVE(2); break;
+                case 4: HULO_WAVE(4); break;
+                case 8: HULO_WAVE(8); break;
+                default: HULO_WAVE(16); break;
+            }
+#undef HULO_WAVE
+            HULO_CUDA(cudaGetLastError());
+            h->launches++;
+            job.skip_draws(T);
+            lap("enqueue");
+            // poll the record's sequence word; the stream is queried now and then so that a failed
+            // launch is reported instead of waited for
+            for (uint32_t spins = 1; *rec_seq != seq; ++spins) {
+                if ((spins & 0xFFFu) == 0) {
+                    const cudaError_t q = cudaStreamQuery(h->stream);
+                    if (q != cudaErrorNotReady) {
+                        HULO_CUDA(q);
+                        if (*rec_seq != seq) { set_error("hulo_resect_acransac: the wave finished without its record"); return HULO_ERR_CUDA; }
+                    }
+                }
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            std::atomic_thread_fence(std::memory_order_acquire);
+            lap("wait");
+            job.absorb(rec);
+            lap("absorb");
+        }
+        job.emit(P, inliers, n_inliers, error_max, found);
+        lap("emit");
+        return HULO_OK;
+    }
 
     std::vector<uint32_t> tri;
     for (size_t T = job.next_T(); T > 0; T = job.next_T()) {
         tri.resize(3 * T);
         job.draw(T, tri.data(), 0);
+        lap("draw");
         HULO_CUDA(h->scratch3.reserve(T * 3 * sizeof(uint32_t)));
         HULO_CUDA(h->scratch1.reserve(T * 48 * sizeof(double) + T * sizeof(int32_t)));
         HULO_CUDA(cudaMemcpyAsync(h->scratch3.ptr, tri.data(), T * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
@@ -1036,11 +1239,15 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
         argmin_kernel<<<1, 256, 0, h->stream>>>(o.nfa, (uint32_t)(4 * T), d_models, d_rec);
         HULO_CUDA(cudaGetLastError());
         h->launches++;
+        lap("enqueue");
         HULO_CUDA(cudaMemcpyAsync(rec, d_rec, sizeof rec, cudaMemcpyDeviceToHost, h->stream));
         HULO_CUDA(cudaStreamSynchronize(h->stream));
+        lap("wait");
         job.absorb(rec);
+        lap("absorb");
     }
     job.emit(P, inliers, n_inliers, error_max, found);
+    lap("emit");
     return HULO_OK;
 }
 

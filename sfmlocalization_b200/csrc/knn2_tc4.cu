@@ -14,6 +14,7 @@
 #include "tc_ptx.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace hulo {
 
@@ -28,12 +29,11 @@ constexpr uint32_t kGroupBytes4 = 8 * kRowBytes4; // 2048
 constexpr uint32_t kABytes4 = 128 * kRowBytes4;   // 32768
 constexpr uint32_t kStageBytes4 = kN4 * kRowBytes4;   // 57344 (the widest stage: sizes the slack of the images)
 constexpr int kStages4 = 3;
-constexpr uint32_t kThreads4 = 320;
 constexpr uint32_t kTmemCols4 = 512;
 constexpr uint32_t kSfCol = 480;
 template <uint32_t N, bool A2>
 constexpr size_t smem_bytes4() {
-    return 1024 + (A2 ? 2 : 1) * kABytes4 + (size_t)kStages4 * N * kRowBytes4 + 256 + 2 * 128 * sizeof(uint2);
+    return 1024 + (A2 ? 2 : 1) * kABytes4 + (size_t)kStages4 * N * kRowBytes4 + 256 + 2 * 2 * 128 * sizeof(uint2);
 }
 
 constexpr float kThrNoneF = -1024.0f;
@@ -180,8 +180,12 @@ __device__ __forceinline__ TcWork4 tc_work4(const TcParams &p, uint32_t w) {
 // N = database rows per accumulator tile (a multiple of 64).  A2 = two searcher-tile buffers: the
 // producer fetches the searcher tile of the next item while the MMAs of the current one run (item
 // mode, where every few tiles bring a new searcher tile; with one buffer each change drained the ring).
-template <uint32_t N, bool A2>
-__global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p) {
+// G = epilogue groups of four warps: every group drains N / G columns of every accumulator.  Two for
+// the flat searches (the lazy epilogue keeps up with the tensor pipe); three for item lists, whose
+// short ranges run the full update on nearly every block and are bound by ALU issue -- four more
+// warps per SM to issue from.
+template <uint32_t N, bool A2, uint32_t G>
+__global__ void __launch_bounds__(64 + 128 * G, 1) knn2_tc4_kernel(const TcParams p) {
     constexpr uint32_t kStageB = N * kRowBytes4;
     constexpr uint32_t kNA = A2 ? 2u : 1u;
     extern __shared__ uint8_t smem_raw[];
@@ -211,7 +215,7 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_acc_full + 8 * b, 1);
-            mbar_init(bar_acc_empty + 8 * b, 8);           // every epilogue warp drains a part of every tile
+            mbar_init(bar_acc_empty + 8 * b, 4 * G);       // every epilogue warp drains a part of every tile
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -322,9 +326,11 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
         // accumulator is drained in half the time and handed back to the MMA thread sooner: with one
         // group per accumulator the tensor pipe sat at 63 % (buffer cycle = MMA time + a whole drain).
         uint32_t acc_base = 0, it = 0;
-        constexpr uint32_t kHalf = N / 2;                        // 112 = 32 + 32 + 32 + 16, or 96 = 32 + 32 + 32
+        constexpr uint32_t kHalf = N / G;                        // 112 = 32 + 32 + 32 + 16, 96 = 32 + 32 + 32, or 64 = 32 + 32
         constexpr bool kTail16 = (kHalf % 32u) != 0u;
-        static_assert(kHalf / 32u == 3u, "the epilogue is written for three full blocks per half");
+        constexpr bool kThree = kHalf / 32u == 3u;
+        static_assert(kHalf * G == N && (kThree || (kHalf == 64u && !kTail16)),
+                      "the epilogue is written for three full blocks (+16 columns) or exactly two per group");
         for (uint32_t w = w_begin; w < w_end; w += w_step, ++it) {
             const TcWork4 k = tc_work4(p, w);
             const uint32_t b_rows = k.b_rows;
@@ -362,6 +368,11 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
                 HULO_LDTM32(vb, taddr + 32u);
                 process(va, 0u);
                 HULO_WAIT_LD32(vb);
+                if constexpr (!kThree) {
+                    release();
+                    process(vb, 1u);
+                    continue;
+                }
                 HULO_LDTM32(va, taddr + 64u);
                 process(vb, 1u);
                 HULO_WAIT_LD32(va);
@@ -381,14 +392,16 @@ __global__ void __launch_bounds__(kThreads4, 1) knn2_tc4_kernel(const TcParams p
             acc_base += n_tiles;
             if (best0 >= kKeyPastEnd) best0 = kKeyNone;           // columns past the end of the range
             if (best1 >= kKeyPastEnd) best1 = kKeyNone;
-            uint2 *slot = xchg_gen + (it & 1u) * 128u + row;
-            if (grp == 1u) *slot = make_uint2(best0, best1);
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            uint2 *slot = xchg_gen + (it & 1u) * 256u + row;     // [parity][group - 1][row]
+            if (grp != 0u) slot[(grp - 1u) * 128u] = make_uint2(best0, best1);
+            asm volatile("bar.sync 1, %0;" ::"n"(128 * G) : "memory");
             if (grp == 0u) {
-                const uint2 o = *slot;
-                const uint32_t lo = min(best0, o.x), mid = max(best0, o.x);
-                const uint32_t second = min(mid, min(best1, o.y));
-                if (row < k.a_rows) p.partial[k.out_slot0 + row] = make_uint2(lo, second);
+#pragma unroll
+                for (uint32_t o_g = 0; o_g + 1u < G; ++o_g) {
+                    const uint2 o = slot[o_g * 128u];
+                    merge2(best0, best1, o.x, o.y);
+                }
+                if (row < k.a_rows) p.partial[k.out_slot0 + row] = make_uint2(best0, best1);
             }
         }
     }
@@ -491,28 +504,31 @@ void knn2_tc4_plan(size_t nA, size_t nB, int n_ctas, uint32_t *n_mtiles, uint32_
     *n_chunks = (uint32_t)((nB + rpc - 1) / rpc);
 }
 
-template <uint32_t N, bool A2>
+template <uint32_t N, bool A2, uint32_t G>
 static cudaError_t launch4(const TcParams &p, int grid, cudaStream_t stream) {
     static thread_local int configured_device = -1;
     constexpr size_t smem = smem_bytes4<N, A2>();
     int dev = 0;
     cudaGetDevice(&dev);
     if (configured_device != dev) {
-        cudaError_t e = cudaFuncSetAttribute(knn2_tc4_kernel<N, A2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(knn2_tc4_kernel<N, A2, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         configured_device = dev;
     }
     const uint64_t n_items = p.items != nullptr ? p.n_items : (uint64_t)p.n_mtiles * p.n_chunks;
     if (n_items == 0) return cudaSuccess;
     if ((uint64_t)grid > n_items) grid = (int)n_items;
-    knn2_tc4_kernel<N, A2><<<grid, kThreads4, smem, stream>>>(p);
+    knn2_tc4_kernel<N, A2, G><<<grid, 64 + 128 * G, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t knn2_tc4_launch(const TcParams &p, int grid, cudaStream_t stream) {
     // item lists: 192-row tiles and two searcher-tile buffers; flat searches: 224-row tiles, one buffer
-    if (p.items != nullptr) return launch4<kN4Items, true>(p, grid, stream);
-    return launch4<kN4, false>(p, grid, stream);
+    if (p.items != nullptr) {
+        static const bool two = getenv("HULO_TC4_ITEM_GROUPS") != nullptr && atoi(getenv("HULO_TC4_ITEM_GROUPS")) == 2;
+        return two ? launch4<kN4Items, true, 2>(p, grid, stream) : launch4<kN4Items, true, 3>(p, grid, stream);
+    }
+    return launch4<kN4, false, 2>(p, grid, stream);
 }
 
 }  // namespace hulo

@@ -150,6 +150,48 @@ __device__ __forceinline__ void scan32(const float (&v)[32], uint32_t row0, uint
     thr = best1 == kKeyNone ? kThrNoneF : (float)(512 - 2 * (int32_t)(best1 >> kKeyIdxBits));
 }
 
+// The same over 64 columns at once (two register blocks of one group): 16-bit keys
+// (distance << 6 | e), one tournament and one widening per 64 columns instead of two.
+__device__ __forceinline__ void scan64(const float (&va)[32], const float (&vb)[32], uint32_t row0, uint32_t &best0,
+                                       uint32_t &best1, float &thr, bool lazy) {
+    if (lazy) {
+        float m[11];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) m[i] = fmax3(va[3 * i], va[3 * i + 1], va[3 * i + 2]);
+        m[10] = fmaxf(va[30], va[31]);
+        float bm = fmax3(fmax3(m[0], m[1], m[2]), fmax3(m[3], m[4], m[5]), fmax3(fmax3(m[6], m[7], m[8]), m[9], m[10]));
+#pragma unroll
+        for (int i = 0; i < 10; ++i) m[i] = fmax3(vb[3 * i], vb[3 * i + 1], vb[3 * i + 2]);
+        m[10] = fmaxf(vb[30], vb[31]);
+        bm = fmaxf(bm, fmax3(fmax3(m[0], m[1], m[2]), fmax3(m[3], m[4], m[5]), fmax3(fmax3(m[6], m[7], m[8]), m[9], m[10])));
+        if (bm <= thr) return;
+    }
+    // key16(e) = distance * 64 + e = 16384 + e - 32 v; columns e (block a) and e + 32 (block b) share a register
+    uint32_t pk[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const uint32_t ta = (uint32_t)__float_as_int(fmaf(va[i], -32.0f, 8388608.0f + 16384.0f + (float)i));
+        const uint32_t tb = (uint32_t)__float_as_int(fmaf(vb[i], -32.0f, 8388608.0f + 16384.0f + (float)(i + 32)));
+        pk[i] = tb * 65536u + ta;
+    }
+    uint32_t lo[16], hi[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { lo[i] = __vminu2(pk[i], pk[i + 16]); hi[i] = __vmaxu2(pk[i], pk[i + 16]); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) merge2x2(lo[i], hi[i], lo[i + 8], hi[i + 8]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) merge2x2(lo[i], hi[i], lo[i + 4], hi[i + 4]);
+    merge2x2(lo[0], hi[0], lo[2], hi[2]);
+    merge2x2(lo[1], hi[1], lo[3], hi[3]);
+    merge2x2(lo[0], hi[0], lo[1], hi[1]);
+    auto full = [&](uint32_t k16) { return ((k16 >> 6) << kKeyIdxBits) + row0 + (k16 & 63u); };
+    uint32_t a0 = full(lo[0] & 0xFFFFu), a1 = full(hi[0] & 0xFFFFu);
+    const uint32_t b0 = full((lo[0] >> 16) - 0x4B00u), b1 = full((hi[0] >> 16) - 0x4B00u);
+    merge2(a0, a1, b0, b1);
+    merge2(best0, best1, a0, a1);
+    thr = best1 == kKeyNone ? kThrNoneF : (float)(512 - 2 * (int32_t)(best1 >> kKeyIdxBits));
+}
+
 struct TcWork4 {
     uint32_t a_group;    // first 8-row group of the searcher tile in image A
     uint32_t a_rows;     // rows of the tile whose keys are written
@@ -363,16 +405,28 @@ __global__ void __launch_bounds__(64 + 128 * G, 1) knn2_tc4_kernel(const TcParam
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
                 };
+                if constexpr (!kThree) {
+                    // two blocks per group: both in registers, one 64-column update
+                    HULO_LDTM32(va, taddr);
+                    HULO_LDTM32(vb, taddr + 32u);
+                    HULO_WAIT_LD32(va);
+                    HULO_WAIT_LD32(vb);
+                    release();
+                    if (n_valid < c0 + 64u) {
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) {
+                            va[e] = c0 + (uint32_t)e < n_valid ? va[e] : kDotPastEnd;
+                            vb[e] = c0 + 32u + (uint32_t)e < n_valid ? vb[e] : kDotPastEnd;
+                        }
+                    }
+                    scan64(va, vb, t * N + c0, best0, best1, thr, lazy);
+                    continue;
+                }
                 HULO_LDTM32(va, taddr);
                 HULO_WAIT_LD32(va);
                 HULO_LDTM32(vb, taddr + 32u);
                 process(va, 0u);
                 HULO_WAIT_LD32(vb);
-                if constexpr (!kThree) {
-                    release();
-                    process(vb, 1u);
-                    continue;
-                }
                 HULO_LDTM32(va, taddr + 64u);
                 process(vb, 1u);
                 HULO_WAIT_LD32(va);

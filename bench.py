@@ -812,6 +812,7 @@ def bench_c1(args, rank, world, local_rank):
                "localized": bool(r["localized"]), "centre_error_m": float(np.linalg.norm(r["center"] - sc["center"]))}
         extra = {"sharded_equals_single_gpu": same}
     clocks = sampler.stop()
+    exchange_kind = g.exchange_kind
     if world > 1:
         g.comm_barrier()
     g.close()
@@ -824,8 +825,12 @@ def bench_c1(args, rank, world, local_rank):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD_NAMES["c1"],
                            "sharding": "single GPU" if world == 1 else
-                                       "views of the map sharded over %d ranks for ONE query; one all-gather of the surviving "
-                                       "matches (12 bytes each), resection on every rank" % world},
+                                       "views of the map sharded over %d ranks for ONE query; the surviving matches (12 bytes "
+                                       "each) are exchanged by %s, resection on every rank"
+                                       % (world, "stores from the compaction's output into every rank's peer-mapped buffer "
+                                                 "(NVLink) + flags, one D2H copy per query"
+                                          if exchange_kind == "peer-store" else
+                                          "one ncclAllGather staged through host buffers")},
                 "e2e": {"value": value, "unit": "localizations/s", "h2d_bytes_per_step": 2000 * 64 + 2000 * 16,
                         "d2h_bytes_per_step": 96,
                         "inputs": "query descriptors and keypoints from host memory, pose back, every query"},

@@ -502,8 +502,8 @@ void hulo_gpu_destroy(hulo_gpu *h) {
         if (h->ev_x[p]) cudaEventDestroy(h->ev_x[p]);
     }
     if (h->xstream) cudaStreamDestroy(h->xstream);
-    DevBuf *bufs[] = {&h->partial, &h->partial_alt, &h->counter, &h->items, &h->knn_idx, &h->knn_dist, &h->packed, &h->gathered,
-                      &h->stageA, &h->stageB, &h->scratch0, &h->scratch1, &h->scratch2, &h->scratch3, &h->lfact, &h->wave_counter};
+    DevBuf *bufs[] = {&h->partial, &h->counter, &h->items, &h->knn_idx, &h->knn_dist, &h->packed, &h->gathered,
+                      &h->stageA, &h->stageB, &h->scratch0, &h->scratch1, &h->scratch2, &h->scratch3, &h->lfact, &h->wave_counter, &h->comm_scratch, &h->partial_alt};
     for (DevBuf *b : bufs) b->release();
     for (auto &e : h->tc_images) e.img.release();
     h->tc_scratchA.release();
@@ -677,21 +677,23 @@ int hulo_knn2_host(hulo_gpu *h, const uint8_t *A, size_t nA, size_t strideA, con
 }
 
 // --------------------------------------------- query localisation, reference direction
-int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, size_t n_views,
-                        const uint8_t *query, size_t nq, size_t q_stride, float ratio, uint32_t *out_view,
-                        uint32_t *out_i, uint32_t *out_j, int32_t *out_d0, size_t cap, size_t *n_out,
-                        uint32_t *view_counts) {
-    HULO_ARG(h != nullptr && map != nullptr && n_out != nullptr, "null argument");
+}  // extern "C"
+
+// hulo_match_to_query up to and including the compaction: the survivors stay on the device
+// (out->d_total == nullptr when nothing was searched).  The stream is NOT synchronised.
+int hulo::match_to_query_device(hulo_gpu *h, const hulo_db *map, const uint32_t *views, size_t n_views,
+                                const uint8_t *query, size_t nq, size_t q_stride, float ratio, QueryMatchesDev *out) {
+    HULO_ARG(h != nullptr && map != nullptr && out != nullptr, "null argument");
     HULO_ARG(nq == 0 || query != nullptr, "query is null");
     HULO_ARG(q_stride >= 1, "stride must be >= 1");
     HULO_ARG(nq <= kMaxChunkRows * 64ull, "query too large");
-    *n_out = 0;
+    *out = QueryMatchesDev{};
     HULO_CUDA(cudaSetDevice(h->device));
     HULO_CUDA(join_exchange(h));
     const size_t n_seg = map->seg.size() - 1;
     if (views == nullptr) n_views = n_seg;
     for (size_t v = 0; views && v < n_views; ++v) HULO_ARG(views[v] < n_seg, "view index out of range");
-    if (view_counts) memset(view_counts, 0, n_views * sizeof(uint32_t));
+    out->n_views = n_views;
     // MatchUtils.cpp:299-301: nothing to do without query rows
     if (nq < 1) return HULO_OK;
 
@@ -846,6 +848,30 @@ int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, 
     int32_t *o_d = reinterpret_cast<int32_t *>(o_j + n_rows);
     { int nl = 0; HULO_CUDA(compact_launch(val, dist, (uint32_t)n_rows, h->scratch1.as<uint64_t>(), (uint32_t)n_views, d_blocks,
                              o_view, o_i, o_j, o_d, d_seg_out, d_total, h->stream, &nl)); h->launches += nl; }
+    out->d_total = d_total; out->d_seg_out = d_seg_out;
+    out->o_view = o_view; out->o_i = o_i; out->o_j = o_j; out->o_d = o_d;
+    out->n_rows = n_rows;
+    return HULO_OK;
+}
+
+extern "C" {
+
+int hulo_match_to_query(hulo_gpu *h, const hulo_db *map, const uint32_t *views, size_t n_views,
+                        const uint8_t *query, size_t nq, size_t q_stride, float ratio, uint32_t *out_view,
+                        uint32_t *out_i, uint32_t *out_j, int32_t *out_d0, size_t cap, size_t *n_out,
+                        uint32_t *view_counts) {
+    HULO_ARG(n_out != nullptr, "null argument");
+    *n_out = 0;
+    QueryMatchesDev dm;
+    int rc = match_to_query_device(h, map, views, n_views, query, nq, q_stride, ratio, &dm);
+    if (rc != HULO_OK) return rc;
+    n_views = dm.n_views;
+    if (view_counts) memset(view_counts, 0, n_views * sizeof(uint32_t));
+    if (dm.d_total == nullptr) return nq < 1 ? HULO_OK : hulo_synchronize(h);
+    const uint64_t n_rows = dm.n_rows;
+    const uint64_t *d_total = dm.d_total;
+    const uint32_t *o_view = dm.o_view, *o_i = dm.o_i, *o_j = dm.o_j;
+    const int32_t *o_d = dm.o_d;
 
     // One round trip in the common case: the totals and per-view offsets travel together with the
     // first `spec` survivors of every output array into pinned memory; only a query with more

@@ -116,8 +116,8 @@ int px_setup(hulo_gpu *h, size_t rows) {
     if (ok && cudaMemsetAsync(h->px_own, 0, bytes, h->stream) != cudaSuccess) { cudaGetLastError(); ok = false; }
     if (ok && cudaIpcGetMemHandle(&mine, h->px_own) != cudaSuccess) { cudaGetLastError(); ok = false; }
     // all-gather the 64-byte handles with the communicator that already exists
-    HULO_CUDA(h->scratch2.reserve((size_t)(h->world + 1) * sizeof(cudaIpcMemHandle_t)));
-    uint8_t *d_all = h->scratch2.as<uint8_t>();
+    HULO_CUDA(h->comm_scratch.reserve((size_t)(h->world + 1) * sizeof(cudaIpcMemHandle_t)));
+    uint8_t *d_all = h->comm_scratch.as<uint8_t>();
     uint8_t *d_mine = d_all + (size_t)h->world * sizeof(cudaIpcMemHandle_t);
     HULO_CUDA(cudaMemcpyAsync(d_mine, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
     HULO_NCCL(g_nccl.AllGather(d_mine, d_all, sizeof mine, ncclChar, (ncclComm_t)h->nccl_comm, h->stream));
@@ -169,6 +169,44 @@ int px_setup(hulo_gpu *h, size_t rows) {
 }
 
 }  // namespace
+
+int gather_query_matches(hulo_gpu *h, const QueryMatchesDev &dm, size_t nv_local, size_t max_nv, size_t slots,
+                         uint32_t *all_words) {
+    const char *ex = getenv("HULO_EXCHANGE");
+    if (h->world <= 1 || h->px_disabled || (ex && strcmp(ex, "nccl") == 0)) return kNoPeerExchange;
+    HULO_CUDA(cudaSetDevice(h->device));
+    const size_t words = 1 + max_nv + 3 * slots;
+    const size_t cap16 = (words * sizeof(uint32_t) + 15) / 16;          // 16-byte records per slot
+    if (!h->px_ready || h->px.cap < cap16) {
+        int rc = px_setup(h, std::max<size_t>(cap16, 4096));             // collective: words is the same on every rank
+        if (rc != HULO_OK) return rc;
+        if (!h->px_ready) return kNoPeerExchange;
+    }
+    HULO_CUDA(join_exchange(h));
+    h->px.seq = ++h->px_seq;
+    HULO_CUDA(query_matches_store_peers_launch(dm.d_total, dm.d_seg_out, (uint32_t)nv_local, (uint32_t)max_nv,
+                                               (uint32_t)slots, dm.o_i, dm.o_j, dm.o_d, h->px, h->stream));
+    HULO_CUDA(peers_wait_launch(h->px, h->stream));
+    h->launches += 2;
+    // this rank's buffer now holds every rank's block for this parity, one per slot
+    const size_t pitch = (size_t)h->px.cap * sizeof(int4);
+    HULO_CUDA(h->hstage0.reserve(words * sizeof(uint32_t) * (size_t)h->world + sizeof(unsigned int)));
+    uint8_t *hp = h->hstage0.as<uint8_t>();
+    const uint8_t *src = reinterpret_cast<const uint8_t *>(h->px.records[h->rank]) + (size_t)(h->px.seq & 1u) * h->world * pitch;
+    HULO_CUDA(cudaMemcpy2DAsync(hp, words * sizeof(uint32_t), src, pitch, words * sizeof(uint32_t), (size_t)h->world,
+                                cudaMemcpyDeviceToHost, h->stream));
+    unsigned int *h_status = reinterpret_cast<unsigned int *>(hp + words * sizeof(uint32_t) * (size_t)h->world);
+    HULO_CUDA(cudaMemcpyAsync(h_status, h->px.status, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
+    HULO_CUDA(cudaStreamSynchronize(h->stream));
+    if (*h_status) {
+        HULO_CUDA(cudaMemset(h->px.status, 0, sizeof(unsigned int)));
+        set_error("gather_query_matches: a peer did not deliver its matches within 10 s");
+        return HULO_ERR_NCCL;
+    }
+    memcpy(all_words, hp, words * sizeof(uint32_t) * (size_t)h->world);
+    return HULO_OK;
+}
+
 }  // namespace hulo
 
 using namespace hulo;
@@ -219,8 +257,8 @@ int hulo_comm_max_f64(hulo_gpu *h, double *value) {
     if (!h->nccl_comm) { set_error("hulo_comm_max_f64: communicator not initialised"); return HULO_ERR_NCCL; }
     HULO_CUDA(cudaSetDevice(h->device));
     HULO_CUDA(join_exchange(h));
-    HULO_CUDA(h->scratch2.reserve(64));
-    double *d = h->scratch2.as<double>();
+    HULO_CUDA(h->comm_scratch.reserve(64));
+    double *d = h->comm_scratch.as<double>();
     HULO_CUDA(cudaMemcpyAsync(d, value, sizeof(double), cudaMemcpyHostToDevice, h->stream));
     HULO_NCCL(g_nccl.AllReduce(d, d, 1, ncclDouble, ncclMax, (ncclComm_t)h->nccl_comm, h->stream));
     HULO_CUDA(cudaMemcpyAsync(value, d, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -236,8 +274,8 @@ int hulo_comm_allgather(hulo_gpu *h, const void *send, size_t bytes, void *recv)
     HULO_CUDA(cudaSetDevice(h->device));
     const size_t slot = (bytes + 15) & ~(size_t)15;
     const size_t world = (size_t)h->world;
-    HULO_CUDA(h->scratch2.reserve(slot * (world + 1)));
-    uint8_t *d_all = h->scratch2.as<uint8_t>();
+    HULO_CUDA(h->comm_scratch.reserve(slot * (world + 1)));
+    uint8_t *d_all = h->comm_scratch.as<uint8_t>();
     uint8_t *d_mine = d_all + slot * world;
     // both directions through pinned memory: the caller's buffers are usually pageable, and a
     // pageable copy of this size costs more than the collective

@@ -125,6 +125,7 @@ struct hulo_gpu {
     hulo::DevBuf knn_idx, knn_dist;   // final nA x 2 results
     hulo::DevBuf packed;       // nA x int4 (sharded exchange)
     hulo::DevBuf gathered;     // world x nA x int4
+    hulo::DevBuf comm_scratch; // set-up collectives (IPC handles, barriers): never a buffer a search has results in
     hulo::DevBuf stageA, stageB;      // uploaded rows of the *_host entry points
     hulo::DevBuf scratch0, scratch1, scratch2, scratch3;   // post-processing / K2
     hulo::HostBuf hstage0, hstage1;
@@ -158,6 +159,24 @@ struct hulo_gpu {
 };
 
 namespace hulo {
+// What hulo_match_to_query leaves on the device before its results are fetched: the view-sharded
+// query hands these to the peer exchange instead of copying them out.
+struct QueryMatchesDev {
+    const uint64_t *d_total = nullptr;     // total survivors; nullptr: nothing was searched (no rows / no views)
+    const uint64_t *d_seg_out = nullptr;   // n_views + 1 output offsets (view v: [v], [v + 1])
+    const uint32_t *o_view = nullptr, *o_i = nullptr, *o_j = nullptr;
+    const int32_t *o_d = nullptr;
+    size_t n_views = 0;
+    uint64_t n_rows = 0;
+};
+int match_to_query_device(hulo_gpu *h, const hulo_db *map, const uint32_t *views, size_t n_views, const uint8_t *query,
+                          size_t nq, size_t q_stride, float ratio, QueryMatchesDev *out);
+// The blocks {n_matches, counts[max_nv], (i, j, d0)[slots]} of all ranks, in rank order, into
+// all_words (world x (1 + max_nv + 3 slots) words, host).  Returns kNoPeerExchange when the
+// peers are not mapped (the caller falls back to the host-staged all-gather).
+int gather_query_matches(hulo_gpu *h, const QueryMatchesDev &dm, size_t nv_local, size_t max_nv, size_t slots,
+                         uint32_t *all_words);
+constexpr int kNoPeerExchange = 1000;
 // Make the main stream wait for every exchange still in flight on the exchange stream.
 inline cudaError_t join_exchange(hulo_gpu *h) {
     if (!h->x_pending) return cudaSuccess;

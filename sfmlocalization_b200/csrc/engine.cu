@@ -560,9 +560,7 @@ int hulo_engine_localize_sharded(hulo_engine *e, const uint8_t *qdesc, size_t nq
     e->m_view.resize(cap); e->m_i.resize(cap); e->m_j.resize(cap); e->m_d0.resize(cap);
     std::vector<uint32_t> local_counts(std::max<size_t>(nv, 1), 0);
     size_t n_m = 0;
-    int rc = hulo_match_to_query(e->h, e->map, my_views.data(), nv, qdesc, nq, q_stride, e->ratio, e->m_view.data(),
-                                 e->m_i.data(), e->m_j.data(), e->m_d0.data(), cap, &n_m, local_counts.data());
-    if (rc != HULO_OK) return rc;
+    int rc;
 
     // ---- exchange.  Block of a rank: {n_matches, counts[max_nv], records[slots] of (i, j, d0)}.  One
     // all-gather when every rank's matches fit the slots, else a second one sized by the largest.
@@ -571,6 +569,35 @@ int hulo_engine_localize_sharded(hulo_engine *e, const uint8_t *qdesc, size_t nq
     size_t slots = std::max<size_t>(256, 4 * nq / (size_t)world);
     std::vector<uint32_t> block, all;
     std::vector<uint64_t> rank_n((size_t)world);
+    // Default: the survivors never leave the device on their own -- the compaction's output goes
+    // straight into every rank's peer-mapped exchange buffer (stores over NVLink, flags), and one
+    // copy brings all ranks' blocks to the host: one synchronisation per query.
+    bool on_device = false;
+    if (strcmp(hulo_comm_exchange_kind(e->h), "peer-store") == 0) {
+        hulo::QueryMatchesDev dm;
+        rc = hulo::match_to_query_device(e->h, e->map, my_views.data(), nv, qdesc, nq, q_stride, e->ratio, &dm);
+        if (rc != HULO_OK) return rc;
+        for (int round = 0; round < 2; ++round) {
+            const size_t words = 1 + max_nv + 3 * slots;
+            all.resize(words * (size_t)world);
+            rc = hulo::gather_query_matches(e->h, dm, nv, max_nv, slots, all.data());
+            if (rc == hulo::kNoPeerExchange) break;
+            if (rc != HULO_OK) return rc;
+            on_device = true;
+            size_t largest = 0;
+            for (int r = 0; r < world; ++r) {
+                rank_n[(size_t)r] = all[words * (size_t)r];
+                largest = std::max<size_t>(largest, (size_t)rank_n[(size_t)r]);
+            }
+            if (largest <= slots) break;
+            slots = largest;                   // the same decision on every rank
+        }
+    }
+    if (!on_device) {
+    // peers not mappable (or HULO_EXCHANGE=nccl): matches to the host, all-gather staged through host buffers
+    rc = hulo_match_to_query(e->h, e->map, my_views.data(), nv, qdesc, nq, q_stride, e->ratio, e->m_view.data(),
+                             e->m_i.data(), e->m_j.data(), e->m_d0.data(), cap, &n_m, local_counts.data());
+    if (rc != HULO_OK) return rc;
     for (int round = 0; round < 2; ++round) {
         const size_t words = 1 + max_nv + 3 * slots;
         block.assign(words, 0);
@@ -592,6 +619,7 @@ int hulo_engine_localize_sharded(hulo_engine *e, const uint8_t *qdesc, size_t nq
         }
         if (largest <= slots) break;
         slots = largest;                       // the same decision on every rank
+    }
     }
     // the matches of all views in list order: exactly what one GPU emits for the whole list
     const size_t words = 1 + max_nv + 3 * slots;

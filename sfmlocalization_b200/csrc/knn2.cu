@@ -458,6 +458,56 @@ __global__ void knn2_merge_store_peers_kernel(const uint2 *__restrict__ partial,
     }
 }
 
+// The view-sharded query's exchange on the same buffers: this rank's surviving matches go from
+// the compaction's output arrays straight into slot [seq&1][rank] of every rank's buffer as the
+// block {n_matches, counts[max_nv], (i, j, d0)[min(n_matches, slots)]} of 32-bit words.
+__global__ void query_matches_store_peers_kernel(const uint64_t *__restrict__ d_total,
+                                                 const uint64_t *__restrict__ d_seg_out, uint32_t nv_local,
+                                                 uint32_t max_nv, uint32_t slots, const uint32_t *__restrict__ o_i,
+                                                 const uint32_t *__restrict__ o_j, const int32_t *__restrict__ o_d,
+                                                 const PeerExchange px) {
+    const uint64_t total = d_total ? *d_total : 0ull;
+    const uint32_t n_fit = (uint32_t)(total < (uint64_t)slots ? total : (uint64_t)slots);
+    const uint32_t n_words = 1u + max_nv + 3u * n_fit;
+    const size_t slot = ((size_t)(px.seq & 1u) * px.world + px.rank) * px.cap;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) {
+        uint32_t v;
+        if (w == 0) {
+            v = (uint32_t)total;
+        } else if (w <= max_nv) {
+            const uint32_t k = w - 1u;
+            v = (d_seg_out && k < nv_local) ? (uint32_t)(d_seg_out[k + 1] - d_seg_out[k]) : 0u;
+        } else {
+            const uint32_t r = w - 1u - max_nv, k = r / 3u, c = r - 3u * k;
+            v = c == 0u ? o_i[k] : c == 1u ? o_j[k] : (uint32_t)o_d[k];
+        }
+        for (int g = 0; g < px.world; ++g) reinterpret_cast<uint32_t *>(px.records[g] + slot)[w] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(px.done_counter, 1u) + 1u;
+        if (done == gridDim.x) {
+            *px.done_counter = 0u;
+            __threadfence_system();
+            for (int g = 0; g < px.world; ++g)
+                st_release_sys(px.flags[g] + (size_t)(px.seq & 1u) * px.world + px.rank, px.seq);
+        }
+    }
+}
+
+// Wait (bounded) until every rank's block for `seq` has landed in the local buffer.
+__global__ void peers_wait_kernel(const PeerExchange px) {
+    const int g = threadIdx.x;
+    if (g >= px.world) return;
+    const uint32_t *fl = px.flags[px.rank] + (size_t)(px.seq & 1u) * px.world;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(fl + g) != px.seq) {
+        if (clock64() - t0 > 20000000000ll) { *px.status = 1u; break; }      // ~10 s
+        __nanosleep(200);
+    }
+}
+
 __global__ void knn2_merge_from_peers_kernel(const PeerExchange px, uint32_t nA, int32_t *out_idx2,
                                              int32_t *out_dist2) {
     __shared__ int s_ok;
@@ -623,6 +673,18 @@ cudaError_t knn2_merge_from_peers_launch(const PeerExchange &px, uint32_t nA, in
     const int threads = 256;
     const uint32_t blocks = nA == 0 ? 1 : (nA + threads - 1) / threads;
     knn2_merge_from_peers_kernel<<<blocks, threads, 0, stream>>>(px, nA, out_idx2, out_dist2);
+    return cudaGetLastError();
+}
+
+cudaError_t query_matches_store_peers_launch(const uint64_t *d_total, const uint64_t *d_seg_out, uint32_t nv_local,
+                                             uint32_t max_nv, uint32_t slots, const uint32_t *o_i, const uint32_t *o_j,
+                                             const int32_t *o_d, const PeerExchange &px, cudaStream_t stream) {
+    query_matches_store_peers_kernel<<<16, 256, 0, stream>>>(d_total, d_seg_out, nv_local, max_nv, slots, o_i, o_j, o_d, px);
+    return cudaGetLastError();
+}
+
+cudaError_t peers_wait_launch(const PeerExchange &px, cudaStream_t stream) {
+    peers_wait_kernel<<<1, 32, 0, stream>>>(px);
     return cudaGetLastError();
 }
 

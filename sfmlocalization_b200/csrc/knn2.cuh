@@ -102,5 +102,11 @@ cudaError_t knn2_merge_store_peers_launch(const uint2 *partial, uint32_t nA, uin
 // merge them per row on (distance, global index).
 cudaError_t knn2_merge_from_peers_launch(const PeerExchange &px, uint32_t nA, int32_t *out_idx2,
                                          int32_t *out_dist2, cudaStream_t stream);
+// The view-sharded query on the same buffers (16 bytes of a slot = 4 words): store this rank's block
+// {n_matches, counts[max_nv], (i, j, d0)[<= slots]} into every rank's buffer, then wait for all blocks.
+cudaError_t query_matches_store_peers_launch(const uint64_t *d_total, const uint64_t *d_seg_out, uint32_t nv_local,
+                                             uint32_t max_nv, uint32_t slots, const uint32_t *o_i, const uint32_t *o_j,
+                                             const int32_t *o_d, const PeerExchange &px, cudaStream_t stream);
+cudaError_t peers_wait_launch(const PeerExchange &px, cudaStream_t stream);
 
 }  // namespace hulo

@@ -131,6 +131,27 @@ def test_acransac_recovers_pose(gpu, orc, N, outl, seed):
     assert r["error_max"] < 2.0 * o["error_max"] + 0.5
 
 
+def test_acransac_above_the_register_sort_limit(gpu, orc):
+    """More than 4096 correspondences: the host-drawn three-kernel waves (shared-memory sort)
+    instead of the two-launch waves of the smaller problems."""
+    sc = synth.resection_scene(5000, 977, outlier_frac=0.5)
+    r = gpu.resect_acransac(sc["x2d"], sc["X3d"], sc["K"], max_iter=1024, seed=3)
+    assert r["found"]
+    _, R, _, c = orc.krt_from_p(r["P"])
+    assert np.linalg.norm(c - (-sc["R"].T @ sc["t"])) < 0.05
+    assert np.abs(R - sc["R"]).max() < 5e-3
+    inl = set(r["inliers"].tolist())
+    truth = set(np.nonzero(sc["inlier_mask"])[0].tolist())
+    assert len(inl & truth) >= 0.85 * len(truth)
+    # and a problem just inside the limit gives the same answer through the batch entry point,
+    # whose waves are host-drawn: same draws, same models, same decisions
+    sc = synth.resection_scene(4096, 978, outlier_frac=0.5)
+    one = gpu.resect_acransac(sc["x2d"], sc["X3d"], sc["K"], max_iter=1024, seed=4)
+    many = gpu.resect_acransac_batch(sc["x2d"], sc["X3d"], [0, 4096], sc["K"], max_iter=1024, seeds=[4])[0]
+    assert one["found"] and many["found"]
+    assert np.array_equal(one["P"], many["P"]) and np.array_equal(one["inliers"], many["inliers"])
+
+
 def test_acransac_not_found_cases(gpu):
     sc = synth.resection_scene(3, 1, outlier_frac=0.0)
     r = gpu.resect_acransac(sc["x2d"], sc["X3d"], sc["K"])

@@ -444,6 +444,7 @@ def localize_bench(g, with_cpu=True, reps=20):
     for k in range(3):
         r = eng.localize(sc["q_desc"], sc["q_xy"], seed=k)
     wall, stages, ok, err = [], [], 0, []
+    launches0 = g.launch_count()
     for k in range(reps):
         t0 = time.perf_counter()
         r = eng.localize(sc["q_desc"], sc["q_xy"], seed=100 + k)
@@ -452,6 +453,7 @@ def localize_bench(g, with_cpu=True, reps=20):
         if r["localized"]:
             ok += 1
             err.append(float(np.linalg.norm(r["center"] - sc["center"])))
+    launches_per_query = (g.launch_count() - launches0) / max(reps, 1)
     # the same with the F-matrix geometric filter between matching and assembly
     # (hulo::geometricMatch, LocalizeEngine.cc:458; ransacRound 25, precision 4 px: LocalizeParam.py:35)
     eng.set_keypoints(sc["map_xy"], sc["view_wh"], synth.IMAGE_WH)
@@ -486,6 +488,7 @@ def localize_bench(g, with_cpu=True, reps=20):
            "stage_ms": {"putMatch": float(st[0]), "assembly": float(st[1]), "PnP": float(st[2])},
            "fraction_localized": ok / reps, "centre_error_m_median": float(np.median(err)) if err else None,
            "correspondences": int(len(r["corr_qfeat"])), "inliers": int(len(r["inliers"])),
+           "kernel_launches_per_query": launches_per_query,
            "target_ms": 5.0,
            "with_geometric_filter": {
                "ms_per_query": float(np.median(gwall)), "localizations_per_s": 1e3 / float(np.median(gwall)),
@@ -790,11 +793,14 @@ def bench_c1(args, rank, world, local_rank):
             eng.localize_sharded(sc["q_desc"], sc["q_xy"], seed=k)
         steps = max(args.steps, 20)
         wall, stages = [], []
+        launches_q = 0
         for k in range(steps):
             g.comm_barrier()
+            l0 = g.launch_count()
             t0 = time.perf_counter()
             r = eng.localize_sharded(sc["q_desc"], sc["q_xy"], seed=100 + k)
             dt = (time.perf_counter() - t0) * 1e3
+            launches_q = g.launch_count() - l0
             wall.append(g.comm_max(dt))
             stages.append(r["times_ms"])
         single = eng.localize(sc["q_desc"], sc["q_xy"], seed=100 + steps - 1)        # the same seed on one GPU
@@ -810,6 +816,7 @@ def bench_c1(args, rank, world, local_rank):
         loc = {"workload": WORKLOAD_NAMES["c1"], "ms_per_query": ms, "localizations_per_s": value,
                "stage_ms": {"putMatch_incl_exchange": float(st[0]), "assembly": float(st[1]), "PnP": float(st[2])},
                "localized": bool(r["localized"]), "centre_error_m": float(np.linalg.norm(r["center"] - sc["center"]))}
+        loc["kernel_launches_per_query"] = launches_q
         extra = {"sharded_equals_single_gpu": same}
     clocks = sampler.stop()
     exchange_kind = g.exchange_kind
@@ -834,7 +841,7 @@ def bench_c1(args, rank, world, local_rank):
                 "e2e": {"value": value, "unit": "localizations/s", "h2d_bytes_per_step": 2000 * 64 + 2000 * 16,
                         "d2h_bytes_per_step": 96,
                         "inputs": "query descriptors and keypoints from host memory, pose back, every query"},
-                "gpu_launches": 11, "clocks": clocks, "localize": loc, "cpu_baseline": loc.get("cpu_baseline")}
+                "gpu_launches": int(round(loc["kernel_launches_per_query"] * steps)), "clocks": clocks, "localize": loc, "cpu_baseline": loc.get("cpu_baseline")}
         line.update(extra)
         print(json.dumps(line))
         if extra and not extra["sharded_equals_single_gpu"]:

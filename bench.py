@@ -444,7 +444,7 @@ def localize_bench(g, with_cpu=True, reps=20):
     for k in range(3):
         r = eng.localize(sc["q_desc"], sc["q_xy"], seed=k)
     wall, stages, ok, err = [], [], 0, []
-    launches0 = g.launch_count()
+    launches0 = g.launch_count
     for k in range(reps):
         t0 = time.perf_counter()
         r = eng.localize(sc["q_desc"], sc["q_xy"], seed=100 + k)
@@ -453,7 +453,7 @@ def localize_bench(g, with_cpu=True, reps=20):
         if r["localized"]:
             ok += 1
             err.append(float(np.linalg.norm(r["center"] - sc["center"])))
-    launches_per_query = (g.launch_count() - launches0) / max(reps, 1)
+    launches_per_query = (g.launch_count - launches0) / max(reps, 1)
     # the same with the F-matrix geometric filter between matching and assembly
     # (hulo::geometricMatch, LocalizeEngine.cc:458; ransacRound 25, precision 4 px: LocalizeParam.py:35)
     eng.set_keypoints(sc["map_xy"], sc["view_wh"], synth.IMAGE_WH)
@@ -796,11 +796,11 @@ def bench_c1(args, rank, world, local_rank):
         launches_q = 0
         for k in range(steps):
             g.comm_barrier()
-            l0 = g.launch_count()
+            l0 = g.launch_count
             t0 = time.perf_counter()
             r = eng.localize_sharded(sc["q_desc"], sc["q_xy"], seed=100 + k)
             dt = (time.perf_counter() - t0) * 1e3
-            launches_q = g.launch_count() - l0
+            launches_q = g.launch_count - l0
             wall.append(g.comm_max(dt))
             stages.append(r["times_ms"])
         single = eng.localize(sc["q_desc"], sc["q_xy"], seed=100 + steps - 1)        # the same seed on one GPU

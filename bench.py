@@ -243,6 +243,16 @@ def leg_parity(args):
     print(json.dumps({"queries": PARITY_QUERIES, "map_rows": N_MAP, "cores": threads}))
 
 
+def matching_dtype(g):
+    """Arithmetic type of the 2-NN behind the matchers on this context: the tensor-core engine's
+    operand type when the engine setting lets searches of this size use it, else the integer pipes."""
+    if g.knn_engine == "int":
+        return "u32"
+    if g.knn_engine == "tc8":
+        return "s8"
+    return "fp4" if os.environ.get("HULO_TC_BITS", "4") != "8" else "s8"
+
+
 def c1_scene():
     return synth.localization_scene(100, 2000, 20000, 2000, 1000)
 
@@ -886,7 +896,7 @@ def bench_pairs(args, rank, world, local_rank):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
                 "warmup": max(1, min(args.warmup, 2)), "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None, "dtype": matching_dtype(g), "data": "synthetic",
                 "config": {"workload": WORKLOAD_NAMES["c2"],
                            "sharding": "pair list partitioned over %d rank(s) by n_I x n_J (LPT), descriptors (64 MB) "
                                        "replicated, no data-path collective" % world,
@@ -960,7 +970,7 @@ def bench_server(args, rank, world, local_rank):
         map_rows = int(sc["rows"].shape[0])
         line = {"metric": "query_localizations_per_s", "value": value, "unit": "localizations/s", "n_gpus": world,
                 "steps": steps, "warmup": 2, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "u32 / f32", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None, "dtype": matching_dtype(g) + " / f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD_NAMES["c4"],
                            "sharding": "queries over %d rank(s), map (%d rows, %d MB) replicated, no data-path "
                                        "collective" % (world, map_rows, map_rows * 64 // 10**6),

@@ -1198,7 +1198,12 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
                     const cudaError_t q = cudaStreamQuery(h->stream);
                     if (q != cudaErrorNotReady) {
                         HULO_CUDA(q);
-                        if (*rec_seq != seq) { set_error("hulo_resect_acransac: the wave finished without its record"); return HULO_ERR_CUDA; }
+                        if (*rec_seq != seq) {
+                            // an earlier wave died half-way and left its blocks-done count behind: start clean next time
+                            cudaMemsetAsync(h->wave_counter.ptr, 0, sizeof(unsigned int), h->stream);
+                            set_error("hulo_resect_acransac: the wave finished without its record");
+                            return HULO_ERR_CUDA;
+                        }
                     }
                 }
 #if defined(__x86_64__)

@@ -206,6 +206,14 @@ int hulo_resect_acransac(hulo_gpu *h, const double *x2d, const double *X3d, size
                          const double *K, size_t max_iter, uint64_t seed, double *P,
                          int32_t *inliers, size_t *n_inliers, double *error_max, int *found);
 
+/* Host-only self-test (no device needed) of the fp64 rescoring behind hulo_resect_acransac: the
+ * production form (radix sort of the residuals' upper key halves with repair of equal runs, NFA
+ * minimum found through a float bracket and evaluated exactly only where the bracket allows) against
+ * a comparison sort and the full log10 scan, on n_cases seeded sets of n_points correspondences with
+ * inliers, outliers, exact duplicates and points on the principal plane.  *n_mismatch = number of
+ * sets on which order, k, k-th residual or NFA differ in any bit (expected: 0). */
+int hulo_selftest_rescoring(uint64_t seed, size_t n_points, size_t n_cases, size_t *n_mismatch);
+
 /* The same with the SEQUENTIAL schedule of openMVG::robust::ACRANSAC kept to the letter: the
  * global phase ends at the first meaningful model in draw order, the pool narrows again at every
  * improvement during the reserved iterations, and a model replaces the best so far only in draw

@@ -61,6 +61,7 @@ SIGNATURES = {
                                        C.POINTER(_f64), C.POINTER(C.c_int)]),
     "hulo_resect_acransac_sequential": (C.c_int, [_vp, _vp, _vp, _sz, _vp, _sz, _u64, _vp, _vp, C.POINTER(_sz),
                                                   C.POINTER(_f64), C.POINTER(C.c_int)]),
+    "hulo_selftest_rescoring": (C.c_int, [_u64, _sz, _sz, C.POINTER(_sz)]),
     "hulo_resect_acransac_batch": (C.c_int, [_vp, _sz, _vp, _vp, _vp, _vp, _sz, _u64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hulo_pose_from_projection": (C.c_int, [_vp, _vp, _vp, _vp]),
     "hulo_geometric_filter": (C.c_int, [_vp, _vp, _vp, _vp, _sz, _vp, _f64, _sz, _u64, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -1451,6 +1451,77 @@ static inline float device_residual(const double *M, const double *X, const doub
     return e == e ? e : INFINITY;
 }
 
+// Host-only self-test of the fp64 rescoring (no device involved): ResectJob::finalize -- radix sort
+// of the upper key halves + repair, bracketed NFA scan -- against a comparison sort and the full
+// scan with log10 on every term, over seeded correspondence sets with clustered inliers, uniform
+// outliers, exact duplicates (ties in the residual) and points on the principal plane (infinite or
+// NaN residuals).  The two must agree bit for bit: order, k, the k-th residual and the NFA.
+int hulo_selftest_rescoring(uint64_t seed, size_t n_points, size_t n_cases, size_t *n_mismatch) {
+    HULO_ARG(n_mismatch != nullptr, "null argument");
+    HULO_ARG(n_points <= kMaxPoints, "more than 32768 correspondences");
+    *n_mismatch = 0;
+    const size_t N = n_points;
+    if (N <= 3) return HULO_OK;
+    const double K[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    const double M[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    std::vector<double> x2d(2 * N), X3d(3 * N);
+    uint64_t rng = seed * 0x9E3779B97F4A7C15ULL + 12345;
+    auto uni = [&]() { return (double)(splitmix64(rng) >> 11) * (1.0 / 9007199254740992.0); };
+    for (size_t c = 0; c < n_cases; ++c) {
+        const double inlier_frac = 0.1 + 0.8 * uni(), sigma = std::pow(10.0, -5.0 + 3.0 * uni());
+        for (size_t i = 0; i < N; ++i) {
+            const double r = uni();
+            if (i > 0 && r < 0.05) {                           // exact duplicate of an earlier point
+                const size_t j = (size_t)(uni() * (double)i);
+                for (int k = 0; k < 3; ++k) X3d[3 * i + k] = X3d[3 * j + k];
+                x2d[2 * i] = x2d[2 * j]; x2d[2 * i + 1] = x2d[2 * j + 1];
+                continue;
+            }
+            const double X = 2.0 * uni() - 1.0, Y = 2.0 * uni() - 1.0;
+            double Z = 1.0 + uni();
+            if (r > 0.98) Z = 0.0;                             // on the principal plane
+            const bool inl = uni() < inlier_frac;
+            const double dx = inl ? sigma * (uni() - 0.5) : 2.0 * uni() - 1.0;
+            const double dy = inl ? sigma * (uni() - 0.5) : 2.0 * uni() - 1.0;
+            X3d[3 * i] = X * Z; X3d[3 * i + 1] = Y * Z; X3d[3 * i + 2] = Z;
+            x2d[2 * i] = X + dx; x2d[2 * i + 1] = Y + dy;
+            if (r > 0.99) { X3d[3 * i] = 0.0; X3d[3 * i + 1] = 0.0; }     // 0 / 0
+        }
+        ResectJob job;
+        job.init(x2d.data(), X3d.data(), N, K, 4096, seed + c);
+        const double got = job.finalize(M);
+        // the plain form
+        std::vector<ResectJob::EI> ref(N);
+        for (size_t i = 0; i < N; ++i) {
+            const double *X = X3d.data() + 3 * i;
+            const double u = M[0] * X[0] + M[1] * X[1] + M[2] * X[2] + M[3];
+            const double v = M[4] * X[0] + M[5] * X[1] + M[6] * X[2] + M[7];
+            const double w = M[8] * X[0] + M[9] * X[1] + M[10] * X[2] + M[11];
+            const double dx = u / w - job.x2dn[2 * i], dy = v / w - job.x2dn[2 * i + 1];
+            double e = dx * dx + dy * dy;
+            if (!(e == e)) e = INFINITY;
+            ref[i] = ResectJob::EI{e, i};
+        }
+        std::sort(ref.begin(), ref.end(),
+                  [](const ResectJob::EI &a, const ResectJob::EI &b) { return a.e < b.e || (a.e == b.e && a.i < b.i); });
+        double bn = INFINITY;
+        size_t bk = 3;
+        for (size_t k = 4; k <= N; ++k) {
+            if (!(ref[k - 1].e < INFINITY)) break;
+            const double logalpha = job.logalpha0 + log10(ref[k - 1].e + (double)FLT_EPSILON);
+            const double nfa = job.loge0 + logalpha * (double)(k - 3) + (double)job.lcn[k] + (double)job.lck[k];
+            if (nfa < bn) { bn = nfa; bk = k; }
+        }
+        bool same = memcmp(&bn, &got, sizeof bn) == 0 && bk == job.best_k;
+        const double want_err = bk >= 1 ? ref[bk - 1].e : 0.0;
+        same = same && memcmp(&want_err, &job.best_err, sizeof want_err) == 0;
+        for (size_t i = 0; same && i < N; ++i)
+            same = ref[i].i == job.ei[i].i && memcmp(&ref[i].e, &job.ei[i].e, sizeof(double)) == 0;
+        if (!same) ++*n_mismatch;
+    }
+    return HULO_OK;
+}
+
 int hulo_resect_acransac_sequential(hulo_gpu *h, const double *x2d, const double *X3d, size_t N, const double *K,
                                     size_t max_iter, uint64_t seed, double *P, int32_t *inliers, size_t *n_inliers,
                                     double *error_max, int *found) {

@@ -462,6 +462,18 @@ int hulo_partition_views(const uint64_t *rows_per_view, size_t n_views, int worl
 int hulo_knn2_sharded(hulo_gpu *h, const hulo_db *A, const hulo_db *B_shard, uint64_t row_base,
                       int32_t *idx2, int32_t *dist2);
 
+/* The same search for a STREAM of searcher tables (a server answering query batch after query
+ * batch): hulo_knn2_sharded_submit issues search s and returns at once; hulo_knn2_sharded_collect
+ * returns the results of the oldest search not collected yet.  At most two searches may be
+ * outstanding (the result arrays are double-buffered), so the pattern is
+ *   submit(0); for k = 1..: { hulo_db_update(A, batch k); submit(k); collect(k - 1); }  collect(last);
+ * and the device never waits for the host: the exchange of search k - 1 and the copy of its
+ * results (on a stream of their own) overlap the K1 of search k.  Results are those of
+ * hulo_knn2_sharded, bit for bit.  Works on a world of one as well (no exchange, the result
+ * copy still overlaps the next search). */
+int hulo_knn2_sharded_submit(hulo_gpu *h, const hulo_db *A, const hulo_db *B_shard, uint64_t row_base);
+int hulo_knn2_sharded_collect(hulo_gpu *h, int32_t *idx2, int32_t *dist2, size_t *n_rows);
+
 /* The merge step on its own, for hosts that move the candidates themselves (another
  * transport, several nodes): cand holds `world` lists of nA records {d0, i0, d1, i1} (int32,
  * global indices, HULO_IDX_NONE / HULO_DIST_NONE for a missing neighbour), list after list.

@@ -96,6 +96,8 @@ SIGNATURES = {
     "hulo_comm_barrier": (C.c_int, [_vp]),
     "hulo_comm_max_f64": (C.c_int, [_vp, C.POINTER(_f64)]),
     "hulo_knn2_sharded": (C.c_int, [_vp, _vp, _vp, _u64, _vp, _vp]),
+    "hulo_knn2_sharded_submit": (C.c_int, [_vp, _vp, _vp, _u64]),
+    "hulo_knn2_sharded_collect": (C.c_int, [_vp, _vp, _vp, C.POINTER(_sz)]),
     "hulo_merge_top2": (C.c_int, [_vp, _vp, _sz, C.c_int, _vp, _vp]),
 }
 

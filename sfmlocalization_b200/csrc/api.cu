@@ -306,6 +306,9 @@ static int run_flat_k1_tc(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B
 int run_flat_k1(hulo_gpu *h, const uint4 *A, size_t nA, const uint4 *B, size_t nB, uint32_t row_base,
                 FlatRun *run) {
     HULO_ARG(nA < (size_t)INT_MAX && nB + (size_t)row_base < (size_t)INT_MAX, "table too large for int32 indices");
+    // a plain search would overwrite the result set of the latest submitted one
+    HULO_ARG(h->in_submit || h->pipe_submitted == h->pipe_collected,
+             "searches issued with hulo_knn2_sharded_submit are outstanding: collect them first");
     HULO_CUDA(h->knn_idx.reserve(std::max<size_t>(nA, 1) * 2 * sizeof(int32_t)));
     HULO_CUDA(h->knn_dist.reserve(std::max<size_t>(nA, 1) * 2 * sizeof(int32_t)));
     h->last_nA = nA;
@@ -502,8 +505,11 @@ void hulo_gpu_destroy(hulo_gpu *h) {
         if (h->ev_x[p]) cudaEventDestroy(h->ev_x[p]);
     }
     if (h->xstream) cudaStreamDestroy(h->xstream);
+    if (h->cstream) { cudaStreamSynchronize(h->cstream); cudaStreamDestroy(h->cstream); }
+    for (int q = 0; q < 2; ++q)
+        if (h->ev_res[q]) cudaEventDestroy(h->ev_res[q]);
     DevBuf *bufs[] = {&h->partial, &h->counter, &h->items, &h->knn_idx, &h->knn_dist, &h->packed, &h->gathered,
-                      &h->stageA, &h->stageB, &h->scratch0, &h->scratch1, &h->scratch2, &h->scratch3, &h->lfact, &h->wave_counter, &h->comm_scratch, &h->partial_alt};
+                      &h->stageA, &h->stageB, &h->scratch0, &h->scratch1, &h->scratch2, &h->scratch3, &h->lfact, &h->wave_counter, &h->comm_scratch, &h->partial_alt, &h->knn_idx_alt, &h->knn_dist_alt};
     for (DevBuf *b : bufs) b->release();
     for (auto &e : h->tc_images) e.img.release();
     h->tc_scratchA.release();

@@ -374,9 +374,65 @@ int hulo_knn2_sharded(hulo_gpu *h, const hulo_db *A, const hulo_db *B_shard, uin
     return HULO_OK;
 }
 
+int hulo_knn2_sharded_submit(hulo_gpu *h, const hulo_db *A, const hulo_db *B_shard, uint64_t row_base) {
+    HULO_ARG(h != nullptr && A != nullptr && B_shard != nullptr, "null argument");
+    HULO_ARG(h->pipe_submitted - h->pipe_collected < 2, "two searches are outstanding: collect one first");
+    HULO_CUDA(cudaSetDevice(h->device));
+    if (!h->cstream) {
+        HULO_CUDA(cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
+        for (int q = 0; q < 2; ++q) HULO_CUDA(cudaEventCreateWithFlags(&h->ev_res[q], cudaEventDisableTiming));
+    }
+    const int q = (int)(h->pipe_submitted & 1);
+    // this search's results go to the set that was collected longest ago
+    std::swap(h->knn_idx, h->knn_idx_alt);
+    std::swap(h->knn_dist, h->knn_dist_alt);
+    h->in_submit = true;
+    int rc = hulo_knn2_sharded(h, A, B_shard, row_base, nullptr, nullptr);
+    h->in_submit = false;
+    if (rc != HULO_OK) return rc;
+    // the results are complete where the search ends: on the exchange stream when it ran there
+    HULO_CUDA(cudaEventRecord(h->ev_res[q], h->x_pending ? h->xstream : h->stream));
+    h->pipe_slot[q].idx = h->knn_idx.ptr;
+    h->pipe_slot[q].dist = h->knn_dist.ptr;
+    h->pipe_slot[q].nA = A->n;
+    h->pipe_slot[q].busy = true;
+    ++h->pipe_submitted;
+    return HULO_OK;
+}
+
+int hulo_knn2_sharded_collect(hulo_gpu *h, int32_t *idx2, int32_t *dist2, size_t *n_rows) {
+    HULO_ARG(h != nullptr, "null context");
+    HULO_ARG(h->pipe_collected < h->pipe_submitted, "nothing was submitted");
+    HULO_CUDA(cudaSetDevice(h->device));
+    const int q = (int)(h->pipe_collected & 1);
+    hulo_gpu::PipeSlot &sl = h->pipe_slot[q];
+    if (n_rows) *n_rows = sl.nA;
+    HULO_CUDA(cudaStreamWaitEvent(h->cstream, h->ev_res[q], 0));
+    if (sl.nA > 0) {
+        if (idx2) HULO_CUDA(cudaMemcpyAsync(idx2, sl.idx, sl.nA * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->cstream));
+        if (dist2) HULO_CUDA(cudaMemcpyAsync(dist2, sl.dist, sl.nA * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->cstream));
+    }
+    HULO_CUDA(cudaStreamSynchronize(h->cstream));
+    sl.busy = false;
+    ++h->pipe_collected;
+    if (h->world > 1 && h->px_ready) {
+        unsigned int st = 0;
+        HULO_CUDA(cudaMemcpyAsync(&st, h->px.status, sizeof st, cudaMemcpyDeviceToHost, h->cstream));
+        HULO_CUDA(cudaStreamSynchronize(h->cstream));
+        if (st) {
+            HULO_CUDA(cudaMemsetAsync(h->px.status, 0, sizeof st, h->cstream));
+            set_error("hulo_knn2_sharded_collect: a peer did not deliver its candidates within 10 s");
+            return HULO_ERR_NCCL;
+        }
+    }
+    return HULO_OK;
+}
+
 int hulo_merge_top2(hulo_gpu *h, const int32_t *cand, size_t nA, int world, int32_t *idx2, int32_t *dist2) {
     HULO_ARG(h != nullptr && world >= 1, "bad argument");
     HULO_ARG(nA == 0 || (cand != nullptr && idx2 != nullptr && dist2 != nullptr), "null argument");
+    HULO_ARG(h->pipe_submitted == h->pipe_collected,
+             "searches issued with hulo_knn2_sharded_submit are outstanding: collect them first");
     HULO_CUDA(cudaSetDevice(h->device));
     HULO_CUDA(join_exchange(h));
     HULO_CUDA(h->knn_idx.reserve(std::max<size_t>(nA, 1) * 2 * sizeof(int32_t)));

@@ -156,6 +156,14 @@ struct hulo_gpu {
     hulo::DevBuf partial_alt;
     bool x_pending = false;
     int x_last = 0;
+    // hulo_knn2_sharded_submit / _collect: two result sets, one event each (results complete),
+    // a stream for the result copies so that they never queue behind the next search's K1
+    hulo::DevBuf knn_idx_alt, knn_dist_alt;
+    struct PipeSlot { const void *idx = nullptr, *dist = nullptr; size_t nA = 0; bool busy = false; } pipe_slot[2];
+    cudaEvent_t ev_res[2] = {nullptr, nullptr};
+    cudaStream_t cstream = nullptr;
+    uint64_t pipe_submitted = 0, pipe_collected = 0;
+    bool in_submit = false;            // the search being issued is a submit (it may run while others are outstanding)
 };
 
 namespace hulo {

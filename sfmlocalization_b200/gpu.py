@@ -169,6 +169,22 @@ class HuloGpu:
         check(self.lib.hulo_knn2_sharded(self.h, A.h, B_shard.h, row_base, _ptr(idx2), _ptr(dist2)))
         return idx2, dist2
 
+    def knn2_sharded_submit(self, A, B_shard, row_base):
+        """Pipelined form: issue the search and return at once (see knn2_sharded_collect)."""
+        check(self.lib.hulo_knn2_sharded_submit(self.h, A.h, B_shard.h, row_base))
+        self._pipe_rows = getattr(self, "_pipe_rows", [])
+        self._pipe_rows.append(len(A))
+
+    def knn2_sharded_collect(self, idx2=None, dist2=None):
+        """Results of the oldest submitted search not collected yet -> (idx2, dist2)."""
+        nA = self._pipe_rows.pop(0)
+        idx2 = np.empty((nA, 2), np.int32) if idx2 is None else idx2
+        dist2 = np.empty((nA, 2), np.int32) if dist2 is None else dist2
+        n = C.c_size_t(0)
+        check(self.lib.hulo_knn2_sharded_collect(self.h, _ptr(idx2), _ptr(dist2), C.byref(n)))
+        assert n.value == nA
+        return idx2, dist2
+
     def merge_top2(self, cand):
         """cand: world x nA x 4 int32 records {d0, i0, d1, i1} with global indices."""
         cand = np.ascontiguousarray(cand, np.int32)

@@ -181,6 +181,16 @@ def main():
             wi_, wd_ = orc.knn2(A_rev, B[lo:hi])
             assert np.array_equal(li_, wi_) and np.array_equal(ld_, wd_)
         g.set_knn_engine("auto")
+        # submit / collect: results one search behind, each equal to the blocking call
+        g.knn2_sharded_submit(dA, dB, lo)
+        g.knn2_sharded_submit(dAr, dB, lo)
+        first = g.knn2_sharded_collect()
+        g.knn2_sharded_submit(dA, dB, lo)
+        second = g.knn2_sharded_collect()
+        third = g.knn2_sharded_collect()
+        assert np.array_equal(first[0], results[0][0]) and np.array_equal(first[1], results[0][1])
+        assert np.array_equal(second[0], results[0][0][::-1]) and np.array_equal(second[1], results[0][1][::-1])
+        assert np.array_equal(third[0], results[0][0]) and np.array_equal(third[1], results[0][1])
         dAr.free()
         for (i_, d_) in results:
             assert np.array_equal(i_, results[0][0]) and np.array_equal(d_, results[0][1])

@@ -80,6 +80,41 @@ def test_device_resident_tables(gpu, orc):
     assert np.array_equal(idx[hit, 0], target[hit])
 
 
+def test_submit_collect_pipeline(gpu, orc):
+    """hulo_knn2_sharded_submit / _collect on a world of one: a stream of searcher batches through one
+    table object, results collected one search behind, each equal to the blocking call; the
+    outstanding-search limits are errors, not overwrites."""
+    from sfmlocalization_b200.gpu import HuloError, check
+    batches = [synth.descriptor_sets(900, 40000, 300 + k)[0] for k in range(5)]
+    _, B, _ = synth.descriptor_sets(8, 40000, 299)
+    want = [orc.knn2(a, B) for a in batches]
+    dA, dB = gpu.db(batches[0]), gpu.db(B)
+    try:
+        got = []
+        gpu.knn2_sharded_submit(dA, dB, 0)
+        for k in range(1, len(batches)):
+            dA.update(batches[k])
+            gpu.knn2_sharded_submit(dA, dB, 0)
+            got.append(gpu.knn2_sharded_collect())
+        with pytest.raises(HuloError):                    # a plain search would clobber the outstanding one
+            gpu.knn2(dA, dB)
+        got.append(gpu.knn2_sharded_collect())
+        for (gi, gd), (wi, wd) in zip(got, want):
+            assert np.array_equal(gi, wi) and np.array_equal(gd, wd)
+        with pytest.raises(HuloError):                    # nothing left to collect
+            check(gpu.lib.hulo_knn2_sharded_collect(gpu.h, None, None, None))
+        gpu.knn2_sharded_submit(dA, dB, 0)
+        gpu.knn2_sharded_submit(dA, dB, 0)
+        with pytest.raises(HuloError):                    # a third outstanding search
+            gpu.knn2_sharded_submit(dA, dB, 0)
+        a = gpu.knn2_sharded_collect(); b = gpu.knn2_sharded_collect()
+        assert np.array_equal(a[0], want[-1][0]) and np.array_equal(b[1], want[-1][1])
+        idx, dist = gpu.knn2(dA, dB)                      # plain calls work again
+        assert np.array_equal(idx, want[-1][0]) and np.array_equal(dist, want[-1][1])
+    finally:
+        dA.free(); dB.free()
+
+
 def test_planted_property_at_scale(gpu):
     """Full-size property check (no oracle): every planted row finds its source as first
     neighbour at the planted distance, and d0 <= d1, on a 4096 x 2M problem."""
